@@ -1,0 +1,138 @@
+/* pixelart_b200.h — C ABI of the B200-native pixel-art remaster path.
+ *
+ * Drop-in boundary for the hot path of marcoc2/pixel-art-remaster-gpu:
+ *
+ *   reference interface (file:line)                         replaced by
+ *   ------------------------------------------------------  ---------------------------------------
+ *   extern "C" Point* launch_kernel(...)  kernel.cu:286-288  launch_kernel() below — same symbol,
+ *     declared by its only caller simpleVBO.cpp:57-60,        same signature, same ownership rules
+ *     called simpleVBO.cpp:151-153
+ *   the per-frame cudaMalloc/cudaFree + 8 launches            par_create() / par_remaster_device() /
+ *     kernel.cu:313-523                                       par_remaster_host(): pooled context,
+ *                                                             batches of frames, one stream
+ *   graph_Kernel + trivial_cross_Kernel  kernel.cu:140-177   par_stage_similarity_graph()
+ *   ambiguous_cross_Kernel               kernel.cu:180-189   par_stage_resolve_crossings()
+ *   (dead) cc_Kernel / extractBorderPoints                    par_stage_cc_labels()  (new subsystem)
+ *     cc_kernel_call.bkp:3-12, cc_functions.cu:348-503
+ *   cells_Kernel + subdivision_Kernel    kernel.cu:192-261   par_stage_polygons()
+ *   triangulate/color/position kernels + glDrawArrays         par_stage_raster()  (direct rasterizer)
+ *     kernel.cu:264-282,67-137; simpleVBO.cpp:236-285
+ *
+ * Plain C: pointers and sizes only.  Every function returns a par_status (0 = success) unless it
+ * says otherwise; par_last_error() gives the message of the last failure on that context.  There is
+ * no CPU fallback: without a CUDA device par_create() fails with PAR_ERR_NO_DEVICE.
+ *
+ * Data conventions (identical to the reference):
+ *   frame   BGR8, `widthstep` bytes per row, row 0 = BOTTOM scanline (main.cpp:59 flips on load)
+ *   graph   1 byte per pixel, dense rows of `width` bytes; bit e <-> neighbour (di,dj):
+ *           0:(-1,+1) 1:(0,+1) 2:(+1,+1) 3:(-1,0) 4:(+1,0) 5:(-1,-1) 6:(0,-1) 7:(+1,-1)
+ *   labels  int32 per pixel = smallest row-major index (within the frame) of the pixel's component
+ *   rgba    (scale*height) rows of (scale*width) RGBA8 pixels; row Y = pipeline row (0 = bottom)
+ *           unless PAR_FLAG_FLIP_OUTPUT is set, in which case row 0 = top scanline
+ *   polygons  PAR_CELL_SLOTS (x,y) float pairs per pixel in cell-local coordinates + int32 count
+ * A batch is `n_frames` frames `frame_stride` bytes apart; all outputs are dense per frame.
+ */
+#ifndef PIXELART_B200_H
+#define PIXELART_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAR_CELL_SLOTS 45 /* kernel.cu:8 CELL_SIZE */
+
+typedef enum par_status
+{
+    PAR_OK = 0,
+    PAR_ERR_INVALID = 1,   /* bad argument */
+    PAR_ERR_NO_DEVICE = 2, /* no usable CUDA device / wrong architecture */
+    PAR_ERR_CUDA = 3,      /* a CUDA call failed; see par_last_error() */
+    PAR_ERR_CAPACITY = 4   /* batch larger than the context was created for */
+} par_status;
+
+enum
+{
+    PAR_FLAG_SUBDIVIDE = 1u << 0,   /* stage E on (launch_kernel's `subdivide`, kernel.cu:288) */
+    PAR_FLAG_FLIP_OUTPUT = 1u << 1, /* rgba row 0 = top scanline (undo main.cpp:59's flip) */
+    PAR_FLAG_NO_TMA = 1u << 2       /* force the plain-load tile path (also taken automatically when
+                                       pointers/strides are not 16-byte multiples) */
+};
+
+typedef struct par_context par_context;
+
+/* One batch of frames and where its results go.  Pointers are DEVICE pointers for
+ * par_remaster_device()/par_stage_*() and HOST pointers for par_remaster_host().  Any output may be
+ * NULL (not produced / not copied). */
+typedef struct par_job
+{
+    const uint8_t* bgr;   /* in : n_frames frames, BGR8                                  */
+    int width, height;    /*      frame size in pixels                                   */
+    int widthstep;        /*      bytes per row (>= 3*width)                             */
+    size_t frame_stride;  /*      bytes between frames (>= widthstep*height); 0 = dense  */
+    int n_frames;
+    int scale;            /*      output magnification s (1..8)                          */
+    unsigned flags;       /*      PAR_FLAG_*                                             */
+    uint8_t* rgba;        /* out: n_frames * (s*height) * (s*width) * 4 bytes            */
+    uint8_t* graph;       /* out: final similarity graph, n_frames * width*height bytes  */
+    uint8_t* graph_aux;   /* out: graph after the trivial-crossing pass (kernel.cu:415)  */
+    int32_t* labels;      /* out: connected-component labels                             */
+    float* polygons;      /* out: n_frames * width*height * 45 * 2 floats                */
+    int32_t* poly_count;  /* out: vertices per polygon (launch_kernel's edge_count_h)    */
+} par_job;
+
+/* Context: device, stream, pooled scratch (graph buffers for `max_frames` frames of up to
+ * max_width x max_height pixels), the 4096-entry cell table.  Not thread-safe; one per host thread. */
+int par_create( par_context** out, int device, int max_width, int max_height, int max_frames );
+void par_destroy( par_context* ctx );
+const char* par_last_error( const par_context* ctx ); /* ctx may be NULL: last par_create failure */
+int par_device( const par_context* ctx );
+/* Run all work on an existing CUDA stream (cudaStream_t passed as void*; NULL is the legacy default
+ * stream).  par_use_own_stream() goes back to the non-blocking stream the context created. */
+int par_set_stream( par_context* ctx, void* cuda_stream );
+int par_use_own_stream( par_context* ctx );
+int par_synchronize( par_context* ctx );
+/* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
+uint64_t par_launch_count( const par_context* ctx );
+
+/* Whole path on device-resident frames; asynchronous on the context's stream. */
+int par_remaster_device( par_context* ctx, const par_job* job );
+/* Whole path on host buffers: H2D of the frames, the kernels, D2H of every non-NULL output, then a
+ * stream synchronize.  Host buffers may be pageable or pinned. */
+int par_remaster_host( par_context* ctx, const par_job* job );
+
+/* Single stages on device pointers (parity tests and embedding callers). */
+int par_stage_similarity_graph( par_context* ctx, const par_job* job );  /* bgr -> graph_aux            */
+int par_stage_resolve_crossings( par_context* ctx, const par_job* job ); /* graph_aux -> graph          */
+int par_stage_cc_labels( par_context* ctx, const par_job* job );         /* graph -> labels             */
+int par_stage_polygons( par_context* ctx, const par_job* job );          /* bgr, graph -> polygons,count */
+int par_stage_raster( par_context* ctx, const par_job* job );            /* bgr, graph -> rgba          */
+
+/* Cell table (stage D): vertices of the cell of pattern key = node | (left&4 ? 1<<8 : 0) |
+ * (left&128 ? 1<<9 : 0) | (right&1 ? 1<<10 : 0) | (right&32 ? 1<<11 : 0); out_xy receives count+1
+ * (x,y) pairs (first repeated last); returns count, or -1 for a bad key.  Host-side, no GPU needed. */
+int par_cell_from_pattern( unsigned key, float* out_xy );
+/* Packed YUV word of one colour as the device computes it (graph_functions.cu:80-98). Host-side. */
+uint32_t par_yuv_word( int byte0, int byte1, int byte2 );
+
+/* ---- multi-GPU: one very large image tiled into horizontal strips over several devices -------- */
+typedef struct par_group par_group;
+int par_group_create( par_group** out, const int* devices, int n_devices, int width, int height, int scale );
+void par_group_destroy( par_group* grp );
+const char* par_group_last_error( const par_group* grp );
+/* Host image in, host outputs out (any may be NULL); strips exchange halo rows over P2P. */
+int par_group_remaster_host( par_group* grp, const par_job* job );
+
+/* ---- the reference's own entry point (kernel.cu:286-288), same symbol and signature ------------ */
+#if defined( __CUDACC__ ) || defined( PAR_HAVE_CUDA_VECTOR_TYPES )
+typedef struct par_point { float x, y; } par_point; /* point.cu:2-11 */
+par_point* launch_kernel( float2* pos, uchar4* colorPos, float time, char* img_data, int img_width, int img_height,
+                          int img_widthstep, int* edge_count_h, char* graph_h, bool subdivide );
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIXELART_B200_H */

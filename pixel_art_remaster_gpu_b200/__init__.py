@@ -1,0 +1,251 @@
+"""B200-native pixel-art remaster path — Python host side over the C ABI (include/pixelart_b200.h).
+
+The product is the CUDA library `libpixelart_b200.so` (hand-written sm_100a kernels); this module
+only binds it with ctypes and moves pointers around.  torch is used for device memory and streams,
+nothing else.  There is NO CPU fallback: importing works anywhere (so the build can be checked on a
+CPU box) but creating a `Remaster` context without a B200 raises.
+
+Mirrors the reference's interface for the path:
+  reference `launch_kernel(pos, colorPos, time, img_data, w, h, widthstep, edge_count_h, graph_h,
+  subdivide)` (kernel.cu:286-288)  ->  `Remaster.remaster(...)` / `launch_kernel(...)` below.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import synth  # noqa: F401  (synthetic inputs for the BASELINE configs)
+
+__all__ = ["Remaster", "RemasterError", "load_library", "library_path", "cell_from_pattern", "yuv_word",
+           "FLAG_SUBDIVIDE", "FLAG_FLIP_OUTPUT", "FLAG_NO_TMA", "CELL_SLOTS", "synth"]
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CELL_SLOTS = 45
+FLAG_SUBDIVIDE, FLAG_FLIP_OUTPUT, FLAG_NO_TMA = 1, 2, 4
+_STATUS = {0: "PAR_OK", 1: "PAR_ERR_INVALID", 2: "PAR_ERR_NO_DEVICE", 3: "PAR_ERR_CUDA", 4: "PAR_ERR_CAPACITY"}
+
+
+class RemasterError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("%s: %s" % (_STATUS.get(status, status), message))
+        self.status = status
+
+
+class ParJob(C.Structure):
+    _fields_ = [("bgr", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("widthstep", C.c_int),
+                ("frame_stride", C.c_size_t), ("n_frames", C.c_int), ("scale", C.c_int), ("flags", C.c_uint),
+                ("rgba", C.c_void_p), ("graph", C.c_void_p), ("graph_aux", C.c_void_p), ("labels", C.c_void_p),
+                ("polygons", C.c_void_p), ("poly_count", C.c_void_p)]
+
+
+_lib = None
+
+
+def library_path():
+    return os.path.join(HERE, "libpixelart_b200.so")
+
+
+def load_library():
+    """Load the CUDA library; raises if it has not been built (python -m pixel_art_remaster_gpu_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError("%s is missing: build it with `python -m pixel_art_remaster_gpu_b200.build` "
+                          "(there is no CPU fallback)" % path)
+    L = C.CDLL(path)
+    P = C.POINTER
+    L.par_create.argtypes = [P(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.par_destroy.argtypes = [C.c_void_p]
+    L.par_destroy.restype = None
+    L.par_last_error.argtypes = [C.c_void_p]
+    L.par_last_error.restype = C.c_char_p
+    L.par_device.argtypes = [C.c_void_p]
+    L.par_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.par_use_own_stream.argtypes = [C.c_void_p]
+    L.par_synchronize.argtypes = [C.c_void_p]
+    L.par_launch_count.argtypes = [C.c_void_p]
+    L.par_launch_count.restype = C.c_uint64
+    for name in ("par_remaster_device", "par_remaster_host", "par_stage_similarity_graph", "par_stage_resolve_crossings",
+                 "par_stage_cc_labels", "par_stage_polygons", "par_stage_raster"):
+        getattr(L, name).argtypes = [C.c_void_p, P(ParJob)]
+    L.par_cell_from_pattern.argtypes = [C.c_uint, P(C.c_float)]
+    L.par_yuv_word.argtypes = [C.c_int, C.c_int, C.c_int]
+    L.par_yuv_word.restype = C.c_uint32
+    _lib = L
+    return L
+
+
+def cell_from_pattern(key):
+    """Vertices (count+1, 2) of the cell of a 12-bit pattern key and its vertex count (host-side table)."""
+    L = load_library()
+    buf = (C.c_float * (2 * CELL_SLOTS))()
+    n = L.par_cell_from_pattern(int(key), buf)
+    if n < 0:
+        raise ValueError("bad key %r" % (key,))
+    return np.array(buf[: 2 * (n + 1)], np.float32).reshape(n + 1, 2), n
+
+
+def yuv_word(b0, b1, b2):
+    return int(load_library().par_yuv_word(int(b0), int(b1), int(b2)))
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Remaster:
+    """One remaster context on one GPU (par_context).  Device tensors in, device tensors out."""
+
+    def __init__(self, device=0, max_width=256, max_height=224, max_frames=64):
+        import torch
+        self._torch = torch
+        self.lib = load_library()
+        self.handle = C.c_void_p()
+        st = self.lib.par_create(C.byref(self.handle), int(device), int(max_width), int(max_height), int(max_frames))
+        if st != 0:
+            self.handle = C.c_void_p()
+            raise RemasterError(st, self.lib.par_last_error(None).decode())
+        self.device = torch.device("cuda", int(device))
+        self.use_torch_stream()
+
+    # -- plumbing --------------------------------------------------------------------------
+    def close(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            self.lib.par_destroy(h)
+            h.value = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def use_torch_stream(self, stream=None):
+        """Run all work on a torch stream (default: torch's current stream on this device), so that
+        torch.cuda.Event timing and tensor lifetimes see it."""
+        s = stream if stream is not None else self._torch.cuda.current_stream(self.device)
+        self._check(self.lib.par_set_stream(self.handle, C.c_void_p(s.cuda_stream)))
+
+    def synchronize(self):
+        self._check(self.lib.par_synchronize(self.handle))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.par_launch_count(self.handle))
+
+    def _check(self, st):
+        if st != 0:
+            raise RemasterError(st, self.lib.par_last_error(self.handle).decode())
+
+    def _job(self, frames, scale, flags, **outs):
+        t = self._torch
+        if frames is not None:
+            assert frames.dtype == t.uint8 and frames.dim() == 4 and frames.shape[3] == 3, "frames: (F, H, W, 3) uint8 BGR"
+            assert frames.stride(3) == 1 and frames.stride(2) == 3, "pixels must be packed BGR"
+            F, H, W = frames.shape[:3]
+            ws, fs = frames.stride(1), frames.stride(0)
+        else:
+            F, H, W = outs["graph"].shape if outs.get("graph") is not None else outs["graph_aux"].shape
+            ws, fs = 3 * W, 0
+        j = ParJob()
+        j.bgr = _ptr(frames)
+        j.width, j.height, j.widthstep, j.frame_stride, j.n_frames = W, H, ws, fs if F > 1 else 0, F
+        j.scale, j.flags = int(scale), int(flags)
+        for k in ("rgba", "graph", "graph_aux", "labels", "polygons", "poly_count"):
+            v = outs.get(k)
+            if v is not None:
+                assert v.is_contiguous()
+            setattr(j, k, _ptr(v))
+        return j
+
+    def _alloc(self, F, H, W, scale, want):
+        t, dev = self._torch, self.device
+        o = {}
+        if "rgba" in want:
+            o["rgba"] = t.empty((F, scale * H, scale * W, 4), dtype=t.uint8, device=dev)
+        if "graph" in want:
+            o["graph"] = t.empty((F, H, W), dtype=t.uint8, device=dev)
+        if "graph_aux" in want:
+            o["graph_aux"] = t.empty((F, H, W), dtype=t.uint8, device=dev)
+        if "labels" in want:
+            o["labels"] = t.empty((F, H, W), dtype=t.int32, device=dev)
+        if "polygons" in want:
+            o["polygons"] = t.empty((F, H * W, CELL_SLOTS, 2), dtype=t.float32, device=dev)
+            o["poly_count"] = t.empty((F, H * W), dtype=t.int32, device=dev)
+        return o
+
+    @staticmethod
+    def _flags(subdivide, flip_output, no_tma):
+        return (FLAG_SUBDIVIDE if subdivide else 0) | (FLAG_FLIP_OUTPUT if flip_output else 0) | (FLAG_NO_TMA if no_tma else 0)
+
+    # -- whole path ------------------------------------------------------------------------
+    def remaster(self, frames, scale=4, subdivide=True, want=("rgba",), out=None, flip_output=False, no_tma=False):
+        """frames: CUDA uint8 (F, H, W, 3) BGR, row 0 = bottom scanline.  Returns a dict of CUDA tensors
+        for the names in `want` (rgba graph graph_aux labels polygons[+poly_count]); asynchronous."""
+        F, H, W = frames.shape[:3]
+        o = out if out is not None else self._alloc(F, H, W, scale, want)
+        j = self._job(frames, scale, self._flags(subdivide, flip_output, no_tma), **o)
+        self._check(self.lib.par_remaster_device(self.handle, C.byref(j)))
+        return o
+
+    def remaster_host(self, frames, scale=4, subdivide=True, want=("rgba",), out=None, flip_output=False):
+        """Same through HOST buffers (torch CPU tensors, ideally pinned): H2D, kernels, D2H, synchronize."""
+        t = self._torch
+        F, H, W = frames.shape[:3]
+        assert not frames.is_cuda
+        if out is None:
+            out = {}
+            shapes = {"rgba": ((F, scale * H, scale * W, 4), t.uint8), "graph": ((F, H, W), t.uint8),
+                      "graph_aux": ((F, H, W), t.uint8), "labels": ((F, H, W), t.int32),
+                      "polygons": ((F, H * W, CELL_SLOTS, 2), t.float32)}
+            for k in want:
+                out[k] = t.empty(shapes[k][0], dtype=shapes[k][1]).pin_memory()
+            if "polygons" in want:
+                out["poly_count"] = t.empty((F, H * W), dtype=t.int32).pin_memory()
+        j = self._job(frames, scale, self._flags(subdivide, flip_output, False), **out)
+        self._check(self.lib.par_remaster_host(self.handle, C.byref(j)))
+        return out
+
+    # -- single stages (parity tests) ------------------------------------------------------
+    def similarity_graph(self, frames, no_tma=False):
+        F, H, W = frames.shape[:3]
+        o = self._alloc(F, H, W, 1, ("graph_aux",))
+        j = self._job(frames, 1, self._flags(False, False, no_tma), **o)
+        self._check(self.lib.par_stage_similarity_graph(self.handle, C.byref(j)))
+        return o["graph_aux"]
+
+    def resolve_crossings(self, graph_aux, no_tma=False):
+        F, H, W = graph_aux.shape
+        g = self._torch.empty_like(graph_aux)
+        j = self._job(None, 1, self._flags(False, False, no_tma), graph_aux=graph_aux, graph=g)
+        self._check(self.lib.par_stage_resolve_crossings(self.handle, C.byref(j)))
+        return g
+
+    def cc_labels(self, graph):
+        lab = self._torch.empty(graph.shape, dtype=self._torch.int32, device=graph.device)
+        j = self._job(None, 1, 0, graph=graph, labels=lab)
+        self._check(self.lib.par_stage_cc_labels(self.handle, C.byref(j)))
+        return lab
+
+    def polygons(self, frames, graph, subdivide=True):
+        F, H, W = frames.shape[:3]
+        o = self._alloc(F, H, W, 1, ("polygons",))
+        j = self._job(frames, 1, self._flags(subdivide, False, False), graph=graph, **o)
+        self._check(self.lib.par_stage_polygons(self.handle, C.byref(j)))
+        return o["polygons"], o["poly_count"]
+
+    def raster(self, frames, graph, scale=4, subdivide=True, flip_output=False, no_tma=False):
+        F, H, W = frames.shape[:3]
+        o = self._alloc(F, H, W, scale, ("rgba",))
+        j = self._job(frames, scale, self._flags(subdivide, flip_output, no_tma), graph=graph, **o)
+        self._check(self.lib.par_stage_raster(self.handle, C.byref(j)))
+        return o["rgba"]

@@ -1,0 +1,128 @@
+// Host-side construction of the 4096-entry cell tables (see cell_table.h).
+//
+// The candidate points of a pattern follow createCellFromPattern (diagram_functions.cu:319-535):
+// walking the eight neighbours clockwise from the up-left one, a linked diagonal pushes the cell
+// corner out by a quarter pixel (one or two points, depending on the adjacent orthogonal links), an
+// unlinked diagonal keeps the square corner unless the neighbouring pixels' diagonal cuts it; an
+// orthogonal link contributes the two square corners of that side.  (The interior "dummy" points
+// the reference adds for unlinked sides never reach the hull and are skipped.)  The hull is the
+// convex hull of those points with collinear points dropped, counter-clockwise from the
+// lexicographically smallest vertex — which is what the reference's sort + monotone chain
+// (diagram_functions.cu:82-129, :238-316) produces for every one of the 4096 patterns
+// (tests/test_cell_table.py compares all of them with the reference build and the oracle).
+#include "cell_table.h"
+#include <algorithm>
+#include <utility>
+#include <vector>
+
+namespace par {
+
+namespace {
+
+typedef std::pair< int, int > Q; // quarter-pixel units
+
+long turn( const Q& o, const Q& a, const Q& b ) { return ( long )( a.first - o.first ) * ( b.second - o.second ) - ( long )( a.second - o.second ) * ( b.first - o.first ); }
+
+std::vector< Q > candidates( unsigned key )
+{
+    const bool n0 = key & 1, n1 = key & 2, n2 = key & 4, n3 = key & 8, n4 = key & 16, n5 = key & 32, n6 = key & 64, n7 = key & 128;
+    const bool cut_ul = key & 256, cut_dl = key & 512, cut_ur = key & 1024, cut_dr = key & 2048;
+    std::vector< Q > p;
+    // up-left corner (0,1)
+    if( n0 )
+    {
+        if( !( n3 && !n1 ) ) p.push_back( Q( -1, 3 ) );
+        if( !( n1 && !n3 ) ) p.push_back( Q( 1, 5 ) );
+    }
+    else
+        p.push_back( cut_ul ? Q( 1, 3 ) : Q( 0, 4 ) );
+    // up-right corner (1,1)
+    if( n2 )
+    {
+        if( !( n1 && !n4 ) ) p.push_back( Q( 3, 5 ) );
+        if( !( n4 && !n1 ) ) p.push_back( Q( 5, 3 ) );
+    }
+    else
+        p.push_back( cut_ur ? Q( 3, 3 ) : Q( 4, 4 ) );
+    // down-right corner (1,0)
+    if( n7 )
+    {
+        if( !( n4 && !n6 ) ) p.push_back( Q( 5, 1 ) );
+        if( !( n6 && !n4 ) ) p.push_back( Q( 3, -1 ) );
+    }
+    else
+        p.push_back( cut_dr ? Q( 3, 1 ) : Q( 4, 0 ) );
+    // down-left corner (0,0)
+    if( n5 )
+    {
+        if( !( n3 && !n6 ) ) p.push_back( Q( -1, 1 ) );
+        if( !( n6 && !n3 ) ) p.push_back( Q( 1, -1 ) );
+    }
+    else
+        p.push_back( cut_dl ? Q( 1, 1 ) : Q( 0, 0 ) );
+    // sides: an orthogonal link keeps both square corners of that side
+    if( n1 ) { p.push_back( Q( 0, 4 ) ); p.push_back( Q( 4, 4 ) ); }
+    if( n4 ) { p.push_back( Q( 4, 4 ) ); p.push_back( Q( 4, 0 ) ); }
+    if( n6 ) { p.push_back( Q( 4, 0 ) ); p.push_back( Q( 0, 0 ) ); }
+    if( n3 ) { p.push_back( Q( 0, 0 ) ); p.push_back( Q( 0, 4 ) ); }
+    return p;
+}
+
+std::vector< Q > convex_hull_ccw( std::vector< Q > p )
+{
+    std::sort( p.begin(), p.end() );
+    p.erase( std::unique( p.begin(), p.end() ), p.end() );
+    std::vector< Q > h( 2 * p.size() );
+    size_t k = 0;
+    for( size_t i = 0; i < p.size(); i++ )
+    {
+        while( k >= 2 && turn( h[ k - 2 ], h[ k - 1 ], p[ i ] ) <= 0 ) k--;
+        h[ k++ ] = p[ i ];
+    }
+    for( size_t i = p.size() - 1, t = k + 1; i-- > 0; )
+    {
+        while( k >= t && turn( h[ k - 2 ], h[ k - 1 ], p[ i ] ) <= 0 ) k--;
+        h[ k++ ] = p[ i ];
+    }
+    h.resize( k - 1 );
+    return h;
+}
+
+// which graph edge a hull edge a->b is shared through (subdivision_functions.cu:245-424, first
+// match wins, in the reference's order), 15 = border.  Quarter units: 1/2 pixel = 2.
+unsigned classify( const Q& a, const Q& b, unsigned node )
+{
+    const int dx = b.first - a.first, dy = b.second - a.second;
+    if( dy == 0 && a.second > 2 && ( node & 2 ) ) return 1;
+    if( dx == 0 && a.first > 2 && ( node & 16 ) ) return 4;
+    if( dy == 0 && a.second < 2 && ( node & 64 ) ) return 6;
+    if( dx == 0 && a.first < 2 && ( node & 8 ) ) return 3;
+    const bool up = dx != 0 && dy == dx, down = dx != 0 && dy == -dx; // slope +1 / -1
+    const int twice_mid_y = a.second + b.second;                        // compare with 2 * (1/2 pixel) = 4
+    if( up && twice_mid_y > 4 && ( node & 1 ) ) return 0;
+    if( down && twice_mid_y > 4 && ( node & 4 ) ) return 2;
+    if( up && twice_mid_y < 4 && ( node & 128 ) ) return 7;
+    if( down && twice_mid_y < 4 && ( node & 32 ) ) return 5;
+    return 15;
+}
+
+} // namespace
+
+void build_cell_tables( CellTables* t )
+{
+    for( unsigned key = 0; key < ( unsigned )kCellKeys; key++ )
+    {
+        std::vector< Q > h = convex_hull_ccw( candidates( key ) );
+        uint64_t packed = ( uint64_t )h.size();
+        uint32_t links = 0;
+        for( size_t v = 0; v < h.size(); v++ )
+        {
+            packed |= ( uint64_t )( ( unsigned )( h[ v ].first + 1 ) | ( unsigned )( h[ v ].second + 1 ) << 3 ) << ( 4 + 6 * v );
+            links |= classify( h[ v ], h[ ( v + 1 ) % h.size() ], key & 0xFFu ) << ( 4 * v );
+        }
+        t->hull[ key ] = packed;
+        t->link[ key ] = links;
+    }
+}
+
+} // namespace par

@@ -1,0 +1,114 @@
+// Shared device/host definitions of the B200 remaster path: graph-byte conventions, the exact
+// packed-YUV conversion, TMA (cp.async.bulk.tensor) + mbarrier wrappers for sm_100a.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace par {
+
+// graph bit e <-> neighbour offset (reference: graph_functions.cu:162-171, calc_index :46-76)
+//   e        0      1      2      3      4      5      6      7
+//   (di,dj) (-1,+1) (0,+1) (+1,+1) (-1,0) (+1,0) (-1,-1) (0,-1) (+1,-1)
+__host__ __device__ __forceinline__ int edge_di( int e )
+{
+    return e == 0 || e == 3 || e == 5 ? -1 : ( e == 1 || e == 6 ? 0 : 1 );
+}
+__host__ __device__ __forceinline__ int edge_dj( int e ) { return e < 3 ? 1 : ( e < 5 ? 0 : -1 ); }
+
+// thresholds on the packed fields (graph_functions.cu:14-19)
+constexpr int kThrY = 0x00050000;
+constexpr int kThrU = 0x00000700;
+constexpr int kThrV = 0x00000006;
+
+// Packed YUV word of the colour whose bytes in memory are (b0,b1,b2) = OpenCV (B,G,R).
+// Restates graph_functions.cu:80-98 as the reference's DEVICE build evaluates it: Y is the double
+// expression 0.299*b0 + 0.587*b1 + 0.114*b2 with nvcc's FMA contraction:
+//     y = trunc( fma(0.114, b2, fma(0.299, b0, 0.587*b1)) )
+// Evaluated here without FP64 on the common path: T = 299*b0 + 587*b1 + 114*b2 is the exact value
+// times 1000; when T is not a multiple of 1000 the double expression is within 1e-12 of T/1000,
+// far from any integer, so trunc() equals T/1000 in integer arithmetic.  Only exact multiples
+// (e.g. every grey) need the real FMA chain, whose rounding decides between y and y-1.
+// U and V are float products truncated toward zero (graph_functions.cu:93-94).
+__host__ __device__ __forceinline__ uint32_t yuv_word( int b0, int b1, int b2 )
+{
+    int T = 299 * b0 + 587 * b1 + 114 * b2;
+    int y = T / 1000;
+    if( T - y * 1000 == 0 )
+    {
+#ifdef __CUDA_ARCH__
+        y = __double2int_rz( __fma_rn( 0.114, ( double )b2, __fma_rn( 0.299, ( double )b0, __dmul_rn( 0.587, ( double )b1 ) ) ) );
+#else
+        y = ( int )__builtin_fma( 0.114, ( double )b2, __builtin_fma( 0.299, ( double )b0, 0.587 * ( double )b1 ) );
+#endif
+    }
+#ifdef __CUDA_ARCH__
+    int u = __float2int_rz( __fmul_rn( ( float )( b2 - y ), 0.492f ) );
+    int v = __float2int_rz( __fmul_rn( ( float )( b0 - y ), 0.877f ) );
+#else
+    int u = ( int )( ( float )( b2 - y ) * 0.492f );
+    int v = ( int )( ( float )( b0 - y ) * 0.877f );
+#endif
+    return ( uint32_t )( y << 16 ) + ( uint32_t )( u * 256 ) + ( uint32_t )v;
+}
+
+// 1 when the two packed words are similar (graph_functions.cu:291-293 negated)
+__host__ __device__ __forceinline__ bool yuv_similar( uint32_t p, uint32_t q )
+{
+    int dy = ( int )( ( p & 0x00FF0000u ) - ( q & 0x00FF0000u ) );
+    int du = ( int )( ( p & 0x0000FF00u ) - ( q & 0x0000FF00u ) );
+    int dv = ( int )( ( p & 0x000000FFu ) - ( q & 0x000000FFu ) );
+    dy = dy < 0 ? -dy : dy;
+    du = du < 0 ? -du : du;
+    dv = dv < 0 ? -dv : dv;
+    return dy <= kThrY && du <= kThrU && dv <= kThrV;
+}
+
+#ifdef __CUDACC__
+// ---- mbarrier + TMA (sm_100a) ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32( const void* p ) { return ( uint32_t )__cvta_generic_to_shared( p ); }
+
+__device__ __forceinline__ void mbar_init( uint64_t* bar, uint32_t count )
+{
+    asm volatile( "mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"( smem_u32( bar ) ), "r"( count ) : "memory" );
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" ); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile( "fence.proxy.async.shared::cta;" ::: "memory" ); }
+__device__ __forceinline__ void mbar_expect_tx( uint64_t* bar, uint32_t bytes )
+{
+    asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"( smem_u32( bar ) ), "r"( bytes ) : "memory" );
+}
+__device__ __forceinline__ void mbar_wait( uint64_t* bar, uint32_t parity )
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"( smem_u32( bar ) ),
+        "r"( parity )
+        : "memory" );
+}
+// 3-D tiled bulk tensor load global -> shared, completion counted on `bar` (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_3d( void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2 )
+{
+    asm volatile( "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                      smem_u32( smem_dst ) ),
+                  "l"( map ), "r"( smem_u32( bar ) ), "r"( c0 ), "r"( c1 ), "r"( c2 )
+                  : "memory" );
+}
+__device__ __forceinline__ void tma_prefetch_desc( const CUtensorMap* map )
+{
+    asm volatile( "prefetch.tensormap [%0];" ::"l"( map ) : "memory" );
+}
+// streaming 128-bit store that does not allocate in L1 (output is written once, never re-read)
+__device__ __forceinline__ void st_stream_v4( void* p, uint4 v )
+{
+    asm volatile( "st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"( p ), "r"( v.x ), "r"( v.y ), "r"( v.z ), "r"( v.w ) : "memory" );
+}
+#endif
+
+} // namespace par

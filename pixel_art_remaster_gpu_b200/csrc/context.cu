@@ -1,0 +1,443 @@
+// C ABI of the remaster path (include/pixelart_b200.h): context, pooled buffers, stage dispatch.
+//
+// Replaces the host orchestration in launch_kernel (kernel.cu:286-526): instead of 10 cudaMalloc /
+// cudaFree and 3 blocking D2H copies per frame, a context owns its scratch for a whole batch of
+// frames, every stage is one launch over the batch (blockIdx.z = frame), and work is asynchronous
+// on one stream.
+#include "../../include/pixelart_b200.h"
+#include "cell_table.h"
+#include "kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+
+using namespace par;
+
+namespace {
+
+std::string g_create_error;
+
+typedef CUresult ( *EncodeTiledFn )( CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
+
+EncodeTiledFn load_encode_tiled()
+{
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if( cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q ) != cudaSuccess || q != cudaDriverEntryPointSuccess )
+        return nullptr;
+    return reinterpret_cast< EncodeTiledFn >( fn );
+}
+
+} // namespace
+
+struct par_context
+{
+    int device = 0;
+    int max_w = 0, max_h = 0, max_frames = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    uint8_t *scratch_aux = nullptr, *scratch_graph = nullptr; // max_frames * max_w * max_h each
+    uint64_t* d_hull = nullptr;
+    uint32_t* d_link = nullptr;
+    EncodeTiledFn encode = nullptr;
+    uint64_t launches = 0;
+    std::string error;
+    // staging for par_remaster_host (grown on demand)
+    uint8_t* h_stage[ 8 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    size_t h_stage_bytes[ 8 ] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+
+    int fail( par_status st, const char* fmt, ... )
+    {
+        char buf[ 512 ];
+        va_list ap;
+        va_start( ap, fmt );
+        vsnprintf( buf, sizeof( buf ), fmt, ap );
+        va_end( ap );
+        error = buf;
+        return st;
+    }
+    int cuda_fail( cudaError_t e, const char* what ) { return fail( PAR_ERR_CUDA, "%s: %s", what, cudaGetErrorString( e ) ); }
+
+    // 3-D byte tensor (row bytes, rows, frames) -> tensor map; false when TMA's alignment rules do not hold
+    bool make_map( CUtensorMap* map, const void* base, uint64_t row_bytes, uint64_t rows, uint64_t frames, uint64_t row_stride,
+                   uint64_t frame_stride, const uint32_t box[ 3 ] )
+    {
+        if( !encode ) return false;
+        if( ( reinterpret_cast< uintptr_t >( base ) & 15u ) || ( row_stride & 15u ) || ( frame_stride & 15u ) ) return false;
+        if( box[ 0 ] > 256 || box[ 1 ] > 256 ) return false;
+        cuuint64_t dims[ 3 ] = { row_bytes, rows, frames };
+        cuuint64_t strides[ 2 ] = { row_stride, frame_stride };
+        cuuint32_t bx[ 3 ] = { box[ 0 ], box[ 1 ], box[ 2 ] };
+        cuuint32_t es[ 3 ] = { 1, 1, 1 };
+        CUresult r = encode( map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast< void* >( base ), dims, strides, bx, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE );
+        return r == CUDA_SUCCESS;
+    }
+};
+
+namespace {
+
+int check_job( par_context* c, const par_job* j, bool need_bgr )
+{
+    if( !c ) return PAR_ERR_INVALID;
+    if( !j ) return c->fail( PAR_ERR_INVALID, "job is NULL" );
+    if( j->width <= 0 || j->height <= 0 || j->n_frames <= 0 ) return c->fail( PAR_ERR_INVALID, "empty frame or batch (%dx%d x %d)", j->width, j->height, j->n_frames );
+    if( need_bgr )
+    {
+        if( !j->bgr ) return c->fail( PAR_ERR_INVALID, "bgr is NULL" );
+        if( j->widthstep < 3 * j->width ) return c->fail( PAR_ERR_INVALID, "widthstep %d < 3*width", j->widthstep );
+        if( j->frame_stride != 0 && j->frame_stride < ( size_t )j->widthstep * j->height ) return c->fail( PAR_ERR_INVALID, "frame_stride too small" );
+    }
+    if( ( size_t )j->width * j->height > ( size_t )1 << 30 ) return c->fail( PAR_ERR_INVALID, "frame too large" );
+    return PAR_OK;
+}
+
+size_t frame_stride_of( const par_job* j ) { return j->frame_stride ? j->frame_stride : ( size_t )j->widthstep * j->height; }
+
+int check_capacity( par_context* c, const par_job* j )
+{
+    if( ( size_t )j->width * j->height * j->n_frames > ( size_t )c->max_w * c->max_h * c->max_frames )
+        return c->fail( PAR_ERR_CAPACITY, "batch of %d %dx%d frames exceeds the context capacity (%d frames of %dx%d)", j->n_frames, j->width,
+                        j->height, c->max_frames, c->max_w, c->max_h );
+    return PAR_OK;
+}
+
+int run_similarity( par_context* c, const par_job* j, uint8_t* aux )
+{
+    GraphArgs a;
+    a.bgr = j->bgr;
+    a.graph_aux = aux;
+    a.width = j->width;
+    a.height = j->height;
+    a.widthstep = j->widthstep;
+    a.n_frames = j->n_frames;
+    a.frame_stride = frame_stride_of( j );
+    CUtensorMap map;
+    uint32_t box[ 3 ];
+    similarity_graph_tma_box( box );
+    bool tma = !( j->flags & PAR_FLAG_NO_TMA ) &&
+               c->make_map( &map, j->bgr, 3ull * j->width, j->height, j->n_frames, j->widthstep, a.frame_stride, box );
+    cudaError_t e = launch_similarity_graph( a, tma ? &map : nullptr, c->stream );
+    c->launches++;
+    return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "similarity_graph" );
+}
+
+bool graph_map( par_context* c, const par_job* j, const uint8_t* g, const uint32_t box[ 3 ], CUtensorMap* map )
+{
+    return !( j->flags & PAR_FLAG_NO_TMA ) &&
+           c->make_map( map, g, j->width, j->height, j->n_frames, j->width, ( uint64_t )j->width * j->height, box );
+}
+
+int run_crossings( par_context* c, const par_job* j, const uint8_t* aux, uint8_t* graph )
+{
+    CrossArgs a;
+    a.graph_aux = aux;
+    a.graph = graph;
+    a.width = j->width;
+    a.height = j->height;
+    a.n_frames = j->n_frames;
+    CUtensorMap map;
+    uint32_t box[ 3 ];
+    resolve_crossings_tma_box( box );
+    bool tma = graph_map( c, j, aux, box, &map );
+    cudaError_t e = launch_resolve_crossings( a, tma ? &map : nullptr, c->stream );
+    c->launches++;
+    return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "resolve_crossings" );
+}
+
+int run_labels( par_context* c, const par_job* j, const uint8_t* graph, int32_t* labels )
+{
+    LabelArgs a;
+    a.graph = graph;
+    a.labels = labels;
+    a.width = j->width;
+    a.height = j->height;
+    a.n_frames = j->n_frames;
+    int n = 0;
+    cudaError_t e = launch_cc_labels( a, c->stream, &n );
+    c->launches += n;
+    return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "cc_labels" );
+}
+
+RasterArgs raster_args( par_context* c, const par_job* j, const uint8_t* graph )
+{
+    RasterArgs a;
+    a.bgr = j->bgr;
+    a.graph = graph;
+    a.cell_table = c->d_hull;
+    a.link_table = c->d_link;
+    a.rgba = j->rgba;
+    a.polygons = j->polygons;
+    a.poly_count = j->poly_count;
+    a.width = j->width;
+    a.height = j->height;
+    a.widthstep = j->widthstep;
+    a.n_frames = j->n_frames;
+    a.frame_stride = frame_stride_of( j );
+    a.scale = j->scale;
+    a.subdivide = ( j->flags & PAR_FLAG_SUBDIVIDE ) ? 1 : 0;
+    a.flip_output = ( j->flags & PAR_FLAG_FLIP_OUTPUT ) ? 1 : 0;
+    return a;
+}
+
+int run_polygons( par_context* c, const par_job* j, const uint8_t* graph )
+{
+    RasterArgs a = raster_args( c, j, graph );
+    cudaError_t e = launch_polygons( a, c->stream );
+    c->launches++;
+    return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "polygons" );
+}
+
+int run_raster( par_context* c, const par_job* j, const uint8_t* graph )
+{
+    if( !raster_scale_supported( j->scale ) ) return c->fail( PAR_ERR_INVALID, "unsupported scale %d (supported: 1,2,3,4,6,8)", j->scale );
+    RasterArgs a = raster_args( c, j, graph );
+    CUtensorMap map;
+    uint32_t box[ 3 ];
+    raster_tma_box( j->scale, box );
+    bool tma = graph_map( c, j, graph, box, &map );
+    cudaError_t e = launch_raster( a, tma ? &map : nullptr, c->stream );
+    c->launches++;
+    return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "raster" );
+}
+
+} // namespace
+
+extern "C" {
+
+int par_create( par_context** out, int device, int max_width, int max_height, int max_frames )
+{
+    if( !out || max_width <= 0 || max_height <= 0 || max_frames <= 0 )
+    {
+        g_create_error = "par_create: bad argument";
+        return PAR_ERR_INVALID;
+    }
+    *out = nullptr;
+    int n_dev = 0;
+    if( cudaGetDeviceCount( &n_dev ) != cudaSuccess || n_dev == 0 || device < 0 || device >= n_dev )
+    {
+        cudaGetLastError();
+        g_create_error = "par_create: no CUDA device (this library has no CPU fallback)";
+        return PAR_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties( &prop, device );
+    if( prop.major != 10 )
+    {
+        g_create_error = std::string( "par_create: device '" ) + prop.name + "' is not sm_100 (kernels are built for sm_100a only)";
+        return PAR_ERR_NO_DEVICE;
+    }
+    par_context* c = new par_context();
+    c->device = device;
+    c->max_w = max_width;
+    c->max_h = max_height;
+    c->max_frames = max_frames;
+    cudaError_t e = cudaSetDevice( device );
+    if( e == cudaSuccess ) e = cudaStreamCreateWithFlags( &c->own_stream, cudaStreamNonBlocking );
+    c->stream = c->own_stream;
+    size_t px = ( size_t )max_width * max_height * max_frames;
+    if( e == cudaSuccess ) e = cudaMalloc( &c->scratch_aux, px );
+    if( e == cudaSuccess ) e = cudaMalloc( &c->scratch_graph, px );
+    if( e == cudaSuccess ) e = cudaMalloc( &c->d_hull, sizeof( uint64_t ) * kCellKeys );
+    if( e == cudaSuccess ) e = cudaMalloc( &c->d_link, sizeof( uint32_t ) * kCellKeys );
+    if( e == cudaSuccess )
+    {
+        static CellTables tables;
+        static std::once_flag once;
+        std::call_once( once, [] { build_cell_tables( &tables ); } );
+        e = cudaMemcpy( c->d_hull, tables.hull, sizeof( tables.hull ), cudaMemcpyHostToDevice );
+        if( e == cudaSuccess ) e = cudaMemcpy( c->d_link, tables.link, sizeof( tables.link ), cudaMemcpyHostToDevice );
+    }
+    if( e != cudaSuccess )
+    {
+        g_create_error = std::string( "par_create: " ) + cudaGetErrorString( e );
+        par_destroy( c );
+        return PAR_ERR_CUDA;
+    }
+    c->encode = load_encode_tiled();
+    *out = c;
+    return PAR_OK;
+}
+
+void par_destroy( par_context* c )
+{
+    if( !c ) return;
+    cudaSetDevice( c->device );
+    if( c->own_stream )
+    {
+        cudaStreamSynchronize( c->own_stream );
+        cudaStreamDestroy( c->own_stream );
+    }
+    cudaFree( c->scratch_aux );
+    cudaFree( c->scratch_graph );
+    cudaFree( c->d_hull );
+    cudaFree( c->d_link );
+    for( int k = 0; k < 8; k++ ) cudaFree( c->h_stage[ k ] );
+    delete c;
+}
+
+const char* par_last_error( const par_context* c ) { return c ? c->error.c_str() : g_create_error.c_str(); }
+int par_device( const par_context* c ) { return c ? c->device : -1; }
+uint64_t par_launch_count( const par_context* c ) { return c ? c->launches : 0; }
+
+int par_set_stream( par_context* c, void* cuda_stream )
+{
+    if( !c ) return PAR_ERR_INVALID;
+    c->stream = static_cast< cudaStream_t >( cuda_stream );
+    return PAR_OK;
+}
+
+int par_use_own_stream( par_context* c )
+{
+    if( !c ) return PAR_ERR_INVALID;
+    c->stream = c->own_stream;
+    return PAR_OK;
+}
+
+int par_synchronize( par_context* c )
+{
+    if( !c ) return PAR_ERR_INVALID;
+    cudaError_t e = cudaStreamSynchronize( c->stream );
+    return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "synchronize" );
+}
+
+int par_stage_similarity_graph( par_context* c, const par_job* j )
+{
+    int st = check_job( c, j, true );
+    if( st ) return st;
+    if( !j->graph_aux ) return c->fail( PAR_ERR_INVALID, "graph_aux is NULL" );
+    cudaSetDevice( c->device );
+    return run_similarity( c, j, j->graph_aux );
+}
+
+int par_stage_resolve_crossings( par_context* c, const par_job* j )
+{
+    int st = check_job( c, j, false );
+    if( st ) return st;
+    if( !j->graph_aux || !j->graph ) return c->fail( PAR_ERR_INVALID, "graph_aux / graph is NULL" );
+    cudaSetDevice( c->device );
+    return run_crossings( c, j, j->graph_aux, j->graph );
+}
+
+int par_stage_cc_labels( par_context* c, const par_job* j )
+{
+    int st = check_job( c, j, false );
+    if( st ) return st;
+    if( !j->graph || !j->labels ) return c->fail( PAR_ERR_INVALID, "graph / labels is NULL" );
+    cudaSetDevice( c->device );
+    return run_labels( c, j, j->graph, j->labels );
+}
+
+int par_stage_polygons( par_context* c, const par_job* j )
+{
+    int st = check_job( c, j, true );
+    if( st ) return st;
+    if( !j->graph || !j->polygons ) return c->fail( PAR_ERR_INVALID, "graph / polygons is NULL" );
+    cudaSetDevice( c->device );
+    return run_polygons( c, j, j->graph );
+}
+
+int par_stage_raster( par_context* c, const par_job* j )
+{
+    int st = check_job( c, j, true );
+    if( st ) return st;
+    if( !j->graph || !j->rgba ) return c->fail( PAR_ERR_INVALID, "graph / rgba is NULL" );
+    cudaSetDevice( c->device );
+    return run_raster( c, j, j->graph );
+}
+
+int par_remaster_device( par_context* c, const par_job* j )
+{
+    int st = check_job( c, j, true );
+    if( st ) return st;
+    cudaSetDevice( c->device );
+    uint8_t* aux = j->graph_aux;
+    uint8_t* graph = j->graph;
+    if( !aux || !graph )
+    {
+        st = check_capacity( c, j );
+        if( st ) return st;
+        if( !aux ) aux = c->scratch_aux;
+        if( !graph ) graph = c->scratch_graph;
+    }
+    if( ( st = run_similarity( c, j, aux ) ) ) return st;
+    if( ( st = run_crossings( c, j, aux, graph ) ) ) return st;
+    if( j->labels && ( st = run_labels( c, j, graph, j->labels ) ) ) return st;
+    if( j->polygons && ( st = run_polygons( c, j, graph ) ) ) return st;
+    if( j->rgba && ( st = run_raster( c, j, graph ) ) ) return st;
+    return PAR_OK;
+}
+
+int par_remaster_host( par_context* c, const par_job* j )
+{
+    int st = check_job( c, j, true );
+    if( st ) return st;
+    cudaSetDevice( c->device );
+    const size_t px = ( size_t )j->width * j->height * j->n_frames;
+    const size_t in_bytes = frame_stride_of( j ) * j->n_frames;
+    const size_t out_px = px * j->scale * j->scale;
+    // device staging: 0 bgr, 1 rgba, 2 graph, 3 graph_aux, 4 labels, 5 polygons, 6 poly_count
+    const size_t need[ 7 ] = { in_bytes + 16,
+                               j->rgba ? out_px * 4 : 0,
+                               px,
+                               px,
+                               j->labels ? px * 4 : 0,
+                               j->polygons ? px * PAR_CELL_SLOTS * 2 * sizeof( float ) : 0,
+                               ( j->polygons && j->poly_count ) ? px * 4 : 0 };
+    for( int k = 0; k < 7; k++ )
+        if( need[ k ] > c->h_stage_bytes[ k ] )
+        {
+            cudaFree( c->h_stage[ k ] );
+            c->h_stage[ k ] = nullptr;
+            c->h_stage_bytes[ k ] = 0;
+            cudaError_t e = cudaMalloc( &c->h_stage[ k ], need[ k ] );
+            if( e != cudaSuccess ) return c->cuda_fail( e, "staging cudaMalloc" );
+            c->h_stage_bytes[ k ] = need[ k ];
+        }
+    cudaError_t e = cudaMemcpyAsync( c->h_stage[ 0 ], j->bgr, in_bytes, cudaMemcpyHostToDevice, c->stream );
+    if( e != cudaSuccess ) return c->cuda_fail( e, "H2D" );
+    par_job d = *j;
+    d.bgr = c->h_stage[ 0 ];
+    d.rgba = j->rgba ? c->h_stage[ 1 ] : nullptr;
+    d.graph = c->h_stage[ 2 ];
+    d.graph_aux = c->h_stage[ 3 ];
+    d.labels = j->labels ? reinterpret_cast< int32_t* >( c->h_stage[ 4 ] ) : nullptr;
+    d.polygons = j->polygons ? reinterpret_cast< float* >( c->h_stage[ 5 ] ) : nullptr;
+    d.poly_count = ( j->polygons && j->poly_count ) ? reinterpret_cast< int32_t* >( c->h_stage[ 6 ] ) : nullptr;
+    if( ( st = par_remaster_device( c, &d ) ) ) return st;
+    if( j->rgba ) e = cudaMemcpyAsync( j->rgba, d.rgba, out_px * 4, cudaMemcpyDeviceToHost, c->stream );
+    if( e == cudaSuccess && j->graph ) e = cudaMemcpyAsync( j->graph, d.graph, px, cudaMemcpyDeviceToHost, c->stream );
+    if( e == cudaSuccess && j->graph_aux ) e = cudaMemcpyAsync( j->graph_aux, d.graph_aux, px, cudaMemcpyDeviceToHost, c->stream );
+    if( e == cudaSuccess && j->labels ) e = cudaMemcpyAsync( j->labels, d.labels, px * 4, cudaMemcpyDeviceToHost, c->stream );
+    if( e == cudaSuccess && j->polygons )
+        e = cudaMemcpyAsync( j->polygons, d.polygons, px * PAR_CELL_SLOTS * 2 * sizeof( float ), cudaMemcpyDeviceToHost, c->stream );
+    if( e == cudaSuccess && d.poly_count ) e = cudaMemcpyAsync( j->poly_count, d.poly_count, px * 4, cudaMemcpyDeviceToHost, c->stream );
+    if( e != cudaSuccess ) return c->cuda_fail( e, "D2H" );
+    e = cudaStreamSynchronize( c->stream );
+    return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "synchronize" );
+}
+
+int par_cell_from_pattern( unsigned key, float* out_xy )
+{
+    if( key >= ( unsigned )kCellKeys || !out_xy ) return -1;
+    static CellTables tables;
+    static std::once_flag once;
+    std::call_once( once, [] { build_cell_tables( &tables ); } );
+    uint64_t h = tables.hull[ key ];
+    int n = hull_count( h );
+    for( int t = 0; t <= n; t++ )
+    {
+        out_xy[ 2 * t ] = 0.25f * ( float )hull_xq( h, t % n );
+        out_xy[ 2 * t + 1 ] = 0.25f * ( float )hull_yq( h, t % n );
+    }
+    return n;
+}
+
+uint32_t par_yuv_word( int b0, int b1, int b2 ) { return yuv_word( b0 & 255, b1 & 255, b2 & 255 ); }
+
+} // extern "C"

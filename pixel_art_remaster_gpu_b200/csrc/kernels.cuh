@@ -1,0 +1,61 @@
+// Launch interfaces of the sm_100a kernels (one translation unit per stage).
+#pragma once
+#include "common.cuh"
+#include <string.h>
+
+namespace par {
+
+struct GraphArgs
+{
+    const uint8_t* bgr;  // frames, BGR8
+    uint8_t* graph_aux;  // out, dense width*height per frame
+    int width, height, widthstep, n_frames;
+    size_t frame_stride;
+};
+
+struct CrossArgs
+{
+    const uint8_t* graph_aux; // in, dense
+    uint8_t* graph;           // out, dense
+    int width, height, n_frames;
+};
+
+struct LabelArgs
+{
+    const uint8_t* graph; // in, dense
+    int32_t* labels;      // out, dense
+    int width, height, n_frames;
+};
+
+struct RasterArgs
+{
+    const uint8_t* bgr;
+    const uint8_t* graph;       // final graph, dense
+    const uint64_t* cell_table; // 4096 packed hulls (cell_table.h)
+    const uint32_t* link_table; // 4096 packed edge classifications
+    uint8_t* rgba;              // out (raster), may be null
+    float* polygons;            // out (polygon export), may be null
+    int32_t* poly_count;        // out (polygon export), may be null
+    int width, height, widthstep, n_frames;
+    size_t frame_stride;
+    int scale;
+    int subdivide;
+    int flip_output;
+};
+
+dim3 similarity_graph_grid( int width, int height, int n_frames );
+void similarity_graph_tma_box( uint32_t box[ 3 ] );
+cudaError_t launch_similarity_graph( const GraphArgs& a, const CUtensorMap* img_map, cudaStream_t stream );
+
+void resolve_crossings_tma_box( uint32_t box[ 3 ] );
+cudaError_t launch_resolve_crossings( const CrossArgs& a, const CUtensorMap* aux_map, cudaStream_t stream );
+
+// labels: returns the number of kernels launched through *n_launches
+cudaError_t launch_cc_labels( const LabelArgs& a, cudaStream_t stream, int* n_launches );
+
+cudaError_t launch_polygons( const RasterArgs& a, cudaStream_t stream );
+void raster_tma_box( int scale, uint32_t box[ 3 ] );
+cudaError_t launch_raster( const RasterArgs& a, const CUtensorMap* graph_map, cudaStream_t stream );
+bool raster_scale_supported( int scale );
+
+} // namespace par

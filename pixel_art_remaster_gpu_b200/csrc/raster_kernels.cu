@@ -1,0 +1,390 @@
+// Stages D + E + direct rasterization in one kernel, and the polygon export kernel.
+//
+// Replaces cells_Kernel, subdivision_Kernel, triangulate_Kernel, color_kernel, position_kernel
+// (kernel.cu:192-282, :67-137) and the OpenGL draw of the 45-slot VBOs (simpleVBO.cpp:236-285):
+// instead of writing 1.1 kB of geometry per source pixel for a GL driver to rasterize, the cell
+// polygons are sampled directly into the (s*W) x (s*H) RGBA8 image.
+//
+// Raster rule (restated GL point sampling; oracle: orc_raster_polygons): output
+// pixel (X,Y) samples ((X+1/2)/s, (Y+1/2)/s); it takes the colour of the HIGHEST-index source
+// pixel whose polygon covers the sample (cells are drawn in row-major order without depth test),
+// black if none; a sample exactly on an edge/vertex is resolved as if displaced by (+eps, -eps^2)
+// (top-left rule).  Coverage is an even-odd crossing count in exact integer arithmetic: vertices
+// are multiples of 1/64, samples odd multiples of 1/(2s); both are scaled to units of 1/(128 s).
+//
+// Design (B200): one CTA per tile of source pixels.  (1) the final-graph bytes of the tile (+halo)
+// are staged in shared memory by one TMA bulk-tensor copy (zero fill outside the image; plain loads
+// when rows are not 16-byte multiples) and turned into 12-bit cell keys; (2) one thread per cell
+// (tile + 1 halo) streams its polygon — hull from the 4096-entry table, corner cutting in
+// registers — straight into a coverage bitmask of the (s + 2h)^2 samples the cell can reach
+// (a cell extends at most 1/4 pixel outside its square, h = floor((s+2)/4)); masks live in shared
+// memory, geometry never touches HBM; (3) one thread per source pixel resolves its s x s output
+// pixels with bit operations over the 3x3 neighbourhood's masks in priority order and writes whole
+// output-row segments with 128-bit streaming stores.
+// Algorithmic HBM traffic: 3 B/px colour + 1 B/px graph in, 4*s*s B/px out.
+#include "kernels.cuh"
+#include "polygon.cuh"
+
+namespace par {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template< int S >
+struct Cfg
+{
+    static constexpr int H = ( S + 2 ) / 4;  // samples a cell reaches beyond its own square, per side
+    static constexpr int R = S + 2 * H;      // samples per axis a cell can cover
+    static constexpr int TW = S <= 4 ? 64 : 32, TH = 16;
+    static constexpr int CW = TW + 2, CH = TH + 2;   // cells whose masks are needed (halo 1)
+    static constexpr int KW = TW + 4, KH = TH + 4;   // cells whose keys are needed (halo 2)
+    static constexpr int GOFF = 16;                  // staged rows begin at column x0 - 16 (TMA: 16-byte aligned start)
+    static constexpr int GP = ( GOFF + TW + 3 + 15 ) / 16 * 16; // staged row pitch (TMA box row), covers x0-3 .. x0+TW+2
+    static constexpr int NC = CW * CH;
+    static constexpr uint32_t FULL = ( 1u << S ) - 1u;
+    // shared memory carve-up (bytes)
+    static constexpr int off_graph = 0;
+    static constexpr int off_keys = off_graph + ( KH * GP + 127 ) / 128 * 128;
+    static constexpr int off_col = off_keys + ( KW * KH * 2 + 15 ) / 16 * 16;
+    static constexpr int off_mask = off_col + NC * 4;
+    static constexpr int off_bar = off_mask + NC * R * 4;
+    static constexpr int smem_bytes = off_bar + 16;
+};
+
+// coordinate of sample k (0..R-1) of a cell, in units of 1/(128 S) pixel, cell-local
+template< int S >
+__device__ __forceinline__ constexpr int sample_coord( int k ) { return ( 2 * ( k - Cfg< S >::H ) + 1 ) * 64; }
+
+// Sink that turns the vertex stream of a polygon into the coverage mask of the cell's R x R samples.
+template< int S >
+struct MaskSink
+{
+    static constexpr int R = Cfg< S >::R;
+    uint32_t row[ R ];
+    int fx, fy, px, py;
+    bool started;
+
+    __device__ __forceinline__ MaskSink() : fx( 0 ), fy( 0 ), px( 0 ), py( 0 ), started( false )
+    {
+#pragma unroll
+        for( int r = 0; r < R; r++ ) row[ r ] = 0u;
+    }
+
+    // toggle, on every sample row the edge crosses, the samples that lie strictly left of the crossing
+    __device__ __forceinline__ void edge( int x0, int y0, int x1, int y1 )
+    {
+        const int dy = y1 - y0;
+        if( dy == 0 ) return;
+        const int dx = x1 - x0;
+        const int ady = dy < 0 ? -dy : dy;
+        const int G = 128 * ady;                                   // F decreases by G per sample column
+        const int base = dx * ( -y0 ) - ( sample_coord< S >( 0 ) - x0 ) * dy; // D at (sample 0, y = 0)
+#pragma unroll
+        for( int r = 0; r < R; r++ )
+        {
+            const int sy = sample_coord< S >( r );
+            if( ( y0 < sy ) != ( y1 < sy ) )
+            {
+                int F = base + dx * sy;
+                F = dy < 0 ? -F : F;
+                int cnt = 0;
+#pragma unroll
+                for( int c = 0; c < R; c++ ) cnt += ( F > c * G ) ? 1 : 0;
+                row[ r ] ^= ( 1u << cnt ) - 1u;
+            }
+        }
+    }
+
+    __device__ __forceinline__ void vertex( int x64, int y64 )
+    {
+        const int x = x64 * 2 * S, y = y64 * 2 * S;
+        if( started )
+            edge( px, py, x, y );
+        else
+        {
+            fx = x;
+            fy = y;
+            started = true;
+        }
+        px = x;
+        py = y;
+    }
+    __device__ __forceinline__ void close()
+    {
+        if( started ) edge( px, py, fx, fy );
+    }
+};
+
+template< int S >
+struct TileEnv
+{
+    const uint16_t* keys; // KW x KH, origin (x0-2, y0-2)
+    int x0, y0;
+    FlatImage img;
+    __device__ __forceinline__ uint32_t key( int i, int j ) const { return keys[ ( j - y0 + 2 ) * Cfg< S >::KW + ( i - x0 + 2 ) ]; }
+    __device__ __forceinline__ bool keep_corner( int i, int j, Q2 p ) const { return img.keep_corner( i, j, p ); }
+};
+
+template< int S, bool kUseTma >
+__global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_constant__ CUtensorMap graph_map, RasterArgs a )
+{
+    typedef Cfg< S > C;
+    extern __shared__ __align__( 128 ) uint8_t smem[];
+    uint8_t* s_graph = smem + C::off_graph;
+    uint16_t* s_keys = reinterpret_cast< uint16_t* >( smem + C::off_keys );
+    uint32_t* s_col = reinterpret_cast< uint32_t* >( smem + C::off_col );
+    uint32_t* s_mask = reinterpret_cast< uint32_t* >( smem + C::off_mask );
+    uint64_t* s_bar = reinterpret_cast< uint64_t* >( smem + C::off_bar );
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * C::TW, y0 = blockIdx.y * C::TH, f = blockIdx.z;
+    const size_t frame_px = ( size_t )a.width * a.height;
+    const uint8_t* frame = a.bgr + ( size_t )f * a.frame_stride;
+    const uint8_t* graph = a.graph + ( size_t )f * frame_px;
+
+    // (1) stage graph bytes: rows y0-2 .. y0+TH+1, columns x0-16 .. x0-16+GP-1; zero outside the image
+    if( kUseTma )
+    {
+        if( tid == 0 )
+        {
+            mbar_init( s_bar, 1 );
+            fence_barrier_init();
+        }
+        __syncthreads();
+        if( tid == 0 )
+        {
+            mbar_expect_tx( s_bar, C::KH * C::GP );
+            tma_load_3d( s_graph, &graph_map, s_bar, x0 - C::GOFF, y0 - 2, f );
+        }
+    }
+    else
+    {
+        for( int idx = tid; idx < C::KH * C::GP; idx += kThreads )
+        {
+            int r = idx / C::GP, c = idx - r * C::GP;
+            int gx = x0 - C::GOFF + c, gy = y0 - 2 + r;
+            uint8_t v = 0;
+            if( gx >= 0 && gy >= 0 && gx < a.width && gy < a.height ) v = graph[ ( size_t )gy * a.width + gx ];
+            s_graph[ idx ] = v;
+        }
+    }
+    // colours of the tile + halo 1 as RGBA words (kernel.cu:98-101: R = byte 2, G = byte 1, B = byte 0)
+    for( int idx = tid; idx < C::NC; idx += kThreads )
+    {
+        int cy = idx / C::CW, cx = idx - cy * C::CW;
+        int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
+        uint32_t w = 0xFF000000u;
+        if( gx >= 0 && gy >= 0 && gx < a.width && gy < a.height )
+        {
+            const uint8_t* p = frame + ( size_t )gy * a.widthstep + 3 * gx;
+            w = ( uint32_t )__ldg( p + 2 ) | ( uint32_t )__ldg( p + 1 ) << 8 | ( uint32_t )__ldg( p ) << 16 | 0xFF000000u;
+        }
+        s_col[ idx ] = w;
+    }
+    if( kUseTma )
+        mbar_wait( s_bar, 0 );
+    __syncthreads();
+
+    // cell keys for tile + halo 2 (left/right neighbour bits, kernel.cu:204-207; zero outside the row)
+    for( int idx = tid; idx < C::KW * C::KH; idx += kThreads )
+    {
+        int ky = idx / C::KW, kx = idx - ky * C::KW;
+        const uint8_t* g = s_graph + ky * C::GP + kx + C::GOFF - 2; // column x0-2+kx sits at staged column kx+GOFF-2
+        s_keys[ idx ] = ( uint16_t )cell_key( g[ 0 ], g[ -1 ], g[ 1 ] );
+    }
+    __syncthreads();
+
+    // (2) coverage mask of every cell of tile + halo 1
+    TileEnv< S > env;
+    env.keys = s_keys;
+    env.x0 = x0;
+    env.y0 = y0;
+    env.img.frame = frame;
+    env.img.width = a.width;
+    env.img.height = a.height;
+    env.img.widthstep = a.widthstep;
+    for( int idx = tid; idx < C::NC; idx += kThreads )
+    {
+        int cy = idx / C::CW, cx = idx - cy * C::CW;
+        int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
+        MaskSink< S > sink;
+        if( gx >= 0 && gy >= 0 && gx < a.width && gy < a.height )
+        {
+            emit_cell_polygon( env, a.cell_table, a.link_table, gx, gy, env.key( gx, gy ), a.subdivide != 0, sink );
+            sink.close();
+        }
+#pragma unroll
+        for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] = sink.row[ r ];
+    }
+    __syncthreads();
+
+    // (3) resolve and write: one thread per source pixel, S output rows of S pixels each
+    const size_t out_w = ( size_t )a.width * S, out_h = ( size_t )a.height * S;
+    uint8_t* out = a.rgba + ( size_t )f * out_w * out_h * 4;
+    for( int idx = tid; idx < C::TW * C::TH; idx += kThreads )
+    {
+        int ly = idx / C::TW, lx = idx - ly * C::TW;
+        int gx = x0 + lx, gy = y0 + ly;
+        if( gx >= a.width || gy >= a.height ) continue;
+        const int cell = ( ly + 1 ) * C::CW + ( lx + 1 );
+#pragma unroll
+        for( int b = 0; b < S; b++ )
+        {
+            uint32_t px[ S ];
+#pragma unroll
+            for( int k = 0; k < S; k++ ) px[ k ] = 0xFF000000u; // background (main.cpp:260)
+            uint32_t rem = C::FULL;
+            // candidates in DESCENDING node index: (dj,di) = (+1,+1) (+1,0) (+1,-1) (0,+1) (0,0) (0,-1) (-1,+1) (-1,0) (-1,-1)
+#pragma unroll
+            for( int dj = 1; dj >= -1; dj-- )
+            {
+                const int ky = b - dj * S + C::H;
+                if( ky < 0 || ky >= C::R ) continue;
+#pragma unroll
+                for( int di = 1; di >= -1; di-- )
+                {
+                    const int nc = cell + dj * C::CW + di;
+                    const uint32_t m = s_mask[ ky * C::NC + nc ];
+                    uint32_t field = di == 0 ? ( m >> C::H ) : ( di > 0 ? ( m << ( S - C::H ) ) : ( m >> ( S + C::H ) ) );
+                    const uint32_t take = field & rem;
+                    if( take )
+                    {
+                        const uint32_t col = s_col[ nc ];
+#pragma unroll
+                        for( int k = 0; k < S; k++ )
+                            if( ( take >> k ) & 1u ) px[ k ] = col;
+                        rem &= ~take;
+                    }
+                }
+            }
+            const size_t oy = a.flip_output ? ( out_h - 1 - ( ( size_t )gy * S + b ) ) : ( ( size_t )gy * S + b );
+            uint8_t* dst = out + ( oy * out_w + ( size_t )gx * S ) * 4;
+            if( S % 4 == 0 )
+            {
+#pragma unroll
+                for( int k = 0; k < S; k += 4 ) st_stream_v4( dst + 4 * k, make_uint4( px[ k ], px[ k + 1 ], px[ k + 2 ], px[ k + 3 ] ) );
+            }
+            else if( S % 2 == 0 )
+            {
+#pragma unroll
+                for( int k = 0; k < S; k += 2 ) *reinterpret_cast< uint2* >( dst + 4 * k ) = make_uint2( px[ k ], px[ k + 1 ] );
+            }
+            else
+            {
+#pragma unroll
+                for( int k = 0; k < S; k++ ) *reinterpret_cast< uint32_t* >( dst + 4 * k ) = px[ k ];
+            }
+        }
+    }
+}
+
+// ---- polygon export: one thread per pixel, everything from global memory ----------------------
+struct GlobalEnv
+{
+    const uint8_t* graph;
+    int width, height;
+    FlatImage img;
+    __device__ __forceinline__ uint32_t node( int i, int j ) const
+    {
+        return ( i >= 0 && j >= 0 && i < width && j < height ) ? __ldg( graph + ( size_t )j * width + i ) : 0u;
+    }
+    __device__ __forceinline__ uint32_t key( int i, int j ) const { return cell_key( node( i, j ), node( i - 1, j ), node( i + 1, j ) ); }
+    __device__ __forceinline__ bool keep_corner( int i, int j, Q2 p ) const { return img.keep_corner( i, j, p ); }
+};
+
+struct VertexSink
+{
+    float* out;
+    int n;
+    __device__ __forceinline__ void vertex( int x64, int y64 )
+    {
+        out[ 2 * n ] = ( float )x64 * 0.015625f;
+        out[ 2 * n + 1 ] = ( float )y64 * 0.015625f;
+        n++;
+    }
+};
+
+__global__ void __launch_bounds__( kThreads ) polygon_kernel( RasterArgs a )
+{
+    const int i = blockIdx.x * 32 + ( threadIdx.x & 31 ), j = blockIdx.y * 8 + ( threadIdx.x >> 5 ), f = blockIdx.z;
+    if( i >= a.width || j >= a.height ) return;
+    const size_t frame_px = ( size_t )a.width * a.height;
+    GlobalEnv env;
+    env.graph = a.graph + ( size_t )f * frame_px;
+    env.width = a.width;
+    env.height = a.height;
+    env.img.frame = a.bgr + ( size_t )f * a.frame_stride;
+    env.img.width = a.width;
+    env.img.height = a.height;
+    env.img.widthstep = a.widthstep;
+    const size_t n = ( size_t )f * frame_px + ( size_t )j * a.width + i;
+    VertexSink sink;
+    sink.out = a.polygons + n * 2 * 45;
+    sink.n = 0;
+    emit_cell_polygon( env, a.cell_table, a.link_table, i, j, env.key( i, j ), a.subdivide != 0, sink );
+    for( int t = sink.n; t < 45; t++ ) // unused slots are zeroed (they are undefined in the reference)
+    {
+        sink.out[ 2 * t ] = 0.0f;
+        sink.out[ 2 * t + 1 ] = 0.0f;
+    }
+    if( a.poly_count ) a.poly_count[ n ] = sink.n;
+}
+
+template< int S >
+cudaError_t launch_raster_s( const RasterArgs& a, const CUtensorMap* graph_map, cudaStream_t stream )
+{
+    typedef Cfg< S > C;
+    dim3 grid( ( a.width + C::TW - 1 ) / C::TW, ( a.height + C::TH - 1 ) / C::TH, a.n_frames );
+    cudaError_t e;
+    if( graph_map )
+    {
+        e = cudaFuncSetAttribute( raster_kernel< S, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes );
+        if( e != cudaSuccess ) return e;
+        raster_kernel< S, true ><<< grid, kThreads, C::smem_bytes, stream >>>( *graph_map, a );
+    }
+    else
+    {
+        CUtensorMap dummy;
+        memset( &dummy, 0, sizeof( dummy ) );
+        e = cudaFuncSetAttribute( raster_kernel< S, false >, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes );
+        if( e != cudaSuccess ) return e;
+        raster_kernel< S, false ><<< grid, kThreads, C::smem_bytes, stream >>>( dummy, a );
+    }
+    return cudaGetLastError();
+}
+
+} // namespace
+
+bool raster_scale_supported( int scale ) { return scale >= 1 && scale <= 8 && scale != 5 && scale != 7; }
+
+void raster_tma_box( int scale, uint32_t box[ 3 ] )
+{
+    const int tw = scale <= 4 ? 64 : 32;
+    box[ 0 ] = ( uint32_t )( ( 16 + tw + 3 + 15 ) / 16 * 16 );
+    box[ 1 ] = 16 + 4;
+    box[ 2 ] = 1;
+}
+
+cudaError_t launch_raster( const RasterArgs& a, const CUtensorMap* graph_map, cudaStream_t stream )
+{
+    switch( a.scale )
+    {
+        case 1: return launch_raster_s< 1 >( a, graph_map, stream );
+        case 2: return launch_raster_s< 2 >( a, graph_map, stream );
+        case 3: return launch_raster_s< 3 >( a, graph_map, stream );
+        case 4: return launch_raster_s< 4 >( a, graph_map, stream );
+        case 6: return launch_raster_s< 6 >( a, graph_map, stream );
+        case 8: return launch_raster_s< 8 >( a, graph_map, stream );
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_polygons( const RasterArgs& a, cudaStream_t stream )
+{
+    dim3 grid( ( a.width + 31 ) / 32, ( a.height + 7 ) / 8, a.n_frames );
+    polygon_kernel<<< grid, kThreads, 0, stream >>>( a );
+    return cudaGetLastError();
+}
+
+} // namespace par
