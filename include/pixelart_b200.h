@@ -59,6 +59,9 @@ enum
     PAR_FLAG_FLIP_OUTPUT = 1u << 1, /* rgba row 0 = top scanline (undo main.cpp:59's flip) */
     PAR_FLAG_NO_TMA = 1u << 2       /* force the plain-load tile path (also taken automatically when
                                        pointers/strides are not 16-byte multiples) */
+    ,
+    PAR_FLAG_DEBUG_WIDE = 1u << 3   /* test hook: rasterize every cell through the exact slow path that
+                                       normally only handles cells reaching beyond their sample mask */
 };
 
 typedef struct par_context par_context;

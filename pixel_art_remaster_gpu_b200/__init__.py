@@ -21,7 +21,7 @@ __all__ = ["Remaster", "RemasterError", "load_library", "library_path", "cell_fr
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CELL_SLOTS = 45
-FLAG_SUBDIVIDE, FLAG_FLIP_OUTPUT, FLAG_NO_TMA = 1, 2, 4
+FLAG_SUBDIVIDE, FLAG_FLIP_OUTPUT, FLAG_NO_TMA, FLAG_DEBUG_WIDE = 1, 2, 4, 8
 _STATUS = {0: "PAR_OK", 1: "PAR_ERR_INVALID", 2: "PAR_ERR_NO_DEVICE", 3: "PAR_ERR_CUDA", 4: "PAR_ERR_CAPACITY"}
 
 
@@ -243,9 +243,10 @@ class Remaster:
         self._check(self.lib.par_stage_polygons(self.handle, C.byref(j)))
         return o["polygons"], o["poly_count"]
 
-    def raster(self, frames, graph, scale=4, subdivide=True, flip_output=False, no_tma=False):
+    def raster(self, frames, graph, scale=4, subdivide=True, flip_output=False, no_tma=False, debug_wide=False):
         F, H, W = frames.shape[:3]
         o = self._alloc(F, H, W, scale, ("rgba",))
-        j = self._job(frames, scale, self._flags(subdivide, flip_output, no_tma), graph=graph, **o)
+        flags = self._flags(subdivide, flip_output, no_tma) | (FLAG_DEBUG_WIDE if debug_wide else 0)
+        j = self._job(frames, scale, flags, graph=graph, **o)
         self._check(self.lib.par_stage_raster(self.handle, C.byref(j)))
         return o["rgba"]

@@ -182,6 +182,7 @@ RasterArgs raster_args( par_context* c, const par_job* j, const uint8_t* graph )
     a.scale = j->scale;
     a.subdivide = ( j->flags & PAR_FLAG_SUBDIVIDE ) ? 1 : 0;
     a.flip_output = ( j->flags & PAR_FLAG_FLIP_OUTPUT ) ? 1 : 0;
+    a.debug_force_wide = ( j->flags & PAR_FLAG_DEBUG_WIDE ) ? 1 : 0;
     return a;
 }
 

@@ -41,6 +41,7 @@ struct RasterArgs
     int scale;
     int subdivide;
     int flip_output;
+    int debug_force_wide; // test hook: treat every cell as reaching beyond its mask (exercises the exact slow path)
 };
 
 dim3 similarity_graph_grid( int width, int height, int n_frames );

@@ -34,41 +34,46 @@ constexpr int kThreads = 256;
 template< int S >
 struct Cfg
 {
-    static constexpr int H = ( S + 2 ) / 4;  // samples a cell reaches beyond its own square, per side
-    static constexpr int R = S + 2 * H;      // samples per axis a cell can cover
+    // A subdivided cell normally reaches at most 22/64 pixel outside its own square (hull vertices reach
+    // 1/4; blending with a neighbour's cut point adds a little).  H = number of samples per side within
+    // that reach: the smallest H whose next sample offset (2H+1)/(2S) exceeds 22/64.  A cell that reaches
+    // further ("wide": only possible when the reference's getPointIndex falls back to vertex 0,
+    // subdivision_functions.cu:537) is flagged and handled exactly by the slow path of the resolve step.
+    static constexpr int H = 11 * S >= 16 ? ( 11 * S - 16 ) / 32 + 1 : 0;
+    static constexpr int R = S + 2 * H;      // samples per axis covered by a cell's mask
+    static constexpr int REACH = ( 2 * H + 1 ) * 64; // first sample offset NOT covered, units of 1/(128 S)
     static constexpr int TW = S <= 4 ? 64 : 32, TH = 16;
     static constexpr int CW = TW + 2, CH = TH + 2;   // cells whose masks are needed (halo 1)
-    static constexpr int KW = TW + 4, KH = TH + 4;   // cells whose keys are needed (halo 2)
+    static constexpr int KW = TW + 4, KH = TH + 4;   // cells whose keys and colours are needed (halo 2)
     static constexpr int GOFF = 16;                  // staged rows begin at column x0 - 16 (TMA: 16-byte aligned start)
     static constexpr int GP = ( GOFF + TW + 3 + 15 ) / 16 * 16; // staged row pitch (TMA box row), covers x0-3 .. x0+TW+2
     static constexpr int NC = CW * CH;
     static constexpr uint32_t FULL = ( 1u << S ) - 1u;
+    static constexpr uint32_t WIDE = 0x80000000u;    // flag carried in mask row 0
     // shared memory carve-up (bytes)
     static constexpr int off_graph = 0;
     static constexpr int off_keys = off_graph + ( KH * GP + 127 ) / 128 * 128;
     static constexpr int off_col = off_keys + ( KW * KH * 2 + 15 ) / 16 * 16;
-    static constexpr int off_mask = off_col + NC * 4;
+    static constexpr int off_mask = off_col + KW * KH * 4;
     static constexpr int off_bar = off_mask + NC * R * 4;
     static constexpr int smem_bytes = off_bar + 16;
 };
 
-// coordinate of sample k (0..R-1) of a cell, in units of 1/(128 S) pixel, cell-local
-template< int S >
-__device__ __forceinline__ constexpr int sample_coord( int k ) { return ( 2 * ( k - Cfg< S >::H ) + 1 ) * 64; }
-
-// Sink that turns the vertex stream of a polygon into the coverage mask of the cell's R x R samples.
-template< int S >
-struct MaskSink
+// Sink that turns the vertex stream of a polygon into an N x N coverage mask.  Sample (c, r) sits at
+// (ox + 128 c, oy + 128 r) in units of 1/(128 S) pixel (cell-local); a vertex at v/64 pixel is 2 S v.
+template< int S, int N >
+struct CoverageSink
 {
-    static constexpr int R = Cfg< S >::R;
-    uint32_t row[ R ];
+    uint32_t row[ N ];
+    int ox, oy;
     int fx, fy, px, py;
+    int lo, hi; // coordinate range of the polygon (for the reach check)
     bool started;
 
-    __device__ __forceinline__ MaskSink() : fx( 0 ), fy( 0 ), px( 0 ), py( 0 ), started( false )
+    __device__ __forceinline__ CoverageSink( int ox_, int oy_ ) : ox( ox_ ), oy( oy_ ), fx( 0 ), fy( 0 ), px( 0 ), py( 0 ), lo( 0 ), hi( 0 ), started( false )
     {
 #pragma unroll
-        for( int r = 0; r < R; r++ ) row[ r ] = 0u;
+        for( int r = 0; r < N; r++ ) row[ r ] = 0u;
     }
 
     // toggle, on every sample row the edge crosses, the samples that lie strictly left of the crossing
@@ -78,19 +83,19 @@ struct MaskSink
         if( dy == 0 ) return;
         const int dx = x1 - x0;
         const int ady = dy < 0 ? -dy : dy;
-        const int G = 128 * ady;                                   // F decreases by G per sample column
-        const int base = dx * ( -y0 ) - ( sample_coord< S >( 0 ) - x0 ) * dy; // D at (sample 0, y = 0)
+        const int G = 128 * ady;                            // F decreases by G per sample column
+        const int base = dx * ( oy - y0 ) - ( ox - x0 ) * dy; // D at sample (0, 0)
 #pragma unroll
-        for( int r = 0; r < R; r++ )
+        for( int r = 0; r < N; r++ )
         {
-            const int sy = sample_coord< S >( r );
+            const int sy = oy + 128 * r;
             if( ( y0 < sy ) != ( y1 < sy ) )
             {
-                int F = base + dx * sy;
+                int F = base + dx * 128 * r;
                 F = dy < 0 ? -F : F;
                 int cnt = 0;
 #pragma unroll
-                for( int c = 0; c < R; c++ ) cnt += ( F > c * G ) ? 1 : 0;
+                for( int c = 0; c < N; c++ ) cnt += ( F > c * G ) ? 1 : 0;
                 row[ r ] ^= ( 1u << cnt ) - 1u;
             }
         }
@@ -100,11 +105,17 @@ struct MaskSink
     {
         const int x = x64 * 2 * S, y = y64 * 2 * S;
         if( started )
+        {
             edge( px, py, x, y );
+            lo = min( lo, min( x, y ) );
+            hi = max( hi, max( x, y ) );
+        }
         else
         {
             fx = x;
             fy = y;
+            lo = min( x, y );
+            hi = max( x, y );
             started = true;
         }
         px = x;
@@ -120,11 +131,38 @@ template< int S >
 struct TileEnv
 {
     const uint16_t* keys; // KW x KH, origin (x0-2, y0-2)
+    const uint32_t* cols; // KW x KH RGBA words, same origin; rows at or above the image height hold colour 0
     int x0, y0;
     FlatImage img;
     __device__ __forceinline__ uint32_t key( int i, int j ) const { return keys[ ( j - y0 + 2 ) * Cfg< S >::KW + ( i - x0 + 2 ) ]; }
-    __device__ __forceinline__ bool keep_corner( int i, int j, Q2 p ) const { return img.keep_corner( i, j, p ); }
+    // checkTJunction (subdivision_functions.cu:170-242).  Away from the first/last column the flat byte
+    // offsets the reference uses (idx +- widthstep +- 3) are exactly the 2-D neighbours, which are staged
+    // in shared memory; at i = 0 / W-1 they wrap to the adjacent rows, so those cells take the flat path.
+    __device__ __forceinline__ bool keep_corner( int i, int j, Q2 p ) const
+    {
+        if( i < 1 || i > img.width - 2 ) return img.keep_corner( i, j, p );
+        if( img.guard( i, j ) ) return true;
+        const bool px0 = p.x == 0, px1 = p.x == 4, py0 = p.y == 0, py1 = p.y == 4;
+        if( !( ( px0 || px1 ) && ( py0 || py1 ) ) ) return false;
+        const int sx = px1 ? 1 : -1, sy = py1 ? 1 : -1; // the corner's quadrant
+        const uint32_t* c = cols + ( j - y0 + 2 ) * Cfg< S >::KW + ( i - x0 + 2 );
+        const uint32_t side = c[ sx ], diag = c[ sy * Cfg< S >::KW + sx ], vert = c[ sy * Cfg< S >::KW ];
+        return side != diag || diag != vert; // the three other pixels around the corner are not one colour
+    }
 };
+
+// slow path of the resolve step: coverage of the S x S samples of target cell (ti,tj) by the polygon of
+// cell (ci,cj) = (ti+di, tj+dj), recomputed from scratch (exact for any reach < 1 pixel)
+template< int S >
+__device__ __noinline__ void window_coverage( const TileEnv< S >& env, const uint64_t* hull_table, const uint32_t* link_table, int ci, int cj,
+                                              int di, int dj, bool subdivide, uint32_t* win )
+{
+    CoverageSink< S, S > sink( 64 - di * 128 * S, 64 - dj * 128 * S );
+    emit_cell_polygon( env, hull_table, link_table, ci, cj, env.key( ci, cj ), subdivide, sink );
+    sink.close();
+#pragma unroll
+    for( int r = 0; r < S; r++ ) win[ r ] = sink.row[ r ];
+}
 
 template< int S, bool kUseTma >
 __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_constant__ CUtensorMap graph_map, RasterArgs a )
@@ -169,11 +207,12 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
             s_graph[ idx ] = v;
         }
     }
-    // colours of the tile + halo 1 as RGBA words (kernel.cu:98-101: R = byte 2, G = byte 1, B = byte 0)
-    for( int idx = tid; idx < C::NC; idx += kThreads )
+    // colours of the tile + halo 2 as RGBA words (kernel.cu:98-101: R = byte 2, G = byte 1, B = byte 0);
+    // pixels outside the image hold colour 0 (the reference's reads beyond the last row see zeros)
+    for( int idx = tid; idx < C::KW * C::KH; idx += kThreads )
     {
-        int cy = idx / C::CW, cx = idx - cy * C::CW;
-        int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
+        int cy = idx / C::KW, cx = idx - cy * C::KW;
+        int gx = x0 - 2 + cx, gy = y0 - 2 + cy;
         uint32_t w = 0xFF000000u;
         if( gx >= 0 && gy >= 0 && gx < a.width && gy < a.height )
         {
@@ -198,21 +237,25 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
     // (2) coverage mask of every cell of tile + halo 1
     TileEnv< S > env;
     env.keys = s_keys;
+    env.cols = s_col;
     env.x0 = x0;
     env.y0 = y0;
     env.img.frame = frame;
     env.img.width = a.width;
     env.img.height = a.height;
     env.img.widthstep = a.widthstep;
+    const bool subdivide = a.subdivide != 0;
     for( int idx = tid; idx < C::NC; idx += kThreads )
     {
         int cy = idx / C::CW, cx = idx - cy * C::CW;
         int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
-        MaskSink< S > sink;
+        CoverageSink< S, C::R > sink( 64 - 128 * C::H, 64 - 128 * C::H );
         if( gx >= 0 && gy >= 0 && gx < a.width && gy < a.height )
         {
-            emit_cell_polygon( env, a.cell_table, a.link_table, gx, gy, env.key( gx, gy ), a.subdivide != 0, sink );
+            emit_cell_polygon( env, a.cell_table, a.link_table, gx, gy, env.key( gx, gy ), subdivide, sink );
             sink.close();
+            // reach check: every sample outside the mask must be strictly outside the polygon's bounding box
+            if( sink.lo <= -C::REACH || sink.hi >= 128 * S + C::REACH || a.debug_force_wide ) sink.row[ 0 ] |= C::WIDE;
         }
 #pragma unroll
         for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] = sink.row[ r ];
@@ -228,7 +271,14 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
         int gx = x0 + lx, gy = y0 + ly;
         if( gx >= a.width || gy >= a.height ) continue;
         const int cell = ( ly + 1 ) * C::CW + ( lx + 1 );
+        const uint32_t* col = s_col + ( ly + 2 ) * C::KW + ( lx + 2 );
+        uint32_t wide = 0;
 #pragma unroll
+        for( int dj = -1; dj <= 1; dj++ )
+#pragma unroll
+            for( int di = -1; di <= 1; di++ ) wide |= s_mask[ cell + dj * C::CW + di ];
+        wide &= C::WIDE;
+#pragma unroll 1
         for( int b = 0; b < S; b++ )
         {
             uint32_t px[ S ];
@@ -236,27 +286,50 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
             for( int k = 0; k < S; k++ ) px[ k ] = 0xFF000000u; // background (main.cpp:260)
             uint32_t rem = C::FULL;
             // candidates in DESCENDING node index: (dj,di) = (+1,+1) (+1,0) (+1,-1) (0,+1) (0,0) (0,-1) (-1,+1) (-1,0) (-1,-1)
-#pragma unroll
-            for( int dj = 1; dj >= -1; dj-- )
+            if( !wide )
             {
-                const int ky = b - dj * S + C::H;
-                if( ky < 0 || ky >= C::R ) continue;
 #pragma unroll
-                for( int di = 1; di >= -1; di-- )
+                for( int dj = 1; dj >= -1; dj-- )
                 {
-                    const int nc = cell + dj * C::CW + di;
-                    const uint32_t m = s_mask[ ky * C::NC + nc ];
-                    uint32_t field = di == 0 ? ( m >> C::H ) : ( di > 0 ? ( m << ( S - C::H ) ) : ( m >> ( S + C::H ) ) );
-                    const uint32_t take = field & rem;
-                    if( take )
-                    {
-                        const uint32_t col = s_col[ nc ];
+                    const int ky = b - dj * S + C::H;
+                    if( ky < 0 || ky >= C::R ) continue;
 #pragma unroll
-                        for( int k = 0; k < S; k++ )
-                            if( ( take >> k ) & 1u ) px[ k ] = col;
-                        rem &= ~take;
+                    for( int di = 1; di >= -1; di-- )
+                    {
+                        const uint32_t m = s_mask[ ky * C::NC + cell + dj * C::CW + di ] & ~C::WIDE;
+                        const uint32_t field = di == 0 ? ( m >> C::H ) : ( di > 0 ? ( m << ( S - C::H ) ) : ( m >> ( S + C::H ) ) );
+                        const uint32_t take = field & rem;
+                        if( take )
+                        {
+                            const uint32_t cw = col[ dj * C::KW + di ];
+#pragma unroll
+                            for( int k = 0; k < S; k++ )
+                                if( ( take >> k ) & 1u ) px[ k ] = cw;
+                            rem &= ~take;
+                        }
                     }
                 }
+            }
+            else
+            {
+                // some cell around reaches beyond its mask: recompute every candidate's coverage of this row exactly
+                for( int dj = 1; dj >= -1; dj-- )
+                    for( int di = 1; di >= -1; di-- )
+                    {
+                        const int ci = gx + di, cj = gy + dj;
+                        if( ci < 0 || cj < 0 || ci >= a.width || cj >= a.height ) continue;
+                        uint32_t win[ S ];
+                        window_coverage< S >( env, a.cell_table, a.link_table, ci, cj, di, dj, subdivide, win );
+                        const uint32_t take = win[ b ] & rem;
+                        if( take )
+                        {
+                            const uint32_t cw = col[ dj * C::KW + di ];
+#pragma unroll
+                            for( int k = 0; k < S; k++ )
+                                if( ( take >> k ) & 1u ) px[ k ] = cw;
+                            rem &= ~take;
+                        }
+                    }
             }
             const size_t oy = a.flip_output ? ( out_h - 1 - ( ( size_t )gy * S + b ) ) : ( ( size_t )gy * S + b );
             uint8_t* dst = out + ( oy * out_w + ( size_t )gx * S ) * 4;

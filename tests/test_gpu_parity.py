@@ -86,6 +86,18 @@ def test_raster_within_one_lsb(ctx, oracle, name, img, scale, subdivide):
         assert diff.max() == 0
 
 
+@pytest.mark.parametrize("scale", [4, 8, 3])
+def test_raster_exact_slow_path(ctx, oracle, scale):
+    """Cells that reach beyond their sample mask are rasterized by an exact slow path; force every cell
+    through it (PAR_FLAG_DEBUG_WIDE) and require the same image."""
+    img = synth.snes_frame(96, 80, synth.BASE_SEED + 3)
+    want = oracle.pipeline(img, scale=scale, want=("graph", "raster"))
+    import torch
+    g = torch.from_numpy(want["graph"][None]).to(ctx.device)
+    rgba = ctx.raster(_dev(ctx, img[None]), g, scale=scale, subdivide=True, debug_wide=True)[0].cpu().numpy()
+    assert np.array_equal(rgba, want["raster"])
+
+
 def test_padded_rows_and_flip(ctx, oracle):
     """widthstep > 3*width (OpenCV row alignment) and the top-scanline-first output option."""
     base = synth.snes_frame(50, 37, 21)
