@@ -55,44 +55,37 @@ PAR_HD void cut_points( Q2 a, Q2 b, int& qx, int& qy, int& rx, int& ry )
 // Sink must provide:  void vertex( int x64, int y64 )
 template< class Env, class Sink >
 PAR_HD void emit_cell_polygon( const Env& env, const uint64_t* __restrict__ hull_table,
-                                                   const uint32_t* __restrict__ link_table, int i, int j, uint32_t key, bool subdivide,
-                                                   Sink& sink )
+                               const uint32_t* __restrict__ link_table, int i, int j, uint32_t key, bool subdivide,
+                               Sink& sink )
 {
     const uint64_t h = PAR_LDG( hull_table + key );
     const int n = hull_count( h );
-    if( !subdivide || ( key & 0xFFu ) == 90u ) // interior nodes are not smoothed (kernel.cu:231)
-    {
-        for( int t = 0; t < n; t++ )
-        {
-            Q2 p = hull_vertex( h, t );
-            sink.vertex( 16 * p.x, 16 * p.y );
-        }
-        return;
-    }
-    const uint32_t links = PAR_LDG( link_table + key );
+    const bool plain = !subdivide || ( key & 0xFFu ) == 90u; // interior nodes are not smoothed (kernel.cu:231)
+    const uint32_t links = plain ? 0u : PAR_LDG( link_table + key );
     int prev_link = ( int )( ( links >> ( 4 * ( n - 1 ) ) ) & 15u );
     Q2 p_prev = hull_vertex( h, n - 1 );
     Q2 p_cur = hull_vertex( h, 0 );
+    // Every hull vertex yields one or two polygon vertices.  The case analysis only computes coordinates;
+    // the sink is fed from ONE place so that the threads of a warp stay converged on its (expensive) code.
     for( int t = 0; t < n; t++ )
     {
         const int cur_link = ( int )( ( links >> ( 4 * t ) ) & 15u );
         const Q2 p_next = hull_vertex( h, t + 1 == n ? 0 : t + 1 );
         const bool cur_border = cur_link == 15, prev_border = prev_link == 15;
-        if( !cur_border && !prev_border )
-            sink.vertex( 16 * p_cur.x, 16 * p_cur.y ); // two shared edges: vertex stays (:651-655)
-        else
+        int ax = 16 * p_cur.x, ay = 16 * p_cur.y, bx = 0, by = 0;
+        bool two = false;
+        if( !plain && ( cur_border || prev_border ) ) // two shared edges: the vertex stays (:651-655)
         {
             int qx, qy, rx, ry, ux, uy;
             cut_points( p_cur, p_next, qx, qy, ux, uy ); // Q of the current edge
             cut_points( p_prev, p_cur, ux, uy, rx, ry ); // R of the previous edge
             if( cur_border && prev_border )
             {
-                if( env.keep_corner( i, j, p_cur ) )
-                    sink.vertex( 16 * p_cur.x, 16 * p_cur.y ); // :583-588
-                else
+                if( !env.keep_corner( i, j, p_cur ) ) // else the corner stays (:583-588)
                 {
-                    sink.vertex( rx, ry ); // :590-598
-                    sink.vertex( qx, qy );
+                    ax = rx; ay = ry; // :590-598
+                    bx = qx; by = qy;
+                    two = true;
                 }
             }
             else
@@ -111,26 +104,29 @@ PAR_HD void emit_cell_polygon( const Env& env, const uint64_t* __restrict__ hull
                     if( c.x == ox && c.y == oy ) op = v;
                 }
                 int aqx, aqy, arx, ary;
+                two = true;
                 if( cur_border )
                 {
                     // neighbour's R on the edge that ENDS at the shared vertex (:125-138)
                     cut_points( hull_vertex( hn, op == 0 ? nn - 1 : op - 1 ), hull_vertex( hn, op ), aqx, aqy, arx, ary );
-                    arx += 64 * di;
-                    ary += 64 * dj;
-                    sink.vertex( ( qx + arx ) >> 1, ( qy + ary ) >> 1 );
-                    sink.vertex( qx, qy );
+                    ax = ( qx + arx + 64 * di ) >> 1;
+                    ay = ( qy + ary + 64 * dj ) >> 1;
+                    bx = qx; by = qy;
                 }
                 else
                 {
                     // neighbour's Q on the edge that STARTS at the shared vertex (:141-154)
                     cut_points( hull_vertex( hn, op ), hull_vertex( hn, op + 1 == nn ? 0 : op + 1 ), aqx, aqy, arx, ary );
-                    aqx += 64 * di;
-                    aqy += 64 * dj;
-                    sink.vertex( rx, ry );
-                    sink.vertex( ( rx + aqx ) >> 1, ( ry + aqy ) >> 1 );
+                    ax = rx; ay = ry;
+                    bx = ( rx + aqx + 64 * di ) >> 1;
+                    by = ( ry + aqy + 64 * dj ) >> 1;
                 }
             }
         }
+#if defined( __CUDA_ARCH__ )
+#pragma unroll 1
+#endif
+        for( int e = 0; e < ( two ? 2 : 1 ); e++ ) sink.vertex( e ? bx : ax, e ? by : ay );
         prev_link = cur_link;
         p_prev = p_cur;
         p_cur = p_next;

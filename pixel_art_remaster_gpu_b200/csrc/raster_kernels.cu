@@ -59,45 +59,44 @@ struct Cfg
     static constexpr int smem_bytes = off_bar + 16;
 };
 
-// Sink that turns the vertex stream of a polygon into an N x N coverage mask.  Sample (c, r) sits at
+// Sink that turns the vertex stream of a polygon into an N x N coverage mask held in memory the caller
+// provides (row r at rows[r * stride]; shared memory on the fast path).  Sample (c, r) sits at
 // (ox + 128 c, oy + 128 r) in units of 1/(128 S) pixel (cell-local); a vertex at v/64 pixel is 2 S v.
 template< int S, int N >
 struct CoverageSink
 {
-    uint32_t row[ N ];
+    uint32_t* rows;
+    int stride;
     int ox, oy;
     int fx, fy, px, py;
     int lo, hi; // coordinate range of the polygon (for the reach check)
     bool started;
 
-    __device__ __forceinline__ CoverageSink( int ox_, int oy_ ) : ox( ox_ ), oy( oy_ ), fx( 0 ), fy( 0 ), px( 0 ), py( 0 ), lo( 0 ), hi( 0 ), started( false )
+    __device__ __forceinline__ CoverageSink( uint32_t* rows_, int stride_, int ox_, int oy_ )
+        : rows( rows_ ), stride( stride_ ), ox( ox_ ), oy( oy_ ), fx( 0 ), fy( 0 ), px( 0 ), py( 0 ), lo( 0 ), hi( 0 ), started( false )
     {
-#pragma unroll
-        for( int r = 0; r < N; r++ ) row[ r ] = 0u;
     }
 
-    // toggle, on every sample row the edge crosses, the samples that lie strictly left of the crossing
+    // toggle, on every sample row the edge crosses, the samples that lie strictly left of the crossing.
+    // Row r (at y = oy + 128 r) is crossed iff min(y0,y1) < y <= max(y0,y1)  [the (y0 < y) != (y1 < y) rule].
     __device__ __forceinline__ void edge( int x0, int y0, int x1, int y1 )
     {
         const int dy = y1 - y0;
         if( dy == 0 ) return;
         const int dx = x1 - x0;
-        const int ady = dy < 0 ? -dy : dy;
-        const int G = 128 * ady;                            // F decreases by G per sample column
-        const int base = dx * ( oy - y0 ) - ( ox - x0 ) * dy; // D at sample (0, 0)
-#pragma unroll
-        for( int r = 0; r < N; r++ )
+        const int r_lo = max( ( ( min( y0, y1 ) - oy ) >> 7 ) + 1, 0 );
+        const int r_hi = min( ( max( y0, y1 ) - oy ) >> 7, N - 1 );
+        const int G = 128 * ( dy < 0 ? -dy : dy );          // F decreases by G per sample column
+        const int step = dy < 0 ? -128 * dx : 128 * dx;     // F increases by step per sample row
+        int F = dx * ( oy - y0 ) - ( ox - x0 ) * dy;         // D at sample (0, 0) ...
+        F = ( dy < 0 ? -F : F ) + r_lo * step;               // ... oriented, at row r_lo
+#pragma unroll 1
+        for( int r = r_lo; r <= r_hi; r++, F += step )
         {
-            const int sy = oy + 128 * r;
-            if( ( y0 < sy ) != ( y1 < sy ) )
-            {
-                int F = base + dx * 128 * r;
-                F = dy < 0 ? -F : F;
-                int cnt = 0;
+            int cnt = 0;
 #pragma unroll
-                for( int c = 0; c < N; c++ ) cnt += ( F > c * G ) ? 1 : 0;
-                row[ r ] ^= ( 1u << cnt ) - 1u;
-            }
+            for( int c = 0; c < N; c++ ) cnt += ( F > c * G ) ? 1 : 0;
+            rows[ r * stride ] ^= ( 1u << cnt ) - 1u;
         }
     }
 
@@ -157,11 +156,10 @@ template< int S >
 __device__ __noinline__ void window_coverage( const TileEnv< S >& env, const uint64_t* hull_table, const uint32_t* link_table, int ci, int cj,
                                               int di, int dj, bool subdivide, uint32_t* win )
 {
-    CoverageSink< S, S > sink( 64 - di * 128 * S, 64 - dj * 128 * S );
+    for( int r = 0; r < S; r++ ) win[ r ] = 0u;
+    CoverageSink< S, S > sink( win, 1, 64 - di * 128 * S, 64 - dj * 128 * S );
     emit_cell_polygon( env, hull_table, link_table, ci, cj, env.key( ci, cj ), subdivide, sink );
     sink.close();
-#pragma unroll
-    for( int r = 0; r < S; r++ ) win[ r ] = sink.row[ r ];
 }
 
 template< int S, bool kUseTma >
@@ -249,16 +247,16 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
     {
         int cy = idx / C::CW, cx = idx - cy * C::CW;
         int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
-        CoverageSink< S, C::R > sink( 64 - 128 * C::H, 64 - 128 * C::H );
+#pragma unroll
+        for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] = 0u;
         if( gx >= 0 && gy >= 0 && gx < a.width && gy < a.height )
         {
+            CoverageSink< S, C::R > sink( s_mask + idx, C::NC, 64 - 128 * C::H, 64 - 128 * C::H );
             emit_cell_polygon( env, a.cell_table, a.link_table, gx, gy, env.key( gx, gy ), subdivide, sink );
             sink.close();
             // reach check: every sample outside the mask must be strictly outside the polygon's bounding box
-            if( sink.lo <= -C::REACH || sink.hi >= 128 * S + C::REACH || a.debug_force_wide ) sink.row[ 0 ] |= C::WIDE;
+            if( sink.lo <= -C::REACH || sink.hi >= 128 * S + C::REACH || a.debug_force_wide ) s_mask[ idx ] |= C::WIDE;
         }
-#pragma unroll
-        for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] = sink.row[ r ];
     }
     __syncthreads();
 
