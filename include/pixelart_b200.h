@@ -100,6 +100,14 @@ int par_synchronize( par_context* ctx );
 /* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
 uint64_t par_launch_count( const par_context* ctx );
 
+/* Per-stage device timing: when enabled, every stage launched by par_remaster_device()/par_stage_*()
+ * is bracketed by CUDA events on the context's stream.  par_profile_read() synchronizes the stream,
+ * adds up the event intervals recorded since the last read and returns, per stage, the total
+ * milliseconds and the number of launches (arrays of PAR_N_STAGES). */
+#define PAR_N_STAGES 5 /* 0 similarity graph, 1 resolve crossings, 2 cc labels, 3 polygons, 4 raster */
+int par_profile_enable( par_context* ctx, int on );
+int par_profile_read( par_context* ctx, double* total_ms, int* launches );
+
 /* Whole path on device-resident frames; asynchronous on the context's stream. */
 int par_remaster_device( par_context* ctx, const par_job* job );
 /* Whole path on host buffers: H2D of the frames, the kernels, D2H of every non-NULL output, then a

@@ -41,6 +41,7 @@ class Oracle:
         L.orc_yuv_word.restype = C.c_uint32
         L.orc_yuv_word.argtypes = [C.c_int] * 4
         L.orc_dissimilar.argtypes = [C.c_uint32, C.c_uint32]
+        L.orc_yuv_all.argtypes = [C.c_int, np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")]
         L.orc_similarity_graph.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p]
         L.orc_trivial_crossings.argtypes = [_u8p, C.c_int, C.c_int, _u8p]
         L.orc_resolve_crossings.argtypes = [_u8p, C.c_int, C.c_int, _u8p, C.POINTER(C.c_int)]
@@ -59,6 +60,11 @@ class Oracle:
     # -- single stages ---------------------------------------------------------------------
     def yuv_word(self, b0, b1, b2, fused=True):
         return int(self.lib.orc_yuv_word(int(b0), int(b1), int(b2), int(fused)))
+
+    def yuv_all(self, fused=True):
+        out = np.zeros(1 << 24, np.uint32)
+        self.lib.orc_yuv_all(int(fused), out)
+        return out
 
     def similarity_graph(self, img, fused=True):
         H, ws = img.shape[0], img.strides[0]
@@ -173,6 +179,7 @@ class RefHost:
         L.ref_host_rgb_to_yuv.restype = C.c_uint32
         L.ref_host_rgb_to_yuv.argtypes = [C.c_int]
         L.ref_host_cell.argtypes = [C.c_int, C.c_int, C.c_int, _f32p]
+        L.ref_host_yuv_all.argtypes = [np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")]
         L.ref_host_pipeline.argtypes = [_u8p] + [C.c_int] * 4 + [C.c_void_p] * 8
 
     @staticmethod
@@ -181,6 +188,11 @@ class RefHost:
 
     def yuv_word(self, c):
         return int(self.lib.ref_host_rgb_to_yuv(int(c)))
+
+    def yuv_all(self):
+        out = np.zeros(1 << 24, np.uint32)
+        self.lib.ref_host_yuv_all(out)
+        return out
 
     def cell(self, node, left, right):
         xy = np.zeros(2 * SLOTS, np.float32)
@@ -203,6 +215,33 @@ class RefHost:
         if stage_ms is not None:
             stage_ms[:] = ms
         return {k: bufs[k] for k in order if k in want}
+
+
+class RefHostCC:
+    """The reference's dead-code border walker (cc_functions.cu) as host C++ (oracle/ref_host_cc_driver.cpp)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_ref", "libref_host_cc.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self.lib.ref_host_border_walks.argtypes = [_u8p, C.c_int, C.c_int, _i32p, _i32p, C.c_int]
+
+    @staticmethod
+    def available():
+        return os.path.exists(os.path.join(HERE, "_ref", "libref_host_cc.so"))
+
+    def border_walks(self, graph):
+        H, W = graph.shape
+        cap = 4 * H * W + 64
+        lst = np.zeros(cap, np.int32)
+        sizes = np.zeros(cap, np.int32)
+        n = self.lib.ref_host_border_walks(np.ascontiguousarray(graph).reshape(-1), W, H, lst, sizes, cap)
+        out, pos = [], 0
+        for k in range(n):
+            out.append(lst[pos:pos + sizes[k]].tolist())
+            pos += sizes[k]
+        return out
 
 
 class RefCuda:

@@ -41,6 +41,11 @@ extern "C" {
 /* packed YUV word of one colour, c = byte0 | byte1<<8 | byte2<<16 (graph_functions.cu:80-98) */
 unsigned int ref_host_rgb_to_yuv( int c ) { return RGBtoYUV( c ); }
 
+void ref_host_yuv_all( unsigned int* out )
+{
+    for( int c = 0; c < ( 1 << 24 ); c++ ) out[ c ] = RGBtoYUV( c );
+}
+
 /* one cell from a pattern (diagram_functions.cu:319); out = 45 (x,y) pairs, returns vertex count */
 int ref_host_cell( int node, int node_left, int node_right, float* out )
 {

@@ -59,6 +59,12 @@ uint32_t orc_yuv_word( int b0, int b1, int b2, int fused )
     return ( uint32_t )( y * 65536 ) + ( uint32_t )( u * 256 ) + ( uint32_t )v; /* :97, two's complement */
 }
 
+/* all 2^24 colours at once (c = byte0 | byte1<<8 | byte2<<16), for the exhaustive tests */
+void orc_yuv_all( int fused, uint32_t* out )
+{
+    for( uint32_t c = 0; c < ( 1u << 24 ); c++ ) out[ c ] = orc_yuv_word( c & 255, ( c >> 8 ) & 255, c >> 16, fused );
+}
+
 static int orc_abs_i32( uint32_t d )
 {
     int a = ( int )d;

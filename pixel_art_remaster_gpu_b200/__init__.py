@@ -16,7 +16,7 @@ import numpy as np
 
 from . import synth  # noqa: F401  (synthetic inputs for the BASELINE configs)
 
-__all__ = ["Remaster", "RemasterError", "load_library", "library_path", "cell_from_pattern", "yuv_word",
+__all__ = ["Remaster", "RemasterGroup", "launch_kernel", "RemasterError", "load_library", "library_path", "cell_from_pattern", "yuv_word",
            "FLAG_SUBDIVIDE", "FLAG_FLIP_OUTPUT", "FLAG_NO_TMA", "CELL_SLOTS", "synth"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -64,12 +64,22 @@ def load_library():
     L.par_device.argtypes = [C.c_void_p]
     L.par_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.par_use_own_stream.argtypes = [C.c_void_p]
+    L.par_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.par_profile_read.argtypes = [C.c_void_p, P(C.c_double), P(C.c_int)]
     L.par_synchronize.argtypes = [C.c_void_p]
     L.par_launch_count.argtypes = [C.c_void_p]
     L.par_launch_count.restype = C.c_uint64
     for name in ("par_remaster_device", "par_remaster_host", "par_stage_similarity_graph", "par_stage_resolve_crossings",
                  "par_stage_cc_labels", "par_stage_polygons", "par_stage_raster"):
         getattr(L, name).argtypes = [C.c_void_p, P(ParJob)]
+    L.par_group_create.argtypes = [P(C.c_void_p), P(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.par_group_destroy.argtypes = [C.c_void_p]
+    L.par_group_destroy.restype = None
+    L.par_group_last_error.argtypes = [C.c_void_p]
+    L.par_group_last_error.restype = C.c_char_p
+    L.par_group_remaster_host.argtypes = [C.c_void_p, P(ParJob)]
+    L.launch_kernel.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_bool]
+    L.launch_kernel.restype = C.c_void_p
     L.par_cell_from_pattern.argtypes = [C.c_uint, P(C.c_float)]
     L.par_yuv_word.argtypes = [C.c_int, C.c_int, C.c_int]
     L.par_yuv_word.restype = C.c_uint32
@@ -137,6 +147,19 @@ class Remaster:
 
     def synchronize(self):
         self._check(self.lib.par_synchronize(self.handle))
+
+    STAGES = ("similarity_graph", "resolve_crossings", "cc_labels", "polygons", "raster")
+
+    def profile(self, on=True):
+        """Bracket every stage launch with CUDA events on the launching stream (par_profile_enable)."""
+        self._check(self.lib.par_profile_enable(self.handle, int(bool(on))))
+
+    def profile_read(self):
+        """{stage: (total_ms, launches)} since the last read; synchronizes the stream."""
+        ms = (C.c_double * 5)()
+        n = (C.c_int * 5)()
+        self._check(self.lib.par_profile_read(self.handle, ms, n))
+        return {k: (ms[i], n[i]) for i, k in enumerate(self.STAGES)}
 
     @property
     def launch_count(self):
@@ -250,3 +273,85 @@ class Remaster:
         j = self._job(frames, scale, flags, graph=graph, **o)
         self._check(self.lib.par_stage_raster(self.handle, C.byref(j)))
         return o["rgba"]
+
+
+class RemasterGroup:
+    """One large image cut into horizontal strips over several GPUs (par_group): host image in, host
+    results out; apron rows travel between neighbouring devices by peer copies.  `devices` may repeat a
+    device index (several strips on one GPU), which is how the single-GPU tests exercise the stitching."""
+
+    def __init__(self, devices, width, height, scale=4):
+        self.lib = load_library()
+        self.handle = C.c_void_p()
+        self.width, self.height, self.scale = int(width), int(height), int(scale)
+        arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+        st = self.lib.par_group_create(C.byref(self.handle), arr, len(devices), self.width, self.height, self.scale)
+        if st != 0:
+            self.handle = C.c_void_p()
+            raise RemasterError(st, self.lib.par_group_last_error(None).decode())
+
+    def close(self):
+        h = getattr(self, "handle", None)
+        if h is not None and h.value:
+            self.lib.par_group_destroy(h)
+            h.value = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def remaster_host(self, image, subdivide=True, want=("rgba", "graph"), flip_output=False):
+        """image: numpy uint8 (H, W, 3) BGR (row stride may exceed 3*W).  Returns numpy arrays."""
+        assert image.dtype == np.uint8 and image.shape[:2] == (self.height, self.width) and image.strides[1:] == (3, 1)
+        H, W, S = self.height, self.width, self.scale
+        out = {}
+        if "rgba" in want:
+            out["rgba"] = np.empty((S * H, S * W, 4), np.uint8)
+        if "graph" in want:
+            out["graph"] = np.empty((H, W), np.uint8)
+        if "graph_aux" in want:
+            out["graph_aux"] = np.empty((H, W), np.uint8)
+        if "labels" in want:
+            out["labels"] = np.empty((H, W), np.int32)
+        j = ParJob()
+        j.bgr = image.ctypes.data
+        j.width, j.height, j.widthstep, j.frame_stride, j.n_frames = W, H, image.strides[0], 0, 1
+        j.scale = S
+        j.flags = (FLAG_SUBDIVIDE if subdivide else 0) | (FLAG_FLIP_OUTPUT if flip_output else 0)
+        for k, v in out.items():
+            setattr(j, k, v.ctypes.data)
+        st = self.lib.par_group_remaster_host(self.handle, C.byref(j))
+        if st != 0:
+            raise RemasterError(st, self.lib.par_group_last_error(self.handle).decode())
+        return out
+
+
+def launch_kernel(img, subdivide=True, want_vbo=False):
+    """The reference's entry point (kernel.cu:286-288) through its C symbol, on the current CUDA device.
+    img: numpy uint8 (H, W, 3) BGR, row 0 = bottom.  Returns (graph (H,W) uint8, edge_count (H*W,) int32,
+    diagram (H*W, 45, 2) float32 triangle list[, pos (H*W,45,2) float32, color (H*W,45,4) uint8])."""
+    import torch
+    L = load_library()
+    H, W = img.shape[:2]
+    N = H * W
+    ws = img.strides[0]
+    flat = np.ascontiguousarray(np.lib.stride_tricks.as_strided(img, shape=(H * ws,), strides=(1,))) if ws != 3 * W else np.ascontiguousarray(img).reshape(-1)
+    pos = torch.empty((N, CELL_SLOTS, 2), dtype=torch.float32, device="cuda")
+    col = torch.empty((N, CELL_SLOTS, 4), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    graph = np.zeros((H, W), np.uint8)
+    count = np.zeros(N, np.int32)
+    ptr = L.launch_kernel(pos.data_ptr(), col.data_ptr(), 0.0, flat.ctypes.data, W, H, ws, count.ctypes.data, graph.ctypes.data, bool(subdivide))
+    diagram = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(N, CELL_SLOTS, 2)).copy()
+    C.CDLL(None).free(C.c_void_p(ptr))  # the caller frees (simpleVBO.cpp:437)
+    if want_vbo:
+        return graph, count, diagram, pos.cpu().numpy(), col.cpu().numpy()
+    return graph, count, diagram

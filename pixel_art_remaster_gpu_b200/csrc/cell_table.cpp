@@ -9,7 +9,7 @@
 // convex hull of those points with collinear points dropped, counter-clockwise from the
 // lexicographically smallest vertex — which is what the reference's sort + monotone chain
 // (diagram_functions.cu:82-129, :238-316) produces for every one of the 4096 patterns
-// (tests/test_cell_table.py compares all of them with the reference build and the oracle).
+// (tests/test_cell_table.py compares all of them with the reference build and the CPU checker).
 #include "cell_table.h"
 #include <algorithm>
 #include <utility>

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <string>
+#include <vector>
 
 using namespace par;
 
@@ -46,6 +47,37 @@ struct par_context
     EncodeTiledFn encode = nullptr;
     uint64_t launches = 0;
     std::string error;
+    // optional per-stage event timing (par_profile_enable)
+    bool profiling = false;
+    struct Span { int stage; cudaEvent_t a, b; };
+    std::vector< Span > spans;
+    std::vector< cudaEvent_t > free_events;
+    cudaEvent_t get_event()
+    {
+        cudaEvent_t e = nullptr;
+        if( !free_events.empty() )
+        {
+            e = free_events.back();
+            free_events.pop_back();
+        }
+        else
+            cudaEventCreate( &e );
+        return e;
+    }
+    cudaEvent_t span_begin()
+    {
+        if( !profiling ) return nullptr;
+        cudaEvent_t e = get_event();
+        cudaEventRecord( e, stream );
+        return e;
+    }
+    void span_end( int stage, cudaEvent_t a )
+    {
+        if( !a ) return;
+        cudaEvent_t b = get_event();
+        cudaEventRecord( b, stream );
+        spans.push_back( Span{ stage, a, b } );
+    }
     // staging for par_remaster_host (grown on demand)
     uint8_t* h_stage[ 8 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     size_t h_stage_bytes[ 8 ] = { 0, 0, 0, 0, 0, 0, 0, 0 };
@@ -122,7 +154,9 @@ int run_similarity( par_context* c, const par_job* j, uint8_t* aux )
     similarity_graph_tma_box( box );
     bool tma = !( j->flags & PAR_FLAG_NO_TMA ) &&
                c->make_map( &map, j->bgr, 3ull * j->width, j->height, j->n_frames, j->widthstep, a.frame_stride, box );
+    cudaEvent_t t0 = c->span_begin();
     cudaError_t e = launch_similarity_graph( a, tma ? &map : nullptr, c->stream );
+    c->span_end( 0, t0 );
     c->launches++;
     return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "similarity_graph" );
 }
@@ -145,7 +179,9 @@ int run_crossings( par_context* c, const par_job* j, const uint8_t* aux, uint8_t
     uint32_t box[ 3 ];
     resolve_crossings_tma_box( box );
     bool tma = graph_map( c, j, aux, box, &map );
+    cudaEvent_t t0 = c->span_begin();
     cudaError_t e = launch_resolve_crossings( a, tma ? &map : nullptr, c->stream );
+    c->span_end( 1, t0 );
     c->launches++;
     return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "resolve_crossings" );
 }
@@ -159,7 +195,9 @@ int run_labels( par_context* c, const par_job* j, const uint8_t* graph, int32_t*
     a.height = j->height;
     a.n_frames = j->n_frames;
     int n = 0;
+    cudaEvent_t t0 = c->span_begin();
     cudaError_t e = launch_cc_labels( a, c->stream, &n );
+    c->span_end( 2, t0 );
     c->launches += n;
     return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "cc_labels" );
 }
@@ -189,7 +227,9 @@ RasterArgs raster_args( par_context* c, const par_job* j, const uint8_t* graph )
 int run_polygons( par_context* c, const par_job* j, const uint8_t* graph )
 {
     RasterArgs a = raster_args( c, j, graph );
+    cudaEvent_t t0 = c->span_begin();
     cudaError_t e = launch_polygons( a, c->stream );
+    c->span_end( 3, t0 );
     c->launches++;
     return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "polygons" );
 }
@@ -202,7 +242,9 @@ int run_raster( par_context* c, const par_job* j, const uint8_t* graph )
     uint32_t box[ 3 ];
     raster_tma_box( j->scale, box );
     bool tma = graph_map( c, j, graph, box, &map );
+    cudaEvent_t t0 = c->span_begin();
     cudaError_t e = launch_raster( a, tma ? &map : nullptr, c->stream );
+    c->span_end( 4, t0 );
     c->launches++;
     return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "raster" );
 }
@@ -279,6 +321,12 @@ void par_destroy( par_context* c )
     cudaFree( c->d_hull );
     cudaFree( c->d_link );
     for( int k = 0; k < 8; k++ ) cudaFree( c->h_stage[ k ] );
+    for( auto& sp : c->spans )
+    {
+        cudaEventDestroy( sp.a );
+        cudaEventDestroy( sp.b );
+    }
+    for( auto e : c->free_events ) cudaEventDestroy( e );
     delete c;
 }
 
@@ -297,6 +345,37 @@ int par_use_own_stream( par_context* c )
 {
     if( !c ) return PAR_ERR_INVALID;
     c->stream = c->own_stream;
+    return PAR_OK;
+}
+
+int par_profile_enable( par_context* c, int on )
+{
+    if( !c ) return PAR_ERR_INVALID;
+    c->profiling = on != 0;
+    return PAR_OK;
+}
+
+int par_profile_read( par_context* c, double* total_ms, int* launches )
+{
+    if( !c ) return PAR_ERR_INVALID;
+    cudaSetDevice( c->device );
+    cudaError_t e = cudaStreamSynchronize( c->stream );
+    if( e != cudaSuccess ) return c->cuda_fail( e, "profile_read" );
+    for( int k = 0; k < PAR_N_STAGES; k++ )
+    {
+        if( total_ms ) total_ms[ k ] = 0.0;
+        if( launches ) launches[ k ] = 0;
+    }
+    for( auto& sp : c->spans )
+    {
+        float ms = 0.f;
+        cudaEventElapsedTime( &ms, sp.a, sp.b );
+        if( total_ms ) total_ms[ sp.stage ] += ms;
+        if( launches ) launches[ sp.stage ]++;
+        c->free_events.push_back( sp.a );
+        c->free_events.push_back( sp.b );
+    }
+    c->spans.clear();
     return PAR_OK;
 }
 

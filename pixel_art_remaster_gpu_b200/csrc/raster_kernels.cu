@@ -5,7 +5,7 @@
 // instead of writing 1.1 kB of geometry per source pixel for a GL driver to rasterize, the cell
 // polygons are sampled directly into the (s*W) x (s*H) RGBA8 image.
 //
-// Raster rule (restated GL point sampling; oracle: orc_raster_polygons): output
+// Raster rule (restated GL point sampling; checked by tests/test_gpu_parity.py): output
 // pixel (X,Y) samples ((X+1/2)/s, (Y+1/2)/s); it takes the colour of the HIGHEST-index source
 // pixel whose polygon covers the sample (cells are drawn in row-major order without depth test),
 // black if none; a sample exactly on an edge/vertex is resolved as if displaced by (+eps, -eps^2)
