@@ -113,15 +113,17 @@ void build_cell_tables( CellTables* t )
     for( unsigned key = 0; key < ( unsigned )kCellKeys; key++ )
     {
         std::vector< Q > h = convex_hull_ccw( candidates( key ) );
-        uint64_t packed = ( uint64_t )h.size();
-        uint32_t links = 0;
-        for( size_t v = 0; v < h.size(); v++ )
+        uint64_t verts = 0, info = ( uint64_t )h.size() << 32, index = 0;
+        for( size_t v = h.size(); v-- > 0; ) // descending, so that the FIRST vertex at a point wins (they are distinct anyway)
         {
-            packed |= ( uint64_t )( ( unsigned )( h[ v ].first + 1 ) | ( unsigned )( h[ v ].second + 1 ) << 3 ) << ( 4 + 6 * v );
-            links |= classify( h[ v ], h[ ( v + 1 ) % h.size() ], key & 0xFFu ) << ( 4 * v );
+            verts |= ( uint64_t )( ( unsigned )( h[ v ].first + 1 ) | ( unsigned )( h[ v ].second + 1 ) << 4 ) << ( 8 * v );
+            info |= ( uint64_t )classify( h[ v ], h[ ( v + 1 ) % h.size() ], key & 0xFFu ) << ( 4 * v );
+            const int code = point_code( h[ v ].first, h[ v ].second );
+            if( code >= 0 ) index = ( index & ~( 15ull << ( 4 * code ) ) ) | ( uint64_t )v << ( 4 * code );
         }
-        t->hull[ key ] = packed;
-        t->link[ key ] = links;
+        t->verts[ key ] = verts;
+        t->info[ key ] = info;
+        t->index[ key ] = index;
     }
 }
 

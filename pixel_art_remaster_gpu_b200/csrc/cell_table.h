@@ -1,49 +1,66 @@
 // Stage D as a table: the cell of a pixel is a pure function of 12 bits (its own graph byte plus the
-// four "corner-cutting" diagonals of its left/right neighbours), so the 4096 hulls and the link
-// classification of their edges are computed once on the host and kept in HBM/L2 (48 KB).
+// four "corner-cutting" diagonals of its left/right neighbours), so the 4096 hulls, the link
+// classification of their edges and a point->vertex index map are computed once on the host and kept
+// in HBM/L2 (96 KB; the few hundred keys a frame actually uses sit in L1).
 //
 // Replaces createCellFromPattern / convex_hull / sort (diagram_functions.cu:319-535, :238-316,
-// :82-129) and isLinkedEdge (subdivision_functions.cu:245-424).
+// :82-129), isLinkedEdge (subdivision_functions.cu:245-424) and the linear search of getPointIndex
+// (:527-538).
 #pragma once
 #include <stdint.h>
+
+#if defined( __CUDACC__ )
+#define PAR_TAB_HD __host__ __device__ __forceinline__
+#else
+#define PAR_TAB_HD inline
+#endif
 
 namespace par {
 
 constexpr int kCellKeys = 4096;
 
 // key = node | left.bit2 << 8 | left.bit7 << 9 | right.bit0 << 10 | right.bit5 << 11
-#if defined( __CUDACC__ )
-__host__ __device__
-#endif
-inline unsigned cell_key( unsigned node, unsigned left, unsigned right )
+PAR_TAB_HD unsigned cell_key( unsigned node, unsigned left, unsigned right )
 {
     return ( node & 0xFFu ) | ( ( left >> 2 ) & 1u ) << 8 | ( ( left >> 7 ) & 1u ) << 9 | ( right & 1u ) << 10 | ( ( right >> 5 ) & 1u ) << 11;
 }
 
-// Packed hull: bits [0,4) = vertex count n (4..8); vertex t at bits [4+6t, 10+6t): low 3 bits =
-// 4*x + 1, high 3 bits = 4*y + 1 (quarter-pixel units, x,y in [-1/4, 5/4]).  Counter-clockwise,
-// starting at the lexicographically smallest vertex, no closing duplicate.
-// Packed links: 4 bits per edge t (vertex t -> t+1 mod n): the graph edge 0..7 the polygon edge is
-// shared through, or 15 for a border edge.
+// Per key, three 64-bit words:
+//   verts : byte t = vertex t of the hull, (4x+1) | (4y+1) << 4, quarter-pixel units, x,y in [-1/4, 5/4];
+//           counter-clockwise from the lexicographically smallest vertex, no closing duplicate
+//   info  : bits [0,32)  4 bits per edge t (vertex t -> t+1 mod n): the graph edge 0..7 the polygon edge
+//                        is shared through, or 15 for a border edge
+//           bits [32,36) vertex count n (4..8)
+//   index : 4 bits per point code (see point_code): the index of the hull vertex at that point, 0 when
+//           the hull has no vertex there (what getPointIndex returns for "not found")
 struct CellTables
 {
-    uint64_t hull[ kCellKeys ];
-    uint32_t link[ kCellKeys ];
+    uint64_t verts[ kCellKeys ];
+    uint64_t info[ kCellKeys ];
+    uint64_t index[ kCellKeys ];
 };
 
 void build_cell_tables( CellTables* t );
 
-#if defined( __CUDACC__ )
-__host__ __device__
+// The 16 points a hull vertex can sit on (square corners, cut corners, the eight diagonal tips), as a
+// code 0..15 = rank of the point in row-major order of the 7x7 quarter-pixel grid [-1,5]^2; -1 for any
+// other point.  (x,y) in quarter pixels.
+constexpr uint64_t kValidPoints = 0x511550155114ull; // bit (y+1)*7 + (x+1)
+#if defined( __CUDA_ARCH__ )
+#define PAR_POPCLL( v ) __popcll( v )
+#else
+#define PAR_POPCLL( v ) __builtin_popcountll( v )
 #endif
-inline int hull_count( uint64_t h ) { return ( int )( h & 15u ); }
-#if defined( __CUDACC__ )
-__host__ __device__
-#endif
-inline int hull_xq( uint64_t h, int t ) { return ( int )( ( h >> ( 4 + 6 * t ) ) & 7u ) - 1; }
-#if defined( __CUDACC__ )
-__host__ __device__
-#endif
-inline int hull_yq( uint64_t h, int t ) { return ( int )( ( h >> ( 7 + 6 * t ) ) & 7u ) - 1; }
+PAR_TAB_HD int point_code( int x, int y )
+{
+    if( ( unsigned )( x + 1 ) > 6u || ( unsigned )( y + 1 ) > 6u ) return -1;
+    const int pos = ( y + 1 ) * 7 + ( x + 1 );
+    if( !( ( kValidPoints >> pos ) & 1u ) ) return -1;
+    return ( int )PAR_POPCLL( kValidPoints & ( ( 1ull << pos ) - 1ull ) );
+}
+
+PAR_TAB_HD int hull_count( uint64_t info ) { return ( int )( ( info >> 32 ) & 15u ); }
+PAR_TAB_HD int hull_xq( uint64_t verts, int t ) { return ( int )( ( verts >> ( 8 * t ) ) & 15u ) - 1; }
+PAR_TAB_HD int hull_yq( uint64_t verts, int t ) { return ( int )( ( verts >> ( 8 * t + 4 ) ) & 15u ) - 1; }
 
 } // namespace par

@@ -42,8 +42,9 @@ struct par_context
     int max_w = 0, max_h = 0, max_frames = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     uint8_t *scratch_aux = nullptr, *scratch_graph = nullptr; // max_frames * max_w * max_h each
-    uint64_t* d_hull = nullptr;
-    uint32_t* d_link = nullptr;
+    uint64_t* d_tables = nullptr;          // verts | info | index, kCellKeys words each
+    uint32_t* d_mask_lut[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // per scale, built on first use
+    CellTablePtrs tables() const { return CellTablePtrs{ d_tables, d_tables + kCellKeys, d_tables + 2 * kCellKeys }; }
     EncodeTiledFn encode = nullptr;
     uint64_t launches = 0;
     std::string error;
@@ -207,8 +208,8 @@ RasterArgs raster_args( par_context* c, const par_job* j, const uint8_t* graph )
     RasterArgs a;
     a.bgr = j->bgr;
     a.graph = graph;
-    a.cell_table = c->d_hull;
-    a.link_table = c->d_link;
+    a.tables = c->tables();
+    a.mask_lut = nullptr;
     a.rgba = j->rgba;
     a.polygons = j->polygons;
     a.poly_count = j->poly_count;
@@ -238,6 +239,15 @@ int run_raster( par_context* c, const par_job* j, const uint8_t* graph )
 {
     if( !raster_scale_supported( j->scale ) ) return c->fail( PAR_ERR_INVALID, "unsupported scale %d (supported: 1,2,3,4,6,8)", j->scale );
     RasterArgs a = raster_args( c, j, graph );
+    if( !c->d_mask_lut[ j->scale ] )
+    {
+        // coverage masks of the 4096 plain hulls at this scale, computed once by the device's own coverage code
+        cudaError_t le = cudaMalloc( &c->d_mask_lut[ j->scale ], mask_lut_words( j->scale ) * sizeof( uint32_t ) );
+        if( le == cudaSuccess ) le = launch_build_mask_lut( j->scale, c->tables(), c->d_mask_lut[ j->scale ], c->stream );
+        c->launches++;
+        if( le != cudaSuccess ) return c->cuda_fail( le, "mask table" );
+    }
+    a.mask_lut = c->d_mask_lut[ j->scale ];
     CUtensorMap map;
     uint32_t box[ 3 ];
     raster_tma_box( j->scale, box );
@@ -286,15 +296,14 @@ int par_create( par_context** out, int device, int max_width, int max_height, in
     size_t px = ( size_t )max_width * max_height * max_frames;
     if( e == cudaSuccess ) e = cudaMalloc( &c->scratch_aux, px );
     if( e == cudaSuccess ) e = cudaMalloc( &c->scratch_graph, px );
-    if( e == cudaSuccess ) e = cudaMalloc( &c->d_hull, sizeof( uint64_t ) * kCellKeys );
-    if( e == cudaSuccess ) e = cudaMalloc( &c->d_link, sizeof( uint32_t ) * kCellKeys );
+    if( e == cudaSuccess ) e = cudaMalloc( &c->d_tables, sizeof( CellTables ) );
     if( e == cudaSuccess )
     {
         static CellTables tables;
         static std::once_flag once;
         std::call_once( once, [] { build_cell_tables( &tables ); } );
-        e = cudaMemcpy( c->d_hull, tables.hull, sizeof( tables.hull ), cudaMemcpyHostToDevice );
-        if( e == cudaSuccess ) e = cudaMemcpy( c->d_link, tables.link, sizeof( tables.link ), cudaMemcpyHostToDevice );
+        static_assert( sizeof( CellTables ) == 3 * kCellKeys * sizeof( uint64_t ), "verts | info | index" );
+        e = cudaMemcpy( c->d_tables, &tables, sizeof( tables ), cudaMemcpyHostToDevice );
     }
     if( e != cudaSuccess )
     {
@@ -318,8 +327,8 @@ void par_destroy( par_context* c )
     }
     cudaFree( c->scratch_aux );
     cudaFree( c->scratch_graph );
-    cudaFree( c->d_hull );
-    cudaFree( c->d_link );
+    cudaFree( c->d_tables );
+    for( int k = 0; k < 9; k++ ) cudaFree( c->d_mask_lut[ k ] );
     for( int k = 0; k < 8; k++ ) cudaFree( c->h_stage[ k ] );
     for( auto& sp : c->spans )
     {
@@ -508,8 +517,8 @@ int par_cell_from_pattern( unsigned key, float* out_xy )
     static CellTables tables;
     static std::once_flag once;
     std::call_once( once, [] { build_cell_tables( &tables ); } );
-    uint64_t h = tables.hull[ key ];
-    int n = hull_count( h );
+    uint64_t h = tables.verts[ key ];
+    int n = hull_count( tables.info[ key ] );
     for( int t = 0; t <= n; t++ )
     {
         out_xy[ 2 * t ] = 0.25f * ( float )hull_xq( h, t % n );

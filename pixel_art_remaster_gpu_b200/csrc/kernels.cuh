@@ -1,6 +1,7 @@
 // Launch interfaces of the sm_100a kernels (one translation unit per stage).
 #pragma once
 #include "common.cuh"
+#include "polygon.cuh"
 #include <string.h>
 
 namespace par {
@@ -31,8 +32,8 @@ struct RasterArgs
 {
     const uint8_t* bgr;
     const uint8_t* graph;       // final graph, dense
-    const uint64_t* cell_table; // 4096 packed hulls (cell_table.h)
-    const uint32_t* link_table; // 4096 packed edge classifications
+    CellTablePtrs tables;       // 4096-entry cell tables (cell_table.h), device pointers
+    const uint32_t* mask_lut;   // per-scale coverage masks of the 4096 plain hulls (raster only)
     uint8_t* rgba;              // out (raster), may be null
     float* polygons;            // out (polygon export), may be null
     int32_t* poly_count;        // out (polygon export), may be null
@@ -56,6 +57,8 @@ cudaError_t launch_cc_labels( const LabelArgs& a, cudaStream_t stream, int* n_la
 
 cudaError_t launch_polygons( const RasterArgs& a, cudaStream_t stream );
 void raster_tma_box( int scale, uint32_t box[ 3 ] );
+size_t mask_lut_words( int scale );
+cudaError_t launch_build_mask_lut( int scale, const CellTablePtrs& tab, uint32_t* lut, cudaStream_t stream );
 cudaError_t launch_raster( const RasterArgs& a, const CUtensorMap* graph_map, cudaStream_t stream );
 bool raster_scale_supported( int scale );
 

@@ -11,7 +11,7 @@
 #include "cell_table.h"
 #include "common.cuh"
 
-// The polygon logic is also compiled for the host (tools/extent_probe.cpp, tests): plain loads there.
+// The polygon logic is also compiled for the host (tools/extent_probe.cpp): plain loads there.
 #if defined( __CUDA_ARCH__ )
 #define PAR_LDG( p ) __ldg( p )
 #else
@@ -25,48 +25,59 @@
 
 namespace par {
 
-// vertex t of a packed hull in quarter-pixel units
-struct Q2 { int x, y; };
-PAR_HD Q2 hull_vertex( uint64_t h, int t )
+struct CellTablePtrs
 {
-    uint32_t v = ( uint32_t )( h >> ( 4 + 6 * t ) );
+    const uint64_t* verts;
+    const uint64_t* info;
+    const uint64_t* index;
+};
+
+// vertex t (0..7) of a packed hull in quarter-pixel units
+struct Q2 { int x, y; };
+PAR_HD Q2 hull_vertex( uint64_t verts, int t )
+{
+#if defined( __CUDA_ARCH__ )
+    const uint32_t b = __byte_perm( ( uint32_t )verts, ( uint32_t )( verts >> 32 ), ( uint32_t )t ) & 0xFFu; // PRMT: byte t of 8
+#else
+    const uint32_t b = ( uint32_t )( verts >> ( 8 * t ) ) & 0xFFu;
+#endif
     Q2 q;
-    q.x = ( int )( v & 7u ) - 1;
-    q.y = ( int )( ( v >> 3 ) & 7u ) - 1;
+    q.x = ( int )( b & 15u ) - 1;
+    q.y = ( int )( b >> 4 ) - 1;
     return q;
 }
 
 // points 1/4 (1/8 when the edge is longer than one pixel) from either end of edge a->b, in 1/64 px
-// (getQ_i / getR_i, subdivision_functions.cu:42-122; "lenght <= 1.0" <=> dx^2+dy^2 <= 16 quarter^2)
+// (getQ_i / getR_i, subdivision_functions.cu:42-122; "lenght <= 1.0" <=> dx^2+dy^2 <= 16 quarter^2):
+// Q = a + w*(b-a), R = b - w*(b-a) with w = 1/4 or 1/8; in 1/64 px a quarter unit is 16.
 PAR_HD void cut_points( Q2 a, Q2 b, int& qx, int& qy, int& rx, int& ry )
 {
-    int dx = b.x - a.x, dy = b.y - a.y;
-    bool is_long = dx * dx + dy * dy > 16;
-    int wa = is_long ? 14 : 12, wb = is_long ? 2 : 4; // 16 * (7/8, 1/8) or 16 * (3/4, 1/4)
-    qx = wa * a.x + wb * b.x;
-    qy = wa * a.y + wb * b.y;
-    rx = wb * a.x + wa * b.x;
-    ry = wb * a.y + wa * b.y;
+    const int dx = b.x - a.x, dy = b.y - a.y;
+    const int w = dx * dx + dy * dy > 16 ? 2 : 4; // 16 * (1/8) or 16 * (1/4)
+    const int ox = dx * w, oy = dy * w;
+    qx = 16 * a.x + ox;
+    qy = 16 * a.y + oy;
+    rx = 16 * b.x - ox;
+    ry = 16 * b.y - oy;
 }
 
 // Env must provide:
 //   uint32_t key( int i, int j )            cell key of an in-image pixel
 //   bool keep_corner( int i, int j, Q2 p )  checkTJunction (subdivision_functions.cu:170-242)
 // Sink must provide:  void vertex( int x64, int y64 )
+// Every hull vertex yields one or two polygon vertices.  The case analysis only computes coordinates;
+// the sink is fed from ONE place so that the threads of a warp stay converged on its code.
 template< class Env, class Sink >
-PAR_HD void emit_cell_polygon( const Env& env, const uint64_t* __restrict__ hull_table,
-                               const uint32_t* __restrict__ link_table, int i, int j, uint32_t key, bool subdivide,
-                               Sink& sink )
+PAR_HD void emit_cell_polygon( const Env& env, const CellTablePtrs& tab, int i, int j, uint32_t key, bool subdivide, Sink& sink )
 {
-    const uint64_t h = PAR_LDG( hull_table + key );
-    const int n = hull_count( h );
+    const uint64_t h = PAR_LDG( tab.verts + key );
+    const uint64_t info = PAR_LDG( tab.info + key );
+    const int n = hull_count( info );
     const bool plain = !subdivide || ( key & 0xFFu ) == 90u; // interior nodes are not smoothed (kernel.cu:231)
-    const uint32_t links = plain ? 0u : PAR_LDG( link_table + key );
+    const uint32_t links = ( uint32_t )info;
     int prev_link = ( int )( ( links >> ( 4 * ( n - 1 ) ) ) & 15u );
     Q2 p_prev = hull_vertex( h, n - 1 );
     Q2 p_cur = hull_vertex( h, 0 );
-    // Every hull vertex yields one or two polygon vertices.  The case analysis only computes coordinates;
-    // the sink is fed from ONE place so that the threads of a warp stay converged on its (expensive) code.
     for( int t = 0; t < n; t++ )
     {
         const int cur_link = ( int )( ( links >> ( 4 * t ) ) & 15u );
@@ -94,15 +105,13 @@ PAR_HD void emit_cell_polygon( const Env& env, const uint64_t* __restrict__ hull
                 // point so that both cells meet on the same curve (:603-647)
                 const int L = cur_border ? prev_link : cur_link;
                 const int di = edge_di( L ), dj = edge_dj( L );
-                const uint64_t hn = PAR_LDG( hull_table + env.key( i + di, j + dj ) );
-                const int nn = hull_count( hn );
-                const int ox = p_cur.x - 4 * di, oy = p_cur.y - 4 * dj; // this vertex in the neighbour's frame
-                int op = 0;
-                for( int v = nn - 1; v >= 0; v-- ) // first match wins, 0 when absent (getPointIndex :527-538)
-                {
-                    Q2 c = hull_vertex( hn, v );
-                    if( c.x == ox && c.y == oy ) op = v;
-                }
+                const uint32_t nkey = env.key( i + di, j + dj );
+                const uint64_t hn = PAR_LDG( tab.verts + nkey );
+                const int nn = hull_count( PAR_LDG( tab.info + nkey ) );
+                // this vertex in the neighbour's frame -> which of the neighbour's vertices it is
+                // (first match, 0 when absent: getPointIndex :527-538, here one table lookup)
+                const int code = point_code( p_cur.x - 4 * di, p_cur.y - 4 * dj );
+                const int op = code < 0 ? 0 : ( int )( ( PAR_LDG( tab.index + nkey ) >> ( 4 * code ) ) & 15u );
                 int aqx, aqy, arx, ary;
                 two = true;
                 if( cur_border )

@@ -14,13 +14,15 @@
 //
 // Design (B200): one CTA per tile of source pixels.  (1) the final-graph bytes of the tile (+halo)
 // are staged in shared memory by one TMA bulk-tensor copy (zero fill outside the image; plain loads
-// when rows are not 16-byte multiples) and turned into 12-bit cell keys; (2) one thread per cell
-// (tile + 1 halo) streams its polygon — hull from the 4096-entry table, corner cutting in
-// registers — straight into a coverage bitmask of the (s + 2h)^2 samples the cell can reach
-// (a cell extends at most 1/4 pixel outside its square, h = floor((s+2)/4)); masks live in shared
-// memory, geometry never touches HBM; (3) one thread per source pixel resolves its s x s output
-// pixels with bit operations over the 3x3 neighbourhood's masks in priority order and writes whole
-// output-row segments with 128-bit streaming stores.
+// when rows are not 16-byte multiples) and turned into 12-bit cell keys; (2) every cell of tile + 1
+// halo gets a coverage bitmask of the (s + 2h)^2 samples it can reach: cells whose polygon is their
+// hull (interior nodes, or subdivision off) copy it from a per-scale 4096-entry mask table, the
+// others are compacted into a work list and processed one thread per cell — the polygon (hull from
+// the cell table, corner cutting in exact 1/64-px integers) is streamed into a small per-thread
+// vertex buffer in shared memory, then a converged loop over its edges toggles the sample rows each
+// edge crosses (masks are 64-bit registers for s <= 4); geometry never touches HBM; (3) one thread
+// per source pixel resolves its s x s output pixels with bit operations over the 3x3 neighbourhood's
+// masks in priority order and writes whole output-row segments with 128-bit streaming stores.
 // Algorithmic HBM traffic: 3 B/px colour + 1 B/px graph in, 4*s*s B/px out.
 #include "kernels.cuh"
 #include "polygon.cuh"
@@ -30,6 +32,7 @@ namespace par {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kMaxVerts = 16; // 8 hull vertices, each replaced by at most two
 
 template< int S >
 struct Cfg
@@ -40,91 +43,128 @@ struct Cfg
     // further ("wide": only possible when the reference's getPointIndex falls back to vertex 0,
     // subdivision_functions.cu:537) is flagged and handled exactly by the slow path of the resolve step.
     static constexpr int H = 11 * S >= 16 ? ( 11 * S - 16 ) / 32 + 1 : 0;
-    static constexpr int R = S + 2 * H;      // samples per axis covered by a cell's mask
-    static constexpr int REACH = ( 2 * H + 1 ) * 64; // first sample offset NOT covered, units of 1/(128 S)
+    static constexpr int R = S + 2 * H;                   // samples per axis covered by a cell's mask
+    // integer units: when S divides 32 a vertex (multiple of 1/64 px) and a sample (odd multiple of
+    // 1/(2S) px) are both integers in units of 1/64 px; otherwise everything is scaled by 2S.
+    static constexpr bool POW2 = ( S & ( S - 1 ) ) == 0 && S <= 32;
+    static constexpr int VM = POW2 ? 1 : 2 * S;           // vertex multiplier
+    static constexpr int SSP = POW2 ? 64 / S : 128;       // distance between samples
+    static constexpr int SSP_LOG2 = SSP == 128 ? 7 : ( SSP == 64 ? 6 : ( SSP == 32 ? 5 : ( SSP == 16 ? 4 : ( SSP == 8 ? 3 : ( SSP == 4 ? 2 : 1 ) ) ) ) );
+    static constexpr int S_FIRST = SSP / 2 - H * SSP;     // coordinate of mask sample 0 (local output index -H)
+    static constexpr int SQUARE = 64 * VM;                // the cell's own square is [0, SQUARE]
+    static constexpr int REACH = H * SSP + SSP / 2;       // offset of the first sample NOT covered by the mask
+    static constexpr bool PACK = R * R <= 63;             // whole mask in one 64-bit word (bit 63 = wide flag)
+    static constexpr int MW = PACK ? 2 : R;               // 32-bit words per mask
     static constexpr int TW = S <= 4 ? 64 : 32, TH = 16;
-    static constexpr int CW = TW + 2, CH = TH + 2;   // cells whose masks are needed (halo 1)
-    static constexpr int KW = TW + 4, KH = TH + 4;   // cells whose keys and colours are needed (halo 2)
-    static constexpr int GOFF = 16;                  // staged rows begin at column x0 - 16 (TMA: 16-byte aligned start)
+    static constexpr int CW = TW + 2, CH = TH + 2;        // cells whose masks are needed (halo 1)
+    static constexpr int KW = TW + 4, KH = TH + 4;        // cells whose keys and colours are needed (halo 2)
+    static constexpr int GOFF = 16;                       // staged rows begin at column x0 - 16 (TMA: 16-byte aligned start)
     static constexpr int GP = ( GOFF + TW + 3 + 15 ) / 16 * 16; // staged row pitch (TMA box row), covers x0-3 .. x0+TW+2
     static constexpr int NC = CW * CH;
     static constexpr uint32_t FULL = ( 1u << S ) - 1u;
-    static constexpr uint32_t WIDE = 0x80000000u;    // flag carried in mask row 0
+    static constexpr uint32_t ROWMASK = ( 1u << R ) - 1u;
+    static constexpr uint32_t WIDE = 0x80000000u;         // flag in the last word (PACK) / in row 0 (rows)
     // shared memory carve-up (bytes)
     static constexpr int off_graph = 0;
     static constexpr int off_keys = off_graph + ( KH * GP + 127 ) / 128 * 128;
     static constexpr int off_col = off_keys + ( KW * KH * 2 + 15 ) / 16 * 16;
     static constexpr int off_mask = off_col + KW * KH * 4;
-    static constexpr int off_bar = off_mask + NC * R * 4;
+    static constexpr int off_vbuf = off_mask + NC * MW * 4;
+    static constexpr int off_work = off_vbuf + kMaxVerts * kThreads * 2;
+    static constexpr int off_bar = ( off_work + NC * 2 + 4 + 15 ) / 16 * 16;
     static constexpr int smem_bytes = off_bar + 16;
 };
 
-// Sink that turns the vertex stream of a polygon into an N x N coverage mask held in memory the caller
-// provides (row r at rows[r * stride]; shared memory on the fast path).  Sample (c, r) sits at
-// (ox + 128 c, oy + 128 r) in units of 1/(128 S) pixel (cell-local); a vertex at v/64 pixel is 2 S v.
+// number of sample columns c in [0,N) with F - c*G > 0, i.e. clamp(ceil(F/G), 0, N), G > 0
 template< int S, int N >
-struct CoverageSink
+__device__ __forceinline__ int columns_left_of( int F, int G, float rcpG )
+{
+    if( Cfg< S >::POW2 )
+    {
+        // (F - 1/2)/G is never an integer and stays >= 1/(2G) >= 4e-5 away from one, far more than the error of
+        // the approximate reciprocal on a quotient of magnitude <= N, so the floor is exact (G <= 64*154).
+        const int q = __float2int_rd( ( ( float )F - 0.5f ) * rcpG ) + 1;
+        return min( max( q, 0 ), N );
+    }
+    int cnt = 0;
+#pragma unroll
+    for( int c = 0; c < N; c++ ) cnt += ( F > c * G ) ? 1 : 0;
+    return cnt;
+}
+
+// Toggle, on every sample row an edge crosses, the samples strictly left of the crossing (even-odd rule with
+// the (+eps, -eps^2) displacement).  Sample (c, r) sits at (ox + SSP c, oy + SSP r).  Row r is crossed iff
+// min(y0,y1) < y_r <= max(y0,y1), which is the (y0 < y) != (y1 < y) rule.
+template< int S, int N, class Toggle >
+__device__ __forceinline__ void cover_edge( int ox, int oy, int x0, int y0, int x1, int y1, Toggle& toggle )
+{
+    typedef Cfg< S > C;
+    const int dy = y1 - y0;
+    if( dy == 0 ) return;
+    const int dx = x1 - x0;
+    const int r_lo = max( ( ( min( y0, y1 ) - oy ) >> C::SSP_LOG2 ) + 1, 0 );
+    const int r_hi = min( ( max( y0, y1 ) - oy ) >> C::SSP_LOG2, N - 1 );
+    const int G = C::SSP * ( dy < 0 ? -dy : dy );                 // F decreases by G per sample column
+    const int step = dy < 0 ? -C::SSP * dx : C::SSP * dx;          // F increases by step per sample row
+    int F = dx * ( oy - y0 ) - ( ox - x0 ) * dy;                   // edge function at sample (0, 0) ...
+    F = ( dy < 0 ? -F : F ) + r_lo * step;                         // ... oriented, at row r_lo
+    const float rcpG = __fdividef( 1.0f, ( float )G );
+#pragma unroll 1
+    for( int r = r_lo; r <= r_hi; r++, F += step ) toggle( r, columns_left_of< S, N >( F, G, rcpG ) );
+}
+
+template< int R >
+struct PackedToggle // R x R mask in one 64-bit register, row r at bits [R r, R r + R)
+{
+    uint64_t m;
+    __device__ __forceinline__ void operator()( int r, int cnt ) { m ^= ( uint64_t )( ( 1u << cnt ) - 1u ) << ( R * r ); }
+};
+struct RowToggle // rows in memory (shared memory on the fast path), row r at rows[r * stride]
 {
     uint32_t* rows;
     int stride;
-    int ox, oy;
-    int fx, fy, px, py;
-    int lo, hi; // coordinate range of the polygon (for the reach check)
-    bool started;
+    __device__ __forceinline__ void operator()( int r, int cnt ) { rows[ r * stride ] ^= ( 1u << cnt ) - 1u; }
+};
 
-    __device__ __forceinline__ CoverageSink( uint32_t* rows_, int stride_, int ox_, int oy_ )
-        : rows( rows_ ), stride( stride_ ), ox( ox_ ), oy( oy_ ), fx( 0 ), fy( 0 ), px( 0 ), py( 0 ), lo( 0 ), hi( 0 ), started( false )
-    {
-    }
-
-    // toggle, on every sample row the edge crosses, the samples that lie strictly left of the crossing.
-    // Row r (at y = oy + 128 r) is crossed iff min(y0,y1) < y <= max(y0,y1)  [the (y0 < y) != (y1 < y) rule].
-    __device__ __forceinline__ void edge( int x0, int y0, int x1, int y1 )
-    {
-        const int dy = y1 - y0;
-        if( dy == 0 ) return;
-        const int dx = x1 - x0;
-        const int r_lo = max( ( ( min( y0, y1 ) - oy ) >> 7 ) + 1, 0 );
-        const int r_hi = min( ( max( y0, y1 ) - oy ) >> 7, N - 1 );
-        const int G = 128 * ( dy < 0 ? -dy : dy );          // F decreases by G per sample column
-        const int step = dy < 0 ? -128 * dx : 128 * dx;     // F increases by step per sample row
-        int F = dx * ( oy - y0 ) - ( ox - x0 ) * dy;         // D at sample (0, 0) ...
-        F = ( dy < 0 ? -F : F ) + r_lo * step;               // ... oriented, at row r_lo
-#pragma unroll 1
-        for( int r = r_lo; r <= r_hi; r++, F += step )
-        {
-            int cnt = 0;
-#pragma unroll
-            for( int c = 0; c < N; c++ ) cnt += ( F > c * G ) ? 1 : 0;
-            rows[ r * stride ] ^= ( 1u << cnt ) - 1u;
-        }
-    }
-
+// Sink of emit_cell_polygon: vertices go to a small buffer (element k at buf[k * stride]), packed as
+// (x64 + 64) << 8 | (y64 + 64); tracks the coordinate range for the reach check.
+struct VertexBufSink
+{
+    uint16_t* buf;
+    int stride, n, lo, hi;
+    __device__ __forceinline__ VertexBufSink( uint16_t* b, int s ) : buf( b ), stride( s ), n( 0 ), lo( 0 ), hi( 0 ) {}
     __device__ __forceinline__ void vertex( int x64, int y64 )
     {
-        const int x = x64 * 2 * S, y = y64 * 2 * S;
-        if( started )
-        {
-            edge( px, py, x, y );
-            lo = min( lo, min( x, y ) );
-            hi = max( hi, max( x, y ) );
-        }
-        else
-        {
-            fx = x;
-            fy = y;
-            lo = min( x, y );
-            hi = max( x, y );
-            started = true;
-        }
-        px = x;
-        py = y;
-    }
-    __device__ __forceinline__ void close()
-    {
-        if( started ) edge( px, py, fx, fy );
+        buf[ n * stride ] = ( uint16_t )( ( ( x64 + 64 ) << 8 ) | ( y64 + 64 ) );
+        n++;
+        lo = min( lo, min( x64, y64 ) );
+        hi = max( hi, max( x64, y64 ) );
     }
 };
+
+// coverage of the buffered polygon over an N x N sample window whose sample (0,0) sits at (ox, oy)
+template< int S, int N, class Toggle >
+__device__ __forceinline__ void cover_polygon( const uint16_t* buf, int stride, int n, int ox, int oy, Toggle& toggle )
+{
+    constexpr int VM = Cfg< S >::VM;
+    uint32_t v = buf[ 0 ];
+    int x0 = ( ( int )( v >> 8 ) - 64 ) * VM, y0 = ( ( int )( v & 255u ) - 64 ) * VM;
+    const int fx = x0, fy = y0;
+#pragma unroll 1
+    for( int k = 1; k <= n; k++ )
+    {
+        int x1 = fx, y1 = fy;
+        if( k < n )
+        {
+            v = buf[ k * stride ];
+            x1 = ( ( int )( v >> 8 ) - 64 ) * VM;
+            y1 = ( ( int )( v & 255u ) - 64 ) * VM;
+        }
+        cover_edge< S, N >( ox, oy, x0, y0, x1, y1, toggle );
+        x0 = x1;
+        y0 = y1;
+    }
+}
 
 template< int S >
 struct TileEnv
@@ -153,13 +193,50 @@ struct TileEnv
 // slow path of the resolve step: coverage of the S x S samples of target cell (ti,tj) by the polygon of
 // cell (ci,cj) = (ti+di, tj+dj), recomputed from scratch (exact for any reach < 1 pixel)
 template< int S >
-__device__ __noinline__ void window_coverage( const TileEnv< S >& env, const uint64_t* hull_table, const uint32_t* link_table, int ci, int cj,
-                                              int di, int dj, bool subdivide, uint32_t* win )
+__device__ __noinline__ void window_coverage( const TileEnv< S >& env, const CellTablePtrs& tab, int ci, int cj, int di, int dj, bool subdivide,
+                                              uint32_t* win )
 {
+    typedef Cfg< S > C;
+    uint16_t verts[ kMaxVerts ];
+    VertexBufSink sink( verts, 1 );
+    emit_cell_polygon( env, tab, ci, cj, env.key( ci, cj ), subdivide, sink );
     for( int r = 0; r < S; r++ ) win[ r ] = 0u;
-    CoverageSink< S, S > sink( win, 1, 64 - di * 128 * S, 64 - dj * 128 * S );
-    emit_cell_polygon( env, hull_table, link_table, ci, cj, env.key( ci, cj ), subdivide, sink );
-    sink.close();
+    RowToggle tg{ win, 1 };
+    cover_polygon< S, S >( verts, 1, sink.n, C::SSP / 2 - di * C::SQUARE, C::SSP / 2 - dj * C::SQUARE, tg );
+}
+
+// mask of a cell whose polygon is its plain hull, for every key: the per-scale table the raster kernel copies from
+struct NoEnv
+{
+    __device__ __forceinline__ uint32_t key( int, int ) const { return 0u; }
+    __device__ __forceinline__ bool keep_corner( int, int, Q2 ) const { return true; }
+};
+
+template< int S >
+__global__ void build_mask_lut_kernel( CellTablePtrs tab, uint32_t* lut )
+{
+    typedef Cfg< S > C;
+    const int key = blockIdx.x * blockDim.x + threadIdx.x;
+    if( key >= kCellKeys ) return;
+    uint16_t verts[ kMaxVerts ];
+    VertexBufSink sink( verts, 1 );
+    NoEnv env;
+    emit_cell_polygon( env, tab, 0, 0, ( uint32_t )key, false, sink );
+    if( C::PACK )
+    {
+        PackedToggle< C::R > tg{ 0ull };
+        cover_polygon< S, C::R >( verts, 1, sink.n, C::S_FIRST, C::S_FIRST, tg );
+        lut[ 2 * key ] = ( uint32_t )tg.m;
+        lut[ 2 * key + 1 ] = ( uint32_t )( tg.m >> 32 );
+    }
+    else
+    {
+        uint32_t rows[ C::R ];
+        for( int r = 0; r < C::R; r++ ) rows[ r ] = 0u;
+        RowToggle tg{ rows, 1 };
+        cover_polygon< S, C::R >( verts, 1, sink.n, C::S_FIRST, C::S_FIRST, tg );
+        for( int r = 0; r < C::R; r++ ) lut[ C::R * key + r ] = rows[ r ];
+    }
 }
 
 template< int S, bool kUseTma >
@@ -170,7 +247,10 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
     uint8_t* s_graph = smem + C::off_graph;
     uint16_t* s_keys = reinterpret_cast< uint16_t* >( smem + C::off_keys );
     uint32_t* s_col = reinterpret_cast< uint32_t* >( smem + C::off_col );
-    uint32_t* s_mask = reinterpret_cast< uint32_t* >( smem + C::off_mask );
+    uint32_t* s_mask = reinterpret_cast< uint32_t* >( smem + C::off_mask );   // PACK: [NC][2]; rows: [R][NC]
+    uint16_t* s_vbuf = reinterpret_cast< uint16_t* >( smem + C::off_vbuf );   // [kMaxVerts][kThreads]
+    uint16_t* s_work = reinterpret_cast< uint16_t* >( smem + C::off_work );   // cells that need the general path
+    int* s_nwork = reinterpret_cast< int* >( smem + C::off_work + C::NC * 2 );
     uint64_t* s_bar = reinterpret_cast< uint64_t* >( smem + C::off_bar );
 
     const int tid = threadIdx.x;
@@ -180,6 +260,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
     const uint8_t* graph = a.graph + ( size_t )f * frame_px;
 
     // (1) stage graph bytes: rows y0-2 .. y0+TH+1, columns x0-16 .. x0-16+GP-1; zero outside the image
+    if( tid == 0 ) *s_nwork = 0;
     if( kUseTma )
     {
         if( tid == 0 )
@@ -232,7 +313,6 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
     }
     __syncthreads();
 
-    // (2) coverage mask of every cell of tile + halo 1
     TileEnv< S > env;
     env.keys = s_keys;
     env.cols = s_col;
@@ -243,19 +323,64 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
     env.img.height = a.height;
     env.img.widthstep = a.widthstep;
     const bool subdivide = a.subdivide != 0;
+    const CellTablePtrs tab = a.tables;
+    const uint32_t force_wide = a.debug_force_wide ? C::WIDE : 0u;
+
+    // (2a) cells whose polygon is their plain hull copy the mask from the table; the rest queue up
     for( int idx = tid; idx < C::NC; idx += kThreads )
     {
         int cy = idx / C::CW, cx = idx - cy * C::CW;
         int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
-#pragma unroll
-        for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] = 0u;
-        if( gx >= 0 && gy >= 0 && gx < a.width && gy < a.height )
+        const bool inside = gx >= 0 && gy >= 0 && gx < a.width && gy < a.height;
+        const uint32_t key = s_keys[ ( cy + 1 ) * C::KW + cx + 1 ];
+        const bool plain = !subdivide || ( key & 0xFFu ) == 90u;
+        if( inside && !plain )
+            s_work[ atomicAdd( s_nwork, 1 ) ] = ( uint16_t )idx;
+        else if( C::PACK )
         {
-            CoverageSink< S, C::R > sink( s_mask + idx, C::NC, 64 - 128 * C::H, 64 - 128 * C::H );
-            emit_cell_polygon( env, a.cell_table, a.link_table, gx, gy, env.key( gx, gy ), subdivide, sink );
-            sink.close();
+            uint2 m = make_uint2( 0u, 0u );
+            if( inside )
+            {
+                m = __ldg( reinterpret_cast< const uint2* >( a.mask_lut ) + key );
+                m.y |= force_wide;
+            }
+            reinterpret_cast< uint2* >( s_mask )[ idx ] = m;
+        }
+        else
+        {
+#pragma unroll
+            for( int r = 0; r < C::R; r++ )
+                s_mask[ r * C::NC + idx ] = inside ? ( __ldg( a.mask_lut + key * C::R + r ) | ( r == 0 ? force_wide : 0u ) ) : 0u;
+        }
+    }
+    __syncthreads();
+
+    // (2b) general path: one thread per queued cell; polygon -> per-thread vertex buffer -> edge loop
+    {
+        const int n_work = *s_nwork;
+        uint16_t* vbuf = s_vbuf + tid;
+        for( int w = tid; w < n_work; w += kThreads )
+        {
+            const int idx = s_work[ w ];
+            int cy = idx / C::CW, cx = idx - cy * C::CW;
+            int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
+            VertexBufSink sink( vbuf, kThreads );
+            emit_cell_polygon( env, tab, gx, gy, s_keys[ ( cy + 1 ) * C::KW + cx + 1 ], true, sink );
             // reach check: every sample outside the mask must be strictly outside the polygon's bounding box
-            if( sink.lo <= -C::REACH || sink.hi >= 128 * S + C::REACH || a.debug_force_wide ) s_mask[ idx ] |= C::WIDE;
+            const uint32_t wide = ( sink.lo * C::VM <= -C::REACH || sink.hi * C::VM >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
+            if( C::PACK )
+            {
+                PackedToggle< C::R > tg{ 0ull };
+                cover_polygon< S, C::R >( vbuf, kThreads, sink.n, C::S_FIRST, C::S_FIRST, tg );
+                reinterpret_cast< uint2* >( s_mask )[ idx ] = make_uint2( ( uint32_t )tg.m, ( uint32_t )( tg.m >> 32 ) | wide );
+            }
+            else
+            {
+#pragma unroll
+                for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] = r == 0 ? wide : 0u;
+                RowToggle tg{ s_mask + idx, C::NC };
+                cover_polygon< S, C::R >( vbuf, kThreads, sink.n, C::S_FIRST, C::S_FIRST, tg );
+            }
         }
     }
     __syncthreads();
@@ -270,20 +395,37 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
         if( gx >= a.width || gy >= a.height ) continue;
         const int cell = ( ly + 1 ) * C::CW + ( lx + 1 );
         const uint32_t* col = s_col + ( ly + 2 ) * C::KW + ( lx + 2 );
+        // the 3x3 neighbourhood's masks; candidates are visited in DESCENDING node index:
+        // (dj,di) = (+1,+1) (+1,0) (+1,-1) (0,+1) (0,0) (0,-1) (-1,+1) (-1,0) (-1,-1)
+        uint64_t pm[ C::PACK ? 9 : 1 ];
         uint32_t wide = 0;
+        if( C::PACK )
+        {
 #pragma unroll
-        for( int dj = -1; dj <= 1; dj++ )
+            for( int dj = -1; dj <= 1; dj++ )
 #pragma unroll
-            for( int di = -1; di <= 1; di++ ) wide |= s_mask[ cell + dj * C::CW + di ];
+                for( int di = -1; di <= 1; di++ )
+                {
+                    const uint2 m = reinterpret_cast< const uint2* >( s_mask )[ cell + dj * C::CW + di ];
+                    wide |= m.y;
+                    pm[ ( dj + 1 ) * 3 + di + 1 ] = ( ( uint64_t )( m.y & ~C::WIDE ) << 32 ) | m.x;
+                }
+        }
+        else
+        {
+#pragma unroll
+            for( int dj = -1; dj <= 1; dj++ )
+#pragma unroll
+                for( int di = -1; di <= 1; di++ ) wide |= s_mask[ cell + dj * C::CW + di ];
+        }
         wide &= C::WIDE;
-#pragma unroll 1
+#pragma unroll( C::PACK ? S : 1 )
         for( int b = 0; b < S; b++ )
         {
             uint32_t px[ S ];
 #pragma unroll
             for( int k = 0; k < S; k++ ) px[ k ] = 0xFF000000u; // background (main.cpp:260)
             uint32_t rem = C::FULL;
-            // candidates in DESCENDING node index: (dj,di) = (+1,+1) (+1,0) (+1,-1) (0,+1) (0,0) (0,-1) (-1,+1) (-1,0) (-1,-1)
             if( !wide )
             {
 #pragma unroll
@@ -294,7 +436,11 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
 #pragma unroll
                     for( int di = 1; di >= -1; di-- )
                     {
-                        const uint32_t m = s_mask[ ky * C::NC + cell + dj * C::CW + di ] & ~C::WIDE;
+                        uint32_t m;
+                        if( C::PACK )
+                            m = ( uint32_t )( pm[ ( dj + 1 ) * 3 + di + 1 ] >> ( C::R * ky ) ) & C::ROWMASK;
+                        else
+                            m = s_mask[ ky * C::NC + cell + dj * C::CW + di ] & ~C::WIDE;
                         const uint32_t field = di == 0 ? ( m >> C::H ) : ( di > 0 ? ( m << ( S - C::H ) ) : ( m >> ( S + C::H ) ) );
                         const uint32_t take = field & rem;
                         if( take )
@@ -317,7 +463,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                         const int ci = gx + di, cj = gy + dj;
                         if( ci < 0 || cj < 0 || ci >= a.width || cj >= a.height ) continue;
                         uint32_t win[ S ];
-                        window_coverage< S >( env, a.cell_table, a.link_table, ci, cj, di, dj, subdivide, win );
+                        window_coverage< S >( env, tab, ci, cj, di, dj, subdivide, win );
                         const uint32_t take = win[ b ] & rem;
                         if( take )
                         {
@@ -393,7 +539,7 @@ __global__ void __launch_bounds__( kThreads ) polygon_kernel( RasterArgs a )
     VertexSink sink;
     sink.out = a.polygons + n * 2 * 45;
     sink.n = 0;
-    emit_cell_polygon( env, a.cell_table, a.link_table, i, j, env.key( i, j ), a.subdivide != 0, sink );
+    emit_cell_polygon( env, a.tables, i, j, env.key( i, j ), a.subdivide != 0, sink );
     for( int t = sink.n; t < 45; t++ ) // unused slots are zeroed (they are undefined in the reference)
     {
         sink.out[ 2 * t ] = 0.0f;
@@ -425,9 +571,44 @@ cudaError_t launch_raster_s( const RasterArgs& a, const CUtensorMap* graph_map, 
     return cudaGetLastError();
 }
 
+template< int S >
+cudaError_t build_lut_s( const CellTablePtrs& tab, uint32_t* lut, cudaStream_t stream )
+{
+    build_mask_lut_kernel< S ><<< kCellKeys / 128, 128, 0, stream >>>( tab, lut );
+    return cudaGetLastError();
+}
+
 } // namespace
 
 bool raster_scale_supported( int scale ) { return scale >= 1 && scale <= 8 && scale != 5 && scale != 7; }
+
+#define PAR_FOR_SCALE( scale, CALL )  \
+    switch( scale )                    \
+    {                                  \
+        case 1: CALL( 1 );             \
+        case 2: CALL( 2 );             \
+        case 3: CALL( 3 );             \
+        case 4: CALL( 4 );             \
+        case 6: CALL( 6 );             \
+        case 8: CALL( 8 );             \
+        default: break;                \
+    }
+
+size_t mask_lut_words( int scale )
+{
+#define PAR_WORDS( S ) return ( size_t )kCellKeys * Cfg< S >::MW
+    PAR_FOR_SCALE( scale, PAR_WORDS )
+#undef PAR_WORDS
+    return 0;
+}
+
+cudaError_t launch_build_mask_lut( int scale, const CellTablePtrs& tab, uint32_t* lut, cudaStream_t stream )
+{
+#define PAR_BUILD( S ) return build_lut_s< S >( tab, lut, stream )
+    PAR_FOR_SCALE( scale, PAR_BUILD )
+#undef PAR_BUILD
+    return cudaErrorInvalidValue;
+}
 
 void raster_tma_box( int scale, uint32_t box[ 3 ] )
 {
@@ -439,16 +620,10 @@ void raster_tma_box( int scale, uint32_t box[ 3 ] )
 
 cudaError_t launch_raster( const RasterArgs& a, const CUtensorMap* graph_map, cudaStream_t stream )
 {
-    switch( a.scale )
-    {
-        case 1: return launch_raster_s< 1 >( a, graph_map, stream );
-        case 2: return launch_raster_s< 2 >( a, graph_map, stream );
-        case 3: return launch_raster_s< 3 >( a, graph_map, stream );
-        case 4: return launch_raster_s< 4 >( a, graph_map, stream );
-        case 6: return launch_raster_s< 6 >( a, graph_map, stream );
-        case 8: return launch_raster_s< 8 >( a, graph_map, stream );
-        default: return cudaErrorInvalidValue;
-    }
+#define PAR_RASTER( S ) return launch_raster_s< S >( a, graph_map, stream )
+    PAR_FOR_SCALE( a.scale, PAR_RASTER )
+#undef PAR_RASTER
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_polygons( const RasterArgs& a, cudaStream_t stream )
