@@ -73,7 +73,7 @@ def build_cli(force=False):
     if not force and not _stale(CLI, deps):
         return CLI
     cmd = ["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", HOST] + srcs + \
-          ["-o", CLI, "-L", HERE, "-lpixelart_b200", "-Wl,-rpath,$ORIGIN"]
+          ["-o", CLI, "-L", HERE, "-lpixelart_b200", "-lz", "-Wl,-rpath,$ORIGIN"]
     subprocess.run(cmd, check=True)
     return CLI
 

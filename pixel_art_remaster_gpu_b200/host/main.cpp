@@ -1,0 +1,161 @@
+// remaster_cli — the reference's program entry point (main.cpp:166-194) without the GLUT window:
+// image in, remastered image out.
+//
+//   remaster_cli <input image> [-o out.png] [-s scale] [--no-subdivide] [--graph g.pgm] [--labels l.pgm]
+//                [--strips N] [--device D] [--convert-only]
+//
+// Kept from the reference: argv[1] is the input path (main.cpp:172-173); load_image() loads in colour,
+// flips the image vertically so that row 0 is the bottom scanline, and publishes img_data / img_width /
+// img_height / img_nchannels / img_widthstep (main.cpp:50-64); allocate_graph() makes the host graph
+// (main.cpp:141-147).  Where the reference enters glutMainLoop and draws 45 vertices per pixel through
+// OpenGL, this program calls the C ABI once and writes the rasterized image (un-flipped again).
+#include "Image.h"
+#include "pixelart_b200.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// the reference's globals (main.cpp:31-38)
+Image* img = nullptr;
+char* img_data = nullptr;
+int img_width = 0, img_height = 0, img_nchannels = 0, img_widthstep = 0;
+char* graph = nullptr;
+
+static bool load_image( const char* path )
+{
+    img = new Image();
+    img->loadImage( path, CV_LOAD_IMAGE_COLOR );
+    if( !img->ok() )
+    {
+        fprintf( stderr, "remaster_cli: %s\n", img->error().c_str() );
+        return false;
+    }
+    img->reverses(); // main.cpp:59
+    img_data = img->getImageData();
+    img_width = img->getWidth();
+    img_height = img->getHeight();
+    img_nchannels = img->getNchannels();
+    img_widthstep = img->getWidthStep();
+    return true;
+}
+
+static void allocate_graph() { graph = ( char* )calloc( ( size_t )img_width * img_height, 1 ); } // main.cpp:141-147
+
+static bool save_plane( const char* path, const void* data, int w, int h, int bytes_per_px )
+{
+    // 1 byte/px -> PGM/PNG grey; 4 byte labels -> RGBA PNG of the raw int32 (lossless)
+    Image out;
+    out.createImage( w, h, IPL_DEPTH_8U, bytes_per_px == 1 ? 1 : 4 );
+    for( int y = 0; y < h; y++ ) // stored top scanline first
+        memcpy( out.getImageData() + ( size_t )y * out.getWidthStep(), ( const char* )data + ( size_t )( h - 1 - y ) * w * bytes_per_px, ( size_t )w * bytes_per_px );
+    out.saveImage( path );
+    return out.error().empty();
+}
+
+int main( int argc, char** argv )
+{
+    if( argc < 2 )
+    {
+        fprintf( stderr, "usage: %s <input image> [-o out.png] [-s scale] [--no-subdivide] [--graph g.pgm] [--labels l.png] [--strips N] [--device D] [--convert-only]\n", argv[ 0 ] );
+        return 2;
+    }
+    std::string out_path = "remastered.png", graph_path, labels_path;
+    int scale = 4, strips = 0, device = 0;
+    bool subdivide = true, convert_only = false;
+    for( int k = 2; k < argc; k++ )
+    {
+        std::string a = argv[ k ];
+        if( a == "-o" && k + 1 < argc ) out_path = argv[ ++k ];
+        else if( a == "-s" && k + 1 < argc ) scale = atoi( argv[ ++k ] );
+        else if( a == "--no-subdivide" ) subdivide = false;
+        else if( a == "--graph" && k + 1 < argc ) graph_path = argv[ ++k ];
+        else if( a == "--labels" && k + 1 < argc ) labels_path = argv[ ++k ];
+        else if( a == "--strips" && k + 1 < argc ) strips = atoi( argv[ ++k ] );
+        else if( a == "--device" && k + 1 < argc ) device = atoi( argv[ ++k ] );
+        else if( a == "--convert-only" ) convert_only = true;
+        else { fprintf( stderr, "remaster_cli: unknown option %s\n", a.c_str() ); return 2; }
+    }
+    if( !load_image( argv[ 1 ] ) ) return 1;
+    allocate_graph();
+    if( convert_only ) // image I/O round trip only (no GPU): load -> flip -> flip back -> save
+    {
+        img->reverses();
+        img->saveImage( out_path.c_str() );
+        if( !img->error().empty() ) { fprintf( stderr, "remaster_cli: %s\n", img->error().c_str() ); return 1; }
+        return 0;
+    }
+    const size_t N = ( size_t )img_width * img_height;
+    std::vector< uint8_t > rgba( N * scale * scale * 4 );
+    std::vector< int32_t > labels( labels_path.empty() ? 0 : N );
+    par_job job;
+    memset( &job, 0, sizeof( job ) );
+    job.bgr = reinterpret_cast< const uint8_t* >( img_data );
+    job.width = img_width;
+    job.height = img_height;
+    job.widthstep = img_widthstep;
+    job.n_frames = 1;
+    job.scale = scale;
+    job.flags = ( subdivide ? PAR_FLAG_SUBDIVIDE : 0u ) | PAR_FLAG_FLIP_OUTPUT; // output rows top scanline first
+    job.rgba = rgba.data();
+    job.graph = reinterpret_cast< uint8_t* >( graph );
+    job.labels = labels.empty() ? nullptr : labels.data();
+    if( strips > 0 )
+    {
+        int n_dev = 0;
+        std::vector< int > devs( strips );
+        for( int k = 0; k < strips; k++ ) devs[ k ] = device + k; // consecutive devices, wrapped below by the library's own check
+        par_group* grp = nullptr;
+        if( par_group_create( &grp, devs.data(), strips, img_width, img_height, scale ) != PAR_OK )
+        {
+            // fewer devices than strips: put several strips on the devices that exist
+            ( void )n_dev;
+            for( int k = 0; k < strips; k++ ) devs[ k ] = device;
+            if( par_group_create( &grp, devs.data(), strips, img_width, img_height, scale ) != PAR_OK )
+            {
+                fprintf( stderr, "remaster_cli: %s\n", par_group_last_error( nullptr ) );
+                return 1;
+            }
+        }
+        if( par_group_remaster_host( grp, &job ) != PAR_OK )
+        {
+            fprintf( stderr, "remaster_cli: %s\n", par_group_last_error( grp ) );
+            return 1;
+        }
+        par_group_destroy( grp );
+    }
+    else
+    {
+        par_context* ctx = nullptr;
+        if( par_create( &ctx, device, img_width, img_height, 1 ) != PAR_OK )
+        {
+            fprintf( stderr, "remaster_cli: %s\n", par_last_error( nullptr ) );
+            return 1;
+        }
+        if( par_remaster_host( ctx, &job ) != PAR_OK )
+        {
+            fprintf( stderr, "remaster_cli: %s\n", par_last_error( ctx ) );
+            return 1;
+        }
+        par_destroy( ctx );
+    }
+    Image out;
+    out.createImage( img_width * scale, img_height * scale, IPL_DEPTH_8U, 3 );
+    for( int y = 0; y < img_height * scale; y++ )
+    {
+        const uint8_t* s = &rgba[ ( size_t )y * img_width * scale * 4 ];
+        char* o = out.getImageData() + ( size_t )y * out.getWidthStep();
+        for( int x = 0; x < img_width * scale; x++ ) { o[ 3 * x ] = ( char )s[ 4 * x + 2 ]; o[ 3 * x + 1 ] = ( char )s[ 4 * x + 1 ]; o[ 3 * x + 2 ] = ( char )s[ 4 * x ]; }
+    }
+    out.saveImage( out_path.c_str() );
+    if( !out.error().empty() ) { fprintf( stderr, "remaster_cli: %s\n", out.error().c_str() ); return 1; }
+    if( !graph_path.empty() && !save_plane( graph_path.c_str(), graph, img_width, img_height, 1 ) ) return 1;
+    if( !labels_path.empty() && !save_plane( labels_path.c_str(), labels.data(), img_width, img_height, 4 ) ) return 1;
+    printf( "%s: %dx%d -> %dx%d (scale %d, subdivide %s) -> %s\n", argv[ 1 ], img_width, img_height, img_width * scale, img_height * scale, scale,
+            subdivide ? "on" : "off", out_path.c_str() );
+    free( graph );
+    delete img;
+    return 0;
+}

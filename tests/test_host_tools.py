@@ -1,0 +1,86 @@
+"""Host entry points kept from the reference: class Image (Image.h/.cpp) and the program
+entry point (main.cpp:166-194: argv[1] = image path; load -> vertical flip -> path -> image out)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from pixel_art_remaster_gpu_b200 import synth
+
+cv2 = pytest.importorskip("cv2")
+
+
+@pytest.fixture(scope="module")
+def cli(lib):
+    from pixel_art_remaster_gpu_b200 import build as b
+    path = b.build_cli()
+    assert path and os.path.exists(path)
+    return path
+
+
+def _bgr_top_down(img_bottom_up):
+    return np.ascontiguousarray(img_bottom_up[::-1])
+
+
+@pytest.mark.parametrize("ext", ["png", "ppm", "bmp"])
+def test_image_io_round_trip(cli, tmp_path, ext):
+    """Image::loadImage -> reverses -> reverses -> saveImage keeps every pixel (odd width: padded rows)."""
+    img = _bgr_top_down(synth.snes_frame(37, 21, 3))
+    src = str(tmp_path / ("in." + ext))
+    assert cv2.imwrite(src, img)
+    for out_ext in ("png", "ppm"):
+        dst = str(tmp_path / ("out." + out_ext))
+        subprocess.run([cli, src, "-o", dst, "--convert-only"], check=True, timeout=60)
+        assert np.array_equal(cv2.imread(dst, cv2.IMREAD_COLOR), img)
+
+
+def test_palette_and_alpha_png_are_read_as_bgr(cli, tmp_path):
+    import zlib, struct
+    # 4-colour palette PNG, 2 bits per pixel, written by hand (cv2 cannot write palette PNGs)
+    w, h = 5, 3
+    pal = bytes([255, 0, 0, 0, 255, 0, 0, 0, 255, 10, 20, 30])
+    idx = (np.arange(w * h).reshape(h, w) % 4).astype(np.uint8)
+    raw = b""
+    for y in range(h):
+        bits = 0
+        for x in range(w):
+            bits = (bits << 2) | int(idx[y, x])
+        bits <<= 2 * (8 - w)  # pad to 2 bytes
+        raw += b"\x00" + struct.pack(">H", bits)
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 2, 3, 0, 0, 0)) + chunk(b"PLTE", pal) + \
+        chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+    src = str(tmp_path / "pal.png")
+    open(src, "wb").write(png)
+    dst = str(tmp_path / "pal_out.png")
+    subprocess.run([cli, src, "-o", dst, "--convert-only"], check=True, timeout=60)
+    want = np.frombuffer(pal, np.uint8).reshape(4, 3)[idx][..., ::-1]
+    assert np.array_equal(cv2.imread(dst, cv2.IMREAD_COLOR), want)
+
+
+def test_missing_file_fails_loudly(cli, tmp_path):
+    r = subprocess.run([cli, str(tmp_path / "nope.png")], capture_output=True, text=True)
+    assert r.returncode != 0 and "cannot read" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("strips", [0, 2])
+def test_cli_image_in_image_out(cli, oracle, tmp_path, strips):
+    """remaster_cli in.png -o out.png: equals the oracle's raster of the flipped frame, flipped back."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    frame = synth.snes_frame(96, 120, 17)                  # pipeline orientation (row 0 = bottom)
+    src = str(tmp_path / "in.png")
+    cv2.imwrite(src, _bgr_top_down(frame))
+    dst, gpath = str(tmp_path / "out.png"), str(tmp_path / "graph.png")
+    cmd = [cli, src, "-o", dst, "-s", "4", "--graph", gpath] + (["--strips", str(strips)] if strips else [])
+    subprocess.run(cmd, check=True, timeout=300)
+    # the CLI pads rows to 4 bytes like IplImage; 96*3 is already aligned, so the oracle sees the same bytes
+    want = oracle.pipeline(frame, scale=4, want=("graph", "raster"))
+    got = cv2.imread(dst, cv2.IMREAD_COLOR)
+    assert np.array_equal(got, want["raster"][::-1, :, 2::-1])   # RGBA bottom-up -> BGR top-down
+    assert np.array_equal(cv2.imread(gpath, cv2.IMREAD_GRAYSCALE), want["graph"][::-1])
