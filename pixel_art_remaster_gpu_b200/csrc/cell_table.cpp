@@ -117,7 +117,9 @@ void build_cell_tables( CellTables* t )
         for( size_t v = h.size(); v-- > 0; ) // descending, so that the FIRST vertex at a point wins (they are distinct anyway)
         {
             verts |= ( uint64_t )( ( unsigned )( h[ v ].first + 1 ) | ( unsigned )( h[ v ].second + 1 ) << 4 ) << ( 8 * v );
-            info |= ( uint64_t )classify( h[ v ], h[ ( v + 1 ) % h.size() ], key & 0xFFu ) << ( 4 * v );
+            const unsigned link = classify( h[ v ], h[ ( v + 1 ) % h.size() ], key & 0xFFu );
+            info |= ( uint64_t )link << ( 4 * v );
+            if( link == 15 ) info |= 1ull << ( 36 + v );
             const int code = point_code( h[ v ].first, h[ v ].second );
             if( code >= 0 ) index = ( index & ~( 15ull << ( 4 * code ) ) ) | ( uint64_t )v << ( 4 * code );
         }

@@ -47,99 +47,123 @@ PAR_HD Q2 hull_vertex( uint64_t verts, int t )
     return q;
 }
 
-// points 1/4 (1/8 when the edge is longer than one pixel) from either end of edge a->b, in 1/64 px
-// (getQ_i / getR_i, subdivision_functions.cu:42-122; "lenght <= 1.0" <=> dx^2+dy^2 <= 16 quarter^2):
-// Q = a + w*(b-a), R = b - w*(b-a) with w = 1/4 or 1/8; in 1/64 px a quarter unit is 16.
-PAR_HD void cut_points( Q2 a, Q2 b, int& qx, int& qy, int& rx, int& ry )
+// the point 1/4 (1/8 when the edge is longer than one pixel) of the way from p toward x, in 1/64 px:
+// getQ_i is cut_toward( P_i, P_i+1 ), getR_i is cut_toward( P_i+1, P_i ) (subdivision_functions.cu:42-122;
+// "lenght <= 1.0" <=> dx^2+dy^2 <= 16 in quarter-pixel units; a quarter pixel is 16/64)
+PAR_HD void cut_toward( Q2 p, Q2 x, int& ox, int& oy )
 {
-    const int dx = b.x - a.x, dy = b.y - a.y;
+    const int dx = x.x - p.x, dy = x.y - p.y;
     const int w = dx * dx + dy * dy > 16 ? 2 : 4; // 16 * (1/8) or 16 * (1/4)
-    const int ox = dx * w, oy = dy * w;
-    qx = 16 * a.x + ox;
-    qy = 16 * a.y + oy;
-    rx = 16 * b.x - ox;
-    ry = 16 * b.y - oy;
+    ox = 16 * p.x + dx * w;
+    oy = 16 * p.y + dy * w;
 }
+
+// The polygon of a cell as up to two vertices per hull vertex: slot 2t (always) and slot 2t+1 (when bit t
+// of `two` is set), to be read in slot order.
+struct CellPoly
+{
+    int n;        // hull vertices
+    uint32_t two; // bit t: hull vertex t was replaced by two vertices
+    PAR_HD int count() const
+    {
+#if defined( __CUDA_ARCH__ )
+        return n + __popc( two );
+#else
+        return n + __builtin_popcount( two );
+#endif
+    }
+};
 
 // Env must provide:
 //   uint32_t key( int i, int j )            cell key of an in-image pixel
-//   bool keep_corner( int i, int j, Q2 p )  checkTJunction (subdivision_functions.cu:170-242)
-// Sink must provide:  void vertex( int x64, int y64 )
-// Every hull vertex yields one or two polygon vertices.  The case analysis only computes coordinates;
-// the sink is fed from ONE place so that the threads of a warp stay converged on its code.
-template< class Env, class Sink >
-PAR_HD void emit_cell_polygon( const Env& env, const CellTablePtrs& tab, int i, int j, uint32_t key, bool subdivide, Sink& sink )
+//   bool guard( int i, int j )              checkTJunction's early "keep everything" test (:187)
+//   bool keep_corner( int i, int j, Q2 p )  the rest of checkTJunction (subdivision_functions.cu:170-242)
+// Slots must provide:  void put( int slot, int x64, int y64 )
+//
+// The hull vertices fall into three classes that are a pure function of the key (border mask of the hull
+// edges): both adjacent edges shared -> the vertex stays (:651-655); both border -> corner cut unless it is
+// a T-junction (:583-598); exactly one shared -> blend with the neighbour cell's cut point so that both cells
+// meet on the same curve (:603-647).  Each class is handled in its own loop so that the threads of a warp
+// run the same code together instead of taking turns through a per-vertex switch.
+template< class Env, class Slots >
+PAR_HD CellPoly build_cell_polygon( const Env& env, const CellTablePtrs& tab, int i, int j, uint32_t key, bool subdivide, Slots& slots )
 {
     const uint64_t h = PAR_LDG( tab.verts + key );
     const uint64_t info = PAR_LDG( tab.info + key );
-    const int n = hull_count( info );
-    const bool plain = !subdivide || ( key & 0xFFu ) == 90u; // interior nodes are not smoothed (kernel.cu:231)
-    const uint32_t links = ( uint32_t )info;
-    int prev_link = ( int )( ( links >> ( 4 * ( n - 1 ) ) ) & 15u );
-    Q2 p_prev = hull_vertex( h, n - 1 );
-    Q2 p_cur = hull_vertex( h, 0 );
+    CellPoly poly;
+    poly.n = hull_count( info );
+    poly.two = 0u;
+    const int n = poly.n;
     for( int t = 0; t < n; t++ )
     {
-        const int cur_link = ( int )( ( links >> ( 4 * t ) ) & 15u );
-        const Q2 p_next = hull_vertex( h, t + 1 == n ? 0 : t + 1 );
-        const bool cur_border = cur_link == 15, prev_border = prev_link == 15;
-        int ax = 16 * p_cur.x, ay = 16 * p_cur.y, bx = 0, by = 0;
-        bool two = false;
-        if( !plain && ( cur_border || prev_border ) ) // two shared edges: the vertex stays (:651-655)
-        {
-            int qx, qy, rx, ry, ux, uy;
-            cut_points( p_cur, p_next, qx, qy, ux, uy ); // Q of the current edge
-            cut_points( p_prev, p_cur, ux, uy, rx, ry ); // R of the previous edge
-            if( cur_border && prev_border )
-            {
-                if( !env.keep_corner( i, j, p_cur ) ) // else the corner stays (:583-588)
-                {
-                    ax = rx; ay = ry; // :590-598
-                    bx = qx; by = qy;
-                    two = true;
-                }
-            }
-            else
-            {
-                // exactly one of the two edges is shared with a neighbour cell: blend with that cell's cut
-                // point so that both cells meet on the same curve (:603-647)
-                const int L = cur_border ? prev_link : cur_link;
-                const int di = edge_di( L ), dj = edge_dj( L );
-                const uint32_t nkey = env.key( i + di, j + dj );
-                const uint64_t hn = PAR_LDG( tab.verts + nkey );
-                const int nn = hull_count( PAR_LDG( tab.info + nkey ) );
-                // this vertex in the neighbour's frame -> which of the neighbour's vertices it is
-                // (first match, 0 when absent: getPointIndex :527-538, here one table lookup)
-                const int code = point_code( p_cur.x - 4 * di, p_cur.y - 4 * dj );
-                const int op = code < 0 ? 0 : ( int )( ( PAR_LDG( tab.index + nkey ) >> ( 4 * code ) ) & 15u );
-                int aqx, aqy, arx, ary;
-                two = true;
-                if( cur_border )
-                {
-                    // neighbour's R on the edge that ENDS at the shared vertex (:125-138)
-                    cut_points( hull_vertex( hn, op == 0 ? nn - 1 : op - 1 ), hull_vertex( hn, op ), aqx, aqy, arx, ary );
-                    ax = ( qx + arx + 64 * di ) >> 1;
-                    ay = ( qy + ary + 64 * dj ) >> 1;
-                    bx = qx; by = qy;
-                }
-                else
-                {
-                    // neighbour's Q on the edge that STARTS at the shared vertex (:141-154)
-                    cut_points( hull_vertex( hn, op ), hull_vertex( hn, op + 1 == nn ? 0 : op + 1 ), aqx, aqy, arx, ary );
-                    ax = rx; ay = ry;
-                    bx = ( rx + aqx + 64 * di ) >> 1;
-                    by = ( ry + aqy + 64 * dj ) >> 1;
-                }
-            }
-        }
-#if defined( __CUDA_ARCH__ )
-#pragma unroll 1
-#endif
-        for( int e = 0; e < ( two ? 2 : 1 ); e++ ) sink.vertex( e ? bx : ax, e ? by : ay );
-        prev_link = cur_link;
-        p_prev = p_cur;
-        p_cur = p_next;
+        const Q2 p = hull_vertex( h, t );
+        slots.put( 2 * t, 16 * p.x, 16 * p.y );
     }
+    if( !subdivide || ( key & 0xFFu ) == 90u ) return poly; // interior nodes are not smoothed (kernel.cu:231)
+    const uint32_t links = ( uint32_t )info;
+    const uint32_t cur_b = hull_border_mask( info );                                         // edge t (leaving vertex t) is border
+    const uint32_t prev_b = ( ( cur_b << 1 ) | ( cur_b >> ( n - 1 ) ) ) & ( ( 1u << n ) - 1u ); // edge t-1 (arriving) is border
+    uint32_t blend = cur_b ^ prev_b, cut = cur_b & prev_b;
+    while( blend )
+    {
+#if defined( __CUDA_ARCH__ )
+        const int t = __ffs( ( int )blend ) - 1;
+#else
+        const int t = __builtin_ctz( blend );
+#endif
+        blend &= blend - 1u;
+        const bool cur_border = ( cur_b >> t ) & 1u; // else the arriving edge is the border one
+        const int tp = t == 0 ? n - 1 : t - 1, tn = t + 1 == n ? 0 : t + 1;
+        const Q2 p = hull_vertex( h, t );
+        // own cut point on the BORDER edge: Q of the current edge, or R of the previous one
+        int ownx, owny;
+        cut_toward( p, hull_vertex( h, cur_border ? tn : tp ), ownx, owny );
+        // the neighbour across the SHARED edge
+        const int L = ( int )( ( links >> ( 4 * ( cur_border ? tp : t ) ) ) & 15u );
+        const int di = edge_di( L ), dj = edge_dj( L );
+        const uint32_t nkey = env.key( i + di, j + dj );
+        const uint64_t hn = PAR_LDG( tab.verts + nkey );
+        const int nn = hull_count( PAR_LDG( tab.info + nkey ) );
+        // this vertex in the neighbour's frame -> which of the neighbour's vertices it is
+        // (first match, 0 when absent: getPointIndex :527-538, here one table lookup)
+        const int code = point_code( p.x - 4 * di, p.y - 4 * dj );
+        const int op = code < 0 ? 0 : ( int )( ( PAR_LDG( tab.index + nkey ) >> ( 4 * code ) ) & 15u );
+        // neighbour's R on the edge that ENDS at that vertex (:125-138) / its Q on the edge that STARTS there (:141-154)
+        const int other = cur_border ? ( op == 0 ? nn - 1 : op - 1 ) : ( op + 1 == nn ? 0 : op + 1 );
+        int nbx, nby;
+        cut_toward( hull_vertex( hn, op ), hull_vertex( hn, other ), nbx, nby );
+        const int mx = ( ownx + nbx + 64 * di ) >> 1, my = ( owny + nby + 64 * dj ) >> 1; // midPoint (:554); sums are even
+        if( cur_border )
+        {
+            slots.put( 2 * t, mx, my );
+            slots.put( 2 * t + 1, ownx, owny );
+        }
+        else
+        {
+            slots.put( 2 * t, ownx, owny );
+            slots.put( 2 * t + 1, mx, my );
+        }
+        poly.two |= 1u << t;
+    }
+    if( cut && !env.guard( i, j ) )
+        while( cut )
+        {
+#if defined( __CUDA_ARCH__ )
+            const int t = __ffs( ( int )cut ) - 1;
+#else
+            const int t = __builtin_ctz( cut );
+#endif
+            cut &= cut - 1u;
+            const Q2 p = hull_vertex( h, t );
+            if( env.keep_corner( i, j, p ) ) continue; // T-junction: the corner stays (:583-588)
+            int rx, ry, qx, qy;
+            cut_toward( p, hull_vertex( h, t == 0 ? n - 1 : t - 1 ), rx, ry ); // R of the previous edge
+            cut_toward( p, hull_vertex( h, t + 1 == n ? 0 : t + 1 ), qx, qy ); // Q of the current edge
+            slots.put( 2 * t, rx, ry );
+            slots.put( 2 * t + 1, qx, qy );
+            poly.two |= 1u << t;
+        }
+    return poly;
 }
 
 // checkTJunction (subdivision_functions.cu:170-242) on the frame as the flat byte array the
@@ -161,9 +185,9 @@ struct FlatImage
         long idx = ( long )j * widthstep + 3L * i;
         return idx - widthstep - 1 < 0 || idx + width + 1 > ( long )height * widthstep - 1; // :187, "width" as written
     }
+    // the corner tests of checkTJunction, for a cell that passed guard()
     PAR_HD bool keep_corner( int i, int j, Q2 p ) const
     {
-        if( guard( i, j ) ) return true;
         const bool x0 = p.x == 0, x1 = p.x == 4, y0 = p.y == 0, y1 = p.y == 4;
         if( !( ( x0 || x1 ) && ( y0 || y1 ) ) ) return false;
         const long idx = ( long )j * widthstep + 3L * i;

@@ -126,41 +126,44 @@ struct RowToggle // rows in memory (shared memory on the fast path), row r at ro
     __device__ __forceinline__ void operator()( int r, int cnt ) { rows[ r * stride ] ^= ( 1u << cnt ) - 1u; }
 };
 
-// Sink of emit_cell_polygon: vertices go to a small buffer (element k at buf[k * stride]), packed as
-// (x64 + 64) << 8 | (y64 + 64); tracks the coordinate range for the reach check.
-struct VertexBufSink
+// Slots of build_cell_polygon in a small buffer (slot k at buf[k * stride]), packed as (x64 + 64) << 8 | (y64 + 64)
+struct PackedSlots
 {
     uint16_t* buf;
-    int stride, n, lo, hi;
-    __device__ __forceinline__ VertexBufSink( uint16_t* b, int s ) : buf( b ), stride( s ), n( 0 ), lo( 0 ), hi( 0 ) {}
-    __device__ __forceinline__ void vertex( int x64, int y64 )
-    {
-        buf[ n * stride ] = ( uint16_t )( ( ( x64 + 64 ) << 8 ) | ( y64 + 64 ) );
-        n++;
-        lo = min( lo, min( x64, y64 ) );
-        hi = max( hi, max( x64, y64 ) );
-    }
+    int stride;
+    __device__ __forceinline__ void put( int slot, int x64, int y64 ) { buf[ slot * stride ] = ( uint16_t )( ( ( x64 + 64 ) << 8 ) | ( y64 + 64 ) ); }
 };
 
-// coverage of the buffered polygon over an N x N sample window whose sample (0,0) sits at (ox, oy)
+// Coverage of the polygon held in `slots` over an N x N sample window whose sample (0,0) sits at (ox, oy).
+// Returns the polygon's coordinate range through lo/hi (vertex units, i.e. already multiplied by VM).
 template< int S, int N, class Toggle >
-__device__ __forceinline__ void cover_polygon( const uint16_t* buf, int stride, int n, int ox, int oy, Toggle& toggle )
+__device__ __forceinline__ void cover_polygon( const uint16_t* buf, int stride, CellPoly poly, int ox, int oy, Toggle& toggle, int& lo, int& hi )
 {
     constexpr int VM = Cfg< S >::VM;
     uint32_t v = buf[ 0 ];
     int x0 = ( ( int )( v >> 8 ) - 64 ) * VM, y0 = ( ( int )( v & 255u ) - 64 ) * VM;
     const int fx = x0, fy = y0;
+    lo = min( x0, y0 );
+    hi = max( x0, y0 );
+    const int last = 2 * poly.n - 1 - ( int )( ( ~poly.two >> ( poly.n - 1 ) ) & 1u ); // last occupied slot
+    int slot = 0;
 #pragma unroll 1
-    for( int k = 1; k <= n; k++ )
+    while( true )
     {
+        // next occupied slot: 2t+1 follows 2t only when hull vertex t was split
+        const bool done = slot == last;
+        slot = ( ( slot & 1 ) || !( ( poly.two >> ( slot >> 1 ) ) & 1u ) ) ? ( slot | 1 ) + 1 : slot + 1;
         int x1 = fx, y1 = fy;
-        if( k < n )
+        if( !done )
         {
-            v = buf[ k * stride ];
+            v = buf[ slot * stride ];
             x1 = ( ( int )( v >> 8 ) - 64 ) * VM;
             y1 = ( ( int )( v & 255u ) - 64 ) * VM;
+            lo = min( lo, min( x1, y1 ) );
+            hi = max( hi, max( x1, y1 ) );
         }
         cover_edge< S, N >( ox, oy, x0, y0, x1, y1, toggle );
+        if( done ) break;
         x0 = x1;
         y0 = y1;
     }
@@ -177,10 +180,10 @@ struct TileEnv
     // checkTJunction (subdivision_functions.cu:170-242).  Away from the first/last column the flat byte
     // offsets the reference uses (idx +- widthstep +- 3) are exactly the 2-D neighbours, which are staged
     // in shared memory; at i = 0 / W-1 they wrap to the adjacent rows, so those cells take the flat path.
+    __device__ __forceinline__ bool guard( int i, int j ) const { return img.guard( i, j ); }
     __device__ __forceinline__ bool keep_corner( int i, int j, Q2 p ) const
     {
         if( i < 1 || i > img.width - 2 ) return img.keep_corner( i, j, p );
-        if( img.guard( i, j ) ) return true;
         const bool px0 = p.x == 0, px1 = p.x == 4, py0 = p.y == 0, py1 = p.y == 4;
         if( !( ( px0 || px1 ) && ( py0 || py1 ) ) ) return false;
         const int sx = px1 ? 1 : -1, sy = py1 ? 1 : -1; // the corner's quadrant
@@ -198,17 +201,19 @@ __device__ __noinline__ void window_coverage( const TileEnv< S >& env, const Cel
 {
     typedef Cfg< S > C;
     uint16_t verts[ kMaxVerts ];
-    VertexBufSink sink( verts, 1 );
-    emit_cell_polygon( env, tab, ci, cj, env.key( ci, cj ), subdivide, sink );
+    PackedSlots slots{ verts, 1 };
+    const CellPoly poly = build_cell_polygon( env, tab, ci, cj, env.key( ci, cj ), subdivide, slots );
     for( int r = 0; r < S; r++ ) win[ r ] = 0u;
     RowToggle tg{ win, 1 };
-    cover_polygon< S, S >( verts, 1, sink.n, C::SSP / 2 - di * C::SQUARE, C::SSP / 2 - dj * C::SQUARE, tg );
+    int lo, hi;
+    cover_polygon< S, S >( verts, 1, poly, C::SSP / 2 - di * C::SQUARE, C::SSP / 2 - dj * C::SQUARE, tg, lo, hi );
 }
 
 // mask of a cell whose polygon is its plain hull, for every key: the per-scale table the raster kernel copies from
 struct NoEnv
 {
     __device__ __forceinline__ uint32_t key( int, int ) const { return 0u; }
+    __device__ __forceinline__ bool guard( int, int ) const { return true; }
     __device__ __forceinline__ bool keep_corner( int, int, Q2 ) const { return true; }
 };
 
@@ -219,13 +224,14 @@ __global__ void build_mask_lut_kernel( CellTablePtrs tab, uint32_t* lut )
     const int key = blockIdx.x * blockDim.x + threadIdx.x;
     if( key >= kCellKeys ) return;
     uint16_t verts[ kMaxVerts ];
-    VertexBufSink sink( verts, 1 );
+    PackedSlots slots{ verts, 1 };
     NoEnv env;
-    emit_cell_polygon( env, tab, 0, 0, ( uint32_t )key, false, sink );
+    const CellPoly poly = build_cell_polygon( env, tab, 0, 0, ( uint32_t )key, false, slots );
+    int lo, hi;
     if( C::PACK )
     {
         PackedToggle< C::R > tg{ 0ull };
-        cover_polygon< S, C::R >( verts, 1, sink.n, C::S_FIRST, C::S_FIRST, tg );
+        cover_polygon< S, C::R >( verts, 1, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
         lut[ 2 * key ] = ( uint32_t )tg.m;
         lut[ 2 * key + 1 ] = ( uint32_t )( tg.m >> 32 );
     }
@@ -234,7 +240,7 @@ __global__ void build_mask_lut_kernel( CellTablePtrs tab, uint32_t* lut )
         uint32_t rows[ C::R ];
         for( int r = 0; r < C::R; r++ ) rows[ r ] = 0u;
         RowToggle tg{ rows, 1 };
-        cover_polygon< S, C::R >( verts, 1, sink.n, C::S_FIRST, C::S_FIRST, tg );
+        cover_polygon< S, C::R >( verts, 1, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
         for( int r = 0; r < C::R; r++ ) lut[ C::R * key + r ] = rows[ r ];
     }
 }
@@ -364,22 +370,24 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
             const int idx = s_work[ w ];
             int cy = idx / C::CW, cx = idx - cy * C::CW;
             int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
-            VertexBufSink sink( vbuf, kThreads );
-            emit_cell_polygon( env, tab, gx, gy, s_keys[ ( cy + 1 ) * C::KW + cx + 1 ], true, sink );
-            // reach check: every sample outside the mask must be strictly outside the polygon's bounding box
-            const uint32_t wide = ( sink.lo * C::VM <= -C::REACH || sink.hi * C::VM >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
+            PackedSlots slots{ vbuf, kThreads };
+            const CellPoly poly = build_cell_polygon( env, tab, gx, gy, s_keys[ ( cy + 1 ) * C::KW + cx + 1 ], true, slots );
+            int lo, hi;
             if( C::PACK )
             {
                 PackedToggle< C::R > tg{ 0ull };
-                cover_polygon< S, C::R >( vbuf, kThreads, sink.n, C::S_FIRST, C::S_FIRST, tg );
+                cover_polygon< S, C::R >( vbuf, kThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
+                // reach check: every sample outside the mask must be strictly outside the polygon's bounding box
+                const uint32_t wide = ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
                 reinterpret_cast< uint2* >( s_mask )[ idx ] = make_uint2( ( uint32_t )tg.m, ( uint32_t )( tg.m >> 32 ) | wide );
             }
             else
             {
 #pragma unroll
-                for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] = r == 0 ? wide : 0u;
+                for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] = 0u;
                 RowToggle tg{ s_mask + idx, C::NC };
-                cover_polygon< S, C::R >( vbuf, kThreads, sink.n, C::S_FIRST, C::S_FIRST, tg );
+                cover_polygon< S, C::R >( vbuf, kThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
+                s_mask[ idx ] |= ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
             }
         }
     }
@@ -507,18 +515,17 @@ struct GlobalEnv
         return ( i >= 0 && j >= 0 && i < width && j < height ) ? __ldg( graph + ( size_t )j * width + i ) : 0u;
     }
     __device__ __forceinline__ uint32_t key( int i, int j ) const { return cell_key( node( i, j ), node( i - 1, j ), node( i + 1, j ) ); }
+    __device__ __forceinline__ bool guard( int i, int j ) const { return img.guard( i, j ); }
     __device__ __forceinline__ bool keep_corner( int i, int j, Q2 p ) const { return img.keep_corner( i, j, p ); }
 };
 
-struct VertexSink
+struct LocalSlots
 {
-    float* out;
-    int n;
-    __device__ __forceinline__ void vertex( int x64, int y64 )
+    int16_t x[ kMaxVerts ], y[ kMaxVerts ];
+    __device__ __forceinline__ void put( int slot, int x64, int y64 )
     {
-        out[ 2 * n ] = ( float )x64 * 0.015625f;
-        out[ 2 * n + 1 ] = ( float )y64 * 0.015625f;
-        n++;
+        x[ slot ] = ( int16_t )x64;
+        y[ slot ] = ( int16_t )y64;
     }
 };
 
@@ -536,16 +543,22 @@ __global__ void __launch_bounds__( kThreads ) polygon_kernel( RasterArgs a )
     env.img.height = a.height;
     env.img.widthstep = a.widthstep;
     const size_t n = ( size_t )f * frame_px + ( size_t )j * a.width + i;
-    VertexSink sink;
-    sink.out = a.polygons + n * 2 * 45;
-    sink.n = 0;
-    emit_cell_polygon( env, a.tables, i, j, env.key( i, j ), a.subdivide != 0, sink );
-    for( int t = sink.n; t < 45; t++ ) // unused slots are zeroed (they are undefined in the reference)
+    LocalSlots slots;
+    const CellPoly poly = build_cell_polygon( env, a.tables, i, j, env.key( i, j ), a.subdivide != 0, slots );
+    float* out = a.polygons + n * 2 * 45;
+    int m = 0;
+    for( int t = 0; t < poly.n; t++ )
+        for( int e = 0; e <= ( int )( ( poly.two >> t ) & 1u ); e++, m++ )
+        {
+            out[ 2 * m ] = ( float )slots.x[ 2 * t + e ] * 0.015625f;
+            out[ 2 * m + 1 ] = ( float )slots.y[ 2 * t + e ] * 0.015625f;
+        }
+    for( int t = m; t < 45; t++ ) // unused slots are zeroed (they are undefined in the reference)
     {
-        sink.out[ 2 * t ] = 0.0f;
-        sink.out[ 2 * t + 1 ] = 0.0f;
+        out[ 2 * t ] = 0.0f;
+        out[ 2 * t + 1 ] = 0.0f;
     }
-    if( a.poly_count ) a.poly_count[ n ] = sink.n;
+    if( a.poly_count ) a.poly_count[ n ] = m;
 }
 
 template< int S >

@@ -97,6 +97,7 @@ void par_group_destroy( par_group* g )
     if( !g ) return;
     for( auto& s : g->strips )
     {
+        if( !s.ctx ) continue; // never created (par_group_create failed part-way): nothing on that device
         cudaSetDevice( s.device );
         if( s.stream ) cudaStreamSynchronize( s.stream );
         cudaFree( s.d_in );

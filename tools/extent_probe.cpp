@@ -8,8 +8,8 @@
 using namespace par;
 static CellTables T;
 // neighbour key may depend on the link direction asked for: we enumerate per (key, L) separately
-struct Env { uint32_t nb; int wantL; mutable bool used; uint32_t key(int i, int j) const { used = true; return nb; } bool keep_corner(int, int, Q2) const { return false; } };
-struct Sink { int lo, hi; void vertex(int x, int y) { if (x < lo) lo = x; if (y < lo) lo = y; if (x > hi) hi = x; if (y > hi) hi = y; } };
+struct Env { uint32_t nb; int wantL; mutable bool used; uint32_t key(int i, int j) const { used = true; return nb; } bool guard(int, int) const { return false; } bool keep_corner(int, int, Q2) const { return false; } };
+struct Sink { int lo, hi; void put(int, int x, int y) { if (x < lo) lo = x; if (y < lo) lo = y; if (x > hi) hi = x; if (y > hi) hi = y; } };
 int main()
 {
     build_cell_tables(&T);
@@ -24,7 +24,7 @@ int main()
                 for (uint32_t nb = 0; nb < 4096; nb++) {
                     if (level >= 1 && !((nb >> (7 - L)) & 1u)) continue; // neighbour must hold the reciprocal link
                     Env e{nb, L, false}; Sink s{0, 64};
-                    emit_cell_polygon(e, CellTablePtrs{T.verts, T.info, T.index}, 1, 1, key, true, s);
+                    build_cell_polygon(e, CellTablePtrs{T.verts, T.info, T.index}, 1, 1, key, true, s);
                     if (s.lo < lo) { lo = s.lo; klo = key; nlo = nb; }
                     if (s.hi > hi) { hi = s.hi; khi = key; nhi = nb; }
                 }
