@@ -58,33 +58,93 @@ PAR_HD void cut_toward( Q2 p, Q2 x, int& ox, int& oy )
     oy = 16 * p.y + dy * w;
 }
 
+// Env must provide:
+//   uint32_t key( int i, int j )            cell key of an in-image pixel
+//   bool guard( int i, int j )              checkTJunction's early "keep everything" test (:187)
+//   bool keep_corner( int i, int j, Q2 p )  the rest of checkTJunction (subdivision_functions.cu:170-242)
+//
+// The hull vertices fall into three classes that are a pure function of the key (border mask of the hull
+// edges): both adjacent edges shared -> the vertex stays (:651-655); both border -> corner cut unless it is
+// a T-junction (:583-598); exactly one shared -> blend with the neighbour cell's cut point so that both cells
+// meet on the same curve (:603-647).
+struct VertexClasses
+{
+    uint32_t cur_border; // bit t: the edge leaving vertex t is a border edge
+    uint32_t blend, cut; // bit t: vertex t is of that class
+};
+PAR_HD VertexClasses classify_vertices( uint64_t info )
+{
+    const int n = hull_count( info );
+    VertexClasses c;
+    c.cur_border = hull_border_mask( info );
+    const uint32_t prev_border = ( ( c.cur_border << 1 ) | ( c.cur_border >> ( n - 1 ) ) ) & ( ( 1u << n ) - 1u ); // edge arriving at t
+    c.blend = c.cur_border ^ prev_border;
+    c.cut = c.cur_border & prev_border;
+    return c;
+}
+
+// "blend" vertex t of cell (i,j): the two vertices that replace it, in emission order
+template< class Env >
+PAR_HD void blend_vertex( const Env& env, const CellTablePtrs& tab, int i, int j, uint64_t h, uint64_t info, int t, int& ax, int& ay, int& bx, int& by )
+{
+    const int n = hull_count( info );
+    const bool cur_border = ( hull_border_mask( info ) >> t ) & 1u; // else the arriving edge is the border one
+    const int tp = t == 0 ? n - 1 : t - 1, tn = t + 1 == n ? 0 : t + 1;
+    const Q2 p = hull_vertex( h, t );
+    // own cut point on the BORDER edge: Q of the current edge, or R of the previous one
+    int ownx, owny;
+    cut_toward( p, hull_vertex( h, cur_border ? tn : tp ), ownx, owny );
+    // the neighbour across the SHARED edge
+    const int L = ( int )( ( ( uint32_t )info >> ( 4 * ( cur_border ? tp : t ) ) ) & 15u );
+    const int di = edge_di( L ), dj = edge_dj( L );
+    const uint32_t nkey = env.key( i + di, j + dj );
+    const uint64_t hn = PAR_LDG( tab.verts + nkey );
+    const int nn = hull_count( PAR_LDG( tab.info + nkey ) );
+    // this vertex in the neighbour's frame -> which of the neighbour's vertices it is
+    // (first match, 0 when absent: getPointIndex :527-538, here one table lookup)
+    const int code = point_code( p.x - 4 * di, p.y - 4 * dj );
+    const int op = code < 0 ? 0 : ( int )( ( PAR_LDG( tab.index + nkey ) >> ( 4 * code ) ) & 15u );
+    // neighbour's R on the edge that ENDS at that vertex (:125-138) / its Q on the edge that STARTS there (:141-154)
+    const int other = cur_border ? ( op == 0 ? nn - 1 : op - 1 ) : ( op + 1 == nn ? 0 : op + 1 );
+    int nbx, nby;
+    cut_toward( hull_vertex( hn, op ), hull_vertex( hn, other ), nbx, nby );
+    const int mx = ( ownx + nbx + 64 * di ) >> 1, my = ( owny + nby + 64 * dj ) >> 1; // midPoint (:554); sums are even
+    ax = cur_border ? mx : ownx;
+    ay = cur_border ? my : owny;
+    bx = cur_border ? ownx : mx;
+    by = cur_border ? owny : my;
+}
+
+// "cut" vertex t of a cell that passed guard(): false when the corner stays (T-junction), else R then Q
+template< class Env >
+PAR_HD bool cut_vertex( const Env& env, int i, int j, uint64_t h, int n, int t, int& rx, int& ry, int& qx, int& qy )
+{
+    const Q2 p = hull_vertex( h, t );
+    if( env.keep_corner( i, j, p ) ) return false; // :583-588
+    cut_toward( p, hull_vertex( h, t == 0 ? n - 1 : t - 1 ), rx, ry ); // R of the previous edge
+    cut_toward( p, hull_vertex( h, t + 1 == n ? 0 : t + 1 ), qx, qy ); // Q of the current edge
+    return true;
+}
+
 // The polygon of a cell as up to two vertices per hull vertex: slot 2t (always) and slot 2t+1 (when bit t
 // of `two` is set), to be read in slot order.
 struct CellPoly
 {
     int n;        // hull vertices
     uint32_t two; // bit t: hull vertex t was replaced by two vertices
-    PAR_HD int count() const
-    {
-#if defined( __CUDA_ARCH__ )
-        return n + __popc( two );
-#else
-        return n + __builtin_popcount( two );
-#endif
-    }
 };
 
-// Env must provide:
-//   uint32_t key( int i, int j )            cell key of an in-image pixel
-//   bool guard( int i, int j )              checkTJunction's early "keep everything" test (:187)
-//   bool keep_corner( int i, int j, Q2 p )  the rest of checkTJunction (subdivision_functions.cu:170-242)
-// Slots must provide:  void put( int slot, int x64, int y64 )
-//
-// The hull vertices fall into three classes that are a pure function of the key (border mask of the hull
-// edges): both adjacent edges shared -> the vertex stays (:651-655); both border -> corner cut unless it is
-// a T-junction (:583-598); exactly one shared -> blend with the neighbour cell's cut point so that both cells
-// meet on the same curve (:603-647).  Each class is handled in its own loop so that the threads of a warp
-// run the same code together instead of taking turns through a per-vertex switch.
+PAR_HD int lowest_bit( uint32_t m )
+{
+#if defined( __CUDA_ARCH__ )
+    return __ffs( ( int )m ) - 1;
+#else
+    return __builtin_ctz( m );
+#endif
+}
+
+// Slots must provide:  void put( int slot, int x64, int y64 ).  Each class is handled in its own loop so that
+// the threads of a warp run the same code together instead of taking turns through a per-vertex switch.
 template< class Env, class Slots >
 PAR_HD CellPoly build_cell_polygon( const Env& env, const CellTablePtrs& tab, int i, int j, uint32_t key, bool subdivide, Slots& slots )
 {
@@ -93,72 +153,30 @@ PAR_HD CellPoly build_cell_polygon( const Env& env, const CellTablePtrs& tab, in
     CellPoly poly;
     poly.n = hull_count( info );
     poly.two = 0u;
-    const int n = poly.n;
-    for( int t = 0; t < n; t++ )
+    for( int t = 0; t < poly.n; t++ )
     {
         const Q2 p = hull_vertex( h, t );
         slots.put( 2 * t, 16 * p.x, 16 * p.y );
     }
     if( !subdivide || ( key & 0xFFu ) == 90u ) return poly; // interior nodes are not smoothed (kernel.cu:231)
-    const uint32_t links = ( uint32_t )info;
-    const uint32_t cur_b = hull_border_mask( info );                                         // edge t (leaving vertex t) is border
-    const uint32_t prev_b = ( ( cur_b << 1 ) | ( cur_b >> ( n - 1 ) ) ) & ( ( 1u << n ) - 1u ); // edge t-1 (arriving) is border
-    uint32_t blend = cur_b ^ prev_b, cut = cur_b & prev_b;
-    while( blend )
+    VertexClasses c = classify_vertices( info );
+    while( c.blend )
     {
-#if defined( __CUDA_ARCH__ )
-        const int t = __ffs( ( int )blend ) - 1;
-#else
-        const int t = __builtin_ctz( blend );
-#endif
-        blend &= blend - 1u;
-        const bool cur_border = ( cur_b >> t ) & 1u; // else the arriving edge is the border one
-        const int tp = t == 0 ? n - 1 : t - 1, tn = t + 1 == n ? 0 : t + 1;
-        const Q2 p = hull_vertex( h, t );
-        // own cut point on the BORDER edge: Q of the current edge, or R of the previous one
-        int ownx, owny;
-        cut_toward( p, hull_vertex( h, cur_border ? tn : tp ), ownx, owny );
-        // the neighbour across the SHARED edge
-        const int L = ( int )( ( links >> ( 4 * ( cur_border ? tp : t ) ) ) & 15u );
-        const int di = edge_di( L ), dj = edge_dj( L );
-        const uint32_t nkey = env.key( i + di, j + dj );
-        const uint64_t hn = PAR_LDG( tab.verts + nkey );
-        const int nn = hull_count( PAR_LDG( tab.info + nkey ) );
-        // this vertex in the neighbour's frame -> which of the neighbour's vertices it is
-        // (first match, 0 when absent: getPointIndex :527-538, here one table lookup)
-        const int code = point_code( p.x - 4 * di, p.y - 4 * dj );
-        const int op = code < 0 ? 0 : ( int )( ( PAR_LDG( tab.index + nkey ) >> ( 4 * code ) ) & 15u );
-        // neighbour's R on the edge that ENDS at that vertex (:125-138) / its Q on the edge that STARTS there (:141-154)
-        const int other = cur_border ? ( op == 0 ? nn - 1 : op - 1 ) : ( op + 1 == nn ? 0 : op + 1 );
-        int nbx, nby;
-        cut_toward( hull_vertex( hn, op ), hull_vertex( hn, other ), nbx, nby );
-        const int mx = ( ownx + nbx + 64 * di ) >> 1, my = ( owny + nby + 64 * dj ) >> 1; // midPoint (:554); sums are even
-        if( cur_border )
-        {
-            slots.put( 2 * t, mx, my );
-            slots.put( 2 * t + 1, ownx, owny );
-        }
-        else
-        {
-            slots.put( 2 * t, ownx, owny );
-            slots.put( 2 * t + 1, mx, my );
-        }
+        const int t = lowest_bit( c.blend );
+        c.blend &= c.blend - 1u;
+        int ax, ay, bx, by;
+        blend_vertex( env, tab, i, j, h, info, t, ax, ay, bx, by );
+        slots.put( 2 * t, ax, ay );
+        slots.put( 2 * t + 1, bx, by );
         poly.two |= 1u << t;
     }
-    if( cut && !env.guard( i, j ) )
-        while( cut )
+    if( c.cut && !env.guard( i, j ) )
+        while( c.cut )
         {
-#if defined( __CUDA_ARCH__ )
-            const int t = __ffs( ( int )cut ) - 1;
-#else
-            const int t = __builtin_ctz( cut );
-#endif
-            cut &= cut - 1u;
-            const Q2 p = hull_vertex( h, t );
-            if( env.keep_corner( i, j, p ) ) continue; // T-junction: the corner stays (:583-588)
+            const int t = lowest_bit( c.cut );
+            c.cut &= c.cut - 1u;
             int rx, ry, qx, qy;
-            cut_toward( p, hull_vertex( h, t == 0 ? n - 1 : t - 1 ), rx, ry ); // R of the previous edge
-            cut_toward( p, hull_vertex( h, t + 1 == n ? 0 : t + 1 ), qx, qy ); // Q of the current edge
+            if( !cut_vertex( env, i, j, h, poly.n, t, rx, ry, qx, qy ) ) continue;
             slots.put( 2 * t, rx, ry );
             slots.put( 2 * t + 1, qx, qy );
             poly.two |= 1u << t;
