@@ -40,8 +40,11 @@ E2E_FRAMES = 512
 ALGO_BYTES_PER_PX = 3 + 1 + 4 * SCALE * SCALE   # BGR in + graph out + RGBA out
 RASTER_BYTES_PER_PX = 3 + 1 + 4 * SCALE * SCALE  # raster kernel: colour + final graph in, RGBA out
 METRIC = "remastered frames/s at 256x224->4x"
-WORKLOAD = ("C3: stream of %d synthetic SNES-style 256x224 16-colour BGR8 frames per GPU -> 4x RGBA, "
-            "subdivision on, CC labels off" % FRAMES_PER_GPU)
+
+
+def workload(n_frames=FRAMES_PER_GPU):
+    return ("C3: stream of %d synthetic SNES-style 256x224 16-colour BGR8 frames per GPU -> 4x RGBA, "
+            "subdivision on, CC labels off" % n_frames)
 
 
 def measured_peak_gbs():
@@ -163,7 +166,7 @@ def run_reference(args):
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "impl": "reference",
-            "config": {"workload": WORKLOAD, "width": W, "height": H, "scale": SCALE, "subdivide": True},
+            "config": {"workload": workload(), "width": W, "height": H, "scale": SCALE, "subdivide": True},
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -262,7 +265,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "width": W, "height": H, "scale": SCALE, "subdivide": True, "labels": False,
+            "config": {"workload": workload(n_frames), "width": W, "height": H, "scale": SCALE, "subdivide": True, "labels": False,
                        "frames_per_gpu": n_frames, "l2": "inputs (%.0f MB) and outputs (%.1f GB) per step exceed the 126 MB L2; no flush needed"
                        % (frames.numel() / 1e6, out["rgba"].numel() / 1e9),
                        "algorithmic_bytes_per_frame": ALGO_BYTES_PER_PX * W * H},
@@ -286,6 +289,18 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
                                     "sample": "%d frames (64 distinct, cycled) of the same stream, %d host threads, %.1f s: reference "
                                               "routines A-F as host C++ + oracle triangle raster at 4x" % (n, threads, dt)}
+            # the reference's own CUDA build (kernel.cu unmodified, sm_100a) on this GPU, as it is designed to run:
+            # one launch_kernel call per frame incl. its per-call cudaMalloc/H2D/D2H/cudaFree.  A reported baseline.
+            try:
+                from oracle.oracle import RefCuda
+                if RefCuda.available():
+                    ms_call = RefCuda().time_calls(synth.snes_frame(W, H, synth.BASE_SEED), True, 20)
+                    line["reference_cuda_baseline"] = {"value": 1e3 / ms_call, "unit": "frames/s", "ms_per_call": ms_call,
+                                                       "what": "reference kernel.cu compiled for sm_100a (-use_fast_math), launch_kernel per frame "
+                                                               "end to end as designed (alloc + H2D + 8 kernels + 365 B/px D2H + free); geometry "
+                                                               "output only, no rasterization (the reference rasterizes in OpenGL)"}
+            except Exception as exc:  # a baseline must never break the bench line
+                line["reference_cuda_baseline"] = {"unavailable": str(exc)[:200]}
         print(json.dumps(line))
     barrier()
     ctx.close()
