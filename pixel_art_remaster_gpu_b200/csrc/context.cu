@@ -44,6 +44,9 @@ struct par_context
     uint8_t *scratch_aux = nullptr, *scratch_graph = nullptr; // max_frames * max_w * max_h each
     uint64_t* d_tables = nullptr;          // verts | info | index, kCellKeys words each
     uint32_t* d_mask_lut[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // per scale, built on first use
+    uint64_t* d_memo[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };     // per scale mask memo
+    unsigned long long* d_memo_stats = nullptr; // 3 counters
+    static constexpr uint32_t kMemoEntries = 1u << 17;
     CellTablePtrs tables() const { return CellTablePtrs{ d_tables, d_tables + kCellKeys, d_tables + 2 * kCellKeys }; }
     EncodeTiledFn encode = nullptr;
     uint64_t launches = 0;
@@ -248,6 +251,21 @@ int run_raster( par_context* c, const par_job* j, const uint8_t* graph )
         if( le != cudaSuccess ) return c->cuda_fail( le, "mask table" );
     }
     a.mask_lut = c->d_mask_lut[ j->scale ];
+    a.memo = nullptr;
+    a.memo_cap_mask = 0;
+    a.memo_stats = c->d_memo_stats;
+    if( a.subdivide && !( j->flags & PAR_FLAG_NO_MEMO ) )
+    {
+        if( !c->d_memo[ j->scale ] )
+        {
+            const size_t bytes = ( size_t )par_context::kMemoEntries * memo_entry_words( j->scale ) * sizeof( uint64_t );
+            cudaError_t me = cudaMalloc( &c->d_memo[ j->scale ], bytes );
+            if( me == cudaSuccess ) me = cudaMemsetAsync( c->d_memo[ j->scale ], 0, bytes, c->stream );
+            if( me != cudaSuccess ) return c->cuda_fail( me, "mask memo" );
+        }
+        a.memo = c->d_memo[ j->scale ];
+        a.memo_cap_mask = par_context::kMemoEntries - 1u;
+    }
     CUtensorMap map;
     uint32_t box[ 3 ];
     raster_tma_box( j->scale, box );
@@ -297,6 +315,8 @@ int par_create( par_context** out, int device, int max_width, int max_height, in
     if( e == cudaSuccess ) e = cudaMalloc( &c->scratch_aux, px );
     if( e == cudaSuccess ) e = cudaMalloc( &c->scratch_graph, px );
     if( e == cudaSuccess ) e = cudaMalloc( &c->d_tables, sizeof( CellTables ) );
+    if( e == cudaSuccess ) e = cudaMalloc( &c->d_memo_stats, 3 * sizeof( unsigned long long ) );
+    if( e == cudaSuccess ) e = cudaMemset( c->d_memo_stats, 0, 3 * sizeof( unsigned long long ) );
     if( e == cudaSuccess )
     {
         static CellTables tables;
@@ -329,6 +349,8 @@ void par_destroy( par_context* c )
     cudaFree( c->scratch_graph );
     cudaFree( c->d_tables );
     for( int k = 0; k < 9; k++ ) cudaFree( c->d_mask_lut[ k ] );
+    for( int k = 0; k < 9; k++ ) cudaFree( c->d_memo[ k ] );
+    cudaFree( c->d_memo_stats );
     for( int k = 0; k < 8; k++ ) cudaFree( c->h_stage[ k ] );
     for( auto& sp : c->spans )
     {
@@ -385,6 +407,18 @@ int par_profile_read( par_context* c, double* total_ms, int* launches )
         c->free_events.push_back( sp.b );
     }
     c->spans.clear();
+    return PAR_OK;
+}
+
+int par_memo_stats( par_context* c, uint64_t* out3 )
+{
+    if( !c || !out3 ) return PAR_ERR_INVALID;
+    cudaSetDevice( c->device );
+    cudaError_t e = cudaStreamSynchronize( c->stream );
+    unsigned long long h[ 3 ] = { 0, 0, 0 };
+    if( e == cudaSuccess ) e = cudaMemcpy( h, c->d_memo_stats, sizeof( h ), cudaMemcpyDeviceToHost );
+    if( e != cudaSuccess ) return c->cuda_fail( e, "memo_stats" );
+    for( int k = 0; k < 3; k++ ) out3[ k ] = h[ k ];
     return PAR_OK;
 }
 

@@ -34,6 +34,9 @@ struct RasterArgs
     const uint8_t* graph;       // final graph, dense
     CellTablePtrs tables;       // 4096-entry cell tables (cell_table.h), device pointers
     const uint32_t* mask_lut;   // per-scale coverage masks of the 4096 plain hulls (raster only)
+    uint64_t* memo;             // per-scale mask memo table (raster only), null = off
+    uint32_t memo_cap_mask;     // entries - 1 (power of two)
+    unsigned long long* memo_stats; // [0] smoothed cells looked up, [1] misses, [2] entries inserted
     uint8_t* rgba;              // out (raster), may be null
     float* polygons;            // out (polygon export), may be null
     int32_t* poly_count;        // out (polygon export), may be null
@@ -58,6 +61,7 @@ cudaError_t launch_cc_labels( const LabelArgs& a, cudaStream_t stream, int* n_la
 cudaError_t launch_polygons( const RasterArgs& a, cudaStream_t stream );
 void raster_tma_box( int scale, uint32_t box[ 3 ] );
 size_t mask_lut_words( int scale );
+size_t memo_entry_words( int scale );
 cudaError_t launch_build_mask_lut( int scale, const CellTablePtrs& tab, uint32_t* lut, cudaStream_t stream );
 cudaError_t launch_raster( const RasterArgs& a, const CUtensorMap* graph_map, cudaStream_t stream );
 bool raster_scale_supported( int scale );

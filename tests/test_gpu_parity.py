@@ -176,3 +176,34 @@ def test_exhaustive_yuv_words(ctx, oracle):
         b0, b1, b2 = int(col) & 255, (int(col) >> 8) & 255, int(col) >> 16
         assert par.yuv_word(b0, b1, b2) == oracle.yuv_word(b0, b1, b2, True)
     del torch
+
+
+def test_mask_memo_is_invisible(lib, oracle):
+    """The mask memo caches a pure function (cell signature -> coverage mask): with it, without it
+    (PAR_FLAG_NO_MEMO), cold and warm, the image is the same and equals the oracle's."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    frames_np = synth.snes_stream(6, 128, 96, first_seed=500)
+    frames = torch.from_numpy(frames_np).cuda()
+    with lib.Remaster(0, 128, 96, 6) as c:
+        cold = c.remaster(frames[:3], scale=4, subdivide=True)["rgba"].cpu().numpy()
+        st1 = c.memo_stats()
+        assert st1["lookups"] > 0 and st1["misses"] > 0 and 0 < st1["inserted"] <= st1["misses"]
+        warm = c.remaster(frames[:3], scale=4, subdivide=True)["rgba"].cpu().numpy()
+        st2 = c.memo_stats()
+        assert st2["misses"] - st1["misses"] < 0.02 * (st2["lookups"] - st1["lookups"])  # second pass: (almost) all hits
+        novel = c.remaster(frames[3:], scale=4, subdivide=True)["rgba"].cpu().numpy()  # unseen frames, warm table
+        st3 = c.memo_stats()
+        assert st3["misses"] - st2["misses"] < 0.5 * (st3["lookups"] - st2["lookups"])
+        c.no_memo = True
+        plain = c.remaster(frames, scale=4, subdivide=True)["rgba"].cpu().numpy()
+        assert c.memo_stats() == st3  # untouched
+    assert np.array_equal(cold, warm) and np.array_equal(cold, plain[:3]) and np.array_equal(novel, plain[3:])
+    for k in range(6):
+        assert np.array_equal(plain[k], oracle.pipeline(frames_np[k], scale=4, want=("raster",))["raster"])
+    with lib.Remaster(0, 128, 96, 6) as c:  # scale 8 uses the row-mask form of the memo
+        a8 = c.remaster(frames[:2], scale=8, subdivide=True)["rgba"].cpu().numpy()
+        b8 = c.remaster(frames[:2], scale=8, subdivide=True)["rgba"].cpu().numpy()
+        assert np.array_equal(a8, b8)
+        assert np.array_equal(a8[0], oracle.pipeline(frames_np[0], scale=8, want=("raster",))["raster"])
