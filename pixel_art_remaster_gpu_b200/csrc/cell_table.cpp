@@ -123,9 +123,26 @@ void build_cell_tables( CellTables* t )
             const int code = point_code( h[ v ].first, h[ v ].second );
             if( code >= 0 ) index = ( index & ~( 15ull << ( 4 * code ) ) ) | ( uint64_t )v << ( 4 * code );
         }
-        t->verts[ key ] = verts;
-        t->info[ key ] = info;
-        t->index[ key ] = index;
+        // blend vertices: the vertex as the neighbour across the shared edge sees it (subdivision_functions.cu:427-474)
+        const int n = ( int )h.size();
+        uint64_t aux = 0;
+        for( int v = 0; v < n; v++ )
+        {
+            const unsigned cur = ( unsigned )( info >> ( 4 * v ) ) & 15u, prev = ( unsigned )( info >> ( 4 * ( ( v + n - 1 ) % n ) ) ) & 15u;
+            unsigned code = 0xFF; // all 16 four-bit codes are real points, so "none" needs a byte
+            if( ( cur == 15 ) != ( prev == 15 ) )
+            {
+                const unsigned L = cur == 15 ? prev : cur; // the shared edge
+                static const int di[ 8 ] = { -1, 0, 1, -1, 1, -1, 0, 1 }, dj[ 8 ] = { 1, 1, 1, 0, 0, -1, -1, -1 };
+                const int c = point_code( h[ v ].first - 4 * di[ L ], h[ v ].second - 4 * dj[ L ] );
+                code = c < 0 ? 0xFFu : ( unsigned )c;
+            }
+            aux |= ( uint64_t )code << ( 8 * v );
+        }
+        t->rec[ key ].verts = verts;
+        t->rec[ key ].info = info;
+        t->rec[ key ].index = index;
+        t->rec[ key ].aux = aux;
     }
 }
 

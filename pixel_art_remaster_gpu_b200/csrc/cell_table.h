@@ -1,7 +1,8 @@
 // Stage D as a table: the cell of a pixel is a pure function of 12 bits (its own graph byte plus the
 // four "corner-cutting" diagonals of its left/right neighbours), so the 4096 hulls, the link
 // classification of their edges and a point->vertex index map are computed once on the host and kept
-// in HBM/L2 (96 KB; the few hundred keys a frame actually uses sit in L1).
+// in HBM/L2 (128 KB as one 32-byte record per key, so that a lookup touches ONE sector; the keys a frame
+// actually uses sit in L1).
 //
 // Replaces createCellFromPattern / convex_hull / sort (diagram_functions.cu:319-535, :238-316,
 // :82-129), isLinkedEdge (subdivision_functions.cu:245-424) and the linear search of getPointIndex
@@ -25,7 +26,7 @@ PAR_TAB_HD unsigned cell_key( unsigned node, unsigned left, unsigned right )
     return ( node & 0xFFu ) | ( ( left >> 2 ) & 1u ) << 8 | ( ( left >> 7 ) & 1u ) << 9 | ( right & 1u ) << 10 | ( ( right >> 5 ) & 1u ) << 11;
 }
 
-// Per key, three 64-bit words:
+// Per key, one 32-byte record of four 64-bit words:
 //   verts : byte t = vertex t of the hull, (4x+1) | (4y+1) << 4, quarter-pixel units, x,y in [-1/4, 5/4];
 //           counter-clockwise from the lexicographically smallest vertex, no closing duplicate
 //   info  : bits [0,32)  4 bits per edge t (vertex t -> t+1 mod n): the graph edge 0..7 the polygon edge
@@ -34,11 +35,15 @@ PAR_TAB_HD unsigned cell_key( unsigned node, unsigned left, unsigned right )
 //           bits [36,44) bit t set when edge t is a border edge
 //   index : 4 bits per point code (see point_code): the index of the hull vertex at that point, 0 when
 //           the hull has no vertex there (what getPointIndex returns for "not found")
+//   aux   : one byte per vertex t: when t is a "blend" vertex (exactly one adjacent edge shared), the point
+//           code of vertex t seen from the neighbour cell across that shared edge; 0xFF = not a hull point
+struct CellRecord
+{
+    uint64_t verts, info, index, aux;
+};
 struct CellTables
 {
-    uint64_t verts[ kCellKeys ];
-    uint64_t info[ kCellKeys ];
-    uint64_t index[ kCellKeys ];
+    CellRecord rec[ kCellKeys ];
 };
 
 void build_cell_tables( CellTables* t );

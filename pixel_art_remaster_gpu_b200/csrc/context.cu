@@ -42,12 +42,12 @@ struct par_context
     int max_w = 0, max_h = 0, max_frames = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     uint8_t *scratch_aux = nullptr, *scratch_graph = nullptr; // max_frames * max_w * max_h each
-    uint64_t* d_tables = nullptr;          // verts | info | index, kCellKeys words each
+    CellRecord* d_tables = nullptr;        // kCellKeys 32-byte records
     uint32_t* d_mask_lut[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // per scale, built on first use
     uint64_t* d_memo[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };     // per scale mask memo
     unsigned long long* d_memo_stats = nullptr; // 3 counters
     static constexpr uint32_t kMemoEntries = 1u << 17;
-    CellTablePtrs tables() const { return CellTablePtrs{ d_tables, d_tables + kCellKeys, d_tables + 2 * kCellKeys }; }
+    CellTablePtrs tables() const { return CellTablePtrs{ d_tables }; }
     EncodeTiledFn encode = nullptr;
     uint64_t launches = 0;
     std::string error;
@@ -322,7 +322,7 @@ int par_create( par_context** out, int device, int max_width, int max_height, in
         static CellTables tables;
         static std::once_flag once;
         std::call_once( once, [] { build_cell_tables( &tables ); } );
-        static_assert( sizeof( CellTables ) == 3 * kCellKeys * sizeof( uint64_t ), "verts | info | index" );
+        static_assert( sizeof( CellTables ) == 32 * kCellKeys, "one 32-byte record per key" );
         e = cudaMemcpy( c->d_tables, &tables, sizeof( tables ), cudaMemcpyHostToDevice );
     }
     if( e != cudaSuccess )
@@ -551,8 +551,8 @@ int par_cell_from_pattern( unsigned key, float* out_xy )
     static CellTables tables;
     static std::once_flag once;
     std::call_once( once, [] { build_cell_tables( &tables ); } );
-    uint64_t h = tables.verts[ key ];
-    int n = hull_count( tables.info[ key ] );
+    uint64_t h = tables.rec[ key ].verts;
+    int n = hull_count( tables.rec[ key ].info );
     for( int t = 0; t <= n; t++ )
     {
         out_xy[ 2 * t ] = 0.25f * ( float )hull_xq( h, t % n );

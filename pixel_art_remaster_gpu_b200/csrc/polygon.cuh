@@ -27,10 +27,23 @@ namespace par {
 
 struct CellTablePtrs
 {
-    const uint64_t* verts;
-    const uint64_t* info;
-    const uint64_t* index;
+    const CellRecord* rec;
 };
+
+// (verts, info) of a key with one 16-byte load; index / aux are the other half of the same 32-byte sector
+PAR_HD void load_hull( const CellTablePtrs& tab, uint32_t key, uint64_t& verts, uint64_t& info )
+{
+#if defined( __CUDA_ARCH__ )
+    const ulonglong2 v = __ldg( reinterpret_cast< const ulonglong2* >( tab.rec + key ) );
+    verts = v.x;
+    info = v.y;
+#else
+    verts = tab.rec[ key ].verts;
+    info = tab.rec[ key ].info;
+#endif
+}
+PAR_HD uint64_t load_index( const CellTablePtrs& tab, uint32_t key ) { return PAR_LDG( &tab.rec[ key ].index ); }
+PAR_HD uint64_t load_aux( const CellTablePtrs& tab, uint32_t key ) { return PAR_LDG( &tab.rec[ key ].aux ); }
 
 // vertex t (0..7) of a packed hull in quarter-pixel units
 struct Q2 { int x, y; };
@@ -85,7 +98,8 @@ PAR_HD VertexClasses classify_vertices( uint64_t info )
 
 // "blend" vertex t of cell (i,j): the two vertices that replace it, in emission order
 template< class Env >
-PAR_HD void blend_vertex( const Env& env, const CellTablePtrs& tab, int i, int j, uint64_t h, uint64_t info, int t, int& ax, int& ay, int& bx, int& by )
+PAR_HD void blend_vertex( const Env& env, const CellTablePtrs& tab, int i, int j, uint64_t h, uint64_t info, uint64_t aux, int t, int& ax, int& ay,
+                          int& bx, int& by )
 {
     const int n = hull_count( info );
     const bool cur_border = ( hull_border_mask( info ) >> t ) & 1u; // else the arriving edge is the border one
@@ -98,12 +112,13 @@ PAR_HD void blend_vertex( const Env& env, const CellTablePtrs& tab, int i, int j
     const int L = ( int )( ( ( uint32_t )info >> ( 4 * ( cur_border ? tp : t ) ) ) & 15u );
     const int di = edge_di( L ), dj = edge_dj( L );
     const uint32_t nkey = env.key( i + di, j + dj );
-    const uint64_t hn = PAR_LDG( tab.verts + nkey );
-    const int nn = hull_count( PAR_LDG( tab.info + nkey ) );
+    uint64_t hn, info_n;
+    load_hull( tab, nkey, hn, info_n );
+    const int nn = hull_count( info_n );
     // this vertex in the neighbour's frame -> which of the neighbour's vertices it is
-    // (first match, 0 when absent: getPointIndex :527-538, here one table lookup)
-    const int code = point_code( p.x - 4 * di, p.y - 4 * dj );
-    const int op = code < 0 ? 0 : ( int )( ( PAR_LDG( tab.index + nkey ) >> ( 4 * code ) ) & 15u );
+    // (first match, 0 when absent: getPointIndex :527-538, here two table lookups)
+    const int code = ( int )( ( aux >> ( 8 * t ) ) & 255u );
+    const int op = code == 255 ? 0 : ( int )( ( load_index( tab, nkey ) >> ( 4 * code ) ) & 15u );
     // neighbour's R on the edge that ENDS at that vertex (:125-138) / its Q on the edge that STARTS there (:141-154)
     const int other = cur_border ? ( op == 0 ? nn - 1 : op - 1 ) : ( op + 1 == nn ? 0 : op + 1 );
     int nbx, nby;
@@ -148,8 +163,8 @@ PAR_HD int lowest_bit( uint32_t m )
 template< class Env, class Slots >
 PAR_HD CellPoly build_cell_polygon( const Env& env, const CellTablePtrs& tab, int i, int j, uint32_t key, bool subdivide, Slots& slots )
 {
-    const uint64_t h = PAR_LDG( tab.verts + key );
-    const uint64_t info = PAR_LDG( tab.info + key );
+    uint64_t h, info;
+    load_hull( tab, key, h, info );
     CellPoly poly;
     poly.n = hull_count( info );
     poly.two = 0u;
@@ -160,12 +175,13 @@ PAR_HD CellPoly build_cell_polygon( const Env& env, const CellTablePtrs& tab, in
     }
     if( !subdivide || ( key & 0xFFu ) == 90u ) return poly; // interior nodes are not smoothed (kernel.cu:231)
     VertexClasses c = classify_vertices( info );
+    const uint64_t aux = c.blend ? load_aux( tab, key ) : 0ull;
     while( c.blend )
     {
         const int t = lowest_bit( c.blend );
         c.blend &= c.blend - 1u;
         int ax, ay, bx, by;
-        blend_vertex( env, tab, i, j, h, info, t, ax, ay, bx, by );
+        blend_vertex( env, tab, i, j, h, info, aux, t, ax, ay, bx, by );
         slots.put( 2 * t, ax, ay );
         slots.put( 2 * t + 1, bx, by );
         poly.two |= 1u << t;

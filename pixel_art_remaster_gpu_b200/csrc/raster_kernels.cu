@@ -287,13 +287,14 @@ __device__ __forceinline__ uint32_t memo_hash( uint64_t w0, uint64_t w1 )
 // table bytes (16 bits).  The neighbour's other 10+ key bits do not matter.  Returns false for the rare
 // cell with more than 6 blended vertices (does not fit 128 bits: never memoised).
 template< class Env >
-__device__ __forceinline__ bool cell_signature( const Env& env, const CellTablePtrs& tab, int i, int j, uint32_t key, uint64_t info, uint64_t& w0,
-                                                uint64_t& w1 )
+__device__ __forceinline__ bool cell_signature( const Env& env, const CellTablePtrs& tab, int i, int j, uint32_t key, uint64_t& w0, uint64_t& w1 )
 {
+    uint64_t h, info;
+    load_hull( tab, key, h, info );
     const int n = hull_count( info );
     VertexClasses cls = classify_vertices( info );
     if( __popc( cls.blend ) > 6 ) return false;
-    const uint64_t h = __ldg( tab.verts + key );
+    const uint64_t aux = cls.blend ? load_aux( tab, key ) : 0ull;
     w0 = key;
     w1 = 0ull;
     int field = 0;
@@ -302,13 +303,12 @@ __device__ __forceinline__ bool cell_signature( const Env& env, const CellTableP
         const int t = __ffs( ( int )m ) - 1;
         const bool cur_border = ( cls.cur_border >> t ) & 1u;
         const int L = ( int )( ( ( uint32_t )info >> ( 4 * ( cur_border ? ( t == 0 ? n - 1 : t - 1 ) : t ) ) ) & 15u ); // the shared edge
-        const int di = edge_di( L ), dj = edge_dj( L );
-        const uint32_t nkey = env.key( i + di, j + dj );
-        const uint64_t hn = __ldg( tab.verts + nkey );
-        const int nn = hull_count( __ldg( tab.info + nkey ) );
-        const Q2 p = hull_vertex( h, t );
-        const int code = point_code( p.x - 4 * di, p.y - 4 * dj );
-        const int op = code < 0 ? 0 : ( int )( ( __ldg( tab.index + nkey ) >> ( 4 * code ) ) & 15u );
+        const uint32_t nkey = env.key( i + edge_di( L ), j + edge_dj( L ) );
+        uint64_t hn, info_n;
+        load_hull( tab, nkey, hn, info_n );
+        const int nn = hull_count( info_n );
+        const int code = ( int )( ( aux >> ( 8 * t ) ) & 255u );
+        const int op = code == 255 ? 0 : ( int )( ( load_index( tab, nkey ) >> ( 4 * code ) ) & 15u );
         const int other = cur_border ? ( op == 0 ? nn - 1 : op - 1 ) : ( op + 1 == nn ? 0 : op + 1 );
         const uint64_t f = ( __byte_perm( ( uint32_t )hn, ( uint32_t )( hn >> 32 ), ( uint32_t )op ) & 0xFFu ) |
                            ( ( __byte_perm( ( uint32_t )hn, ( uint32_t )( hn >> 32 ), ( uint32_t )other ) & 0xFFu ) << 8 );
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
             if( use_memo )
             {
                 uint64_t w0, w1, mw[ Memo< S >::MASK_WORDS ];
-                hit = cell_signature( env, tab, gx, gy, key, __ldg( tab.info + key ), w0, w1 ) &&
+                hit = cell_signature( env, tab, gx, gy, key, w0, w1 ) &&
                       memo_lookup< S >( a.memo, a.memo_cap_mask, w0, w1, mw );
                 if( hit )
                 {
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                     uint64_t w0, w1;
                     const uint32_t key = s_keys[ ( cy + 1 ) * C::KW + cx + 1 ];
                     const uint64_t mw = tg.m | ( ( uint64_t )wide << 32 );
-                    if( cell_signature( env, tab, gx, gy, key, __ldg( tab.info + key ), w0, w1 ) &&
+                    if( cell_signature( env, tab, gx, gy, key, w0, w1 ) &&
                         memo_insert< S >( a.memo, a.memo_cap_mask, w0, w1, &mw ) )
                         atomicAdd( a.memo_stats + 2, 1ull );
                 }
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                 {
                     uint64_t w0, w1, mw[ Memo< S >::MASK_WORDS ];
                     const uint32_t key = s_keys[ ( cy + 1 ) * C::KW + cx + 1 ];
-                    const bool sig_ok = cell_signature( env, tab, gx, gy, key, __ldg( tab.info + key ), w0, w1 );
+                    const bool sig_ok = cell_signature( env, tab, gx, gy, key, w0, w1 );
 #pragma unroll
                     for( int k = 0; k < Memo< S >::MASK_WORDS; k++ ) mw[ k ] = 0ull;
 #pragma unroll

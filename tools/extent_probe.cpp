@@ -17,14 +17,14 @@ int main()
         int lo = 0, hi = 64; uint32_t klo = 0, khi = 0, nlo = 0, nhi = 0;
         for (uint32_t key = 0; key < 4096; key++) {
             // which links does this cell consult?  (every non-border edge id)
-            uint32_t links = (uint32_t)T.info[key]; int n = hull_count(T.info[key]);
+            uint32_t links = (uint32_t)T.rec[key].info; int n = hull_count(T.rec[key].info);
             for (int L = 0; L < 8; L++) {
                 bool has = false; for (int t = 0; t < n; t++) if (((links >> (4 * t)) & 15u) == (uint32_t)L) has = true;
                 if (!has) continue;
                 for (uint32_t nb = 0; nb < 4096; nb++) {
                     if (level >= 1 && !((nb >> (7 - L)) & 1u)) continue; // neighbour must hold the reciprocal link
                     Env e{nb, L, false}; Sink s{0, 64};
-                    build_cell_polygon(e, CellTablePtrs{T.verts, T.info, T.index}, 1, 1, key, true, s);
+                    build_cell_polygon(e, CellTablePtrs{T.rec}, 1, 1, key, true, s);
                     if (s.lo < lo) { lo = s.lo; klo = key; nlo = nb; }
                     if (s.hi > hi) { hi = s.hi; khi = key; nhi = nb; }
                 }
