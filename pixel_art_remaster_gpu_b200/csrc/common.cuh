@@ -10,11 +10,9 @@ namespace par {
 // graph bit e <-> neighbour offset (reference: graph_functions.cu:162-171, calc_index :46-76)
 //   e        0      1      2      3      4      5      6      7
 //   (di,dj) (-1,+1) (0,+1) (+1,+1) (-1,0) (+1,0) (-1,-1) (0,-1) (+1,-1)
-__host__ __device__ __forceinline__ int edge_di( int e )
-{
-    return e == 0 || e == 3 || e == 5 ? -1 : ( e == 1 || e == 6 ? 0 : 1 );
-}
-__host__ __device__ __forceinline__ int edge_dj( int e ) { return e < 3 ? 1 : ( e < 5 ? 0 : -1 ); }
+// (two bits per edge, value + 1, packed: di+1 = 0,1,2,0,2,0,1,2 and dj+1 = 2,2,2,1,1,0,0,0)
+__host__ __device__ __forceinline__ int edge_di( int e ) { return ( int )( ( 0x9224u >> ( 2 * e ) ) & 3u ) - 1; }
+__host__ __device__ __forceinline__ int edge_dj( int e ) { return ( int )( ( 0x016Au >> ( 2 * e ) ) & 3u ) - 1; }
 
 // thresholds on the packed fields (graph_functions.cu:14-19)
 constexpr int kThrY = 0x00050000;

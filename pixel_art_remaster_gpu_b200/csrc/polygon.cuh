@@ -214,10 +214,13 @@ struct FlatImage
         uint32_t b2 = idx + 2 < end ? PAR_LDG( frame + idx + 2 ) : 0u;
         return b0 | b1 << 8 | b2 << 16;
     }
+    // checkTJunction's early exit (:187): with idx = j*widthstep + 3i it returns "keep" when
+    //     idx - widthstep - 1 < 0   ||   idx + width + 1 > height*widthstep - 1      ("width", as written).
+    // For widthstep >= 3*width the first test holds exactly on row 0 and at pixel (0,1); the second can only
+    // hold on the top row, where it reads 3i + width + 2 > widthstep.  Same truth table, 32-bit arithmetic.
     PAR_HD bool guard( int i, int j ) const
     {
-        long idx = ( long )j * widthstep + 3L * i;
-        return idx - widthstep - 1 < 0 || idx + width + 1 > ( long )height * widthstep - 1; // :187, "width" as written
+        return j == 0 || ( j == 1 && i == 0 ) || ( j == height - 1 && 3 * i + width + 2 > widthstep );
     }
     // the corner tests of checkTJunction, for a cell that passed guard()
     PAR_HD bool keep_corner( int i, int j, Q2 p ) const

@@ -258,7 +258,7 @@ template< int S >
 struct Memo
 {
     static constexpr int MASK_WORDS = Cfg< S >::PACK ? 1 : ( Cfg< S >::R * 2 + 7 ) / 8;
-    static constexpr int ENTRY_WORDS = 3 + MASK_WORDS;
+    static constexpr int ENTRY_WORDS = ( 3 + MASK_WORDS + 1 ) / 2 * 2; // even: entries stay 16-byte aligned
     static constexpr int PROBES = 8;
 };
 
@@ -285,12 +285,15 @@ __device__ __forceinline__ uint32_t memo_hash( uint64_t w0, uint64_t w1 )
 // between two border edges; and per blended vertex (ascending t) the TWO neighbour hull vertices its
 // blend reads — the one matched to the shared vertex and the one before/after it — as their packed
 // table bytes (16 bits).  The neighbour's other 10+ key bits do not matter.  Returns false for the rare
-// cell with more than 6 blended vertices (does not fit 128 bits: never memoised).
+// cell with more than 6 blended vertices (does not fit 128 bits: never memoised).  `is_hull` is set when
+// nothing moves at all (no blended vertex and every corner kept): the polygon is the plain hull.
 template< class Env >
-__device__ __forceinline__ bool cell_signature( const Env& env, const CellTablePtrs& tab, int i, int j, uint32_t key, uint64_t& w0, uint64_t& w1 )
+__device__ __forceinline__ bool cell_signature( const Env& env, const CellTablePtrs& tab, int i, int j, uint32_t key, uint64_t& w0, uint64_t& w1,
+                                                bool& is_hull )
 {
     uint64_t h, info;
     load_hull( tab, key, h, info );
+    is_hull = false;
     const int n = hull_count( info );
     VertexClasses cls = classify_vertices( info );
     if( __popc( cls.blend ) > 6 ) return false;
@@ -330,9 +333,13 @@ __device__ __forceinline__ bool cell_signature( const Env& env, const CellTableP
             }
     }
     w0 |= ( uint64_t )kept << 12;
+    is_hull = cls.blend == 0u && kept == cls.cut;
     return true;
 }
 
+// Entries are immutable once their state reads 2 and the writer publishes the state with a release store
+// after the payload, so probes may use ordinary L1-cached loads: a stale line can only show an older state
+// (0 or 1), which is a harmless miss, never a wrong mask.  Hot signatures then hit in L1.
 template< int S >
 __device__ __forceinline__ bool memo_lookup( const uint64_t* table, uint32_t cap_mask, uint64_t w0, uint64_t w1, uint64_t* mask_words )
 {
@@ -342,12 +349,15 @@ __device__ __forceinline__ bool memo_lookup( const uint64_t* table, uint32_t cap
     for( int p = 0; p < M::PROBES; p++ )
     {
         const uint64_t* e = table + ( size_t )( ( h + p ) & cap_mask ) * M::ENTRY_WORDS;
-        const uint32_t state = ld_acquire_u32( reinterpret_cast< const uint32_t* >( e + 2 ) );
+        const ulonglong2 sig = __ldca( reinterpret_cast< const ulonglong2* >( e ) );     // w0, w1
+        const ulonglong2 sm = __ldca( reinterpret_cast< const ulonglong2* >( e + 2 ) );  // state, first mask word
+        const uint32_t state = ( uint32_t )sm.x;
         if( state == 0u ) return false;
-        if( state == 2u && __ldcg( e ) == w0 && __ldcg( e + 1 ) == w1 )
+        if( state == 2u && sig.x == w0 && sig.y == w1 )
         {
+            mask_words[ 0 ] = sm.y;
 #pragma unroll
-            for( int k = 0; k < M::MASK_WORDS; k++ ) mask_words[ k ] = __ldcg( e + 3 + k );
+            for( int k = 1; k < M::MASK_WORDS; k++ ) mask_words[ k ] = __ldca( e + 3 + k );
             return true;
         }
     }
@@ -474,7 +484,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
         int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
         const bool inside = gx >= 0 && gy >= 0 && gx < a.width && gy < a.height;
         const uint32_t key = s_keys[ ( cy + 1 ) * C::KW + cx + 1 ];
-        const bool plain = !subdivide || ( key & 0xFFu ) == 90u;
+        bool plain = !subdivide || ( key & 0xFFu ) == 90u;
         if( inside && !plain )
         {
             // smoothed cell: its mask is a pure function of its signature -> look it up in the memo first
@@ -482,8 +492,8 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
             if( use_memo )
             {
                 uint64_t w0, w1, mw[ Memo< S >::MASK_WORDS ];
-                hit = cell_signature( env, tab, gx, gy, key, w0, w1 ) &&
-                      memo_lookup< S >( a.memo, a.memo_cap_mask, w0, w1, mw );
+                const bool sig_ok = cell_signature( env, tab, gx, gy, key, w0, w1, plain ); // plain: nothing moves, the hull it is
+                hit = !plain && sig_ok && memo_lookup< S >( a.memo, a.memo_cap_mask, w0, w1, mw );
                 if( hit )
                 {
                     if( C::PACK )
@@ -498,25 +508,28 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                         }
                     }
                 }
+                atomicAdd( s_nwork + 1, 1 );
             }
-            if( !hit ) s_work[ atomicAdd( s_nwork, 1 ) ] = ( uint16_t )idx;
-            if( use_memo ) atomicAdd( s_nwork + 1, 1 );
+            if( !hit && !plain ) s_work[ atomicAdd( s_nwork, 1 ) ] = ( uint16_t )idx;
         }
-        else if( C::PACK )
+        if( !inside || plain )
         {
-            uint2 m = make_uint2( 0u, 0u );
-            if( inside )
+            if( C::PACK )
             {
-                m = __ldg( reinterpret_cast< const uint2* >( a.mask_lut ) + key );
-                m.y |= force_wide;
+                uint2 m = make_uint2( 0u, 0u );
+                if( inside )
+                {
+                    m = __ldg( reinterpret_cast< const uint2* >( a.mask_lut ) + key );
+                    m.y |= force_wide;
+                }
+                reinterpret_cast< uint2* >( s_mask )[ idx ] = m;
             }
-            reinterpret_cast< uint2* >( s_mask )[ idx ] = m;
-        }
-        else
-        {
+            else
+            {
 #pragma unroll
-            for( int r = 0; r < C::R; r++ )
-                s_mask[ r * C::NC + idx ] = inside ? ( __ldg( a.mask_lut + key * C::R + r ) | ( r == 0 ? force_wide : 0u ) ) : 0u;
+                for( int r = 0; r < C::R; r++ )
+                    s_mask[ r * C::NC + idx ] = inside ? ( __ldg( a.mask_lut + key * C::R + r ) | ( r == 0 ? force_wide : 0u ) ) : 0u;
+            }
         }
     }
     __syncthreads();
@@ -545,8 +558,8 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                     uint64_t w0, w1;
                     const uint32_t key = s_keys[ ( cy + 1 ) * C::KW + cx + 1 ];
                     const uint64_t mw = tg.m | ( ( uint64_t )wide << 32 );
-                    if( cell_signature( env, tab, gx, gy, key, w0, w1 ) &&
-                        memo_insert< S >( a.memo, a.memo_cap_mask, w0, w1, &mw ) )
+                    bool is_hull;
+                    if( cell_signature( env, tab, gx, gy, key, w0, w1, is_hull ) && memo_insert< S >( a.memo, a.memo_cap_mask, w0, w1, &mw ) )
                         atomicAdd( a.memo_stats + 2, 1ull );
                 }
             }
@@ -562,7 +575,8 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                 {
                     uint64_t w0, w1, mw[ Memo< S >::MASK_WORDS ];
                     const uint32_t key = s_keys[ ( cy + 1 ) * C::KW + cx + 1 ];
-                    const bool sig_ok = cell_signature( env, tab, gx, gy, key, w0, w1 );
+                    bool is_hull;
+                    const bool sig_ok = cell_signature( env, tab, gx, gy, key, w0, w1, is_hull );
 #pragma unroll
                     for( int k = 0; k < Memo< S >::MASK_WORDS; k++ ) mw[ k ] = 0ull;
 #pragma unroll
