@@ -270,8 +270,11 @@ int run_raster( par_context* c, const par_job* j, const uint8_t* graph )
     uint32_t box[ 3 ];
     raster_tma_box( j->scale, box );
     bool tma = graph_map( c, j, graph, box, &map );
+    CUtensorMap img_map;
+    raster_img_tma_box( j->scale, box );
+    tma = tma && c->make_map( &img_map, j->bgr, 3ull * j->width, j->height, j->n_frames, j->widthstep, a.frame_stride, box );
     cudaEvent_t t0 = c->span_begin();
-    cudaError_t e = launch_raster( a, tma ? &map : nullptr, c->stream );
+    cudaError_t e = launch_raster( a, tma ? &map : nullptr, tma ? &img_map : nullptr, c->stream );
     c->span_end( 4, t0 );
     c->launches++;
     return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "raster" );

@@ -63,7 +63,8 @@ void raster_tma_box( int scale, uint32_t box[ 3 ] );
 size_t mask_lut_words( int scale );
 size_t memo_entry_words( int scale );
 cudaError_t launch_build_mask_lut( int scale, const CellTablePtrs& tab, uint32_t* lut, cudaStream_t stream );
-cudaError_t launch_raster( const RasterArgs& a, const CUtensorMap* graph_map, cudaStream_t stream );
+void raster_img_tma_box( int scale, uint32_t box[ 3 ] );
+cudaError_t launch_raster( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream );
 bool raster_scale_supported( int scale );
 
 } // namespace par

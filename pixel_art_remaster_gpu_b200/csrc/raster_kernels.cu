@@ -66,6 +66,8 @@ struct Cfg
     static constexpr int KW = TW + 4, KH = TH + 4;        // cells whose keys and colours are needed (halo 2)
     static constexpr int GOFF = 16;                       // staged rows begin at column x0 - 16 (TMA: 16-byte aligned start)
     static constexpr int GP = ( GOFF + TW + 3 + 15 ) / 16 * 16; // staged row pitch (TMA box row), covers x0-3 .. x0+TW+2
+    static constexpr int RAWP = ( 16 + 3 * ( TW + 2 ) + 15 ) / 16 * 16; // staged BGR row: bytes 3*x0-16 .. (TMA box row)
+    static constexpr int RAWOFF = 16 - 6;                 // byte offset of pixel x0-2 in a staged row
     static constexpr int NC = CW * CH;
     static constexpr uint32_t FULL = ( 1u << S ) - 1u;
     static constexpr uint32_t ROWMASK = ( 1u << R ) - 1u;
@@ -75,9 +77,11 @@ struct Cfg
     static constexpr int off_keys = off_graph + ( KH * GP + 127 ) / 128 * 128;
     static constexpr int off_col = off_keys + ( KW * KH * 2 + 15 ) / 16 * 16;
     static constexpr int off_mask = off_col + KW * KH * 4;
-    static constexpr int off_vbuf = off_mask + NC * MW * 4;
+    static constexpr int off_vbuf = ( off_mask + NC * MW * 4 + 127 ) / 128 * 128;
+    static constexpr int off_raw = off_vbuf;              // the staged BGR rows are dead before the vertex buffers are used
     static constexpr int off_work = off_vbuf + kMaxVerts * kThreads * 2;
     static constexpr int off_bar = ( off_work + NC * 2 + 8 + 15 ) / 16 * 16;
+    static_assert( KH * RAWP <= kMaxVerts * kThreads * 2, "raw colour rows alias the vertex buffers" );
     static constexpr int smem_bytes = off_bar + 16;
 };
 
@@ -390,7 +394,8 @@ __device__ __forceinline__ bool memo_insert( uint64_t* table, uint32_t cap_mask,
 }
 
 template< int S, bool kUseTma >
-__global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_constant__ CUtensorMap graph_map, RasterArgs a )
+__global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_constant__ CUtensorMap graph_map, const __grid_constant__ CUtensorMap img_map,
+                                                           RasterArgs a )
 {
     typedef Cfg< S > C;
     extern __shared__ __align__( 128 ) uint8_t smem[];
@@ -421,8 +426,9 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
         __syncthreads();
         if( tid == 0 )
         {
-            mbar_expect_tx( s_bar, C::KH * C::GP );
+            mbar_expect_tx( s_bar, C::KH * C::GP + C::KH * C::RAWP );
             tma_load_3d( s_graph, &graph_map, s_bar, x0 - C::GOFF, y0 - 2, f );
+            tma_load_3d( smem + C::off_raw, &img_map, s_bar, 3 * x0 - 16, y0 - 2, f ); // BGR bytes of tile + halo 2
         }
     }
     else
@@ -438,20 +444,35 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
     }
     // colours of the tile + halo 2 as RGBA words (kernel.cu:98-101: R = byte 2, G = byte 1, B = byte 0);
     // pixels outside the image hold colour 0 (the reference's reads beyond the last row see zeros)
-    for( int idx = tid; idx < C::KW * C::KH; idx += kThreads )
-    {
-        int cy = idx / C::KW, cx = idx - cy * C::KW;
-        int gx = x0 - 2 + cx, gy = y0 - 2 + cy;
-        uint32_t w = 0xFF000000u;
-        if( gx >= 0 && gy >= 0 && gx < a.width && gy < a.height )
-        {
-            const uint8_t* p = frame + ( size_t )gy * a.widthstep + 3 * gx;
-            w = ( uint32_t )__ldg( p + 2 ) | ( uint32_t )__ldg( p + 1 ) << 8 | ( uint32_t )__ldg( p ) << 16 | 0xFF000000u;
-        }
-        s_col[ idx ] = w;
-    }
     if( kUseTma )
+    {
         mbar_wait( s_bar, 0 );
+        const uint8_t* s_raw = smem + C::off_raw;
+        for( int idx = tid; idx < C::KW * C::KH; idx += kThreads )
+        {
+            int cy = idx / C::KW, cx = idx - cy * C::KW;
+            int gx = x0 - 2 + cx, gy = y0 - 2 + cy;
+            const uint8_t* p = s_raw + cy * C::RAWP + C::RAWOFF + 3 * cx;
+            uint32_t w = ( uint32_t )p[ 2 ] | ( uint32_t )p[ 1 ] << 8 | ( uint32_t )p[ 0 ] << 16 | 0xFF000000u;
+            if( gx < 0 || gy < 0 || gx >= a.width || gy >= a.height ) w = 0xFF000000u; // (row padding bytes are not colours)
+            s_col[ idx ] = w;
+        }
+    }
+    else
+    {
+        for( int idx = tid; idx < C::KW * C::KH; idx += kThreads )
+        {
+            int cy = idx / C::KW, cx = idx - cy * C::KW;
+            int gx = x0 - 2 + cx, gy = y0 - 2 + cy;
+            uint32_t w = 0xFF000000u;
+            if( gx >= 0 && gy >= 0 && gx < a.width && gy < a.height )
+            {
+                const uint8_t* p = frame + ( size_t )gy * a.widthstep + 3 * gx;
+                w = ( uint32_t )__ldg( p + 2 ) | ( uint32_t )__ldg( p + 1 ) << 8 | ( uint32_t )__ldg( p ) << 16 | 0xFF000000u;
+            }
+            s_col[ idx ] = w;
+        }
+    }
     __syncthreads();
 
     // cell keys for tile + halo 2 (left/right neighbour bits, kernel.cu:204-207; zero outside the row)
@@ -766,16 +787,16 @@ __global__ void __launch_bounds__( kThreads ) polygon_kernel( RasterArgs a )
 }
 
 template< int S >
-cudaError_t launch_raster_s( const RasterArgs& a, const CUtensorMap* graph_map, cudaStream_t stream )
+cudaError_t launch_raster_s( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream )
 {
     typedef Cfg< S > C;
     dim3 grid( ( a.width + C::TW - 1 ) / C::TW, ( a.height + C::TH - 1 ) / C::TH, a.n_frames );
     cudaError_t e;
-    if( graph_map )
+    if( graph_map && img_map )
     {
         e = cudaFuncSetAttribute( raster_kernel< S, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes );
         if( e != cudaSuccess ) return e;
-        raster_kernel< S, true ><<< grid, kThreads, C::smem_bytes, stream >>>( *graph_map, a );
+        raster_kernel< S, true ><<< grid, kThreads, C::smem_bytes, stream >>>( *graph_map, *img_map, a );
     }
     else
     {
@@ -783,7 +804,7 @@ cudaError_t launch_raster_s( const RasterArgs& a, const CUtensorMap* graph_map, 
         memset( &dummy, 0, sizeof( dummy ) );
         e = cudaFuncSetAttribute( raster_kernel< S, false >, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes );
         if( e != cudaSuccess ) return e;
-        raster_kernel< S, false ><<< grid, kThreads, C::smem_bytes, stream >>>( dummy, a );
+        raster_kernel< S, false ><<< grid, kThreads, C::smem_bytes, stream >>>( dummy, dummy, a );
     }
     return cudaGetLastError();
 }
@@ -843,9 +864,21 @@ void raster_tma_box( int scale, uint32_t box[ 3 ] )
     box[ 2 ] = 1;
 }
 
-cudaError_t launch_raster( const RasterArgs& a, const CUtensorMap* graph_map, cudaStream_t stream )
+void raster_img_tma_box( int scale, uint32_t box[ 3 ] )
 {
-#define PAR_RASTER( S ) return launch_raster_s< S >( a, graph_map, stream )
+    box[ 0 ] = 0;
+    box[ 1 ] = 16 + 4;
+    box[ 2 ] = 1;
+#define PAR_RAWP( S )                          \
+    box[ 0 ] = ( uint32_t )Cfg< S >::RAWP;     \
+    return
+    PAR_FOR_SCALE( scale, PAR_RAWP )
+#undef PAR_RAWP
+}
+
+cudaError_t launch_raster( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream )
+{
+#define PAR_RASTER( S ) return launch_raster_s< S >( a, graph_map, img_map, stream )
     PAR_FOR_SCALE( a.scale, PAR_RASTER )
 #undef PAR_RASTER
     return cudaErrorInvalidValue;
