@@ -498,59 +498,79 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
     const uint32_t force_wide = a.debug_force_wide ? C::WIDE : 0u;
     const bool use_memo = a.memo != nullptr && !a.debug_force_wide;
 
-    // (2a) cells whose polygon is their plain hull copy the mask from the table; the rest queue up
+    // (2a) cells whose polygon is their plain hull copy the mask from the table; smoothed cells are compacted
+    // into a list so that the next pass runs with full warps
+    uint16_t* s_gen = reinterpret_cast< uint16_t* >( smem + C::off_vbuf ); // (the vertex buffers are not in use yet)
     for( int idx = tid; idx < C::NC; idx += kThreads )
     {
         int cy = idx / C::CW, cx = idx - cy * C::CW;
         int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
         const bool inside = gx >= 0 && gy >= 0 && gx < a.width && gy < a.height;
         const uint32_t key = s_keys[ ( cy + 1 ) * C::KW + cx + 1 ];
-        bool plain = !subdivide || ( key & 0xFFu ) == 90u;
+        const bool plain = !subdivide || ( key & 0xFFu ) == 90u;
         if( inside && !plain )
+            s_gen[ atomicAdd( s_nwork + 1, 1 ) ] = ( uint16_t )idx;
+        else if( C::PACK )
         {
-            // smoothed cell: its mask is a pure function of its signature -> look it up in the memo first
-            bool hit = false;
+            uint2 m = make_uint2( 0u, 0u );
+            if( inside )
+            {
+                m = __ldg( reinterpret_cast< const uint2* >( a.mask_lut ) + key );
+                m.y |= force_wide;
+            }
+            reinterpret_cast< uint2* >( s_mask )[ idx ] = m;
+        }
+        else
+        {
+#pragma unroll
+            for( int r = 0; r < C::R; r++ )
+                s_mask[ r * C::NC + idx ] = inside ? ( __ldg( a.mask_lut + key * C::R + r ) | ( r == 0 ? force_wide : 0u ) ) : 0u;
+        }
+    }
+    __syncthreads();
+    // smoothed cells: the mask is a pure function of the cell's signature -> look it up in the memo first
+    {
+        const int n_gen = s_nwork[ 1 ];
+        for( int w = tid; w < n_gen; w += kThreads )
+        {
+            const int idx = s_gen[ w ];
+            int cy = idx / C::CW, cx = idx - cy * C::CW;
+            int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
+            const uint32_t key = s_keys[ ( cy + 1 ) * C::KW + cx + 1 ];
+            bool hit = false, is_hull = false;
+            uint64_t mw[ Memo< S >::MASK_WORDS ];
             if( use_memo )
             {
-                uint64_t w0, w1, mw[ Memo< S >::MASK_WORDS ];
-                const bool sig_ok = cell_signature( env, tab, gx, gy, key, w0, w1, plain ); // plain: nothing moves, the hull it is
-                hit = !plain && sig_ok && memo_lookup< S >( a.memo, a.memo_cap_mask, w0, w1, mw );
-                if( hit )
+                uint64_t w0, w1;
+                const bool sig_ok = cell_signature( env, tab, gx, gy, key, w0, w1, is_hull ); // is_hull: nothing moves
+                hit = !is_hull && sig_ok && memo_lookup< S >( a.memo, a.memo_cap_mask, w0, w1, mw );
+            }
+            if( is_hull )
+            {
+                if( C::PACK )
+                    reinterpret_cast< uint2* >( s_mask )[ idx ] = __ldg( reinterpret_cast< const uint2* >( a.mask_lut ) + key );
+                else
                 {
-                    if( C::PACK )
-                        reinterpret_cast< uint2* >( s_mask )[ idx ] = make_uint2( ( uint32_t )mw[ 0 ], ( uint32_t )( mw[ 0 ] >> 32 ) );
-                    else
-                    {
 #pragma unroll
-                        for( int r = 0; r < C::R; r++ )
-                        {
-                            const uint32_t row = ( uint32_t )( mw[ r >> 2 ] >> ( 16 * ( r & 3 ) ) ) & 0xFFFFu;
-                            s_mask[ r * C::NC + idx ] = ( row & 0x7FFFu ) | ( ( r == 0 && ( row & 0x8000u ) ) ? C::WIDE : 0u );
-                        }
+                    for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] = __ldg( a.mask_lut + key * C::R + r );
+                }
+            }
+            else if( hit )
+            {
+                if( C::PACK )
+                    reinterpret_cast< uint2* >( s_mask )[ idx ] = make_uint2( ( uint32_t )mw[ 0 ], ( uint32_t )( mw[ 0 ] >> 32 ) );
+                else
+                {
+#pragma unroll
+                    for( int r = 0; r < C::R; r++ )
+                    {
+                        const uint32_t row = ( uint32_t )( mw[ r >> 2 ] >> ( 16 * ( r & 3 ) ) ) & 0xFFFFu;
+                        s_mask[ r * C::NC + idx ] = ( row & 0x7FFFu ) | ( ( r == 0 && ( row & 0x8000u ) ) ? C::WIDE : 0u );
                     }
                 }
-                atomicAdd( s_nwork + 1, 1 );
-            }
-            if( !hit && !plain ) s_work[ atomicAdd( s_nwork, 1 ) ] = ( uint16_t )idx;
-        }
-        if( !inside || plain )
-        {
-            if( C::PACK )
-            {
-                uint2 m = make_uint2( 0u, 0u );
-                if( inside )
-                {
-                    m = __ldg( reinterpret_cast< const uint2* >( a.mask_lut ) + key );
-                    m.y |= force_wide;
-                }
-                reinterpret_cast< uint2* >( s_mask )[ idx ] = m;
             }
             else
-            {
-#pragma unroll
-                for( int r = 0; r < C::R; r++ )
-                    s_mask[ r * C::NC + idx ] = inside ? ( __ldg( a.mask_lut + key * C::R + r ) | ( r == 0 ? force_wide : 0u ) ) : 0u;
-            }
+                s_work[ atomicAdd( s_nwork, 1 ) ] = ( uint16_t )idx;
         }
     }
     __syncthreads();
