@@ -123,6 +123,15 @@ void build_cell_tables( CellTables* t )
             const int code = point_code( h[ v ].first, h[ v ].second );
             if( code >= 0 ) index = ( index & ~( 15ull << ( 4 * code ) ) ) | ( uint64_t )v << ( 4 * code );
         }
+        // which hull vertex sits on each corner of the pixel square (checkTJunction only looks at those, :205-239)
+        static const int corner_x[ 4 ] = { 0, 4, 4, 0 }, corner_y[ 4 ] = { 0, 0, 4, 4 };
+        for( int c = 0; c < 4; c++ )
+        {
+            uint64_t at = 15;
+            for( size_t v = 0; v < h.size(); v++ )
+                if( h[ v ].first == corner_x[ c ] && h[ v ].second == corner_y[ c ] ) at = v;
+            info |= at << ( 44 + 4 * c );
+        }
         // blend vertices: the vertex as the neighbour across the shared edge sees it (subdivision_functions.cu:427-474)
         const int n = ( int )h.size();
         uint64_t aux = 0;

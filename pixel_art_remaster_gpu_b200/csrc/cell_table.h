@@ -33,6 +33,7 @@ PAR_TAB_HD unsigned cell_key( unsigned node, unsigned left, unsigned right )
 //                        is shared through, or 15 for a border edge
 //           bits [32,36) vertex count n (4..8)
 //           bits [36,44) bit t set when edge t is a border edge
+//           bits [44,60) 4 bits per square corner (0,0) (1,0) (1,1) (0,1): the hull vertex sitting there, 15 = none
 //   index : 4 bits per point code (see point_code): the index of the hull vertex at that point, 0 when
 //           the hull has no vertex there (what getPointIndex returns for "not found")
 //   aux   : one byte per vertex t: when t is a "blend" vertex (exactly one adjacent edge shared), the point
@@ -67,6 +68,7 @@ PAR_TAB_HD int point_code( int x, int y )
 
 PAR_TAB_HD int hull_count( uint64_t info ) { return ( int )( ( info >> 32 ) & 15u ); }
 PAR_TAB_HD uint32_t hull_border_mask( uint64_t info ) { return ( uint32_t )( info >> 36 ) & 255u; }
+PAR_TAB_HD uint32_t hull_corner_vertices( uint64_t info ) { return ( uint32_t )( info >> 44 ) & 0xFFFFu; }
 PAR_TAB_HD int hull_xq( uint64_t verts, int t ) { return ( int )( ( verts >> ( 8 * t ) ) & 15u ) - 1; }
 PAR_TAB_HD int hull_yq( uint64_t verts, int t ) { return ( int )( ( verts >> ( 8 * t + 4 ) ) & 15u ) - 1; }
 

@@ -80,7 +80,8 @@ struct Cfg
     static constexpr int off_vbuf = ( off_mask + NC * MW * 4 + 127 ) / 128 * 128;
     static constexpr int off_raw = off_vbuf;              // the staged BGR rows are dead before the vertex buffers are used
     static constexpr int off_work = off_vbuf + kMaxVerts * kThreads * 2;
-    static constexpr int off_bar = ( off_work + NC * 2 + 8 + 15 ) / 16 * 16;
+    static constexpr int off_cflags = off_work + NC * 2 + 8;  // per cell: bits 0-3 corner kept, bit 4 guard
+    static constexpr int off_bar = ( off_cflags + NC + 15 ) / 16 * 16;
     static_assert( KH * RAWP <= kMaxVerts * kThreads * 2, "raw colour rows alias the vertex buffers" );
     static constexpr int smem_bytes = off_bar + 16;
 };
@@ -292,8 +293,8 @@ __device__ __forceinline__ uint32_t memo_hash( uint64_t w0, uint64_t w1 )
 // cell with more than 6 blended vertices (does not fit 128 bits: never memoised).  `is_hull` is set when
 // nothing moves at all (no blended vertex and every corner kept): the polygon is the plain hull.
 template< class Env >
-__device__ __forceinline__ bool cell_signature( const Env& env, const CellTablePtrs& tab, int i, int j, uint32_t key, uint64_t& w0, uint64_t& w1,
-                                                bool& is_hull )
+__device__ __forceinline__ bool cell_signature( const Env& env, const CellTablePtrs& tab, int i, int j, uint32_t key, uint32_t cflags, uint64_t& w0,
+                                                uint64_t& w1, bool& is_hull )
 {
     uint64_t h, info;
     load_hull( tab, key, h, info );
@@ -324,17 +325,24 @@ __device__ __forceinline__ bool cell_signature( const Env& env, const CellTableP
         else
             w1 |= f << ( 16 * ( field - 2 ) );
     }
+    // corners kept by checkTJunction: all of them under its early exit, else the square corners whose three
+    // other pixels are not one colour (precomputed per cell, see the classify pass)
     uint32_t kept = 0u;
     if( cls.cut )
     {
-        if( env.guard( i, j ) )
+        if( cflags & 16u )
             kept = cls.cut;
         else
-            for( uint32_t m = cls.cut; m; m &= m - 1u )
+        {
+            const uint32_t cv = hull_corner_vertices( info );
+#pragma unroll
+            for( int c = 0; c < 4; c++ )
             {
-                const int t = __ffs( ( int )m ) - 1;
-                if( env.keep_corner( i, j, hull_vertex( h, t ) ) ) kept |= 1u << t;
+                const uint32_t v = ( cv >> ( 4 * c ) ) & 15u;
+                if( ( ( cflags >> c ) & 1u ) && v != 15u ) kept |= 1u << v;
             }
+            kept &= cls.cut;
+        }
     }
     w0 |= ( uint64_t )kept << 12;
     is_hull = cls.blend == 0u && kept == cls.cut;
@@ -501,6 +509,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
     // (2a) cells whose polygon is their plain hull copy the mask from the table; smoothed cells are compacted
     // into a list so that the next pass runs with full warps
     uint16_t* s_gen = reinterpret_cast< uint16_t* >( smem + C::off_vbuf ); // (the vertex buffers are not in use yet)
+    uint8_t* s_cflags = smem + C::off_cflags;
     for( int idx = tid; idx < C::NC; idx += kThreads )
     {
         int cy = idx / C::CW, cx = idx - cy * C::CW;
@@ -509,7 +518,29 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
         const uint32_t key = s_keys[ ( cy + 1 ) * C::KW + cx + 1 ];
         const bool plain = !subdivide || ( key & 0xFFu ) == 90u;
         if( inside && !plain )
+        {
             s_gen[ atomicAdd( s_nwork + 1, 1 ) ] = ( uint16_t )idx;
+            // checkTJunction for the four corners of the pixel square, once per cell and with every lane busy
+            uint32_t cf = 0u;
+            if( env.guard( gx, gy ) )
+                cf = 16u;
+            else if( gx >= 1 && gx <= a.width - 2 )
+            {
+                const uint32_t* c = s_col + ( cy + 1 ) * C::KW + ( cx + 1 );
+                const uint32_t l = c[ -1 ], r = c[ 1 ], d = c[ -C::KW ], u = c[ C::KW ];
+                const uint32_t dl = c[ -C::KW - 1 ], dr = c[ -C::KW + 1 ], ul = c[ C::KW - 1 ], ur = c[ C::KW + 1 ];
+                cf = ( ( l != dl || dl != d ) ? 1u : 0u ) | ( ( r != dr || dr != d ) ? 2u : 0u ) | ( ( r != ur || ur != u ) ? 4u : 0u ) |
+                     ( ( l != ul || ul != u ) ? 8u : 0u );
+            }
+            else
+            {
+                const Q2 corner[ 4 ] = { { 0, 0 }, { 4, 0 }, { 4, 4 }, { 0, 4 } };
+#pragma unroll
+                for( int c = 0; c < 4; c++ )
+                    if( env.img.keep_corner( gx, gy, corner[ c ] ) ) cf |= 1u << c; // flat byte offsets wrap at the first/last column
+            }
+            s_cflags[ idx ] = ( uint8_t )cf;
+        }
         else if( C::PACK )
         {
             uint2 m = make_uint2( 0u, 0u );
@@ -542,7 +573,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
             if( use_memo )
             {
                 uint64_t w0, w1;
-                const bool sig_ok = cell_signature( env, tab, gx, gy, key, w0, w1, is_hull ); // is_hull: nothing moves
+                const bool sig_ok = cell_signature( env, tab, gx, gy, key, s_cflags[ idx ], w0, w1, is_hull ); // is_hull: nothing moves
                 hit = !is_hull && sig_ok && memo_lookup< S >( a.memo, a.memo_cap_mask, w0, w1, mw );
             }
             if( is_hull )
@@ -600,7 +631,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                     const uint32_t key = s_keys[ ( cy + 1 ) * C::KW + cx + 1 ];
                     const uint64_t mw = tg.m | ( ( uint64_t )wide << 32 );
                     bool is_hull;
-                    if( cell_signature( env, tab, gx, gy, key, w0, w1, is_hull ) && memo_insert< S >( a.memo, a.memo_cap_mask, w0, w1, &mw ) )
+                    if( cell_signature( env, tab, gx, gy, key, s_cflags[ idx ], w0, w1, is_hull ) && memo_insert< S >( a.memo, a.memo_cap_mask, w0, w1, &mw ) )
                         atomicAdd( a.memo_stats + 2, 1ull );
                 }
             }
@@ -617,7 +648,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                     uint64_t w0, w1, mw[ Memo< S >::MASK_WORDS ];
                     const uint32_t key = s_keys[ ( cy + 1 ) * C::KW + cx + 1 ];
                     bool is_hull;
-                    const bool sig_ok = cell_signature( env, tab, gx, gy, key, w0, w1, is_hull );
+                    const bool sig_ok = cell_signature( env, tab, gx, gy, key, s_cflags[ idx ], w0, w1, is_hull );
 #pragma unroll
                     for( int k = 0; k < Memo< S >::MASK_WORDS; k++ ) mw[ k ] = 0ull;
 #pragma unroll
