@@ -39,16 +39,16 @@ struct __align__( 128 ) GraphSmem
     uint64_t bar;
 };
 
-// similarity of two packed words, each a byte triple (0,Y,U,V) after masking: per-byte absolute
-// difference against per-byte thresholds (5,7,6), which is what graph_functions.cu:291-293 computes
-// on the masked fields
+// Similarity of two staged words.  A staged word is the packed YUV word's low three bytes (V, U, Y — the
+// fields graph_functions.cu:291-293 masks out and compares) with a top byte of 0x00 for a pixel inside the
+// image and 0x80 for one outside.  One VABSDIFF4 gives the four per-byte absolute differences; a byte
+// exceeds its threshold (top 0, Y 5, U 7, V 6) iff its bit 7 is set or its low 7 bits plus (0x7F - threshold)
+// carry into bit 7.  In-image vs out-of-image differs by 0x80 in the top byte, so it is never similar.
 __device__ __forceinline__ uint32_t sim( uint32_t p, uint32_t q )
 {
-    uint32_t d = __vabsdiffu4( p & 0x00FFFFFFu, q & 0x00FFFFFFu );
-    uint32_t t1 = ( d & 0x00FF00FFu ) + 0x00FA00F9u; // Y > 5 -> bit 24, V > 6 -> bit 8
-    uint32_t t2 = ( d & 0x0000FF00u ) + 0x0000F800u; // U > 7 -> bit 16
-    uint32_t over = ( ( t1 & 0x01000100u ) | ( t2 & 0x00010000u ) ) | ( ( p | q ) & kInvalid );
-    return over == 0u ? 1u : 0u;
+    const uint32_t d = __vabsdiffu4( p, q );
+    const uint32_t s = ( d & 0x7F7F7F7Fu ) + 0x7F7A7879u;
+    return ( ( ( s | d ) & 0x80808080u ) == 0u ) ? 1u : 0u;
 }
 
 template< bool kUseTma >
@@ -90,28 +90,40 @@ __global__ void __launch_bounds__( kThreads ) similarity_graph_kernel( const __g
     }
 
     // packed YUV word per pixel, once
-    for( int idx = tid; idx < kYH * kYW; idx += kThreads )
+    for( int idx = tid, r = tid / kYW, c = tid % kYW; idx < kYH * kYW; idx += kThreads )
     {
-        int r = idx / kYW, c = idx - r * kYW;
         int gx = x0 - 1 + c, gy = y0 - 1 + r;
         const uint8_t* p = &s.raw[ r * kRawPitch + kRawOff + 3 * c ];
         uint32_t w = yuv_word( p[ 0 ], p[ 1 ], p[ 2 ] ) & 0x00FFFFFFu;
         if( gx < 0 || gy < 0 || gx >= a.width || gy >= a.height ) w = kInvalid;
         s.yuv[ r * kYuvPitch + c ] = w;
+        c += kThreads % kYW; // next element of this thread, without a division
+        r += kThreads / kYW;
+        if( c >= kYW )
+        {
+            c -= kYW;
+            r++;
+        }
     }
     __syncthreads();
 
     // one 2x2 block per step: bit0 = bottom side, bit1 = left side, bit2 = "/" diagonal, bit3 = "\" diagonal,
     // diagonals already cleared when all four sides are linked (stage B)
-    for( int idx = tid; idx < kBH * kBW; idx += kThreads )
+    for( int idx = tid, r = tid / kBW, c = tid % kBW; idx < kBH * kBW; idx += kThreads )
     {
-        int r = idx / kBW, c = idx - r * kBW;
         uint32_t p00 = s.yuv[ r * kYuvPitch + c ], p10 = s.yuv[ r * kYuvPitch + c + 1 ];
         uint32_t p01 = s.yuv[ ( r + 1 ) * kYuvPitch + c ], p11 = s.yuv[ ( r + 1 ) * kYuvPitch + c + 1 ];
         uint32_t hb = sim( p00, p10 ), ht = sim( p01, p11 ), vl = sim( p00, p01 ), vr = sim( p10, p11 );
         uint32_t d1 = sim( p00, p11 ), d2 = sim( p10, p01 );
         uint32_t keep = ( hb & ht & vl & vr ) ^ 1u;
         s.blk[ r * kBlkPitch + c ] = ( uint8_t )( hb | ( vl << 1 ) | ( ( d1 & keep ) << 2 ) | ( ( d2 & keep ) << 3 ) );
+        c += kThreads % kBW;
+        r += kThreads / kBW;
+        if( c >= kBW )
+        {
+            c -= kBW;
+            r++;
+        }
     }
     __syncthreads();
 
