@@ -1,0 +1,19 @@
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / initcheck): every kernel, TMA and plain
+tile paths, odd sizes, labels, polygons, launch_kernel, two strips."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import pixel_art_remaster_gpu_b200 as par
+from pixel_art_remaster_gpu_b200 import synth
+for (W, H, S) in ((96, 80, 4), (50, 37, 8), (65, 33, 3)):
+    frames = torch.from_numpy(synth.snes_stream(2, W, H, first_seed=7)).cuda()
+    with par.Remaster(0, W, H, 2) as ctx:
+        for no_tma in (False, True):
+            out = ctx.remaster(frames, S, True, want=("rgba", "graph", "graph_aux", "labels", "polygons"), no_tma=no_tma)
+            out = ctx.remaster(frames, S, True, want=("rgba",), no_tma=no_tma)  # memo hits
+        torch.cuda.synchronize()
+img = synth.adversarial_sprite(96, 100, 3)
+par.launch_kernel(img, True)
+with par.RemasterGroup([0, 0], 96, 100, 4) as g:
+    g.remaster_host(img, want=("rgba", "graph", "labels"))
+print("sanitize run done")
