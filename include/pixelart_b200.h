@@ -60,7 +60,8 @@ enum
     PAR_FLAG_NO_TMA = 1u << 2       /* force the plain-load tile path (also taken automatically when
                                        pointers/strides are not 16-byte multiples) */
     ,
-    PAR_FLAG_NO_MEMO = 1u << 4      /* do not use the mask memo (every smoothed cell takes the geometric path) */
+    PAR_FLAG_NO_SMOOTH_TABLES = 1u << 4 /* do not use the smoothing tables: every smoothed cell builds its polygon
+                                           and rasterizes it (the geometric path; same image, for tests) */
     ,
     PAR_FLAG_DEBUG_WIDE = 1u << 3   /* test hook: rasterize every cell through the exact slow path that
                                        normally only handles cells reaching beyond their sample mask */
@@ -110,10 +111,10 @@ uint64_t par_launch_count( const par_context* ctx );
 int par_profile_enable( par_context* ctx, int on );
 int par_profile_read( par_context* ctx, double* total_ms, int* launches );
 
-/* Mask memo statistics since par_create (synchronizes the stream): out3[0] = smoothed cells looked up,
- * out3[1] = of which missed (took the geometric path), out3[2] = entries inserted.  The memo caches a
- * pure function (cell signature -> coverage mask); it never changes results, only how they are obtained. */
-int par_memo_stats( par_context* ctx, uint64_t* out3 );
+/* Smoothing statistics since par_create (synchronizes the stream): out2[0] = smoothed cells (stage E ran on
+ * them), out2[1] = of which took the geometric path (polygon built and rasterized) instead of the
+ * precomputed smoothing tables.  Both paths give the same mask; the tables only make it cheaper. */
+int par_smooth_stats( par_context* ctx, uint64_t* out2 );
 
 /* Whole path on device-resident frames; asynchronous on the context's stream. */
 int par_remaster_device( par_context* ctx, const par_job* job );

@@ -21,7 +21,7 @@ __all__ = ["Remaster", "RemasterGroup", "launch_kernel", "RemasterError", "load_
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CELL_SLOTS = 45
-FLAG_SUBDIVIDE, FLAG_FLIP_OUTPUT, FLAG_NO_TMA, FLAG_DEBUG_WIDE, FLAG_NO_MEMO = 1, 2, 4, 8, 16
+FLAG_SUBDIVIDE, FLAG_FLIP_OUTPUT, FLAG_NO_TMA, FLAG_DEBUG_WIDE, FLAG_NO_SMOOTH_TABLES = 1, 2, 4, 8, 16
 _STATUS = {0: "PAR_OK", 1: "PAR_ERR_INVALID", 2: "PAR_ERR_NO_DEVICE", 3: "PAR_ERR_CUDA", 4: "PAR_ERR_CAPACITY"}
 
 
@@ -64,7 +64,7 @@ def load_library():
     L.par_device.argtypes = [C.c_void_p]
     L.par_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.par_use_own_stream.argtypes = [C.c_void_p]
-    L.par_memo_stats.argtypes = [C.c_void_p, P(C.c_uint64)]
+    L.par_smooth_stats.argtypes = [C.c_void_p, P(C.c_uint64)]
     L.par_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.par_profile_read.argtypes = [C.c_void_p, P(C.c_double), P(C.c_int)]
     L.par_synchronize.argtypes = [C.c_void_p]
@@ -162,11 +162,12 @@ class Remaster:
         self._check(self.lib.par_profile_read(self.handle, ms, n))
         return {k: (ms[i], n[i]) for i, k in enumerate(self.STAGES)}
 
-    def memo_stats(self):
-        """{'lookups', 'misses', 'inserted'} of the mask memo since the context was created."""
-        out = (C.c_uint64 * 3)()
-        self._check(self.lib.par_memo_stats(self.handle, out))
-        return {"lookups": int(out[0]), "misses": int(out[1]), "inserted": int(out[2])}
+    def smooth_stats(self):
+        """{'smoothed', 'geometric'}: cells stage E ran on since the context was created, and how many of them
+        built and rasterized their polygon instead of using the precomputed smoothing tables."""
+        out = (C.c_uint64 * 2)()
+        self._check(self.lib.par_smooth_stats(self.handle, out))
+        return {"smoothed": int(out[0]), "geometric": int(out[1])}
 
     @property
     def launch_count(self):
@@ -213,11 +214,11 @@ class Remaster:
             o["poly_count"] = t.empty((F, H * W), dtype=t.int32, device=dev)
         return o
 
-    no_memo = False  # set True to bypass the mask memo on every call of this context
+    no_tables = False  # set True to bypass the smoothing tables (geometric path for every smoothed cell) on every call of this context
 
     def _flags(self, subdivide, flip_output, no_tma):
         return (FLAG_SUBDIVIDE if subdivide else 0) | (FLAG_FLIP_OUTPUT if flip_output else 0) | (FLAG_NO_TMA if no_tma else 0) | \
-            (FLAG_NO_MEMO if self.no_memo else 0)
+            (FLAG_NO_SMOOTH_TABLES if self.no_tables else 0)
 
     # -- whole path ------------------------------------------------------------------------
     def remaster(self, frames, scale=4, subdivide=True, want=("rgba",), out=None, flip_output=False, no_tma=False):

@@ -44,9 +44,15 @@ struct par_context
     uint8_t *scratch_aux = nullptr, *scratch_graph = nullptr; // max_frames * max_w * max_h each
     CellRecord* d_tables = nullptr;        // kCellKeys 32-byte records
     uint32_t* d_mask_lut[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // per scale, built on first use
-    uint64_t* d_memo[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };     // per scale mask memo
-    unsigned long long* d_memo_stats = nullptr; // 3 counters
-    static constexpr uint32_t kMemoEntries = 1u << 17;
+    // smoothing tables (smooth_table.h): link descriptors + neighbour bytes + class list (scale-independent), CUT / LINK masks per scale
+    uint4* d_smooth_rec = nullptr;
+    uint8_t* d_smooth_nbr = nullptr;
+    LinkClass* d_link_classes = nullptr;
+    int n_link_classes = 0;
+    uint32_t link_entries = 0;
+    uint64_t* d_cut[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    uint64_t* d_link[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    unsigned long long* d_smooth_stats = nullptr; // 2 counters
     CellTablePtrs tables() const { return CellTablePtrs{ d_tables }; }
     EncodeTiledFn encode = nullptr;
     uint64_t launches = 0;
@@ -251,20 +257,29 @@ int run_raster( par_context* c, const par_job* j, const uint8_t* graph )
         if( le != cudaSuccess ) return c->cuda_fail( le, "mask table" );
     }
     a.mask_lut = c->d_mask_lut[ j->scale ];
-    a.memo = nullptr;
-    a.memo_cap_mask = 0;
-    a.memo_stats = c->d_memo_stats;
-    if( a.subdivide && !( j->flags & PAR_FLAG_NO_MEMO ) )
+    a.smooth = SmoothTablePtrs{ c->d_smooth_rec, c->d_smooth_nbr, nullptr, nullptr };
+    a.smooth_stats = c->d_smooth_stats;
+    if( a.subdivide && !( j->flags & PAR_FLAG_NO_SMOOTH_TABLES ) )
     {
-        if( !c->d_memo[ j->scale ] )
+        if( !c->d_cut[ j->scale ] )
         {
-            const size_t bytes = ( size_t )par_context::kMemoEntries * memo_entry_words( j->scale ) * sizeof( uint64_t );
-            cudaError_t me = cudaMalloc( &c->d_memo[ j->scale ], bytes );
-            if( me == cudaSuccess ) me = cudaMemsetAsync( c->d_memo[ j->scale ], 0, bytes, c->stream );
-            if( me != cudaSuccess ) return c->cuda_fail( me, "mask memo" );
+            // CUT / LINK masks at this scale, computed once by the device's own coverage code
+            const size_t ew = smooth_entry_words( j->scale ) * sizeof( uint64_t );
+            cudaError_t me = cudaMalloc( &c->d_cut[ j->scale ], ( size_t )kCellKeys * 16 * ew );
+            if( me == cudaSuccess ) me = cudaMalloc( &c->d_link[ j->scale ], ( size_t )c->link_entries * ew );
+            if( me == cudaSuccess )
+                me = launch_build_smooth_tables( j->scale, c->tables(), c->d_link_classes, c->n_link_classes, c->d_cut[ j->scale ], c->d_link[ j->scale ],
+                                                 c->stream );
+            c->launches += 2;
+            if( me != cudaSuccess )
+            {
+                cudaFree( c->d_cut[ j->scale ] );
+                c->d_cut[ j->scale ] = nullptr;
+                return c->cuda_fail( me, "smoothing tables" );
+            }
         }
-        a.memo = c->d_memo[ j->scale ];
-        a.memo_cap_mask = par_context::kMemoEntries - 1u;
+        a.smooth.cut = c->d_cut[ j->scale ];
+        a.smooth.link = c->d_link[ j->scale ];
     }
     CUtensorMap map;
     uint32_t box[ 3 ];
@@ -318,15 +333,29 @@ int par_create( par_context** out, int device, int max_width, int max_height, in
     if( e == cudaSuccess ) e = cudaMalloc( &c->scratch_aux, px );
     if( e == cudaSuccess ) e = cudaMalloc( &c->scratch_graph, px );
     if( e == cudaSuccess ) e = cudaMalloc( &c->d_tables, sizeof( CellTables ) );
-    if( e == cudaSuccess ) e = cudaMalloc( &c->d_memo_stats, 3 * sizeof( unsigned long long ) );
-    if( e == cudaSuccess ) e = cudaMemset( c->d_memo_stats, 0, 3 * sizeof( unsigned long long ) );
+    if( e == cudaSuccess ) e = cudaMalloc( &c->d_smooth_stats, 2 * sizeof( unsigned long long ) );
+    if( e == cudaSuccess ) e = cudaMemset( c->d_smooth_stats, 0, 2 * sizeof( unsigned long long ) );
     if( e == cudaSuccess )
     {
         static CellTables tables;
+        static SmoothTables smooth;
         static std::once_flag once;
-        std::call_once( once, [] { build_cell_tables( &tables ); } );
+        std::call_once( once, [] {
+            build_cell_tables( &tables );
+            build_smooth_tables( tables, &smooth );
+        } );
         static_assert( sizeof( CellTables ) == 32 * kCellKeys, "one 32-byte record per key" );
+        static_assert( sizeof( SmoothRecord ) == 16, "one 16-byte record per key" );
         e = cudaMemcpy( c->d_tables, &tables, sizeof( tables ), cudaMemcpyHostToDevice );
+        c->n_link_classes = ( int )smooth.classes.size();
+        c->link_entries = smooth.link_entries;
+        if( e == cudaSuccess ) e = cudaMalloc( &c->d_smooth_rec, sizeof( smooth.rec ) );
+        if( e == cudaSuccess ) e = cudaMalloc( &c->d_smooth_nbr, sizeof( smooth.nbr ) );
+        if( e == cudaSuccess ) e = cudaMalloc( &c->d_link_classes, smooth.classes.size() * sizeof( LinkClass ) );
+        if( e == cudaSuccess ) e = cudaMemcpy( c->d_smooth_rec, smooth.rec, sizeof( smooth.rec ), cudaMemcpyHostToDevice );
+        if( e == cudaSuccess ) e = cudaMemcpy( c->d_smooth_nbr, smooth.nbr, sizeof( smooth.nbr ), cudaMemcpyHostToDevice );
+        if( e == cudaSuccess )
+            e = cudaMemcpy( c->d_link_classes, smooth.classes.data(), smooth.classes.size() * sizeof( LinkClass ), cudaMemcpyHostToDevice );
     }
     if( e != cudaSuccess )
     {
@@ -352,8 +381,12 @@ void par_destroy( par_context* c )
     cudaFree( c->scratch_graph );
     cudaFree( c->d_tables );
     for( int k = 0; k < 9; k++ ) cudaFree( c->d_mask_lut[ k ] );
-    for( int k = 0; k < 9; k++ ) cudaFree( c->d_memo[ k ] );
-    cudaFree( c->d_memo_stats );
+    for( int k = 0; k < 9; k++ ) cudaFree( c->d_cut[ k ] );
+    for( int k = 0; k < 9; k++ ) cudaFree( c->d_link[ k ] );
+    cudaFree( c->d_smooth_rec );
+    cudaFree( c->d_smooth_nbr );
+    cudaFree( c->d_link_classes );
+    cudaFree( c->d_smooth_stats );
     for( int k = 0; k < 8; k++ ) cudaFree( c->h_stage[ k ] );
     for( auto& sp : c->spans )
     {
@@ -413,15 +446,15 @@ int par_profile_read( par_context* c, double* total_ms, int* launches )
     return PAR_OK;
 }
 
-int par_memo_stats( par_context* c, uint64_t* out3 )
+int par_smooth_stats( par_context* c, uint64_t* out2 )
 {
-    if( !c || !out3 ) return PAR_ERR_INVALID;
+    if( !c || !out2 ) return PAR_ERR_INVALID;
     cudaSetDevice( c->device );
     cudaError_t e = cudaStreamSynchronize( c->stream );
-    unsigned long long h[ 3 ] = { 0, 0, 0 };
-    if( e == cudaSuccess ) e = cudaMemcpy( h, c->d_memo_stats, sizeof( h ), cudaMemcpyDeviceToHost );
-    if( e != cudaSuccess ) return c->cuda_fail( e, "memo_stats" );
-    for( int k = 0; k < 3; k++ ) out3[ k ] = h[ k ];
+    unsigned long long h[ 2 ] = { 0, 0 };
+    if( e == cudaSuccess ) e = cudaMemcpy( h, c->d_smooth_stats, sizeof( h ), cudaMemcpyDeviceToHost );
+    if( e != cudaSuccess ) return c->cuda_fail( e, "smooth_stats" );
+    for( int k = 0; k < 2; k++ ) out2[ k ] = h[ k ];
     return PAR_OK;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "polygon.cuh"
+#include "smooth_table.h"
 #include <string.h>
 
 namespace par {
@@ -28,15 +29,23 @@ struct LabelArgs
     int width, height, n_frames;
 };
 
+// device pointers of the smoothing tables (smooth_table.h); cut / link are per scale
+struct SmoothTablePtrs
+{
+    const uint4* rec;     // [kCellKeys] link descriptors
+    const uint8_t* nbr;   // [kCellKeys][16] neighbour bytes
+    const uint64_t* cut;  // [kCellKeys][16] entries
+    const uint64_t* link; // [link_entries] entries
+};
+
 struct RasterArgs
 {
     const uint8_t* bgr;
     const uint8_t* graph;       // final graph, dense
     CellTablePtrs tables;       // 4096-entry cell tables (cell_table.h), device pointers
     const uint32_t* mask_lut;   // per-scale coverage masks of the 4096 plain hulls (raster only)
-    uint64_t* memo;             // per-scale mask memo table (raster only), null = off
-    uint32_t memo_cap_mask;     // entries - 1 (power of two)
-    unsigned long long* memo_stats; // [0] smoothed cells looked up, [1] misses, [2] entries inserted
+    SmoothTablePtrs smooth;     // smoothing tables (raster only); cut == null: every smoothed cell takes the geometric path
+    unsigned long long* smooth_stats; // [0] smoothed cells, [1] of which took the geometric path (may be null)
     uint8_t* rgba;              // out (raster), may be null
     float* polygons;            // out (polygon export), may be null
     int32_t* poly_count;        // out (polygon export), may be null
@@ -61,7 +70,9 @@ cudaError_t launch_cc_labels( const LabelArgs& a, cudaStream_t stream, int* n_la
 cudaError_t launch_polygons( const RasterArgs& a, cudaStream_t stream );
 void raster_tma_box( int scale, uint32_t box[ 3 ] );
 size_t mask_lut_words( int scale );
-size_t memo_entry_words( int scale );
+size_t smooth_entry_words( int scale ); // 64-bit words per CUT / LINK entry
+cudaError_t launch_build_smooth_tables( int scale, const CellTablePtrs& tab, const LinkClass* d_classes, int n_classes, uint64_t* cut, uint64_t* link,
+                                        cudaStream_t stream );
 cudaError_t launch_build_mask_lut( int scale, const CellTablePtrs& tab, uint32_t* lut, cudaStream_t stream );
 void raster_img_tma_box( int scale, uint32_t box[ 3 ] );
 cudaError_t launch_raster( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream );

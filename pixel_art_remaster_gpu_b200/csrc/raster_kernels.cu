@@ -23,12 +23,11 @@
 // edge crosses (masks are 64-bit registers for s <= 4); geometry never touches HBM; (3) one thread
 // per source pixel resolves its s x s output pixels with bit operations over the 3x3 neighbourhood's
 // masks in priority order and writes whole output-row segments with 128-bit streaming stores.
-// Mask memo: the mask of a smoothed cell is a PURE function of a small signature — its own 12-bit
-// key, the two neighbour hull vertices each of its blended vertices reads, and one "corner kept" bit
-// per corner between two border edges — so masks are memoised in a device hash table that lives in the
-// context (per scale, content-independent, never invalidated).  Pixel art repeats local shapes: a
-// stream of independent 256x224 frames settles at < 0.5 % misses after ~15 frames.  Hits cost a
-// signature + one 32-byte probe; misses are compacted and take the full geometric path, then insert.
+// Smoothed cells do not build their polygon at all on the fast path: even-odd coverage is XOR-linear in the
+// polygon's edges, so the mask is the XOR of a few precomputed pieces (smooth_table.h) — one CUT entry for the
+// cell's own key and kept corners, one LINK entry per shared edge with a blended end, indexed by one byte
+// read from the neighbour's key.  The tables are content-independent and built once per context and scale
+// by this file's own coverage code; cells they cannot express take the geometric path above.
 // Algorithmic HBM traffic: 3 B/px colour + 1 B/px graph in, 4*s*s B/px out.
 #include "kernels.cuh"
 #include "polygon.cuh"
@@ -256,149 +255,234 @@ __global__ void build_mask_lut_kernel( CellTablePtrs tab, uint32_t* lut )
     }
 }
 
-// ---- mask memo ---------------------------------------------------------------------------------
-// Entry (64-bit words): [0] w0, [1] w1 = the signature, [2] state (0 empty, 1 being written, 2 valid),
-// [3..] the mask: PACK -> one word (bit 63 = wide); rows -> R 16-bit rows, wide flag in bit 15 of row 0.
+// ---- smoothing tables (smooth_table.h) -------------------------------------------------------------
+// Table entry = the coverage mask as 64-bit words: PACK -> one word, bit 63 = wide; rows -> R 16-bit rows,
+// four per word, wide flag in bit 15 of row 0.
 template< int S >
-struct Memo
+struct Entry
 {
-    static constexpr int MASK_WORDS = Cfg< S >::PACK ? 1 : ( Cfg< S >::R * 2 + 7 ) / 8;
-    static constexpr int ENTRY_WORDS = ( 3 + MASK_WORDS + 1 ) / 2 * 2; // even: entries stay 16-byte aligned
-    static constexpr int PROBES = 8;
+    static constexpr int EW = Cfg< S >::PACK ? 1 : ( Cfg< S >::R * 2 + 7 ) / 8;
+    static constexpr uint64_t FLAG = Cfg< S >::PACK ? ( 1ull << 63 ) : ( 1ull << 15 );
 };
 
-__device__ __forceinline__ uint32_t ld_acquire_u32( const uint32_t* p )
+// coverage of the closed polygon (xs[k], ys[k]), k < m (1/64 px, cell-local), as a table entry
+template< int S >
+__device__ void cover_to_entry( const int* xs, const int* ys, int m, uint64_t* out )
 {
-    uint32_t v;
-    asm volatile( "ld.acquire.gpu.global.u32 %0, [%1];" : "=r"( v ) : "l"( p ) : "memory" );
-    return v;
-}
-__device__ __forceinline__ void st_release_u32( uint32_t* p, uint32_t v )
-{
-    asm volatile( "st.release.gpu.global.u32 [%0], %1;" ::"l"( p ), "r"( v ) : "memory" );
-}
-__device__ __forceinline__ uint32_t memo_hash( uint64_t w0, uint64_t w1 )
-{
-    uint64_t h = ( w0 ^ ( w1 * 0x9E3779B97F4A7C15ull ) ) * 0xD6E8FEB86659FD93ull;
-    h ^= h >> 32;
-    h *= 0xD6E8FEB86659FD93ull;
-    return ( uint32_t )( h >> 32 );
+    typedef Cfg< S > C;
+    int lo = 1 << 30, hi = -( 1 << 30 );
+    for( int k = 0; k < m; k++ )
+    {
+        lo = min( lo, min( xs[ k ], ys[ k ] ) * C::VM );
+        hi = max( hi, max( xs[ k ], ys[ k ] ) * C::VM );
+    }
+    const bool wide = lo <= -C::REACH || hi >= C::SQUARE + C::REACH;
+    if( C::PACK )
+    {
+        PackedToggle< C::R > tg{ 0ull };
+        for( int k = 0; k < m; k++ )
+        {
+            const int k1 = k + 1 == m ? 0 : k + 1;
+            cover_edge< S, C::R >( C::S_FIRST, C::S_FIRST, xs[ k ] * C::VM, ys[ k ] * C::VM, xs[ k1 ] * C::VM, ys[ k1 ] * C::VM, tg );
+        }
+        out[ 0 ] = tg.m | ( wide ? Entry< S >::FLAG : 0ull );
+    }
+    else
+    {
+        uint32_t rows[ C::R ];
+        for( int r = 0; r < C::R; r++ ) rows[ r ] = 0u;
+        RowToggle tg{ rows, 1 };
+        for( int k = 0; k < m; k++ )
+        {
+            const int k1 = k + 1 == m ? 0 : k + 1;
+            cover_edge< S, C::R >( C::S_FIRST, C::S_FIRST, xs[ k ] * C::VM, ys[ k ] * C::VM, xs[ k1 ] * C::VM, ys[ k1 ] * C::VM, tg );
+        }
+        for( int w = 0; w < Entry< S >::EW; w++ ) out[ w ] = 0ull;
+        for( int r = 0; r < C::R; r++ ) out[ r >> 2 ] |= ( uint64_t )( rows[ r ] & 0x7FFFu ) << ( 16 * ( r & 3 ) );
+        if( wide ) out[ 0 ] |= Entry< S >::FLAG;
+    }
 }
 
-// Signature of a smoothed cell: everything its polygon depends on besides the constant tables, kept as
-// small as possible so that equal shapes share an entry.  Own key (12 bits); one "kept" bit per corner
-// between two border edges; and per blended vertex (ascending t) the TWO neighbour hull vertices its
-// blend reads — the one matched to the shared vertex and the one before/after it — as their packed
-// table bytes (16 bits).  The neighbour's other 10+ key bits do not matter.  Returns false for the rare
-// cell with more than 6 blended vertices (does not fit 128 bits: never memoised).  `is_hull` is set when
-// nothing moves at all (no blended vertex and every corner kept): the polygon is the plain hull.
-template< class Env >
-__device__ __forceinline__ bool cell_signature( const Env& env, const CellTablePtrs& tab, int i, int j, uint32_t key, uint32_t cflags, uint64_t& w0,
-                                                uint64_t& w1, bool& is_hull )
+// CUT[key][kept]: the hull with its cut vertices replaced by R(prev), Q(cur) (subdivision_functions.cu:583-598),
+// except the square corners (0,0) (1,0) (1,1) (0,1) whose bit in `kept` is set
+template< int S >
+__global__ void build_cut_table_kernel( CellTablePtrs tab, uint64_t* cut )
 {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if( id >= kCellKeys * 16 ) return;
+    const uint32_t key = ( uint32_t )id >> 4, kept = ( uint32_t )id & 15u;
     uint64_t h, info;
     load_hull( tab, key, h, info );
-    is_hull = false;
     const int n = hull_count( info );
-    VertexClasses cls = classify_vertices( info );
-    if( __popc( cls.blend ) > 6 ) return false;
-    const uint64_t aux = cls.blend ? load_aux( tab, key ) : 0ull;
-    w0 = key;
-    w1 = 0ull;
-    int field = 0;
-    for( uint32_t m = cls.blend; m; m &= m - 1u, field++ )
+    const VertexClasses cls = classify_vertices( info );
+    const uint32_t cv = hull_corner_vertices( info );
+    uint32_t keptv = 0u;
+    for( int c = 0; c < 4; c++ )
     {
-        const int t = __ffs( ( int )m ) - 1;
-        const bool cur_border = ( cls.cur_border >> t ) & 1u;
-        const int L = ( int )( ( ( uint32_t )info >> ( 4 * ( cur_border ? ( t == 0 ? n - 1 : t - 1 ) : t ) ) ) & 15u ); // the shared edge
-        const uint32_t nkey = env.key( i + edge_di( L ), j + edge_dj( L ) );
-        uint64_t hn, info_n;
-        load_hull( tab, nkey, hn, info_n );
-        const int nn = hull_count( info_n );
-        const int code = ( int )( ( aux >> ( 8 * t ) ) & 255u );
-        const int op = code == 255 ? 0 : ( int )( ( load_index( tab, nkey ) >> ( 4 * code ) ) & 15u );
-        const int other = cur_border ? ( op == 0 ? nn - 1 : op - 1 ) : ( op + 1 == nn ? 0 : op + 1 );
-        const uint64_t f = ( __byte_perm( ( uint32_t )hn, ( uint32_t )( hn >> 32 ), ( uint32_t )op ) & 0xFFu ) |
-                           ( ( __byte_perm( ( uint32_t )hn, ( uint32_t )( hn >> 32 ), ( uint32_t )other ) & 0xFFu ) << 8 );
-        if( field < 2 )
-            w0 |= f << ( 20 + 16 * field );
-        else
-            w1 |= f << ( 16 * ( field - 2 ) );
+        const uint32_t v = ( cv >> ( 4 * c ) ) & 15u;
+        if( ( ( kept >> c ) & 1u ) && v != 15u ) keptv |= 1u << v;
     }
-    // corners kept by checkTJunction: all of them under its early exit, else the square corners whose three
-    // other pixels are not one colour (precomputed per cell, see the classify pass)
-    uint32_t kept = 0u;
-    if( cls.cut )
+    int xs[ kMaxVerts ], ys[ kMaxVerts ], m = 0;
+    for( int t = 0; t < n; t++ )
     {
-        if( cflags & 16u )
-            kept = cls.cut;
+        const Q2 p = hull_vertex( h, t );
+        if( ( ( cls.cut >> t ) & 1u ) && !( ( keptv >> t ) & 1u ) )
+        {
+            cut_toward( p, hull_vertex( h, t == 0 ? n - 1 : t - 1 ), xs[ m ], ys[ m ] );
+            m++;
+            cut_toward( p, hull_vertex( h, t + 1 == n ? 0 : t + 1 ), xs[ m ], ys[ m ] );
+            m++;
+        }
         else
         {
-            const uint32_t cv = hull_corner_vertices( info );
-#pragma unroll
-            for( int c = 0; c < 4; c++ )
+            xs[ m ] = 16 * p.x;
+            ys[ m ] = 16 * p.y;
+            m++;
+        }
+    }
+    cover_to_entry< S >( xs, ys, m, cut + ( size_t )id * Entry< S >::EW );
+}
+
+// the point with a given code (inverse of point_code, cell_table.h), quarter pixels
+__device__ __forceinline__ Q2 point_of_code( int code )
+{
+    Q2 q{ 0, 0 };
+    int seen = 0;
+    for( int pos = 0; pos < 49; pos++ )
+        if( ( kValidPoints >> pos ) & 1ull )
+        {
+            if( seen == code )
             {
-                const uint32_t v = ( cv >> ( 4 * c ) ) & 15u;
-                if( ( ( cflags >> c ) & 1u ) && v != 15u ) kept |= 1u << v;
+                q.x = pos % 7 - 1;
+                q.y = pos / 7 - 1;
             }
-            kept &= cls.cut;
+            seen++;
         }
-    }
-    w0 |= ( uint64_t )kept << 12;
-    is_hull = cls.blend == 0u && kept == cls.cut;
-    return true;
+    return q;
 }
 
-// Entries are immutable once their state reads 2 and the writer publishes the state with a release store
-// after the payload, so probes may use ordinary L1-cached loads: a stale line can only show an older state
-// (0 or 1), which is a harmless miss, never a wrong mask.  Hot signatures then hit in L1.
+// LINK[class][a][b]: the loop between the hull path and the smoothed path around one shared edge
+// (subdivision_functions.cu:603-647 for the two blended vertices, see smooth_table.h)
 template< int S >
-__device__ __forceinline__ bool memo_lookup( const uint64_t* table, uint32_t cap_mask, uint64_t w0, uint64_t w1, uint64_t* mask_words )
+__global__ void build_link_table_kernel( const LinkClass* classes, uint64_t* link )
 {
-    typedef Memo< S > M;
-    const uint32_t h = memo_hash( w0, w1 );
-#pragma unroll 1
-    for( int p = 0; p < M::PROBES; p++ )
+    const LinkClass c = classes[ blockIdx.x ];
+    const int sub = threadIdx.x;
+    if( sub >= ( int )c.count ) return;
+    const int a = ( c.hasA && c.hasB ) ? sub >> 4 : sub, b = ( c.hasA && c.hasB ) ? sub & 15 : sub;
+    const int di = edge_di( c.e ), dj = edge_dj( c.e );
+    const Q2 P0{ c.px[ 0 ], c.py[ 0 ] }, P1{ c.px[ 1 ], c.py[ 1 ] }, P2{ c.px[ 2 ], c.py[ 2 ] }, P3{ c.px[ 3 ], c.py[ 3 ] };
+    int xs[ 6 ], ys[ 6 ], m = 0;
+    if( c.hasA )
     {
-        const uint64_t* e = table + ( size_t )( ( h + p ) & cap_mask ) * M::ENTRY_WORDS;
-        const ulonglong2 sig = __ldca( reinterpret_cast< const ulonglong2* >( e ) );     // w0, w1
-        const ulonglong2 sm = __ldca( reinterpret_cast< const ulonglong2* >( e + 2 ) );  // state, first mask word
-        const uint32_t state = ( uint32_t )sm.x;
-        if( state == 0u ) return false;
-        if( state == 2u && sig.x == w0 && sig.y == w1 )
-        {
-            mask_words[ 0 ] = sm.y;
-#pragma unroll
-            for( int k = 1; k < M::MASK_WORDS; k++ ) mask_words[ k ] = __ldca( e + 3 + k );
-            return true;
-        }
+        int rx, ry, qx, qy;
+        cut_toward( P1, P0, rx, ry );                                                   // own R on the border edge arriving at P1
+        cut_toward( Q2{ P1.x - 4 * di, P1.y - 4 * dj }, point_of_code( a ), qx, qy );  // neighbour's Q on the edge leaving P1
+        xs[ m ] = rx;
+        ys[ m ] = ry;
+        m++;
+        xs[ m ] = ( rx + qx + 64 * di ) >> 1;
+        ys[ m ] = ( ry + qy + 64 * dj ) >> 1;
+        m++;
     }
-    return false;
+    else
+    {
+        xs[ m ] = 16 * P1.x;
+        ys[ m ] = 16 * P1.y;
+        m++;
+    }
+    if( c.hasB )
+    {
+        int qx, qy, rx, ry;
+        cut_toward( P2, P3, qx, qy );                                                   // own Q on the border edge leaving P2
+        cut_toward( Q2{ P2.x - 4 * di, P2.y - 4 * dj }, point_of_code( b ), rx, ry );  // neighbour's R on the edge arriving at P2
+        xs[ m ] = ( qx + rx + 64 * di ) >> 1;
+        ys[ m ] = ( qy + ry + 64 * dj ) >> 1;
+        m++;
+        xs[ m ] = qx;
+        ys[ m ] = qy;
+        m++;
+    }
+    xs[ m ] = 16 * P2.x;
+    ys[ m ] = 16 * P2.y;
+    m++;
+    if( c.hasA )
+    {
+        xs[ m ] = 16 * P1.x;
+        ys[ m ] = 16 * P1.y;
+        m++;
+    }
+    cover_to_entry< S >( xs, ys, m, link + ( size_t )( c.first + sub ) * Entry< S >::EW );
 }
 
+// Mask of a smoothed cell from the tables: false when a blended vertex is not a vertex of the neighbour's
+// hull (the reference's getPointIndex fallback) — the caller then takes the geometric path.
 template< int S >
-__device__ __forceinline__ bool memo_insert( uint64_t* table, uint32_t cap_mask, uint64_t w0, uint64_t w1, const uint64_t* mask_words )
+__device__ __forceinline__ bool smooth_lookup( const SmoothTablePtrs& st, const uint32_t* mask_lut, const uint16_t* keys_at_cell, uint32_t key, uint32_t cflags,
+                                               uint64_t* m, bool& wide )
 {
-    typedef Memo< S > M;
-    const uint32_t h = memo_hash( w0, w1 );
-#pragma unroll 1
-    for( int p = 0; p < M::PROBES; p++ )
+    typedef Cfg< S > C;
+    typedef Entry< S > E;
+    const uint4 rec = __ldg( st.rec + key );
+    uint64_t flags = 0ull;
+    if( cflags & 16u ) // checkTJunction's early exit keeps every cut vertex: the plain hull
     {
-        uint64_t* e = table + ( size_t )( ( h + p ) & cap_mask ) * M::ENTRY_WORDS;
-        uint32_t* state = reinterpret_cast< uint32_t* >( e + 2 );
-        const uint32_t old = atomicCAS( state, 0u, 1u );
-        if( old == 0u )
+        if( C::PACK )
         {
-            e[ 0 ] = w0;
-            e[ 1 ] = w1;
-#pragma unroll
-            for( int k = 0; k < M::MASK_WORDS; k++ ) e[ 3 + k ] = mask_words[ k ];
-            st_release_u32( state, 2u ); // publishes the entry: readers acquire the state before they look at it
-            return true;
+            const uint2 v = __ldg( reinterpret_cast< const uint2* >( mask_lut ) + key );
+            m[ 0 ] = ( uint64_t )v.y << 32 | v.x;
         }
-        if( old == 2u && __ldcg( e ) == w0 && __ldcg( e + 1 ) == w1 ) return false; // somebody else was faster
+        else
+        {
+#pragma unroll
+            for( int w = 0; w < E::EW; w++ ) m[ w ] = 0ull;
+#pragma unroll
+            for( int r = 0; r < C::R; r++ ) m[ r >> 2 ] |= ( uint64_t )__ldg( mask_lut + key * C::R + r ) << ( 16 * ( r & 3 ) );
+        }
     }
-    return false; // neighbourhood full: the mask is simply not cached
+    else
+    {
+        const uint64_t* e = st.cut + ( size_t )( key * 16u + ( cflags & 15u ) ) * E::EW;
+#pragma unroll
+        for( int w = 0; w < E::EW; w++ ) m[ w ] = __ldg( e + w );
+    }
+    bool ok = rec.x != kSmoothSlow;
+    const uint32_t links[ 4 ] = { rec.x, rec.y, rec.z, rec.w };
+#pragma unroll
+    for( int k = 0; k < kMaxLinks; k++ )
+    {
+        const uint32_t d = links[ k ];
+        if( d == 0u || !ok ) break;
+        const int e = ( int )( d & 7u );
+        const uint32_t nkey = keys_at_cell[ edge_dj( e ) * C::KW + edge_di( e ) ];
+        const uint8_t* nb = st.nbr + nkey * 16u;
+        const uint32_t codeA = ( d >> 5 ) & 15u, codeB = ( d >> 9 ) & 15u;
+        uint32_t sub = 0u;
+        if( d & 8u )
+        {
+            const uint32_t a = ( uint32_t )__ldg( nb + codeA ) & 15u;
+            ok = ok && a != codeA;
+            sub = a;
+        }
+        if( d & 16u )
+        {
+            const uint32_t b = ( uint32_t )__ldg( nb + codeB ) >> 4;
+            ok = ok && b != codeB;
+            sub = ( d & 8u ) ? sub * 16u + b : b;
+        }
+        const uint64_t* le = st.link + ( size_t )( ( d >> 13 ) + sub ) * E::EW;
+#pragma unroll
+        for( int w = 0; w < E::EW; w++ )
+        {
+            const uint64_t v = __ldg( le + w );
+            if( w == 0 ) flags |= v;
+            m[ w ] ^= v;
+        }
+    }
+    // the flag bit of word 0 was XORed along with the masks: restore it from the CUT entry (never wide) and the OR
+    wide = ( flags & E::FLAG ) != 0ull;
+    m[ 0 ] &= ~E::FLAG;
+    return ok;
 }
 
 template< int S, bool kUseTma >
@@ -504,7 +588,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
     const bool subdivide = a.subdivide != 0;
     const CellTablePtrs tab = a.tables;
     const uint32_t force_wide = a.debug_force_wide ? C::WIDE : 0u;
-    const bool use_memo = a.memo != nullptr && !a.debug_force_wide;
+    const bool use_tables = a.smooth.cut != nullptr && !a.debug_force_wide;
 
     // (2a) cells whose polygon is their plain hull copy the mask from the table; smoothed cells are compacted
     // into a list so that the next pass runs with full warps
@@ -559,44 +643,28 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
         }
     }
     __syncthreads();
-    // smoothed cells: the mask is a pure function of the cell's signature -> look it up in the memo first
+    // smoothed cells: the mask is assembled from the smoothing tables (one CUT entry + one LINK entry per shared
+    // edge with a blended end); the rare cell the tables cannot express is queued for the geometric path
     {
         const int n_gen = s_nwork[ 1 ];
         for( int w = tid; w < n_gen; w += kThreads )
         {
             const int idx = s_gen[ w ];
             int cy = idx / C::CW, cx = idx - cy * C::CW;
-            int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
-            const uint32_t key = s_keys[ ( cy + 1 ) * C::KW + cx + 1 ];
-            bool hit = false, is_hull = false;
-            uint64_t mw[ Memo< S >::MASK_WORDS ];
-            if( use_memo )
-            {
-                uint64_t w0, w1;
-                const bool sig_ok = cell_signature( env, tab, gx, gy, key, s_cflags[ idx ], w0, w1, is_hull ); // is_hull: nothing moves
-                hit = !is_hull && sig_ok && memo_lookup< S >( a.memo, a.memo_cap_mask, w0, w1, mw );
-            }
-            if( is_hull )
+            const uint16_t* kc = s_keys + ( cy + 1 ) * C::KW + cx + 1;
+            uint64_t mw[ Entry< S >::EW ];
+            bool wide = false;
+            if( use_tables && smooth_lookup< S >( a.smooth, a.mask_lut, kc, *kc, s_cflags[ idx ], mw, wide ) )
             {
                 if( C::PACK )
-                    reinterpret_cast< uint2* >( s_mask )[ idx ] = __ldg( reinterpret_cast< const uint2* >( a.mask_lut ) + key );
-                else
-                {
-#pragma unroll
-                    for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] = __ldg( a.mask_lut + key * C::R + r );
-                }
-            }
-            else if( hit )
-            {
-                if( C::PACK )
-                    reinterpret_cast< uint2* >( s_mask )[ idx ] = make_uint2( ( uint32_t )mw[ 0 ], ( uint32_t )( mw[ 0 ] >> 32 ) );
+                    reinterpret_cast< uint2* >( s_mask )[ idx ] = make_uint2( ( uint32_t )mw[ 0 ], ( uint32_t )( mw[ 0 ] >> 32 ) | ( wide ? C::WIDE : 0u ) );
                 else
                 {
 #pragma unroll
                     for( int r = 0; r < C::R; r++ )
                     {
-                        const uint32_t row = ( uint32_t )( mw[ r >> 2 ] >> ( 16 * ( r & 3 ) ) ) & 0xFFFFu;
-                        s_mask[ r * C::NC + idx ] = ( row & 0x7FFFu ) | ( ( r == 0 && ( row & 0x8000u ) ) ? C::WIDE : 0u );
+                        const uint32_t row = ( uint32_t )( mw[ r >> 2 ] >> ( 16 * ( r & 3 ) ) ) & 0x7FFFu;
+                        s_mask[ r * C::NC + idx ] = row | ( ( r == 0 && wide ) ? C::WIDE : 0u );
                     }
                 }
             }
@@ -625,15 +693,6 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                 // reach check: every sample outside the mask must be strictly outside the polygon's bounding box
                 const uint32_t wide = ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
                 reinterpret_cast< uint2* >( s_mask )[ idx ] = make_uint2( ( uint32_t )tg.m, ( uint32_t )( tg.m >> 32 ) | wide );
-                if( use_memo )
-                {
-                    uint64_t w0, w1;
-                    const uint32_t key = s_keys[ ( cy + 1 ) * C::KW + cx + 1 ];
-                    const uint64_t mw = tg.m | ( ( uint64_t )wide << 32 );
-                    bool is_hull;
-                    if( cell_signature( env, tab, gx, gy, key, s_cflags[ idx ], w0, w1, is_hull ) && memo_insert< S >( a.memo, a.memo_cap_mask, w0, w1, &mw ) )
-                        atomicAdd( a.memo_stats + 2, 1ull );
-                }
             }
             else
             {
@@ -643,30 +702,14 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                 cover_polygon< S, C::R >( vbuf, kThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
                 const uint32_t wide = ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
                 s_mask[ idx ] |= wide;
-                if( use_memo )
-                {
-                    uint64_t w0, w1, mw[ Memo< S >::MASK_WORDS ];
-                    const uint32_t key = s_keys[ ( cy + 1 ) * C::KW + cx + 1 ];
-                    bool is_hull;
-                    const bool sig_ok = cell_signature( env, tab, gx, gy, key, s_cflags[ idx ], w0, w1, is_hull );
-#pragma unroll
-                    for( int k = 0; k < Memo< S >::MASK_WORDS; k++ ) mw[ k ] = 0ull;
-#pragma unroll
-                    for( int r = 0; r < C::R; r++ )
-                    {
-                        const uint32_t row = ( s_mask[ r * C::NC + idx ] & 0x7FFFu ) | ( ( r == 0 && wide ) ? 0x8000u : 0u );
-                        mw[ r >> 2 ] |= ( uint64_t )row << ( 16 * ( r & 3 ) );
-                    }
-                    if( sig_ok && memo_insert< S >( a.memo, a.memo_cap_mask, w0, w1, mw ) ) atomicAdd( a.memo_stats + 2, 1ull );
-                }
             }
         }
     }
     __syncthreads();
-    if( use_memo && tid == 0 )
+    if( a.smooth_stats && tid == 0 )
     {
-        atomicAdd( a.memo_stats, ( unsigned long long )s_nwork[ 1 ] );     // smoothed cells looked up
-        atomicAdd( a.memo_stats + 1, ( unsigned long long )s_nwork[ 0 ] ); // ... of which missed
+        atomicAdd( a.smooth_stats, ( unsigned long long )s_nwork[ 1 ] );     // smoothed cells
+        atomicAdd( a.smooth_stats + 1, ( unsigned long long )s_nwork[ 0 ] ); // ... of which took the geometric path
     }
 
     // (3) resolve and write: one thread per source pixel, S output rows of S pixels each
@@ -874,12 +917,12 @@ bool raster_scale_supported( int scale ) { return scale >= 1 && scale <= 8 && sc
 #define PAR_FOR_SCALE( scale, CALL )  \
     switch( scale )                    \
     {                                  \
-        case 1: CALL( 1 );             \
-        case 2: CALL( 2 );             \
-        case 3: CALL( 3 );             \
-        case 4: CALL( 4 );             \
-        case 6: CALL( 6 );             \
-        case 8: CALL( 8 );             \
+        case 1: { CALL( 1 ); }         \
+        case 2: { CALL( 2 ); }         \
+        case 3: { CALL( 3 ); }         \
+        case 4: { CALL( 4 ); }         \
+        case 6: { CALL( 6 ); }         \
+        case 8: { CALL( 8 ); }         \
         default: break;                \
     }
 
@@ -899,12 +942,24 @@ cudaError_t launch_build_mask_lut( int scale, const CellTablePtrs& tab, uint32_t
     return cudaErrorInvalidValue;
 }
 
-size_t memo_entry_words( int scale )
+size_t smooth_entry_words( int scale )
 {
-#define PAR_EW( S ) return ( size_t )Memo< S >::ENTRY_WORDS
+#define PAR_EW( S ) return ( size_t )Entry< S >::EW
     PAR_FOR_SCALE( scale, PAR_EW )
 #undef PAR_EW
     return 0;
+}
+
+cudaError_t launch_build_smooth_tables( int scale, const CellTablePtrs& tab, const LinkClass* d_classes, int n_classes, uint64_t* cut, uint64_t* link,
+                                        cudaStream_t stream )
+{
+#define PAR_BUILD_SMOOTH( S )                                                                        \
+    build_cut_table_kernel< S ><<< kCellKeys * 16 / 128, 128, 0, stream >>>( tab, cut );             \
+    build_link_table_kernel< S ><<< n_classes, 256, 0, stream >>>( d_classes, link );                \
+    return cudaGetLastError()
+    PAR_FOR_SCALE( scale, PAR_BUILD_SMOOTH )
+#undef PAR_BUILD_SMOOTH
+    return cudaErrorInvalidValue;
 }
 
 void raster_tma_box( int scale, uint32_t box[ 3 ] )

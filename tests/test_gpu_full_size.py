@@ -1,7 +1,7 @@
 """BASELINE.json's full-size configurations, checked through size-independent properties (the oracle
 is only run on windows it finishes in seconds):
   C3  stream of 4096 256x224 frames in ONE batch == the same frames remastered one at a time on a fresh
-      context with the mask memo off; a sample of them == the oracle
+      context with the smoothing tables off; a sample of them == the oracle
   C4  one 4096x4096 map: 8 strips with aprons and stitched labels == the whole image on one context;
       random windows (with the exact 40-row/column apron) == the oracle
 """
@@ -37,8 +37,8 @@ def test_c3_stream_of_4096_frames(lib, oracle):
         src0 = (7 * a + 0) % 256
         twin = [k for k in range(256) if (7 * k + 1) % 256 == src0][0] + 256
         assert torch.equal(out["rgba"][a], out["rgba"][twin])
-    with lib.Remaster(0, W, H, 1) as fresh:                                     # no memo, one frame at a time
-        fresh.no_memo = True
+    with lib.Remaster(0, W, H, 1) as fresh:                                     # geometric path, one frame at a time
+        fresh.no_tables = True
         for k in (0, 777, 2048, 4095):
             one = fresh.remaster(frames[k:k + 1], scale=4, subdivide=True, want=("rgba", "graph"))
             assert torch.equal(one["rgba"][0], out["rgba"][k]) and torch.equal(one["graph"][0], out["graph"][k])

@@ -178,32 +178,33 @@ def test_exhaustive_yuv_words(ctx, oracle):
     del torch
 
 
-def test_mask_memo_is_invisible(lib, oracle):
-    """The mask memo caches a pure function (cell signature -> coverage mask): with it, without it
-    (PAR_FLAG_NO_MEMO), cold and warm, the image is the same and equals the oracle's."""
+def test_smoothing_tables_equal_the_geometric_path(lib, oracle):
+    """Stage E through the precomputed smoothing tables (XOR of CUT and LINK pieces) gives exactly the image of
+    the geometric path (PAR_FLAG_NO_SMOOTH_TABLES: polygon built and rasterized per cell) at every scale, on
+    ordinary frames, on the adversarial sprite and on raw noise, and both equal the oracle."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
-    frames_np = synth.snes_stream(6, 128, 96, first_seed=500)
-    frames = torch.from_numpy(frames_np).cuda()
-    with lib.Remaster(0, 128, 96, 6) as c:
-        cold = c.remaster(frames[:3], scale=4, subdivide=True)["rgba"].cpu().numpy()
-        st1 = c.memo_stats()
-        assert st1["lookups"] > 0 and st1["misses"] > 0 and 0 < st1["inserted"] <= st1["misses"]
-        warm = c.remaster(frames[:3], scale=4, subdivide=True)["rgba"].cpu().numpy()
-        st2 = c.memo_stats()
-        assert st2["misses"] - st1["misses"] < 0.02 * (st2["lookups"] - st1["lookups"])  # second pass: (almost) all hits
-        novel = c.remaster(frames[3:], scale=4, subdivide=True)["rgba"].cpu().numpy()  # unseen frames, warm table
-        st3 = c.memo_stats()
-        assert st3["misses"] - st2["misses"] < 0.5 * (st3["lookups"] - st2["lookups"])
-        c.no_memo = True
-        plain = c.remaster(frames, scale=4, subdivide=True)["rgba"].cpu().numpy()
-        assert c.memo_stats() == st3  # untouched
-    assert np.array_equal(cold, warm) and np.array_equal(cold, plain[:3]) and np.array_equal(novel, plain[3:])
-    for k in range(6):
-        assert np.array_equal(plain[k], oracle.pipeline(frames_np[k], scale=4, want=("raster",))["raster"])
-    with lib.Remaster(0, 128, 96, 6) as c:  # scale 8 uses the row-mask form of the memo
-        a8 = c.remaster(frames[:2], scale=8, subdivide=True)["rgba"].cpu().numpy()
-        b8 = c.remaster(frames[:2], scale=8, subdivide=True)["rgba"].cpu().numpy()
-        assert np.array_equal(a8, b8)
-        assert np.array_equal(a8[0], oracle.pipeline(frames_np[0], scale=8, want=("raster",))["raster"])
+    rng = np.random.default_rng(77)
+    pal = rng.integers(0, 256, (3, 3), dtype=np.uint8)
+    noise = pal[rng.integers(0, 3, (2, 96, 128))]                      # 3-colour noise: every key, not-found blends
+    noise[1, :, :] = (pal[rng.integers(0, 2, (96, 128))])              # 2-colour noise
+    sets = {"snes": synth.snes_stream(3, 128, 96, first_seed=500),
+            "adversarial": synth.adversarial_sprite(128, 96, 9)[None],
+            "noise": np.ascontiguousarray(noise)}
+    for name, frames_np in sets.items():
+        frames = torch.from_numpy(frames_np).cuda()
+        for scale in (1, 2, 3, 4, 6, 8):
+            with lib.Remaster(0, 128, 96, frames_np.shape[0]) as c:
+                tab = c.remaster(frames, scale=scale, subdivide=True)["rgba"].cpu().numpy()
+                st = c.smooth_stats()
+                assert st["smoothed"] > 0
+                if name == "snes":
+                    assert st["geometric"] < 0.01 * st["smoothed"], st       # the tables cover (almost) everything
+                c.no_tables = True
+                geo = c.remaster(frames, scale=scale, subdivide=True)["rgba"].cpu().numpy()
+                st2 = c.smooth_stats()
+                assert st2["geometric"] - st["geometric"] == st2["smoothed"] - st["smoothed"]
+            assert np.array_equal(tab, geo), (name, scale, int((tab != geo).any(-1).sum()))
+            if scale in (4, 8):
+                assert np.array_equal(tab[0], oracle.pipeline(frames_np[0], scale=scale, want=("raster",))["raster"]), (name, scale)

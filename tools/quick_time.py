@@ -34,8 +34,8 @@ g = ctx.resolve_crossings(aux)
 t = timeit(lambda: ctx.cc_labels(g)); print(f"K3 labels     : {t:.3f} ms  {5 * px / t / 1e6:,.1f} GB/s")
 for sub in (True, False):
     t = timeit(lambda: ctx.raster(frames, g, S, sub)); print(f"K4 raster sub={sub}: {t:.3f} ms  {(4 + 4 * S * S) * px / t / 1e6:,.1f} GB/s")
-print("memo", ctx.memo_stats())
-ctx.no_memo = True
-t = timeit(lambda: ctx.raster(frames, g, S, True)); print(f"K4 raster sub=True NO MEMO: {t:.3f} ms  {(4 + 4 * S * S) * px / t / 1e6:,.1f} GB/s")
-ctx.no_memo = False
+print("smooth", ctx.smooth_stats())
+ctx.no_tables = True
+t = timeit(lambda: ctx.raster(frames, g, S, True)); print(f"K4 raster sub=True NO TABLES: {t:.3f} ms  {(4 + 4 * S * S) * px / t / 1e6:,.1f} GB/s")
+ctx.no_tables = False
 t = timeit(lambda: out["rgba"].fill_(7)); print(f"memset rgba   : {t:.3f} ms  {4 * S * S * px / t / 1e6:,.1f} GB/s")

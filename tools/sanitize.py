@@ -10,7 +10,7 @@ for (W, H, S) in ((96, 80, 4), (50, 37, 8), (65, 33, 3)):
     with par.Remaster(0, W, H, 2) as ctx:
         for no_tma in (False, True):
             out = ctx.remaster(frames, S, True, want=("rgba", "graph", "graph_aux", "labels", "polygons"), no_tma=no_tma)
-            out = ctx.remaster(frames, S, True, want=("rgba",), no_tma=no_tma)  # memo hits
+            out = ctx.remaster(frames, S, True, want=("rgba",), no_tma=no_tma)  # smoothing tables
         torch.cuda.synchronize()
 img = synth.adversarial_sprite(96, 100, 3)
 par.launch_kernel(img, True)
