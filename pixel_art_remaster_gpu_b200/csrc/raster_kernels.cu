@@ -70,7 +70,21 @@ struct Cfg
     static constexpr int NC = CW * CH;
     static constexpr uint32_t FULL = ( 1u << S ) - 1u;
     static constexpr uint32_t ROWMASK = ( 1u << R ) - 1u;
-    static constexpr uint32_t WIDE = 0x80000000u;         // flag in the last word (PACK) / in row 0 (rows)
+    static constexpr uint32_t WIDE = PACK ? 0x40000000u : 0x80000000u; // flag in the high word (PACK, window form) / in row 0 (rows)
+    // PACK masks live in shared memory and in the tables in WINDOW form (to_window below): four 16-bit fields, each
+    // already positioned on the S x S output pixels (bit S*y + x) of the cell whose resolver will read it:
+    //   lo[0,16)  F0 the cell's own S x S samples
+    //   lo[16,32) F1 bit S*y+S-1 <- halo sample (-1, y): it lies in the LEFT neighbour's square, last column there;
+    //                bit S*y     <- halo sample (S, y): first column of the RIGHT neighbour's square
+    //   hi[0,16)  F2 bit S*(S-1)+x <- halo sample (x, -1): top row of the square BELOW; bit x <- (x, S): bottom row ABOVE
+    //   hi[16,32) F3 the four corner halo samples: bit S*S-1 <- (-1,-1), bit S*(S-1) <- (S,-1), bit S-1 <- (-1,S),
+    //                bit 0 <- (S,S); bit 14 = WIDE
+    static constexpr uint32_t ALL = PACK ? ( 1u << ( S * S ) ) - 1u : 0u;
+    static constexpr uint32_t M_COL0 = S == 1 ? 1u : ( S == 2 ? 0x5u : ( S == 3 ? 0x49u : 0x1111u ) ); // bits S*y, y < S
+    static constexpr uint32_t M_LEFTCOL = M_COL0;                       // my column 0   <- F1 of the cell to the left
+    static constexpr uint32_t M_RIGHTCOL = M_COL0 << ( S - 1 );         // my column S-1 <- F1 of the cell to the right
+    static constexpr uint32_t M_BOTROW = ( 1u << S ) - 1u;              // my row 0      <- F2 of the cell below
+    static constexpr uint32_t M_TOPROW = M_BOTROW << ( S * ( S - 1 ) ); // my row S-1    <- F2 of the cell above
     // shared memory carve-up (bytes)
     static constexpr int off_graph = 0;
     static constexpr int off_keys = off_graph + ( KH * GP + 127 ) / 128 * 128;
@@ -79,7 +93,7 @@ struct Cfg
     static constexpr int off_vbuf = ( off_mask + NC * MW * 4 + 127 ) / 128 * 128;
     static constexpr int off_raw = off_vbuf;              // the staged BGR rows are dead before the vertex buffers are used
     static constexpr int off_work = off_vbuf + kMaxVerts * kThreads * 2;
-    static constexpr int off_cflags = off_work + NC * 2 + 8;  // per cell: bits 0-3 corner kept, bit 4 guard
+    static constexpr int off_cflags = off_work + NC * 2 + 16; // per cell: bits 0-3 corner kept, bit 4 guard
     static constexpr int off_bar = ( off_cflags + NC + 15 ) / 16 * 16;
     static_assert( KH * RAWP <= kMaxVerts * kThreads * 2, "raw colour rows alias the vertex buffers" );
     static constexpr int smem_bytes = off_bar + 16;
@@ -136,6 +150,34 @@ struct RowToggle // rows in memory (shared memory on the fast path), row r at ro
     __device__ __forceinline__ void operator()( int r, int cnt ) { rows[ r * stride ] ^= ( 1u << cnt ) - 1u; }
 };
 
+// R-stride packed mask (bit R*r + c = sample (c - H, r - H)) -> window form (see Cfg)
+template< int S >
+__device__ __forceinline__ uint2 to_window( uint64_t m )
+{
+    typedef Cfg< S > C;
+    constexpr int R = C::R, H = C::H;
+    uint32_t f0 = 0u, f1 = 0u, f2 = 0u, f3 = 0u;
+#pragma unroll
+    for( int y = 0; y < S; y++ )
+    {
+        const uint32_t row = ( uint32_t )( m >> ( R * ( y + H ) ) );
+        f0 |= ( ( row >> H ) & C::FULL ) << ( S * y );
+        if( H > 0 )
+        {
+            f1 |= ( row & 1u ) << ( S * y + S - 1 );
+            f1 |= ( ( row >> ( S + H ) ) & 1u ) << ( S * y );
+        }
+    }
+    if( H > 0 )
+    {
+        const uint32_t bot = ( uint32_t )m, top = ( uint32_t )( m >> ( R * ( S + H ) ) );
+        f2 = ( ( ( bot >> H ) & C::FULL ) << ( S * ( S - 1 ) ) ) | ( ( top >> H ) & C::FULL );
+        f3 = ( ( bot & 1u ) << ( S * S - 1 ) ) | ( ( ( bot >> ( S + H ) ) & 1u ) << ( S * ( S - 1 ) ) ) | ( ( top & 1u ) << ( S - 1 ) ) |
+             ( ( top >> ( S + H ) ) & 1u );
+    }
+    return make_uint2( f0 | f1 << 16, f2 | f3 << 16 );
+}
+
 // Slots of build_cell_polygon in a small buffer (slot k at buf[k * stride]), packed as (x64 + 64) << 8 | (y64 + 64)
 struct PackedSlots
 {
@@ -176,6 +218,27 @@ __device__ __forceinline__ void cover_polygon( const uint16_t* buf, int stride, 
         if( done ) break;
         x0 = x1;
         y0 = y1;
+    }
+}
+
+// one output row segment of a source pixel: S RGBA words, widest stores the alignment allows
+template< int S >
+__device__ __forceinline__ void store_row( uint8_t* dst, const uint32_t* px )
+{
+    if( S % 4 == 0 )
+    {
+#pragma unroll
+        for( int k = 0; k < S; k += 4 ) st_stream_v4( dst + 4 * k, make_uint4( px[ k ], px[ k + 1 ], px[ k + 2 ], px[ k + 3 ] ) );
+    }
+    else if( S % 2 == 0 )
+    {
+#pragma unroll
+        for( int k = 0; k < S; k += 2 ) *reinterpret_cast< uint2* >( dst + 4 * k ) = make_uint2( px[ k ], px[ k + 1 ] );
+    }
+    else
+    {
+#pragma unroll
+        for( int k = 0; k < S; k++ ) *reinterpret_cast< uint32_t* >( dst + 4 * k ) = px[ k ];
     }
 }
 
@@ -242,8 +305,9 @@ __global__ void build_mask_lut_kernel( CellTablePtrs tab, uint32_t* lut )
     {
         PackedToggle< C::R > tg{ 0ull };
         cover_polygon< S, C::R >( verts, 1, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
-        lut[ 2 * key ] = ( uint32_t )tg.m;
-        lut[ 2 * key + 1 ] = ( uint32_t )( tg.m >> 32 );
+        const uint2 w = to_window< S >( tg.m );
+        lut[ 2 * key ] = w.x;
+        lut[ 2 * key + 1 ] = w.y;
     }
     else
     {
@@ -256,13 +320,13 @@ __global__ void build_mask_lut_kernel( CellTablePtrs tab, uint32_t* lut )
 }
 
 // ---- smoothing tables (smooth_table.h) -------------------------------------------------------------
-// Table entry = the coverage mask as 64-bit words: PACK -> one word, bit 63 = wide; rows -> R 16-bit rows,
-// four per word, wide flag in bit 15 of row 0.
+// Table entry = the coverage mask as 64-bit words: PACK -> one word in window form (wide flag = Cfg::WIDE of the
+// high half); rows -> R 16-bit rows, four per word, wide flag in bit 15 of row 0.
 template< int S >
 struct Entry
 {
     static constexpr int EW = Cfg< S >::PACK ? 1 : ( Cfg< S >::R * 2 + 7 ) / 8;
-    static constexpr uint64_t FLAG = Cfg< S >::PACK ? ( 1ull << 63 ) : ( 1ull << 15 );
+    static constexpr uint64_t FLAG = Cfg< S >::PACK ? ( ( uint64_t )Cfg< S >::WIDE << 32 ) : ( 1ull << 15 );
 };
 
 // coverage of the closed polygon (xs[k], ys[k]), k < m (1/64 px, cell-local), as a table entry
@@ -285,7 +349,8 @@ __device__ void cover_to_entry( const int* xs, const int* ys, int m, uint64_t* o
             const int k1 = k + 1 == m ? 0 : k + 1;
             cover_edge< S, C::R >( C::S_FIRST, C::S_FIRST, xs[ k ] * C::VM, ys[ k ] * C::VM, xs[ k1 ] * C::VM, ys[ k1 ] * C::VM, tg );
         }
-        out[ 0 ] = tg.m | ( wide ? Entry< S >::FLAG : 0ull );
+        const uint2 w = to_window< S >( tg.m );
+        out[ 0 ] = ( ( uint64_t )w.y << 32 | w.x ) | ( wide ? Entry< S >::FLAG : 0ull );
     }
     else
     {
@@ -507,7 +572,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
     const uint8_t* graph = a.graph + ( size_t )f * frame_px;
 
     // (1) stage graph bytes: rows y0-2 .. y0+TH+1, columns x0-16 .. x0-16+GP-1; zero outside the image
-    if( tid < 2 ) s_nwork[ tid ] = 0;
+    if( tid < 3 ) s_nwork[ tid ] = 0; // [0] geometric work items, [1] smoothed cells, [2] PACK: some cell of the tile is wide
     if( kUseTma )
     {
         if( tid == 0 )
@@ -535,7 +600,19 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
         }
     }
     // colours of the tile + halo 2 as RGBA words (kernel.cu:98-101: R = byte 2, G = byte 1, B = byte 0);
-    // pixels outside the image hold colour 0 (the reference's reads beyond the last row see zeros)
+    // pixels outside the image hold colour 0 (the reference's reads beyond the last row see zeros), except the two
+    // virtual columns x = -1 and x = width: checkTJunction addresses the pixels around a corner as FLAT byte
+    // offsets idx +- widthstep +- 3 (subdivision_functions.cu:195-202), so for the first / last pixel of a row "the
+    // pixel to the left / right" is the three bytes just before / after the row (the end of the previous row, the
+    // start of the next one, or row padding; zero beyond the end of the image, SURVEY App. B-3 contract).
+    auto virtual_colour = [ & ]( int gx, int gy ) -> uint32_t {
+        const long end = ( long )a.height * a.widthstep;
+        const long at = ( long )gy * a.widthstep + 3L * gx;
+        uint32_t b[ 3 ];
+#pragma unroll
+        for( int k = 0; k < 3; k++ ) b[ k ] = ( at + k >= 0 && at + k < end ) ? ( uint32_t )__ldg( frame + at + k ) : 0u;
+        return b[ 2 ] | b[ 1 ] << 8 | b[ 0 ] << 16 | 0xFF000000u;
+    };
     if( kUseTma )
     {
         mbar_wait( s_bar, 0 );
@@ -546,7 +623,8 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
             int gx = x0 - 2 + cx, gy = y0 - 2 + cy;
             const uint8_t* p = s_raw + cy * C::RAWP + C::RAWOFF + 3 * cx;
             uint32_t w = ( uint32_t )p[ 2 ] | ( uint32_t )p[ 1 ] << 8 | ( uint32_t )p[ 0 ] << 16 | 0xFF000000u;
-            if( gx < 0 || gy < 0 || gx >= a.width || gy >= a.height ) w = 0xFF000000u; // (row padding bytes are not colours)
+            if( gx < 0 || gy < 0 || gx >= a.width || gy >= a.height ) // (row padding bytes are not colours)
+                w = ( gx == -1 || gx == a.width ) ? virtual_colour( gx, gy ) : 0xFF000000u;
             s_col[ idx ] = w;
         }
     }
@@ -562,6 +640,8 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                 const uint8_t* p = frame + ( size_t )gy * a.widthstep + 3 * gx;
                 w = ( uint32_t )__ldg( p + 2 ) | ( uint32_t )__ldg( p + 1 ) << 8 | ( uint32_t )__ldg( p ) << 16 | 0xFF000000u;
             }
+            else if( gx == -1 || gx == a.width )
+                w = virtual_colour( gx, gy );
             s_col[ idx ] = w;
         }
     }
@@ -608,20 +688,13 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
             uint32_t cf = 0u;
             if( env.guard( gx, gy ) )
                 cf = 16u;
-            else if( gx >= 1 && gx <= a.width - 2 )
+            else
             {
                 const uint32_t* c = s_col + ( cy + 1 ) * C::KW + ( cx + 1 );
                 const uint32_t l = c[ -1 ], r = c[ 1 ], d = c[ -C::KW ], u = c[ C::KW ];
                 const uint32_t dl = c[ -C::KW - 1 ], dr = c[ -C::KW + 1 ], ul = c[ C::KW - 1 ], ur = c[ C::KW + 1 ];
                 cf = ( ( l != dl || dl != d ) ? 1u : 0u ) | ( ( r != dr || dr != d ) ? 2u : 0u ) | ( ( r != ur || ur != u ) ? 4u : 0u ) |
                      ( ( l != ul || ul != u ) ? 8u : 0u );
-            }
-            else
-            {
-                const Q2 corner[ 4 ] = { { 0, 0 }, { 4, 0 }, { 4, 4 }, { 0, 4 } };
-#pragma unroll
-                for( int c = 0; c < 4; c++ )
-                    if( env.img.keep_corner( gx, gy, corner[ c ] ) ) cf |= 1u << c; // flat byte offsets wrap at the first/last column
             }
             s_cflags[ idx ] = ( uint8_t )cf;
         }
@@ -657,7 +730,10 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
             if( use_tables && smooth_lookup< S >( a.smooth, a.mask_lut, kc, *kc, s_cflags[ idx ], mw, wide ) )
             {
                 if( C::PACK )
+                {
                     reinterpret_cast< uint2* >( s_mask )[ idx ] = make_uint2( ( uint32_t )mw[ 0 ], ( uint32_t )( mw[ 0 ] >> 32 ) | ( wide ? C::WIDE : 0u ) );
+                    if( wide ) s_nwork[ 2 ] = 1;
+                }
                 else
                 {
 #pragma unroll
@@ -692,7 +768,10 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                 cover_polygon< S, C::R >( vbuf, kThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
                 // reach check: every sample outside the mask must be strictly outside the polygon's bounding box
                 const uint32_t wide = ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
-                reinterpret_cast< uint2* >( s_mask )[ idx ] = make_uint2( ( uint32_t )tg.m, ( uint32_t )( tg.m >> 32 ) | wide );
+                uint2 wm = to_window< S >( tg.m );
+                wm.y |= wide;
+                reinterpret_cast< uint2* >( s_mask )[ idx ] = wm;
+                if( wide ) s_nwork[ 2 ] = 1;
             }
             else
             {
@@ -715,109 +794,188 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
     // (3) resolve and write: one thread per source pixel, S output rows of S pixels each
     const size_t out_w = ( size_t )a.width * S, out_h = ( size_t )a.height * S;
     uint8_t* out = a.rgba + ( size_t )f * out_w * out_h * 4;
-    for( int idx = tid; idx < C::TW * C::TH; idx += kThreads )
+    if constexpr( C::PACK )
     {
-        int ly = idx / C::TW, lx = idx - ly * C::TW;
-        int gx = x0 + lx, gy = y0 + ly;
-        if( gx >= a.width || gy >= a.height ) continue;
-        const int cell = ( ly + 1 ) * C::CW + ( lx + 1 );
-        const uint32_t* col = s_col + ( ly + 2 ) * C::KW + ( lx + 2 );
-        // the 3x3 neighbourhood's masks; candidates are visited in DESCENDING node index:
-        // (dj,di) = (+1,+1) (+1,0) (+1,-1) (0,+1) (0,0) (0,-1) (-1,+1) (-1,0) (-1,-1)
-        uint64_t pm[ C::PACK ? 9 : 1 ];
-        uint32_t wide = 0;
-        if( C::PACK )
+        // Window form: every candidate's coverage of my S x S output pixels is one masked 16-bit field of its
+        // mask, so the priority resolve runs once on whole-cell bit sets instead of once per output row.
+        const bool tile_wide = s_nwork[ 2 ] != 0 || a.debug_force_wide;
+        for( int idx = tid; idx < C::TW * C::TH; idx += kThreads )
         {
+            int ly = idx / C::TW, lx = idx - ly * C::TW;
+            int gx = x0 + lx, gy = y0 + ly;
+            if( gx >= a.width || gy >= a.height ) continue;
+            const uint2* mk = reinterpret_cast< const uint2* >( s_mask ) + ( ly + 1 ) * C::CW + ( lx + 1 );
+            const uint32_t* col = s_col + ( ly + 2 ) * C::KW + ( lx + 2 );
+            // candidates in DESCENDING node index: (dj,di) = (+1,+1) (+1,0) (+1,-1) (0,+1) (0,0) (0,-1) (-1,+1) (-1,0) (-1,-1)
+            uint32_t cov[ 9 ];
+            bool slow = false;
+            if( tile_wide )
+            {
+                uint32_t wide = 0u;
 #pragma unroll
-            for( int dj = -1; dj <= 1; dj++ )
+                for( int dj = -1; dj <= 1; dj++ )
 #pragma unroll
-                for( int di = -1; di <= 1; di++ )
+                    for( int di = -1; di <= 1; di++ ) wide |= mk[ dj * C::CW + di ].y;
+                slow = ( wide & C::WIDE ) != 0u;
+            }
+            if( !slow )
+            {
+                cov[ 0 ] = ( mk[ C::CW + 1 ].y >> 16 ) & ( 1u << ( S * S - 1 ) );
+                cov[ 1 ] = mk[ C::CW ].y & C::M_TOPROW;
+                cov[ 2 ] = ( mk[ C::CW - 1 ].y >> 16 ) & ( 1u << ( S * ( S - 1 ) ) );
+                cov[ 3 ] = ( mk[ 1 ].x >> 16 ) & C::M_RIGHTCOL;
+                cov[ 4 ] = mk[ 0 ].x & C::ALL;
+                cov[ 5 ] = ( mk[ -1 ].x >> 16 ) & C::M_LEFTCOL;
+                cov[ 6 ] = ( mk[ -C::CW + 1 ].y >> 16 ) & ( 1u << ( S - 1 ) );
+                cov[ 7 ] = mk[ -C::CW ].y & C::M_BOTROW;
+                cov[ 8 ] = ( mk[ -C::CW - 1 ].y >> 16 ) & 1u;
+                if( C::H == 0 ) // no halo samples at this scale: only the cell itself can cover its pixels
+                    cov[ 0 ] = cov[ 1 ] = cov[ 2 ] = cov[ 3 ] = cov[ 5 ] = cov[ 6 ] = cov[ 7 ] = cov[ 8 ] = 0u;
+            }
+            else
+            {
+                // some cell around reaches beyond its mask: recompute every candidate's coverage exactly
+                int k = 0;
+                for( int dj = 1; dj >= -1; dj-- )
+                    for( int di = 1; di >= -1; di--, k++ )
+                    {
+                        const int ci = gx + di, cj = gy + dj;
+                        cov[ k ] = 0u;
+                        if( ci < 0 || cj < 0 || ci >= a.width || cj >= a.height ) continue;
+                        uint32_t win[ S ];
+                        window_coverage< S >( env, tab, ci, cj, di, dj, subdivide, win );
+                        for( int r = 0; r < S; r++ ) cov[ k ] |= win[ r ] << ( S * r );
+                    }
+            }
+            uint32_t rem = C::ALL, take[ 9 ];
+#pragma unroll
+            for( int k = 0; k < 9; k++ )
+            {
+                take[ k ] = cov[ k ] & rem;
+                rem &= ~cov[ k ];
+            }
+            uint32_t px[ S * S ];
+            const uint32_t own = col[ 0 ];
+#pragma unroll
+            for( int k = 0; k < S * S; k++ ) px[ k ] = own;
+            if( slow )
+            {
+                // after the exact path a candidate may hold any pixel of the cell
+#pragma unroll 1
+                for( int k = 0; k < 9; k++ )
                 {
-                    const uint2 m = reinterpret_cast< const uint2* >( s_mask )[ cell + dj * C::CW + di ];
-                    wide |= m.y;
-                    pm[ ( dj + 1 ) * 3 + di + 1 ] = ( ( uint64_t )( m.y & ~C::WIDE ) << 32 ) | m.x;
+                    const uint32_t cw = col[ ( 1 - k / 3 ) * C::KW + 1 - k % 3 ];
+#pragma unroll
+                    for( int bit = 0; bit < S * S; bit++ )
+                        if( ( take[ k ] >> bit ) & 1u ) px[ bit ] = cw;
                 }
+#pragma unroll
+                for( int bit = 0; bit < S * S; bit++ )
+                    if( ( rem >> bit ) & 1u ) px[ bit ] = 0xFF000000u;
+            }
+            else if( take[ 4 ] != C::ALL )
+            {
+#pragma unroll
+                for( int k = 0; k < 9; k++ )
+                {
+                    if( k == 4 || take[ k ] == 0u ) continue;
+                    const int dj = 1 - k / 3, di = 1 - k % 3;
+                    const uint32_t cw = col[ dj * C::KW + di ];
+                    // a candidate can only hold pixels of its own window
+#pragma unroll
+                    for( int bit = 0; bit < S * S; bit++ )
+                    {
+                        const int bx = bit % S, by = bit / S;
+                        const bool in_window = ( di == 0 || bx == ( di > 0 ? S - 1 : 0 ) ) && ( dj == 0 || by == ( dj > 0 ? S - 1 : 0 ) );
+                        if( in_window && ( ( take[ k ] >> bit ) & 1u ) ) px[ bit ] = cw;
+                    }
+                }
+                if( rem ) // nobody covers these: background (main.cpp:260)
+                {
+#pragma unroll
+                    for( int bit = 0; bit < S * S; bit++ )
+                        if( ( rem >> bit ) & 1u ) px[ bit ] = 0xFF000000u;
+                }
+            }
+#pragma unroll
+            for( int b = 0; b < S; b++ )
+            {
+                const size_t oy = a.flip_output ? ( out_h - 1 - ( ( size_t )gy * S + b ) ) : ( ( size_t )gy * S + b );
+                store_row< S >( out + ( oy * out_w + ( size_t )gx * S ) * 4, px + S * b );
+            }
         }
-        else
+    }
+    else
+    {
+        for( int idx = tid; idx < C::TW * C::TH; idx += kThreads )
         {
+            int ly = idx / C::TW, lx = idx - ly * C::TW;
+            int gx = x0 + lx, gy = y0 + ly;
+            if( gx >= a.width || gy >= a.height ) continue;
+            const int cell = ( ly + 1 ) * C::CW + ( lx + 1 );
+            const uint32_t* col = s_col + ( ly + 2 ) * C::KW + ( lx + 2 );
+            // the 3x3 neighbourhood's masks; candidates are visited in DESCENDING node index:
+            // (dj,di) = (+1,+1) (+1,0) (+1,-1) (0,+1) (0,0) (0,-1) (-1,+1) (-1,0) (-1,-1)
+            uint32_t wide = 0;
 #pragma unroll
             for( int dj = -1; dj <= 1; dj++ )
 #pragma unroll
                 for( int di = -1; di <= 1; di++ ) wide |= s_mask[ cell + dj * C::CW + di ];
-        }
-        wide &= C::WIDE;
-#pragma unroll( C::PACK ? S : 1 )
-        for( int b = 0; b < S; b++ )
-        {
-            uint32_t px[ S ];
-#pragma unroll
-            for( int k = 0; k < S; k++ ) px[ k ] = 0xFF000000u; // background (main.cpp:260)
-            uint32_t rem = C::FULL;
-            if( !wide )
+            wide &= C::WIDE;
+#pragma unroll 1
+            for( int b = 0; b < S; b++ )
             {
+                uint32_t px[ S ];
 #pragma unroll
-                for( int dj = 1; dj >= -1; dj-- )
+                for( int k = 0; k < S; k++ ) px[ k ] = 0xFF000000u; // background (main.cpp:260)
+                uint32_t rem = C::FULL;
+                if( !wide )
                 {
-                    const int ky = b - dj * S + C::H;
-                    if( ky < 0 || ky >= C::R ) continue;
 #pragma unroll
-                    for( int di = 1; di >= -1; di-- )
+                    for( int dj = 1; dj >= -1; dj-- )
                     {
-                        uint32_t m;
-                        if( C::PACK )
-                            m = ( uint32_t )( pm[ ( dj + 1 ) * 3 + di + 1 ] >> ( C::R * ky ) ) & C::ROWMASK;
-                        else
-                            m = s_mask[ ky * C::NC + cell + dj * C::CW + di ] & ~C::WIDE;
-                        const uint32_t field = di == 0 ? ( m >> C::H ) : ( di > 0 ? ( m << ( S - C::H ) ) : ( m >> ( S + C::H ) ) );
-                        const uint32_t take = field & rem;
-                        if( take )
-                        {
-                            const uint32_t cw = col[ dj * C::KW + di ];
+                        const int ky = b - dj * S + C::H;
+                        if( ky < 0 || ky >= C::R ) continue;
 #pragma unroll
-                            for( int k = 0; k < S; k++ )
-                                if( ( take >> k ) & 1u ) px[ k ] = cw;
-                            rem &= ~take;
+                        for( int di = 1; di >= -1; di-- )
+                        {
+                            const uint32_t m = s_mask[ ky * C::NC + cell + dj * C::CW + di ] & ~C::WIDE;
+                            const uint32_t field = di == 0 ? ( m >> C::H ) : ( di > 0 ? ( m << ( S - C::H ) ) : ( m >> ( S + C::H ) ) );
+                            const uint32_t take = field & rem;
+                            if( take )
+                            {
+                                const uint32_t cw = col[ dj * C::KW + di ];
+#pragma unroll
+                                for( int k = 0; k < S; k++ )
+                                    if( ( take >> k ) & 1u ) px[ k ] = cw;
+                                rem &= ~take;
+                            }
                         }
                     }
                 }
-            }
-            else
-            {
-                // some cell around reaches beyond its mask: recompute every candidate's coverage of this row exactly
-                for( int dj = 1; dj >= -1; dj-- )
-                    for( int di = 1; di >= -1; di-- )
-                    {
-                        const int ci = gx + di, cj = gy + dj;
-                        if( ci < 0 || cj < 0 || ci >= a.width || cj >= a.height ) continue;
-                        uint32_t win[ S ];
-                        window_coverage< S >( env, tab, ci, cj, di, dj, subdivide, win );
-                        const uint32_t take = win[ b ] & rem;
-                        if( take )
+                else
+                {
+                    // some cell around reaches beyond its mask: recompute every candidate's coverage of this row exactly
+                    for( int dj = 1; dj >= -1; dj-- )
+                        for( int di = 1; di >= -1; di-- )
                         {
-                            const uint32_t cw = col[ dj * C::KW + di ];
+                            const int ci = gx + di, cj = gy + dj;
+                            if( ci < 0 || cj < 0 || ci >= a.width || cj >= a.height ) continue;
+                            uint32_t win[ S ];
+                            window_coverage< S >( env, tab, ci, cj, di, dj, subdivide, win );
+                            const uint32_t take = win[ b ] & rem;
+                            if( take )
+                            {
+                                const uint32_t cw = col[ dj * C::KW + di ];
 #pragma unroll
-                            for( int k = 0; k < S; k++ )
-                                if( ( take >> k ) & 1u ) px[ k ] = cw;
-                            rem &= ~take;
+                                for( int k = 0; k < S; k++ )
+                                    if( ( take >> k ) & 1u ) px[ k ] = cw;
+                                rem &= ~take;
+                            }
                         }
-                    }
-            }
-            const size_t oy = a.flip_output ? ( out_h - 1 - ( ( size_t )gy * S + b ) ) : ( ( size_t )gy * S + b );
-            uint8_t* dst = out + ( oy * out_w + ( size_t )gx * S ) * 4;
-            if( S % 4 == 0 )
-            {
-#pragma unroll
-                for( int k = 0; k < S; k += 4 ) st_stream_v4( dst + 4 * k, make_uint4( px[ k ], px[ k + 1 ], px[ k + 2 ], px[ k + 3 ] ) );
-            }
-            else if( S % 2 == 0 )
-            {
-#pragma unroll
-                for( int k = 0; k < S; k += 2 ) *reinterpret_cast< uint2* >( dst + 4 * k ) = make_uint2( px[ k ], px[ k + 1 ] );
-            }
-            else
-            {
-#pragma unroll
-                for( int k = 0; k < S; k++ ) *reinterpret_cast< uint32_t* >( dst + 4 * k ) = px[ k ];
+                }
+                const size_t oy = a.flip_output ? ( out_h - 1 - ( ( size_t )gy * S + b ) ) : ( ( size_t )gy * S + b );
+                store_row< S >( out + ( oy * out_w + ( size_t )gx * S ) * 4, px );
             }
         }
     }
