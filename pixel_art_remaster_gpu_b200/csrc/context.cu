@@ -46,7 +46,7 @@ struct par_context
     uint32_t* d_mask_lut[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // per scale, built on first use
     // smoothing tables (smooth_table.h): link descriptors + neighbour bytes + class list (scale-independent), CUT / LINK masks per scale
     uint4* d_smooth_rec = nullptr;
-    uint8_t* d_smooth_nbr = nullptr;
+    uint16_t* d_smooth_nbr = nullptr;
     LinkClass* d_link_classes = nullptr;
     int n_link_classes = 0;
     uint32_t link_entries = 0;

@@ -33,7 +33,7 @@ struct LabelArgs
 struct SmoothTablePtrs
 {
     const uint4* rec;     // [kCellKeys] link descriptors
-    const uint8_t* nbr;   // [kCellKeys][16] neighbour bytes
+    const uint16_t* nbr;  // [kCellKeys][8] neighbour records
     const uint64_t* cut;  // [kCellKeys][16] entries
     const uint64_t* link; // [link_entries] entries
 };

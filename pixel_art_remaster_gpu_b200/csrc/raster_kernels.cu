@@ -221,6 +221,17 @@ __device__ __forceinline__ void cover_polygon( const uint16_t* buf, int stride, 
     }
 }
 
+// next free slot of a shared-memory list, for the lanes that call it together: one atomic per warp
+__device__ __forceinline__ int warp_slot( int* counter )
+{
+    const uint32_t peers = __activemask();
+    const uint32_t lane = threadIdx.x & 31u;
+    int base = 0;
+    if( lane == ( uint32_t )__ffs( ( int )peers ) - 1u ) base = atomicAdd( counter, __popc( peers ) );
+    base = __shfl_sync( peers, base, __ffs( ( int )peers ) - 1 );
+    return base + __popc( peers & ( ( 1u << lane ) - 1u ) );
+}
+
 // one output row segment of a source pixel: S RGBA words, widest stores the alignment allows
 template< int S >
 __device__ __forceinline__ void store_row( uint8_t* dst, const uint32_t* px )
@@ -269,10 +280,21 @@ struct TileEnv
 // slow path of the resolve step: coverage of the S x S samples of target cell (ti,tj) by the polygon of
 // cell (ci,cj) = (ti+di, tj+dj), recomputed from scratch (exact for any reach < 1 pixel)
 template< int S >
-__device__ __noinline__ void window_coverage( const TileEnv< S >& env, const CellTablePtrs& tab, int ci, int cj, int di, int dj, bool subdivide,
-                                              uint32_t* win )
+__device__ __noinline__ void window_coverage( const uint16_t* keys, const uint32_t* cols, int x0, int y0, const uint8_t* frame, int width, int height,
+                                              int widthstep, const CellRecord* rec, int ci, int cj, int di, int dj, bool subdivide, uint32_t* win )
 {
     typedef Cfg< S > C;
+    // (everything by value: a reference to the caller's TileEnv would force it into local memory on the fast path too)
+    TileEnv< S > env;
+    env.keys = keys;
+    env.cols = cols;
+    env.x0 = x0;
+    env.y0 = y0;
+    env.img.frame = frame;
+    env.img.width = width;
+    env.img.height = height;
+    env.img.widthstep = widthstep;
+    const CellTablePtrs tab{ rec };
     uint16_t verts[ kMaxVerts ];
     PackedSlots slots{ verts, 1 };
     const CellPoly poly = build_cell_polygon( env, tab, ci, cj, env.key( ci, cj ), subdivide, slots );
@@ -280,6 +302,17 @@ __device__ __noinline__ void window_coverage( const TileEnv< S >& env, const Cel
     RowToggle tg{ win, 1 };
     int lo, hi;
     cover_polygon< S, S >( verts, 1, poly, C::SSP / 2 - di * C::SQUARE, C::SSP / 2 - dj * C::SQUARE, tg, lo, hi );
+}
+
+// the same as one bit set over the S x S pixels of the target cell (bit S*y + x), S <= 4
+template< int S >
+__device__ __noinline__ uint32_t window_coverage_bits( const uint16_t* keys, const uint32_t* cols, int x0, int y0, const uint8_t* frame, int width,
+                                                       int height, int widthstep, const CellRecord* rec, int ci, int cj, int di, int dj, bool subdivide )
+{
+    uint32_t win[ S ], bits = 0u;
+    window_coverage< S >( keys, cols, x0, y0, frame, width, height, widthstep, rec, ci, cj, di, dj, subdivide, win );
+    for( int r = 0; r < S; r++ ) bits |= win[ r ] << ( S * r );
+    return bits;
 }
 
 // mask of a cell whose polygon is its plain hull, for every key: the per-scale table the raster kernel copies from
@@ -434,7 +467,7 @@ __global__ void build_link_table_kernel( const LinkClass* classes, uint64_t* lin
     const LinkClass c = classes[ blockIdx.x ];
     const int sub = threadIdx.x;
     if( sub >= ( int )c.count ) return;
-    const int a = ( c.hasA && c.hasB ) ? sub >> 4 : sub, b = ( c.hasA && c.hasB ) ? sub & 15 : sub;
+    const int a = ( c.hasA && c.hasB ) ? sub & 15 : sub, b = ( c.hasA && c.hasB ) ? sub >> 4 : sub;
     const int di = edge_di( c.e ), dj = edge_dj( c.e );
     const Q2 P0{ c.px[ 0 ], c.py[ 0 ] }, P1{ c.px[ 1 ], c.py[ 1 ] }, P2{ c.px[ 2 ], c.py[ 2 ] }, P3{ c.px[ 3 ], c.py[ 3 ] };
     int xs[ 6 ], ys[ 6 ], m = 0;
@@ -511,35 +544,42 @@ __device__ __forceinline__ bool smooth_lookup( const SmoothTablePtrs& st, const 
 #pragma unroll
         for( int w = 0; w < E::EW; w++ ) m[ w ] = __ldg( e + w );
     }
+    // All four descriptor slots are processed without branches (a warp runs as long as its busiest lane anyway, and
+    // the loads of the four slots overlap); an unused slot (0) loads nothing.
     bool ok = rec.x != kSmoothSlow;
-    const uint32_t links[ 4 ] = { rec.x, rec.y, rec.z, rec.w };
+    const uint32_t links[ 4 ] = { ok ? rec.x : 0u, rec.y, rec.z, rec.w };
+    uint32_t nb[ kMaxLinks ];
 #pragma unroll
     for( int k = 0; k < kMaxLinks; k++ )
     {
         const uint32_t d = links[ k ];
-        if( d == 0u || !ok ) break;
-        const int e = ( int )( d & 7u );
-        const uint32_t nkey = keys_at_cell[ edge_dj( e ) * C::KW + edge_di( e ) ];
-        const uint8_t* nb = st.nbr + nkey * 16u;
-        const uint32_t codeA = ( d >> 5 ) & 15u, codeB = ( d >> 9 ) & 15u;
-        uint32_t sub = 0u;
-        if( d & 8u )
-        {
-            const uint32_t a = ( uint32_t )__ldg( nb + codeA ) & 15u;
-            ok = ok && a != codeA;
-            sub = a;
-        }
-        if( d & 16u )
-        {
-            const uint32_t b = ( uint32_t )__ldg( nb + codeB ) >> 4;
-            ok = ok && b != codeB;
-            sub = ( d & 8u ) ? sub * 16u + b : b;
-        }
+        const uint32_t e = d & 7u;
+        // neighbour across graph edge e: offset in the key tile, one signed byte per edge
+        constexpr int KW = C::KW;
+        constexpr uint32_t off_lo = ( uint32_t )( uint8_t )( KW - 1 ) | ( uint32_t )( uint8_t )( KW ) << 8 | ( uint32_t )( uint8_t )( KW + 1 ) << 16 |
+                                    ( uint32_t )( uint8_t )( -1 ) << 24;
+        constexpr uint32_t off_hi = ( uint32_t )( uint8_t )( 1 ) | ( uint32_t )( uint8_t )( -KW - 1 ) << 8 | ( uint32_t )( uint8_t )( -KW ) << 16 |
+                                    ( uint32_t )( uint8_t )( -KW + 1 ) << 24;
+        const int koff = ( int )( int8_t )__byte_perm( off_lo, off_hi, e );
+        const uint32_t nkey = keys_at_cell[ koff ];
+        nb[ k ] = d ? ( uint32_t )__ldg( st.nbr + nkey * 8u + ( 7u - e ) ) : 0u;
+    }
+#pragma unroll
+    for( int k = 0; k < kMaxLinks; k++ )
+    {
+        const uint32_t d = links[ k ];
+        const bool hasA = ( d & 8u ) != 0u, hasB = ( d & 16u ) != 0u;
+        // the blended vertices must be the end (A) / start (B) of the neighbour's edge
+        const uint32_t must = ( hasA ? 0x0F00u : 0u ) | ( hasB ? 0xF000u : 0u );
+        const uint32_t r = nb[ k ];
+        const bool match = ( ( ( r ^ ( d << 3 ) ) & must ) == 0u ) && ( ( ( r >> 8 ) ^ ( r >> 12 ) ) & 15u ) != 0u; // (d << 3: codeA -> [8,12), codeB -> [12,16))
+        ok = ok && ( d == 0u || match );
+        const uint32_t sub = ( hasA ? r : r >> 4 ) & ( ( hasA && hasB ) ? 255u : 15u );
         const uint64_t* le = st.link + ( size_t )( ( d >> 13 ) + sub ) * E::EW;
 #pragma unroll
         for( int w = 0; w < E::EW; w++ )
         {
-            const uint64_t v = __ldg( le + w );
+            const uint64_t v = d ? __ldg( le + w ) : 0ull;
             if( w == 0 ) flags |= v;
             m[ w ] ^= v;
         }
@@ -551,7 +591,7 @@ __device__ __forceinline__ bool smooth_lookup( const SmoothTablePtrs& st, const 
 }
 
 template< int S, bool kUseTma >
-__global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_constant__ CUtensorMap graph_map, const __grid_constant__ CUtensorMap img_map,
+__global__ void __launch_bounds__( kThreads, S <= 4 ? 4 : 3 ) raster_kernel( const __grid_constant__ CUtensorMap graph_map, const __grid_constant__ CUtensorMap img_map,
                                                            RasterArgs a )
 {
     typedef Cfg< S > C;
@@ -559,7 +599,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
     uint8_t* s_graph = smem + C::off_graph;
     uint16_t* s_keys = reinterpret_cast< uint16_t* >( smem + C::off_keys );
     uint32_t* s_col = reinterpret_cast< uint32_t* >( smem + C::off_col );
-    uint32_t* s_mask = reinterpret_cast< uint32_t* >( smem + C::off_mask );   // PACK: [NC][2]; rows: [R][NC]
+    uint32_t* s_mask = reinterpret_cast< uint32_t* >( smem + C::off_mask );   // PACK: [2][NC]; rows: [R][NC]
     uint16_t* s_vbuf = reinterpret_cast< uint16_t* >( smem + C::off_vbuf );   // [kMaxVerts][kThreads]
     uint16_t* s_work = reinterpret_cast< uint16_t* >( smem + C::off_work );   // cells that need the general path
     int* s_nwork = reinterpret_cast< int* >( smem + C::off_work + C::NC * 2 );
@@ -683,7 +723,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
         const bool plain = !subdivide || ( key & 0xFFu ) == 90u;
         if( inside && !plain )
         {
-            s_gen[ atomicAdd( s_nwork + 1, 1 ) ] = ( uint16_t )idx;
+            s_gen[ warp_slot( s_nwork + 1 ) ] = ( uint16_t )idx;
             // checkTJunction for the four corners of the pixel square, once per cell and with every lane busy
             uint32_t cf = 0u;
             if( env.guard( gx, gy ) )
@@ -706,7 +746,8 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                 m = __ldg( reinterpret_cast< const uint2* >( a.mask_lut ) + key );
                 m.y |= force_wide;
             }
-            reinterpret_cast< uint2* >( s_mask )[ idx ] = m;
+            s_mask[ idx ] = m.x; // (PACK: the two halves live in separate arrays, conflict-free 32-bit accesses)
+            s_mask[ C::NC + idx ] = m.y;
         }
         else
         {
@@ -731,7 +772,8 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
             {
                 if( C::PACK )
                 {
-                    reinterpret_cast< uint2* >( s_mask )[ idx ] = make_uint2( ( uint32_t )mw[ 0 ], ( uint32_t )( mw[ 0 ] >> 32 ) | ( wide ? C::WIDE : 0u ) );
+                    s_mask[ idx ] = ( uint32_t )mw[ 0 ];
+                    s_mask[ C::NC + idx ] = ( uint32_t )( mw[ 0 ] >> 32 ) | ( wide ? C::WIDE : 0u );
                     if( wide ) s_nwork[ 2 ] = 1;
                 }
                 else
@@ -745,7 +787,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                 }
             }
             else
-                s_work[ atomicAdd( s_nwork, 1 ) ] = ( uint16_t )idx;
+                s_work[ warp_slot( s_nwork ) ] = ( uint16_t )idx;
         }
     }
     __syncthreads();
@@ -770,7 +812,8 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                 const uint32_t wide = ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
                 uint2 wm = to_window< S >( tg.m );
                 wm.y |= wide;
-                reinterpret_cast< uint2* >( s_mask )[ idx ] = wm;
+                s_mask[ idx ] = wm.x;
+                s_mask[ C::NC + idx ] = wm.y;
                 if( wide ) s_nwork[ 2 ] = 1;
             }
             else
@@ -794,6 +837,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
     // (3) resolve and write: one thread per source pixel, S output rows of S pixels each
     const size_t out_w = ( size_t )a.width * S, out_h = ( size_t )a.height * S;
     uint8_t* out = a.rgba + ( size_t )f * out_w * out_h * 4;
+    const ptrdiff_t row_step = a.flip_output ? -( ptrdiff_t )( out_w * 4 ) : ( ptrdiff_t )( out_w * 4 ); // bytes from one output row to the next
     if constexpr( C::PACK )
     {
         // Window form: every candidate's coverage of my S x S output pixels is one masked 16-bit field of its
@@ -804,7 +848,8 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
             int ly = idx / C::TW, lx = idx - ly * C::TW;
             int gx = x0 + lx, gy = y0 + ly;
             if( gx >= a.width || gy >= a.height ) continue;
-            const uint2* mk = reinterpret_cast< const uint2* >( s_mask ) + ( ly + 1 ) * C::CW + ( lx + 1 );
+            const uint32_t* mlo = s_mask + ( ly + 1 ) * C::CW + ( lx + 1 ); // F0 | F1 << 16
+            const uint32_t* mhi = mlo + C::NC;                             // F2 | F3 << 16
             const uint32_t* col = s_col + ( ly + 2 ) * C::KW + ( lx + 2 );
             // candidates in DESCENDING node index: (dj,di) = (+1,+1) (+1,0) (+1,-1) (0,+1) (0,0) (0,-1) (-1,+1) (-1,0) (-1,-1)
             uint32_t cov[ 9 ];
@@ -815,79 +860,84 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
 #pragma unroll
                 for( int dj = -1; dj <= 1; dj++ )
 #pragma unroll
-                    for( int di = -1; di <= 1; di++ ) wide |= mk[ dj * C::CW + di ].y;
+                    for( int di = -1; di <= 1; di++ ) wide |= mhi[ dj * C::CW + di ];
                 slow = ( wide & C::WIDE ) != 0u;
-            }
-            if( !slow )
-            {
-                cov[ 0 ] = ( mk[ C::CW + 1 ].y >> 16 ) & ( 1u << ( S * S - 1 ) );
-                cov[ 1 ] = mk[ C::CW ].y & C::M_TOPROW;
-                cov[ 2 ] = ( mk[ C::CW - 1 ].y >> 16 ) & ( 1u << ( S * ( S - 1 ) ) );
-                cov[ 3 ] = ( mk[ 1 ].x >> 16 ) & C::M_RIGHTCOL;
-                cov[ 4 ] = mk[ 0 ].x & C::ALL;
-                cov[ 5 ] = ( mk[ -1 ].x >> 16 ) & C::M_LEFTCOL;
-                cov[ 6 ] = ( mk[ -C::CW + 1 ].y >> 16 ) & ( 1u << ( S - 1 ) );
-                cov[ 7 ] = mk[ -C::CW ].y & C::M_BOTROW;
-                cov[ 8 ] = ( mk[ -C::CW - 1 ].y >> 16 ) & 1u;
-                if( C::H == 0 ) // no halo samples at this scale: only the cell itself can cover its pixels
-                    cov[ 0 ] = cov[ 1 ] = cov[ 2 ] = cov[ 3 ] = cov[ 5 ] = cov[ 6 ] = cov[ 7 ] = cov[ 8 ] = 0u;
-            }
-            else
-            {
-                // some cell around reaches beyond its mask: recompute every candidate's coverage exactly
-                int k = 0;
-                for( int dj = 1; dj >= -1; dj-- )
-                    for( int di = 1; di >= -1; di--, k++ )
-                    {
-                        const int ci = gx + di, cj = gy + dj;
-                        cov[ k ] = 0u;
-                        if( ci < 0 || cj < 0 || ci >= a.width || cj >= a.height ) continue;
-                        uint32_t win[ S ];
-                        window_coverage< S >( env, tab, ci, cj, di, dj, subdivide, win );
-                        for( int r = 0; r < S; r++ ) cov[ k ] |= win[ r ] << ( S * r );
-                    }
-            }
-            uint32_t rem = C::ALL, take[ 9 ];
-#pragma unroll
-            for( int k = 0; k < 9; k++ )
-            {
-                take[ k ] = cov[ k ] & rem;
-                rem &= ~cov[ k ];
             }
             uint32_t px[ S * S ];
             const uint32_t own = col[ 0 ];
 #pragma unroll
             for( int k = 0; k < S * S; k++ ) px[ k ] = own;
-            if( slow )
+            bool done = false;
+            if( !slow )
             {
-                // after the exact path a candidate may hold any pixel of the cell
-#pragma unroll 1
-                for( int k = 0; k < 9; k++ )
+                // the four candidates drawn after this cell, then the cell itself: most pixels are settled here
+                cov[ 0 ] = ( mhi[ C::CW + 1 ] >> 16 ) & ( 1u << ( S * S - 1 ) );
+                cov[ 1 ] = mhi[ C::CW ] & C::M_TOPROW;
+                cov[ 2 ] = ( mhi[ C::CW - 1 ] >> 16 ) & ( 1u << ( S * ( S - 1 ) ) );
+                cov[ 3 ] = ( mlo[ 1 ] >> 16 ) & C::M_RIGHTCOL;
+                cov[ 4 ] = mlo[ 0 ] & C::ALL;
+                if( C::H == 0 ) cov[ 0 ] = cov[ 1 ] = cov[ 2 ] = cov[ 3 ] = 0u; // no halo samples at this scale
+                done = ( cov[ 4 ] & ~( cov[ 0 ] | cov[ 1 ] | cov[ 2 ] | cov[ 3 ] ) ) == C::ALL;
+                if( !done )
                 {
-                    const uint32_t cw = col[ ( 1 - k / 3 ) * C::KW + 1 - k % 3 ];
-#pragma unroll
-                    for( int bit = 0; bit < S * S; bit++ )
-                        if( ( take[ k ] >> bit ) & 1u ) px[ bit ] = cw;
+                    cov[ 5 ] = ( mlo[ -1 ] >> 16 ) & C::M_LEFTCOL;
+                    cov[ 6 ] = ( mhi[ -C::CW + 1 ] >> 16 ) & ( 1u << ( S - 1 ) );
+                    cov[ 7 ] = mhi[ -C::CW ] & C::M_BOTROW;
+                    cov[ 8 ] = ( mhi[ -C::CW - 1 ] >> 16 ) & 1u;
+                    if( C::H == 0 ) cov[ 5 ] = cov[ 6 ] = cov[ 7 ] = cov[ 8 ] = 0u;
                 }
-#pragma unroll
-                for( int bit = 0; bit < S * S; bit++ )
-                    if( ( rem >> bit ) & 1u ) px[ bit ] = 0xFF000000u;
             }
-            else if( take[ 4 ] != C::ALL )
+            else
             {
+                // some cell around reaches beyond its mask: recompute every candidate's coverage exactly
+#pragma unroll
+                for( int k = 0; k < 9; k++ ) // (unrolled: cov[] must stay in registers)
+                {
+                    const int dj = 1 - k / 3, di = 1 - k % 3;
+                    const int ci = gx + di, cj = gy + dj;
+                    cov[ k ] = 0u;
+                    if( ci < 0 || cj < 0 || ci >= a.width || cj >= a.height ) continue;
+                    cov[ k ] = window_coverage_bits< S >( s_keys, s_col, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, ci, cj, di, dj, subdivide );
+                }
+            }
+            if( !done )
+            {
+                uint32_t rem = C::ALL, take[ 9 ];
 #pragma unroll
                 for( int k = 0; k < 9; k++ )
                 {
-                    if( k == 4 || take[ k ] == 0u ) continue;
-                    const int dj = 1 - k / 3, di = 1 - k % 3;
-                    const uint32_t cw = col[ dj * C::KW + di ];
-                    // a candidate can only hold pixels of its own window
+                    take[ k ] = cov[ k ] & rem;
+                    rem &= ~cov[ k ];
+                }
+                if( slow )
+                {
+                    // after the exact path a candidate may hold any pixel of the cell
 #pragma unroll
-                    for( int bit = 0; bit < S * S; bit++ )
+                    for( int k = 0; k < 9; k++ )
                     {
-                        const int bx = bit % S, by = bit / S;
-                        const bool in_window = ( di == 0 || bx == ( di > 0 ? S - 1 : 0 ) ) && ( dj == 0 || by == ( dj > 0 ? S - 1 : 0 ) );
-                        if( in_window && ( ( take[ k ] >> bit ) & 1u ) ) px[ bit ] = cw;
+                        if( take[ k ] == 0u ) continue;
+                        const uint32_t cw = col[ ( 1 - k / 3 ) * C::KW + 1 - k % 3 ];
+#pragma unroll
+                        for( int bit = 0; bit < S * S; bit++ )
+                            if( ( take[ k ] >> bit ) & 1u ) px[ bit ] = cw;
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for( int k = 0; k < 9; k++ )
+                    {
+                        if( k == 4 || take[ k ] == 0u ) continue;
+                        const int dj = 1 - k / 3, di = 1 - k % 3;
+                        const uint32_t cw = col[ dj * C::KW + di ];
+                        // a candidate can only hold pixels of its own window
+#pragma unroll
+                        for( int bit = 0; bit < S * S; bit++ )
+                        {
+                            const int bx = bit % S, by = bit / S;
+                            const bool in_window = ( di == 0 || bx == ( di > 0 ? S - 1 : 0 ) ) && ( dj == 0 || by == ( dj > 0 ? S - 1 : 0 ) );
+                            if( in_window && ( ( take[ k ] >> bit ) & 1u ) ) px[ bit ] = cw;
+                        }
                     }
                 }
                 if( rem ) // nobody covers these: background (main.cpp:260)
@@ -897,12 +947,9 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                         if( ( rem >> bit ) & 1u ) px[ bit ] = 0xFF000000u;
                 }
             }
+            uint8_t* dst = out + ( ( size_t )( a.flip_output ? out_h - 1 - ( size_t )gy * S : ( size_t )gy * S ) * out_w + ( size_t )gx * S ) * 4;
 #pragma unroll
-            for( int b = 0; b < S; b++ )
-            {
-                const size_t oy = a.flip_output ? ( out_h - 1 - ( ( size_t )gy * S + b ) ) : ( ( size_t )gy * S + b );
-                store_row< S >( out + ( oy * out_w + ( size_t )gx * S ) * 4, px + S * b );
-            }
+            for( int b = 0; b < S; b++ ) store_row< S >( dst + ( ptrdiff_t )b * row_step, px + S * b );
         }
     }
     else
@@ -962,7 +1009,7 @@ __global__ void __launch_bounds__( kThreads ) raster_kernel( const __grid_consta
                             const int ci = gx + di, cj = gy + dj;
                             if( ci < 0 || cj < 0 || ci >= a.width || cj >= a.height ) continue;
                             uint32_t win[ S ];
-                            window_coverage< S >( env, tab, ci, cj, di, dj, subdivide, win );
+                            window_coverage< S >( s_keys, s_col, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, ci, cj, di, dj, subdivide, win );
                             const uint32_t take = win[ b ] & rem;
                             if( take )
                             {

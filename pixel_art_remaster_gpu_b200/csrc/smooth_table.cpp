@@ -1,5 +1,5 @@
 // Host-side construction of the smoothing tables (see smooth_table.h): per key the link descriptors, per
-// (key, point code) the neighbour byte, and the list of link classes the device turns into masks.
+// (key, link direction) the neighbour record, and the list of link classes the device turns into masks.
 #include "smooth_table.h"
 #include <map>
 #include <string.h>
@@ -44,19 +44,15 @@ void build_smooth_tables( const CellTables& cells, SmoothTables* out )
     {
         const CellRecord& r = cells.rec[ key ];
         const Hull h = hull_of( r );
-        // neighbour bytes: for every point code the codes of the hull vertices after / before the vertex there
-        for( int code = 0; code < 16; code++ )
+        // neighbour records: for every link direction the hull edge shared through it, and the vertices around it
+        for( int e = 0; e < 8; e++ ) out->nbr[ key ][ e ] = 0; // start == end: no such edge
+        for( int t = 0; t < h.n; t++ )
         {
-            const int op = ( int )( ( r.index >> ( 4 * code ) ) & 15u );
-            const bool found = point_code( h.x[ op ], h.y[ op ] ) == code;
-            int next = code, prev = code;
-            if( found )
-            {
-                const int a = ( op + 1 ) % h.n, b = ( op + h.n - 1 ) % h.n;
-                next = point_code( h.x[ a ], h.y[ a ] );
-                prev = point_code( h.x[ b ], h.y[ b ] );
-            }
-            out->nbr[ key ][ code ] = ( uint8_t )( next | prev << 4 );
+            if( h.border[ t ] ) continue;
+            const int tn = ( t + 1 ) % h.n, tnn = ( t + 2 ) % h.n, tp = ( t + h.n - 1 ) % h.n;
+            const int start = point_code( h.x[ t ], h.y[ t ] ), end = point_code( h.x[ tn ], h.y[ tn ] );
+            const int after = point_code( h.x[ tnn ], h.y[ tnn ] ), before = point_code( h.x[ tp ], h.y[ tp ] );
+            out->nbr[ key ][ h.link[ t ] ] = ( uint16_t )( after | before << 4 | end << 8 | start << 12 );
         }
         // link descriptors
         int n_links = 0;

@@ -15,10 +15,15 @@
 //   the vertex after (end A, neighbour's Q, :141-154) / before (end B, neighbour's R, :125-138) the shared
 //   vertex in the neighbour across the edge, given as a 4-bit point code a / b.
 //
-// The neighbour side is one byte per (neighbour key, point code): NBR[key][code] = next | prev << 4, the
-// point codes of the hull vertices after / before the vertex sitting at `code`; when the neighbour has no
-// vertex there (getPointIndex's "not found -> 0" fallback, :527-538) both nibbles repeat `code` itself,
-// which no real successor can equal, and the cell takes the exact geometric path instead.
+// The neighbour side is 16 bits per (neighbour key, link direction): NBR[key][e'] describes the neighbour's hull
+// edge that is shared through ITS graph edge e' = 7 - e (a hull has at most one per direction):
+//     bits [0,4)  a = point code of the vertex AFTER the edge's end      (what end A needs)
+//     bits [4,8)  b = point code of the vertex BEFORE the edge's start   (what end B needs)
+//     bits [8,12) point code of the edge's end, bits [12,16) of its start; start == end: no such edge.
+// The cell's blended vertex must BE that end (A) / start (B) — the reference finds it by coordinates
+// (getPointIndex, :527-538) and then takes the vertex after / before it, which is the same thing whenever it
+// is there.  When it is not (codes differ, or no such edge: getPointIndex's "not found -> 0" fallback and a few
+// consistent-but-unusual hull pairs) the cell takes the exact geometric path instead.
 //
 // Everything here is content-independent and built once per context (the masks per scale, on the device,
 // by the same coverage code the geometric path uses).
@@ -34,7 +39,7 @@ namespace par {
 //   [4]     hasB  the vertex the edge ends at is blended (edge after it is a border edge)
 //   [5,9)   codeA the start vertex as a point code in the neighbour's frame
 //   [9,13)  codeB the end vertex as a point code in the neighbour's frame
-//   [13,32) first entry of the class in the link table; entry = first + (hasA && hasB ? 16 a + b : hasA ? a : b)
+//   [13,32) first entry of the class in the link table; entry = first + (hasA && hasB ? a + 16 b : hasA ? a : b)
 constexpr int kMaxLinks = 4;
 constexpr uint32_t kSmoothSlow = 0xFFFFFFFFu; // in link[0]: this key always takes the geometric path
 
@@ -55,7 +60,7 @@ struct LinkClass
 struct SmoothTables
 {
     SmoothRecord rec[ kCellKeys ];
-    uint8_t nbr[ kCellKeys ][ 16 ];
+    uint16_t nbr[ kCellKeys ][ 8 ];
     std::vector< LinkClass > classes;
     uint32_t link_entries = 0; // total entries of the link table
     uint32_t slow_keys = 0;    // keys that always take the geometric path
