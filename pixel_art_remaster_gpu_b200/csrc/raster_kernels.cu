@@ -655,17 +655,33 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 4 : 3 ) raster_kernel( con
     };
     if( kUseTma )
     {
+        // Four pixels per thread from aligned 32-bit words of the staged rows: byte permutes build the RGBA words
+        // and the cell keys (left/right neighbour bits, kernel.cu:204-207), 128- / 64-bit stores.  TMA zero-filled
+        // everything outside the image (row padding included), which is exactly "colour 0" / "no links".
         mbar_wait( s_bar, 0 );
-        const uint8_t* s_raw = smem + C::off_raw;
-        for( int idx = tid; idx < C::KW * C::KH; idx += kThreads )
+        static_assert( C::KW % 4 == 0 && C::RAWOFF == 10 && C::GOFF == 16, "group layout of the vectorised staging pass" );
+        constexpr int QW = C::KW / 4;
+        const int vl = x0 == 0 ? 1 : -1, vr = a.width - x0 + 2; // tile columns of the virtual colour columns x = -1, x = width
+        for( int idx = tid; idx < QW * C::KH; idx += kThreads )
         {
-            int cy = idx / C::KW, cx = idx - cy * C::KW;
-            int gx = x0 - 2 + cx, gy = y0 - 2 + cy;
-            const uint8_t* p = s_raw + cy * C::RAWP + C::RAWOFF + 3 * cx;
-            uint32_t w = ( uint32_t )p[ 2 ] | ( uint32_t )p[ 1 ] << 8 | ( uint32_t )p[ 0 ] << 16 | 0xFF000000u;
-            if( gx < 0 || gy < 0 || gx >= a.width || gy >= a.height ) // (row padding bytes are not colours)
-                w = ( gx == -1 || gx == a.width ) ? virtual_colour( gx, gy ) : 0xFF000000u;
-            s_col[ idx ] = w;
+            const int cy = idx / QW, q = idx - cy * QW;
+            const uint32_t* rw = reinterpret_cast< const uint32_t* >( smem + C::off_raw + cy * C::RAWP + 8 + 12 * q ); // pixel 4q starts at byte 10 + 12 q
+            const uint32_t w0 = rw[ 0 ], w1 = rw[ 1 ], w2 = rw[ 2 ], w3 = rw[ 3 ];
+            uint32_t c[ 4 ] = { __byte_perm( w0, w1, 0x2234 ) | 0xFF000000u, __byte_perm( w1, w1, 0x1123 ) | 0xFF000000u,
+                                __byte_perm( w2, w2, 0x0012 ) | 0xFF000000u, __byte_perm( w2, w3, 0x3345 ) | 0xFF000000u };
+            if( ( vl >> 2 ) == q || ( vr >> 2 ) == q )
+            {
+#pragma unroll
+                for( int k = 0; k < 4; k++ )
+                    if( 4 * q + k == vl || 4 * q + k == vr ) c[ k ] = virtual_colour( x0 - 2 + 4 * q + k, y0 - 2 + cy );
+            }
+            *reinterpret_cast< uint4* >( s_col + cy * C::KW + 4 * q ) = make_uint4( c[ 0 ], c[ 1 ], c[ 2 ], c[ 3 ] );
+            const uint32_t* gw = reinterpret_cast< const uint32_t* >( s_graph + cy * C::GP + C::GOFF - 4 + 4 * q ); // cell 4q sits at staged column 14 + 4 q
+            const uint32_t g0 = gw[ 0 ], g1 = gw[ 1 ];
+            const uint32_t node = __byte_perm( g0, g1, 0x5432 ), left = __byte_perm( g0, g1, 0x4321 ), right = __byte_perm( g0, g1, 0x6543 );
+            const uint32_t high = ( ( left >> 2 ) & 0x01010101u ) | ( ( left >> 6 ) & 0x02020202u ) | ( ( right << 2 ) & 0x04040404u ) |
+                                  ( ( right >> 2 ) & 0x08080808u ); // cell_key's bits 8..11, one byte per cell
+            *reinterpret_cast< uint2* >( s_keys + cy * C::KW + 4 * q ) = make_uint2( __byte_perm( node, high, 0x5140 ), __byte_perm( node, high, 0x7362 ) );
         }
     }
     else
@@ -684,15 +700,14 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 4 : 3 ) raster_kernel( con
                 w = virtual_colour( gx, gy );
             s_col[ idx ] = w;
         }
-    }
-    __syncthreads();
-
-    // cell keys for tile + halo 2 (left/right neighbour bits, kernel.cu:204-207; zero outside the row)
-    for( int idx = tid; idx < C::KW * C::KH; idx += kThreads )
-    {
-        int ky = idx / C::KW, kx = idx - ky * C::KW;
-        const uint8_t* g = s_graph + ky * C::GP + kx + C::GOFF - 2; // column x0-2+kx sits at staged column kx+GOFF-2
-        s_keys[ idx ] = ( uint16_t )cell_key( g[ 0 ], g[ -1 ], g[ 1 ] );
+        __syncthreads();
+        // cell keys for tile + halo 2 (left/right neighbour bits, kernel.cu:204-207; zero outside the row)
+        for( int idx = tid; idx < C::KW * C::KH; idx += kThreads )
+        {
+            int ky = idx / C::KW, kx = idx - ky * C::KW;
+            const uint8_t* g = s_graph + ky * C::GP + kx + C::GOFF - 2; // column x0-2+kx sits at staged column kx+GOFF-2
+            s_keys[ idx ] = ( uint16_t )cell_key( g[ 0 ], g[ -1 ], g[ 1 ] );
+        }
     }
     __syncthreads();
 
