@@ -32,9 +32,10 @@ enum : uint8_t { kNone = 0, kSlashDies = 1, kBackslashDies = 2, kPending = 3 };
 struct __align__( 128 ) CrossSmem
 {
     uint8_t aux[ kAH * kAuxPitch ];
-    uint8_t dec[ kBH * kDecPitch ];
-    uint16_t work[ kBH * kBW ];
-    int n_work;
+    alignas( 4 ) uint8_t dec[ kBH * kDecPitch ];
+    uint16_t amb[ kBH * kDecPitch ]; // ambiguous blocks (index into dec)
+    uint16_t work[ kBH * kBW ];      // ... of which need the curve-length walks (index r * kBW + c)
+    int n_amb, n_work;
     uint64_t bar;
 };
 
@@ -68,7 +69,11 @@ __global__ void __launch_bounds__( kThreads ) resolve_crossings_kernel( const __
     const size_t frame_px = ( size_t )a.width * a.height;
     const uint8_t* aux_g = a.graph_aux + ( size_t )f * frame_px;
 
-    if( tid == 0 ) s.n_work = 0;
+    if( tid == 0 )
+    {
+        s.n_amb = 0;
+        s.n_work = 0;
+    }
     if( kUseTma )
     {
         if( tid == 0 )
@@ -97,17 +102,40 @@ __global__ void __launch_bounds__( kThreads ) resolve_crossings_kernel( const __
         __syncthreads();
     }
 
-    // one decision per 2x2 block; block (c,r) has its lower-left pixel at staged position (c,r)
-    for( int idx = tid; idx < kBH * kBW; idx += kThreads )
+    // one decision per 2x2 block; block (c,r) has its lower-left pixel at staged position (c,r).  Four blocks per
+    // step: a block is ambiguous iff both of its diagonals survived stage B — "/" is bit 2 of i1 and bit 5 of i4,
+    // "\" is bit 7 of i2 and bit 0 of i3 (graph_functions.cu:1476-1512 guards) — which is one AND over byte-shifted
+    // words.  Ambiguous blocks are queued so that the rules below run with full warps.
+    static_assert( kAuxOff == 15 && kAuxPitch % 4 == 0 && kDecPitch % 4 == 0, "word layout of the block pass" );
+    for( int idx = tid; idx < kBH * ( kDecPitch / 4 ); idx += kThreads )
     {
-        int r = idx / kBW, c = idx - r * kBW;
-        const uint8_t* row0 = &s.aux[ r * kAuxPitch + kAuxOff + c ];
-        uint32_t i1 = row0[ 0 ], i3 = row0[ 1 ];
-        uint32_t i2 = row0[ kAuxPitch ], i4 = row0[ kAuxPitch + 1 ];
-        uint8_t d = kNone;
-        if( ( i1 & 4u ) && ( i2 & 128u ) && ( i3 & 1u ) && ( i4 & 32u ) ) // graph_functions.cu:1476-1512 guards
+        const int r = idx / ( kDecPitch / 4 ), c0 = ( idx - r * ( kDecPitch / 4 ) ) * 4;
+        const uint32_t* w0 = reinterpret_cast< const uint32_t* >( &s.aux[ r * kAuxPitch + 12 + c0 ] ); // pixel c0 is byte 3 of this word
+        const uint32_t* w1 = reinterpret_cast< const uint32_t* >( &s.aux[ ( r + 1 ) * kAuxPitch + 12 + c0 ] );
+        const uint32_t a1 = w0[ 1 ], b1 = w1[ 1 ];                                                 // pixels c0+1 .. c0+4 of both rows
+        const uint32_t a0 = __byte_perm( w0[ 0 ], a1, 0x6543 ), b0 = __byte_perm( w1[ 0 ], b1, 0x6543 ); // pixels c0 .. c0+3
+        uint32_t amb = ( a0 >> 2 ) & ( b0 >> 7 ) & a1 & ( b1 >> 5 ) & 0x01010101u;
+        if( c0 + 3 >= kBW ) amb &= 0xFFFFFFFFu >> ( 8 * ( c0 + 4 - kBW ) ); // the last group holds fewer than four blocks
+        *reinterpret_cast< uint32_t* >( &s.dec[ r * kDecPitch + c0 ] ) = 0u;
+        if( amb )
         {
-            int o1 = others( i1, 2 ), o4 = others( i4, 5 ), o3 = others( i3, 0 ), o2 = others( i2, 7 );
+            const int n = __popc( amb );
+            int slot = atomicAdd( &s.n_amb, n );
+#pragma unroll 1
+            for( ; amb; amb &= amb - 1u ) s.amb[ slot++ ] = ( uint16_t )( r * kDecPitch + c0 + ( ( __ffs( ( int )amb ) - 1 ) >> 3 ) );
+        }
+    }
+    __syncthreads();
+    // the four local rules of processHeuristics2 (graph_functions.cu:781-809); what falls through is queued for the walks
+    {
+        const int n_amb = s.n_amb;
+        for( int w = tid; w < n_amb; w += kThreads )
+        {
+            const int at = s.amb[ w ], r = at / kDecPitch, c = at - r * kDecPitch;
+            const uint8_t* row0 = &s.aux[ r * kAuxPitch + kAuxOff + c ];
+            const uint32_t i1 = row0[ 0 ], i3 = row0[ 1 ], i2 = row0[ kAuxPitch ], i4 = row0[ kAuxPitch + 1 ];
+            const int o1 = others( i1, 2 ), o4 = others( i4, 5 ), o3 = others( i3, 0 ), o2 = others( i2, 7 );
+            uint8_t d;
             if( o1 == 1 && o4 == 1 ) d = kBackslashDies;                                      // :781-785
             else if( o3 == 1 && o2 == 1 ) d = kSlashDies;                                     // :791-795
             else if( ( o1 == 0 || o4 == 0 ) && o3 != 0 && o2 != 0 ) d = kBackslashDies;       // :798-802
@@ -115,10 +143,10 @@ __global__ void __launch_bounds__( kThreads ) resolve_crossings_kernel( const __
             else
             {
                 d = kPending;
-                s.work[ atomicAdd( &s.n_work, 1 ) ] = ( uint16_t )idx;
+                s.work[ atomicAdd( &s.n_work, 1 ) ] = ( uint16_t )( r * kBW + c );
             }
+            s.dec[ at ] = d;
         }
-        s.dec[ r * kDecPitch + c ] = d;
     }
     __syncthreads();
 
@@ -162,17 +190,17 @@ __global__ void __launch_bounds__( kThreads ) resolve_crossings_kernel( const __
         const uint8_t* up = &s.dec[ ( ly + 1 ) * kDecPitch + lx ];
         const uint8_t* dn = &s.dec[ ly * kDecPitch + lx ];
         const uint8_t* px = &s.aux[ ( ly + 1 ) * kAuxPitch + kAuxOff + lx + 1 ];
-        uint32_t bytes = 0;
-#pragma unroll
-        for( int k = 0; k < 4; k++ )
-        {
-            uint32_t b = px[ k ];
-            if( up[ k ] == kBackslashDies ) b &= ~1u;       // pixel is i3 of its up-left block
-            if( up[ k + 1 ] == kSlashDies ) b &= ~4u;       // pixel is i1 of its up-right block
-            if( dn[ k ] == kSlashDies ) b &= ~32u;          // pixel is i4 of its down-left block
-            if( dn[ k + 1 ] == kBackslashDies ) b &= ~128u; // pixel is i2 of its down-right block
-            bytes |= b << ( 8 * k );
-        }
+        // decisions are 0 (none), 1 ("/" dies) or 2 ("\" dies) by now: bit 0 / bit 1 of the decision byte, tested on all
+        // four pixels at once.  Up-left / down-left blocks of pixel lx+k are decision columns lx+k, up-right / down-right lx+k+1.
+        const uint32_t* upw = reinterpret_cast< const uint32_t* >( up );
+        const uint32_t* dnw = reinterpret_cast< const uint32_t* >( dn );
+        const uint32_t ul = upw[ 0 ], dl = dnw[ 0 ];
+        const uint32_t ur = __byte_perm( ul, upw[ 1 ], 0x4321 ), dr = __byte_perm( dl, dnw[ 1 ], 0x4321 );
+        const uint32_t dead = ( ( ul >> 1 ) & 0x01010101u )    // "\" of the up-left block dies: pixel is its i3, bit 0
+                              | ( ( ur << 2 ) & 0x04040404u )  // "/" of the up-right block dies: pixel is its i1, bit 2
+                              | ( ( dl << 5 ) & 0x20202020u )  // "/" of the down-left block dies: pixel is its i4, bit 5
+                              | ( ( dr << 6 ) & 0x80808080u ); // "\" of the down-right block dies: pixel is its i2, bit 7
+        const uint32_t bytes = *reinterpret_cast< const uint32_t* >( px ) & ~dead; // (staged column of pixel lx is 16 + lx: word aligned)
         size_t o = ( size_t )gy * a.width + gx;
         if( word_ok && gx + 3 < a.width )
             *reinterpret_cast< uint32_t* >( out + o ) = bytes;

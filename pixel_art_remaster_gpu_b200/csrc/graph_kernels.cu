@@ -20,22 +20,28 @@ namespace par {
 namespace {
 
 constexpr int kTW = 64, kTH = 32;            // pixels per tile
-constexpr int kYW = kTW + 2, kYH = kTH + 2;  // pixels whose colour is needed (halo 1)
-constexpr int kRawOff = 13;                  // TMA needs a 16-byte aligned start: rows begin at byte 3*x0 - 16
+constexpr int kYW = kTW + 2, kYH = kTH + 2;  // pixels whose colour is needed (halo 1); pixel column c = x - (x0 - 1)
+constexpr int kRawOff = 13;                  // TMA needs a 16-byte aligned start: rows begin at byte 3*x0 - 16, pixel c at 13 + 3c
 constexpr int kRawPitch = 224;               // bytes per staged row: 13 + 3*66 = 211 rounded up to 16
-constexpr int kYuvPitch = kYW + 1;           // words
-constexpr int kBW = kTW + 1, kBH = kTH + 1;  // 2x2 blocks per tile (one extra column/row at left/bottom)
-constexpr int kBlkPitch = 68;                // bytes
+// Everything after staging works on groups of FOUR pixel columns c = 4g-3 .. 4g (g = 0..17), stored at index c + 3
+// so that a group is one aligned 16-byte (YUV words) / 4-byte (block bytes) unit; the group's 12 raw bytes start
+// at byte 13 + 3(4g-3) = 4 + 12g, which is word aligned as well.
+constexpr int kGroups = 18;
+constexpr int kYuvPitch = 4 * kGroups;       // words
+constexpr int kBH = kTH + 1;                 // 2x2 block rows per tile (block (c,r): lower-left pixel (c,r), c = 0..64)
+constexpr int kBlkGroups = 17;               // block columns 4g-3 .. 4g, g = 0..16
+constexpr int kBlkPitch = 4 * kGroups;       // bytes
 constexpr int kThreads = 256;
 constexpr uint32_t kInvalid = 0x80000000u;   // pixel outside the image
 
 static_assert( kRawPitch >= kRawOff + 3 * kYW && kRawPitch % 16 == 0, "TMA box rows are multiples of 16 bytes" );
+static_assert( 4 + 12 * kGroups <= kRawPitch, "the last group's raw bytes are inside the staged row" );
 
 struct __align__( 128 ) GraphSmem
 {
     uint8_t raw[ kYH * kRawPitch ];
-    uint32_t yuv[ kYH * kYuvPitch ];
-    uint8_t blk[ kBH * kBlkPitch ];
+    alignas( 16 ) uint32_t yuv[ kYH * kYuvPitch ];
+    alignas( 16 ) uint8_t blk[ kBH * kBlkPitch ];
     uint64_t bar;
 };
 
@@ -89,45 +95,57 @@ __global__ void __launch_bounds__( kThreads ) similarity_graph_kernel( const __g
         __syncthreads();
     }
 
-    // packed YUV word per pixel, once
-    for( int idx = tid, r = tid / kYW, c = tid % kYW; idx < kYH * kYW; idx += kThreads )
+    // packed YUV word per pixel, once; four pixels (three raw words) per step, one 128-bit store
+    for( int idx = tid; idx < kYH * kGroups; idx += kThreads )
     {
-        int gx = x0 - 1 + c, gy = y0 - 1 + r;
-        const uint8_t* p = &s.raw[ r * kRawPitch + kRawOff + 3 * c ];
-        uint32_t w = yuv_word( p[ 0 ], p[ 1 ], p[ 2 ] ) & 0x00FFFFFFu;
-        if( gx < 0 || gy < 0 || gx >= a.width || gy >= a.height ) w = kInvalid;
-        s.yuv[ r * kYuvPitch + c ] = w;
-        c += kThreads % kYW; // next element of this thread, without a division
-        r += kThreads / kYW;
-        if( c >= kYW )
+        const int r = idx / kGroups, g = idx - r * kGroups;
+        const uint32_t* rw = reinterpret_cast< const uint32_t* >( &s.raw[ r * kRawPitch + 4 + 12 * g ] );
+        const uint32_t w0 = rw[ 0 ], w1 = rw[ 1 ], w2 = rw[ 2 ];
+        uint32_t y[ 4 ];
+        y[ 0 ] = yuv_word( w0 & 255u, ( w0 >> 8 ) & 255u, ( w0 >> 16 ) & 255u ) & 0x00FFFFFFu;
+        y[ 1 ] = yuv_word( w0 >> 24, w1 & 255u, ( w1 >> 8 ) & 255u ) & 0x00FFFFFFu;
+        y[ 2 ] = yuv_word( ( w1 >> 16 ) & 255u, w1 >> 24, w2 & 255u ) & 0x00FFFFFFu;
+        y[ 3 ] = yuv_word( ( w2 >> 8 ) & 255u, ( w2 >> 16 ) & 255u, w2 >> 24 ) & 0x00FFFFFFu;
+        const int gx = x0 - 4 + 4 * g, gy = y0 - 1 + r; // image column of the group's first pixel (c = 4g - 3)
+        if( gy < 0 || gy >= a.height )
+            y[ 0 ] = y[ 1 ] = y[ 2 ] = y[ 3 ] = kInvalid;
+        else if( gx < 0 || gx + 3 >= a.width )
         {
-            c -= kYW;
-            r++;
+#pragma unroll
+            for( int k = 0; k < 4; k++ )
+                if( gx + k < 0 || gx + k >= a.width ) y[ k ] = kInvalid;
         }
+        *reinterpret_cast< uint4* >( &s.yuv[ r * kYuvPitch + 4 * g ] ) = make_uint4( y[ 0 ], y[ 1 ], y[ 2 ], y[ 3 ] );
     }
     __syncthreads();
 
-    // one 2x2 block per step: bit0 = bottom side, bit1 = left side, bit2 = "/" diagonal, bit3 = "\" diagonal,
-    // diagonals already cleared when all four sides are linked (stage B)
-    for( int idx = tid, r = tid / kBW, c = tid % kBW; idx < kBH * kBW; idx += kThreads )
+    // four 2x2 blocks per step (block columns 4g-3 .. 4g): bit0 = bottom side, bit1 = left side, bit2 = "/" diagonal,
+    // bit3 = "\" diagonal, diagonals already cleared when all four sides are linked (stage B)
+    for( int idx = tid; idx < kBH * kBlkGroups; idx += kThreads )
     {
-        uint32_t p00 = s.yuv[ r * kYuvPitch + c ], p10 = s.yuv[ r * kYuvPitch + c + 1 ];
-        uint32_t p01 = s.yuv[ ( r + 1 ) * kYuvPitch + c ], p11 = s.yuv[ ( r + 1 ) * kYuvPitch + c + 1 ];
-        uint32_t hb = sim( p00, p10 ), ht = sim( p01, p11 ), vl = sim( p00, p01 ), vr = sim( p10, p11 );
-        uint32_t d1 = sim( p00, p11 ), d2 = sim( p10, p01 );
-        uint32_t keep = ( hb & ht & vl & vr ) ^ 1u;
-        s.blk[ r * kBlkPitch + c ] = ( uint8_t )( hb | ( vl << 1 ) | ( ( d1 & keep ) << 2 ) | ( ( d2 & keep ) << 3 ) );
-        c += kThreads % kBW;
-        r += kThreads / kBW;
-        if( c >= kBW )
+        const int r = idx / kBlkGroups, g = idx - r * kBlkGroups;
+        const uint32_t* lo = &s.yuv[ r * kYuvPitch + 4 * g ];
+        const uint32_t* hi = lo + kYuvPitch;
+        const uint4 l4 = *reinterpret_cast< const uint4* >( lo ), h4 = *reinterpret_cast< const uint4* >( hi );
+        const uint32_t p[ 5 ] = { l4.x, l4.y, l4.z, l4.w, lo[ 4 ] }, q[ 5 ] = { h4.x, h4.y, h4.z, h4.w, hi[ 4 ] };
+        uint32_t v[ 5 ];
+#pragma unroll
+        for( int k = 0; k < 5; k++ ) v[ k ] = sim( p[ k ], q[ k ] ); // vertical sides
+        uint32_t word = 0u;
+#pragma unroll
+        for( int k = 0; k < 4; k++ )
         {
-            c -= kBW;
-            r++;
+            const uint32_t hb = sim( p[ k ], p[ k + 1 ] ), ht = sim( q[ k ], q[ k + 1 ] );
+            const uint32_t d1 = sim( p[ k ], q[ k + 1 ] ), d2 = sim( p[ k + 1 ], q[ k ] );
+            const uint32_t keep = ( hb & ht & v[ k ] & v[ k + 1 ] ) ^ 1u;
+            word |= ( hb | ( v[ k ] << 1 ) | ( ( d1 & keep ) << 2 ) | ( ( d2 & keep ) << 3 ) ) << ( 8 * k );
         }
+        *reinterpret_cast< uint32_t* >( &s.blk[ r * kBlkPitch + 4 * g ] ) = word;
     }
     __syncthreads();
 
-    // assemble 4 horizontally adjacent pixel bytes per thread
+    // assemble 4 horizontally adjacent pixel bytes per thread, all four at once on byte lanes.  Pixel (lx+k, ly) is
+    // column c = lx+k+1 of staged row ly+1; around it: UL = block (c-1, ly+1), UR = (c, ly+1), DL = (c-1, ly), DR = (c, ly).
     uint8_t* out = a.graph_aux + ( size_t )f * a.width * a.height;
     const bool word_ok = ( a.width & 3 ) == 0;
     for( int idx = tid; idx < ( kTW / 4 ) * kTH; idx += kThreads )
@@ -135,23 +153,18 @@ __global__ void __launch_bounds__( kThreads ) similarity_graph_kernel( const __g
         int ly = idx / ( kTW / 4 ), lx = ( idx - ly * ( kTW / 4 ) ) * 4;
         int gx = x0 + lx, gy = y0 + ly;
         if( gx >= a.width || gy >= a.height ) continue;
-        const uint8_t* up = &s.blk[ ( ly + 1 ) * kBlkPitch + lx ]; // blocks whose lower-left pixel is (lx-1.., ly)
-        const uint8_t* dn = &s.blk[ ly * kBlkPitch + lx ];         // ... and (lx-1.., ly-1)
-        uint32_t bytes = 0;
-#pragma unroll
-        for( int k = 0; k < 4; k++ )
-        {
-            uint32_t e10 = up[ k ], e00 = up[ k + 1 ], e11 = dn[ k ], e01 = dn[ k + 1 ];
-            uint32_t b = ( ( e10 >> 3 ) & 1u )          // bit 0: "\" of the up-left block
-                         | ( ( ( e00 >> 1 ) & 1u ) << 1 ) // bit 1: up
-                         | ( ( ( e00 >> 2 ) & 1u ) << 2 ) // bit 2: "/" of the up-right block
-                         | ( ( e10 & 1u ) << 3 )          // bit 3: left
-                         | ( ( e00 & 1u ) << 4 )          // bit 4: right
-                         | ( ( ( e11 >> 2 ) & 1u ) << 5 ) // bit 5: "/" of the down-left block
-                         | ( ( ( e01 >> 1 ) & 1u ) << 6 ) // bit 6: down
-                         | ( ( ( e01 >> 3 ) & 1u ) << 7 ); // bit 7: "\" of the down-right block
-            bytes |= b << ( 8 * k );
-        }
+        const uint32_t* up = reinterpret_cast< const uint32_t* >( &s.blk[ ( ly + 1 ) * kBlkPitch + lx ] ); // block column lx-3 .. : bytes lx ..
+        const uint32_t* dn = reinterpret_cast< const uint32_t* >( &s.blk[ ly * kBlkPitch + lx ] );
+        const uint32_t ur = up[ 1 ], dr = dn[ 1 ];                                                    // block columns lx+1 .. lx+4
+        const uint32_t ul = __byte_perm( up[ 0 ], ur, 0x6543 ), dl = __byte_perm( dn[ 0 ], dr, 0x6543 ); // block columns lx .. lx+3
+        const uint32_t bytes = ( ( ul >> 3 ) & 0x01010101u )    // bit 0: "\" of the up-left block
+                               | ( ur & 0x02020202u )           // bit 1: up (left side of the up-right block)
+                               | ( ur & 0x04040404u )           // bit 2: "/" of the up-right block
+                               | ( ( ul << 3 ) & 0x08080808u )  // bit 3: left (bottom side of the up-left block)
+                               | ( ( ur << 4 ) & 0x10101010u )  // bit 4: right (bottom side of the up-right block)
+                               | ( ( dl << 3 ) & 0x20202020u )  // bit 5: "/" of the down-left block
+                               | ( ( dr << 5 ) & 0x40404040u )  // bit 6: down (left side of the down-right block)
+                               | ( ( dr << 4 ) & 0x80808080u ); // bit 7: "\" of the down-right block
         size_t o = ( size_t )gy * a.width + gx;
         if( word_ok && gx + 3 < a.width )
             *reinterpret_cast< uint32_t* >( out + o ) = bytes;
