@@ -45,8 +45,7 @@ struct par_context
     CellRecord* d_tables = nullptr;        // kCellKeys 32-byte records
     uint32_t* d_mask_lut[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // per scale, built on first use
     // smoothing tables (smooth_table.h): link descriptors + neighbour bytes + class list (scale-independent), CUT / LINK masks per scale
-    uint4* d_smooth_rec = nullptr;
-    uint16_t* d_smooth_nbr = nullptr;
+    SmoothRecord* d_smooth_rec = nullptr;
     LinkClass* d_link_classes = nullptr;
     int n_link_classes = 0;
     uint32_t link_entries = 0;
@@ -257,7 +256,7 @@ int run_raster( par_context* c, const par_job* j, const uint8_t* graph )
         if( le != cudaSuccess ) return c->cuda_fail( le, "mask table" );
     }
     a.mask_lut = c->d_mask_lut[ j->scale ];
-    a.smooth = SmoothTablePtrs{ c->d_smooth_rec, c->d_smooth_nbr, nullptr, nullptr };
+    a.smooth = SmoothTablePtrs{ c->d_smooth_rec, nullptr, nullptr };
     a.smooth_stats = c->d_smooth_stats;
     if( a.subdivide && !( j->flags & PAR_FLAG_NO_SMOOTH_TABLES ) )
     {
@@ -345,15 +344,13 @@ int par_create( par_context** out, int device, int max_width, int max_height, in
             build_smooth_tables( tables, &smooth );
         } );
         static_assert( sizeof( CellTables ) == 32 * kCellKeys, "one 32-byte record per key" );
-        static_assert( sizeof( SmoothRecord ) == 16, "one 16-byte record per key" );
+        static_assert( sizeof( SmoothRecord ) == 32, "one 32-byte record per key" );
         e = cudaMemcpy( c->d_tables, &tables, sizeof( tables ), cudaMemcpyHostToDevice );
         c->n_link_classes = ( int )smooth.classes.size();
         c->link_entries = smooth.link_entries;
         if( e == cudaSuccess ) e = cudaMalloc( &c->d_smooth_rec, sizeof( smooth.rec ) );
-        if( e == cudaSuccess ) e = cudaMalloc( &c->d_smooth_nbr, sizeof( smooth.nbr ) );
         if( e == cudaSuccess ) e = cudaMalloc( &c->d_link_classes, smooth.classes.size() * sizeof( LinkClass ) );
         if( e == cudaSuccess ) e = cudaMemcpy( c->d_smooth_rec, smooth.rec, sizeof( smooth.rec ), cudaMemcpyHostToDevice );
-        if( e == cudaSuccess ) e = cudaMemcpy( c->d_smooth_nbr, smooth.nbr, sizeof( smooth.nbr ), cudaMemcpyHostToDevice );
         if( e == cudaSuccess )
             e = cudaMemcpy( c->d_link_classes, smooth.classes.data(), smooth.classes.size() * sizeof( LinkClass ), cudaMemcpyHostToDevice );
     }
@@ -384,7 +381,6 @@ void par_destroy( par_context* c )
     for( int k = 0; k < 9; k++ ) cudaFree( c->d_cut[ k ] );
     for( int k = 0; k < 9; k++ ) cudaFree( c->d_link[ k ] );
     cudaFree( c->d_smooth_rec );
-    cudaFree( c->d_smooth_nbr );
     cudaFree( c->d_link_classes );
     cudaFree( c->d_smooth_stats );
     for( int k = 0; k < 8; k++ ) cudaFree( c->h_stage[ k ] );

@@ -32,8 +32,7 @@ struct LabelArgs
 // device pointers of the smoothing tables (smooth_table.h); cut / link are per scale
 struct SmoothTablePtrs
 {
-    const uint4* rec;     // [kCellKeys] link descriptors
-    const uint16_t* nbr;  // [kCellKeys][8] neighbour records
+    const SmoothRecord* rec; // [kCellKeys] link descriptors + neighbour records, 32 bytes each
     const uint64_t* cut;  // [kCellKeys][16] entries
     const uint64_t* link; // [link_entries] entries
 };

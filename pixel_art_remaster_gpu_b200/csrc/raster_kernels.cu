@@ -465,9 +465,8 @@ template< int S >
 __global__ void build_link_table_kernel( const LinkClass* classes, uint64_t* link )
 {
     const LinkClass c = classes[ blockIdx.x ];
-    const int sub = threadIdx.x;
-    if( sub >= ( int )c.count ) return;
-    const int a = ( c.hasA && c.hasB ) ? sub & 15 : sub, b = ( c.hasA && c.hasB ) ? sub >> 4 : sub;
+    const int sub = threadIdx.x;                 // = a | b << 4 (a class with one blended end ignores the other nibble)
+    const int a = sub & 15, b = sub >> 4;
     const int di = edge_di( c.e ), dj = edge_dj( c.e );
     const Q2 P0{ c.px[ 0 ], c.py[ 0 ] }, P1{ c.px[ 1 ], c.py[ 1 ] }, P2{ c.px[ 2 ], c.py[ 2 ] }, P3{ c.px[ 3 ], c.py[ 3 ] };
     int xs[ 6 ], ys[ 6 ], m = 0;
@@ -510,7 +509,7 @@ __global__ void build_link_table_kernel( const LinkClass* classes, uint64_t* lin
         ys[ m ] = 16 * P1.y;
         m++;
     }
-    cover_to_entry< S >( xs, ys, m, link + ( size_t )( c.first + sub ) * Entry< S >::EW );
+    cover_to_entry< S >( xs, ys, m, link + ( size_t )( c.block * 256u + sub ) * Entry< S >::EW );
 }
 
 // Mask of a smoothed cell from the tables: false when a blended vertex is not a vertex of the neighbour's
@@ -521,7 +520,7 @@ __device__ __forceinline__ bool smooth_lookup( const SmoothTablePtrs& st, const 
 {
     typedef Cfg< S > C;
     typedef Entry< S > E;
-    const uint4 rec = __ldg( st.rec + key );
+    const uint4 rec = __ldg( reinterpret_cast< const uint4* >( st.rec + key ) ); // the four link descriptors
     uint64_t flags = 0ull;
     if( cflags & 16u ) // checkTJunction's early exit keeps every cut vertex: the plain hull
     {
@@ -540,12 +539,12 @@ __device__ __forceinline__ bool smooth_lookup( const SmoothTablePtrs& st, const 
     }
     else
     {
-        const uint64_t* e = st.cut + ( size_t )( key * 16u + ( cflags & 15u ) ) * E::EW;
+        const uint64_t* e = st.cut + ( size_t )( key * 16u + ( cflags & ( rec.x >> 4 ) & 15u ) ) * E::EW; // (only corners with a cut vertex matter)
 #pragma unroll
         for( int w = 0; w < E::EW; w++ ) m[ w ] = __ldg( e + w );
     }
     // All four descriptor slots are processed without branches (a warp runs as long as its busiest lane anyway, and
-    // the loads of the four slots overlap); an unused slot (0) loads nothing.
+    // the loads of the four slots overlap); an unused slot (0) compares nothing and XORs the all-zero entry 0.
     bool ok = rec.x != kSmoothSlow;
     const uint32_t links[ 4 ] = { ok ? rec.x : 0u, rec.y, rec.z, rec.w };
     uint32_t nb[ kMaxLinks ];
@@ -562,28 +561,25 @@ __device__ __forceinline__ bool smooth_lookup( const SmoothTablePtrs& st, const 
                                     ( uint32_t )( uint8_t )( -KW + 1 ) << 24;
         const int koff = ( int )( int8_t )__byte_perm( off_lo, off_hi, e );
         const uint32_t nkey = keys_at_cell[ koff ];
-        nb[ k ] = d ? ( uint32_t )__ldg( st.nbr + nkey * 8u + ( 7u - e ) ) : 0u;
+        nb[ k ] = ( d >> 16 ) ? ( uint32_t )__ldg( &st.rec[ nkey ].nbr[ e ^ 7u ] ) : 0u; // (an unused slot loads nothing)
     }
+    uint32_t mismatch = 0u;
 #pragma unroll
     for( int k = 0; k < kMaxLinks; k++ )
     {
-        const uint32_t d = links[ k ];
-        const bool hasA = ( d & 8u ) != 0u, hasB = ( d & 16u ) != 0u;
-        // the blended vertices must be the end (A) / start (B) of the neighbour's edge
-        const uint32_t must = ( hasA ? 0x0F00u : 0u ) | ( hasB ? 0xF000u : 0u );
-        const uint32_t r = nb[ k ];
-        const bool match = ( ( ( r ^ ( d << 3 ) ) & must ) == 0u ) && ( ( ( r >> 8 ) ^ ( r >> 12 ) ) & 15u ) != 0u; // (d << 3: codeA -> [8,12), codeB -> [12,16))
-        ok = ok && ( d == 0u || match );
-        const uint32_t sub = ( hasA ? r : r >> 4 ) & ( ( hasA && hasB ) ? 255u : 15u );
-        const uint64_t* le = st.link + ( size_t )( ( d >> 13 ) + sub ) * E::EW;
+        const uint32_t d = links[ k ], r = nb[ k ];
+        const uint32_t ends = ( d >> 16 ) & 255u;
+        mismatch |= ( ( r ^ d ) >> 8 ) & ends; // the blended vertices must be the end (A) / start (B) of the neighbour's edge
+        const uint64_t* le = st.link + ( size_t )( ( d >> 24 ) * 256u + ( r & ends ) ) * E::EW;
 #pragma unroll
         for( int w = 0; w < E::EW; w++ )
         {
-            const uint64_t v = d ? __ldg( le + w ) : 0ull;
+            const uint64_t v = ( d >> 16 ) ? __ldg( le + w ) : 0ull;
             if( w == 0 ) flags |= v;
             m[ w ] ^= v;
         }
     }
+    ok = ok && mismatch == 0u;
     // the flag bit of word 0 was XORed along with the masks: restore it from the CUT entry (never wide) and the OR
     wide = ( flags & E::FLAG ) != 0ull;
     m[ 0 ] &= ~E::FLAG;
@@ -1175,6 +1171,7 @@ cudaError_t launch_build_smooth_tables( int scale, const CellTablePtrs& tab, con
 {
 #define PAR_BUILD_SMOOTH( S )                                                                        \
     build_cut_table_kernel< S ><<< kCellKeys * 16 / 128, 128, 0, stream >>>( tab, cut );             \
+    cudaMemsetAsync( link, 0, 256 * Entry< S >::EW * sizeof( uint64_t ), stream ); /* block 0: the all-zero block */ \
     build_link_table_kernel< S ><<< n_classes, 256, 0, stream >>>( d_classes, link );                \
     return cudaGetLastError()
     PAR_FOR_SCALE( scale, PAR_BUILD_SMOOTH )

@@ -36,23 +36,30 @@ void build_smooth_tables( const CellTables& cells, SmoothTables* out )
 {
     memset( out->rec, 0, sizeof( out->rec ) );
     out->classes.clear();
-    out->link_entries = 0;
+    out->link_entries = 256; // block 0: the all-zero block unused descriptor slots point at
     out->slow_keys = 0;
     typedef std::tuple< int, int, int, int, int, int, int, int, int, int, int > ClassKey; // e, hasA, hasB, 4 x (x, y)
-    std::map< ClassKey, uint32_t > class_first;
+    std::map< ClassKey, uint32_t > class_block;
+    uint32_t expected[ 8 ] = { 0, 0, 0, 0, 0, 0, 0, 0 }; // per link direction e: point codes some cell expects at the neighbour's edge ends
+    bool has_edge[ kCellKeys ][ 8 ];
     for( unsigned key = 0; key < ( unsigned )kCellKeys; key++ )
     {
         const CellRecord& r = cells.rec[ key ];
         const Hull h = hull_of( r );
         // neighbour records: for every link direction the hull edge shared through it, and the vertices around it
-        for( int e = 0; e < 8; e++ ) out->nbr[ key ][ e ] = 0; // start == end: no such edge
+        for( int e = 0; e < 8; e++ )
+        {
+            out->rec[ key ].nbr[ e ] = 0;
+            has_edge[ key ][ e ] = false;
+        }
         for( int t = 0; t < h.n; t++ )
         {
             if( h.border[ t ] ) continue;
             const int tn = ( t + 1 ) % h.n, tnn = ( t + 2 ) % h.n, tp = ( t + h.n - 1 ) % h.n;
             const int start = point_code( h.x[ t ], h.y[ t ] ), end = point_code( h.x[ tn ], h.y[ tn ] );
             const int after = point_code( h.x[ tnn ], h.y[ tnn ] ), before = point_code( h.x[ tp ], h.y[ tp ] );
-            out->nbr[ key ][ h.link[ t ] ] = ( uint16_t )( after | before << 4 | end << 8 | start << 12 );
+            out->rec[ key ].nbr[ h.link[ t ] ] = ( uint16_t )( after | before << 4 | end << 8 | start << 12 );
+            has_edge[ key ][ h.link[ t ] ] = true;
         }
         // link descriptors
         int n_links = 0;
@@ -70,10 +77,12 @@ void build_smooth_tables( const CellTables& cells, SmoothTables* out )
                 slow = true; // the vertex is not one of the 16 hull points in the neighbour's frame: never found there
                 break;
             }
+            if( hasA ) expected[ h.link[ t ] ] |= 1u << codeA;
+            if( hasB ) expected[ h.link[ t ] ] |= 1u << codeB;
             const ClassKey ck( h.link[ t ], hasA, hasB, hasA ? h.x[ tp ] : 0, hasA ? h.y[ tp ] : 0, h.x[ t ], h.y[ t ], h.x[ tn ], h.y[ tn ],
                                hasB ? h.x[ tnn ] : 0, hasB ? h.y[ tnn ] : 0 );
-            auto it = class_first.find( ck );
-            if( it == class_first.end() )
+            auto it = class_block.find( ck );
+            if( it == class_block.end() )
             {
                 LinkClass c;
                 memset( &c, 0, sizeof( c ) );
@@ -86,23 +95,50 @@ void build_smooth_tables( const CellTables& cells, SmoothTables* out )
                     c.px[ k ] = ( int8_t )h.x[ idx[ k ] ];
                     c.py[ k ] = ( int8_t )h.y[ idx[ k ] ];
                 }
-                c.first = out->link_entries;
-                c.count = ( hasA && hasB ) ? 256u : 16u;
-                out->link_entries += c.count;
+                c.block = out->link_entries / 256;
+                out->link_entries += 256;
                 out->classes.push_back( c );
-                it = class_first.insert( std::make_pair( ck, c.first ) ).first;
+                it = class_block.insert( std::make_pair( ck, c.block ) ).first;
             }
-            links[ n_links++ ] = ( uint32_t )h.link[ t ] | ( hasA ? 8u : 0u ) | ( hasB ? 16u : 0u ) | ( hasA ? codeA << 5 : 0u ) |
-                                 ( hasB ? codeB << 9 : 0u ) | it->second << 13;
+            links[ n_links++ ] = ( uint32_t )h.link[ t ] | ( ( hasA ? codeA : 0u ) | ( hasB ? codeB << 4 : 0u ) ) << 8 |
+                                 ( ( hasA ? 0x0Fu : 0u ) | ( hasB ? 0xF0u : 0u ) ) << 16 | it->second << 24;
         }
-        if( slow || n_links > kMaxLinks )
+        if( slow || n_links > kMaxLinks || out->link_entries / 256 > 255 )
         {
             out->rec[ key ].link[ 0 ] = kSmoothSlow;
             out->slow_keys++;
             continue;
         }
         for( int k = 0; k < n_links; k++ ) out->rec[ key ].link[ k ] = links[ k ];
+        // square corners that hold a cut vertex (both adjacent hull edges are border edges)
+        uint32_t corners = 0;
+        for( int c = 0; c < 4; c++ )
+        {
+            const int v = ( int )( ( r.info >> ( 44 + 4 * c ) ) & 15u );
+            if( v != 15 && h.border[ v ] && h.border[ ( v + h.n - 1 ) % h.n ] ) corners |= 1u << c;
+        }
+        out->rec[ key ].link[ 0 ] |= corners << 4;
     }
+    // a neighbour without an edge for direction e' is asked through the cell's link e = 7 - e': give it end/start codes
+    // that nobody expects there, so the comparison fails without a separate validity test
+    for( int e = 0; e < 8; e++ )
+    {
+        int never = -1;
+        for( int code = 0; code < 16; code++ )
+            if( !( ( expected[ e ] >> code ) & 1u ) ) never = code;
+        for( unsigned key = 0; key < ( unsigned )kCellKeys; key++ )
+        {
+            if( has_edge[ key ][ 7 - e ] ) continue;
+            if( never < 0 )
+            {
+                out->slow_keys = kCellKeys; // (cannot happen: a direction's shared edges touch only a few of the 16 points)
+                continue;
+            }
+            out->rec[ key ].nbr[ 7 - e ] = ( uint16_t )( never << 8 | never << 12 );
+        }
+    }
+    if( out->slow_keys == ( uint32_t )kCellKeys )
+        for( unsigned key = 0; key < ( unsigned )kCellKeys; key++ ) out->rec[ key ].link[ 0 ] = kSmoothSlow;
 }
 
 } // namespace par

@@ -19,7 +19,8 @@
 // edge that is shared through ITS graph edge e' = 7 - e (a hull has at most one per direction):
 //     bits [0,4)  a = point code of the vertex AFTER the edge's end      (what end A needs)
 //     bits [4,8)  b = point code of the vertex BEFORE the edge's start   (what end B needs)
-//     bits [8,12) point code of the edge's end, bits [12,16) of its start; start == end: no such edge.
+//     bits [8,12) point code of the edge's end, bits [12,16) of its start.  A direction without such an edge
+//     holds a code pair that no cell ever expects for that direction, so it can never compare equal.
 // The cell's blended vertex must BE that end (A) / start (B) — the reference finds it by coordinates
 // (getPointIndex, :527-538) and then takes the vertex after / before it, which is the same thing whenever it
 // is there.  When it is not (codes differ, or no such edge: getPointIndex's "not found -> 0" fallback and a few
@@ -33,19 +34,24 @@
 
 namespace par {
 
-// Link descriptor (32 bits), up to kMaxLinks per key; 0 = unused slot.
-//   [0,3)   e     graph edge the hull edge is shared through = direction of the neighbour
-//   [3]     hasA  the vertex the edge starts at is blended (edge before it is a border edge)
-//   [4]     hasB  the vertex the edge ends at is blended (edge after it is a border edge)
-//   [5,9)   codeA the start vertex as a point code in the neighbour's frame
-//   [9,13)  codeB the end vertex as a point code in the neighbour's frame
-//   [13,32) first entry of the class in the link table; entry = first + (hasA && hasB ? a + 16 b : hasA ? a : b)
+// Link descriptor (32 bits), up to kMaxLinks per key, laid out so that the kernel decodes it with a few shifts:
+//   [0,3)   e       graph edge the hull edge is shared through = direction of the neighbour
+//   [4,8)   corners (slot 0 only) which square corners (0,0) (1,0) (1,1) (0,1) hold a cut vertex of the hull: the
+//                   `kept` bits of the others do not matter and are masked off before CUT is indexed
+//   [8,16)  expect  codeA | codeB << 4: the edge's start / end vertex as point codes in the neighbour's frame,
+//                   to be compared with bits [8,16) of the neighbour record
+//   [16,24) ends    0x0F: the start vertex is blended (end A), 0xF0: the end vertex is (end B), 0xFF: both.
+//                   Masks the comparison above AND selects the index inside the class: entry = 256 block + (nbr & ends)
+//   [24,32) block   the class's 256-entry block of the link table (block 0 is all zero)
+// An unused slot is 0: it compares nothing, selects entry 0 of block 0 and so contributes an empty mask.
 constexpr int kMaxLinks = 4;
 constexpr uint32_t kSmoothSlow = 0xFFFFFFFFu; // in link[0]: this key always takes the geometric path
 
+// One 32-byte record per key (one sector): the key's own link descriptors and, for its neighbours, its records.
 struct SmoothRecord
 {
     uint32_t link[ kMaxLinks ];
+    uint16_t nbr[ 8 ];
 };
 
 // geometry of one class, consumed by the device table builder (quarter-pixel units)
@@ -53,16 +59,15 @@ struct LinkClass
 {
     int8_t e, hasA, hasB, pad;
     int8_t px[ 4 ], py[ 4 ]; // hull vertices t-1, t, t+1, t+2
-    uint32_t first;          // first entry in the link table
-    uint32_t count;          // 16 or 256
+    uint32_t block;          // its 256-entry block of the link table (>= 1)
+    uint32_t pad2;
 };
 
 struct SmoothTables
 {
     SmoothRecord rec[ kCellKeys ];
-    uint16_t nbr[ kCellKeys ][ 8 ];
     std::vector< LinkClass > classes;
-    uint32_t link_entries = 0; // total entries of the link table
+    uint32_t link_entries = 0; // total entries of the link table (256 per class + the zero block)
     uint32_t slow_keys = 0;    // keys that always take the geometric path
 };
 
