@@ -465,8 +465,14 @@ template< int S >
 __global__ void build_link_table_kernel( const LinkClass* classes, uint64_t* link )
 {
     const LinkClass c = classes[ blockIdx.x ];
-    const int sub = threadIdx.x;                 // = a | b << 4 (a class with one blended end ignores the other nibble)
-    const int a = sub & 15, b = sub >> 4;
+    const int sub = threadIdx.x;                 // = rank a | rank b << 4 (a class with one blended end ignores the other nibble)
+    uint64_t* entry = link + ( size_t )( c.block * 256u + sub ) * Entry< S >::EW;
+    if( ( sub & 15 ) >= 4 || ( sub >> 4 ) >= 4 )  // ranks are 0..3: the rest of the block is never addressed
+    {
+        for( int w = 0; w < Entry< S >::EW; w++ ) entry[ w ] = 0ull;
+        return;
+    }
+    const int a = c.after[ sub & 15 ], b = c.before[ sub >> 4 ];
     const int di = edge_di( c.e ), dj = edge_dj( c.e );
     const Q2 P0{ c.px[ 0 ], c.py[ 0 ] }, P1{ c.px[ 1 ], c.py[ 1 ] }, P2{ c.px[ 2 ], c.py[ 2 ] }, P3{ c.px[ 3 ], c.py[ 3 ] };
     int xs[ 6 ], ys[ 6 ], m = 0;
@@ -509,7 +515,7 @@ __global__ void build_link_table_kernel( const LinkClass* classes, uint64_t* lin
         ys[ m ] = 16 * P1.y;
         m++;
     }
-    cover_to_entry< S >( xs, ys, m, link + ( size_t )( c.block * 256u + sub ) * Entry< S >::EW );
+    cover_to_entry< S >( xs, ys, m, entry );
 }
 
 // Mask of a smoothed cell from the tables: false when a blended vertex is not a vertex of the neighbour's

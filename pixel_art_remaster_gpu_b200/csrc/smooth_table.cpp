@@ -41,7 +41,38 @@ void build_smooth_tables( const CellTables& cells, SmoothTables* out )
     typedef std::tuple< int, int, int, int, int, int, int, int, int, int, int > ClassKey; // e, hasA, hasB, 4 x (x, y)
     std::map< ClassKey, uint32_t > class_block;
     uint32_t expected[ 8 ] = { 0, 0, 0, 0, 0, 0, 0, 0 }; // per link direction e: point codes some cell expects at the neighbour's edge ends
-    bool has_edge[ kCellKeys ][ 8 ];
+    static bool has_edge[ kCellKeys ][ 8 ];
+    // per direction, the points that occur after the end / before the start of the hull edge shared through it, ranked
+    int after_rank[ 8 ][ 16 ], before_rank[ 8 ][ 16 ], after_code[ 8 ][ 4 ], before_code[ 8 ][ 4 ], n_after[ 8 ], n_before[ 8 ];
+    bool ranks_ok = true;
+    for( int e = 0; e < 8; e++ )
+    {
+        n_after[ e ] = n_before[ e ] = 0;
+        for( int c = 0; c < 16; c++ ) after_rank[ e ][ c ] = before_rank[ e ][ c ] = -1;
+        for( int k = 0; k < 4; k++ ) after_code[ e ][ k ] = before_code[ e ][ k ] = 0;
+    }
+    for( unsigned key = 0; key < ( unsigned )kCellKeys; key++ )
+    {
+        const Hull h = hull_of( cells.rec[ key ] );
+        for( int t = 0; t < h.n; t++ )
+        {
+            if( h.border[ t ] ) continue;
+            const int e = h.link[ t ], tnn = ( t + 2 ) % h.n, tp = ( t + h.n - 1 ) % h.n;
+            const int after = point_code( h.x[ tnn ], h.y[ tnn ] ), before = point_code( h.x[ tp ], h.y[ tp ] );
+            if( after_rank[ e ][ after ] < 0 )
+            {
+                if( n_after[ e ] == 4 ) { ranks_ok = false; continue; }
+                after_code[ e ][ n_after[ e ] ] = after;
+                after_rank[ e ][ after ] = n_after[ e ]++;
+            }
+            if( before_rank[ e ][ before ] < 0 )
+            {
+                if( n_before[ e ] == 4 ) { ranks_ok = false; continue; }
+                before_code[ e ][ n_before[ e ] ] = before;
+                before_rank[ e ][ before ] = n_before[ e ]++;
+            }
+        }
+    }
     for( unsigned key = 0; key < ( unsigned )kCellKeys; key++ )
     {
         const CellRecord& r = cells.rec[ key ];
@@ -58,7 +89,8 @@ void build_smooth_tables( const CellTables& cells, SmoothTables* out )
             const int tn = ( t + 1 ) % h.n, tnn = ( t + 2 ) % h.n, tp = ( t + h.n - 1 ) % h.n;
             const int start = point_code( h.x[ t ], h.y[ t ] ), end = point_code( h.x[ tn ], h.y[ tn ] );
             const int after = point_code( h.x[ tnn ], h.y[ tnn ] ), before = point_code( h.x[ tp ], h.y[ tp ] );
-            out->rec[ key ].nbr[ h.link[ t ] ] = ( uint16_t )( after | before << 4 | end << 8 | start << 12 );
+            out->rec[ key ].nbr[ h.link[ t ] ] =
+                ( uint16_t )( ( after_rank[ h.link[ t ] ][ after ] & 15 ) | ( before_rank[ h.link[ t ] ][ before ] & 15 ) << 4 | end << 8 | start << 12 );
             has_edge[ key ][ h.link[ t ] ] = true;
         }
         // link descriptors
@@ -95,6 +127,11 @@ void build_smooth_tables( const CellTables& cells, SmoothTables* out )
                     c.px[ k ] = ( int8_t )h.x[ idx[ k ] ];
                     c.py[ k ] = ( int8_t )h.y[ idx[ k ] ];
                 }
+                for( int k = 0; k < 4; k++ ) // the neighbour's edge is shared through ITS graph edge 7 - e
+                {
+                    c.after[ k ] = ( int8_t )after_code[ 7 - h.link[ t ] ][ k ];
+                    c.before[ k ] = ( int8_t )before_code[ 7 - h.link[ t ] ][ k ];
+                }
                 c.block = out->link_entries / 256;
                 out->link_entries += 256;
                 out->classes.push_back( c );
@@ -103,7 +140,7 @@ void build_smooth_tables( const CellTables& cells, SmoothTables* out )
             links[ n_links++ ] = ( uint32_t )h.link[ t ] | ( ( hasA ? codeA : 0u ) | ( hasB ? codeB << 4 : 0u ) ) << 8 |
                                  ( ( hasA ? 0x0Fu : 0u ) | ( hasB ? 0xF0u : 0u ) ) << 16 | it->second << 24;
         }
-        if( slow || n_links > kMaxLinks || out->link_entries / 256 > 255 )
+        if( slow || !ranks_ok || n_links > kMaxLinks || out->link_entries / 256 > 255 )
         {
             out->rec[ key ].link[ 0 ] = kSmoothSlow;
             out->slow_keys++;

@@ -17,8 +17,10 @@
 //
 // The neighbour side is 16 bits per (neighbour key, link direction): NBR[key][e'] describes the neighbour's hull
 // edge that is shared through ITS graph edge e' = 7 - e (a hull has at most one per direction):
-//     bits [0,4)  a = point code of the vertex AFTER the edge's end      (what end A needs)
-//     bits [4,8)  b = point code of the vertex BEFORE the edge's start   (what end B needs)
+//     bits [0,4)  a = which vertex comes AFTER the edge's end      (what end A needs)
+//     bits [4,8)  b = which vertex comes BEFORE the edge's start   (what end B needs)
+//       both as a rank 0..3: over all 4096 hulls only four different points occur in either role for a given
+//       direction, so a class's masks are 4 x 4 entries and each a-row is one 32-byte sector
 //     bits [8,12) point code of the edge's end, bits [12,16) of its start.  A direction without such an edge
 //     holds a code pair that no cell ever expects for that direction, so it can never compare equal.
 // The cell's blended vertex must BE that end (A) / start (B) — the reference finds it by coordinates
@@ -60,6 +62,7 @@ struct LinkClass
     int8_t e, hasA, hasB, pad;
     int8_t px[ 4 ], py[ 4 ]; // hull vertices t-1, t, t+1, t+2
     uint32_t block;          // its 256-entry block of the link table (>= 1)
+    int8_t after[ 4 ], before[ 4 ]; // rank -> point code of the neighbour's vertex after the edge end / before its start
     uint32_t pad2;
 };
 
