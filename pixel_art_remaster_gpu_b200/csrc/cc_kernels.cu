@@ -52,28 +52,55 @@ __device__ __forceinline__ void unite( int* lab, int a, int b )
     }
 }
 
+// Tile pass.  Two things keep the shared-memory forest shallow and the number of unions small:
+//  * horizontal runs first: a warp owns 32 consecutive pixels of a row, one ballot gives the "linked to the right"
+//    bits and every pixel starts with the index of the first pixel of its run as its label — no union at all;
+//  * a link to the row above is only united when it can connect two runs that are not already connected through
+//    the pixel to the left (same run below, same run above, also linked upwards), and a diagonal link only when its
+//    target is not in the run of an orthogonal link that is united anyway.
+// What remains is roughly one union per pair of touching runs.
 __global__ void __launch_bounds__( kThreads ) cc_tile_kernel( LabelArgs a )
 {
     __shared__ int s_lab[ kTW * kTH ];
+    __shared__ uint8_t s_g[ kTW * kTH ]; // node bytes with the links that leave the tile (or the image) removed
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH, f = blockIdx.z;
     const size_t frame_px = ( size_t )a.width * a.height;
     const uint8_t* g = a.graph + ( size_t )f * frame_px;
     int* out = a.labels + ( size_t )f * frame_px;
-    for( int idx = threadIdx.x; idx < kTW * kTH; idx += kThreads ) s_lab[ idx ] = idx;
-    __syncthreads();
-    // each undirected edge once: right (4), up-left (0), up (1), up-right (2)
+    const uint32_t lane = threadIdx.x & 31u;
+    static_assert( kTW % 32 == 0 && ( kTW * kTH ) % kThreads == 0, "a warp owns 32 consecutive pixels of one tile row" );
     for( int idx = threadIdx.x; idx < kTW * kTH; idx += kThreads )
     {
-        int ly = idx / kTW, lx = idx - ly * kTW, gx = x0 + lx, gy = y0 + ly;
-        if( gx >= a.width || gy >= a.height ) continue;
-        uint32_t node = g[ ( size_t )gy * a.width + gx ];
-        if( ( node & 16u ) && lx + 1 < kTW && gx + 1 < a.width ) unite( s_lab, idx, idx + 1 );
-        if( ly + 1 < kTH && gy + 1 < a.height )
+        const int ly = idx / kTW, lx = idx - ly * kTW, gx = x0 + lx, gy = y0 + ly;
+        uint32_t node = 0u;
+        if( gx < a.width && gy < a.height )
         {
-            if( ( node & 2u ) ) unite( s_lab, idx, idx + kTW );
-            if( ( node & 1u ) && lx > 0 ) unite( s_lab, idx, idx + kTW - 1 );
-            if( ( node & 4u ) && lx + 1 < kTW && gx + 1 < a.width ) unite( s_lab, idx, idx + kTW + 1 );
+            node = g[ ( size_t )gy * a.width + gx ];
+            const bool right_ok = lx + 1 < kTW && gx + 1 < a.width, up_ok = ly + 1 < kTH && gy + 1 < a.height;
+            if( !right_ok ) node &= ~( 16u | 4u );
+            if( !up_ok ) node &= ~( 1u | 2u | 4u );
+            if( lx == 0 ) node &= ~1u;
         }
+        s_g[ idx ] = ( uint8_t )node;
+        // run start inside the warp's 32 pixels: the lane after the last lane below me that is NOT linked to its right
+        const uint32_t linked = __ballot_sync( 0xFFFFFFFFu, ( node & 16u ) != 0u );
+        const uint32_t breaks = ~linked & ( ( 1u << lane ) - 1u );
+        const int start = breaks ? 32 - __clz( ( int )breaks ) : 0;
+        s_lab[ idx ] = idx - ( int )lane + start;
+    }
+    __syncthreads();
+    for( int idx = threadIdx.x; idx < kTW * kTH; idx += kThreads )
+    {
+        const int lx = idx & ( kTW - 1 );
+        const uint32_t node = s_g[ idx ];
+        if( ( node & 16u ) && lane == 31u ) unite( s_lab, idx, idx + 1 ); // a run that continues into the next warp's pixels
+        if( !( node & 7u ) ) continue;
+        const uint32_t left = lx > 0 ? s_g[ idx - 1 ] : 0u, right = lx + 1 < kTW ? s_g[ idx + 1 ] : 0u;
+        const uint32_t up = s_g[ idx + kTW ], up_left = lx > 0 ? s_g[ idx + kTW - 1 ] : 0u; // (only read when a link says the row exists)
+        const bool same_run_left = lane > 0u && ( left & 16u );                             // in the same run as the pixel to the left
+        if( ( node & 2u ) && !( same_run_left && ( left & 2u ) && ( up_left & 16u ) ) ) unite( s_lab, idx, idx + kTW );
+        if( ( node & 1u ) && !( ( ( node & 2u ) && ( up_left & 16u ) ) || ( same_run_left && ( left & 2u ) ) ) ) unite( s_lab, idx, idx + kTW - 1 );
+        if( ( node & 4u ) && !( ( ( node & 2u ) && ( up & 16u ) ) || ( lane < 31u && ( node & 16u ) && ( right & 2u ) ) ) ) unite( s_lab, idx, idx + kTW + 1 );
     }
     __syncthreads();
     for( int idx = threadIdx.x; idx < kTW * kTH; idx += kThreads )
@@ -86,13 +113,32 @@ __global__ void __launch_bounds__( kThreads ) cc_tile_kernel( LabelArgs a )
     }
 }
 
+// Seam pass: one thread per pixel that sits on a tile seam (top row of a tile, first / last column of a tile),
+// enumerated directly — the launch does not visit the other 90 % of the pixels.
 __global__ void __launch_bounds__( kThreads ) cc_seam_kernel( LabelArgs a )
 {
-    const int gx = blockIdx.x * 32 + ( threadIdx.x & 31 ), gy = blockIdx.y * 8 + ( threadIdx.x >> 5 ), f = blockIdx.z;
+    const int f = blockIdx.y;
+    const int tile_rows = ( a.height + kTH - 1 ) / kTH, tile_cols = ( a.width + kTW - 1 ) / kTW;
+    const int n_top = tile_rows * a.width, n_side = 2 * tile_cols * a.height;
+    const int t = blockIdx.x * kThreads + threadIdx.x;
+    int gx, gy;
+    if( t < n_top )
+    {
+        gy = ( t / a.width ) * kTH + kTH - 1;
+        gx = t - ( t / a.width ) * a.width;
+    }
+    else if( t < n_top + n_side )
+    {
+        const int u = t - n_top, col = u / a.height;
+        gy = u - col * a.height;
+        gx = ( col >> 1 ) * kTW + ( ( col & 1 ) ? kTW - 1 : 0 );
+        if( gy % kTH == kTH - 1 ) return; // (the top-row threads own the corner pixels)
+    }
+    else
+        return;
     if( gx >= a.width || gy >= a.height ) return;
     const int lx = gx % kTW, ly = gy % kTH;
     const bool right_seam = lx == kTW - 1, left_seam = lx == 0, top_seam = ly == kTH - 1;
-    if( !right_seam && !left_seam && !top_seam ) return;
     const size_t frame_px = ( size_t )a.width * a.height;
     const uint8_t* g = a.graph + ( size_t )f * frame_px;
     int* lab = a.labels + ( size_t )f * frame_px;
@@ -124,8 +170,15 @@ cudaError_t launch_cc_labels( const LabelArgs& a, cudaStream_t stream, int* n_la
 {
     dim3 tiles( ( a.width + kTW - 1 ) / kTW, ( a.height + kTH - 1 ) / kTH, a.n_frames );
     cc_tile_kernel<<< tiles, kThreads, 0, stream >>>( a );
-    dim3 px( ( a.width + 31 ) / 32, ( a.height + 7 ) / 8, a.n_frames );
-    cc_seam_kernel<<< px, kThreads, 0, stream >>>( a );
+    const int seam_px = ( ( a.height + kTH - 1 ) / kTH ) * a.width + 2 * ( ( a.width + kTW - 1 ) / kTW ) * a.height;
+    for( int f0 = 0; f0 < a.n_frames; f0 += 65535 ) // (grid.y limit)
+    {
+        LabelArgs part = a;
+        part.graph = a.graph + ( size_t )f0 * a.width * a.height;
+        part.labels = a.labels + ( size_t )f0 * a.width * a.height;
+        part.n_frames = a.n_frames - f0 < 65535 ? a.n_frames - f0 : 65535;
+        cc_seam_kernel<<< dim3( ( seam_px + kThreads - 1 ) / kThreads, part.n_frames ), kThreads, 0, stream >>>( part );
+    }
     const size_t total = ( size_t )a.width * a.height * a.n_frames;
     cc_flatten_kernel<<< ( unsigned )( ( total + kThreads - 1 ) / kThreads ), kThreads, 0, stream >>>( a );
     if( n_launches ) *n_launches = 3;

@@ -40,7 +40,7 @@ struct par_context
 {
     int device = 0;
     int max_w = 0, max_h = 0, max_frames = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr; // copy_stream: D2H of par_remaster_host
     uint8_t *scratch_aux = nullptr, *scratch_graph = nullptr; // max_frames * max_w * max_h each
     CellRecord* d_tables = nullptr;        // kCellKeys 32-byte records
     uint32_t* d_mask_lut[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // per scale, built on first use
@@ -374,6 +374,7 @@ void par_destroy( par_context* c )
         cudaStreamSynchronize( c->own_stream );
         cudaStreamDestroy( c->own_stream );
     }
+    if( c->copy_stream ) cudaStreamDestroy( c->copy_stream );
     cudaFree( c->scratch_aux );
     cudaFree( c->scratch_graph );
     cudaFree( c->d_tables );
@@ -554,27 +555,58 @@ int par_remaster_host( par_context* c, const par_job* j )
             if( e != cudaSuccess ) return c->cuda_fail( e, "staging cudaMalloc" );
             c->h_stage_bytes[ k ] = need[ k ];
         }
-    cudaError_t e = cudaMemcpyAsync( c->h_stage[ 0 ], j->bgr, in_bytes, cudaMemcpyHostToDevice, c->stream );
-    if( e != cudaSuccess ) return c->cuda_fail( e, "H2D" );
-    par_job d = *j;
-    d.bgr = c->h_stage[ 0 ];
-    d.rgba = j->rgba ? c->h_stage[ 1 ] : nullptr;
-    d.graph = c->h_stage[ 2 ];
-    d.graph_aux = c->h_stage[ 3 ];
-    d.labels = j->labels ? reinterpret_cast< int32_t* >( c->h_stage[ 4 ] ) : nullptr;
-    d.polygons = j->polygons ? reinterpret_cast< float* >( c->h_stage[ 5 ] ) : nullptr;
-    d.poly_count = ( j->polygons && j->poly_count ) ? reinterpret_cast< int32_t* >( c->h_stage[ 6 ] ) : nullptr;
-    if( ( st = par_remaster_device( c, &d ) ) ) return st;
-    if( j->rgba ) e = cudaMemcpyAsync( j->rgba, d.rgba, out_px * 4, cudaMemcpyDeviceToHost, c->stream );
-    if( e == cudaSuccess && j->graph ) e = cudaMemcpyAsync( j->graph, d.graph, px, cudaMemcpyDeviceToHost, c->stream );
-    if( e == cudaSuccess && j->graph_aux ) e = cudaMemcpyAsync( j->graph_aux, d.graph_aux, px, cudaMemcpyDeviceToHost, c->stream );
-    if( e == cudaSuccess && j->labels ) e = cudaMemcpyAsync( j->labels, d.labels, px * 4, cudaMemcpyDeviceToHost, c->stream );
-    if( e == cudaSuccess && j->polygons )
-        e = cudaMemcpyAsync( j->polygons, d.polygons, px * PAR_CELL_SLOTS * 2 * sizeof( float ), cudaMemcpyDeviceToHost, c->stream );
-    if( e == cudaSuccess && d.poly_count ) e = cudaMemcpyAsync( j->poly_count, d.poly_count, px * 4, cudaMemcpyDeviceToHost, c->stream );
+    // The batch runs in chunks so that the copies overlap the kernels and each other: chunk k's results go back
+    // on a second stream (PCIe is full duplex) while chunk k+1 is uploaded and computed on the context's stream.
+    // Frames are independent, so chunking cannot change a result.
+    if( !c->copy_stream )
+    {
+        cudaError_t se = cudaStreamCreateWithFlags( &c->copy_stream, cudaStreamNonBlocking );
+        if( se != cudaSuccess ) return c->cuda_fail( se, "copy stream" );
+    }
+    const size_t fpx = ( size_t )j->width * j->height, fin = frame_stride_of( j ), fout = fpx * j->scale * j->scale * 4;
+    const int n_chunks = j->n_frames >= 64 ? 8 : 1;
+    std::vector< cudaEvent_t > done;
+    cudaError_t e = cudaSuccess;
+    for( int k = 0; k < n_chunks && e == cudaSuccess; k++ )
+    {
+        const int f0 = ( int )( ( long long )j->n_frames * k / n_chunks ), f1 = ( int )( ( long long )j->n_frames * ( k + 1 ) / n_chunks );
+        if( f1 == f0 ) continue;
+        const size_t nf = ( size_t )( f1 - f0 );
+        // (the last frame may be shorter than frame_stride in the caller's buffer: copy exactly what check_job validated)
+        const size_t in_n = ( f1 == j->n_frames && j->frame_stride ) ? ( nf - 1 ) * fin + ( size_t )j->widthstep * j->height : nf * fin;
+        e = cudaMemcpyAsync( c->h_stage[ 0 ] + f0 * fin, j->bgr + f0 * fin, in_n, cudaMemcpyHostToDevice, c->stream );
+        if( e != cudaSuccess ) return c->cuda_fail( e, "H2D" );
+        par_job d = *j;
+        d.n_frames = ( int )nf;
+        d.frame_stride = fin;
+        d.bgr = c->h_stage[ 0 ] + f0 * fin;
+        d.rgba = j->rgba ? c->h_stage[ 1 ] + f0 * fout : nullptr;
+        d.graph = c->h_stage[ 2 ] + f0 * fpx;
+        d.graph_aux = c->h_stage[ 3 ] + f0 * fpx;
+        d.labels = j->labels ? reinterpret_cast< int32_t* >( c->h_stage[ 4 ] ) + f0 * fpx : nullptr;
+        d.polygons = j->polygons ? reinterpret_cast< float* >( c->h_stage[ 5 ] ) + f0 * fpx * PAR_CELL_SLOTS * 2 : nullptr;
+        d.poly_count = ( j->polygons && j->poly_count ) ? reinterpret_cast< int32_t* >( c->h_stage[ 6 ] ) + f0 * fpx : nullptr;
+        if( ( st = par_remaster_device( c, &d ) ) ) return st;
+        cudaEvent_t ev = c->get_event();
+        done.push_back( ev );
+        e = cudaEventRecord( ev, c->stream );
+        if( e == cudaSuccess ) e = cudaStreamWaitEvent( c->copy_stream, ev, 0 );
+        cudaStream_t cs = c->copy_stream;
+        if( e == cudaSuccess && j->rgba ) e = cudaMemcpyAsync( j->rgba + f0 * fout, d.rgba, nf * fout, cudaMemcpyDeviceToHost, cs );
+        if( e == cudaSuccess && j->graph ) e = cudaMemcpyAsync( j->graph + f0 * fpx, d.graph, nf * fpx, cudaMemcpyDeviceToHost, cs );
+        if( e == cudaSuccess && j->graph_aux ) e = cudaMemcpyAsync( j->graph_aux + f0 * fpx, d.graph_aux, nf * fpx, cudaMemcpyDeviceToHost, cs );
+        if( e == cudaSuccess && j->labels ) e = cudaMemcpyAsync( j->labels + f0 * fpx, d.labels, nf * fpx * 4, cudaMemcpyDeviceToHost, cs );
+        if( e == cudaSuccess && j->polygons )
+            e = cudaMemcpyAsync( j->polygons + f0 * fpx * PAR_CELL_SLOTS * 2, d.polygons, nf * fpx * PAR_CELL_SLOTS * 2 * sizeof( float ),
+                                 cudaMemcpyDeviceToHost, cs );
+        if( e == cudaSuccess && d.poly_count ) e = cudaMemcpyAsync( j->poly_count + f0 * fpx, d.poly_count, nf * fpx * 4, cudaMemcpyDeviceToHost, cs );
+    }
+    cudaError_t e2 = cudaStreamSynchronize( c->copy_stream );
+    cudaError_t e3 = cudaStreamSynchronize( c->stream );
+    for( auto ev : done ) c->free_events.push_back( ev );
     if( e != cudaSuccess ) return c->cuda_fail( e, "D2H" );
-    e = cudaStreamSynchronize( c->stream );
-    return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "synchronize" );
+    if( e2 != cudaSuccess ) return c->cuda_fail( e2, "synchronize" );
+    return e3 == cudaSuccess ? PAR_OK : c->cuda_fail( e3, "synchronize" );
 }
 
 int par_cell_from_pattern( unsigned key, float* out_xy )
