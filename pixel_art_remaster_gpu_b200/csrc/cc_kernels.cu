@@ -7,9 +7,10 @@
 // canonical minimum-index label produced here, so any correct labeller is bit-exact.
 //
 // Design: lock-free union-find with link-by-minimum-index over the label array itself.
-//   (1) tile pass: one CTA per 64x16 tile builds the tile's forest in SHARED memory (init, union of
-//       every in-tile edge, flatten) and writes tile-local roots as global indices;
-//   (2) seam pass: threads on tile borders union across the seams with global atomicMin;
+//   (1) tile pass: one CTA per 64x16 tile builds the tile's forest in SHARED memory (horizontal runs by
+//       warp ballot, the few unions that can still connect two runs queued and executed one per lane,
+//       flatten) and writes tile-local roots as global indices;
+//   (2) seam pass: one thread per seam pixel unions across the seams with global atomicMin;
 //   (3) flatten pass: every pixel replaces its label by its root.
 // Roots only ever point to smaller indices, so the root of a set is its minimum index.
 // Algorithmic HBM traffic: 1 B/px in + 4 B/px out.
@@ -62,7 +63,10 @@ __device__ __forceinline__ void unite( int* lab, int a, int b )
 __global__ void __launch_bounds__( kThreads ) cc_tile_kernel( LabelArgs a )
 {
     __shared__ int s_lab[ kTW * kTH ];
-    __shared__ uint8_t s_g[ kTW * kTH ]; // node bytes with the links that leave the tile (or the image) removed
+    __shared__ uint8_t s_g[ kTW * kTH ];       // node bytes with the links that leave the tile (or the image) removed
+    __shared__ uint32_t s_req[ 3 * kTW * kTH + kTW * kTH / 32 ]; // queued unions, a << 16 | b (three per pixel, one more for a warp's last lane)
+    __shared__ int s_n;
+    if( threadIdx.x == 0 ) s_n = 0;
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH, f = blockIdx.z;
     const size_t frame_px = ( size_t )a.width * a.height;
     const uint8_t* g = a.graph + ( size_t )f * frame_px;
@@ -89,18 +93,48 @@ __global__ void __launch_bounds__( kThreads ) cc_tile_kernel( LabelArgs a )
         s_lab[ idx ] = idx - ( int )lane + start;
     }
     __syncthreads();
+    // the unions that are left are queued first and then executed one per lane: a warp that unites as it goes spends
+    // the time of its slowest lane three times per pixel (up, up-left, up-right), mostly on idle lanes
     for( int idx = threadIdx.x; idx < kTW * kTH; idx += kThreads )
     {
         const int lx = idx & ( kTW - 1 );
         const uint32_t node = s_g[ idx ];
-        if( ( node & 16u ) && lane == 31u ) unite( s_lab, idx, idx + 1 ); // a run that continues into the next warp's pixels
-        if( !( node & 7u ) ) continue;
-        const uint32_t left = lx > 0 ? s_g[ idx - 1 ] : 0u, right = lx + 1 < kTW ? s_g[ idx + 1 ] : 0u;
-        const uint32_t up = s_g[ idx + kTW ], up_left = lx > 0 ? s_g[ idx + kTW - 1 ] : 0u; // (only read when a link says the row exists)
-        const bool same_run_left = lane > 0u && ( left & 16u );                             // in the same run as the pixel to the left
-        if( ( node & 2u ) && !( same_run_left && ( left & 2u ) && ( up_left & 16u ) ) ) unite( s_lab, idx, idx + kTW );
-        if( ( node & 1u ) && !( ( ( node & 2u ) && ( up_left & 16u ) ) || ( same_run_left && ( left & 2u ) ) ) ) unite( s_lab, idx, idx + kTW - 1 );
-        if( ( node & 4u ) && !( ( ( node & 2u ) && ( up & 16u ) ) || ( lane < 31u && ( node & 16u ) && ( right & 2u ) ) ) ) unite( s_lab, idx, idx + kTW + 1 );
+        uint32_t want = ( ( node & 16u ) && lane == 31u ) ? 8u : 0u; // a run that continues into the next warp's pixels
+        if( node & 7u )
+        {
+            const uint32_t left = lx > 0 ? s_g[ idx - 1 ] : 0u, right = lx + 1 < kTW ? s_g[ idx + 1 ] : 0u;
+            const uint32_t up = s_g[ idx + kTW ], up_left = lx > 0 ? s_g[ idx + kTW - 1 ] : 0u; // (a link says the row above exists)
+            const bool same_run_left = lane > 0u && ( left & 16u );                             // in the same run as the pixel to the left
+            if( ( node & 2u ) && !( same_run_left && ( left & 2u ) && ( up_left & 16u ) ) ) want |= 2u;
+            if( ( node & 1u ) && !( ( ( node & 2u ) && ( up_left & 16u ) ) || ( same_run_left && ( left & 2u ) ) ) ) want |= 1u;
+            if( ( node & 4u ) && !( ( ( node & 2u ) && ( up & 16u ) ) || ( lane < 31u && ( node & 16u ) && ( right & 2u ) ) ) ) want |= 4u;
+        }
+        // slots for this warp's requests: one shared atomic per warp
+        const int mine = __popc( want );
+        int before = mine;
+#pragma unroll
+        for( int d = 1; d < 32; d <<= 1 )
+        {
+            const int v = __shfl_up_sync( 0xFFFFFFFFu, before, d );
+            if( ( int )lane >= d ) before += v;
+        }
+        int base = 0;
+        if( lane == 31u && before ) base = atomicAdd( &s_n, before );
+        base = __shfl_sync( 0xFFFFFFFFu, base, 31 );
+        int slot = base + before - mine;
+        if( want & 8u ) s_req[ slot++ ] = ( uint32_t )idx << 16 | ( uint32_t )( idx + 1 );
+        if( want & 2u ) s_req[ slot++ ] = ( uint32_t )idx << 16 | ( uint32_t )( idx + kTW );
+        if( want & 1u ) s_req[ slot++ ] = ( uint32_t )idx << 16 | ( uint32_t )( idx + kTW - 1 );
+        if( want & 4u ) s_req[ slot++ ] = ( uint32_t )idx << 16 | ( uint32_t )( idx + kTW + 1 );
+    }
+    __syncthreads();
+    {
+        const int n = s_n;
+        for( int w = threadIdx.x; w < n; w += kThreads )
+        {
+            const uint32_t r = s_req[ w ];
+            unite( s_lab, ( int )( r >> 16 ), ( int )( r & 0xFFFFu ) );
+        }
     }
     __syncthreads();
     for( int idx = threadIdx.x; idx < kTW * kTH; idx += kThreads )
