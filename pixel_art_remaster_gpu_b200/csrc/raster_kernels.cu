@@ -315,6 +315,41 @@ __device__ __noinline__ uint32_t window_coverage_bits( const uint16_t* keys, con
     return bits;
 }
 
+// Exact resolve of a whole tile (packed scales): every candidate's coverage of every pixel recomputed from its
+// polygon.  Only runs for tiles that contain a cell reaching beyond its mask, or under PAR_FLAG_DEBUG_WIDE.
+template< int S >
+__device__ __noinline__ void resolve_tile_exact( const uint16_t* keys, const uint32_t* cols, int x0, int y0, const uint8_t* frame, int width, int height,
+                                                 int widthstep, const CellRecord* rec, bool subdivide, uint8_t* out, bool flip )
+{
+    typedef Cfg< S > C;
+    const size_t out_w = ( size_t )width * S, out_h = ( size_t )height * S;
+    for( int idx = threadIdx.x; idx < C::TW * C::TH; idx += kThreads )
+    {
+        const int ly = idx / C::TW, lx = idx - ly * C::TW, gx = x0 + lx, gy = y0 + ly;
+        if( gx >= width || gy >= height ) continue;
+        const uint32_t* col = cols + ( ly + 2 ) * C::KW + ( lx + 2 );
+        uint32_t px[ S * S ], rem = C::ALL;
+        for( int bit = 0; bit < S * S; bit++ ) px[ bit ] = 0xFF000000u; // background (main.cpp:260)
+        // candidates in DESCENDING node index
+        for( int dj = 1; dj >= -1; dj-- )
+            for( int di = 1; di >= -1; di-- )
+            {
+                const int ci = gx + di, cj = gy + dj;
+                if( ci < 0 || cj < 0 || ci >= width || cj >= height ) continue;
+                const uint32_t take = window_coverage_bits< S >( keys, cols, x0, y0, frame, width, height, widthstep, rec, ci, cj, di, dj, subdivide ) & rem;
+                rem &= ~take;
+                const uint32_t cw = col[ dj * C::KW + di ];
+                for( int bit = 0; bit < S * S; bit++ )
+                    if( ( take >> bit ) & 1u ) px[ bit ] = cw;
+            }
+        for( int b = 0; b < S; b++ )
+        {
+            const size_t oy = flip ? ( out_h - 1 - ( ( size_t )gy * S + b ) ) : ( ( size_t )gy * S + b );
+            store_row< S >( out + ( oy * out_w + ( size_t )gx * S ) * 4, px + S * b );
+        }
+    }
+}
+
 // mask of a cell whose polygon is its plain hull, for every key: the per-scale table the raster kernel copies from
 struct NoEnv
 {
@@ -857,9 +892,15 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 4 : 3 ) raster_kernel( con
     const ptrdiff_t row_step = a.flip_output ? -( ptrdiff_t )( out_w * 4 ) : ( ptrdiff_t )( out_w * 4 ); // bytes from one output row to the next
     if constexpr( C::PACK )
     {
+        if( s_nwork[ 2 ] != 0 || a.debug_force_wide )
+        {
+            // some cell of this tile reaches beyond its mask (never seen on real frames): the whole tile is resolved by
+            // the exact path, kept out of line so that it costs the common path neither registers nor code
+            resolve_tile_exact< S >( s_keys, s_col, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, subdivide, out, a.flip_output != 0 );
+            return;
+        }
         // Window form: every candidate's coverage of my S x S output pixels is one masked 16-bit field of its
         // mask, so the priority resolve runs once on whole-cell bit sets instead of once per output row.
-        const bool tile_wide = s_nwork[ 2 ] != 0 || a.debug_force_wide;
         for( int idx = tid; idx < C::TW * C::TH; idx += kThreads )
         {
             int ly = idx / C::TW, lx = idx - ly * C::TW;
@@ -868,93 +909,42 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 4 : 3 ) raster_kernel( con
             const uint32_t* mlo = s_mask + ( ly + 1 ) * C::CW + ( lx + 1 ); // F0 | F1 << 16
             const uint32_t* mhi = mlo + C::NC;                             // F2 | F3 << 16
             const uint32_t* col = s_col + ( ly + 2 ) * C::KW + ( lx + 2 );
-            // candidates in DESCENDING node index: (dj,di) = (+1,+1) (+1,0) (+1,-1) (0,+1) (0,0) (0,-1) (-1,+1) (-1,0) (-1,-1)
-            uint32_t cov[ 9 ];
-            bool slow = false;
-            if( tile_wide )
-            {
-                uint32_t wide = 0u;
-#pragma unroll
-                for( int dj = -1; dj <= 1; dj++ )
-#pragma unroll
-                    for( int di = -1; di <= 1; di++ ) wide |= mhi[ dj * C::CW + di ];
-                slow = ( wide & C::WIDE ) != 0u;
-            }
             uint32_t px[ S * S ];
             const uint32_t own = col[ 0 ];
 #pragma unroll
             for( int k = 0; k < S * S; k++ ) px[ k ] = own;
-            bool done = false;
-            if( !slow )
+            // candidates in DESCENDING node index: (dj,di) = (+1,+1) (+1,0) (+1,-1) (0,+1) (0,0) (0,-1) (-1,+1) (-1,0) (-1,-1);
+            // the four drawn after this cell, then the cell itself: most pixels are settled by those
+            uint32_t cov[ 9 ];
+            cov[ 0 ] = ( mhi[ C::CW + 1 ] >> 16 ) & ( 1u << ( S * S - 1 ) );
+            cov[ 1 ] = mhi[ C::CW ] & C::M_TOPROW;
+            cov[ 2 ] = ( mhi[ C::CW - 1 ] >> 16 ) & ( 1u << ( S * ( S - 1 ) ) );
+            cov[ 3 ] = ( mlo[ 1 ] >> 16 ) & C::M_RIGHTCOL;
+            cov[ 4 ] = mlo[ 0 ] & C::ALL;
+            if( C::H == 0 ) cov[ 0 ] = cov[ 1 ] = cov[ 2 ] = cov[ 3 ] = 0u; // no halo samples at this scale
+            if( ( cov[ 4 ] & ~( cov[ 0 ] | cov[ 1 ] | cov[ 2 ] | cov[ 3 ] ) ) != C::ALL )
             {
-                // the four candidates drawn after this cell, then the cell itself: most pixels are settled here
-                cov[ 0 ] = ( mhi[ C::CW + 1 ] >> 16 ) & ( 1u << ( S * S - 1 ) );
-                cov[ 1 ] = mhi[ C::CW ] & C::M_TOPROW;
-                cov[ 2 ] = ( mhi[ C::CW - 1 ] >> 16 ) & ( 1u << ( S * ( S - 1 ) ) );
-                cov[ 3 ] = ( mlo[ 1 ] >> 16 ) & C::M_RIGHTCOL;
-                cov[ 4 ] = mlo[ 0 ] & C::ALL;
-                if( C::H == 0 ) cov[ 0 ] = cov[ 1 ] = cov[ 2 ] = cov[ 3 ] = 0u; // no halo samples at this scale
-                done = ( cov[ 4 ] & ~( cov[ 0 ] | cov[ 1 ] | cov[ 2 ] | cov[ 3 ] ) ) == C::ALL;
-                if( !done )
-                {
-                    cov[ 5 ] = ( mlo[ -1 ] >> 16 ) & C::M_LEFTCOL;
-                    cov[ 6 ] = ( mhi[ -C::CW + 1 ] >> 16 ) & ( 1u << ( S - 1 ) );
-                    cov[ 7 ] = mhi[ -C::CW ] & C::M_BOTROW;
-                    cov[ 8 ] = ( mhi[ -C::CW - 1 ] >> 16 ) & 1u;
-                    if( C::H == 0 ) cov[ 5 ] = cov[ 6 ] = cov[ 7 ] = cov[ 8 ] = 0u;
-                }
-            }
-            else
-            {
-                // some cell around reaches beyond its mask: recompute every candidate's coverage exactly
-#pragma unroll
-                for( int k = 0; k < 9; k++ ) // (unrolled: cov[] must stay in registers)
-                {
-                    const int dj = 1 - k / 3, di = 1 - k % 3;
-                    const int ci = gx + di, cj = gy + dj;
-                    cov[ k ] = 0u;
-                    if( ci < 0 || cj < 0 || ci >= a.width || cj >= a.height ) continue;
-                    cov[ k ] = window_coverage_bits< S >( s_keys, s_col, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, ci, cj, di, dj, subdivide );
-                }
-            }
-            if( !done )
-            {
-                uint32_t rem = C::ALL, take[ 9 ];
+                cov[ 5 ] = ( mlo[ -1 ] >> 16 ) & C::M_LEFTCOL;
+                cov[ 6 ] = ( mhi[ -C::CW + 1 ] >> 16 ) & ( 1u << ( S - 1 ) );
+                cov[ 7 ] = mhi[ -C::CW ] & C::M_BOTROW;
+                cov[ 8 ] = ( mhi[ -C::CW - 1 ] >> 16 ) & 1u;
+                if( C::H == 0 ) cov[ 5 ] = cov[ 6 ] = cov[ 7 ] = cov[ 8 ] = 0u;
+                uint32_t rem = C::ALL;
 #pragma unroll
                 for( int k = 0; k < 9; k++ )
                 {
-                    take[ k ] = cov[ k ] & rem;
+                    const uint32_t take = cov[ k ] & rem;
                     rem &= ~cov[ k ];
-                }
-                if( slow )
-                {
-                    // after the exact path a candidate may hold any pixel of the cell
+                    if( k == 4 || take == 0u ) continue;
+                    const int dj = 1 - k / 3, di = 1 - k % 3;
+                    const uint32_t cw = col[ dj * C::KW + di ];
+                    // a candidate can only hold pixels of its own window
 #pragma unroll
-                    for( int k = 0; k < 9; k++ )
+                    for( int bit = 0; bit < S * S; bit++ )
                     {
-                        if( take[ k ] == 0u ) continue;
-                        const uint32_t cw = col[ ( 1 - k / 3 ) * C::KW + 1 - k % 3 ];
-#pragma unroll
-                        for( int bit = 0; bit < S * S; bit++ )
-                            if( ( take[ k ] >> bit ) & 1u ) px[ bit ] = cw;
-                    }
-                }
-                else
-                {
-#pragma unroll
-                    for( int k = 0; k < 9; k++ )
-                    {
-                        if( k == 4 || take[ k ] == 0u ) continue;
-                        const int dj = 1 - k / 3, di = 1 - k % 3;
-                        const uint32_t cw = col[ dj * C::KW + di ];
-                        // a candidate can only hold pixels of its own window
-#pragma unroll
-                        for( int bit = 0; bit < S * S; bit++ )
-                        {
-                            const int bx = bit % S, by = bit / S;
-                            const bool in_window = ( di == 0 || bx == ( di > 0 ? S - 1 : 0 ) ) && ( dj == 0 || by == ( dj > 0 ? S - 1 : 0 ) );
-                            if( in_window && ( ( take[ k ] >> bit ) & 1u ) ) px[ bit ] = cw;
-                        }
+                        const int bx = bit % S, by = bit / S;
+                        const bool in_window = ( di == 0 || bx == ( di > 0 ? S - 1 : 0 ) ) && ( dj == 0 || by == ( dj > 0 ? S - 1 : 0 ) );
+                        if( in_window && ( ( take >> bit ) & 1u ) ) px[ bit ] = cw;
                     }
                 }
                 if( rem ) // nobody covers these: background (main.cpp:260)
