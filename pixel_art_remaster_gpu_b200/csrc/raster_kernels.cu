@@ -304,19 +304,8 @@ __device__ __noinline__ void window_coverage( const uint16_t* keys, const uint32
     cover_polygon< S, S >( verts, 1, poly, C::SSP / 2 - di * C::SQUARE, C::SSP / 2 - dj * C::SQUARE, tg, lo, hi );
 }
 
-// the same as one bit set over the S x S pixels of the target cell (bit S*y + x), S <= 4
-template< int S >
-__device__ __noinline__ uint32_t window_coverage_bits( const uint16_t* keys, const uint32_t* cols, int x0, int y0, const uint8_t* frame, int width,
-                                                       int height, int widthstep, const CellRecord* rec, int ci, int cj, int di, int dj, bool subdivide )
-{
-    uint32_t win[ S ], bits = 0u;
-    window_coverage< S >( keys, cols, x0, y0, frame, width, height, widthstep, rec, ci, cj, di, dj, subdivide, win );
-    for( int r = 0; r < S; r++ ) bits |= win[ r ] << ( S * r );
-    return bits;
-}
-
-// Exact resolve of a whole tile (packed scales): every candidate's coverage of every pixel recomputed from its
-// polygon.  Only runs for tiles that contain a cell reaching beyond its mask, or under PAR_FLAG_DEBUG_WIDE.
+// Exact resolve of a whole tile: every candidate's coverage of every pixel recomputed from its polygon.  Only runs
+// for tiles that contain a cell reaching beyond its mask, or under PAR_FLAG_DEBUG_WIDE.
 template< int S >
 __device__ __noinline__ void resolve_tile_exact( const uint16_t* keys, const uint32_t* cols, int x0, int y0, const uint8_t* frame, int width, int height,
                                                  int widthstep, const CellRecord* rec, bool subdivide, uint8_t* out, bool flip )
@@ -328,19 +317,25 @@ __device__ __noinline__ void resolve_tile_exact( const uint16_t* keys, const uin
         const int ly = idx / C::TW, lx = idx - ly * C::TW, gx = x0 + lx, gy = y0 + ly;
         if( gx >= width || gy >= height ) continue;
         const uint32_t* col = cols + ( ly + 2 ) * C::KW + ( lx + 2 );
-        uint32_t px[ S * S ], rem = C::ALL;
-        for( int bit = 0; bit < S * S; bit++ ) px[ bit ] = 0xFF000000u; // background (main.cpp:260)
+        uint32_t px[ S * S ], rem[ S ];
+        for( int k = 0; k < S * S; k++ ) px[ k ] = 0xFF000000u; // background (main.cpp:260)
+        for( int b = 0; b < S; b++ ) rem[ b ] = C::FULL;
         // candidates in DESCENDING node index
         for( int dj = 1; dj >= -1; dj-- )
             for( int di = 1; di >= -1; di-- )
             {
                 const int ci = gx + di, cj = gy + dj;
                 if( ci < 0 || cj < 0 || ci >= width || cj >= height ) continue;
-                const uint32_t take = window_coverage_bits< S >( keys, cols, x0, y0, frame, width, height, widthstep, rec, ci, cj, di, dj, subdivide ) & rem;
-                rem &= ~take;
+                uint32_t win[ S ];
+                window_coverage< S >( keys, cols, x0, y0, frame, width, height, widthstep, rec, ci, cj, di, dj, subdivide, win );
                 const uint32_t cw = col[ dj * C::KW + di ];
-                for( int bit = 0; bit < S * S; bit++ )
-                    if( ( take >> bit ) & 1u ) px[ bit ] = cw;
+                for( int b = 0; b < S; b++ )
+                {
+                    const uint32_t take = win[ b ] & rem[ b ];
+                    rem[ b ] &= ~take;
+                    for( int k = 0; k < S; k++ )
+                        if( ( take >> k ) & 1u ) px[ S * b + k ] = cw;
+                }
             }
         for( int b = 0; b < S; b++ )
         {
@@ -628,7 +623,7 @@ __device__ __forceinline__ bool smooth_lookup( const SmoothTablePtrs& st, const 
 }
 
 template< int S, bool kUseTma >
-__global__ void __launch_bounds__( kThreads, S <= 4 ? 4 : 3 ) raster_kernel( const __grid_constant__ CUtensorMap graph_map, const __grid_constant__ CUtensorMap img_map,
+__global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( const __grid_constant__ CUtensorMap graph_map, const __grid_constant__ CUtensorMap img_map,
                                                            RasterArgs a )
 {
     typedef Cfg< S > C;
@@ -836,6 +831,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 4 : 3 ) raster_kernel( con
                         const uint32_t row = ( uint32_t )( mw[ r >> 2 ] >> ( 16 * ( r & 3 ) ) ) & 0x7FFFu;
                         s_mask[ r * C::NC + idx ] = row | ( ( r == 0 && wide ) ? C::WIDE : 0u );
                     }
+                    if( wide ) s_nwork[ 2 ] = 1;
                 }
             }
             else
@@ -876,6 +872,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 4 : 3 ) raster_kernel( con
                 cover_polygon< S, C::R >( vbuf, kThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
                 const uint32_t wide = ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
                 s_mask[ idx ] |= wide;
+                if( wide ) s_nwork[ 2 ] = 1;
             }
         }
     }
@@ -890,15 +887,15 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 4 : 3 ) raster_kernel( con
     const size_t out_w = ( size_t )a.width * S, out_h = ( size_t )a.height * S;
     uint8_t* out = a.rgba + ( size_t )f * out_w * out_h * 4;
     const ptrdiff_t row_step = a.flip_output ? -( ptrdiff_t )( out_w * 4 ) : ( ptrdiff_t )( out_w * 4 ); // bytes from one output row to the next
+    if( s_nwork[ 2 ] != 0 || a.debug_force_wide )
+    {
+        // some cell of this tile reaches beyond its mask (never seen on real frames): the whole tile is resolved by
+        // the exact path, kept out of line so that it costs the common path neither registers nor code
+        resolve_tile_exact< S >( s_keys, s_col, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, subdivide, out, a.flip_output != 0 );
+        return;
+    }
     if constexpr( C::PACK )
     {
-        if( s_nwork[ 2 ] != 0 || a.debug_force_wide )
-        {
-            // some cell of this tile reaches beyond its mask (never seen on real frames): the whole tile is resolved by
-            // the exact path, kept out of line so that it costs the common path neither registers nor code
-            resolve_tile_exact< S >( s_keys, s_col, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, subdivide, out, a.flip_output != 0 );
-            return;
-        }
         // Window form: every candidate's coverage of my S x S output pixels is one masked 16-bit field of its
         // mask, so the priority resolve runs once on whole-cell bit sets instead of once per output row.
         for( int idx = tid; idx < C::TW * C::TH; idx += kThreads )
@@ -970,12 +967,6 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 4 : 3 ) raster_kernel( con
             const uint32_t* col = s_col + ( ly + 2 ) * C::KW + ( lx + 2 );
             // the 3x3 neighbourhood's masks; candidates are visited in DESCENDING node index:
             // (dj,di) = (+1,+1) (+1,0) (+1,-1) (0,+1) (0,0) (0,-1) (-1,+1) (-1,0) (-1,-1)
-            uint32_t wide = 0;
-#pragma unroll
-            for( int dj = -1; dj <= 1; dj++ )
-#pragma unroll
-                for( int di = -1; di <= 1; di++ ) wide |= s_mask[ cell + dj * C::CW + di ];
-            wide &= C::WIDE;
 #pragma unroll 1
             for( int b = 0; b < S; b++ )
             {
@@ -983,50 +974,26 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 4 : 3 ) raster_kernel( con
 #pragma unroll
                 for( int k = 0; k < S; k++ ) px[ k ] = 0xFF000000u; // background (main.cpp:260)
                 uint32_t rem = C::FULL;
-                if( !wide )
+#pragma unroll
+                for( int dj = 1; dj >= -1; dj-- )
                 {
+                    const int ky = b - dj * S + C::H;
+                    if( ky < 0 || ky >= C::R ) continue;
 #pragma unroll
-                    for( int dj = 1; dj >= -1; dj-- )
+                    for( int di = 1; di >= -1; di-- )
                     {
-                        const int ky = b - dj * S + C::H;
-                        if( ky < 0 || ky >= C::R ) continue;
-#pragma unroll
-                        for( int di = 1; di >= -1; di-- )
+                        const uint32_t m = s_mask[ ky * C::NC + cell + dj * C::CW + di ] & ~C::WIDE;
+                        const uint32_t field = di == 0 ? ( m >> C::H ) : ( di > 0 ? ( m << ( S - C::H ) ) : ( m >> ( S + C::H ) ) );
+                        const uint32_t take = field & rem;
+                        if( take )
                         {
-                            const uint32_t m = s_mask[ ky * C::NC + cell + dj * C::CW + di ] & ~C::WIDE;
-                            const uint32_t field = di == 0 ? ( m >> C::H ) : ( di > 0 ? ( m << ( S - C::H ) ) : ( m >> ( S + C::H ) ) );
-                            const uint32_t take = field & rem;
-                            if( take )
-                            {
-                                const uint32_t cw = col[ dj * C::KW + di ];
+                            const uint32_t cw = col[ dj * C::KW + di ];
 #pragma unroll
-                                for( int k = 0; k < S; k++ )
-                                    if( ( take >> k ) & 1u ) px[ k ] = cw;
-                                rem &= ~take;
-                            }
+                            for( int k = 0; k < S; k++ )
+                                if( ( take >> k ) & 1u ) px[ k ] = cw;
+                            rem &= ~take;
                         }
                     }
-                }
-                else
-                {
-                    // some cell around reaches beyond its mask: recompute every candidate's coverage of this row exactly
-                    for( int dj = 1; dj >= -1; dj-- )
-                        for( int di = 1; di >= -1; di-- )
-                        {
-                            const int ci = gx + di, cj = gy + dj;
-                            if( ci < 0 || cj < 0 || ci >= a.width || cj >= a.height ) continue;
-                            uint32_t win[ S ];
-                            window_coverage< S >( s_keys, s_col, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, ci, cj, di, dj, subdivide, win );
-                            const uint32_t take = win[ b ] & rem;
-                            if( take )
-                            {
-                                const uint32_t cw = col[ dj * C::KW + di ];
-#pragma unroll
-                                for( int k = 0; k < S; k++ )
-                                    if( ( take >> k ) & 1u ) px[ k ] = cw;
-                                rem &= ~take;
-                            }
-                        }
                 }
                 const size_t oy = a.flip_output ? ( out_h - 1 - ( ( size_t )gy * S + b ) ) : ( ( size_t )gy * S + b );
                 store_row< S >( out + ( oy * out_w + ( size_t )gx * S ) * 4, px );
