@@ -47,6 +47,17 @@ def workload(n_frames=FRAMES_PER_GPU):
             "subdivision on, CC labels off" % n_frames)
 
 
+def profiled_traffic_per_frame():
+    """DRAM bytes (read + write) per frame of the raster kernel from the committed `ncu --set full` capture
+    (profiles/r1_raster_traffic.json, written by tools/ncu_traffic.py); None when the capture is absent."""
+    p = os.path.join(ROOT, "profiles", "r1_raster_traffic.json")
+    try:
+        t = json.load(open(p))
+        return float(t["dram_bytes_per_frame"]), t.get("source", "profiles/r1_raster_traffic.json")
+    except Exception:
+        return None, None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -287,6 +298,7 @@ def run_ours(args):
                                    "what": "the reference's default (simpleVBO.cpp:43 subdivide = false): hull cells only"}
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
+        traffic_pf, traffic_src = profiled_traffic_per_frame()
         r_ms, r_n = prof["raster"]
         px = n_frames * W * H
         raster_gbs = (RASTER_BYTES_PER_PX * px) / ((r_ms / max(r_n, 1)) * 1e-3) / 1e9
@@ -301,8 +313,12 @@ def run_ours(args):
                        "algorithmic_bytes_per_frame": ALGO_BYTES_PER_PX * W * H},
             "hbm_gbs_algorithmic": value / world * ALGO_BYTES_PER_PX * W * H / 1e9,
             "roofline": {"kernel": "raster_kernel<4> (cells + subdivision + direct raster)", "bound": "hbm",
-                         "achieved": raster_gbs, "peak": peak, "unit": "GB/s", "frac": raster_gbs / peak, "traffic": None,
-                         "peak_source": peak_src, "launch_ms": r_ms / max(r_n, 1), "bytes_per_launch": RASTER_BYTES_PER_PX * px},
+                         "achieved": raster_gbs, "peak": peak, "unit": "GB/s", "frac": raster_gbs / peak,
+                         "traffic": (traffic_pf * n_frames) if traffic_pf else None, "traffic_source": traffic_src,
+                         "peak_source": peak_src, "launch_ms": r_ms / max(r_n, 1), "bytes_per_launch": RASTER_BYTES_PER_PX * px,
+                         "other_kernels": {k: {"launch_ms": stage_ms[k], "achieved": b * px / (stage_ms[k] * 1e-3) / 1e9,
+                                               "frac": b * px / (stage_ms[k] * 1e-3) / 1e9 / peak, "bytes_per_px": b}
+                                           for k, b in (("similarity_graph", 4), ("resolve_crossings", 2)) if k in stage_ms}},
             "stage_ms_per_step": stage_ms,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(pin_in.numel()),
                     "d2h_bytes_per_step": int(pin_out["rgba"].numel() + pin_out["graph"].numel()),
