@@ -11,6 +11,10 @@ for (W, H, S) in ((96, 80, 4), (50, 37, 8), (65, 33, 3)):
         for no_tma in (False, True):
             out = ctx.remaster(frames, S, True, want=("rgba", "graph", "graph_aux", "labels", "polygons"), no_tma=no_tma)
             out = ctx.remaster(frames, S, True, want=("rgba",), no_tma=no_tma)  # smoothing tables
+            ctx.no_tables = True
+            out = ctx.remaster(frames, S, True, want=("rgba",), no_tma=no_tma)  # geometric path for every smoothed cell
+            ctx.no_tables = False
+            out = ctx.remaster(frames, S, False, want=("rgba",), no_tma=no_tma)  # hull cells only
         torch.cuda.synchronize()
 img = synth.adversarial_sprite(96, 100, 3)
 par.launch_kernel(img, True)
