@@ -65,6 +65,12 @@ enum
     ,
     PAR_FLAG_DEBUG_WIDE = 1u << 3   /* test hook: rasterize every cell through the exact slow path that
                                        normally only handles cells reaching beyond their sample mask */
+    ,
+    /* Anti-aliased output (the reference's GL_MULTISAMPLE toggle, simpleVBO.cpp:238-253, main.cpp:233): every output
+     * pixel is the mean of 2x2 / 4x4 ordered-grid samples (the point-sampling rule at 2x / 4x the scale, averaged per
+     * channel, halves rounded up).  scale x samples must be a supported scale: AA2 with scale 1,2,3,4; AA4 with 1,2. */
+    PAR_FLAG_AA2 = 1u << 5,
+    PAR_FLAG_AA4 = 1u << 6
 };
 
 typedef struct par_context par_context;

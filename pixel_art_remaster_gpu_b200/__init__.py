@@ -21,7 +21,7 @@ __all__ = ["Remaster", "RemasterGroup", "launch_kernel", "RemasterError", "load_
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CELL_SLOTS = 45
-FLAG_SUBDIVIDE, FLAG_FLIP_OUTPUT, FLAG_NO_TMA, FLAG_DEBUG_WIDE, FLAG_NO_SMOOTH_TABLES = 1, 2, 4, 8, 16
+FLAG_SUBDIVIDE, FLAG_FLIP_OUTPUT, FLAG_NO_TMA, FLAG_DEBUG_WIDE, FLAG_NO_SMOOTH_TABLES, FLAG_AA2, FLAG_AA4 = 1, 2, 4, 8, 16, 32, 64
 _STATUS = {0: "PAR_OK", 1: "PAR_ERR_INVALID", 2: "PAR_ERR_NO_DEVICE", 3: "PAR_ERR_CUDA", 4: "PAR_ERR_CAPACITY"}
 
 
@@ -215,10 +215,11 @@ class Remaster:
         return o
 
     no_tables = False  # set True to bypass the smoothing tables (geometric path for every smoothed cell) on every call of this context
+    aa = 1             # samples per output pixel and axis (1 = point sampling, 2 or 4 = anti-aliased: PAR_FLAG_AA2 / AA4)
 
     def _flags(self, subdivide, flip_output, no_tma):
         return (FLAG_SUBDIVIDE if subdivide else 0) | (FLAG_FLIP_OUTPUT if flip_output else 0) | (FLAG_NO_TMA if no_tma else 0) | \
-            (FLAG_NO_SMOOTH_TABLES if self.no_tables else 0)
+            (FLAG_NO_SMOOTH_TABLES if self.no_tables else 0) | {1: 0, 2: FLAG_AA2, 4: FLAG_AA4}[self.aa]
 
     # -- whole path ------------------------------------------------------------------------
     def remaster(self, frames, scale=4, subdivide=True, want=("rgba",), out=None, flip_output=False, no_tma=False):

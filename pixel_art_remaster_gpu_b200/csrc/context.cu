@@ -226,7 +226,8 @@ RasterArgs raster_args( par_context* c, const par_job* j, const uint8_t* graph )
     a.widthstep = j->widthstep;
     a.n_frames = j->n_frames;
     a.frame_stride = frame_stride_of( j );
-    a.scale = j->scale;
+    a.aa = ( j->flags & PAR_FLAG_AA4 ) ? 4 : ( ( j->flags & PAR_FLAG_AA2 ) ? 2 : 1 );
+    a.scale = j->scale * a.aa; // the kernels' sampling scale
     a.subdivide = ( j->flags & PAR_FLAG_SUBDIVIDE ) ? 1 : 0;
     a.flip_output = ( j->flags & PAR_FLAG_FLIP_OUTPUT ) ? 1 : 0;
     a.debug_force_wide = ( j->flags & PAR_FLAG_DEBUG_WIDE ) ? 1 : 0;
@@ -245,47 +246,50 @@ int run_polygons( par_context* c, const par_job* j, const uint8_t* graph )
 
 int run_raster( par_context* c, const par_job* j, const uint8_t* graph )
 {
-    if( !raster_scale_supported( j->scale ) ) return c->fail( PAR_ERR_INVALID, "unsupported scale %d (supported: 1,2,3,4,6,8)", j->scale );
     RasterArgs a = raster_args( c, j, graph );
-    if( !c->d_mask_lut[ j->scale ] )
+    if( !raster_aa_supported( j->scale, a.aa ) )
+        return c->fail( PAR_ERR_INVALID, "unsupported scale %d with %dx%d samples per pixel (scale x samples must be one of 1,2,3,4,6,8)", j->scale,
+                        a.aa, a.aa );
+    const int S = a.scale; // the sampling scale: tables and tile shapes depend on it
+    if( !c->d_mask_lut[ S ] )
     {
         // coverage masks of the 4096 plain hulls at this scale, computed once by the device's own coverage code
-        cudaError_t le = cudaMalloc( &c->d_mask_lut[ j->scale ], mask_lut_words( j->scale ) * sizeof( uint32_t ) );
-        if( le == cudaSuccess ) le = launch_build_mask_lut( j->scale, c->tables(), c->d_mask_lut[ j->scale ], c->stream );
+        cudaError_t le = cudaMalloc( &c->d_mask_lut[ S ], mask_lut_words( S ) * sizeof( uint32_t ) );
+        if( le == cudaSuccess ) le = launch_build_mask_lut( S, c->tables(), c->d_mask_lut[ S ], c->stream );
         c->launches++;
         if( le != cudaSuccess ) return c->cuda_fail( le, "mask table" );
     }
-    a.mask_lut = c->d_mask_lut[ j->scale ];
+    a.mask_lut = c->d_mask_lut[ S ];
     a.smooth = SmoothTablePtrs{ c->d_smooth_rec, nullptr, nullptr };
     a.smooth_stats = c->d_smooth_stats;
     if( a.subdivide && !( j->flags & PAR_FLAG_NO_SMOOTH_TABLES ) )
     {
-        if( !c->d_cut[ j->scale ] )
+        if( !c->d_cut[ S ] )
         {
             // CUT / LINK masks at this scale, computed once by the device's own coverage code
-            const size_t ew = smooth_entry_words( j->scale ) * sizeof( uint64_t );
-            cudaError_t me = cudaMalloc( &c->d_cut[ j->scale ], ( size_t )kCellKeys * 16 * ew );
-            if( me == cudaSuccess ) me = cudaMalloc( &c->d_link[ j->scale ], ( size_t )c->link_entries * ew );
+            const size_t ew = smooth_entry_words( S ) * sizeof( uint64_t );
+            cudaError_t me = cudaMalloc( &c->d_cut[ S ], ( size_t )kCellKeys * 16 * ew );
+            if( me == cudaSuccess ) me = cudaMalloc( &c->d_link[ S ], ( size_t )c->link_entries * ew );
             if( me == cudaSuccess )
-                me = launch_build_smooth_tables( j->scale, c->tables(), c->d_link_classes, c->n_link_classes, c->d_cut[ j->scale ], c->d_link[ j->scale ],
+                me = launch_build_smooth_tables( S, c->tables(), c->d_link_classes, c->n_link_classes, c->d_cut[ S ], c->d_link[ S ],
                                                  c->stream );
             c->launches += 2;
             if( me != cudaSuccess )
             {
-                cudaFree( c->d_cut[ j->scale ] );
-                c->d_cut[ j->scale ] = nullptr;
+                cudaFree( c->d_cut[ S ] );
+                c->d_cut[ S ] = nullptr;
                 return c->cuda_fail( me, "smoothing tables" );
             }
         }
-        a.smooth.cut = c->d_cut[ j->scale ];
-        a.smooth.link = c->d_link[ j->scale ];
+        a.smooth.cut = c->d_cut[ S ];
+        a.smooth.link = c->d_link[ S ];
     }
     CUtensorMap map;
     uint32_t box[ 3 ];
-    raster_tma_box( j->scale, box );
+    raster_tma_box( S, box );
     bool tma = graph_map( c, j, graph, box, &map );
     CUtensorMap img_map;
-    raster_img_tma_box( j->scale, box );
+    raster_img_tma_box( S, box );
     tma = tma && c->make_map( &img_map, j->bgr, 3ull * j->width, j->height, j->n_frames, j->widthstep, a.frame_stride, box );
     cudaEvent_t t0 = c->span_begin();
     cudaError_t e = launch_raster( a, tma ? &map : nullptr, tma ? &img_map : nullptr, c->stream );

@@ -50,7 +50,8 @@ struct RasterArgs
     int32_t* poly_count;        // out (polygon export), may be null
     int width, height, widthstep, n_frames;
     size_t frame_stride;
-    int scale;
+    int scale;            // sampling scale S (= output scale x aa)
+    int aa;               // samples per output pixel and axis (1 = off, 2, 4): A x A samples are averaged in the resolve step
     int subdivide;
     int flip_output;
     int debug_force_wide; // test hook: treat every cell as reaching beyond its mask (exercises the exact slow path)
@@ -76,5 +77,6 @@ cudaError_t launch_build_mask_lut( int scale, const CellTablePtrs& tab, uint32_t
 void raster_img_tma_box( int scale, uint32_t box[ 3 ] );
 cudaError_t launch_raster( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream );
 bool raster_scale_supported( int scale );
+bool raster_aa_supported( int out_scale, int aa );
 
 } // namespace par

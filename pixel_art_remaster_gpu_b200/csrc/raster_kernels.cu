@@ -253,6 +253,57 @@ __device__ __forceinline__ void store_row( uint8_t* dst, const uint32_t* px )
     }
 }
 
+// Anti-aliased output (the reference's GL_MULTISAMPLE toggle, simpleVBO.cpp:238-253, as ordered-grid
+// supersampling): the kernel samples at S = A x the output scale and averages A x A samples per output pixel
+// right in the resolve step — the supersampled image never exists in memory.  RGBA sums on two pairs of 16-bit lanes.
+struct ColourSum
+{
+    uint32_t rb = 0u, ga = 0u;
+    __device__ __forceinline__ void add( uint32_t w )
+    {
+        rb += w & 0x00FF00FFu;
+        ga += ( w >> 8 ) & 0x00FF00FFu;
+    }
+    template< int N > // mean of N = 4 or 16 samples per channel, rounded to nearest (halves up)
+    __device__ __forceinline__ uint32_t mean() const
+    {
+        constexpr int SH = N == 4 ? 2 : 4;
+        constexpr uint32_t BIAS = ( N / 2 ) * 0x00010001u;
+        return ( ( ( rb + BIAS ) >> SH ) & 0x00FF00FFu ) | ( ( ( ( ga + BIAS ) >> SH ) & 0x00FF00FFu ) << 8 );
+    }
+};
+
+// S x S sample colours of one source pixel (row-major) -> its (S/A) x (S/A) output pixels, written as whole row segments
+template< int S, int A >
+__device__ __forceinline__ void store_cell( uint8_t* dst, ptrdiff_t row_step, const uint32_t* px )
+{
+    constexpr int O = S / A;
+    if( A == 1 )
+    {
+#pragma unroll
+        for( int b = 0; b < S; b++ ) store_row< S >( dst + ( ptrdiff_t )b * row_step, px + S * b );
+    }
+    else
+    {
+#pragma unroll
+        for( int oy = 0; oy < O; oy++ )
+        {
+            uint32_t row[ O ];
+#pragma unroll
+            for( int ox = 0; ox < O; ox++ )
+            {
+                ColourSum sum;
+#pragma unroll
+                for( int j = 0; j < A; j++ )
+#pragma unroll
+                    for( int i = 0; i < A; i++ ) sum.add( px[ ( oy * A + j ) * S + ox * A + i ] );
+                row[ ox ] = sum.template mean< A * A >();
+            }
+            store_row< O >( dst + ( ptrdiff_t )oy * row_step, row );
+        }
+    }
+}
+
 template< int S >
 struct TileEnv
 {
@@ -306,12 +357,13 @@ __device__ __noinline__ void window_coverage( const uint16_t* keys, const uint32
 
 // Exact resolve of a whole tile: every candidate's coverage of every pixel recomputed from its polygon.  Only runs
 // for tiles that contain a cell reaching beyond its mask, or under PAR_FLAG_DEBUG_WIDE.
-template< int S >
+template< int S, int A >
 __device__ __noinline__ void resolve_tile_exact( const uint16_t* keys, const uint32_t* cols, int x0, int y0, const uint8_t* frame, int width, int height,
                                                  int widthstep, const CellRecord* rec, bool subdivide, uint8_t* out, bool flip )
 {
     typedef Cfg< S > C;
-    const size_t out_w = ( size_t )width * S, out_h = ( size_t )height * S;
+    constexpr int O = S / A;
+    const size_t out_w = ( size_t )width * O, out_h = ( size_t )height * O;
     for( int idx = threadIdx.x; idx < C::TW * C::TH; idx += kThreads )
     {
         const int ly = idx / C::TW, lx = idx - ly * C::TW, gx = x0 + lx, gy = y0 + ly;
@@ -337,11 +389,8 @@ __device__ __noinline__ void resolve_tile_exact( const uint16_t* keys, const uin
                         if( ( take >> k ) & 1u ) px[ S * b + k ] = cw;
                 }
             }
-        for( int b = 0; b < S; b++ )
-        {
-            const size_t oy = flip ? ( out_h - 1 - ( ( size_t )gy * S + b ) ) : ( ( size_t )gy * S + b );
-            store_row< S >( out + ( oy * out_w + ( size_t )gx * S ) * 4, px + S * b );
-        }
+        const ptrdiff_t row_step = flip ? -( ptrdiff_t )( out_w * 4 ) : ( ptrdiff_t )( out_w * 4 );
+        store_cell< S, A >( out + ( ( flip ? out_h - 1 - ( size_t )gy * O : ( size_t )gy * O ) * out_w + ( size_t )gx * O ) * 4, row_step, px );
     }
 }
 
@@ -622,7 +671,7 @@ __device__ __forceinline__ bool smooth_lookup( const SmoothTablePtrs& st, const 
     return ok;
 }
 
-template< int S, bool kUseTma >
+template< int S, int A, bool kUseTma >
 __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( const __grid_constant__ CUtensorMap graph_map, const __grid_constant__ CUtensorMap img_map,
                                                            RasterArgs a )
 {
@@ -884,14 +933,15 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     }
 
     // (3) resolve and write: one thread per source pixel, S output rows of S pixels each
-    const size_t out_w = ( size_t )a.width * S, out_h = ( size_t )a.height * S;
+    constexpr int O = S / A; // output pixels per source pixel and axis (A > 1: A x A samples are averaged per output pixel)
+    const size_t out_w = ( size_t )a.width * O, out_h = ( size_t )a.height * O;
     uint8_t* out = a.rgba + ( size_t )f * out_w * out_h * 4;
     const ptrdiff_t row_step = a.flip_output ? -( ptrdiff_t )( out_w * 4 ) : ( ptrdiff_t )( out_w * 4 ); // bytes from one output row to the next
     if( s_nwork[ 2 ] != 0 || a.debug_force_wide )
     {
         // some cell of this tile reaches beyond its mask (never seen on real frames): the whole tile is resolved by
         // the exact path, kept out of line so that it costs the common path neither registers nor code
-        resolve_tile_exact< S >( s_keys, s_col, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, subdivide, out, a.flip_output != 0 );
+        resolve_tile_exact< S, A >( s_keys, s_col, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, subdivide, out, a.flip_output != 0 );
         return;
     }
     if constexpr( C::PACK )
@@ -951,9 +1001,8 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
                         if( ( rem >> bit ) & 1u ) px[ bit ] = 0xFF000000u;
                 }
             }
-            uint8_t* dst = out + ( ( size_t )( a.flip_output ? out_h - 1 - ( size_t )gy * S : ( size_t )gy * S ) * out_w + ( size_t )gx * S ) * 4;
-#pragma unroll
-            for( int b = 0; b < S; b++ ) store_row< S >( dst + ( ptrdiff_t )b * row_step, px + S * b );
+            uint8_t* dst = out + ( ( size_t )( a.flip_output ? out_h - 1 - ( size_t )gy * O : ( size_t )gy * O ) * out_w + ( size_t )gx * O ) * 4;
+            store_cell< S, A >( dst, row_step, px );
         }
     }
     else
@@ -967,36 +1016,52 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
             const uint32_t* col = s_col + ( ly + 2 ) * C::KW + ( lx + 2 );
             // the 3x3 neighbourhood's masks; candidates are visited in DESCENDING node index:
             // (dj,di) = (+1,+1) (+1,0) (+1,-1) (0,+1) (0,0) (0,-1) (-1,+1) (-1,0) (-1,-1)
+            uint8_t* dst = out + ( ( size_t )( a.flip_output ? out_h - 1 - ( size_t )gy * O : ( size_t )gy * O ) * out_w + ( size_t )gx * O ) * 4;
 #pragma unroll 1
-            for( int b = 0; b < S; b++ )
+            for( int ob = 0; ob < O; ob++ ) // one output row = A sample rows
             {
+                ColourSum sum[ O ];
                 uint32_t px[ S ];
-#pragma unroll
-                for( int k = 0; k < S; k++ ) px[ k ] = 0xFF000000u; // background (main.cpp:260)
-                uint32_t rem = C::FULL;
-#pragma unroll
-                for( int dj = 1; dj >= -1; dj-- )
+#pragma unroll 1
+                for( int r = 0; r < A; r++ )
                 {
-                    const int ky = b - dj * S + C::H;
-                    if( ky < 0 || ky >= C::R ) continue;
+                    const int b = ob * A + r;
 #pragma unroll
-                    for( int di = 1; di >= -1; di-- )
+                    for( int k = 0; k < S; k++ ) px[ k ] = 0xFF000000u; // background (main.cpp:260)
+                    uint32_t rem = C::FULL;
+#pragma unroll
+                    for( int dj = 1; dj >= -1; dj-- )
                     {
-                        const uint32_t m = s_mask[ ky * C::NC + cell + dj * C::CW + di ] & ~C::WIDE;
-                        const uint32_t field = di == 0 ? ( m >> C::H ) : ( di > 0 ? ( m << ( S - C::H ) ) : ( m >> ( S + C::H ) ) );
-                        const uint32_t take = field & rem;
-                        if( take )
-                        {
-                            const uint32_t cw = col[ dj * C::KW + di ];
+                        const int ky = b - dj * S + C::H;
+                        if( ky < 0 || ky >= C::R ) continue;
 #pragma unroll
-                            for( int k = 0; k < S; k++ )
-                                if( ( take >> k ) & 1u ) px[ k ] = cw;
-                            rem &= ~take;
+                        for( int di = 1; di >= -1; di-- )
+                        {
+                            const uint32_t m = s_mask[ ky * C::NC + cell + dj * C::CW + di ] & ~C::WIDE;
+                            const uint32_t field = di == 0 ? ( m >> C::H ) : ( di > 0 ? ( m << ( S - C::H ) ) : ( m >> ( S + C::H ) ) );
+                            const uint32_t take = field & rem;
+                            if( take )
+                            {
+                                const uint32_t cw = col[ dj * C::KW + di ];
+#pragma unroll
+                                for( int k = 0; k < S; k++ )
+                                    if( ( take >> k ) & 1u ) px[ k ] = cw;
+                                rem &= ~take;
+                            }
                         }
                     }
+                    if( A > 1 )
+                    {
+#pragma unroll
+                        for( int k = 0; k < S; k++ ) sum[ k / A ].add( px[ k ] );
+                    }
                 }
-                const size_t oy = a.flip_output ? ( out_h - 1 - ( ( size_t )gy * S + b ) ) : ( ( size_t )gy * S + b );
-                store_row< S >( out + ( oy * out_w + ( size_t )gx * S ) * 4, px );
+                if( A > 1 )
+                {
+#pragma unroll
+                    for( int k = 0; k < O; k++ ) px[ k ] = sum[ k ].template mean< A * A >();
+                }
+                store_row< O >( dst + ( ptrdiff_t )ob * row_step, px );
             }
         }
     }
@@ -1059,27 +1124,39 @@ __global__ void __launch_bounds__( kThreads ) polygon_kernel( RasterArgs a )
     if( a.poly_count ) a.poly_count[ n ] = m;
 }
 
-template< int S >
-cudaError_t launch_raster_s( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream )
+template< int S, int A >
+cudaError_t launch_raster_sa( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream )
 {
     typedef Cfg< S > C;
     dim3 grid( ( a.width + C::TW - 1 ) / C::TW, ( a.height + C::TH - 1 ) / C::TH, a.n_frames );
     cudaError_t e;
     if( graph_map && img_map )
     {
-        e = cudaFuncSetAttribute( raster_kernel< S, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes );
+        e = cudaFuncSetAttribute( raster_kernel< S, A, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes );
         if( e != cudaSuccess ) return e;
-        raster_kernel< S, true ><<< grid, kThreads, C::smem_bytes, stream >>>( *graph_map, *img_map, a );
+        raster_kernel< S, A, true ><<< grid, kThreads, C::smem_bytes, stream >>>( *graph_map, *img_map, a );
     }
     else
     {
         CUtensorMap dummy;
         memset( &dummy, 0, sizeof( dummy ) );
-        e = cudaFuncSetAttribute( raster_kernel< S, false >, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes );
+        e = cudaFuncSetAttribute( raster_kernel< S, A, false >, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes );
         if( e != cudaSuccess ) return e;
-        raster_kernel< S, false ><<< grid, kThreads, C::smem_bytes, stream >>>( dummy, dummy, a );
+        raster_kernel< S, A, false ><<< grid, kThreads, C::smem_bytes, stream >>>( dummy, dummy, a );
     }
     return cudaGetLastError();
+}
+
+// a.scale is the SAMPLING scale S; a.aa = A (1, 2 or 4) samples per output pixel and axis, S % A == 0
+template< int S >
+cudaError_t launch_raster_s( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream )
+{
+    if( a.aa == 1 ) return launch_raster_sa< S, 1 >( a, graph_map, img_map, stream );
+    if constexpr( S % 2 == 0 )
+        if( a.aa == 2 ) return launch_raster_sa< S, 2 >( a, graph_map, img_map, stream );
+    if constexpr( S % 4 == 0 )
+        if( a.aa == 4 ) return launch_raster_sa< S, 4 >( a, graph_map, img_map, stream );
+    return cudaErrorInvalidValue;
 }
 
 template< int S >
@@ -1092,6 +1169,10 @@ cudaError_t build_lut_s( const CellTablePtrs& tab, uint32_t* lut, cudaStream_t s
 } // namespace
 
 bool raster_scale_supported( int scale ) { return scale >= 1 && scale <= 8 && scale != 5 && scale != 7; }
+bool raster_aa_supported( int out_scale, int aa )
+{
+    return ( aa == 1 || aa == 2 || aa == 4 ) && out_scale >= 1 && raster_scale_supported( out_scale * aa );
+}
 
 #define PAR_FOR_SCALE( scale, CALL )  \
     switch( scale )                    \

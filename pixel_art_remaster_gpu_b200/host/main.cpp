@@ -1,7 +1,7 @@
 // remaster_cli — the reference's program entry point (main.cpp:166-194) without the GLUT window:
 // image in, remastered image out.
 //
-//   remaster_cli <input image> [-o out.png] [-s scale] [--no-subdivide] [--graph g.pgm] [--labels l.pgm]
+//   remaster_cli <input image> [-o out.png] [-s scale] [--aa 2|4] [--no-subdivide] [--graph g.pgm] [--labels l.pgm]
 //                [--strips N] [--device D] [--convert-only]
 //
 // Kept from the reference: argv[1] is the input path (main.cpp:172-173); load_image() loads in colour,
@@ -59,17 +59,18 @@ int main( int argc, char** argv )
 {
     if( argc < 2 )
     {
-        fprintf( stderr, "usage: %s <input image> [-o out.png] [-s scale] [--no-subdivide] [--graph g.pgm] [--labels l.png] [--strips N] [--device D] [--convert-only]\n", argv[ 0 ] );
+        fprintf( stderr, "usage: %s <input image> [-o out.png] [-s scale] [--aa 2|4] [--no-subdivide] [--graph g.pgm] [--labels l.png] [--strips N] [--device D] [--convert-only]\n", argv[ 0 ] );
         return 2;
     }
     std::string out_path = "remastered.png", graph_path, labels_path;
-    int scale = 4, strips = 0, device = 0;
+    int scale = 4, strips = 0, device = 0, aa = 1; // aa: anti-aliasing samples per axis (the reference's GL_MULTISAMPLE toggle, simpleVBO.cpp:238-253)
     bool subdivide = true, convert_only = false;
     for( int k = 2; k < argc; k++ )
     {
         std::string a = argv[ k ];
         if( a == "-o" && k + 1 < argc ) out_path = argv[ ++k ];
         else if( a == "-s" && k + 1 < argc ) scale = atoi( argv[ ++k ] );
+        else if( a == "--aa" && k + 1 < argc ) aa = atoi( argv[ ++k ] );
         else if( a == "--no-subdivide" ) subdivide = false;
         else if( a == "--graph" && k + 1 < argc ) graph_path = argv[ ++k ];
         else if( a == "--labels" && k + 1 < argc ) labels_path = argv[ ++k ];
@@ -99,6 +100,8 @@ int main( int argc, char** argv )
     job.n_frames = 1;
     job.scale = scale;
     job.flags = ( subdivide ? PAR_FLAG_SUBDIVIDE : 0u ) | PAR_FLAG_FLIP_OUTPUT; // output rows top scanline first
+    if( aa == 2 ) job.flags |= PAR_FLAG_AA2;
+    if( aa == 4 ) job.flags |= PAR_FLAG_AA4;
     job.rgba = rgba.data();
     job.graph = reinterpret_cast< uint8_t* >( graph );
     job.labels = labels.empty() ? nullptr : labels.data();

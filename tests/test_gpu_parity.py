@@ -208,3 +208,30 @@ def test_smoothing_tables_equal_the_geometric_path(lib, oracle):
             assert np.array_equal(tab, geo), (name, scale, int((tab != geo).any(-1).sum()))
             if scale in (4, 8):
                 assert np.array_equal(tab[0], oracle.pipeline(frames_np[0], scale=scale, want=("raster",))["raster"]), (name, scale)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale,aa", [(4, 2), (2, 2), (2, 4), (1, 4), (1, 2), (3, 2)])
+def test_antialiased_output_is_the_mean_of_the_supersampled_image(lib, oracle, scale, aa):
+    """PAR_FLAG_AA2 / AA4: every output pixel is the per-channel mean (halves up) of aa x aa ordered-grid samples, i.e. of
+    the point-sampled image at aa x the scale — compared here with the oracle's raster at that scale, averaged in numpy.
+    (The reference's GL_MULTISAMPLE pattern is driver-defined, SURVEY §8(f)-2: this pins OUR rule, bit-exactly.)"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    for frames_np in (synth.snes_stream(2, 96, 80, first_seed=31), synth.adversarial_sprite(96, 80, 5)[None]):
+        F, H, W = frames_np.shape[:3]
+        with lib.Remaster(0, W, H, F) as c:
+            c.aa = aa
+            for subdivide in (True, False):
+                got = c.remaster(torch.from_numpy(frames_np).cuda(), scale=scale, subdivide=subdivide)["rgba"].cpu().numpy()
+                assert got.shape == (F, H * scale, W * scale, 4)
+                for k in range(F):
+                    big = oracle.pipeline(frames_np[k], subdivide, True, scale * aa, ("raster",))["raster"].astype(np.uint32)
+                    want = (big.reshape(H * scale, aa, W * scale, aa, 4).sum(axis=(1, 3)) + aa * aa // 2) // (aa * aa)
+                    assert np.array_equal(got[k], want.astype(np.uint8)), (scale, aa, subdivide, k)
+            c.aa = 1
+    with lib.Remaster(0, 32, 32, 1) as c:  # scale x samples must be a supported sampling scale
+        c.aa = 4
+        with pytest.raises(Exception):
+            c.remaster(torch.zeros((1, 32, 32, 3), dtype=torch.uint8).cuda(), scale=4, subdivide=True)
