@@ -122,6 +122,20 @@ int par_profile_read( par_context* ctx, double* total_ms, int* launches );
  * precomputed smoothing tables.  Both paths give the same mask; the tables only make it cheaper. */
 int par_smooth_stats( par_context* ctx, uint64_t* out2 );
 
+/* Border walk of every connected component: for each component the walk the reference's
+ * extractBorderPoints (cc_functions.cu:348-503 — dead code there) makes from the component's first node in raster
+ * order (= its label): clockwise along the outer face (nextNodeClockwise, :295-318) until the loop closes (:415-416);
+ * dropped, as in the reference, when it steps on an interior node (== 90) or meets its start early (:425-438).  An
+ * island (undefined in the reference) is a walk of one node.  All pointers are DEVICE pointers; asynchronous.
+ *   graph, labels : n_frames * width*height (final graph, and its labels from par_stage_cc_labels / par_remaster_*)
+ *   walk_len      : out, per pixel: nodes of the walk that starts there (0 for other pixels and dropped walks)
+ *   walk_begin    : out, per pixel: where that walk starts in the frame's walk_nodes (walks are concatenated in raster
+ *                   order of their start — the reference's CClist / CCsizes layout)
+ *   walk_nodes    : out, n_frames * capacity_per_frame node indices
+ *   total         : out, per frame: entries the frame's walks need; a frame with total > capacity_per_frame writes none */
+int par_border_walks( par_context* ctx, const uint8_t* graph, const int32_t* labels, int width, int height, int n_frames, int32_t* walk_len,
+                      int32_t* walk_begin, int32_t* walk_nodes, long long capacity_per_frame, long long* total );
+
 /* Whole path on device-resident frames; asynchronous on the context's stream. */
 int par_remaster_device( par_context* ctx, const par_job* job );
 /* Whole path on host buffers: H2D of the frames, the kernels, D2H of every non-NULL output, then a

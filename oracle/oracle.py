@@ -52,6 +52,8 @@ class Oracle:
         L.orc_ear_clip.argtypes = [_f32p, C.c_int, _f32p]
         L.orc_triangulate.argtypes = [_f32p, _i32p, C.c_int, C.c_int, _f32p, _i32p]
         L.orc_cc_labels.argtypes = [_u8p, C.c_int, C.c_int, _i32p]
+        L.orc_border_walks.argtypes = [_u8p, _i32p, C.c_int, C.c_int, _i32p, _i32p, C.c_long]
+        L.orc_border_walks.restype = C.c_long
         L.orc_all_dyadic64.argtypes = [_f32p, C.c_long]
         L.orc_raster_triangles.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _i32p, _u8p]
         L.orc_raster_polygons.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _i32p, _u8p]
@@ -123,6 +125,21 @@ class Oracle:
         lab = np.zeros((H, W), np.int32)
         self.lib.orc_cc_labels(np.ascontiguousarray(g).reshape(-1), W, H, lab.reshape(-1))
         return lab
+
+    def border_walks(self, g, labels=None):
+        """{start node: [nodes]} — the first border walk of every component (dropped walks are absent)."""
+        H, W = g.shape
+        lab = self.cc_labels(g) if labels is None else labels
+        cap = 16 * H * W + 64
+        wl = np.zeros(H * W, np.int32)
+        nodes = np.zeros(cap, np.int32)
+        used = self.lib.orc_border_walks(np.ascontiguousarray(g).reshape(-1), np.ascontiguousarray(lab, np.int32).reshape(-1), W, H, wl, nodes, cap)
+        assert used >= 0
+        out, pos = {}, 0
+        for n in np.nonzero(wl)[0]:
+            out[int(n)] = nodes[pos:pos + wl[n]].tolist()
+            pos += int(wl[n])
+        return out
 
     def all_dyadic64(self, xy):
         a = np.ascontiguousarray(xy, np.float32).reshape(-1)

@@ -614,6 +614,79 @@ void orc_cc_labels( const uint8_t* graph, int W, int H, int32_t* label )
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* Border walk of every connected component: the FIRST walk the reference's      */
+/* extractBorderPoints (cc_functions.cu:348-503, dead code) makes for a component — the one that   */
+/* starts at the component's first node in raster order, which is its label.  For that walk the   */
+/* reference's serial bookkeeping (listed / discarded, :394-444) reduces to pure functions of the  */
+/* graph: the walk is dropped when it steps on an interior node (== 90, :425) or comes back to its */
+/* start node before the loop closes (the start is the only node of this component in `listed`,    */
+/* :426), otherwise it is the node sequence below.  Later walks of the same component (the         */
+/* reference starts one from every node not yet listed) depend on the scan state and are not       */
+/* restated.  An island (node == 0) is undefined in the reference (getFirstLink returns -1 and     */
+/* c_neighbor_index( ., -1, . ) falls off its switch, :215-246): here it is a walk of one node.    */
+/* walk_len[n] = nodes in the walk that starts at n (0 for every other pixel and for dropped       */
+/* walks); nodes = the walks concatenated in raster order of their start (capacity entries);       */
+/* returns the number of entries written, or -1 when capacity is too small.                        */
+/* ------------------------------------------------------------------------------------------- */
+static const int ORC_CLOCK_TO_BIT[ 8 ] = { 0, 1, 2, 4, 7, 6, 5, 3 }; /* getRealLinkIndex, :68-99 */
+static const int ORC_BIT_TO_CLOCK[ 8 ] = { 0, 1, 2, 7, 3, 6, 5, 4 }; /* getClockLinkIndex, :153-184 */
+long orc_border_walks( const uint8_t* graph, const int32_t* label, int W, int H, int32_t* walk_len, int32_t* nodes, long capacity )
+{
+    const int N = W * H;
+    long used = 0;
+    for( int n = 0; n < N; n++ ) walk_len[ n ] = 0;
+    for( int start = 0; start < N; start++ )
+    {
+        if( label[ start ] != start ) continue;
+        const unsigned first = graph[ start ];
+        if( first == 0u ) /* island */
+        {
+            if( used + 1 > capacity ) return -1;
+            nodes[ used++ ] = start;
+            walk_len[ start ] = 1;
+            continue;
+        }
+        int edge = -1; /* getFirstLink, :107-118 */
+        for( int c = 0; c < 8 && edge < 0; c++ )
+            if( first & ( 1u << ORC_CLOCK_TO_BIT[ c ] ) ) edge = ORC_CLOCK_TO_BIT[ c ];
+        int arrival = edge; /* nextEdgeCounterClockwise, :262-285 */
+        if( orc_popcount8( first ) != 1 )
+        {
+            const int c0 = ORC_BIT_TO_CLOCK[ edge ];
+            for( int c = c0 + 7; c >= c0 + 1; c-- )
+                if( first & ( 1u << ORC_CLOCK_TO_BIT[ c % 8 ] ) ) { arrival = ORC_CLOCK_TO_BIT[ c % 8 ]; break; }
+        }
+        const long begin = used;
+        int index = start, ok = 1;
+        if( used + 1 > capacity ) return -1;
+        nodes[ used++ ] = start;
+        long guard = 0;
+        while( index + ORC_DJ[ edge ] * W + ORC_DI[ edge ] != start || 7 - edge != arrival ) /* :415-416 */
+        {
+            /* nextNodeClockwise, :295-318 */
+            index += ORC_DJ[ edge ] * W + ORC_DI[ edge ];
+            const unsigned node = graph[ index ];
+            if( orc_popcount8( node ) == 1 )
+                edge = 7 - edge;
+            else
+            {
+                const int c0 = ORC_BIT_TO_CLOCK[ 7 - edge ];
+                for( int c = c0 + 1; c <= c0 + 7; c++ )
+                    if( node & ( 1u << ORC_CLOCK_TO_BIT[ c % 8 ] ) ) { edge = ORC_CLOCK_TO_BIT[ c % 8 ]; break; }
+            }
+            if( node == 90u || index == start || ++guard > 16L * N ) { ok = 0; break; } /* :425-438 */
+            if( used + 1 > capacity ) return -1;
+            nodes[ used++ ] = index;
+        }
+        if( ok )
+            walk_len[ start ] = ( int32_t )( used - begin );
+        else
+            used = begin;
+    }
+    return used;
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* Direct rasterization (NEW; replaces glDrawArrays(GL_TRIANGLES), simpleVBO.cpp:281).            */
 /* PARITY UNPINNED by the reference: the reference rasterizes inside the OpenGL driver.  Restated */
 /* rule: output (s*W)x(s*H) RGBA8, row Y = pipeline row (0 = bottom); output    */

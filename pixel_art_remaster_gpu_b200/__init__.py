@@ -64,6 +64,8 @@ def load_library():
     L.par_device.argtypes = [C.c_void_p]
     L.par_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.par_use_own_stream.argtypes = [C.c_void_p]
+    L.par_border_walks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_longlong, C.c_void_p]
     L.par_smooth_stats.argtypes = [C.c_void_p, P(C.c_uint64)]
     L.par_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.par_profile_read.argtypes = [C.c_void_p, P(C.c_double), P(C.c_int)]
@@ -269,6 +271,28 @@ class Remaster:
         j = self._job(None, 1, 0, graph=graph, labels=lab)
         self._check(self.lib.par_stage_cc_labels(self.handle, C.byref(j)))
         return lab
+
+    def border_walks(self, graph, labels, capacity_per_frame=None):
+        """Border walk of every component (par_border_walks): returns device tensors (walk_len, walk_begin, walk_nodes,
+        total).  walk_len / walk_begin are per pixel; walk_nodes is (F, capacity); total is per frame."""
+        t = self._torch
+        F, H, W = graph.shape
+        cap = int(capacity_per_frame) if capacity_per_frame else 4 * H * W
+        wl = t.empty((F, H, W), dtype=t.int32, device=graph.device)
+        wb = t.empty((F, H, W), dtype=t.int32, device=graph.device)
+        nodes = t.empty((F, cap), dtype=t.int32, device=graph.device)
+        total = t.empty((F,), dtype=t.int64, device=graph.device)
+        self._check(self.lib.par_border_walks(self.handle, graph.data_ptr(), labels.data_ptr(), W, H, F, wl.data_ptr(), wb.data_ptr(),
+                                              nodes.data_ptr(), cap, total.data_ptr()))
+        return wl, wb, nodes, total
+
+    @staticmethod
+    def walks_as_dict(walk_len, walk_begin, walk_nodes, frame=0):
+        """{start node: [nodes]} of one frame, on the host (tests, small inputs)."""
+        wl = walk_len[frame].reshape(-1).cpu().numpy()
+        wb = walk_begin[frame].reshape(-1).cpu().numpy()
+        nodes = walk_nodes[frame].cpu().numpy()
+        return {int(n): nodes[wb[n]:wb[n] + wl[n]].tolist() for n in wl.nonzero()[0]}
 
     def polygons(self, frames, graph, subdivide=True):
         F, H, W = frames.shape[:3]

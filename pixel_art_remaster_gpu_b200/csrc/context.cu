@@ -511,6 +511,19 @@ int par_stage_raster( par_context* c, const par_job* j )
     return run_raster( c, j, j->graph );
 }
 
+int par_border_walks( par_context* c, const uint8_t* graph, const int32_t* labels, int width, int height, int n_frames, int32_t* walk_len,
+                      int32_t* walk_begin, int32_t* walk_nodes, long long capacity_per_frame, long long* total )
+{
+    if( !c ) return PAR_ERR_INVALID;
+    if( !graph || !labels || !walk_len || !walk_begin || !walk_nodes || !total ) return c->fail( PAR_ERR_INVALID, "border_walks: NULL pointer" );
+    if( width <= 0 || height <= 0 || n_frames <= 0 || capacity_per_frame <= 0 ) return c->fail( PAR_ERR_INVALID, "border_walks: empty frame, batch or capacity" );
+    if( ( size_t )width * height > ( size_t )1 << 30 ) return c->fail( PAR_ERR_INVALID, "frame too large" );
+    cudaSetDevice( c->device );
+    cudaError_t e = launch_border_walks( graph, labels, width, height, n_frames, walk_len, walk_begin, total, walk_nodes, capacity_per_frame, c->stream );
+    c->launches += 3 * ( ( n_frames + 65534 ) / 65535 );
+    return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "border_walks" );
+}
+
 int par_remaster_device( par_context* c, const par_job* j )
 {
     int st = check_job( c, j, true );

@@ -67,6 +67,9 @@ cudaError_t launch_resolve_crossings( const CrossArgs& a, const CUtensorMap* aux
 // labels: returns the number of kernels launched through *n_launches
 cudaError_t launch_cc_labels( const LabelArgs& a, cudaStream_t stream, int* n_launches );
 
+cudaError_t launch_border_walks( const uint8_t* graph, const int32_t* labels, int width, int height, int n_frames, int32_t* walk_len,
+                                 int32_t* walk_begin, long long* total, int32_t* nodes, long long capacity, cudaStream_t stream );
+
 cudaError_t launch_polygons( const RasterArgs& a, cudaStream_t stream );
 void raster_tma_box( int scale, uint32_t box[ 3 ] );
 size_t mask_lut_words( int scale );

@@ -119,3 +119,35 @@ def test_stages_d_to_raster_from_reference_dumps(oracle):
         tri, nt = oracle.triangulate(hull, cnt, W, H)
         assert (nt == cnt - 2).all()
         assert np.array_equal(oracle.raster_triangles(img, 4, tri, nt), oracle.raster_polygons(img, 4, hull, cnt))
+
+
+def _first_walks(oracle, case):
+    """The reference walker's output on one golden graph, reduced to the first walk of every component."""
+    g = np.array(case["graph"], np.uint8).reshape(case["H"], case["W"])
+    lab = oracle.cc_labels(g).reshape(-1)
+    first = {}
+    for w in case["walks"]:
+        if lab[w[0]] == w[0] and w[0] not in first:
+            first[w[0]] = w
+    return g, lab, first
+
+
+def test_border_walks_equal_the_reference_walker(oracle):
+    """the oracle's border walk per component against what the reference's own (dead-code) walker,
+    cc_functions.cu:348-503, produced on 10 small graphs + its 24x24 'alex' dump (tests/golden/make_border_walks.py,
+    make_golden.py): every first walk of a component is identical, node for node; components the reference drops are dropped."""
+    cases = json.load(open(os.path.join(GOLD, "border_walks_small.json")))
+    assert len(cases) >= 8
+    compared = 0
+    for case in cases:
+        g, lab, first = _first_walks(oracle, case)
+        mine = oracle.border_walks(g)
+        assert set(mine) == set(first), case["name"]
+        for s0, w in first.items():
+            assert mine[s0] == w, (case["name"], s0)
+            compared += 1
+    assert compared > 250
+    z = np.load(os.path.join(GOLD, "graph_dumps.npz"))
+    walker = json.load(open(os.path.join(GOLD, "border_walks_alex.json")))
+    mine = oracle.border_walks(z["alex"])
+    assert len(mine) == 19 and all(mine[w[0]] == w for w in walker)

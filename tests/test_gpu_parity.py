@@ -235,3 +235,45 @@ def test_antialiased_output_is_the_mean_of_the_supersampled_image(lib, oracle, s
         c.aa = 4
         with pytest.raises(Exception):
             c.remaster(torch.zeros((1, 32, 32, 3), dtype=torch.uint8).cuda(), scale=4, subdivide=True)
+
+
+@pytest.mark.gpu
+def test_border_walks(lib, oracle):
+    """par_border_walks: bit-exact against the oracle on whole batches of synthetic frames, and against
+    the reference's own walker through the golden graphs it survived (tests/golden/border_walks_small.json)."""
+    import json, os
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    for frames_np in (synth.snes_stream(3, 96, 80, first_seed=77), synth.adversarial_sprite(120, 90, 3)[None], synth.snes_stream(2, 33, 21, first_seed=5)):
+        F, H, W = frames_np.shape[:3]
+        with lib.Remaster(0, W, H, F) as c:
+            out = c.remaster(torch.from_numpy(frames_np).cuda(), scale=1, subdivide=False, want=("graph", "labels"))
+            wl, wb, nodes, total = c.border_walks(out["graph"], out["labels"])
+            torch.cuda.synchronize()
+            for k in range(F):
+                g = out["graph"][k].cpu().numpy()
+                want = oracle.border_walks(g, out["labels"][k].cpu().numpy())
+                got = c.walks_as_dict(wl, wb, nodes, k)
+                assert got == want, (W, H, k)
+                assert int(total[k]) == sum(len(w) for w in want.values())
+                assert list(got) == sorted(got) and [int(wb[k].reshape(-1)[s]) for s in got] == list(np.cumsum([0] + [len(w) for w in got.values()])[:-1])
+            # a capacity that is too small is reported, not overrun
+            wl2, wb2, nodes2, total2 = c.border_walks(out["graph"], out["labels"], capacity_per_frame=8)
+            torch.cuda.synchronize()
+            assert torch.equal(total2, total) and torch.equal(wl2, wl)
+    here = os.path.dirname(os.path.abspath(__file__))
+    cases = json.load(open(os.path.join(here, "golden", "border_walks_small.json")))
+    for case in cases:
+        g = np.array(case["graph"], np.uint8).reshape(case["H"], case["W"])
+        lab = oracle.cc_labels(g)
+        first = {}
+        for w in case["walks"]:
+            if lab.reshape(-1)[w[0]] == w[0] and w[0] not in first:
+                first[w[0]] = w
+        with lib.Remaster(0, case["W"], case["H"], 1) as c:
+            gd = torch.from_numpy(g[None]).cuda()
+            labd = c.cc_labels(gd)
+            assert np.array_equal(labd[0].cpu().numpy(), lab)
+            got = c.walks_as_dict(*c.border_walks(gd, labd)[:3])
+        assert got == first, case["name"]
