@@ -343,19 +343,16 @@ class RemasterGroup:
     def __exit__(self, *exc):
         self.close()
 
-    def remaster_host(self, image, subdivide=True, want=("rgba", "graph"), flip_output=False):
-        """image: numpy uint8 (H, W, 3) BGR (row stride may exceed 3*W).  Returns numpy arrays."""
+    def remaster_host(self, image, subdivide=True, want=("rgba", "graph"), flip_output=False, out=None):
+        """image: numpy uint8 (H, W, 3) BGR (row stride may exceed 3*W).  Returns numpy arrays; `out` may supply them
+        (e.g. views of pinned memory: pageable buffers limit the copies to a few GB/s)."""
         assert image.dtype == np.uint8 and image.shape[:2] == (self.height, self.width) and image.strides[1:] == (3, 1)
         H, W, S = self.height, self.width, self.scale
-        out = {}
-        if "rgba" in want:
-            out["rgba"] = np.empty((S * H, S * W, 4), np.uint8)
-        if "graph" in want:
-            out["graph"] = np.empty((H, W), np.uint8)
-        if "graph_aux" in want:
-            out["graph_aux"] = np.empty((H, W), np.uint8)
-        if "labels" in want:
-            out["labels"] = np.empty((H, W), np.int32)
+        shapes = {"rgba": ((S * H, S * W, 4), np.uint8), "graph": ((H, W), np.uint8), "graph_aux": ((H, W), np.uint8), "labels": ((H, W), np.int32)}
+        if out is None:
+            out = {k: np.empty(*shapes[k]) for k in ("rgba", "graph", "graph_aux", "labels") if k in want}
+        for k, v in out.items():
+            assert v.shape == shapes[k][0] and v.dtype == shapes[k][1] and v.flags["C_CONTIGUOUS"], k
         j = ParJob()
         j.bgr = image.ctypes.data
         j.width, j.height, j.widthstep, j.frame_stride, j.n_frames = W, H, image.strides[0], 0, 1

@@ -19,7 +19,6 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
-#include <map>
 #include <string>
 #include <vector>
 
@@ -34,12 +33,12 @@ struct Strip
     int device = 0;
     int own_b = 0, own_e = 0, load_b = 0, load_e = 0; // image rows
     par_context* ctx = nullptr;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr; // copy_stream: image / graph rows back to the host while the labels are stitched
     uint8_t *d_in = nullptr, *d_rgba = nullptr, *d_graph = nullptr, *d_aux = nullptr;
     int32_t* d_labels = nullptr;
     int32_t *d_map_keys = nullptr, *d_map_vals = nullptr;
     size_t map_cap = 0;
-    cudaEvent_t uploaded = nullptr;
+    cudaEvent_t uploaded = nullptr, computed = nullptr;
 };
 
 __global__ void offset_labels_kernel( int32_t* lab, size_t n, int32_t offset )
@@ -108,6 +107,8 @@ void par_group_destroy( par_group* g )
         cudaFree( s.d_map_keys );
         cudaFree( s.d_map_vals );
         if( s.uploaded ) cudaEventDestroy( s.uploaded );
+        if( s.computed ) cudaEventDestroy( s.computed );
+        if( s.copy_stream ) cudaStreamDestroy( s.copy_stream );
         if( s.ctx ) par_destroy( s.ctx );
         if( s.stream ) cudaStreamDestroy( s.stream );
     }
@@ -166,6 +167,8 @@ int par_group_create( par_group** out, const int* devices, int n_devices, int wi
         if( e == cudaSuccess ) e = cudaMalloc( &s.d_aux, px );
         if( e == cudaSuccess ) e = cudaMalloc( &s.d_labels, px * 4 );
         if( e == cudaSuccess ) e = cudaEventCreateWithFlags( &s.uploaded, cudaEventDisableTiming );
+        if( e == cudaSuccess ) e = cudaEventCreateWithFlags( &s.computed, cudaEventDisableTiming );
+        if( e == cudaSuccess ) e = cudaStreamCreateWithFlags( &s.copy_stream, cudaStreamNonBlocking );
         if( e != cudaSuccess )
         {
             g_group_create_error = std::string( "par_group_create: " ) + cudaGetErrorString( e );
@@ -256,6 +259,7 @@ int par_group_remaster_host( par_group* g, const par_job* j )
         d.poly_count = nullptr;
         int st = par_remaster_device( s.ctx, &d );
         if( st != PAR_OK ) return g->fail( st, "strip on device %d: %s", s.device, par_last_error( s.ctx ) );
+        cudaEventRecord( s.computed, s.stream );
         if( j->labels )
         {
             // Label only rows whose graph bytes are exact: the strip's own rows plus ONE row either side (needed
@@ -273,46 +277,73 @@ int par_group_remaster_host( par_group* g, const par_job* j )
             offset_labels_kernel<<< ( unsigned )( ( n + 255 ) / 256 ), 256, 0, s.stream >>>( l.labels, n, win_b * W );
         }
     }
-    // (4) stitch the labels: on the last own row of strip k both k and k+1 labelled the same pixels
+    // (4) own rows of the image and the graphs go back to the host as soon as the strip has them — the big copies
+    // overlap the label stitching below (the labels follow once they are final)
+    const size_t out_row = ( size_t )W * S * 4;
+    for( auto& s : g->strips )
+    {
+        cudaSetDevice( s.device );
+        const size_t own_px = ( size_t )W * ( s.own_e - s.own_b ), off_px = ( size_t )W * ( s.own_b - s.load_b );
+        cudaStream_t cs = s.copy_stream;
+        cudaStreamWaitEvent( cs, s.computed, 0 );
+        if( j->rgba )
+        {
+            const bool flip = ( j->flags & PAR_FLAG_FLIP_OUTPUT ) != 0;
+            const size_t src_row = flip ? ( size_t )( s.load_e - s.own_e ) * S : ( size_t )( s.own_b - s.load_b ) * S;
+            const size_t dst_row = flip ? ( size_t )( g->height - s.own_e ) * S : ( size_t )s.own_b * S;
+            e = cudaMemcpyAsync( j->rgba + dst_row * out_row, s.d_rgba + src_row * out_row, ( size_t )( s.own_e - s.own_b ) * S * out_row,
+                                 cudaMemcpyDeviceToHost, cs );
+        }
+        if( e == cudaSuccess && j->graph ) e = cudaMemcpyAsync( j->graph + ( size_t )W * s.own_b, s.d_graph + off_px, own_px, cudaMemcpyDeviceToHost, cs );
+        if( e == cudaSuccess && j->graph_aux )
+            e = cudaMemcpyAsync( j->graph_aux + ( size_t )W * s.own_b, s.d_aux + off_px, own_px, cudaMemcpyDeviceToHost, cs );
+        if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "D2H: %s", cudaGetErrorString( e ) );
+    }
+    // (5) stitch the labels: on the last own row of strip k both k and k+1 labelled the same pixels.  All seam rows
+    // are fetched at once; the equivalences (<= 7 x 4096 pairs) are closed by a union-find over the distinct labels.
+    std::vector< int32_t > keys, vals; // relabelling map, alive until the final synchronize
     if( j->labels && g->strips.size() > 1 )
     {
-        std::map< int32_t, int32_t > parent;
-        auto find = [ & ]( int32_t x ) {
-            while( true )
-            {
-                auto it = parent.find( x );
-                if( it == parent.end() || it->second == x ) return x;
-                x = it->second;
-            }
-        };
-        std::vector< int32_t > ra( W ), rb( W );
-        for( size_t k = 0; k + 1 < g->strips.size(); k++ )
+        const size_t n_seams = g->strips.size() - 1;
+        std::vector< int32_t > rows( 2 * n_seams * W );
+        for( size_t k = 0; k < n_seams; k++ )
         {
             Strip &a = g->strips[ k ], &b = g->strips[ k + 1 ];
             const int row = a.own_e - 1;
             cudaSetDevice( a.device );
-            cudaMemcpyAsync( ra.data(), a.d_labels + ( size_t )( row - a.load_b ) * W, ( size_t )W * 4, cudaMemcpyDeviceToHost, a.stream );
-            cudaStreamSynchronize( a.stream );
+            cudaMemcpyAsync( rows.data() + ( 2 * k ) * W, a.d_labels + ( size_t )( row - a.load_b ) * W, ( size_t )W * 4, cudaMemcpyDeviceToHost, a.stream );
             cudaSetDevice( b.device );
-            cudaMemcpyAsync( rb.data(), b.d_labels + ( size_t )( row - b.load_b ) * W, ( size_t )W * 4, cudaMemcpyDeviceToHost, b.stream );
-            e = cudaStreamSynchronize( b.stream );
+            cudaMemcpyAsync( rows.data() + ( 2 * k + 1 ) * W, b.d_labels + ( size_t )( row - b.load_b ) * W, ( size_t )W * 4, cudaMemcpyDeviceToHost, b.stream );
+        }
+        for( auto& s : g->strips )
+        {
+            cudaSetDevice( s.device );
+            e = cudaStreamSynchronize( s.stream );
             if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "label rows: %s", cudaGetErrorString( e ) );
+        }
+        std::vector< int32_t > ids( rows ); // the distinct labels on the seams, sorted: position = union-find node
+        std::sort( ids.begin(), ids.end() );
+        ids.erase( std::unique( ids.begin(), ids.end() ), ids.end() );
+        std::vector< int32_t > parent( ids.size() );
+        for( size_t k = 0; k < parent.size(); k++ ) parent[ k ] = ( int32_t )k;
+        auto node = [ & ]( int32_t label ) { return ( int32_t )( std::lower_bound( ids.begin(), ids.end(), label ) - ids.begin() ); };
+        auto find = [ & ]( int32_t x ) {
+            while( parent[ x ] != x ) x = parent[ x ] = parent[ parent[ x ] ];
+            return x;
+        };
+        for( size_t k = 0; k < n_seams; k++ )
             for( int x = 0; x < W; x++ )
             {
-                int32_t p = find( ra[ x ] ), q = find( rb[ x ] );
-                parent.emplace( p, p );
-                parent.emplace( q, q );
-                if( p != q ) parent[ std::max( p, q ) ] = std::min( p, q ); // keep the smaller index as the root
+                const int32_t p = find( node( rows[ ( 2 * k ) * W + x ] ) ), q = find( node( rows[ ( 2 * k + 1 ) * W + x ] ) );
+                if( p != q ) parent[ std::max( p, q ) ] = std::min( p, q ); // ids are sorted: the smaller node is the smaller label
             }
-        }
-        std::vector< int32_t > keys, vals;
-        for( auto& kv : parent )
+        for( size_t k = 0; k < ids.size(); k++ )
         {
-            int32_t r = find( kv.first );
-            if( r != kv.first )
+            const int32_t r = find( ( int32_t )k );
+            if( r != ( int32_t )k )
             {
-                keys.push_back( kv.first ); // std::map iterates in key order: already sorted
-                vals.push_back( r );
+                keys.push_back( ids[ k ] ); // ascending: the relabel kernel searches them
+                vals.push_back( ids[ r ] );
             }
         }
         if( !keys.empty() )
@@ -332,29 +363,22 @@ int par_group_remaster_host( par_group* g, const par_job* j )
                 const size_t n = ( size_t )W * ( s.own_e - s.own_b );
                 relabel_kernel<<< ( unsigned )( ( n + 255 ) / 256 ), 256, 0, s.stream >>>(
                     s.d_labels + ( size_t )( s.own_b - s.load_b ) * W, n, s.d_map_keys, s.d_map_vals, ( int )keys.size() );
-                cudaStreamSynchronize( s.stream ); // keys/vals are host vectors about to go out of scope
             }
     }
-    // (5) own rows back to the host
-    const size_t out_row = ( size_t )W * S * 4;
+    if( j->labels )
+        for( auto& s : g->strips )
+        {
+            cudaSetDevice( s.device );
+            const size_t own_px = ( size_t )W * ( s.own_e - s.own_b ), off_px = ( size_t )W * ( s.own_b - s.load_b );
+            e = cudaMemcpyAsync( j->labels + ( size_t )W * s.own_b, s.d_labels + off_px, own_px * 4, cudaMemcpyDeviceToHost, s.stream );
+            if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "D2H: %s", cudaGetErrorString( e ) );
+        }
     for( auto& s : g->strips )
     {
         cudaSetDevice( s.device );
-        const size_t own_px = ( size_t )W * ( s.own_e - s.own_b ), off_px = ( size_t )W * ( s.own_b - s.load_b );
-        if( j->rgba )
-        {
-            const bool flip = ( j->flags & PAR_FLAG_FLIP_OUTPUT ) != 0;
-            const size_t src_row = flip ? ( size_t )( s.load_e - s.own_e ) * S : ( size_t )( s.own_b - s.load_b ) * S;
-            const size_t dst_row = flip ? ( size_t )( g->height - s.own_e ) * S : ( size_t )s.own_b * S;
-            e = cudaMemcpyAsync( j->rgba + dst_row * out_row, s.d_rgba + src_row * out_row, ( size_t )( s.own_e - s.own_b ) * S * out_row,
-                                 cudaMemcpyDeviceToHost, s.stream );
-        }
-        if( e == cudaSuccess && j->graph ) e = cudaMemcpyAsync( j->graph + ( size_t )W * s.own_b, s.d_graph + off_px, own_px, cudaMemcpyDeviceToHost, s.stream );
-        if( e == cudaSuccess && j->graph_aux )
-            e = cudaMemcpyAsync( j->graph_aux + ( size_t )W * s.own_b, s.d_aux + off_px, own_px, cudaMemcpyDeviceToHost, s.stream );
-        if( e == cudaSuccess && j->labels )
-            e = cudaMemcpyAsync( j->labels + ( size_t )W * s.own_b, s.d_labels + off_px, own_px * 4, cudaMemcpyDeviceToHost, s.stream );
-        if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "D2H: %s", cudaGetErrorString( e ) );
+        e = cudaStreamSynchronize( s.copy_stream );
+        if( e == cudaSuccess ) e = cudaStreamSynchronize( s.stream );
+        if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "strip on device %d: %s", s.device, cudaGetErrorString( e ) );
     }
     for( auto& s : g->strips )
     {
