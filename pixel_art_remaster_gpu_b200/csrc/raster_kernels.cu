@@ -413,7 +413,7 @@ __global__ void build_mask_lut_kernel( CellTablePtrs tab, uint32_t* lut )
     NoEnv env;
     const CellPoly poly = build_cell_polygon( env, tab, 0, 0, ( uint32_t )key, false, slots );
     int lo, hi;
-    if( C::PACK )
+    if constexpr( C::PACK )
     {
         PackedToggle< C::R > tg{ 0ull };
         cover_polygon< S, C::R >( verts, 1, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
@@ -453,7 +453,7 @@ __device__ void cover_to_entry( const int* xs, const int* ys, int m, uint64_t* o
         hi = max( hi, max( xs[ k ], ys[ k ] ) * C::VM );
     }
     const bool wide = lo <= -C::REACH || hi >= C::SQUARE + C::REACH;
-    if( C::PACK )
+    if constexpr( C::PACK )
     {
         PackedToggle< C::R > tg{ 0ull };
         for( int k = 0; k < m; k++ )
@@ -901,7 +901,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
             PackedSlots slots{ vbuf, kThreads };
             const CellPoly poly = build_cell_polygon( env, tab, gx, gy, s_keys[ ( cy + 1 ) * C::KW + cx + 1 ], true, slots );
             int lo, hi;
-            if( C::PACK )
+            if constexpr( C::PACK )
             {
                 PackedToggle< C::R > tg{ 0ull };
                 cover_polygon< S, C::R >( vbuf, kThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
