@@ -37,7 +37,8 @@ namespace par {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kMaxVerts = 16; // 8 hull vertices, each replaced by at most two
+constexpr int kMaxVerts = 16;    // 8 hull vertices, each replaced by at most two
+constexpr int kGeoThreads = 128; // threads that take part in the (rare) geometric path: one vertex buffer each
 
 template< int S >
 struct Cfg
@@ -85,18 +86,23 @@ struct Cfg
     static constexpr uint32_t M_RIGHTCOL = M_COL0 << ( S - 1 );         // my column S-1 <- F1 of the cell to the right
     static constexpr uint32_t M_BOTROW = ( 1u << S ) - 1u;              // my row 0      <- F2 of the cell below
     static constexpr uint32_t M_TOPROW = M_BOTROW << ( S * ( S - 1 ) ); // my row S-1    <- F2 of the cell above
-    // shared memory carve-up (bytes)
+    // Shared memory carve-up (bytes).  The first region has three lives: (1) the staged graph and BGR rows (the TMA
+    // destinations) until the staging pass has turned them into keys and colours; (2) the list of smoothed cells
+    // (classification -> table pass) next to the list of cells for the geometric path; (3) the geometric path's vertex
+    // buffers, over the first list, which is dead by then.  Keeping the CTA at 24 KB lets five of them share an SM
+    // with 124 KB left as L1 for the tables — the kernel is sensitive to both.
     static constexpr int off_graph = 0;
-    static constexpr int off_keys = off_graph + ( KH * GP + 127 ) / 128 * 128;
+    static constexpr int off_raw = ( KH * GP + 127 ) / 128 * 128;
+    static constexpr int off_gen = 0, off_vbuf = 0;
+    static constexpr int sz_first_list = NC * 2 > kMaxVerts * kGeoThreads * 2 ? NC * 2 : kMaxVerts * kGeoThreads * 2;
+    static constexpr int off_work = ( sz_first_list + 15 ) / 16 * 16;
+    static constexpr int sz_stage = off_raw + KH * RAWP, sz_lists = off_work + NC * 2;
+    static constexpr int off_keys = ( ( sz_stage > sz_lists ? sz_stage : sz_lists ) + 127 ) / 128 * 128;
     static constexpr int off_col = off_keys + ( KW * KH * 2 + 15 ) / 16 * 16;
     static constexpr int off_mask = off_col + KW * KH * 4;
-    static constexpr int off_vbuf = ( off_mask + NC * MW * 4 + 127 ) / 128 * 128;
-    static constexpr int off_raw = off_vbuf;              // the staged BGR rows are dead before the vertex buffers are used
-    static constexpr int off_work = off_vbuf + kMaxVerts * kThreads * 2;
-    static constexpr int off_cflags = off_work + NC * 2 + 16; // per cell: bits 0-3 corner kept, bit 4 guard
-    static constexpr int off_bar = ( off_cflags + NC + 15 ) / 16 * 16;
-    static_assert( KH * RAWP <= kMaxVerts * kThreads * 2, "raw colour rows alias the vertex buffers" );
-    static constexpr int smem_bytes = off_bar + 16;
+    static constexpr int off_bar = ( off_mask + NC * MW * 4 + 15 ) / 16 * 16;
+    static constexpr int off_nwork = off_bar + 16; // four counters / flags
+    static constexpr int smem_bytes = off_nwork + 16;
 };
 
 // number of sample columns c in [0,N) with F - c*G > 0, i.e. clamp(ceil(F/G), 0, N), G > 0
@@ -681,9 +687,9 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     uint16_t* s_keys = reinterpret_cast< uint16_t* >( smem + C::off_keys );
     uint32_t* s_col = reinterpret_cast< uint32_t* >( smem + C::off_col );
     uint32_t* s_mask = reinterpret_cast< uint32_t* >( smem + C::off_mask );   // PACK: [2][NC]; rows: [R][NC]
-    uint16_t* s_vbuf = reinterpret_cast< uint16_t* >( smem + C::off_vbuf );   // [kMaxVerts][kThreads]
+    uint16_t* s_vbuf = reinterpret_cast< uint16_t* >( smem + C::off_vbuf );   // [kMaxVerts][kGeoThreads]
     uint16_t* s_work = reinterpret_cast< uint16_t* >( smem + C::off_work );   // cells that need the general path
-    int* s_nwork = reinterpret_cast< int* >( smem + C::off_work + C::NC * 2 );
+    int* s_nwork = reinterpret_cast< int* >( smem + C::off_nwork );
     uint64_t* s_bar = reinterpret_cast< uint64_t* >( smem + C::off_bar );
 
     const int tid = threadIdx.x;
@@ -808,8 +814,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
 
     // (2a) cells whose polygon is their plain hull copy the mask from the table; smoothed cells are compacted
     // into a list so that the next pass runs with full warps
-    uint16_t* s_gen = reinterpret_cast< uint16_t* >( smem + C::off_vbuf ); // (the vertex buffers are not in use yet)
-    uint8_t* s_cflags = smem + C::off_cflags;
+    uint16_t* s_gen = reinterpret_cast< uint16_t* >( smem + C::off_gen ); // (the staged rows are dead, the vertex buffers not in use yet)
     for( int idx = tid; idx < C::NC; idx += kThreads )
     {
         int cy = idx / C::CW, cx = idx - cy * C::CW;
@@ -820,19 +825,6 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
         if( inside && !plain )
         {
             s_gen[ warp_slot( s_nwork + 1 ) ] = ( uint16_t )idx;
-            // checkTJunction for the four corners of the pixel square, once per cell and with every lane busy
-            uint32_t cf = 0u;
-            if( env.guard( gx, gy ) )
-                cf = 16u;
-            else
-            {
-                const uint32_t* c = s_col + ( cy + 1 ) * C::KW + ( cx + 1 );
-                const uint32_t l = c[ -1 ], r = c[ 1 ], d = c[ -C::KW ], u = c[ C::KW ];
-                const uint32_t dl = c[ -C::KW - 1 ], dr = c[ -C::KW + 1 ], ul = c[ C::KW - 1 ], ur = c[ C::KW + 1 ];
-                cf = ( ( l != dl || dl != d ) ? 1u : 0u ) | ( ( r != dr || dr != d ) ? 2u : 0u ) | ( ( r != ur || ur != u ) ? 4u : 0u ) |
-                     ( ( l != ul || ul != u ) ? 8u : 0u );
-            }
-            s_cflags[ idx ] = ( uint8_t )cf;
         }
         else if( C::PACK )
         {
@@ -862,9 +854,19 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
             const int idx = s_gen[ w ];
             int cy = idx / C::CW, cx = idx - cy * C::CW;
             const uint16_t* kc = s_keys + ( cy + 1 ) * C::KW + cx + 1;
+            // checkTJunction for the four corners of the pixel square (bit c: corner c stays), 16 = its early exit
+            uint32_t cf = 16u;
+            if( !env.guard( x0 - 1 + cx, y0 - 1 + cy ) )
+            {
+                const uint32_t* c = s_col + ( cy + 1 ) * C::KW + ( cx + 1 );
+                const uint32_t l = c[ -1 ], r = c[ 1 ], d = c[ -C::KW ], u = c[ C::KW ];
+                const uint32_t dl = c[ -C::KW - 1 ], dr = c[ -C::KW + 1 ], ul = c[ C::KW - 1 ], ur = c[ C::KW + 1 ];
+                cf = ( ( l != dl || dl != d ) ? 1u : 0u ) | ( ( r != dr || dr != d ) ? 2u : 0u ) | ( ( r != ur || ur != u ) ? 4u : 0u ) |
+                     ( ( l != ul || ul != u ) ? 8u : 0u );
+            }
             uint64_t mw[ Entry< S >::EW ];
             bool wide = false;
-            if( use_tables && smooth_lookup< S >( a.smooth, a.mask_lut, kc, *kc, s_cflags[ idx ], mw, wide ) )
+            if( use_tables && smooth_lookup< S >( a.smooth, a.mask_lut, kc, *kc, cf, mw, wide ) )
             {
                 if( C::PACK )
                 {
@@ -893,18 +895,18 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     {
         const int n_work = *s_nwork;
         uint16_t* vbuf = s_vbuf + tid;
-        for( int w = tid; w < n_work; w += kThreads )
+        for( int w = tid; w < n_work && tid < kGeoThreads; w += kGeoThreads )
         {
             const int idx = s_work[ w ];
             int cy = idx / C::CW, cx = idx - cy * C::CW;
             int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
-            PackedSlots slots{ vbuf, kThreads };
+            PackedSlots slots{ vbuf, kGeoThreads };
             const CellPoly poly = build_cell_polygon( env, tab, gx, gy, s_keys[ ( cy + 1 ) * C::KW + cx + 1 ], true, slots );
             int lo, hi;
             if constexpr( C::PACK )
             {
                 PackedToggle< C::R > tg{ 0ull };
-                cover_polygon< S, C::R >( vbuf, kThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
+                cover_polygon< S, C::R >( vbuf, kGeoThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
                 // reach check: every sample outside the mask must be strictly outside the polygon's bounding box
                 const uint32_t wide = ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
                 uint2 wm = to_window< S >( tg.m );
@@ -918,7 +920,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
 #pragma unroll
                 for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] = 0u;
                 RowToggle tg{ s_mask + idx, C::NC };
-                cover_polygon< S, C::R >( vbuf, kThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
+                cover_polygon< S, C::R >( vbuf, kGeoThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
                 const uint32_t wide = ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
                 s_mask[ idx ] |= wide;
                 if( wide ) s_nwork[ 2 ] = 1;
