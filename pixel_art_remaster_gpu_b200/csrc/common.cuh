@@ -32,13 +32,26 @@ __host__ __device__ __forceinline__ uint32_t yuv_word( int b0, int b1, int b2 )
 {
     int T = 299 * b0 + 587 * b1 + 114 * b2;
     int y = T / 1000;
-    if( T - y * 1000 == 0 )
+    if( T - y * 1000 == 0 && T != 0 ) // (black stays 0: the chain of three zeros is exact)
     {
+        if( b0 == b1 && b1 == b2 )
+        {
+            // greys: T = 1000 v exactly, and for 75 of the 256 values the rounded chain lands just below v (SURVEY
+            // App. B-1).  Bit v of this 256-bit table says so; it is checked against the chain for every grey
+            // (tests/test_golden.py) and, like every colour, against the reference's device code on the GPU.
+            const int word = b0 >> 5;
+            const uint32_t w = word == 0 ? 0x8c212116u : word == 1 ? 0xea528481u : word == 2 ? 0xc8324001u : word == 3 ? 0xd4449104u :
+                               word == 4 ? 0x18200881u : word == 5 ? 0x50c08704u : word == 6 ? 0xc1030a18u : 0x53129890u;
+            y -= ( int )( ( w >> ( b0 & 31 ) ) & 1u );
+        }
+        else
+        {
 #ifdef __CUDA_ARCH__
-        y = __double2int_rz( __fma_rn( 0.114, ( double )b2, __fma_rn( 0.299, ( double )b0, __dmul_rn( 0.587, ( double )b1 ) ) ) );
+            y = __double2int_rz( __fma_rn( 0.114, ( double )b2, __fma_rn( 0.299, ( double )b0, __dmul_rn( 0.587, ( double )b1 ) ) ) );
 #else
-        y = ( int )__builtin_fma( 0.114, ( double )b2, __builtin_fma( 0.299, ( double )b0, 0.587 * ( double )b1 ) );
+            y = ( int )__builtin_fma( 0.114, ( double )b2, __builtin_fma( 0.299, ( double )b0, 0.587 * ( double )b1 ) );
 #endif
+        }
     }
 #ifdef __CUDA_ARCH__
     int u = __float2int_rz( __fmul_rn( ( float )( b2 - y ), 0.492f ) );

@@ -151,3 +151,22 @@ def test_border_walks_equal_the_reference_walker(oracle):
     walker = json.load(open(os.path.join(GOLD, "border_walks_alex.json")))
     mine = oracle.border_walks(z["alex"])
     assert len(mine) == 19 and all(mine[w[0]] == w for w in walker)
+
+
+def test_product_yuv_word_on_the_host(oracle):
+    """The product's packed-YUV conversion (csrc/common.cuh, the same function the kernels inline, here through the C ABI's
+    host entry par_yuv_word): every grey (the 256-bit rounding table), every colour whose 299 b0 + 587 b1 + 114 b2 is a
+    multiple of 1000 (the only ones the FMA chain decides), and a random sample, against the oracle's fused conversion."""
+    import pixel_art_remaster_gpu_b200 as par
+    for v in range(256):
+        assert par.yuv_word(v, v, v) == oracle.yuv_word(v, v, v, True), v
+    b = np.arange(256)
+    T = (299 * b[:, None, None] + 587 * b[None, :, None] + 114 * b[None, None, :])
+    hits = np.argwhere(T % 1000 == 0)
+    assert 15000 < len(hits) < 20000
+    for b0, b1, b2 in hits[::3]:
+        assert par.yuv_word(int(b0), int(b1), int(b2)) == oracle.yuv_word(int(b0), int(b1), int(b2), True), (b0, b1, b2)
+    rng = np.random.default_rng(3)
+    for col in rng.integers(0, 1 << 24, 20000):
+        b0, b1, b2 = int(col) & 255, (int(col) >> 8) & 255, int(col) >> 16
+        assert par.yuv_word(b0, b1, b2) == oracle.yuv_word(b0, b1, b2, True)
