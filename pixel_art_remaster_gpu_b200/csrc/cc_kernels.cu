@@ -33,6 +33,22 @@ __device__ __forceinline__ int find_root( const int* lab, int x )
     return x;
 }
 
+// find with path halving for the shared-memory forest: every step re-points x at its grandparent.  The write is an
+// atomicMin: parents only ever decrease, so concurrent unions and other halving writes can only be improved on, never
+// undone (and a plain store here would be a benign but reportable race).
+__device__ __forceinline__ int find_root_halving( int* lab, int x )
+{
+    int p = lab[ x ];
+    while( p != x )
+    {
+        const int gp = lab[ p ];
+        if( gp != p ) atomicMin( &lab[ x ], gp );
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+
 // volatile-free lock-free union: hang the larger root under the smaller one
 __device__ __forceinline__ void unite( int* lab, int a, int b )
 {
@@ -60,6 +76,25 @@ __device__ __forceinline__ void unite( int* lab, int a, int b )
 //    the pixel to the left (same run below, same run above, also linked upwards), and a diagonal link only when its
 //    target is not in the run of an orthogonal link that is united anyway.
 // What remains is roughly one union per pair of touching runs.
+__device__ __forceinline__ void unite_halving( int* lab, int a, int b )
+{
+    for( ;; )
+    {
+        a = find_root_halving( lab, a );
+        b = find_root_halving( lab, b );
+        if( a == b ) return;
+        if( a < b )
+        {
+            int t = a;
+            a = b;
+            b = t;
+        }
+        int old = atomicMin( &lab[ a ], b );
+        if( old == a ) return;
+        a = old;
+    }
+}
+
 __global__ void __launch_bounds__( kThreads ) cc_tile_kernel( LabelArgs a )
 {
     __shared__ int s_lab[ kTW * kTH ];
@@ -133,7 +168,7 @@ __global__ void __launch_bounds__( kThreads ) cc_tile_kernel( LabelArgs a )
         for( int w = threadIdx.x; w < n; w += kThreads )
         {
             const uint32_t r = s_req[ w ];
-            unite( s_lab, ( int )( r >> 16 ), ( int )( r & 0xFFFFu ) );
+            unite_halving( s_lab, ( int )( r >> 16 ), ( int )( r & 0xFFFFu ) );
         }
     }
     __syncthreads();
@@ -190,12 +225,10 @@ __global__ void __launch_bounds__( kThreads ) cc_seam_kernel( LabelArgs a )
 __global__ void __launch_bounds__( kThreads ) cc_flatten_kernel( LabelArgs a )
 {
     const size_t frame_px = ( size_t )a.width * a.height;
-    const size_t t = ( size_t )blockIdx.x * kThreads + threadIdx.x;
-    if( t >= frame_px * a.n_frames ) return;
-    const size_t f = t / frame_px;
-    int* lab = a.labels + f * frame_px;
-    const int n = ( int )( t - f * frame_px );
-    lab[ n ] = find_root( lab, n );
+    const size_t n = ( size_t )blockIdx.x * kThreads + threadIdx.x;
+    if( n >= frame_px ) return;
+    int* lab = a.labels + ( size_t )blockIdx.y * frame_px;
+    lab[ n ] = find_root( lab, ( int )n );
 }
 
 } // namespace
@@ -213,8 +246,13 @@ cudaError_t launch_cc_labels( const LabelArgs& a, cudaStream_t stream, int* n_la
         part.n_frames = a.n_frames - f0 < 65535 ? a.n_frames - f0 : 65535;
         cc_seam_kernel<<< dim3( ( seam_px + kThreads - 1 ) / kThreads, part.n_frames ), kThreads, 0, stream >>>( part );
     }
-    const size_t total = ( size_t )a.width * a.height * a.n_frames;
-    cc_flatten_kernel<<< ( unsigned )( ( total + kThreads - 1 ) / kThreads ), kThreads, 0, stream >>>( a );
+    for( int f0 = 0; f0 < a.n_frames; f0 += 65535 )
+    {
+        LabelArgs part = a;
+        part.labels = a.labels + ( size_t )f0 * a.width * a.height;
+        part.n_frames = a.n_frames - f0 < 65535 ? a.n_frames - f0 : 65535;
+        cc_flatten_kernel<<< dim3( ( unsigned )( ( ( size_t )a.width * a.height + kThreads - 1 ) / kThreads ), part.n_frames ), kThreads, 0, stream >>>( part );
+    }
     if( n_launches ) *n_launches = 3;
     return cudaGetLastError();
 }
