@@ -277,3 +277,24 @@ def test_border_walks(lib, oracle):
             assert np.array_equal(labd[0].cpu().numpy(), lab)
             got = c.walks_as_dict(*c.border_walks(gd, labd)[:3])
         assert got == first, case["name"]
+
+
+@pytest.mark.gpu
+def test_antialiased_output_on_every_code_path(lib):
+    """The averaging sits in the resolve step of every variant: TMA and plain tile staging, flipped rows, the exact
+    out-of-line tile resolve (PAR_FLAG_DEBUG_WIDE), the geometric path — all give the same anti-aliased image."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    frames_np = synth.snes_stream(2, 65, 33, first_seed=12)          # odd sizes: partial tiles
+    frames = torch.from_numpy(frames_np).cuda()
+    for scale, aa in ((2, 2), (4, 2), (2, 4)):
+        with lib.Remaster(0, 65, 33, 2) as c:
+            c.aa = aa
+            g = c.resolve_crossings(c.similarity_graph(frames))
+            base = c.raster(frames, g, scale, True).cpu().numpy()
+            assert np.array_equal(c.raster(frames, g, scale, True, no_tma=True).cpu().numpy(), base)
+            assert np.array_equal(c.raster(frames, g, scale, True, debug_wide=True).cpu().numpy(), base)
+            assert np.array_equal(c.raster(frames, g, scale, True, flip_output=True).cpu().numpy(), base[:, ::-1])
+            c.no_tables = True
+            assert np.array_equal(c.raster(frames, g, scale, True).cpu().numpy(), base)
