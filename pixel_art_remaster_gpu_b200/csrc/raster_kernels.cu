@@ -12,22 +12,22 @@
 // (top-left rule).  Coverage is an even-odd crossing count in exact integer arithmetic: vertices
 // are multiples of 1/64, samples odd multiples of 1/(2s); both are scaled to units of 1/(128 s).
 //
-// Design (B200): one CTA per tile of source pixels.  (1) the final-graph bytes of the tile (+halo)
-// are staged in shared memory by one TMA bulk-tensor copy (zero fill outside the image; plain loads
-// when rows are not 16-byte multiples) and turned into 12-bit cell keys; (2) every cell of tile + 1
-// halo gets a coverage bitmask of the (s + 2h)^2 samples it can reach: cells whose polygon is their
-// hull (interior nodes, or subdivision off) copy it from a per-scale 4096-entry mask table, the
-// others are compacted into a work list and processed one thread per cell — the polygon (hull from
-// the cell table, corner cutting in exact 1/64-px integers) is streamed into a small per-thread
-// vertex buffer in shared memory, then a converged loop over its edges toggles the sample rows each
-// edge crosses (masks are 64-bit registers for s <= 4); geometry never touches HBM; (3) one thread
-// per source pixel resolves its s x s output pixels with bit operations over the 3x3 neighbourhood's
-// masks in priority order and writes whole output-row segments with 128-bit streaming stores.
-// Smoothed cells do not build their polygon at all on the fast path: even-odd coverage is XOR-linear in the
-// polygon's edges, so the mask is the XOR of a few precomputed pieces (smooth_table.h) — one CUT entry for the
-// cell's own key and kept corners, one LINK entry per shared edge with a blended end, indexed by one byte
-// read from the neighbour's key.  The tables are content-independent and built once per context and scale
-// by this file's own coverage code; cells they cannot express take the geometric path above.
+// Design (B200): one CTA per 32x32 (s <= 4) / 32x16 tile of source pixels, 24 KB of shared memory, five / four CTAs
+// per SM.  (1) The final-graph bytes and the BGR bytes of the tile (+halo) are staged in shared memory by two TMA
+// bulk-tensor copies (zero fill outside the image; plain loads when rows are not 16-byte multiples) and turned, four
+// pixels per thread, into 12-bit cell keys and RGBA words.  (2) Every cell of tile + 1 halo gets a coverage bitmask of
+// the (s + 2h)^2 samples it can reach.  Cells whose polygon is their hull (interior nodes, or subdivision off) copy it
+// from a per-scale 4096-entry mask table.  Smoothed cells are compacted into a list and do not build their polygon
+// at all: even-odd coverage is XOR-linear in the polygon's edges, so the mask is the XOR of a few precomputed pieces
+// (smooth_table.h) — one CUT entry for the cell's own key and kept corners, one LINK entry per shared edge with a
+// blended end, indexed by a 16-bit record read from the neighbour's key.  The tables are content-independent and built
+// once per context and scale by this file's own coverage code.  The few cells they cannot express take the geometric
+// path: one thread per cell, the polygon (hull from the cell table, corner cutting in exact 1/64-px integers) streamed
+// into a small per-thread vertex buffer in shared memory, then a converged loop over its edges toggling the sample
+// rows each edge crosses.  Geometry never touches HBM.  (3) One thread per source pixel resolves its s x s output
+// pixels with bit operations over the 3x3 neighbourhood's masks in priority order (for s <= 4 on whole-cell bit sets:
+// the masks are kept in a "window form" whose fields are already positioned on the reader's pixels) and writes whole
+// output-row segments with 128-bit streaming stores; with anti-aliasing on, A x A samples are averaged right there.
 // Algorithmic HBM traffic: 3 B/px colour + 1 B/px graph in, 4*s*s B/px out.
 #include "kernels.cuh"
 #include "polygon.cuh"
@@ -61,7 +61,7 @@ struct Cfg
     static constexpr int REACH = H * SSP + SSP / 2;       // offset of the first sample NOT covered by the mask
     static constexpr bool PACK = R * R <= 63;             // whole mask in one 64-bit word (bit 63 = wide flag)
     static constexpr int MW = PACK ? 2 : R;               // 32-bit words per mask
-    static constexpr int TW = S <= 4 ? 64 : 32, TH = 16;
+    static constexpr int TW = 32, TH = S <= 4 ? 32 : 16;
     static constexpr int CW = TW + 2, CH = TH + 2;        // cells whose masks are needed (halo 1)
     static constexpr int KW = TW + 4, KH = TH + 4;        // cells whose keys and colours are needed (halo 2)
     static constexpr int GOFF = 16;                       // staged rows begin at column x0 - 16 (TMA: 16-byte aligned start)
@@ -1227,16 +1227,16 @@ cudaError_t launch_build_smooth_tables( int scale, const CellTablePtrs& tab, con
 
 void raster_tma_box( int scale, uint32_t box[ 3 ] )
 {
-    const int tw = scale <= 4 ? 64 : 32;
+    const int tw = 32;
     box[ 0 ] = ( uint32_t )( ( 16 + tw + 3 + 15 ) / 16 * 16 );
-    box[ 1 ] = 16 + 4;
+    box[ 1 ] = ( scale <= 4 ? 32 : 16 ) + 4;
     box[ 2 ] = 1;
 }
 
 void raster_img_tma_box( int scale, uint32_t box[ 3 ] )
 {
     box[ 0 ] = 0;
-    box[ 1 ] = 16 + 4;
+    box[ 1 ] = ( scale <= 4 ? 32 : 16 ) + 4;
     box[ 2 ] = 1;
 #define PAR_RAWP( S )                          \
     box[ 0 ] = ( uint32_t )Cfg< S >::RAWP;     \
