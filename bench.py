@@ -150,6 +150,38 @@ def cpu_reference_fps(frames, threads, seconds_budget=20.0):
     return done / dt, kind, done, dt
 
 
+def time_drop_in(par, img, n_calls):
+    """ms per call of the product's `launch_kernel` export (kernel.cu:286-288 signature) on one frame, end to end."""
+    import ctypes as C
+    import torch
+    L = par.load_library()
+    Hh, Ww = img.shape[:2]
+    N = Hh * Ww
+    flat = np.ascontiguousarray(img).reshape(-1)
+    pos = torch.empty((N, par.CELL_SLOTS, 2), dtype=torch.float32, device="cuda")
+    col = torch.empty((N, par.CELL_SLOTS, 4), dtype=torch.uint8, device="cuda")
+    graph = np.zeros((Hh, Ww), np.uint8)
+    count = np.zeros(N, np.int32)
+    free = C.CDLL(None).free
+    free.argtypes = [C.c_void_p]
+
+    def call():
+        ptr = L.launch_kernel(pos.data_ptr(), col.data_ptr(), 0.0, flat.ctypes.data, Ww, Hh, 3 * Ww, count.ctypes.data, graph.ctypes.data, True)
+        free(C.c_void_p(ptr))
+
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(n_calls):
+        call()
+    torch.cuda.synchronize()
+    ms = 1e3 * (time.perf_counter() - t0) / n_calls
+    return {"value": 1e3 / ms, "unit": "frames/s", "ms_per_call": ms,
+            "what": "this library's launch_kernel (the reference's symbol and signature) per frame, end to end: H2D, graph, crossings, "
+                    "cells + subdivision + ear clipping into the 45-slot VBO arrays, D2H of the triangle list, graph and counts"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -351,6 +383,12 @@ def run_ours(args):
                                                                "output only, no rasterization (the reference rasterizes in OpenGL)"}
             except Exception as exc:  # a baseline must never break the bench line
                 line["reference_cuda_baseline"] = {"unavailable": str(exc)[:200]}
+            # like for like with the line above: OUR export of the same symbol (launch_kernel, same arguments, same outputs
+            # incl. the 45-slot VBO arrays and the host triangle list) called once per frame on the same frame
+            try:
+                line["launch_kernel_drop_in"] = time_drop_in(par, synth.snes_frame(W, H, synth.BASE_SEED), 20)
+            except Exception as exc:
+                line["launch_kernel_drop_in"] = {"unavailable": str(exc)[:200]}
         print(json.dumps(line))
     barrier()
     ctx.close()
