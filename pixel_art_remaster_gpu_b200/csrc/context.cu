@@ -538,6 +538,13 @@ int par_remaster_device( par_context* c, const par_job* j )
         if( !aux ) aux = c->scratch_aux;
         if( !graph ) graph = c->scratch_graph;
     }
+    if( j->rgba ) // refuse an impossible raster request before anything is launched
+    {
+        const int aa = ( j->flags & PAR_FLAG_AA4 ) ? 4 : ( ( j->flags & PAR_FLAG_AA2 ) ? 2 : 1 );
+        if( !raster_aa_supported( j->scale, aa ) )
+            return c->fail( PAR_ERR_INVALID, "unsupported scale %d with %dx%d samples per pixel (scale x samples must be one of 1,2,3,4,6,8)", j->scale,
+                            aa, aa );
+    }
     if( ( st = run_similarity( c, j, aux ) ) ) return st;
     if( ( st = run_crossings( c, j, aux, graph ) ) ) return st;
     if( j->labels && ( st = run_labels( c, j, graph, j->labels ) ) ) return st;

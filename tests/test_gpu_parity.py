@@ -298,3 +298,38 @@ def test_antialiased_output_on_every_code_path(lib):
             assert np.array_equal(c.raster(frames, g, scale, True, flip_output=True).cpu().numpy(), base[:, ::-1])
             c.no_tables = True
             assert np.array_equal(c.raster(frames, g, scale, True).cpu().numpy(), base)
+
+
+@pytest.mark.gpu
+def test_c_abi_error_behaviour(lib):
+    """Bad jobs are refused with a status and a message, nothing is launched and the context stays usable."""
+    import ctypes as C
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    L = lib.load_library()
+    frames = torch.from_numpy(synth.snes_stream(2, 40, 30, first_seed=3)).cuda()
+    with lib.Remaster(0, 40, 30, 2) as c:
+        good = c.remaster(frames, scale=2, subdivide=True)["rgba"].clone()
+        launches = c.launch_count
+        rgba = torch.empty((2, 60, 80, 4), dtype=torch.uint8, device="cuda")
+
+        def job(**kw):
+            j = lib.ParJob()
+            j.bgr, j.width, j.height, j.widthstep, j.frame_stride, j.n_frames, j.scale, j.flags = frames.data_ptr(), 40, 30, 120, 0, 2, 2, 1
+            j.rgba = rgba.data_ptr()
+            for k, v in kw.items():
+                setattr(j, k, v)
+            return j
+
+        INVALID, CAPACITY = 1, 4
+        for bad, status in ((job(n_frames=0), INVALID), (job(width=0), INVALID), (job(height=-3), INVALID), (job(bgr=None), INVALID),
+                            (job(widthstep=100), INVALID), (job(frame_stride=100), INVALID), (job(scale=5), INVALID), (job(scale=7), INVALID),
+                            (job(scale=4, flags=1 | 64), INVALID),            # 4x4 samples at scale 4 would need a sampling scale of 16
+                            (job(n_frames=3), CAPACITY)):                     # more frames than the context was created for (scratch graphs)
+            assert L.par_remaster_device(c.handle, C.byref(bad)) == status
+            assert len(L.par_last_error(c.handle)) > 0
+        assert L.par_remaster_device(c.handle, None) == INVALID
+        assert L.par_border_walks(c.handle, None, None, 40, 30, 2, None, None, None, 10, None) == INVALID
+        assert c.launch_count == launches                                     # nothing ran
+        assert torch.equal(c.remaster(frames, scale=2, subdivide=True)["rgba"], good)
