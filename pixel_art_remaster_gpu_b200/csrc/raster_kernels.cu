@@ -984,9 +984,9 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
                 {
                     const uint32_t take = cov[ k ] & rem;
                     rem &= ~cov[ k ];
-                    if( k == 4 || take == 0u ) continue;
+                    if( k == 4 ) continue;
                     const int dj = 1 - k / 3, di = 1 - k % 3;
-                    const uint32_t cw = col[ dj * C::KW + di ];
+                    const uint32_t cw = take ? col[ dj * C::KW + di ] : 0u; // (predicated load: no branch per candidate)
                     // a candidate can only hold pixels of its own window
 #pragma unroll
                     for( int bit = 0; bit < S * S; bit++ )
