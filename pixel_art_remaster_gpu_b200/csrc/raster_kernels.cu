@@ -550,14 +550,9 @@ template< int S >
 __global__ void build_link_table_kernel( const LinkClass* classes, uint64_t* link )
 {
     const LinkClass c = classes[ blockIdx.x ];
-    const int sub = threadIdx.x;                 // = rank a | rank b << 4 (a class with one blended end ignores the other nibble)
-    uint64_t* entry = link + ( size_t )( c.block * 256u + sub ) * Entry< S >::EW;
-    if( ( sub & 15 ) >= 4 || ( sub >> 4 ) >= 4 )  // ranks are 0..3: the rest of the block is never addressed
-    {
-        for( int w = 0; w < Entry< S >::EW; w++ ) entry[ w ] = 0ull;
-        return;
-    }
-    const int a = c.after[ sub & 15 ], b = c.before[ sub >> 4 ];
+    const int sub = threadIdx.x;                 // = rank a | rank b << 2 (a class with one blended end ignores the other rank)
+    uint64_t* entry = link + ( size_t )( c.block * 16u + sub ) * Entry< S >::EW;
+    const int a = c.after[ sub & 3 ], b = c.before[ sub >> 2 ];
     const int di = edge_di( c.e ), dj = edge_dj( c.e );
     const Q2 P0{ c.px[ 0 ], c.py[ 0 ] }, P1{ c.px[ 1 ], c.py[ 1 ] }, P2{ c.px[ 2 ], c.py[ 2 ] }, P3{ c.px[ 3 ], c.py[ 3 ] };
     int xs[ 6 ], ys[ 6 ], m = 0;
@@ -661,7 +656,8 @@ __device__ __forceinline__ bool smooth_lookup( const SmoothTablePtrs& st, const 
         const uint32_t d = links[ k ], r = nb[ k ];
         const uint32_t ends = ( d >> 16 ) & 255u;
         mismatch |= ( ( r ^ d ) >> 8 ) & ends; // the blended vertices must be the end (A) / start (B) of the neighbour's edge
-        const uint64_t* le = st.link + ( size_t )( ( d >> 24 ) * 256u + ( r & ends ) ) * E::EW;
+        const uint32_t sub = r & ends; // rank a | rank b << 4 -> the class's 4 x 4 block (one 128-byte line at s <= 4)
+        const uint64_t* le = st.link + ( size_t )( ( d >> 24 ) * 16u + ( ( sub & 3u ) | ( ( sub >> 2 ) & 12u ) ) ) * E::EW;
 #pragma unroll
         for( int w = 0; w < E::EW; w++ )
         {
@@ -1217,8 +1213,8 @@ cudaError_t launch_build_smooth_tables( int scale, const CellTablePtrs& tab, con
 {
 #define PAR_BUILD_SMOOTH( S )                                                                        \
     build_cut_table_kernel< S ><<< kCellKeys * 16 / 128, 128, 0, stream >>>( tab, cut );             \
-    cudaMemsetAsync( link, 0, 256 * Entry< S >::EW * sizeof( uint64_t ), stream ); /* block 0: the all-zero block */ \
-    build_link_table_kernel< S ><<< n_classes, 256, 0, stream >>>( d_classes, link );                \
+    cudaMemsetAsync( link, 0, 16 * Entry< S >::EW * sizeof( uint64_t ), stream ); /* block 0: the all-zero block */ \
+    build_link_table_kernel< S ><<< n_classes, 16, 0, stream >>>( d_classes, link );                 \
     return cudaGetLastError()
     PAR_FOR_SCALE( scale, PAR_BUILD_SMOOTH )
 #undef PAR_BUILD_SMOOTH

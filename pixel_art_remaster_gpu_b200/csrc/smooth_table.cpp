@@ -36,7 +36,7 @@ void build_smooth_tables( const CellTables& cells, SmoothTables* out )
 {
     memset( out->rec, 0, sizeof( out->rec ) );
     out->classes.clear();
-    out->link_entries = 256; // block 0: the all-zero block unused descriptor slots point at
+    out->link_entries = 16; // block 0: the all-zero block unused descriptor slots point at
     out->slow_keys = 0;
     typedef std::tuple< int, int, int, int, int, int, int, int, int, int, int > ClassKey; // e, hasA, hasB, 4 x (x, y)
     std::map< ClassKey, uint32_t > class_block;
@@ -132,15 +132,15 @@ void build_smooth_tables( const CellTables& cells, SmoothTables* out )
                     c.after[ k ] = ( int8_t )after_code[ 7 - h.link[ t ] ][ k ];
                     c.before[ k ] = ( int8_t )before_code[ 7 - h.link[ t ] ][ k ];
                 }
-                c.block = out->link_entries / 256;
-                out->link_entries += 256;
+                c.block = out->link_entries / 16;
+                out->link_entries += 16;
                 out->classes.push_back( c );
                 it = class_block.insert( std::make_pair( ck, c.block ) ).first;
             }
             links[ n_links++ ] = ( uint32_t )h.link[ t ] | ( ( hasA ? codeA : 0u ) | ( hasB ? codeB << 4 : 0u ) ) << 8 |
                                  ( ( hasA ? 0x0Fu : 0u ) | ( hasB ? 0xF0u : 0u ) ) << 16 | it->second << 24;
         }
-        if( slow || !ranks_ok || n_links > kMaxLinks || out->link_entries / 256 > 255 )
+        if( slow || !ranks_ok || n_links > kMaxLinks || out->link_entries / 16 > 255 )
         {
             out->rec[ key ].link[ 0 ] = kSmoothSlow;
             out->slow_keys++;

@@ -43,8 +43,8 @@ namespace par {
 //   [8,16)  expect  codeA | codeB << 4: the edge's start / end vertex as point codes in the neighbour's frame,
 //                   to be compared with bits [8,16) of the neighbour record
 //   [16,24) ends    0x0F: the start vertex is blended (end A), 0xF0: the end vertex is (end B), 0xFF: both.
-//                   Masks the comparison above AND selects the index inside the class: entry = 256 block + (nbr & ends)
-//   [24,32) block   the class's 256-entry block of the link table (block 0 is all zero)
+//                   Masks the comparison above AND selects the ranks: entry = 16 block + (rank a | rank b << 2)
+//   [24,32) block   the class's 16-entry block of the link table: 4 x 4 ranks, one 128-byte line at s <= 4 (block 0 is all zero)
 // An unused slot is 0: it compares nothing, selects entry 0 of block 0 and so contributes an empty mask.
 constexpr int kMaxLinks = 4;
 constexpr uint32_t kSmoothSlow = 0xFFFFFFFFu; // in link[0]: this key always takes the geometric path
@@ -61,7 +61,7 @@ struct LinkClass
 {
     int8_t e, hasA, hasB, pad;
     int8_t px[ 4 ], py[ 4 ]; // hull vertices t-1, t, t+1, t+2
-    uint32_t block;          // its 256-entry block of the link table (>= 1)
+    uint32_t block;          // its 16-entry block of the link table (>= 1)
     int8_t after[ 4 ], before[ 4 ]; // rank -> point code of the neighbour's vertex after the edge end / before its start
     uint32_t pad2;
 };
@@ -70,7 +70,7 @@ struct SmoothTables
 {
     SmoothRecord rec[ kCellKeys ];
     std::vector< LinkClass > classes;
-    uint32_t link_entries = 0; // total entries of the link table (256 per class + the zero block)
+    uint32_t link_entries = 0; // total entries of the link table (16 per class + the zero block)
     uint32_t slow_keys = 0;    // keys that always take the geometric path
 };
 
