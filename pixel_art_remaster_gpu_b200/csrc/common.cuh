@@ -28,10 +28,14 @@ constexpr int kThrV = 0x00000006;
 // far from any integer, so trunc() equals T/1000 in integer arithmetic.  Only exact multiples
 // (e.g. every grey) need the real FMA chain, whose rounding decides between y and y-1.
 // U and V are float products truncated toward zero (graph_functions.cu:93-94).
-__host__ __device__ __forceinline__ uint32_t yuv_word( int b0, int b1, int b2 )
+// (T = 299*b0 + 587*b1 + 114*b2 is passed in: the graph kernel forms it with two dot-product instructions)
+__host__ __device__ __forceinline__ uint32_t yuv_word_t( int T, int b0, int b1, int b2 )
 {
-    int T = 299 * b0 + 587 * b1 + 114 * b2;
+#ifdef __CUDA_ARCH__
+    int y = ( int )__umulhi( ( unsigned )T, 4294968u ); // = T / 1000 exactly for T <= 255000 (4294968 * 1000 - 2^32 = 704, 704 T < 2^32)
+#else
     int y = T / 1000;
+#endif
     if( T - y * 1000 == 0 && T != 0 ) // (black stays 0: the chain of three zeros is exact)
     {
         if( b0 == b1 && b1 == b2 )
@@ -62,6 +66,7 @@ __host__ __device__ __forceinline__ uint32_t yuv_word( int b0, int b1, int b2 )
 #endif
     return ( uint32_t )( y << 16 ) + ( uint32_t )( u * 256 ) + ( uint32_t )v;
 }
+__host__ __device__ __forceinline__ uint32_t yuv_word( int b0, int b1, int b2 ) { return yuv_word_t( 299 * b0 + 587 * b1 + 114 * b2, b0, b1, b2 ); }
 
 // 1 when the two packed words are similar (graph_functions.cu:291-293 negated)
 __host__ __device__ __forceinline__ bool yuv_similar( uint32_t p, uint32_t q )

@@ -7,11 +7,16 @@
 // Design (B200): one CTA per 64x32-pixel tile of one frame.  The BGR bytes of the tile plus a
 // 1-pixel halo are brought into shared memory by ONE TMA bulk-tensor copy (out-of-image bytes are
 // zero-filled by the TMA unit); a plain-load path fills the same layout when the frame pointer or
-// strides are not 16-byte multiples.  Each pixel is converted to its packed YUV word once.  The
-// graph is undirected, so instead of 8 comparisons per pixel the kernel evaluates each 2x2 block
-// once (lower-left pixel owns it): the four side edges and the two diagonals, and — since a block
-// whose four sides are all linked loses both diagonals (crossCheck_4) — stage B is folded into the
-// same step.  The pixel byte is then assembled from the four blocks that touch the pixel.
+// strides are not 16-byte multiples.  Each pixel is converted to its packed YUV word once, and the
+// words of four neighbouring pixels are stored PLANAR (one 32-bit word of four V bytes, one of U, one of
+// Y), so that one VABSDIFF4 compares a field of four pixel pairs at once.  The graph is undirected, so
+// instead of 8 comparisons per pixel the kernel evaluates each 2x2 block once (lower-left pixel owns it):
+// the four side edges and the two diagonals — six tests of four pairs each per four blocks — and, since a
+// block whose four sides are all linked loses both diagonals (crossCheck_4), stage B is folded into the
+// same step.  The pixel byte is then assembled from the four blocks that touch the pixel.  Pixels outside
+// the image are staged as zeros (black) and never marked: the links that point out of the image are
+// cleared when the bytes are assembled, and a block across the image border can only differ from the
+// reference's in its diagonals, which all point out of the image.
 // Algorithmic HBM traffic: 3 B/px in + 1 B/px out.
 #include "kernels.cuh"
 
@@ -27,12 +32,10 @@ constexpr int kRawPitch = 224;               // bytes per staged row: 13 + 3*66 
 // so that a group is one aligned 16-byte (YUV words) / 4-byte (block bytes) unit; the group's 12 raw bytes start
 // at byte 13 + 3(4g-3) = 4 + 12g, which is word aligned as well.
 constexpr int kGroups = 18;
-constexpr int kYuvPitch = 4 * kGroups;       // words
 constexpr int kBH = kTH + 1;                 // 2x2 block rows per tile (block (c,r): lower-left pixel (c,r), c = 0..64)
 constexpr int kBlkGroups = 17;               // block columns 4g-3 .. 4g, g = 0..16
 constexpr int kBlkPitch = 4 * kGroups;       // bytes
 constexpr int kThreads = 256;
-constexpr uint32_t kInvalid = 0x80000000u;   // pixel outside the image
 
 static_assert( kRawPitch >= kRawOff + 3 * kYW && kRawPitch % 16 == 0, "TMA box rows are multiples of 16 bytes" );
 static_assert( 4 + 12 * kGroups <= kRawPitch, "the last group's raw bytes are inside the staged row" );
@@ -40,21 +43,26 @@ static_assert( 4 + 12 * kGroups <= kRawPitch, "the last group's raw bytes are in
 struct __align__( 128 ) GraphSmem
 {
     uint8_t raw[ kYH * kRawPitch ];
-    alignas( 16 ) uint32_t yuv[ kYH * kYuvPitch ];
+    alignas( 16 ) uint4 planes[ kYH * kGroups ]; // per group of four pixels: x = their V bytes, y = U bytes, z = Y bytes (w unused)
     alignas( 16 ) uint8_t blk[ kBH * kBlkPitch ];
     uint64_t bar;
 };
 
-// Similarity of two staged words.  A staged word is the packed YUV word's low three bytes (V, U, Y — the
-// fields graph_functions.cu:291-293 masks out and compares) with a top byte of 0x00 for a pixel inside the
-// image and 0x80 for one outside.  One VABSDIFF4 gives the four per-byte absolute differences; a byte
-// exceeds its threshold (top 0, Y 5, U 7, V 6) iff its bit 7 is set or its low 7 bits plus (0x7F - threshold)
-// carry into bit 7.  In-image vs out-of-image differs by 0x80 in the top byte, so it is never similar.
-__device__ __forceinline__ uint32_t sim( uint32_t p, uint32_t q )
+// Four pixel pairs at once: p and q hold the V, U, Y bytes of four pixels each (one word per field).  Returns 0x80 in
+// byte k when pair k is NOT similar: a field's absolute difference (one VABSDIFF4 for the four pairs) exceeds its
+// threshold (graph_functions.cu:14-19, 291-293: Y 5, U 7, V 6) iff its bit 7 is set or its low 7 bits plus
+// (0x7F - threshold) carry into bit 7.
+__device__ __forceinline__ uint32_t dissimilar4( const uint4& p, const uint4& q )
 {
-    const uint32_t d = __vabsdiffu4( p, q );
-    const uint32_t s = ( d & 0x7F7F7F7Fu ) + 0x7F7A7879u;
-    return ( ( ( s | d ) & 0x80808080u ) == 0u ) ? 1u : 0u;
+    const uint32_t dv = __vabsdiffu4( p.x, q.x ), du = __vabsdiffu4( p.y, q.y ), dy = __vabsdiffu4( p.z, q.z );
+    const uint32_t tv = ( dv & 0x7F7F7F7Fu ) + 0x79797979u, tu = ( du & 0x7F7F7F7Fu ) + 0x78787878u, ty = ( dy & 0x7F7F7F7Fu ) + 0x7A7A7A7Au;
+    return ( tv | dv | tu | du | ty | dy ) & 0x80808080u;
+}
+
+// the same four fields one pixel further right: bytes 1..3 of this group and byte 0 of the next
+__device__ __forceinline__ uint4 shifted( const uint4& g, const uint4& next )
+{
+    return make_uint4( __byte_perm( g.x, next.x, 0x4321 ), __byte_perm( g.y, next.y, 0x4321 ), __byte_perm( g.z, next.z, 0x4321 ), 0u );
 }
 
 template< bool kUseTma >
@@ -95,51 +103,42 @@ __global__ void __launch_bounds__( kThreads ) similarity_graph_kernel( const __g
         __syncthreads();
     }
 
-    // packed YUV word per pixel, once; four pixels (three raw words) per step, one 128-bit store
+    // packed YUV word per pixel, once; four pixels (three raw words) per step.  T = 299 b0 + 587 b1 + 114 b2 of a
+    // pixel is two 16 x 8-bit dot products (IDP.2A) on the raw words, wherever its three bytes sit in them.
     for( int idx = tid; idx < kYH * kGroups; idx += kThreads )
     {
         const int r = idx / kGroups, g = idx - r * kGroups;
         const uint32_t* rw = reinterpret_cast< const uint32_t* >( &s.raw[ r * kRawPitch + 4 + 12 * g ] );
         const uint32_t w0 = rw[ 0 ], w1 = rw[ 1 ], w2 = rw[ 2 ];
-        uint32_t y[ 4 ];
-        y[ 0 ] = yuv_word( w0 & 255u, ( w0 >> 8 ) & 255u, ( w0 >> 16 ) & 255u ) & 0x00FFFFFFu;
-        y[ 1 ] = yuv_word( w0 >> 24, w1 & 255u, ( w1 >> 8 ) & 255u ) & 0x00FFFFFFu;
-        y[ 2 ] = yuv_word( ( w1 >> 16 ) & 255u, w1 >> 24, w2 & 255u ) & 0x00FFFFFFu;
-        y[ 3 ] = yuv_word( ( w2 >> 8 ) & 255u, ( w2 >> 16 ) & 255u, w2 >> 24 ) & 0x00FFFFFFu;
-        const int gx = x0 - 4 + 4 * g, gy = y0 - 1 + r; // image column of the group's first pixel (c = 4g - 3)
-        if( gy < 0 || gy >= a.height )
-            y[ 0 ] = y[ 1 ] = y[ 2 ] = y[ 3 ] = kInvalid;
-        else if( gx < 0 || gx + 3 >= a.width )
-        {
-#pragma unroll
-            for( int k = 0; k < 4; k++ )
-                if( gx + k < 0 || gx + k >= a.width ) y[ k ] = kInvalid;
-        }
-        *reinterpret_cast< uint4* >( &s.yuv[ r * kYuvPitch + 4 * g ] ) = make_uint4( y[ 0 ], y[ 1 ], y[ 2 ], y[ 3 ] );
+        constexpr uint32_t k299_587 = 299u | 587u << 16, k114_0 = 114u, k0_299 = 299u << 16, k587_114 = 587u | 114u << 16;
+        const uint32_t t0 = __dp2a_hi( k114_0, w0, __dp2a_lo( k299_587, w0, 0u ) );   // bytes 0 1 2 of w0
+        const uint32_t t1 = __dp2a_lo( k587_114, w1, __dp2a_hi( k0_299, w0, 0u ) );   // byte 3 of w0, bytes 0 1 of w1
+        const uint32_t t2 = __dp2a_lo( k114_0, w2, __dp2a_hi( k299_587, w1, 0u ) );   // bytes 2 3 of w1, byte 0 of w2
+        const uint32_t t3 = __dp2a_hi( k587_114, w2, __dp2a_lo( k0_299, w2, 0u ) );   // bytes 1 2 3 of w2
+        const uint32_t y0w = yuv_word_t( ( int )t0, w0 & 255u, ( w0 >> 8 ) & 255u, ( w0 >> 16 ) & 255u );
+        const uint32_t y1w = yuv_word_t( ( int )t1, w0 >> 24, w1 & 255u, ( w1 >> 8 ) & 255u );
+        const uint32_t y2w = yuv_word_t( ( int )t2, ( w1 >> 16 ) & 255u, w1 >> 24, w2 & 255u );
+        const uint32_t y3w = yuv_word_t( ( int )t3, ( w2 >> 8 ) & 255u, ( w2 >> 16 ) & 255u, w2 >> 24 );
+        // 4 x 3 byte transpose: word k = (V, U, Y, -) of pixel k  ->  (V0 V1 V2 V3), (U0 ..), (Y0 ..)
+        const uint32_t vu01 = __byte_perm( y0w, y1w, 0x5140 ), vu23 = __byte_perm( y2w, y3w, 0x5140 ); // V0 V1 U0 U1
+        const uint32_t yy01 = __byte_perm( y0w, y1w, 0x7362 ), yy23 = __byte_perm( y2w, y3w, 0x7362 ); // Y0 Y1 .  .
+        s.planes[ idx ] = make_uint4( __byte_perm( vu01, vu23, 0x5410 ), __byte_perm( vu01, vu23, 0x7632 ), __byte_perm( yy01, yy23, 0x5410 ), 0u );
     }
     __syncthreads();
 
-    // four 2x2 blocks per step (block columns 4g-3 .. 4g): bit0 = bottom side, bit1 = left side, bit2 = "/" diagonal,
-    // bit3 = "\" diagonal, diagonals already cleared when all four sides are linked (stage B)
+    // four 2x2 blocks per step (block columns 4g-3 .. 4g, lower-left pixels = group g of row r): bit0 = bottom side,
+    // bit1 = left side, bit2 = "/" diagonal, bit3 = "\" diagonal, diagonals already cleared when all four sides are
+    // linked (stage B)
     for( int idx = tid; idx < kBH * kBlkGroups; idx += kThreads )
     {
         const int r = idx / kBlkGroups, g = idx - r * kBlkGroups;
-        const uint32_t* lo = &s.yuv[ r * kYuvPitch + 4 * g ];
-        const uint32_t* hi = lo + kYuvPitch;
-        const uint4 l4 = *reinterpret_cast< const uint4* >( lo ), h4 = *reinterpret_cast< const uint4* >( hi );
-        const uint32_t p[ 5 ] = { l4.x, l4.y, l4.z, l4.w, lo[ 4 ] }, q[ 5 ] = { h4.x, h4.y, h4.z, h4.w, hi[ 4 ] };
-        uint32_t v[ 5 ];
-#pragma unroll
-        for( int k = 0; k < 5; k++ ) v[ k ] = sim( p[ k ], q[ k ] ); // vertical sides
-        uint32_t word = 0u;
-#pragma unroll
-        for( int k = 0; k < 4; k++ )
-        {
-            const uint32_t hb = sim( p[ k ], p[ k + 1 ] ), ht = sim( q[ k ], q[ k + 1 ] );
-            const uint32_t d1 = sim( p[ k ], q[ k + 1 ] ), d2 = sim( p[ k + 1 ], q[ k ] );
-            const uint32_t keep = ( hb & ht & v[ k ] & v[ k + 1 ] ) ^ 1u;
-            word |= ( hb | ( v[ k ] << 1 ) | ( ( d1 & keep ) << 2 ) | ( ( d2 & keep ) << 3 ) ) << ( 8 * k );
-        }
+        const uint4* lo = &s.planes[ r * kGroups + g ];
+        const uint4 p = lo[ 0 ], q = lo[ kGroups ];                                      // pixels (c, r), (c, r+1)
+        const uint4 ps = shifted( p, lo[ 1 ] ), qs = shifted( q, lo[ kGroups + 1 ] );    // pixels (c+1, r), (c+1, r+1)
+        const uint32_t hb = dissimilar4( p, ps ), ht = dissimilar4( q, qs ), vl = dissimilar4( p, q ), vr = dissimilar4( ps, qs );
+        const uint32_t d1 = dissimilar4( p, qs ), d2 = dissimilar4( ps, q );
+        const uint32_t keep = hb | ht | vl | vr; // 0x80: some side is missing, the diagonals stay
+        const uint32_t word = ( ( hb ^ 0x80808080u ) >> 7 ) | ( ( vl ^ 0x80808080u ) >> 6 ) | ( ( ~d1 & keep ) >> 5 ) | ( ( ~d2 & keep ) >> 4 );
         *reinterpret_cast< uint32_t* >( &s.blk[ r * kBlkPitch + 4 * g ] ) = word;
     }
     __syncthreads();
@@ -157,14 +156,21 @@ __global__ void __launch_bounds__( kThreads ) similarity_graph_kernel( const __g
         const uint32_t* dn = reinterpret_cast< const uint32_t* >( &s.blk[ ly * kBlkPitch + lx ] );
         const uint32_t ur = up[ 1 ], dr = dn[ 1 ];                                                    // block columns lx+1 .. lx+4
         const uint32_t ul = __byte_perm( up[ 0 ], ur, 0x6543 ), dl = __byte_perm( dn[ 0 ], dr, 0x6543 ); // block columns lx .. lx+3
-        const uint32_t bytes = ( ( ul >> 3 ) & 0x01010101u )    // bit 0: "\" of the up-left block
-                               | ( ur & 0x02020202u )           // bit 1: up (left side of the up-right block)
-                               | ( ur & 0x04040404u )           // bit 2: "/" of the up-right block
-                               | ( ( ul << 3 ) & 0x08080808u )  // bit 3: left (bottom side of the up-left block)
-                               | ( ( ur << 4 ) & 0x10101010u )  // bit 4: right (bottom side of the up-right block)
-                               | ( ( dl << 3 ) & 0x20202020u )  // bit 5: "/" of the down-left block
-                               | ( ( dr << 5 ) & 0x40404040u )  // bit 6: down (left side of the down-right block)
-                               | ( ( dr << 4 ) & 0x80808080u ); // bit 7: "\" of the down-right block
+        uint32_t bytes = ( ( ul >> 3 ) & 0x01010101u )    // bit 0: "\" of the up-left block
+                         | ( ur & 0x02020202u )           // bit 1: up (left side of the up-right block)
+                         | ( ur & 0x04040404u )           // bit 2: "/" of the up-right block
+                         | ( ( ul << 3 ) & 0x08080808u )  // bit 3: left (bottom side of the up-left block)
+                         | ( ( ur << 4 ) & 0x10101010u )  // bit 4: right (bottom side of the up-right block)
+                         | ( ( dl << 3 ) & 0x20202020u )  // bit 5: "/" of the down-left block
+                         | ( ( dr << 5 ) & 0x40404040u )  // bit 6: down (left side of the down-right block)
+                         | ( ( dr << 4 ) & 0x80808080u ); // bit 7: "\" of the down-right block
+        // no links out of the image (graph_functions.cu:162-171 test the neighbour's coordinates): bits 5 6 7 point
+        // down, 0 1 2 up, 0 3 5 left, 2 4 7 right
+        if( gy == 0 ) bytes &= 0x1F1F1F1Fu;
+        if( gy == a.height - 1 ) bytes &= 0xF8F8F8F8u;
+        if( gx == 0 ) bytes &= 0xFFFFFFD6u;
+        const int last = a.width - 1 - gx; // byte lane of the image's last column
+        if( last < 4 ) bytes &= ~( 0x94u << ( 8 * last ) );
         size_t o = ( size_t )gy * a.width + gx;
         if( word_ok && gx + 3 < a.width )
             *reinterpret_cast< uint32_t* >( out + o ) = bytes;

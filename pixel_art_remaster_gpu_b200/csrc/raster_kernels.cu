@@ -17,7 +17,7 @@
 // bulk-tensor copies (zero fill outside the image; plain loads when rows are not 16-byte multiples) and turned, four
 // pixels per thread, into 12-bit cell keys and RGBA words.  (2) Every cell of tile + 1 halo gets a coverage bitmask of
 // the (s + 2h)^2 samples it can reach.  Cells whose polygon is their hull (interior nodes, or subdivision off) copy it
-// from a per-scale 4096-entry mask table.  Smoothed cells are compacted into a list and do not build their polygon
+// from a per-scale 4096-entry mask table.  Smoothed cells are handled in tile order and do not build their polygon
 // at all: even-odd coverage is XOR-linear in the polygon's edges, so the mask is the XOR of a few precomputed pieces
 // (smooth_table.h) — one CUT entry for the cell's own key and kept corners, one LINK entry per shared edge with a
 // blended end, indexed by a 16-bit record read from the neighbour's key.  The tables are content-independent and built
@@ -86,16 +86,14 @@ struct Cfg
     static constexpr uint32_t M_RIGHTCOL = M_COL0 << ( S - 1 );         // my column S-1 <- F1 of the cell to the right
     static constexpr uint32_t M_BOTROW = ( 1u << S ) - 1u;              // my row 0      <- F2 of the cell below
     static constexpr uint32_t M_TOPROW = M_BOTROW << ( S * ( S - 1 ) ); // my row S-1    <- F2 of the cell above
-    // Shared memory carve-up (bytes).  The first region has three lives: (1) the staged graph and BGR rows (the TMA
-    // destinations) until the staging pass has turned them into keys and colours; (2) the list of smoothed cells
-    // (classification -> table pass) next to the list of cells for the geometric path; (3) the geometric path's vertex
-    // buffers, over the first list, which is dead by then.  Keeping the CTA at 24 KB lets five of them share an SM
-    // with 124 KB left as L1 for the tables — the kernel is sensitive to both.
+    // Shared memory carve-up (bytes).  The first region has two lives: (1) the staged graph and BGR rows (the TMA
+    // destinations) until the staging pass has turned them into keys and colours; (2) the geometric path's vertex
+    // buffers next to the list of cells queued for it.  Keeping the CTA at 24 KB lets five of them share an SM with
+    // 124 KB left as L1 for the tables — the kernel is sensitive to both.
     static constexpr int off_graph = 0;
     static constexpr int off_raw = ( KH * GP + 127 ) / 128 * 128;
-    static constexpr int off_gen = 0, off_vbuf = 0;
-    static constexpr int sz_first_list = NC * 2 > kMaxVerts * kGeoThreads * 2 ? NC * 2 : kMaxVerts * kGeoThreads * 2;
-    static constexpr int off_work = ( sz_first_list + 15 ) / 16 * 16;
+    static constexpr int off_vbuf = 0;
+    static constexpr int off_work = ( kMaxVerts * kGeoThreads * 2 + 15 ) / 16 * 16;
     static constexpr int sz_stage = off_raw + KH * RAWP, sz_lists = off_work + NC * 2;
     static constexpr int off_keys = ( ( sz_stage > sz_lists ? sz_stage : sz_lists ) + 127 ) / 128 * 128;
     static constexpr int off_col = off_keys + ( KW * KH * 2 + 15 ) / 16 * 16;
@@ -695,7 +693,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     const uint8_t* graph = a.graph + ( size_t )f * frame_px;
 
     // (1) stage graph bytes: rows y0-2 .. y0+TH+1, columns x0-16 .. x0-16+GP-1; zero outside the image
-    if( tid < 3 ) s_nwork[ tid ] = 0; // [0] geometric work items, [1] smoothed cells, [2] PACK: some cell of the tile is wide
+    if( tid < 3 ) s_nwork[ tid ] = 0; // [0] geometric work items, [1] smoothed cells (statistics), [2] some cell of the tile is wide
     if( kUseTma )
     {
         if( tid == 0 )
@@ -808,51 +806,27 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     const uint32_t force_wide = a.debug_force_wide ? C::WIDE : 0u;
     const bool use_tables = a.smooth.cut != nullptr && !a.debug_force_wide;
 
-    // (2a) cells whose polygon is their plain hull copy the mask from the table; smoothed cells are compacted
-    // into a list so that the next pass runs with full warps
-    uint16_t* s_gen = reinterpret_cast< uint16_t* >( smem + C::off_gen ); // (the staged rows are dead, the vertex buffers not in use yet)
+    // (2a) Every cell of tile + halo 1 gets its mask, in tile order: a warp's cells are neighbours, so the key, colour
+    // and mask accesses are conflict-free and nothing is queued.  Cells whose polygon is their plain hull copy the mask
+    // from the per-scale table; smoothed cells assemble it from the smoothing tables (one CUT entry + one LINK entry per
+    // shared edge with a blended end); the rare cell the tables cannot express is queued for the geometric path.
+    // (Compacting the smoothed cells into a list first, so that the lookups run with full warps, was 3 % slower on the
+    // busy frames of the bench — 83 % of the cells are smoothed — and 9 % faster on frames of flat 4 x 4 blocks.)
+    int n_smoothed = 0;
     for( int idx = tid; idx < C::NC; idx += kThreads )
     {
         int cy = idx / C::CW, cx = idx - cy * C::CW;
         int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
         const bool inside = gx >= 0 && gy >= 0 && gx < a.width && gy < a.height;
-        const uint32_t key = s_keys[ ( cy + 1 ) * C::KW + cx + 1 ];
+        const uint16_t* kc = s_keys + ( cy + 1 ) * C::KW + cx + 1;
+        const uint32_t key = *kc;
         const bool plain = !subdivide || ( key & 0xFFu ) == 90u;
         if( inside && !plain )
         {
-            s_gen[ warp_slot( s_nwork + 1 ) ] = ( uint16_t )idx;
-        }
-        else if( C::PACK )
-        {
-            uint2 m = make_uint2( 0u, 0u );
-            if( inside )
-            {
-                m = __ldg( reinterpret_cast< const uint2* >( a.mask_lut ) + key );
-                m.y |= force_wide;
-            }
-            s_mask[ idx ] = m.x; // (PACK: the two halves live in separate arrays, conflict-free 32-bit accesses)
-            s_mask[ C::NC + idx ] = m.y;
-        }
-        else
-        {
-#pragma unroll
-            for( int r = 0; r < C::R; r++ )
-                s_mask[ r * C::NC + idx ] = inside ? ( __ldg( a.mask_lut + key * C::R + r ) | ( r == 0 ? force_wide : 0u ) ) : 0u;
-        }
-    }
-    __syncthreads();
-    // smoothed cells: the mask is assembled from the smoothing tables (one CUT entry + one LINK entry per shared
-    // edge with a blended end); the rare cell the tables cannot express is queued for the geometric path
-    {
-        const int n_gen = s_nwork[ 1 ];
-        for( int w = tid; w < n_gen; w += kThreads )
-        {
-            const int idx = s_gen[ w ];
-            int cy = idx / C::CW, cx = idx - cy * C::CW;
-            const uint16_t* kc = s_keys + ( cy + 1 ) * C::KW + cx + 1;
+            n_smoothed++;
             // checkTJunction for the four corners of the pixel square (bit c: corner c stays), 16 = its early exit
             uint32_t cf = 16u;
-            if( !env.guard( x0 - 1 + cx, y0 - 1 + cy ) )
+            if( !env.guard( gx, gy ) )
             {
                 const uint32_t* c = s_col + ( cy + 1 ) * C::KW + ( cx + 1 );
                 const uint32_t l = c[ -1 ], r = c[ 1 ], d = c[ -C::KW ], u = c[ C::KW ];
@@ -862,7 +836,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
             }
             uint64_t mw[ Entry< S >::EW ];
             bool wide = false;
-            if( use_tables && smooth_lookup< S >( a.smooth, a.mask_lut, kc, *kc, cf, mw, wide ) )
+            if( use_tables && smooth_lookup< S >( a.smooth, a.mask_lut, kc, key, cf, mw, wide ) )
             {
                 if( C::PACK )
                 {
@@ -884,6 +858,28 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
             else
                 s_work[ warp_slot( s_nwork ) ] = ( uint16_t )idx;
         }
+        else if( C::PACK )
+        {
+            uint2 m = make_uint2( 0u, 0u );
+            if( inside )
+            {
+                m = __ldg( reinterpret_cast< const uint2* >( a.mask_lut ) + key );
+                m.y |= force_wide;
+            }
+            s_mask[ idx ] = m.x; // (PACK: the two halves live in separate arrays, conflict-free 32-bit accesses)
+            s_mask[ C::NC + idx ] = m.y;
+        }
+        else
+        {
+#pragma unroll
+            for( int r = 0; r < C::R; r++ )
+                s_mask[ r * C::NC + idx ] = inside ? ( __ldg( a.mask_lut + key * C::R + r ) | ( r == 0 ? force_wide : 0u ) ) : 0u;
+        }
+    }
+    if( a.smooth_stats ) // (statistics for the bench line)
+    {
+        n_smoothed = __reduce_add_sync( 0xFFFFFFFFu, n_smoothed );
+        if( ( tid & 31 ) == 0 ) atomicAdd( s_nwork + 1, n_smoothed );
     }
     __syncthreads();
 
@@ -923,7 +919,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
             }
         }
     }
-    __syncthreads();
+    if( *s_nwork != 0 ) __syncthreads(); // (uniform: the counter is final since the barrier before this pass)
     if( a.smooth_stats && tid == 0 )
     {
         atomicAdd( a.smooth_stats, ( unsigned long long )s_nwork[ 1 ] );     // smoothed cells

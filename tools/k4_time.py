@@ -11,6 +11,8 @@ F = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 4
 W, H = 256, 224
 base = synth.snes_stream(64, W, H)
+if os.environ.get("K4_SPARSE"):  # flat 4x4 blocks: few smoothed cells per warp (the compacted pass of the raster kernel)
+    base = np.ascontiguousarray(np.repeat(np.repeat(base[:, ::4, ::4], 4, 1), 4, 2))
 frames = torch.from_numpy(np.concatenate([base] * (F // 64), 0)).cuda()
 ctx = par.Remaster(0, W, H, F)
 g = ctx.resolve_crossings(ctx.similarity_graph(frames))

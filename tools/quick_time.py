@@ -3,6 +3,8 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import pixel_art_remaster_gpu_b200 as par
+if os.environ.get("PAR_LIB"):  # A/B runs: another build of the library
+    par.library_path = lambda: os.environ["PAR_LIB"]
 from pixel_art_remaster_gpu_b200 import synth
 
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 256
