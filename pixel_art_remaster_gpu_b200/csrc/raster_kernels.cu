@@ -32,6 +32,7 @@
 #include "kernels.cuh"
 #include "polygon.cuh"
 
+
 namespace par {
 
 namespace {
@@ -395,6 +396,60 @@ __device__ __noinline__ void resolve_tile_exact( const uint16_t* keys, const uin
             }
         const ptrdiff_t row_step = flip ? -( ptrdiff_t )( out_w * 4 ) : ( ptrdiff_t )( out_w * 4 );
         store_cell< S, A >( out + ( ( flip ? out_h - 1 - ( size_t )gy * O : ( size_t )gy * O ) * out_w + ( size_t )gx * O ) * 4, row_step, px );
+    }
+}
+
+// General path of the mask pass: one thread per queued cell; polygon -> per-thread vertex buffer -> edge loop.  Only runs
+// for the few cells the smoothing tables cannot express (or all smoothed cells under PAR_FLAG_NO_SMOOTH_TABLES).
+template< int S >
+__device__ __noinline__ void geometric_cells( const uint16_t* keys, const uint32_t* cols, uint32_t* s_mask, const uint16_t* s_work, uint16_t* s_vbuf, int* s_nwork,
+                                              int x0, int y0, const uint8_t* frame, int width, int height, int widthstep, const CellRecord* rec,
+                                              uint32_t force_wide )
+{
+    typedef Cfg< S > C;
+    TileEnv< S > env;
+    env.keys = keys;
+    env.cols = cols;
+    env.x0 = x0;
+    env.y0 = y0;
+    env.img.frame = frame;
+    env.img.width = width;
+    env.img.height = height;
+    env.img.widthstep = widthstep;
+    const CellTablePtrs tab{ rec };
+    const int tid = threadIdx.x;
+    const int n_work = *s_nwork;
+    uint16_t* vbuf = s_vbuf + tid;
+    for( int w = tid; w < n_work && tid < kGeoThreads; w += kGeoThreads )
+    {
+        const int idx = s_work[ w ];
+        int cy = idx / C::CW, cx = idx - cy * C::CW;
+        int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
+        PackedSlots slots{ vbuf, kGeoThreads };
+        const CellPoly poly = build_cell_polygon( env, tab, gx, gy, keys[ ( cy + 1 ) * C::KW + cx + 1 ], true, slots );
+        int lo, hi;
+        if constexpr( C::PACK )
+        {
+            PackedToggle< C::R > tg{ 0ull };
+            cover_polygon< S, C::R >( vbuf, kGeoThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
+            // reach check: every sample outside the mask must be strictly outside the polygon's bounding box
+            const uint32_t wide = ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
+            uint2 wm = to_window< S >( tg.m );
+            wm.y |= wide;
+            s_mask[ idx ] = wm.x;
+            s_mask[ C::NC + idx ] = wm.y;
+            if( wide ) s_nwork[ 2 ] = 1;
+        }
+        else
+        {
+#pragma unroll
+            for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] = 0u;
+            RowToggle tg{ s_mask + idx, C::NC };
+            cover_polygon< S, C::R >( vbuf, kGeoThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
+            const uint32_t wide = ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
+            s_mask[ idx ] |= wide;
+            if( wide ) s_nwork[ 2 ] = 1;
+        }
     }
 }
 
@@ -883,43 +938,12 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     }
     __syncthreads();
 
-    // (2b) general path: one thread per queued cell; polygon -> per-thread vertex buffer -> edge loop
+    // (2b) general path, out of line (rarely runs: it costs the common path neither registers nor code)
+    if( *s_nwork != 0 )
     {
-        const int n_work = *s_nwork;
-        uint16_t* vbuf = s_vbuf + tid;
-        for( int w = tid; w < n_work && tid < kGeoThreads; w += kGeoThreads )
-        {
-            const int idx = s_work[ w ];
-            int cy = idx / C::CW, cx = idx - cy * C::CW;
-            int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
-            PackedSlots slots{ vbuf, kGeoThreads };
-            const CellPoly poly = build_cell_polygon( env, tab, gx, gy, s_keys[ ( cy + 1 ) * C::KW + cx + 1 ], true, slots );
-            int lo, hi;
-            if constexpr( C::PACK )
-            {
-                PackedToggle< C::R > tg{ 0ull };
-                cover_polygon< S, C::R >( vbuf, kGeoThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
-                // reach check: every sample outside the mask must be strictly outside the polygon's bounding box
-                const uint32_t wide = ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
-                uint2 wm = to_window< S >( tg.m );
-                wm.y |= wide;
-                s_mask[ idx ] = wm.x;
-                s_mask[ C::NC + idx ] = wm.y;
-                if( wide ) s_nwork[ 2 ] = 1;
-            }
-            else
-            {
-#pragma unroll
-                for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] = 0u;
-                RowToggle tg{ s_mask + idx, C::NC };
-                cover_polygon< S, C::R >( vbuf, kGeoThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
-                const uint32_t wide = ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
-                s_mask[ idx ] |= wide;
-                if( wide ) s_nwork[ 2 ] = 1;
-            }
-        }
+        geometric_cells< S >( s_keys, s_col, s_mask, s_work, s_vbuf, s_nwork, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, force_wide );
+        __syncthreads(); // (uniform: the counter is final since the barrier before this pass)
     }
-    if( *s_nwork != 0 ) __syncthreads(); // (uniform: the counter is final since the barrier before this pass)
     if( a.smooth_stats && tid == 0 )
     {
         atomicAdd( a.smooth_stats, ( unsigned long long )s_nwork[ 1 ] );     // smoothed cells

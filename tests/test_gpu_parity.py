@@ -48,6 +48,26 @@ def test_graph_stages_bit_exact(ctx, oracle, name, img, no_tma):
     assert np.array_equal(g[0].cpu().numpy(), want["graph"]), "stage C differs"
 
 
+@pytest.mark.parametrize("w,h", [(1, 1), (2, 3), (4, 4), (7, 5), (63, 31), (64, 32), (65, 33), (128, 64), (129, 35), (200, 70)])
+@pytest.mark.parametrize("no_tma", [False, True], ids=["tma", "plain"])
+def test_graph_black_and_dark_pixels_on_the_border(ctx, oracle, w, h, no_tma):
+    """The graph kernel stages pixels outside the image as zeros (black) and clears the links that leave the image when
+    the bytes are assembled: black and near-black pixels (similar to black: Y <= 5, U <= 7, V <= 6) on the image border,
+    in the corners and at tile edges must not link outwards, and blocks across the border must not lose diagonals."""
+    rng = np.random.default_rng(1000 * w + h)
+    palette = np.array([[0, 0, 0], [1, 2, 1], [4, 4, 4], [3, 0, 5], [200, 30, 90], [0, 0, 0], [2, 2, 2], [250, 250, 250]], np.uint8)
+    for k in range(3):
+        img = palette[rng.integers(0, len(palette) if k else 4, (h, w))]
+        if k == 2:
+            img[:] = 0  # an all-black frame: every in-image link set, none outwards
+        img = np.ascontiguousarray(img)
+        want = oracle.pipeline(img, want=("graph_aux", "graph"))
+        aux = ctx.similarity_graph(_dev(ctx, img[None]), no_tma=no_tma)
+        g = ctx.resolve_crossings(aux, no_tma=no_tma)
+        assert np.array_equal(aux[0].cpu().numpy(), want["graph_aux"]), "stage A+B differs"
+        assert np.array_equal(g[0].cpu().numpy(), want["graph"]), "stage C differs"
+
+
 @pytest.mark.parametrize("name,img", _cases(), ids=[c[0] for c in _cases()])
 def test_cc_labels_bit_exact(ctx, oracle, name, img):
     want = oracle.pipeline(img, want=("graph", "labels"))

@@ -50,6 +50,23 @@ def test_every_stage_equals_reference(oracle, ref_host, name, make, subdivide):
     assert np.array_equal(got["tri"][m], ref["tri"][m])                # stage F
 
 
+@pytest.mark.parametrize("w,h", [(4, 4), (7, 5), (65, 33), (129, 35)])
+def test_dark_pixels_on_the_border_equal_reference(oracle, ref_host, w, h):
+    """Black and near-black pixels on the image border (what the graph kernel's zero-filled staging must not link to):
+    the oracle's graph equals the reference's own routines there too."""
+    rng = np.random.default_rng(1000 * w + h)
+    palette = np.array([[0, 0, 0], [1, 2, 1], [4, 4, 4], [3, 0, 5], [200, 30, 90], [0, 0, 0], [2, 2, 2], [250, 250, 250]], np.uint8)
+    for k in range(3):
+        img = palette[rng.integers(0, len(palette) if k else 4, (h, w))]
+        if k == 2:
+            img[:] = 0
+        img = np.ascontiguousarray(img)
+        ref = ref_host.pipeline(img, False, ("graph_aux", "graph"))
+        got = oracle.pipeline(img, False, True, 4, ("graph_aux", "graph"))
+        assert np.array_equal(got["graph_aux"], ref["graph_aux"])
+        assert np.array_equal(got["graph"], ref["graph"])
+
+
 def test_plain_host_arithmetic_variant(oracle, ref_host_plain):
     """The unfused-Y variant of the oracle equals the reference built with -ffp-contract=off."""
     img = synth.snes_frame(96, 80, 123)
