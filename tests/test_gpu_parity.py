@@ -231,6 +231,29 @@ def test_smoothing_tables_equal_the_geometric_path(lib, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("scale", [4, 8])
+def test_large_batch_of_small_frames(lib, oracle, scale):
+    """A large batch (grid.z = 2047 frames, cycling through 16 distinct ones): every frame equals the oracle's image of
+    its source frame — with the smoothing tables, on the geometric path, on the exact tile resolve and without TMA."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    W, H, n, distinct = 96, 80, 2047, 16
+    base = synth.snes_stream(distinct, W, H, first_seed=synth.BASE_SEED + 900)
+    want = torch.from_numpy(np.stack([oracle.pipeline(b, scale=scale, want=("raster",))["raster"] for b in base])).cuda()
+    frames = torch.from_numpy(np.concatenate([base] * (n // distinct + 1))[:n]).cuda()
+    index = torch.arange(n, device="cuda") % distinct
+    with lib.Remaster(0, W, H, n) as c:
+        g = c.resolve_crossings(c.similarity_graph(frames))
+        for mode in ("tables", "geometric", "exact", "plain_loads"):
+            c.no_tables = mode == "geometric"
+            rgba = c.raster(frames, g, scale, True, debug_wide=mode == "exact", no_tma=mode == "plain_loads")
+            bad = (rgba != want[index]).flatten(1).any(1)
+            assert not bool(bad.any()), (mode, scale, bad.nonzero().flatten()[:8].tolist())
+            del rgba
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("scale,aa", [(4, 2), (2, 2), (2, 4), (1, 4), (1, 2), (3, 2)])
 def test_antialiased_output_is_the_mean_of_the_supersampled_image(lib, oracle, scale, aa):
     """PAR_FLAG_AA2 / AA4: every output pixel is the per-channel mean (halves up) of aa x aa ordered-grid samples, i.e. of
