@@ -28,35 +28,44 @@ constexpr int kThrV = 0x00000006;
 // far from any integer, so trunc() equals T/1000 in integer arithmetic.  Only exact multiples
 // (e.g. every grey) need the real FMA chain, whose rounding decides between y and y-1.
 // U and V are float products truncated toward zero (graph_functions.cu:93-94).
-// (T = 299*b0 + 587*b1 + 114*b2 is passed in: the graph kernel forms it with two dot-product instructions)
-__host__ __device__ __forceinline__ uint32_t yuv_word_t( int T, int b0, int b1, int b2 )
+// The pieces (the graph kernel calls them one by one so that the rare case costs its four pixels ONE branch; T is passed
+// in because the kernel forms it with two dot-product instructions):
+//   T * M with M = ceil(2^32 / 1000) = 4294968:  high word = T / 1000 exactly for T <= 255000 (M * 1000 - 2^32 = 704 and
+//   704 T < 2^32); low word = 704 (T / 1000) + (T mod 1000) M without wrapping (999 M + 704 * 255 < 2^32), i.e. below M
+//   exactly when T is a multiple of 1000.
+constexpr uint32_t kDiv1000 = 4294968u;
+__host__ __device__ __forceinline__ int luma_div( int T )
 {
 #ifdef __CUDA_ARCH__
-    int y = ( int )__umulhi( ( unsigned )T, 4294968u ); // = T / 1000 exactly for T <= 255000 (4294968 * 1000 - 2^32 = 704, 704 T < 2^32)
+    return ( int )__umulhi( ( unsigned )T, kDiv1000 );
 #else
-    int y = T / 1000;
+    return ( int )( ( ( unsigned long long )( unsigned )T * kDiv1000 ) >> 32 );
 #endif
-    if( T - y * 1000 == 0 && T != 0 ) // (black stays 0: the chain of three zeros is exact)
+}
+// T is a non-zero multiple of 1000: rounding decides (black stays 0: the chain of three zeros is exact)
+__host__ __device__ __forceinline__ bool luma_needs_chain( int T ) { return ( uint32_t )T * kDiv1000 - 1u < kDiv1000 - 1u; }
+// y for such a colour, given y = T / 1000
+__host__ __device__ __forceinline__ int luma_chain( int y, int b0, int b1, int b2 )
+{
+    if( b0 == b1 && b1 == b2 )
     {
-        if( b0 == b1 && b1 == b2 )
-        {
-            // greys: T = 1000 v exactly, and for 75 of the 256 values the rounded chain lands just below v (SURVEY
-            // App. B-1).  Bit v of this 256-bit table says so; it is checked against the chain for every grey
-            // (tests/test_golden.py) and, like every colour, against the reference's device code on the GPU.
-            const int word = b0 >> 5;
-            const uint32_t w = word == 0 ? 0x8c212116u : word == 1 ? 0xea528481u : word == 2 ? 0xc8324001u : word == 3 ? 0xd4449104u :
-                               word == 4 ? 0x18200881u : word == 5 ? 0x50c08704u : word == 6 ? 0xc1030a18u : 0x53129890u;
-            y -= ( int )( ( w >> ( b0 & 31 ) ) & 1u );
-        }
-        else
-        {
-#ifdef __CUDA_ARCH__
-            y = __double2int_rz( __fma_rn( 0.114, ( double )b2, __fma_rn( 0.299, ( double )b0, __dmul_rn( 0.587, ( double )b1 ) ) ) );
-#else
-            y = ( int )__builtin_fma( 0.114, ( double )b2, __builtin_fma( 0.299, ( double )b0, 0.587 * ( double )b1 ) );
-#endif
-        }
+        // greys: T = 1000 v exactly, and for 75 of the 256 values the rounded chain lands just below v (SURVEY
+        // App. B-1).  Bit v of this 256-bit table says so; it is checked against the chain for every grey
+        // (tests/test_golden.py) and, like every colour, against the reference's device code on the GPU.
+        const int word = b0 >> 5;
+        const uint32_t w = word == 0 ? 0x8c212116u : word == 1 ? 0xea528481u : word == 2 ? 0xc8324001u : word == 3 ? 0xd4449104u :
+                           word == 4 ? 0x18200881u : word == 5 ? 0x50c08704u : word == 6 ? 0xc1030a18u : 0x53129890u;
+        return y - ( int )( ( w >> ( b0 & 31 ) ) & 1u );
     }
+#ifdef __CUDA_ARCH__
+    return __double2int_rz( __fma_rn( 0.114, ( double )b2, __fma_rn( 0.299, ( double )b0, __dmul_rn( 0.587, ( double )b1 ) ) ) );
+#else
+    return ( int )__builtin_fma( 0.114, ( double )b2, __builtin_fma( 0.299, ( double )b0, 0.587 * ( double )b1 ) );
+#endif
+}
+// U and V from y, the packed word (graph_functions.cu:93-97)
+__host__ __device__ __forceinline__ uint32_t yuv_pack( int y, int b0, int b2 )
+{
 #ifdef __CUDA_ARCH__
     int u = __float2int_rz( __fmul_rn( ( float )( b2 - y ), 0.492f ) );
     int v = __float2int_rz( __fmul_rn( ( float )( b0 - y ), 0.877f ) );
@@ -65,6 +74,12 @@ __host__ __device__ __forceinline__ uint32_t yuv_word_t( int T, int b0, int b1, 
     int v = ( int )( ( float )( b0 - y ) * 0.877f );
 #endif
     return ( uint32_t )( y << 16 ) + ( uint32_t )( u * 256 ) + ( uint32_t )v;
+}
+__host__ __device__ __forceinline__ uint32_t yuv_word_t( int T, int b0, int b1, int b2 )
+{
+    int y = luma_div( T );
+    if( luma_needs_chain( T ) ) y = luma_chain( y, b0, b1, b2 );
+    return yuv_pack( y, b0, b2 );
 }
 __host__ __device__ __forceinline__ uint32_t yuv_word( int b0, int b1, int b2 ) { return yuv_word_t( 299 * b0 + 587 * b1 + 114 * b2, b0, b1, b2 ); }
 

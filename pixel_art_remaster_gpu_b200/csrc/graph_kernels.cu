@@ -115,10 +115,19 @@ __global__ void __launch_bounds__( kThreads ) similarity_graph_kernel( const __g
         const uint32_t t1 = __dp2a_lo( k587_114, w1, __dp2a_hi( k0_299, w0, 0u ) );   // byte 3 of w0, bytes 0 1 of w1
         const uint32_t t2 = __dp2a_lo( k114_0, w2, __dp2a_hi( k299_587, w1, 0u ) );   // bytes 2 3 of w1, byte 0 of w2
         const uint32_t t3 = __dp2a_hi( k587_114, w2, __dp2a_lo( k0_299, w2, 0u ) );   // bytes 1 2 3 of w2
-        const uint32_t y0w = yuv_word_t( ( int )t0, w0 & 255u, ( w0 >> 8 ) & 255u, ( w0 >> 16 ) & 255u );
-        const uint32_t y1w = yuv_word_t( ( int )t1, w0 >> 24, w1 & 255u, ( w1 >> 8 ) & 255u );
-        const uint32_t y2w = yuv_word_t( ( int )t2, ( w1 >> 16 ) & 255u, w1 >> 24, w2 & 255u );
-        const uint32_t y3w = yuv_word_t( ( int )t3, ( w2 >> 8 ) & 255u, ( w2 >> 16 ) & 255u, w2 >> 24 );
+        // y = T / 1000; the colours whose rounding needs the reference's FP64 chain (non-zero multiples of 1000: rare)
+        // are fixed up behind one branch for the four pixels
+        int l0 = luma_div( ( int )t0 ), l1 = luma_div( ( int )t1 ), l2 = luma_div( ( int )t2 ), l3 = luma_div( ( int )t3 );
+        const bool c0 = luma_needs_chain( ( int )t0 ), c1 = luma_needs_chain( ( int )t1 ), c2 = luma_needs_chain( ( int )t2 ), c3 = luma_needs_chain( ( int )t3 );
+        if( c0 || c1 || c2 || c3 )
+        {
+            if( c0 ) l0 = luma_chain( l0, w0 & 255u, ( w0 >> 8 ) & 255u, ( w0 >> 16 ) & 255u );
+            if( c1 ) l1 = luma_chain( l1, w0 >> 24, w1 & 255u, ( w1 >> 8 ) & 255u );
+            if( c2 ) l2 = luma_chain( l2, ( w1 >> 16 ) & 255u, w1 >> 24, w2 & 255u );
+            if( c3 ) l3 = luma_chain( l3, ( w2 >> 8 ) & 255u, ( w2 >> 16 ) & 255u, w2 >> 24 );
+        }
+        const uint32_t y0w = yuv_pack( l0, w0 & 255u, ( w0 >> 16 ) & 255u ), y1w = yuv_pack( l1, w0 >> 24, ( w1 >> 8 ) & 255u );
+        const uint32_t y2w = yuv_pack( l2, ( w1 >> 16 ) & 255u, w2 & 255u ), y3w = yuv_pack( l3, ( w2 >> 8 ) & 255u, w2 >> 24 );
         // 4 x 3 byte transpose: word k = (V, U, Y, -) of pixel k  ->  (V0 V1 V2 V3), (U0 ..), (Y0 ..)
         const uint32_t vu01 = __byte_perm( y0w, y1w, 0x5140 ), vu23 = __byte_perm( y2w, y3w, 0x5140 ); // V0 V1 U0 U1
         const uint32_t yy01 = __byte_perm( y0w, y1w, 0x7362 ), yy23 = __byte_perm( y2w, y3w, 0x7362 ); // Y0 Y1 .  .
