@@ -651,11 +651,57 @@ __global__ void build_link_table_kernel( const LinkClass* classes, uint64_t* lin
     cover_to_entry< S >( xs, ys, m, entry );
 }
 
-// Mask of a smoothed cell from the tables: false when a blended vertex is not a vertex of the neighbour's
-// hull (the reference's getPointIndex fallback) — the caller then takes the geometric path.
+// NS link descriptors of a smoothed cell, without branches (the loads of the slots overlap; an unused slot (0)
+// compares nothing and loads nothing): XORs their LINK entries into m, ORs word 0 of the entries into `flags`, returns
+// the mismatch bits (non-zero: a blended vertex is not the end / start of the neighbour's edge).
+template< int S, int NS >
+__device__ __forceinline__ uint32_t link_slots( const SmoothTablePtrs& st, const uint16_t* keys_at_cell, const uint32_t* links, uint64_t* m, uint64_t& flags )
+{
+    typedef Cfg< S > C;
+    typedef Entry< S > E;
+    uint32_t nb[ NS ];
+#pragma unroll
+    for( int k = 0; k < NS; k++ )
+    {
+        const uint32_t d = links[ k ];
+        const uint32_t e = d & 7u;
+        // neighbour across graph edge e: offset in the key tile, one signed byte per edge
+        constexpr int KW = C::KW;
+        constexpr uint32_t off_lo = ( uint32_t )( uint8_t )( KW - 1 ) | ( uint32_t )( uint8_t )( KW ) << 8 | ( uint32_t )( uint8_t )( KW + 1 ) << 16 |
+                                    ( uint32_t )( uint8_t )( -1 ) << 24;
+        constexpr uint32_t off_hi = ( uint32_t )( uint8_t )( 1 ) | ( uint32_t )( uint8_t )( -KW - 1 ) << 8 | ( uint32_t )( uint8_t )( -KW ) << 16 |
+                                    ( uint32_t )( uint8_t )( -KW + 1 ) << 24;
+        const int koff = ( int )( int8_t )__byte_perm( off_lo, off_hi, e );
+        const uint32_t nkey = keys_at_cell[ koff ];
+        nb[ k ] = ( d >> 16 ) ? ( uint32_t )__ldg( &st.rec[ nkey ].nbr[ e ^ 7u ] ) : 0u; // (an unused slot loads nothing)
+    }
+    uint32_t mismatch = 0u;
+#pragma unroll
+    for( int k = 0; k < NS; k++ )
+    {
+        const uint32_t d = links[ k ], r = nb[ k ];
+        const uint32_t ends = ( d >> 16 ) & 255u;
+        mismatch |= ( ( r ^ d ) >> 8 ) & ends; // the blended vertices must be the end (A) / start (B) of the neighbour's edge
+        const uint32_t sub = r & ends; // rank a | rank b << 4 -> the class's 4 x 4 block (one 128-byte line at s <= 4)
+        const uint64_t* le = st.link + ( size_t )( ( d >> 24 ) * 16u + ( ( sub & 3u ) | ( ( sub >> 2 ) & 12u ) ) ) * E::EW;
+#pragma unroll
+        for( int w = 0; w < E::EW; w++ )
+        {
+            const uint64_t v = ( d >> 16 ) ? __ldg( le + w ) : 0ull;
+            if( w == 0 ) flags |= v;
+            m[ w ] ^= v;
+        }
+    }
+    return mismatch;
+}
+
+// Mask of a smoothed cell from the tables, FIRST pass: the CUT entry and the first two link descriptors (nine cells in
+// ten have no more).  `more` is set when the key has a third descriptor: the caller queues the cell for
+// smooth_lookup_more.  Returns false when a blended vertex is not a vertex of the neighbour's hull (the reference's
+// getPointIndex fallback) — the caller then takes the geometric path.
 template< int S >
 __device__ __forceinline__ bool smooth_lookup( const SmoothTablePtrs& st, const uint32_t* mask_lut, const uint16_t* keys_at_cell, uint32_t key, uint32_t cflags,
-                                               uint64_t* m, bool& wide )
+                                               uint64_t* m, bool& wide, bool& more )
 {
     typedef Cfg< S > C;
     typedef Entry< S > E;
@@ -682,45 +728,28 @@ __device__ __forceinline__ bool smooth_lookup( const SmoothTablePtrs& st, const 
 #pragma unroll
         for( int w = 0; w < E::EW; w++ ) m[ w ] = __ldg( e + w );
     }
-    // All four descriptor slots are processed without branches (a warp runs as long as its busiest lane anyway, and
-    // the loads of the four slots overlap); an unused slot (0) compares nothing and XORs the all-zero entry 0.
     bool ok = rec.x != kSmoothSlow;
-    const uint32_t links[ 4 ] = { ok ? rec.x : 0u, rec.y, rec.z, rec.w };
-    uint32_t nb[ kMaxLinks ];
-#pragma unroll
-    for( int k = 0; k < kMaxLinks; k++ )
-    {
-        const uint32_t d = links[ k ];
-        const uint32_t e = d & 7u;
-        // neighbour across graph edge e: offset in the key tile, one signed byte per edge
-        constexpr int KW = C::KW;
-        constexpr uint32_t off_lo = ( uint32_t )( uint8_t )( KW - 1 ) | ( uint32_t )( uint8_t )( KW ) << 8 | ( uint32_t )( uint8_t )( KW + 1 ) << 16 |
-                                    ( uint32_t )( uint8_t )( -1 ) << 24;
-        constexpr uint32_t off_hi = ( uint32_t )( uint8_t )( 1 ) | ( uint32_t )( uint8_t )( -KW - 1 ) << 8 | ( uint32_t )( uint8_t )( -KW ) << 16 |
-                                    ( uint32_t )( uint8_t )( -KW + 1 ) << 24;
-        const int koff = ( int )( int8_t )__byte_perm( off_lo, off_hi, e );
-        const uint32_t nkey = keys_at_cell[ koff ];
-        nb[ k ] = ( d >> 16 ) ? ( uint32_t )__ldg( &st.rec[ nkey ].nbr[ e ^ 7u ] ) : 0u; // (an unused slot loads nothing)
-    }
-    uint32_t mismatch = 0u;
-#pragma unroll
-    for( int k = 0; k < kMaxLinks; k++ )
-    {
-        const uint32_t d = links[ k ], r = nb[ k ];
-        const uint32_t ends = ( d >> 16 ) & 255u;
-        mismatch |= ( ( r ^ d ) >> 8 ) & ends; // the blended vertices must be the end (A) / start (B) of the neighbour's edge
-        const uint32_t sub = r & ends; // rank a | rank b << 4 -> the class's 4 x 4 block (one 128-byte line at s <= 4)
-        const uint64_t* le = st.link + ( size_t )( ( d >> 24 ) * 16u + ( ( sub & 3u ) | ( ( sub >> 2 ) & 12u ) ) ) * E::EW;
-#pragma unroll
-        for( int w = 0; w < E::EW; w++ )
-        {
-            const uint64_t v = ( d >> 16 ) ? __ldg( le + w ) : 0ull;
-            if( w == 0 ) flags |= v;
-            m[ w ] ^= v;
-        }
-    }
-    ok = ok && mismatch == 0u;
+    const uint32_t links[ 2 ] = { ok ? rec.x : 0u, rec.y };
+    more = ( rec.z >> 16 ) != 0u; // (descriptors fill the slots from 0)
+    ok = ok && link_slots< S, 2 >( st, keys_at_cell, links, m, flags ) == 0u;
     // the flag bit of word 0 was XORed along with the masks: restore it from the CUT entry (never wide) and the OR
+    wide = ( flags & E::FLAG ) != 0ull;
+    m[ 0 ] &= ~E::FLAG;
+    return ok;
+}
+
+// SECOND pass, for the cells whose key has three or four link descriptors: the XOR of the remaining LINK entries (flag
+// bit cleared), `wide` from their flags; false on a mismatch as above.
+template< int S >
+__device__ __forceinline__ bool smooth_lookup_more( const SmoothTablePtrs& st, const uint16_t* keys_at_cell, uint32_t key, uint64_t* m, bool& wide )
+{
+    typedef Entry< S > E;
+    const uint2 rec = __ldg( reinterpret_cast< const uint2* >( &st.rec[ key ].link[ 2 ] ) );
+    const uint32_t links[ 2 ] = { rec.x, rec.y };
+    uint64_t flags = 0ull;
+#pragma unroll
+    for( int w = 0; w < E::EW; w++ ) m[ w ] = 0ull;
+    const bool ok = link_slots< S, 2 >( st, keys_at_cell, links, m, flags ) == 0u;
     wide = ( flags & E::FLAG ) != 0ull;
     m[ 0 ] &= ~E::FLAG;
     return ok;
@@ -748,7 +777,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     const uint8_t* graph = a.graph + ( size_t )f * frame_px;
 
     // (1) stage graph bytes: rows y0-2 .. y0+TH+1, columns x0-16 .. x0-16+GP-1; zero outside the image
-    if( tid < 3 ) s_nwork[ tid ] = 0; // [0] geometric work items, [1] smoothed cells (statistics), [2] some cell of the tile is wide
+    if( tid < 4 ) s_nwork[ tid ] = 0; // [0] geometric work items, [1] smoothed cells (statistics), [2] some cell of the tile is wide, [3] cells with a third link
     if( kUseTma )
     {
         if( tid == 0 )
@@ -890,9 +919,10 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
                      ( ( l != ul || ul != u ) ? 8u : 0u );
             }
             uint64_t mw[ Entry< S >::EW ];
-            bool wide = false;
-            if( use_tables && smooth_lookup< S >( a.smooth, a.mask_lut, kc, key, cf, mw, wide ) )
+            bool wide = false, more = false;
+            if( use_tables && smooth_lookup< S >( a.smooth, a.mask_lut, kc, key, cf, mw, wide, more ) )
             {
+                if( more ) s_work[ C::NC - 1 - warp_slot( s_nwork + 3 ) ] = ( uint16_t )idx; // (second list, from the top of the array)
                 if( C::PACK )
                 {
                     s_mask[ idx ] = ( uint32_t )mw[ 0 ];
@@ -937,6 +967,39 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
         if( ( tid & 31 ) == 0 ) atomicAdd( s_nwork + 1, n_smoothed );
     }
     __syncthreads();
+
+    // (2a') cells with three or four link descriptors (one in ten): the remaining LINK entries are XORed in, with full
+    // warps over the queued cells.  (All four slots in the first pass would cost every warp of it the instructions of
+    // the two slots that nine cells in ten do not use.)  The two lists share one array — the geometric path's grows from
+    // the bottom, this one from the top, a cell is in one of them — so a mismatch found here cannot be queued for the
+    // geometric path any more: the tile then takes the exact resolve, which does not look at the masks.
+    if( s_nwork[ 3 ] != 0 ) // (uniform)
+    {
+        const int n_more = s_nwork[ 3 ];
+        for( int w = tid; w < n_more; w += kThreads )
+        {
+            const int idx = s_work[ C::NC - 1 - w ];
+            const int cy = idx / C::CW, cx = idx - cy * C::CW;
+            const uint16_t* kc = s_keys + ( cy + 1 ) * C::KW + cx + 1;
+            uint64_t mw[ Entry< S >::EW ];
+            bool wide = false;
+            const bool ok = smooth_lookup_more< S >( a.smooth, kc, *kc, mw, wide );
+            if( C::PACK )
+            {
+                s_mask[ idx ] ^= ( uint32_t )mw[ 0 ];
+                s_mask[ C::NC + idx ] ^= ( uint32_t )( mw[ 0 ] >> 32 );
+                if( wide ) s_mask[ C::NC + idx ] |= C::WIDE;
+            }
+            else
+            {
+#pragma unroll
+                for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] ^= ( uint32_t )( mw[ r >> 2 ] >> ( 16 * ( r & 3 ) ) ) & 0x7FFFu;
+                if( wide ) s_mask[ idx ] |= C::WIDE;
+            }
+            if( wide || !ok ) s_nwork[ 2 ] = 1;
+        }
+        __syncthreads();
+    }
 
     // (2b) general path, out of line (rarely runs: it costs the common path neither registers nor code)
     if( *s_nwork != 0 )
