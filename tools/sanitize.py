@@ -16,6 +16,14 @@ for (W, H, S) in ((96, 80, 4), (50, 37, 8), (65, 33, 3)):
             ctx.no_tables = False
             out = ctx.remaster(frames, S, False, want=("rgba",), no_tma=no_tma)  # hull cells only
         torch.cuda.synchronize()
+# 3-colour noise: every key, cells with three and four link descriptors (second table pass), blends whose vertex the
+# neighbour does not have (geometric path, and from the second pass the exact tile resolve)
+rng = np.random.default_rng(5)
+noise = torch.from_numpy(rng.integers(0, 256, (3, 3), dtype=np.uint8)[rng.integers(0, 3, (2, 70, 90))]).cuda()
+with par.Remaster(0, 90, 70, 2) as ctx:
+    for S in (4, 6):
+        out = ctx.remaster(noise, S, True, want=("rgba",))
+    torch.cuda.synchronize()
 img = synth.adversarial_sprite(96, 100, 3)
 par.launch_kernel(img, True)
 with par.RemasterGroup([0, 0], 96, 100, 4) as g:
