@@ -403,7 +403,7 @@ __device__ __noinline__ void resolve_tile_exact( const uint16_t* keys, const uin
 // for the few cells the smoothing tables cannot express (or all smoothed cells under PAR_FLAG_NO_SMOOTH_TABLES).
 template< int S >
 __device__ __noinline__ void geometric_cells( const uint16_t* keys, const uint32_t* cols, uint32_t* s_mask, const uint16_t* s_work, uint16_t* s_vbuf, int* s_nwork,
-                                              int x0, int y0, const uint8_t* frame, int width, int height, int widthstep, const CellRecord* rec,
+                                              int capacity, int x0, int y0, const uint8_t* frame, int width, int height, int widthstep, const CellRecord* rec,
                                               uint32_t force_wide )
 {
     typedef Cfg< S > C;
@@ -418,7 +418,7 @@ __device__ __noinline__ void geometric_cells( const uint16_t* keys, const uint32
     env.img.widthstep = widthstep;
     const CellTablePtrs tab{ rec };
     const int tid = threadIdx.x;
-    const int n_work = *s_nwork;
+    const int n_work = min( *s_nwork, capacity ); // (the list shares its array with the second table pass's)
     uint16_t* vbuf = s_vbuf + tid;
     for( int w = tid; w < n_work && tid < kGeoThreads; w += kGeoThreads )
     {
@@ -971,11 +971,13 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     // (2a') cells with three or four link descriptors (one in ten): the remaining LINK entries are XORed in, with full
     // warps over the queued cells.  (All four slots in the first pass would cost every warp of it the instructions of
     // the two slots that nine cells in ten do not use.)  The two lists share one array — the geometric path's grows from
-    // the bottom, this one from the top, a cell is in one of them — so a mismatch found here cannot be queued for the
-    // geometric path any more: the tile then takes the exact resolve, which does not look at the masks.
-    if( s_nwork[ 3 ] != 0 ) // (uniform)
+    // the bottom, this one from the top, a cell is in one of them.  A mismatch found here queues the cell for the
+    // geometric path like one found in the first pass (which then rebuilds its whole mask) as long as that list stays
+    // below this one; beyond that — more than half of a tile's cells with a third link and a mismatch, never seen —
+    // the tile takes the exact resolve, which does not look at the masks.
+    const int n_more = s_nwork[ 3 ];
+    if( n_more != 0 ) // (uniform)
     {
-        const int n_more = s_nwork[ 3 ];
         for( int w = tid; w < n_more; w += kThreads )
         {
             const int idx = s_work[ C::NC - 1 - w ];
@@ -996,7 +998,15 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
                 for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] ^= ( uint32_t )( mw[ r >> 2 ] >> ( 16 * ( r & 3 ) ) ) & 0x7FFFu;
                 if( wide ) s_mask[ idx ] |= C::WIDE;
             }
-            if( wide || !ok ) s_nwork[ 2 ] = 1;
+            if( wide ) s_nwork[ 2 ] = 1;
+            if( !ok )
+            {
+                const int slot = warp_slot( s_nwork );
+                if( slot < C::NC - n_more )
+                    s_work[ slot ] = ( uint16_t )idx;
+                else
+                    s_nwork[ 2 ] = 1;
+            }
         }
         __syncthreads();
     }
@@ -1004,7 +1014,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     // (2b) general path, out of line (rarely runs: it costs the common path neither registers nor code)
     if( *s_nwork != 0 )
     {
-        geometric_cells< S >( s_keys, s_col, s_mask, s_work, s_vbuf, s_nwork, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, force_wide );
+        geometric_cells< S >( s_keys, s_col, s_mask, s_work, s_vbuf, s_nwork, C::NC - n_more, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, force_wide );
         __syncthreads(); // (uniform: the counter is final since the barrier before this pass)
     }
     if( a.smooth_stats && tid == 0 )

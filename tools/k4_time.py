@@ -13,6 +13,9 @@ W, H = 256, 224
 base = synth.snes_stream(64, W, H)
 if os.environ.get("K4_SPARSE"):  # flat 4x4 blocks: few smoothed cells per warp (the compacted pass of the raster kernel)
     base = np.ascontiguousarray(np.repeat(np.repeat(base[:, ::4, ::4], 4, 1), 4, 2))
+if os.environ.get("K4_NOISE"):  # 3-colour noise: every key, many blends whose vertex the neighbour does not have (geometric path)
+    rng = np.random.default_rng(5)
+    base = np.ascontiguousarray(rng.integers(0, 256, (3, 3), dtype=np.uint8)[rng.integers(0, 3, (64, H, W))])
 frames = torch.from_numpy(np.concatenate([base] * (F // 64), 0)).cuda()
 ctx = par.Remaster(0, W, H, F)
 g = ctx.resolve_crossings(ctx.similarity_graph(frames))
