@@ -101,7 +101,7 @@ struct Cfg
     static constexpr int off_mask = off_col + KW * KH * 4;
     static constexpr int off_bar = ( off_mask + NC * MW * 4 + 15 ) / 16 * 16;
     static constexpr int off_nwork = off_bar + 16; // four counters / flags
-    static constexpr int smem_bytes = off_nwork + 16;
+    static constexpr int smem_bytes = off_nwork + 16 + 4 * ( ( NC + kThreads - 1 ) / kThreads ) * ( kThreads / 32 ); // counters, then the ballots of the mask pass
 };
 
 // number of sample columns c in [0,N) with F - c*G > 0, i.e. clamp(ceil(F/G), 0, N), G > 0
@@ -403,7 +403,7 @@ __device__ __noinline__ void resolve_tile_exact( const uint16_t* keys, const uin
 // for the few cells the smoothing tables cannot express (or all smoothed cells under PAR_FLAG_NO_SMOOTH_TABLES).
 template< int S >
 __device__ __noinline__ void geometric_cells( const uint16_t* keys, const uint32_t* cols, uint32_t* s_mask, const uint16_t* s_work, uint16_t* s_vbuf, int* s_nwork,
-                                              int capacity, int x0, int y0, const uint8_t* frame, int width, int height, int widthstep, const CellRecord* rec,
+                                              int x0, int y0, const uint8_t* frame, int width, int height, int widthstep, const CellRecord* rec,
                                               uint32_t force_wide )
 {
     typedef Cfg< S > C;
@@ -418,7 +418,7 @@ __device__ __noinline__ void geometric_cells( const uint16_t* keys, const uint32
     env.img.widthstep = widthstep;
     const CellTablePtrs tab{ rec };
     const int tid = threadIdx.x;
-    const int n_work = min( *s_nwork, capacity ); // (the list shares its array with the second table pass's)
+    const int n_work = *s_nwork;
     uint16_t* vbuf = s_vbuf + tid;
     for( int w = tid; w < n_work && tid < kGeoThreads; w += kGeoThreads )
     {
@@ -696,7 +696,7 @@ __device__ __forceinline__ uint32_t link_slots( const SmoothTablePtrs& st, const
 }
 
 // Mask of a smoothed cell from the tables, FIRST pass: the CUT entry and the first two link descriptors (nine cells in
-// ten have no more).  `more` is set when the key has a third descriptor: the caller queues the cell for
+// ten have no more).  `more` is set when the key has a third descriptor: the caller marks the cell for
 // smooth_lookup_more.  Returns false when a blended vertex is not a vertex of the neighbour's hull (the reference's
 // getPointIndex fallback) — the caller then takes the geometric path.
 template< int S >
@@ -777,7 +777,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     const uint8_t* graph = a.graph + ( size_t )f * frame_px;
 
     // (1) stage graph bytes: rows y0-2 .. y0+TH+1, columns x0-16 .. x0-16+GP-1; zero outside the image
-    if( tid < 4 ) s_nwork[ tid ] = 0; // [0] geometric work items, [1] smoothed cells (statistics), [2] some cell of the tile is wide, [3] cells with a third link
+    if( tid < 3 ) s_nwork[ tid ] = 0; // [0] geometric work items, [1] smoothed cells (statistics), [2] some cell of the tile is wide
     if( kUseTma )
     {
         if( tid == 0 )
@@ -897,15 +897,23 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     // (Compacting the smoothed cells into a list first, so that the lookups run with full warps, was 3 % slower on the
     // busy frames of the bench — 83 % of the cells are smoothed — and 9 % faster on frames of flat 4 x 4 blocks.)
     int n_smoothed = 0;
-    for( int idx = tid; idx < C::NC; idx += kThreads )
+    constexpr int kRounds = ( C::NC + kThreads - 1 ) / kThreads;
+    uint32_t* s_more = reinterpret_cast< uint32_t* >( s_nwork + 4 ); // [kRounds][8 warps]: the cells of a round with a third link, as ballots
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll 1
+    for( int round = 0; round < kRounds; round++ ) // (whole warps: the vote at the end needs every lane)
     {
+        const int idx = round * kThreads + tid;
+        bool third_link = false;
         int cy = idx / C::CW, cx = idx - cy * C::CW;
         int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
         const bool inside = gx >= 0 && gy >= 0 && gx < a.width && gy < a.height;
         const uint16_t* kc = s_keys + ( cy + 1 ) * C::KW + cx + 1;
-        const uint32_t key = *kc;
+        const uint32_t key = idx < C::NC ? *kc : 90u;
         const bool plain = !subdivide || ( key & 0xFFu ) == 90u;
-        if( inside && !plain )
+        if( idx >= C::NC )
+            ;
+        else if( inside && !plain )
         {
             n_smoothed++;
             // checkTJunction for the four corners of the pixel square (bit c: corner c stays), 16 = its early exit
@@ -922,7 +930,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
             bool wide = false, more = false;
             if( use_tables && smooth_lookup< S >( a.smooth, a.mask_lut, kc, key, cf, mw, wide, more ) )
             {
-                if( more ) s_work[ C::NC - 1 - warp_slot( s_nwork + 3 ) ] = ( uint16_t )idx; // (second list, from the top of the array)
+                third_link = more;
                 if( C::PACK )
                 {
                     s_mask[ idx ] = ( uint32_t )mw[ 0 ];
@@ -960,27 +968,40 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
             for( int r = 0; r < C::R; r++ )
                 s_mask[ r * C::NC + idx ] = inside ? ( __ldg( a.mask_lut + key * C::R + r ) | ( r == 0 ? force_wide : 0u ) ) : 0u;
         }
+        const uint32_t vote = __ballot_sync( 0xFFFFFFFFu, third_link );
+        if( lane == 0 ) s_more[ round * ( kThreads / 32 ) + warp ] = vote;
     }
-    if( a.smooth_stats ) // (statistics for the bench line)
+    // (2a') cells with three or four link descriptors (one in ten): the remaining LINK entries are XORed in.  (All four
+    // slots in the first pass would cost every warp of it the instructions of the two slots that nine cells in ten do
+    // not use.)  Each warp takes the cells of its own rounds, found in the ballots it left above: no list, no atomics and
+    // no barrier — the dependent gathers of these few cells run under the other warps' first pass.
+    __syncwarp();
     {
-        n_smoothed = __reduce_add_sync( 0xFFFFFFFFu, n_smoothed );
-        if( ( tid & 31 ) == 0 ) atomicAdd( s_nwork + 1, n_smoothed );
-    }
-    __syncthreads();
-
-    // (2a') cells with three or four link descriptors (one in ten): the remaining LINK entries are XORed in, with full
-    // warps over the queued cells.  (All four slots in the first pass would cost every warp of it the instructions of
-    // the two slots that nine cells in ten do not use.)  The two lists share one array — the geometric path's grows from
-    // the bottom, this one from the top, a cell is in one of them.  A mismatch found here queues the cell for the
-    // geometric path like one found in the first pass (which then rebuilds its whole mask) as long as that list stays
-    // below this one; beyond that — more than half of a tile's cells with a third link and a mismatch, never seen —
-    // the tile takes the exact resolve, which does not look at the masks.
-    const int n_more = s_nwork[ 3 ];
-    if( n_more != 0 ) // (uniform)
-    {
-        for( int w = tid; w < n_more; w += kThreads )
+        uint32_t votes[ kRounds ];
+        int total = 0;
+#pragma unroll
+        for( int r = 0; r < kRounds; r++ )
         {
-            const int idx = s_work[ C::NC - 1 - w ];
+            votes[ r ] = s_more[ r * ( kThreads / 32 ) + warp ];
+            total += __popc( votes[ r ] );
+        }
+        for( int j = lane; j < total; j += 32 ) // lane j takes the j-th marked cell
+        {
+            int skip = j, round = 0;
+            uint32_t word = votes[ 0 ];
+#pragma unroll
+            for( int r = 0; r + 1 < kRounds; r++ )
+            {
+                const int c = __popc( votes[ r ] );
+                if( round == r && skip >= c )
+                {
+                    skip -= c;
+                    round = r + 1;
+                    word = votes[ r + 1 ];
+                }
+            }
+            for( ; skip > 0; skip-- ) word &= word - 1u;
+            const int idx = round * kThreads + warp * 32 + ( __ffs( ( int )word ) - 1 );
             const int cy = idx / C::CW, cx = idx - cy * C::CW;
             const uint16_t* kc = s_keys + ( cy + 1 ) * C::KW + cx + 1;
             uint64_t mw[ Entry< S >::EW ];
@@ -999,22 +1020,20 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
                 if( wide ) s_mask[ idx ] |= C::WIDE;
             }
             if( wide ) s_nwork[ 2 ] = 1;
-            if( !ok )
-            {
-                const int slot = warp_slot( s_nwork );
-                if( slot < C::NC - n_more )
-                    s_work[ slot ] = ( uint16_t )idx;
-                else
-                    s_nwork[ 2 ] = 1;
-            }
+            if( !ok ) s_work[ warp_slot( s_nwork ) ] = ( uint16_t )idx; // the geometric path rebuilds the whole mask
         }
-        __syncthreads();
     }
+    if( a.smooth_stats ) // (statistics for the bench line)
+    {
+        n_smoothed = __reduce_add_sync( 0xFFFFFFFFu, n_smoothed );
+        if( lane == 0 ) atomicAdd( s_nwork + 1, n_smoothed );
+    }
+    __syncthreads();
 
     // (2b) general path, out of line (rarely runs: it costs the common path neither registers nor code)
     if( *s_nwork != 0 )
     {
-        geometric_cells< S >( s_keys, s_col, s_mask, s_work, s_vbuf, s_nwork, C::NC - n_more, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, force_wide );
+        geometric_cells< S >( s_keys, s_col, s_mask, s_work, s_vbuf, s_nwork, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, force_wide );
         __syncthreads(); // (uniform: the counter is final since the barrier before this pass)
     }
     if( a.smooth_stats && tid == 0 )
