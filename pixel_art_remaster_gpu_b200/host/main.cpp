@@ -2,7 +2,12 @@
 // image in, remastered image out.
 //
 //   remaster_cli <input image> [-o out.png] [-s scale] [--aa 2|4] [--no-subdivide] [--graph g.pgm] [--labels l.pgm]
-//                [--strips N] [--device D] [--convert-only]
+//                [--graph-image g.png] [--draw-graph g.pgm] [--strips N] [--device D] [--convert-only]
+//
+// --graph-image draws the similarity graph the way the reference's debug view does (printToImage / display_graph,
+// main.cpp:79-163): a white image, scale_graph = 20 pixels per source pixel, a black stroke from each pixel's centre
+// half-way towards every linked neighbour.  --draw-graph takes the graph from a plane written by --graph instead of
+// computing it (no GPU needed).
 //
 // Kept from the reference: argv[1] is the input path (main.cpp:172-173); load_image() loads in colour,
 // flips the image vertically so that row 0 is the bottom scanline, and publishes img_data / img_width /
@@ -44,6 +49,61 @@ static bool load_image( const char* path )
 
 static void allocate_graph() { graph = ( char* )calloc( ( size_t )img_width * img_height, 1 ); } // main.cpp:141-147
 
+int scale_graph = 20;       // main.cpp:24
+Image* graph_img = nullptr; // main.cpp:28
+
+// black 1-pixel stroke (the reference draws with cvLine(..., CV_AA): OpenCV's anti-aliased line is outside this path,
+// a plain Bresenham line stands in for it)
+static void draw_line( Image* im, int x0, int y0, int x1, int y1 )
+{
+    const int dx = abs( x1 - x0 ), dy = -abs( y1 - y0 ), sx = x0 < x1 ? 1 : -1, sy = y0 < y1 ? 1 : -1;
+    int err = dx + dy;
+    for( ;; )
+    {
+        if( x0 >= 0 && y0 >= 0 && x0 < im->getWidth() && y0 < im->getHeight() )
+        {
+            char* p = im->getImageData() + ( size_t )y0 * im->getWidthStep() + 3 * x0;
+            p[ 0 ] = p[ 1 ] = p[ 2 ] = 0;
+        }
+        if( x0 == x1 && y0 == y1 ) break;
+        const int e2 = 2 * err;
+        if( e2 >= dy ) { err += dy; x0 += sx; }
+        if( e2 <= dx ) { err += dx; y0 += sy; }
+    }
+}
+
+/* Make a image representation of the graph (main.cpp:79-139): bit e of a node <-> neighbour (di,dj) of graph_functions.cu:162-171 */
+void printToImage( char* graph, Image* src, Image* img_out )
+{
+    static const int di[ 8 ] = { -1, 0, 1, -1, 1, -1, 0, 1 }, dj[ 8 ] = { 1, 1, 1, 0, 0, -1, -1, -1 };
+    const int half_sg = scale_graph / 2;
+    for( int j = 0; j < src->getHeight(); j++ )
+        for( int i = 0; i < src->getWidth(); i++ )
+        {
+            const int index = j * src->getWidth() + i;
+            const int n_j = j * scale_graph + half_sg - 1, n_i = i * scale_graph + half_sg - 1;
+            for( int e = 0; e < 8; e++ )
+                if( CHECK_BIT( graph[ index ], e ) ) draw_line( img_out, n_i + di[ e ] * half_sg, n_j + dj[ e ] * half_sg, n_i, n_j );
+        }
+}
+
+// display_graph (main.cpp:152-163) into a file: row 0 of the drawing is the bottom scanline (the frame is flipped,
+// glDrawPixels shows it upright), so it is flipped back before it is stored
+static bool save_graph_image( const char* path )
+{
+    graph_img = new Image();
+    graph_img->createImage( img->getWidth() * scale_graph, img->getHeight() * scale_graph, IPL_DEPTH_8U, 3 );
+    graph_img->setAllPixels( 255, 255, 255 );
+    printToImage( graph, img, graph_img );
+    graph_img->reverses();
+    graph_img->saveImage( path );
+    const bool ok = graph_img->error().empty();
+    if( !ok ) fprintf( stderr, "remaster_cli: %s\n", graph_img->error().c_str() );
+    delete graph_img;
+    graph_img = nullptr;
+    return ok;
+}
+
 static bool save_plane( const char* path, const void* data, int w, int h, int bytes_per_px )
 {
     // 1 byte/px -> PGM/PNG grey; 4 byte labels -> RGBA PNG of the raw int32 (lossless)
@@ -59,10 +119,10 @@ int main( int argc, char** argv )
 {
     if( argc < 2 )
     {
-        fprintf( stderr, "usage: %s <input image> [-o out.png] [-s scale] [--aa 2|4] [--no-subdivide] [--graph g.pgm] [--labels l.png] [--strips N] [--device D] [--convert-only]\n", argv[ 0 ] );
+        fprintf( stderr, "usage: %s <input image> [-o out.png] [-s scale] [--aa 2|4] [--no-subdivide] [--graph g.pgm] [--labels l.png] [--graph-image g.png] [--draw-graph g.pgm] [--strips N] [--device D] [--convert-only]\n", argv[ 0 ] );
         return 2;
     }
-    std::string out_path = "remastered.png", graph_path, labels_path;
+    std::string out_path = "remastered.png", graph_path, labels_path, graph_image_path, draw_graph_path;
     int scale = 4, strips = 0, device = 0, aa = 1; // aa: anti-aliasing samples per axis (the reference's GL_MULTISAMPLE toggle, simpleVBO.cpp:238-253)
     bool subdivide = true, convert_only = false;
     for( int k = 2; k < argc; k++ )
@@ -74,6 +134,8 @@ int main( int argc, char** argv )
         else if( a == "--no-subdivide" ) subdivide = false;
         else if( a == "--graph" && k + 1 < argc ) graph_path = argv[ ++k ];
         else if( a == "--labels" && k + 1 < argc ) labels_path = argv[ ++k ];
+        else if( a == "--graph-image" && k + 1 < argc ) graph_image_path = argv[ ++k ];
+        else if( a == "--draw-graph" && k + 1 < argc ) draw_graph_path = argv[ ++k ];
         else if( a == "--strips" && k + 1 < argc ) strips = atoi( argv[ ++k ] );
         else if( a == "--device" && k + 1 < argc ) device = atoi( argv[ ++k ] );
         else if( a == "--convert-only" ) convert_only = true;
@@ -81,6 +143,19 @@ int main( int argc, char** argv )
     }
     if( !load_image( argv[ 1 ] ) ) return 1;
     allocate_graph();
+    if( !draw_graph_path.empty() ) // the graph of an earlier run (--graph) as a picture; no GPU
+    {
+        Image plane;
+        plane.loadImage( draw_graph_path.c_str(), CV_LOAD_IMAGE_GRAYSCALE );
+        if( !plane.ok() || plane.getWidth() != img_width || plane.getHeight() != img_height || plane.getNchannels() != 1 )
+        {
+            fprintf( stderr, "remaster_cli: %s is not a %dx%d graph plane\n", draw_graph_path.c_str(), img_width, img_height );
+            return 1;
+        }
+        for( int y = 0; y < img_height; y++ ) // planes are stored top scanline first, the graph's row 0 is the bottom one
+            memcpy( graph + ( size_t )( img_height - 1 - y ) * img_width, plane.getImageData() + ( size_t )y * plane.getWidthStep(), ( size_t )img_width );
+        return save_graph_image( graph_image_path.empty() ? out_path.c_str() : graph_image_path.c_str() ) ? 0 : 1;
+    }
     if( convert_only ) // image I/O round trip only (no GPU): load -> flip -> flip back -> save
     {
         img->reverses();
@@ -156,6 +231,7 @@ int main( int argc, char** argv )
     if( !out.error().empty() ) { fprintf( stderr, "remaster_cli: %s\n", out.error().c_str() ); return 1; }
     if( !graph_path.empty() && !save_plane( graph_path.c_str(), graph, img_width, img_height, 1 ) ) return 1;
     if( !labels_path.empty() && !save_plane( labels_path.c_str(), labels.data(), img_width, img_height, 4 ) ) return 1;
+    if( !graph_image_path.empty() && !save_graph_image( graph_image_path.c_str() ) ) return 1;
     printf( "%s: %dx%d -> %dx%d (scale %d, subdivide %s) -> %s\n", argv[ 1 ], img_width, img_height, img_width * scale, img_height * scale, scale,
             subdivide ? "on" : "off", out_path.c_str() );
     free( graph );

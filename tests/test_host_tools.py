@@ -61,6 +61,33 @@ def test_palette_and_alpha_png_are_read_as_bgr(cli, tmp_path):
     assert np.array_equal(cv2.imread(dst, cv2.IMREAD_COLOR), want)
 
 
+def test_graph_picture_of_a_given_graph(cli, tmp_path):
+    """--draw-graph / --graph-image: the reference's debug view of the similarity graph (printToImage, main.cpp:79-139) —
+    20 pixels per source pixel, a black stroke from each pixel's centre (19 + 20 i - 10, rows counted from the bottom)
+    half-way towards every linked neighbour, white elsewhere.  The graph comes from a plane as --graph writes it."""
+    w, h, sg = 3, 2, 20
+    cv2.imwrite(str(tmp_path / "in.png"), np.zeros((h, w, 3), np.uint8))
+    g = np.zeros((h, w), np.uint8)          # pipeline orientation: row 0 = bottom scanline
+    g[0, 0] = 1 << 4                        # bottom-left pixel: linked to the right (+1, 0)
+    g[0, 1] = (1 << 3) | (1 << 2)           # its right neighbour: left (-1, 0) and up-right (+1, +1)
+    g[1, 2] = 1 << 5                        # top-right pixel: down-left (-1, -1)
+    cv2.imwrite(str(tmp_path / "g.pgm"), np.ascontiguousarray(g[::-1]))   # planes are stored top scanline first
+    out = str(tmp_path / "graph.png")
+    subprocess.run([cli, str(tmp_path / "in.png"), "--draw-graph", str(tmp_path / "g.pgm"), "--graph-image", out], check=True, timeout=60)
+    pic = cv2.imread(out, cv2.IMREAD_COLOR)
+    assert pic.shape == (h * sg, w * sg, 3)
+    up = pic[::-1, :, 0]                    # rows counted from the bottom, like the drawing
+    black = up == 0
+    assert set(np.unique(pic)) <= {0, 255}
+    c = lambda k: k * sg + sg // 2 - 1      # centre of source pixel k
+    assert black[c(0), c(0):c(0) + 11].all()                       # (0,0) -> right, half-way
+    assert black[c(0), c(1) - 10:c(1) + 1].all()                   # (1,0) -> left: the two strokes meet
+    assert all(black[c(0) + t, c(1) + t] for t in range(11))       # (1,0) -> up-right diagonal
+    assert all(black[c(1) - t, c(2) - t] for t in range(11))       # (2,1) -> down-left diagonal: meets it half-way
+    assert not black[c(1), c(0) - 3:c(0) + 4].any()                # the unlinked top-left pixel has no stroke
+    assert int(black.sum()) == 4 * 11 - 3                          # four strokes, three shared end pixels
+
+
 def test_missing_file_fails_loudly(cli, tmp_path):
     r = subprocess.run([cli, str(tmp_path / "nope.png")], capture_output=True, text=True)
     assert r.returncode != 0 and "cannot read" in r.stderr
