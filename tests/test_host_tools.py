@@ -103,11 +103,16 @@ def test_cli_image_in_image_out(cli, oracle, tmp_path, strips):
     frame = synth.snes_frame(96, 120, 17)                  # pipeline orientation (row 0 = bottom)
     src = str(tmp_path / "in.png")
     cv2.imwrite(src, _bgr_top_down(frame))
-    dst, gpath = str(tmp_path / "out.png"), str(tmp_path / "graph.png")
-    cmd = [cli, src, "-o", dst, "-s", "4", "--graph", gpath] + (["--strips", str(strips)] if strips else [])
+    dst, gpath, gimg = str(tmp_path / "out.png"), str(tmp_path / "graph.png"), str(tmp_path / "graph_picture.png")
+    cmd = [cli, src, "-o", dst, "-s", "4", "--graph", gpath, "--graph-image", gimg] + (["--strips", str(strips)] if strips else [])
     subprocess.run(cmd, check=True, timeout=300)
     # the CLI pads rows to 4 bytes like IplImage; 96*3 is already aligned, so the oracle sees the same bytes
     want = oracle.pipeline(frame, scale=4, want=("graph", "raster"))
     got = cv2.imread(dst, cv2.IMREAD_COLOR)
     assert np.array_equal(got, want["raster"][::-1, :, 2::-1])   # RGBA bottom-up -> BGR top-down
     assert np.array_equal(cv2.imread(gpath, cv2.IMREAD_GRAYSCALE), want["graph"][::-1])
+    # the graph picture of the same run equals the one drawn from the stored plane
+    again = str(tmp_path / "graph_picture_again.png")
+    subprocess.run([cli, src, "--draw-graph", gpath, "--graph-image", again], check=True, timeout=60)
+    pic = cv2.imread(gimg, cv2.IMREAD_COLOR)
+    assert pic.shape == (120 * 20, 96 * 20, 3) and np.array_equal(pic, cv2.imread(again, cv2.IMREAD_COLOR))
