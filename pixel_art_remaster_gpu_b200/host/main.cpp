@@ -3,6 +3,13 @@
 //
 //   remaster_cli <input image> [-o out.png] [-s scale] [--aa 2|4] [--no-subdivide] [--graph g.pgm] [--labels l.pgm]
 //                [--graph-image g.png] [--draw-graph g.pgm] [--strips N] [--device D] [--convert-only]
+//   remaster_cli <image that gives the frame size> --raw-video in.bin --raw-out out.bin [--skip K] [--frames M] [-s scale] ...
+//
+// --raw-video is the stream the reference's author had wired in and commented out (main.cpp:67-75, simpleVBO.cpp:154): a
+// file of consecutive frames of img_height * img_widthstep bytes each, in the layout launch_kernel is given (BGR8, row 0 =
+// bottom scanline), the image in argv[1] only supplying the size; --skip frames are passed over (the reference seeks past
+// 40), at most --frames are read (2000 there).  The frames go through the batch entry point 64 at a time; --raw-out
+// receives the remastered frames back to back, (s*height) x (s*width) RGBA8, rows in the same bottom-up order.
 //
 // --graph-image draws the similarity graph the way the reference's debug view does (printToImage / display_graph,
 // main.cpp:79-163): a white image, scale_graph = 20 pixels per source pixel, a black stroke from each pixel's centre
@@ -119,10 +126,11 @@ int main( int argc, char** argv )
 {
     if( argc < 2 )
     {
-        fprintf( stderr, "usage: %s <input image> [-o out.png] [-s scale] [--aa 2|4] [--no-subdivide] [--graph g.pgm] [--labels l.png] [--graph-image g.png] [--draw-graph g.pgm] [--strips N] [--device D] [--convert-only]\n", argv[ 0 ] );
+        fprintf( stderr, "usage: %s <input image> [-o out.png] [-s scale] [--aa 2|4] [--no-subdivide] [--graph g.pgm] [--labels l.png] [--graph-image g.png] [--draw-graph g.pgm] [--strips N] [--device D] [--convert-only] [--raw-video in.bin --raw-out out.bin [--skip K] [--frames M]]\n", argv[ 0 ] );
         return 2;
     }
-    std::string out_path = "remastered.png", graph_path, labels_path, graph_image_path, draw_graph_path;
+    std::string out_path = "remastered.png", graph_path, labels_path, graph_image_path, draw_graph_path, raw_video_path, raw_out_path;
+    long skip_frames = 0, max_video_frames = 2000;
     int scale = 4, strips = 0, device = 0, aa = 1; // aa: anti-aliasing samples per axis (the reference's GL_MULTISAMPLE toggle, simpleVBO.cpp:238-253)
     bool subdivide = true, convert_only = false;
     for( int k = 2; k < argc; k++ )
@@ -136,6 +144,10 @@ int main( int argc, char** argv )
         else if( a == "--labels" && k + 1 < argc ) labels_path = argv[ ++k ];
         else if( a == "--graph-image" && k + 1 < argc ) graph_image_path = argv[ ++k ];
         else if( a == "--draw-graph" && k + 1 < argc ) draw_graph_path = argv[ ++k ];
+        else if( a == "--raw-video" && k + 1 < argc ) raw_video_path = argv[ ++k ];
+        else if( a == "--raw-out" && k + 1 < argc ) raw_out_path = argv[ ++k ];
+        else if( a == "--skip" && k + 1 < argc ) skip_frames = atol( argv[ ++k ] );
+        else if( a == "--frames" && k + 1 < argc ) max_video_frames = atol( argv[ ++k ] );
         else if( a == "--strips" && k + 1 < argc ) strips = atoi( argv[ ++k ] );
         else if( a == "--device" && k + 1 < argc ) device = atoi( argv[ ++k ] );
         else if( a == "--convert-only" ) convert_only = true;
@@ -161,6 +173,47 @@ int main( int argc, char** argv )
         img->reverses();
         img->saveImage( out_path.c_str() );
         if( !img->error().empty() ) { fprintf( stderr, "remaster_cli: %s\n", img->error().c_str() ); return 1; }
+        return 0;
+    }
+    if( !raw_video_path.empty() ) // a stream of raw frames of the image's size through the batch entry point
+    {
+        if( raw_out_path.empty() ) { fprintf( stderr, "remaster_cli: --raw-video needs --raw-out\n" ); return 2; }
+        FILE* in = fopen( raw_video_path.c_str(), "rb" );
+        FILE* outf = in ? fopen( raw_out_path.c_str(), "wb" ) : nullptr;
+        if( !in || !outf ) { fprintf( stderr, "remaster_cli: cannot open %s\n", in ? raw_out_path.c_str() : raw_video_path.c_str() ); return 1; }
+        const size_t frame_bytes = ( size_t )img_height * img_widthstep, out_bytes = ( size_t )img_width * img_height * scale * scale * 4;
+        const int batch = 64;
+        if( fseek( in, ( long )( skip_frames * ( long )frame_bytes ), SEEK_SET ) != 0 ) { fprintf( stderr, "remaster_cli: cannot seek in %s\n", raw_video_path.c_str() ); return 1; }
+        par_context* ctx = nullptr;
+        if( par_create( &ctx, device, img_width, img_height, batch ) != PAR_OK ) { fprintf( stderr, "remaster_cli: %s\n", par_last_error( nullptr ) ); return 1; }
+        std::vector< uint8_t > frames( frame_bytes * batch ), result( out_bytes * batch );
+        long done = 0;
+        while( done < max_video_frames )
+        {
+            const long want = max_video_frames - done < batch ? max_video_frames - done : batch;
+            const int n = ( int )( fread( frames.data(), 1, frame_bytes * ( size_t )want, in ) / frame_bytes ); // (a trailing partial frame is dropped)
+            if( n == 0 ) break;
+            par_job vj;
+            memset( &vj, 0, sizeof( vj ) );
+            vj.bgr = frames.data();
+            vj.width = img_width;
+            vj.height = img_height;
+            vj.widthstep = img_widthstep;
+            vj.n_frames = n;
+            vj.scale = scale;
+            vj.flags = subdivide ? PAR_FLAG_SUBDIVIDE : 0u;
+            if( aa == 2 ) vj.flags |= PAR_FLAG_AA2;
+            if( aa == 4 ) vj.flags |= PAR_FLAG_AA4;
+            vj.rgba = result.data();
+            if( par_remaster_host( ctx, &vj ) != PAR_OK ) { fprintf( stderr, "remaster_cli: %s\n", par_last_error( ctx ) ); return 1; }
+            if( fwrite( result.data(), 1, out_bytes * ( size_t )n, outf ) != out_bytes * ( size_t )n ) { fprintf( stderr, "remaster_cli: cannot write %s\n", raw_out_path.c_str() ); return 1; }
+            done += n;
+        }
+        par_destroy( ctx );
+        fclose( in );
+        if( fclose( outf ) != 0 ) { fprintf( stderr, "remaster_cli: cannot write %s\n", raw_out_path.c_str() ); return 1; }
+        printf( "%s: %ld frames of %dx%d -> %dx%d RGBA (scale %d, subdivide %s) -> %s\n", raw_video_path.c_str(), done, img_width, img_height, img_width * scale,
+                img_height * scale, scale, subdivide ? "on" : "off", raw_out_path.c_str() );
         return 0;
     }
     const size_t N = ( size_t )img_width * img_height;

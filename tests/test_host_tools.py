@@ -116,3 +116,27 @@ def test_cli_image_in_image_out(cli, oracle, tmp_path, strips):
     subprocess.run([cli, src, "--draw-graph", gpath, "--graph-image", again], check=True, timeout=60)
     pic = cv2.imread(gimg, cv2.IMREAD_COLOR)
     assert pic.shape == (120 * 20, 96 * 20, 3) and np.array_equal(pic, cv2.imread(again, cv2.IMREAD_COLOR))
+
+
+@pytest.mark.gpu
+def test_cli_raw_video_stream(cli, oracle, tmp_path):
+    """remaster_cli size.png --raw-video in.bin --raw-out out.bin: the frame stream the reference's author had wired in
+    (main.cpp:67-75: frames of height * widthstep bytes in launch_kernel's layout, some skipped, a bounded number read):
+    every remastered frame equals the oracle's raster of its source frame.  50 pixels wide: rows are padded to 152 bytes."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    w, h, n, skip, take = 50, 37, 70, 2, 67              # 67 frames: one full batch of 64 and a tail of 3
+    frames = synth.snes_stream(n, w, h, first_seed=4242)
+    cv2.imwrite(str(tmp_path / "size.png"), _bgr_top_down(frames[0]))
+    padded = np.zeros((n, h, 152), np.uint8)
+    padded[:, :, :3 * w] = frames.reshape(n, h, 3 * w)
+    padded.tofile(str(tmp_path / "in.bin"))
+    out = str(tmp_path / "out.bin")
+    subprocess.run([cli, str(tmp_path / "size.png"), "--raw-video", str(tmp_path / "in.bin"), "--raw-out", out, "--skip", str(skip),
+                    "--frames", str(take), "-s", "2"], check=True, timeout=300)
+    got = np.fromfile(out, np.uint8).reshape(take, 2 * h, 2 * w, 4)
+    for k in (0, 1, 63, 64, 66):
+        src = np.lib.stride_tricks.as_strided(padded[skip + k], shape=(h, w, 3), strides=(152, 3, 1))  # the same padding bytes
+        want = oracle.pipeline(src, scale=2, want=("raster",))["raster"]
+        assert np.array_equal(got[k], want), k
