@@ -67,7 +67,9 @@ struct Cfg
     static constexpr int KW = TW + 4, KH = TH + 4;        // cells whose keys and colours are needed (halo 2)
     static constexpr int GOFF = 16;                       // staged rows begin at column x0 - 16 (TMA: 16-byte aligned start)
     static constexpr int GP = ( GOFF + TW + 3 + 15 ) / 16 * 16; // staged row pitch (TMA box row), covers x0-3 .. x0+TW+2
-    static constexpr int RAWP = ( 16 + 3 * ( TW + 2 ) + 15 ) / 16 * 16; // staged BGR row: bytes 3*x0-16 .. (TMA box row)
+    // staged BGR row (TMA box row): bytes 3*x0-16 .. ; 16 bytes more than needed, because a 128-byte pitch would put every
+    // row on the same banks and the staging pass (a warp reads four rows at once) would take 4-way conflicts
+    static constexpr int RAWP = ( 16 + 3 * ( TW + 2 ) + 15 ) / 16 * 16 + ( ( 16 + 3 * ( TW + 2 ) + 15 ) / 16 * 16 % 128 == 0 ? 16 : 0 );
     static constexpr int RAWOFF = 16 - 6;                 // byte offset of pixel x0-2 in a staged row
     static constexpr int NC = CW * CH;
     static constexpr uint32_t FULL = ( 1u << S ) - 1u;
