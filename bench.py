@@ -71,11 +71,21 @@ def measured_peak_gbs():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp")
+    # The sampler is started BEFORE the warm-up steps: nvidia-smi needs 50-150 ms before its first sample, as long as the
+    # whole timed region of a 10-step run.  Samples carry a timestamp; those inside [mark_begin, mark_end] (host clock
+    # around the timed region, 30 ms of slack) are the ones reported, the warm-up's (same load) only if none fell inside.
 
     def __init__(self, device_index):
         self.idx = device_index
         self.proc = None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -94,22 +104,31 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, reasons = [], [], set()
+        import datetime
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in out.splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                sm, mx = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for k, name in enumerate(names):
-                if f[5 + k].lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            when = None
+            if len(f) > 9:
+                try:
+                    when = datetime.datetime.strptime(f[9], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    pass
+            rows.append((when, sm, mx, {name for k, name in enumerate(names) if f[5 + k].lower().startswith("active")}))
+        inside = [r for r in rows if r[0] is not None and self.t0 is not None and self.t1 is not None and self.t0 - 0.03 <= r[0] <= self.t1 + 0.03]
+        used = inside or rows
+        reasons = set()
+        for r in used:
+            reasons |= r[3]
+        return {"sm_mhz": statistics.median([r[1] for r in used]) if used else None, "sm_max_mhz": max(r[2] for r in used) if used else None,
+                "reasons": sorted(reasons), "samples": len(used), "samples_in_timed_region": len(inside)}
 
 
 def host_threads():
@@ -249,6 +268,9 @@ def run_ours(args):
     def step():
         ctx.remaster(frames, SCALE, True, out=out)
 
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -256,16 +278,15 @@ def run_ours(args):
     ctx.profile_read()
     smooth0 = ctx.smooth_stats()
     launches0 = ctx.launch_count
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     barrier()
+    clocks.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     barrier()
+    clocks.mark_end()
     clock_info = clocks.stop() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     prof = ctx.profile_read()
