@@ -55,23 +55,33 @@ typedef enum par_status
 
 enum
 {
-    PAR_FLAG_SUBDIVIDE = 1u << 0,   /* stage E on (launch_kernel's `subdivide`, kernel.cu:288) */
-    PAR_FLAG_FLIP_OUTPUT = 1u << 1, /* rgba row 0 = top scanline (undo main.cpp:59's flip) */
-    PAR_FLAG_NO_TMA = 1u << 2       /* force the plain-load tile path (also taken automatically when
-                                       pointers/strides are not 16-byte multiples) */
-    ,
-    PAR_FLAG_NO_SMOOTH_TABLES = 1u << 4 /* do not use the smoothing tables: every smoothed cell builds its polygon
-                                           and rasterizes it (the geometric path; same image, for tests) */
-    ,
-    PAR_FLAG_DEBUG_WIDE = 1u << 3   /* test hook: rasterize every cell through the exact slow path that
-                                       normally only handles cells reaching beyond their sample mask */
-    ,
+    PAR_FLAG_SUBDIVIDE = 1u << 0,        /* stage E on (launch_kernel's `subdivide`, kernel.cu:288) */
+    PAR_FLAG_FLIP_OUTPUT = 1u << 1,      /* image row 0 = top scanline (undo main.cpp:59's flip) */
+    PAR_FLAG_NO_TMA = 1u << 2,           /* force the plain-load tile path (also taken automatically when pointers/strides
+                                            are not 16-byte multiples) */
+    PAR_FLAG_DEBUG_WIDE = 1u << 3,       /* test hook: rasterize every cell through the exact slow path that normally only
+                                            handles cells reaching beyond their sample mask */
+    PAR_FLAG_NO_SMOOTH_TABLES = 1u << 4, /* do not use the smoothing tables: every smoothed cell builds its polygon and
+                                            rasterizes it (the geometric path; same image, for tests) */
     /* Anti-aliased output (the reference's GL_MULTISAMPLE toggle, simpleVBO.cpp:238-253, main.cpp:233): every output
      * pixel is the mean of 2x2 / 4x4 ordered-grid samples (the point-sampling rule at 2x / 4x the scale, averaged per
-     * channel, halves rounded up).  scale x samples must be a supported scale: AA2 with scale 1,2,3,4; AA4 with 1,2. */
+     * channel, halves rounded up).  scale x samples must be a supported scale (1..8): AA2 with scale 1..4; AA4 with 1,2. */
     PAR_FLAG_AA2 = 1u << 5,
     PAR_FLAG_AA4 = 1u << 6
 };
+
+/* Layout of the output image (par_job.out_format).  Every output pixel of the point-sampled image is the colour of a
+ * source pixel (kernel.cu:98-101) or the black background (main.cpp:260), so the image has at most as many colours as
+ * the frame + 1 and can be returned losslessly as palette indices: a quarter of the bytes of RGBA8. */
+typedef enum par_out_format
+{
+    PAR_OUT_RGBA8 = 0,  /* 4 bytes per pixel: R, G, B, 255 (the colours of the reference's colour VBO, kernel.cu:98-101) */
+    PAR_OUT_BGR8 = 1,   /* 3 bytes per pixel: B, G, R — the 3-channel image Image::saveImage writes (Image.cpp:64-71) */
+    PAR_OUT_INDEX8 = 2  /* 1 byte per pixel: index into the frame's palette (par_job.palette: 256 RGBA8 entries per frame,
+                           ascending by R<<16|G<<8|B, entry 0 is always black = the background; par_job.palette_count: entries
+                           used).  A frame with more than 256 colours reports its count (> 256) and its index image is
+                           undefined: ask for RGBA8 / BGR8 for such frames.  Not available with PAR_FLAG_AA2 / AA4. */
+} par_out_format;
 
 typedef struct par_context par_context;
 
@@ -85,14 +95,20 @@ typedef struct par_job
     int widthstep;        /*      bytes per row (>= 3*width)                             */
     size_t frame_stride;  /*      bytes between frames (>= widthstep*height); 0 = dense  */
     int n_frames;
-    int scale;            /*      output magnification s (1..8)                          */
+    int scale;            /*      output magnification s: an integer 1..8 (the reference's viewer
+                                  steps a float scale by 0.5, callbacks.cpp:162-166; the rasterizer
+                                  here samples on an integer grid only)                          */
     unsigned flags;       /*      PAR_FLAG_*                                             */
-    uint8_t* rgba;        /* out: n_frames * (s*height) * (s*width) * 4 bytes            */
+    uint8_t* rgba;        /* out: the image, n_frames * (s*height) * (s*width) * {4,3,1} bytes
+                                  (out_format below; RGBA8 unless set)                           */
     uint8_t* graph;       /* out: final similarity graph, n_frames * width*height bytes  */
     uint8_t* graph_aux;   /* out: graph after the trivial-crossing pass (kernel.cu:415)  */
     int32_t* labels;      /* out: connected-component labels                             */
     float* polygons;      /* out: n_frames * width*height * 45 * 2 floats                */
     int32_t* poly_count;  /* out: vertices per polygon (launch_kernel's edge_count_h)    */
+    int out_format;       /*      par_out_format of `rgba` (0 = PAR_OUT_RGBA8)                   */
+    uint32_t* palette;    /* out (INDEX8): n_frames * 256 RGBA8 words (R | G<<8 | B<<16 | 255<<24) */
+    int32_t* palette_count; /* out (INDEX8): colours per frame incl. black; > 256: not representable */
 } par_job;
 
 /* Context: device, stream, pooled scratch (graph buffers for `max_frames` frames of up to
@@ -106,6 +122,10 @@ int par_device( const par_context* ctx );
 int par_set_stream( par_context* ctx, void* cuda_stream );
 int par_use_own_stream( par_context* ctx );
 int par_synchronize( par_context* ctx );
+/* par_remaster_device() runs a batch in rounds of `frames` frames through all stages (0, the default: one launch per stage
+ * over the whole batch).  Frames are independent units, so results do not depend on it; it only decides whether the
+ * intermediates of a round (2 bytes per pixel) are still in L2 when the next stage reads them. */
+int par_set_sub_batch( par_context* ctx, int frames );
 /* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
 uint64_t par_launch_count( const par_context* ctx );
 
@@ -113,7 +133,7 @@ uint64_t par_launch_count( const par_context* ctx );
  * is bracketed by CUDA events on the context's stream.  par_profile_read() synchronizes the stream,
  * adds up the event intervals recorded since the last read and returns, per stage, the total
  * milliseconds and the number of launches (arrays of PAR_N_STAGES). */
-#define PAR_N_STAGES 5 /* 0 similarity graph, 1 resolve crossings, 2 cc labels, 3 polygons, 4 raster */
+#define PAR_N_STAGES 6 /* 0 similarity graph, 1 resolve crossings, 2 cc labels, 3 polygons, 4 raster, 5 palette */
 int par_profile_enable( par_context* ctx, int on );
 int par_profile_read( par_context* ctx, double* total_ms, int* launches );
 
@@ -161,8 +181,32 @@ typedef struct par_group par_group;
 int par_group_create( par_group** out, const int* devices, int n_devices, int width, int height, int scale );
 void par_group_destroy( par_group* grp );
 const char* par_group_last_error( const par_group* grp );
-/* Host image in, host outputs out (any may be NULL); strips exchange halo rows over P2P. */
+/* Host image in, host outputs out (any may be NULL); strips exchange halo rows over P2P.  job->out_format may be
+ * PAR_OUT_RGBA8 or PAR_OUT_BGR8 (a palette would be per strip). */
 int par_group_remaster_host( par_group* grp, const par_job* job );
+/* Device-resident tiled path (SURVEY §8(e), config 4 without the PCIe round trip).  Strip k owns image rows
+ * [own_begin, own_end) and holds rows [load_begin, load_end) (its 40-row aprons included); all its buffers are dense rows
+ * starting at row load_begin on `device`: bgr 3*width bytes per row (IN: the caller writes the strip's OWN rows, complete
+ * before the call — e.g. cudaMemcpy, or a producer kernel followed by a synchronize), image scale*scale*{4,3} bytes per
+ * pixel, graph / graph_aux 1, labels 4 (global pixel indices).  par_group_remaster_device() pulls the apron rows from the
+ * neighbouring devices (peer copies over NVLink), runs the path on every strip, labels and stitches across the seams on
+ * the devices and returns after synchronizing all strips; only the OWN rows of the outputs are meaningful. */
+typedef struct par_strip
+{
+    int device;
+    int own_begin, own_end, load_begin, load_end;
+    uint8_t* bgr;
+    uint8_t* image;
+    uint8_t* graph;
+    uint8_t* graph_aux;
+    int32_t* labels;
+} par_strip;
+int par_group_n_strips( const par_group* grp );
+int par_group_strip( const par_group* grp, int k, par_strip* out );
+int par_group_remaster_device( par_group* grp, unsigned flags, int out_format, int want_image, int want_labels );
+/* Duration of the last par_group_remaster_device(): host wall clock from the first enqueue to the last synchronize, and
+ * the longest strip's own device time (CUDA events on its stream: waits for the neighbours included). */
+int par_group_last_ms( const par_group* grp, double* wall_ms, double* device_ms );
 
 /* ---- the reference's own entry point (kernel.cu:286-288), same symbol and signature ------------ */
 #if defined( __CUDACC__ ) || defined( PAR_HAVE_CUDA_VECTOR_TYPES )

@@ -17,11 +17,13 @@ import numpy as np
 from . import synth  # noqa: F401  (synthetic inputs for the BASELINE configs)
 
 __all__ = ["Remaster", "RemasterGroup", "launch_kernel", "RemasterError", "load_library", "library_path", "cell_from_pattern", "yuv_word",
-           "FLAG_SUBDIVIDE", "FLAG_FLIP_OUTPUT", "FLAG_NO_TMA", "CELL_SLOTS", "synth"]
+           "FLAG_SUBDIVIDE", "FLAG_FLIP_OUTPUT", "FLAG_NO_TMA", "CELL_SLOTS", "OUT_RGBA8", "OUT_BGR8", "OUT_INDEX8", "synth"]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CELL_SLOTS = 45
 FLAG_SUBDIVIDE, FLAG_FLIP_OUTPUT, FLAG_NO_TMA, FLAG_DEBUG_WIDE, FLAG_NO_SMOOTH_TABLES, FLAG_AA2, FLAG_AA4 = 1, 2, 4, 8, 16, 32, 64
+OUT_RGBA8, OUT_BGR8, OUT_INDEX8 = 0, 1, 2   # par_out_format
+_BPP = {OUT_RGBA8: 4, OUT_BGR8: 3, OUT_INDEX8: 1}
 _STATUS = {0: "PAR_OK", 1: "PAR_ERR_INVALID", 2: "PAR_ERR_NO_DEVICE", 3: "PAR_ERR_CUDA", 4: "PAR_ERR_CAPACITY"}
 
 
@@ -35,7 +37,20 @@ class ParJob(C.Structure):
     _fields_ = [("bgr", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("widthstep", C.c_int),
                 ("frame_stride", C.c_size_t), ("n_frames", C.c_int), ("scale", C.c_int), ("flags", C.c_uint),
                 ("rgba", C.c_void_p), ("graph", C.c_void_p), ("graph_aux", C.c_void_p), ("labels", C.c_void_p),
-                ("polygons", C.c_void_p), ("poly_count", C.c_void_p)]
+                ("polygons", C.c_void_p), ("poly_count", C.c_void_p),
+                ("out_format", C.c_int), ("palette", C.c_void_p), ("palette_count", C.c_void_p)]
+
+
+class ParStrip(C.Structure):
+    _fields_ = [("device", C.c_int), ("own_begin", C.c_int), ("own_end", C.c_int), ("load_begin", C.c_int), ("load_end", C.c_int),
+                ("bgr", C.c_void_p), ("image", C.c_void_p), ("graph", C.c_void_p), ("graph_aux", C.c_void_p), ("labels", C.c_void_p)]
+
+
+class _DeviceBuffer:
+    """A raw device allocation of the library seen as an array (torch.as_tensor aliases it through this interface)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
 _lib = None
@@ -64,6 +79,7 @@ def load_library():
     L.par_device.argtypes = [C.c_void_p]
     L.par_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.par_use_own_stream.argtypes = [C.c_void_p]
+    L.par_set_sub_batch.argtypes = [C.c_void_p, C.c_int]
     L.par_border_walks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_longlong, C.c_void_p]
     L.par_smooth_stats.argtypes = [C.c_void_p, P(C.c_uint64)]
@@ -81,6 +97,10 @@ def load_library():
     L.par_group_last_error.argtypes = [C.c_void_p]
     L.par_group_last_error.restype = C.c_char_p
     L.par_group_remaster_host.argtypes = [C.c_void_p, P(ParJob)]
+    L.par_group_n_strips.argtypes = [C.c_void_p]
+    L.par_group_strip.argtypes = [C.c_void_p, C.c_int, P(ParStrip)]
+    L.par_group_remaster_device.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int]
+    L.par_group_last_ms.argtypes = [C.c_void_p, P(C.c_double), P(C.c_double)]
     L.launch_kernel.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_bool]
     L.launch_kernel.restype = C.c_void_p
     L.par_cell_from_pattern.argtypes = [C.c_uint, P(C.c_float)]
@@ -121,7 +141,8 @@ class Remaster:
             self.handle = C.c_void_p()
             raise RemasterError(st, self.lib.par_last_error(None).decode())
         self.device = torch.device("cuda", int(device))
-        self.use_torch_stream()
+        self._pinned_stream = None
+        self._bind_stream()
 
     # -- plumbing --------------------------------------------------------------------------
     def close(self):
@@ -143,15 +164,24 @@ class Remaster:
         self.close()
 
     def use_torch_stream(self, stream=None):
-        """Run all work on a torch stream (default: torch's current stream on this device), so that
-        torch.cuda.Event timing and tensor lifetimes see it."""
-        s = stream if stream is not None else self._torch.cuda.current_stream(self.device)
+        """Pin all work of this context to one torch stream.  With stream=None (the default state) every call runs on
+        torch's CURRENT stream of the context's device at the time of the call, so that outputs allocated under
+        `with torch.cuda.stream(s)` are produced on s, and torch.cuda.Event timing and tensor lifetimes see the work."""
+        self._pinned_stream = stream
+        self._bind_stream()
+
+    def _bind_stream(self):
+        s = self._pinned_stream if self._pinned_stream is not None else self._torch.cuda.current_stream(self.device)
         self._check(self.lib.par_set_stream(self.handle, C.c_void_p(s.cuda_stream)))
+
+    def set_sub_batch(self, frames):
+        """Run batches in rounds of `frames` frames through all stages (0 = one launch per stage over the whole batch)."""
+        self._check(self.lib.par_set_sub_batch(self.handle, int(frames)))
 
     def synchronize(self):
         self._check(self.lib.par_synchronize(self.handle))
 
-    STAGES = ("similarity_graph", "resolve_crossings", "cc_labels", "polygons", "raster")
+    STAGES = ("similarity_graph", "resolve_crossings", "cc_labels", "polygons", "raster", "palette")
 
     def profile(self, on=True):
         """Bracket every stage launch with CUDA events on the launching stream (par_profile_enable)."""
@@ -159,8 +189,8 @@ class Remaster:
 
     def profile_read(self):
         """{stage: (total_ms, launches)} since the last read; synchronizes the stream."""
-        ms = (C.c_double * 5)()
-        n = (C.c_int * 5)()
+        ms = (C.c_double * len(self.STAGES))()
+        n = (C.c_int * len(self.STAGES))()
         self._check(self.lib.par_profile_read(self.handle, ms, n))
         return {k: (ms[i], n[i]) for i, k in enumerate(self.STAGES)}
 
@@ -179,8 +209,12 @@ class Remaster:
         if st != 0:
             raise RemasterError(st, self.lib.par_last_error(self.handle).decode())
 
-    def _job(self, frames, scale, flags, **outs):
+    def _job(self, frames, scale, flags, out_format=OUT_RGBA8, **outs):
         t = self._torch
+        self._bind_stream()  # (every launch goes to the stream that is current now, unless one was pinned)
+        for v in [frames] + list(outs.values()):
+            if v is not None and v.is_cuda and v.device != self.device:
+                raise ValueError("tensor on %s passed to a context on %s" % (v.device, self.device))
         if frames is not None:
             assert frames.dtype == t.uint8 and frames.dim() == 4 and frames.shape[3] == 3, "frames: (F, H, W, 3) uint8 BGR"
             assert frames.stride(3) == 1 and frames.stride(2) == 3, "pixels must be packed BGR"
@@ -192,28 +226,40 @@ class Remaster:
         j = ParJob()
         j.bgr = _ptr(frames)
         j.width, j.height, j.widthstep, j.frame_stride, j.n_frames = W, H, ws, fs if F > 1 else 0, F
-        j.scale, j.flags = int(scale), int(flags)
-        for k in ("rgba", "graph", "graph_aux", "labels", "polygons", "poly_count"):
+        j.scale, j.flags, j.out_format = int(scale), int(flags), int(out_format)
+        for k in ("rgba", "graph", "graph_aux", "labels", "polygons", "poly_count", "palette", "palette_count"):
             v = outs.get(k)
             if v is not None:
                 assert v.is_contiguous()
             setattr(j, k, _ptr(v))
         return j
 
-    def _alloc(self, F, H, W, scale, want):
-        t, dev = self._torch, self.device
+    @staticmethod
+    def image_shape(F, H, W, scale, out_format):
+        """Shape of the output image tensor `rgba` for a format: (F, sH, sW, 4 | 3) or (F, sH, sW) for INDEX8."""
+        return (F, scale * H, scale * W) + ((_BPP[out_format],) if out_format != OUT_INDEX8 else ())
+
+    def _alloc(self, F, H, W, scale, want, out_format=OUT_RGBA8, host=False):
+        t = self._torch
+
+        def mk(shape, dtype):
+            return t.empty(shape, dtype=dtype).pin_memory() if host else t.empty(shape, dtype=dtype, device=self.device)
+
         o = {}
         if "rgba" in want:
-            o["rgba"] = t.empty((F, scale * H, scale * W, 4), dtype=t.uint8, device=dev)
+            o["rgba"] = mk(self.image_shape(F, H, W, scale, out_format), t.uint8)
+            if out_format == OUT_INDEX8:
+                o["palette"] = mk((F, 256), t.int32)   # RGBA8 words
+                o["palette_count"] = mk((F,), t.int32)
         if "graph" in want:
-            o["graph"] = t.empty((F, H, W), dtype=t.uint8, device=dev)
+            o["graph"] = mk((F, H, W), t.uint8)
         if "graph_aux" in want:
-            o["graph_aux"] = t.empty((F, H, W), dtype=t.uint8, device=dev)
+            o["graph_aux"] = mk((F, H, W), t.uint8)
         if "labels" in want:
-            o["labels"] = t.empty((F, H, W), dtype=t.int32, device=dev)
+            o["labels"] = mk((F, H, W), t.int32)
         if "polygons" in want:
-            o["polygons"] = t.empty((F, H * W, CELL_SLOTS, 2), dtype=t.float32, device=dev)
-            o["poly_count"] = t.empty((F, H * W), dtype=t.int32, device=dev)
+            o["polygons"] = mk((F, H * W, CELL_SLOTS, 2), t.float32)
+            o["poly_count"] = mk((F, H * W), t.int32)
         return o
 
     no_tables = False  # set True to bypass the smoothing tables (geometric path for every smoothed cell) on every call of this context
@@ -224,32 +270,33 @@ class Remaster:
             (FLAG_NO_SMOOTH_TABLES if self.no_tables else 0) | {1: 0, 2: FLAG_AA2, 4: FLAG_AA4}[self.aa]
 
     # -- whole path ------------------------------------------------------------------------
-    def remaster(self, frames, scale=4, subdivide=True, want=("rgba",), out=None, flip_output=False, no_tma=False):
+    def remaster(self, frames, scale=4, subdivide=True, want=("rgba",), out=None, flip_output=False, no_tma=False, out_format=OUT_RGBA8):
         """frames: CUDA uint8 (F, H, W, 3) BGR, row 0 = bottom scanline.  Returns a dict of CUDA tensors
-        for the names in `want` (rgba graph graph_aux labels polygons[+poly_count]); asynchronous."""
+        for the names in `want` (rgba graph graph_aux labels polygons[+poly_count]); asynchronous.  `out_format` chooses the
+        layout of the image `rgba` (OUT_RGBA8, OUT_BGR8, OUT_INDEX8: + `palette` (F, 256) RGBA words, `palette_count` (F,))."""
         F, H, W = frames.shape[:3]
-        o = out if out is not None else self._alloc(F, H, W, scale, want)
-        j = self._job(frames, scale, self._flags(subdivide, flip_output, no_tma), **o)
+        o = out if out is not None else self._alloc(F, H, W, scale, want, out_format)
+        j = self._job(frames, scale, self._flags(subdivide, flip_output, no_tma), out_format, **o)
         self._check(self.lib.par_remaster_device(self.handle, C.byref(j)))
         return o
 
-    def remaster_host(self, frames, scale=4, subdivide=True, want=("rgba",), out=None, flip_output=False):
+    def remaster_host(self, frames, scale=4, subdivide=True, want=("rgba",), out=None, flip_output=False, out_format=OUT_RGBA8):
         """Same through HOST buffers (torch CPU tensors, ideally pinned): H2D, kernels, D2H, synchronize."""
-        t = self._torch
         F, H, W = frames.shape[:3]
         assert not frames.is_cuda
         if out is None:
-            out = {}
-            shapes = {"rgba": ((F, scale * H, scale * W, 4), t.uint8), "graph": ((F, H, W), t.uint8),
-                      "graph_aux": ((F, H, W), t.uint8), "labels": ((F, H, W), t.int32),
-                      "polygons": ((F, H * W, CELL_SLOTS, 2), t.float32)}
-            for k in want:
-                out[k] = t.empty(shapes[k][0], dtype=shapes[k][1]).pin_memory()
-            if "polygons" in want:
-                out["poly_count"] = t.empty((F, H * W), dtype=t.int32).pin_memory()
-        j = self._job(frames, scale, self._flags(subdivide, flip_output, False), **out)
+            out = self._alloc(F, H, W, scale, want, out_format, host=True)
+        j = self._job(frames, scale, self._flags(subdivide, flip_output, False), out_format, **out)
         self._check(self.lib.par_remaster_host(self.handle, C.byref(j)))
         return out
+
+    @staticmethod
+    def expand_indexed(index, palette):
+        """(F, sH, sW) palette indices + (F, 256) RGBA words -> (F, sH, sW, 4) uint8 RGBA (numpy, host side; tests and tools)."""
+        idx = index.cpu().numpy() if hasattr(index, "cpu") else np.asarray(index)
+        pal = (palette.cpu().numpy() if hasattr(palette, "cpu") else np.asarray(palette)).view(np.uint32).reshape(idx.shape[0], 256)
+        rgba = np.take_along_axis(pal, idx.reshape(idx.shape[0], -1).astype(np.int64), axis=1)
+        return rgba.view(np.uint8).reshape(idx.shape + (4,))
 
     # -- single stages (parity tests) ------------------------------------------------------
     def similarity_graph(self, frames, no_tma=False):
@@ -301,13 +348,14 @@ class Remaster:
         self._check(self.lib.par_stage_polygons(self.handle, C.byref(j)))
         return o["polygons"], o["poly_count"]
 
-    def raster(self, frames, graph, scale=4, subdivide=True, flip_output=False, no_tma=False, debug_wide=False):
+    def raster(self, frames, graph, scale=4, subdivide=True, flip_output=False, no_tma=False, debug_wide=False, out_format=OUT_RGBA8):
+        """Stage D+E+raster alone.  Returns the image; for OUT_INDEX8 the dict {rgba, palette, palette_count}."""
         F, H, W = frames.shape[:3]
-        o = self._alloc(F, H, W, scale, ("rgba",))
+        o = self._alloc(F, H, W, scale, ("rgba",), out_format)
         flags = self._flags(subdivide, flip_output, no_tma) | (FLAG_DEBUG_WIDE if debug_wide else 0)
-        j = self._job(frames, scale, flags, graph=graph, **o)
+        j = self._job(frames, scale, flags, out_format, graph=graph, **o)
         self._check(self.lib.par_stage_raster(self.handle, C.byref(j)))
-        return o["rgba"]
+        return o["rgba"] if out_format != OUT_INDEX8 else o
 
 
 class RemasterGroup:
@@ -343,12 +391,46 @@ class RemasterGroup:
     def __exit__(self, *exc):
         self.close()
 
-    def remaster_host(self, image, subdivide=True, want=("rgba", "graph"), flip_output=False, out=None):
+    def strips(self):
+        """The strips as dicts: device, own / load row ranges, and torch tensors ALIASING the strip's device buffers
+        (rows load_begin .. load_end): bgr (rows, W, 3), graph / graph_aux (rows, W), labels (rows, W) int32, and
+        image(out_format) -> (rows * S, W * S, 4 | 3)."""
+        import torch
+        out = []
+        W, S = self.width, self.scale
+        for k in range(self.lib.par_group_n_strips(self.handle)):
+            st = ParStrip()
+            assert self.lib.par_group_strip(self.handle, k, C.byref(st)) == 0
+            rows = st.load_end - st.load_begin
+            dev = "cuda:%d" % st.device
+
+            def view(ptr, shape, typestr, dev=dev):
+                with torch.cuda.device(dev):
+                    return torch.as_tensor(_DeviceBuffer(ptr, shape, typestr), device=dev)
+
+            out.append({"device": st.device, "own": (st.own_begin, st.own_end), "load": (st.load_begin, st.load_end),
+                        "bgr": view(st.bgr, (rows, W, 3), "|u1"), "graph": view(st.graph, (rows, W), "|u1"),
+                        "graph_aux": view(st.graph_aux, (rows, W), "|u1"), "labels": view(st.labels, (rows, W), "<i4"),
+                        "image": (lambda fmt, ptr=st.image, rows=rows, view=view: view(ptr, (rows * S, W * S, _BPP[fmt]), "|u1"))})
+        return out
+
+    def remaster_device(self, subdivide=True, out_format=OUT_RGBA8, want_image=True, want_labels=True, flip_output=False):
+        """The device-resident tiled path (par_group_remaster_device): every strip's own rows are already in its `bgr`
+        buffer (see strips()); results stay on the devices.  Returns (wall_ms, longest strip's device ms)."""
+        flags = (FLAG_SUBDIVIDE if subdivide else 0) | (FLAG_FLIP_OUTPUT if flip_output else 0)
+        st = self.lib.par_group_remaster_device(self.handle, flags, int(out_format), int(bool(want_image)), int(bool(want_labels)))
+        if st != 0:
+            raise RemasterError(st, self.lib.par_group_last_error(self.handle).decode())
+        wall, dev = C.c_double(), C.c_double()
+        self.lib.par_group_last_ms(self.handle, C.byref(wall), C.byref(dev))
+        return wall.value, dev.value
+
+    def remaster_host(self, image, subdivide=True, want=("rgba", "graph"), flip_output=False, out=None, out_format=OUT_RGBA8):
         """image: numpy uint8 (H, W, 3) BGR (row stride may exceed 3*W).  Returns numpy arrays; `out` may supply them
         (e.g. views of pinned memory: pageable buffers limit the copies to a few GB/s)."""
         assert image.dtype == np.uint8 and image.shape[:2] == (self.height, self.width) and image.strides[1:] == (3, 1)
         H, W, S = self.height, self.width, self.scale
-        shapes = {"rgba": ((S * H, S * W, 4), np.uint8), "graph": ((H, W), np.uint8), "graph_aux": ((H, W), np.uint8), "labels": ((H, W), np.int32)}
+        shapes = {"rgba": ((S * H, S * W, _BPP[out_format]), np.uint8), "graph": ((H, W), np.uint8), "graph_aux": ((H, W), np.uint8), "labels": ((H, W), np.int32)}
         if out is None:
             out = {k: np.empty(*shapes[k]) for k in ("rgba", "graph", "graph_aux", "labels") if k in want}
         for k, v in out.items():
@@ -357,6 +439,7 @@ class RemasterGroup:
         j.bgr = image.ctypes.data
         j.width, j.height, j.widthstep, j.frame_stride, j.n_frames = W, H, image.strides[0], 0, 1
         j.scale = S
+        j.out_format = int(out_format)
         j.flags = (FLAG_SUBDIVIDE if subdivide else 0) | (FLAG_FLIP_OUTPUT if flip_output else 0)
         for k, v in out.items():
             setattr(j, k, v.ctypes.data)

@@ -114,7 +114,7 @@ void die( const char* what, const char* msg )
 struct Cache
 {
     par_context* ctx = nullptr;
-    int w = 0, h = 0;
+    int w = 0, h = 0, device = -1;
     uint8_t *d_img = nullptr, *d_graph = nullptr;
     float* d_diagram = nullptr;
     int32_t* d_count = nullptr;
@@ -131,16 +131,18 @@ extern "C" par_point* launch_kernel( float2* pos, uchar4* colorPos, float /*time
     Cache& c = g_cache;
     int dev = 0;
     if( cudaGetDevice( &dev ) != cudaSuccess ) die( "cudaGetDevice", "no CUDA device" );
-    if( !c.ctx || c.w != img_width || c.h != img_height || c.img_bytes != img_bytes )
+    if( !c.ctx || c.w != img_width || c.h != img_height || c.img_bytes != img_bytes || c.device != dev )
     {
         if( c.ctx )
         {
+            cudaSetDevice( c.device ); // (its buffers live there)
             par_destroy( c.ctx );
             cudaFree( c.d_img );
             cudaFree( c.d_graph );
             cudaFree( c.d_diagram );
             cudaFree( c.d_count );
             c = Cache();
+            cudaSetDevice( dev );
         }
         if( par_create( &c.ctx, dev, img_width, img_height, 1 ) != PAR_OK ) die( "par_create", par_last_error( nullptr ) );
         par_set_stream( c.ctx, nullptr ); // the reference runs on the default stream (kernel.cu:402-475)
@@ -152,6 +154,7 @@ extern "C" par_point* launch_kernel( float2* pos, uchar4* colorPos, float /*time
         c.w = img_width;
         c.h = img_height;
         c.img_bytes = img_bytes;
+        c.device = dev;
     }
     cudaError_t e = cudaMemcpy( c.d_img, img_data, img_bytes, cudaMemcpyHostToDevice ); // kernel.cu:319
     if( e != cudaSuccess ) die( "cudaMemcpy H2D", cudaGetErrorString( e ) );

@@ -21,6 +21,24 @@ namespace {
 
 std::string g_create_error;
 
+// every entry point runs on its context's device and leaves the caller's current device as it found it
+struct DeviceGuard
+{
+    int prev = -1;
+    explicit DeviceGuard( int device )
+    {
+        if( cudaGetDevice( &prev ) != cudaSuccess ) prev = -1;
+        if( prev != device ) cudaSetDevice( device );
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if( prev >= 0 ) cudaSetDevice( prev );
+    }
+};
+
+constexpr int kMaxFramesPerLaunch = 65535; // grid.z
+
 typedef CUresult ( *EncodeTiledFn )( CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
@@ -41,6 +59,7 @@ struct par_context
     int device = 0;
     int max_w = 0, max_h = 0, max_frames = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr; // copy_stream: D2H of par_remaster_host
+    int sub_batch = 0; // frames per round of stage launches (0 = the whole batch per launch), par_set_sub_batch
     uint8_t *scratch_aux = nullptr, *scratch_graph = nullptr; // max_frames * max_w * max_h each
     CellRecord* d_tables = nullptr;        // kCellKeys 32-byte records
     uint32_t* d_mask_lut[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // per scale, built on first use
@@ -88,8 +107,12 @@ struct par_context
         spans.push_back( Span{ stage, a, b } );
     }
     // staging for par_remaster_host (grown on demand)
-    uint8_t* h_stage[ 8 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
-    size_t h_stage_bytes[ 8 ] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    uint8_t* h_stage[ 10 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    size_t h_stage_bytes[ 10 ] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    // palette scratch of par_remaster_device (INDEX8): lookup tables and counts, grown on demand
+    uint32_t* d_pal_lut = nullptr;
+    int32_t* d_pal_count = nullptr;
+    int pal_frames = 0;
 
     int fail( par_status st, const char* fmt, ... )
     {
@@ -135,10 +158,57 @@ int check_job( par_context* c, const par_job* j, bool need_bgr )
         if( j->frame_stride != 0 && j->frame_stride < ( size_t )j->widthstep * j->height ) return c->fail( PAR_ERR_INVALID, "frame_stride too small" );
     }
     if( ( size_t )j->width * j->height > ( size_t )1 << 30 ) return c->fail( PAR_ERR_INVALID, "frame too large" );
+    if( j->out_format < PAR_OUT_RGBA8 || j->out_format > PAR_OUT_INDEX8 ) return c->fail( PAR_ERR_INVALID, "unknown out_format %d", j->out_format );
+    return PAR_OK;
+}
+
+int bytes_per_pixel( int out_format ) { return out_format == PAR_OUT_RGBA8 ? 4 : ( out_format == PAR_OUT_BGR8 ? 3 : 1 ); }
+
+// what a raster request needs, checked before anything is launched
+int check_raster( par_context* c, const par_job* j, bool device_pointers )
+{
+    const int aa = ( j->flags & PAR_FLAG_AA4 ) ? 4 : ( ( j->flags & PAR_FLAG_AA2 ) ? 2 : 1 );
+    if( !raster_aa_supported( j->scale, aa ) )
+        return c->fail( PAR_ERR_INVALID, "unsupported scale %d with %dx%d samples per pixel (scale x samples must be an integer 1..8)", j->scale, aa, aa );
+    if( j->out_format == PAR_OUT_INDEX8 && aa != 1 ) return c->fail( PAR_ERR_INVALID, "PAR_OUT_INDEX8 cannot hold anti-aliased output (averaged samples are not palette colours)" );
+    if( device_pointers && ( reinterpret_cast< uintptr_t >( j->rgba ) & 15u ) ) return c->fail( PAR_ERR_INVALID, "the output image must be 16-byte aligned" );
     return PAR_OK;
 }
 
 size_t frame_stride_of( const par_job* j ) { return j->frame_stride ? j->frame_stride : ( size_t )j->widthstep * j->height; }
+
+// frames [f0, f0 + n) of a job as a job of its own (frames are independent units)
+par_job slice_job( const par_job& j, int f0, int n )
+{
+    par_job d = j;
+    const size_t fpx = ( size_t )j.width * j.height, fin = frame_stride_of( &j );
+    const size_t fout = fpx * j.scale * j.scale * bytes_per_pixel( j.out_format );
+    d.n_frames = n;
+    d.frame_stride = fin;
+    if( j.bgr ) d.bgr = j.bgr + ( size_t )f0 * fin;
+    if( j.rgba ) d.rgba = j.rgba + ( size_t )f0 * fout;
+    if( j.graph ) d.graph = j.graph + ( size_t )f0 * fpx;
+    if( j.graph_aux ) d.graph_aux = j.graph_aux + ( size_t )f0 * fpx;
+    if( j.labels ) d.labels = j.labels + ( size_t )f0 * fpx;
+    if( j.polygons ) d.polygons = j.polygons + ( size_t )f0 * fpx * PAR_CELL_SLOTS * 2;
+    if( j.poly_count ) d.poly_count = j.poly_count + ( size_t )f0 * fpx;
+    if( j.palette ) d.palette = j.palette + ( size_t )f0 * 256;
+    if( j.palette_count ) d.palette_count = j.palette_count + f0;
+    return d;
+}
+
+// a stage over a batch of any size: one launch per kMaxFramesPerLaunch frames
+template< class Run >
+int for_launch_chunks( const par_job* j, Run run )
+{
+    for( int f0 = 0; f0 < j->n_frames; f0 += kMaxFramesPerLaunch )
+    {
+        const par_job d = slice_job( *j, f0, j->n_frames - f0 < kMaxFramesPerLaunch ? j->n_frames - f0 : kMaxFramesPerLaunch );
+        const int st = run( &d );
+        if( st ) return st;
+    }
+    return PAR_OK;
+}
 
 int check_capacity( par_context* c, const par_job* j )
 {
@@ -231,6 +301,9 @@ RasterArgs raster_args( par_context* c, const par_job* j, const uint8_t* graph )
     a.subdivide = ( j->flags & PAR_FLAG_SUBDIVIDE ) ? 1 : 0;
     a.flip_output = ( j->flags & PAR_FLAG_FLIP_OUTPUT ) ? 1 : 0;
     a.debug_force_wide = ( j->flags & PAR_FLAG_DEBUG_WIDE ) ? 1 : 0;
+    a.out_format = j->out_format;
+    a.pal_lut = nullptr;
+    a.pal_count = nullptr;
     return a;
 }
 
@@ -244,13 +317,37 @@ int run_polygons( par_context* c, const par_job* j, const uint8_t* graph )
     return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "polygons" );
 }
 
-int run_raster( par_context* c, const par_job* j, const uint8_t* graph )
+// colour -> palette index tables of the job's frames (INDEX8) into lut / count; the palette itself into j->palette
+int run_palette( par_context* c, const par_job* j, uint32_t* lut, int32_t* count )
+{
+    PaletteArgs p;
+    p.bgr = j->bgr;
+    p.width = j->width;
+    p.height = j->height;
+    p.widthstep = j->widthstep;
+    p.n_frames = j->n_frames;
+    p.frame_stride = frame_stride_of( j );
+    p.lut = lut;
+    p.count = count;
+    p.palette = j->palette;
+    int n = 0;
+    cudaEvent_t t0 = c->span_begin();
+    cudaError_t e = launch_palette( p, c->stream, &n );
+    c->span_end( 5, t0 );
+    c->launches += n;
+    return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "palette" );
+}
+
+int run_raster( par_context* c, const par_job* j, const uint8_t* graph, const uint32_t* pal_lut = nullptr, const int32_t* pal_count = nullptr )
 {
     RasterArgs a = raster_args( c, j, graph );
-    if( !raster_aa_supported( j->scale, a.aa ) )
-        return c->fail( PAR_ERR_INVALID, "unsupported scale %d with %dx%d samples per pixel (scale x samples must be one of 1,2,3,4,6,8)", j->scale,
-                        a.aa, a.aa );
+    int st = check_raster( c, j, true );
+    if( st ) return st;
+    if( j->out_format == PAR_OUT_INDEX8 && ( !pal_lut || !pal_count ) ) return c->fail( PAR_ERR_INVALID, "PAR_OUT_INDEX8 needs the palette stage" );
+    a.pal_lut = pal_lut;
+    a.pal_count = pal_count;
     const int S = a.scale; // the sampling scale: tables and tile shapes depend on it
+    bool built = false;
     if( !c->d_mask_lut[ S ] )
     {
         // coverage masks of the 4096 plain hulls at this scale, computed once by the device's own coverage code
@@ -258,6 +355,7 @@ int run_raster( par_context* c, const par_job* j, const uint8_t* graph )
         if( le == cudaSuccess ) le = launch_build_mask_lut( S, c->tables(), c->d_mask_lut[ S ], c->stream );
         c->launches++;
         if( le != cudaSuccess ) return c->cuda_fail( le, "mask table" );
+        built = true;
     }
     a.mask_lut = c->d_mask_lut[ S ];
     a.smooth = SmoothTablePtrs{ c->d_smooth_rec, nullptr, nullptr };
@@ -280,9 +378,16 @@ int run_raster( par_context* c, const par_job* j, const uint8_t* graph )
                 c->d_cut[ S ] = nullptr;
                 return c->cuda_fail( me, "smoothing tables" );
             }
+            built = true;
         }
         a.smooth.cut = c->d_cut[ S ];
         a.smooth.link = c->d_link[ S ];
+    }
+    if( built )
+    {
+        // the tables were built on the stream that is current NOW; a later par_set_stream must find them complete
+        cudaError_t se = cudaStreamSynchronize( c->stream );
+        if( se != cudaSuccess ) return c->cuda_fail( se, "table build" );
     }
     CUtensorMap map;
     uint32_t box[ 3 ];
@@ -329,7 +434,8 @@ int par_create( par_context** out, int device, int max_width, int max_height, in
     c->max_w = max_width;
     c->max_h = max_height;
     c->max_frames = max_frames;
-    cudaError_t e = cudaSetDevice( device );
+    DeviceGuard guard( device );
+    cudaError_t e = cudaSuccess;
     if( e == cudaSuccess ) e = cudaStreamCreateWithFlags( &c->own_stream, cudaStreamNonBlocking );
     c->stream = c->own_stream;
     size_t px = ( size_t )max_width * max_height * max_frames;
@@ -372,7 +478,7 @@ int par_create( par_context** out, int device, int max_width, int max_height, in
 void par_destroy( par_context* c )
 {
     if( !c ) return;
-    cudaSetDevice( c->device );
+    DeviceGuard guard( c->device );
     if( c->own_stream )
     {
         cudaStreamSynchronize( c->own_stream );
@@ -388,7 +494,9 @@ void par_destroy( par_context* c )
     cudaFree( c->d_smooth_rec );
     cudaFree( c->d_link_classes );
     cudaFree( c->d_smooth_stats );
-    for( int k = 0; k < 8; k++ ) cudaFree( c->h_stage[ k ] );
+    cudaFree( c->d_pal_lut );
+    cudaFree( c->d_pal_count );
+    for( int k = 0; k < 10; k++ ) cudaFree( c->h_stage[ k ] );
     for( auto& sp : c->spans )
     {
         cudaEventDestroy( sp.a );
@@ -416,6 +524,13 @@ int par_use_own_stream( par_context* c )
     return PAR_OK;
 }
 
+int par_set_sub_batch( par_context* c, int frames )
+{
+    if( !c || frames < 0 ) return PAR_ERR_INVALID;
+    c->sub_batch = frames;
+    return PAR_OK;
+}
+
 int par_profile_enable( par_context* c, int on )
 {
     if( !c ) return PAR_ERR_INVALID;
@@ -426,7 +541,7 @@ int par_profile_enable( par_context* c, int on )
 int par_profile_read( par_context* c, double* total_ms, int* launches )
 {
     if( !c ) return PAR_ERR_INVALID;
-    cudaSetDevice( c->device );
+    DeviceGuard guard( c->device );
     cudaError_t e = cudaStreamSynchronize( c->stream );
     if( e != cudaSuccess ) return c->cuda_fail( e, "profile_read" );
     for( int k = 0; k < PAR_N_STAGES; k++ )
@@ -450,7 +565,7 @@ int par_profile_read( par_context* c, double* total_ms, int* launches )
 int par_smooth_stats( par_context* c, uint64_t* out2 )
 {
     if( !c || !out2 ) return PAR_ERR_INVALID;
-    cudaSetDevice( c->device );
+    DeviceGuard guard( c->device );
     cudaError_t e = cudaStreamSynchronize( c->stream );
     unsigned long long h[ 2 ] = { 0, 0 };
     if( e == cudaSuccess ) e = cudaMemcpy( h, c->d_smooth_stats, sizeof( h ), cudaMemcpyDeviceToHost );
@@ -462,6 +577,7 @@ int par_smooth_stats( par_context* c, uint64_t* out2 )
 int par_synchronize( par_context* c )
 {
     if( !c ) return PAR_ERR_INVALID;
+    DeviceGuard guard( c->device );
     cudaError_t e = cudaStreamSynchronize( c->stream );
     return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "synchronize" );
 }
@@ -471,8 +587,8 @@ int par_stage_similarity_graph( par_context* c, const par_job* j )
     int st = check_job( c, j, true );
     if( st ) return st;
     if( !j->graph_aux ) return c->fail( PAR_ERR_INVALID, "graph_aux is NULL" );
-    cudaSetDevice( c->device );
-    return run_similarity( c, j, j->graph_aux );
+    DeviceGuard guard( c->device );
+    return for_launch_chunks( j, [ & ]( const par_job* d ) { return run_similarity( c, d, d->graph_aux ); } );
 }
 
 int par_stage_resolve_crossings( par_context* c, const par_job* j )
@@ -480,8 +596,8 @@ int par_stage_resolve_crossings( par_context* c, const par_job* j )
     int st = check_job( c, j, false );
     if( st ) return st;
     if( !j->graph_aux || !j->graph ) return c->fail( PAR_ERR_INVALID, "graph_aux / graph is NULL" );
-    cudaSetDevice( c->device );
-    return run_crossings( c, j, j->graph_aux, j->graph );
+    DeviceGuard guard( c->device );
+    return for_launch_chunks( j, [ & ]( const par_job* d ) { return run_crossings( c, d, d->graph_aux, d->graph ); } );
 }
 
 int par_stage_cc_labels( par_context* c, const par_job* j )
@@ -489,8 +605,8 @@ int par_stage_cc_labels( par_context* c, const par_job* j )
     int st = check_job( c, j, false );
     if( st ) return st;
     if( !j->graph || !j->labels ) return c->fail( PAR_ERR_INVALID, "graph / labels is NULL" );
-    cudaSetDevice( c->device );
-    return run_labels( c, j, j->graph, j->labels );
+    DeviceGuard guard( c->device );
+    return for_launch_chunks( j, [ & ]( const par_job* d ) { return run_labels( c, d, d->graph, d->labels ); } );
 }
 
 int par_stage_polygons( par_context* c, const par_job* j )
@@ -498,8 +614,24 @@ int par_stage_polygons( par_context* c, const par_job* j )
     int st = check_job( c, j, true );
     if( st ) return st;
     if( !j->graph || !j->polygons ) return c->fail( PAR_ERR_INVALID, "graph / polygons is NULL" );
-    cudaSetDevice( c->device );
-    return run_polygons( c, j, j->graph );
+    DeviceGuard guard( c->device );
+    return for_launch_chunks( j, [ & ]( const par_job* d ) { return run_polygons( c, d, d->graph ); } );
+}
+
+// palette scratch for n frames (INDEX8)
+static int ensure_palette_scratch( par_context* c, int n_frames )
+{
+    if( n_frames <= c->pal_frames ) return PAR_OK;
+    cudaFree( c->d_pal_lut );
+    cudaFree( c->d_pal_count );
+    c->d_pal_lut = nullptr;
+    c->d_pal_count = nullptr;
+    c->pal_frames = 0;
+    cudaError_t e = cudaMalloc( &c->d_pal_lut, ( size_t )n_frames * kPaletteSlots * sizeof( uint32_t ) );
+    if( e == cudaSuccess ) e = cudaMalloc( &c->d_pal_count, ( size_t )n_frames * sizeof( int32_t ) );
+    if( e != cudaSuccess ) return c->cuda_fail( e, "palette scratch" );
+    c->pal_frames = n_frames;
+    return PAR_OK;
 }
 
 int par_stage_raster( par_context* c, const par_job* j )
@@ -507,8 +639,15 @@ int par_stage_raster( par_context* c, const par_job* j )
     int st = check_job( c, j, true );
     if( st ) return st;
     if( !j->graph || !j->rgba ) return c->fail( PAR_ERR_INVALID, "graph / rgba is NULL" );
-    cudaSetDevice( c->device );
-    return run_raster( c, j, j->graph );
+    if( ( st = check_raster( c, j, true ) ) ) return st;
+    DeviceGuard guard( c->device );
+    if( j->out_format == PAR_OUT_INDEX8 && ( st = ensure_palette_scratch( c, j->n_frames < kMaxFramesPerLaunch ? j->n_frames : kMaxFramesPerLaunch ) ) ) return st;
+    return for_launch_chunks( j, [ & ]( const par_job* d ) {
+        if( d->out_format != PAR_OUT_INDEX8 ) return run_raster( c, d, d->graph );
+        int32_t* count = d->palette_count ? d->palette_count : c->d_pal_count;
+        int s2 = run_palette( c, d, c->d_pal_lut, count );
+        return s2 ? s2 : run_raster( c, d, d->graph, c->d_pal_lut, count );
+    } );
 }
 
 int par_border_walks( par_context* c, const uint8_t* graph, const int32_t* labels, int width, int height, int n_frames, int32_t* walk_len,
@@ -518,7 +657,7 @@ int par_border_walks( par_context* c, const uint8_t* graph, const int32_t* label
     if( !graph || !labels || !walk_len || !walk_begin || !walk_nodes || !total ) return c->fail( PAR_ERR_INVALID, "border_walks: NULL pointer" );
     if( width <= 0 || height <= 0 || n_frames <= 0 || capacity_per_frame <= 0 ) return c->fail( PAR_ERR_INVALID, "border_walks: empty frame, batch or capacity" );
     if( ( size_t )width * height > ( size_t )1 << 30 ) return c->fail( PAR_ERR_INVALID, "frame too large" );
-    cudaSetDevice( c->device );
+    DeviceGuard guard( c->device );
     cudaError_t e = launch_border_walks( graph, labels, width, height, n_frames, walk_len, walk_begin, total, walk_nodes, capacity_per_frame, c->stream );
     c->launches += 3 * ( ( n_frames + 65534 ) / 65535 );
     return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "border_walks" );
@@ -528,28 +667,36 @@ int par_remaster_device( par_context* c, const par_job* j )
 {
     int st = check_job( c, j, true );
     if( st ) return st;
-    cudaSetDevice( c->device );
-    uint8_t* aux = j->graph_aux;
-    uint8_t* graph = j->graph;
-    if( !aux || !graph )
+    DeviceGuard guard( c->device );
+    par_job job = *j;
+    if( !job.graph_aux || !job.graph )
     {
         st = check_capacity( c, j );
         if( st ) return st;
-        if( !aux ) aux = c->scratch_aux;
-        if( !graph ) graph = c->scratch_graph;
+        if( !job.graph_aux ) job.graph_aux = c->scratch_aux;
+        if( !job.graph ) job.graph = c->scratch_graph;
     }
-    if( j->rgba ) // refuse an impossible raster request before anything is launched
+    if( job.rgba && ( st = check_raster( c, j, true ) ) ) return st; // refuse an impossible raster request before anything is launched
+    // Frames are independent, so the batch may run in rounds of `sub_batch` frames through all stages: the 2 bytes per
+    // pixel of intermediates (graph_aux, graph) of a round are then still in L2 when the next stage reads them.
+    int round = c->sub_batch > 0 ? c->sub_batch : job.n_frames;
+    if( round > kMaxFramesPerLaunch ) round = kMaxFramesPerLaunch;
+    const bool indexed = job.rgba && job.out_format == PAR_OUT_INDEX8;
+    if( indexed && ( st = ensure_palette_scratch( c, round < job.n_frames ? round : job.n_frames ) ) ) return st;
+    for( int f0 = 0; f0 < job.n_frames; f0 += round )
     {
-        const int aa = ( j->flags & PAR_FLAG_AA4 ) ? 4 : ( ( j->flags & PAR_FLAG_AA2 ) ? 2 : 1 );
-        if( !raster_aa_supported( j->scale, aa ) )
-            return c->fail( PAR_ERR_INVALID, "unsupported scale %d with %dx%d samples per pixel (scale x samples must be one of 1,2,3,4,6,8)", j->scale,
-                            aa, aa );
+        const par_job d = slice_job( job, f0, job.n_frames - f0 < round ? job.n_frames - f0 : round );
+        if( ( st = run_similarity( c, &d, d.graph_aux ) ) ) return st;
+        if( ( st = run_crossings( c, &d, d.graph_aux, d.graph ) ) ) return st;
+        if( d.labels && ( st = run_labels( c, &d, d.graph, d.labels ) ) ) return st;
+        if( d.polygons && ( st = run_polygons( c, &d, d.graph ) ) ) return st;
+        if( d.rgba )
+        {
+            int32_t* count = d.palette_count ? d.palette_count : c->d_pal_count;
+            if( indexed && ( st = run_palette( c, &d, c->d_pal_lut, count ) ) ) return st;
+            if( ( st = run_raster( c, &d, d.graph, indexed ? c->d_pal_lut : nullptr, indexed ? count : nullptr ) ) ) return st;
+        }
     }
-    if( ( st = run_similarity( c, j, aux ) ) ) return st;
-    if( ( st = run_crossings( c, j, aux, graph ) ) ) return st;
-    if( j->labels && ( st = run_labels( c, j, graph, j->labels ) ) ) return st;
-    if( j->polygons && ( st = run_polygons( c, j, graph ) ) ) return st;
-    if( j->rgba && ( st = run_raster( c, j, graph ) ) ) return st;
     return PAR_OK;
 }
 
@@ -557,19 +704,24 @@ int par_remaster_host( par_context* c, const par_job* j )
 {
     int st = check_job( c, j, true );
     if( st ) return st;
-    cudaSetDevice( c->device );
+    if( j->rgba && ( st = check_raster( c, j, false ) ) ) return st; // (before the staging buffers are sized from the scale)
+    DeviceGuard guard( c->device );
     const size_t px = ( size_t )j->width * j->height * j->n_frames;
     const size_t in_bytes = frame_stride_of( j ) * j->n_frames;
     const size_t out_px = px * j->scale * j->scale;
-    // device staging: 0 bgr, 1 rgba, 2 graph, 3 graph_aux, 4 labels, 5 polygons, 6 poly_count
-    const size_t need[ 7 ] = { in_bytes + 16,
-                               j->rgba ? out_px * 4 : 0,
+    const int bpp = bytes_per_pixel( j->out_format );
+    const bool indexed = j->rgba && j->out_format == PAR_OUT_INDEX8;
+    // device staging: 0 bgr, 1 image, 2 graph, 3 graph_aux, 4 labels, 5 polygons, 6 poly_count, 7 palette, 8 palette_count
+    const size_t need[ 9 ] = { in_bytes + 16,
+                               j->rgba ? out_px * bpp : 0,
                                px,
                                px,
                                j->labels ? px * 4 : 0,
                                j->polygons ? px * PAR_CELL_SLOTS * 2 * sizeof( float ) : 0,
-                               ( j->polygons && j->poly_count ) ? px * 4 : 0 };
-    for( int k = 0; k < 7; k++ )
+                               ( j->polygons && j->poly_count ) ? px * 4 : 0,
+                               indexed ? ( size_t )j->n_frames * 256 * 4 : 0,
+                               indexed ? ( size_t )j->n_frames * 4 : 0 };
+    for( int k = 0; k < 9; k++ )
         if( need[ k ] > c->h_stage_bytes[ k ] )
         {
             cudaFree( c->h_stage[ k ] );
@@ -587,8 +739,8 @@ int par_remaster_host( par_context* c, const par_job* j )
         cudaError_t se = cudaStreamCreateWithFlags( &c->copy_stream, cudaStreamNonBlocking );
         if( se != cudaSuccess ) return c->cuda_fail( se, "copy stream" );
     }
-    const size_t fpx = ( size_t )j->width * j->height, fin = frame_stride_of( j ), fout = fpx * j->scale * j->scale * 4;
-    const int n_chunks = j->n_frames >= 64 ? 8 : 1;
+    const size_t fpx = ( size_t )j->width * j->height, fin = frame_stride_of( j ), fout = fpx * j->scale * j->scale * bpp;
+    const int n_chunks = j->n_frames >= 512 ? 16 : ( j->n_frames >= 64 ? 8 : 1 );
     std::vector< cudaEvent_t > done;
     cudaError_t e = cudaSuccess;
     for( int k = 0; k < n_chunks && e == cudaSuccess; k++ )
@@ -610,6 +762,8 @@ int par_remaster_host( par_context* c, const par_job* j )
         d.labels = j->labels ? reinterpret_cast< int32_t* >( c->h_stage[ 4 ] ) + f0 * fpx : nullptr;
         d.polygons = j->polygons ? reinterpret_cast< float* >( c->h_stage[ 5 ] ) + f0 * fpx * PAR_CELL_SLOTS * 2 : nullptr;
         d.poly_count = ( j->polygons && j->poly_count ) ? reinterpret_cast< int32_t* >( c->h_stage[ 6 ] ) + f0 * fpx : nullptr;
+        d.palette = indexed ? reinterpret_cast< uint32_t* >( c->h_stage[ 7 ] ) + ( size_t )f0 * 256 : nullptr;
+        d.palette_count = indexed ? reinterpret_cast< int32_t* >( c->h_stage[ 8 ] ) + f0 : nullptr;
         if( ( st = par_remaster_device( c, &d ) ) ) return st;
         cudaEvent_t ev = c->get_event();
         done.push_back( ev );
@@ -624,6 +778,8 @@ int par_remaster_host( par_context* c, const par_job* j )
             e = cudaMemcpyAsync( j->polygons + f0 * fpx * PAR_CELL_SLOTS * 2, d.polygons, nf * fpx * PAR_CELL_SLOTS * 2 * sizeof( float ),
                                  cudaMemcpyDeviceToHost, cs );
         if( e == cudaSuccess && d.poly_count ) e = cudaMemcpyAsync( j->poly_count + f0 * fpx, d.poly_count, nf * fpx * 4, cudaMemcpyDeviceToHost, cs );
+        if( e == cudaSuccess && indexed && j->palette ) e = cudaMemcpyAsync( j->palette + ( size_t )f0 * 256, d.palette, nf * 256 * 4, cudaMemcpyDeviceToHost, cs );
+        if( e == cudaSuccess && indexed && j->palette_count ) e = cudaMemcpyAsync( j->palette_count + f0, d.palette_count, nf * 4, cudaMemcpyDeviceToHost, cs );
     }
     cudaError_t e2 = cudaStreamSynchronize( c->copy_stream );
     cudaError_t e3 = cudaStreamSynchronize( c->stream );

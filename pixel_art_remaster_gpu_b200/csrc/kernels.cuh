@@ -1,5 +1,6 @@
 // Launch interfaces of the sm_100a kernels (one translation unit per stage).
 #pragma once
+#include "../../include/pixelart_b200.h"
 #include "common.cuh"
 #include "polygon.cuh"
 #include "smooth_table.h"
@@ -55,7 +56,24 @@ struct RasterArgs
     int subdivide;
     int flip_output;
     int debug_force_wide; // test hook: treat every cell as reaching beyond its mask (exercises the exact slow path)
+    int out_format;       // par_out_format of `rgba`
+    const uint32_t* pal_lut;  // INDEX8: per frame kPaletteSlots words index << 24 | colour (palette_kernels.cu)
+    const int32_t* pal_count; // INDEX8: colours per frame (> 256: the frame's index image is undefined)
 };
+
+// per-frame colour -> palette index lookup table (open addressing, linear probing)
+constexpr int kPaletteSlots = 1024;
+struct PaletteArgs
+{
+    const uint8_t* bgr;
+    int width, height, widthstep, n_frames;
+    size_t frame_stride;
+    uint32_t* lut;       // [n_frames][kPaletteSlots] scratch -> out: index << 24 | (R | G << 8 | B << 16), empty 0xFFFFFFFF
+    int32_t* count;      // [n_frames] out: colours incl. black
+    uint32_t* palette;   // [n_frames][256] out: RGBA8 words, ascending by B << 16 | G << 8 | R; may be null
+};
+// returns the number of kernels launched through *n_launches
+cudaError_t launch_palette( const PaletteArgs& a, cudaStream_t stream, int* n_launches );
 
 dim3 similarity_graph_grid( int width, int height, int n_frames );
 void similarity_graph_tma_box( uint32_t box[ 3 ] );
@@ -79,6 +97,8 @@ cudaError_t launch_build_smooth_tables( int scale, const CellTablePtrs& tab, con
 cudaError_t launch_build_mask_lut( int scale, const CellTablePtrs& tab, uint32_t* lut, cudaStream_t stream );
 void raster_img_tma_box( int scale, uint32_t box[ 3 ] );
 cudaError_t launch_raster( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream );
+cudaError_t launch_raster_bgr8( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream );
+cudaError_t launch_raster_index8( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream );
 bool raster_scale_supported( int scale );
 bool raster_aa_supported( int out_scale, int aa );
 

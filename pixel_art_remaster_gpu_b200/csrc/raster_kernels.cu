@@ -29,1155 +29,11 @@
 // the masks are kept in a "window form" whose fields are already positioned on the reader's pixels) and writes whole
 // output-row segments with 128-bit streaming stores; with anti-aliasing on, A x A samples are averaged right there.
 // Algorithmic HBM traffic: 3 B/px colour + 1 B/px graph in, 4*s*s B/px out.
-#include "kernels.cuh"
-#include "polygon.cuh"
-
+#include "raster_impl.cuh"
 
 namespace par {
 
 namespace {
-
-constexpr int kThreads = 256;
-constexpr int kMaxVerts = 16;    // 8 hull vertices, each replaced by at most two
-constexpr int kGeoThreads = 128; // threads that take part in the (rare) geometric path: one vertex buffer each
-
-template< int S >
-struct Cfg
-{
-    // A subdivided cell normally reaches at most 22/64 pixel outside its own square (hull vertices reach
-    // 1/4; blending with a neighbour's cut point adds a little).  H = number of samples per side within
-    // that reach: the smallest H whose next sample offset (2H+1)/(2S) exceeds 22/64.  A cell that reaches
-    // further ("wide": only possible when the reference's getPointIndex falls back to vertex 0,
-    // subdivision_functions.cu:537) is flagged and handled exactly by the slow path of the resolve step.
-    static constexpr int H = 11 * S >= 16 ? ( 11 * S - 16 ) / 32 + 1 : 0;
-    static constexpr int R = S + 2 * H;                   // samples per axis covered by a cell's mask
-    // integer units: when S divides 32 a vertex (multiple of 1/64 px) and a sample (odd multiple of
-    // 1/(2S) px) are both integers in units of 1/64 px; otherwise everything is scaled by 2S.
-    static constexpr bool POW2 = ( S & ( S - 1 ) ) == 0 && S <= 32;
-    static constexpr int VM = POW2 ? 1 : 2 * S;           // vertex multiplier
-    static constexpr int SSP = POW2 ? 64 / S : 128;       // distance between samples
-    static constexpr int SSP_LOG2 = SSP == 128 ? 7 : ( SSP == 64 ? 6 : ( SSP == 32 ? 5 : ( SSP == 16 ? 4 : ( SSP == 8 ? 3 : ( SSP == 4 ? 2 : 1 ) ) ) ) );
-    static constexpr int S_FIRST = SSP / 2 - H * SSP;     // coordinate of mask sample 0 (local output index -H)
-    static constexpr int SQUARE = 64 * VM;                // the cell's own square is [0, SQUARE]
-    static constexpr int REACH = H * SSP + SSP / 2;       // offset of the first sample NOT covered by the mask
-    static constexpr bool PACK = R * R <= 63;             // whole mask in one 64-bit word (bit 63 = wide flag)
-    static constexpr int MW = PACK ? 2 : R;               // 32-bit words per mask
-    static constexpr int TW = 32, TH = S <= 4 ? 32 : 16;
-    static constexpr int CW = TW + 2, CH = TH + 2;        // cells whose masks are needed (halo 1)
-    static constexpr int KW = TW + 4, KH = TH + 4;        // cells whose keys and colours are needed (halo 2)
-    static constexpr int GOFF = 16;                       // staged rows begin at column x0 - 16 (TMA: 16-byte aligned start)
-    static constexpr int GP = ( GOFF + TW + 3 + 15 ) / 16 * 16; // staged row pitch (TMA box row), covers x0-3 .. x0+TW+2
-    // staged BGR row (TMA box row): bytes 3*x0-16 .. ; 16 bytes more than needed, because a 128-byte pitch would put every
-    // row on the same banks and the staging pass (a warp reads four rows at once) would take 4-way conflicts
-    static constexpr int RAWP = ( 16 + 3 * ( TW + 2 ) + 15 ) / 16 * 16 + ( ( 16 + 3 * ( TW + 2 ) + 15 ) / 16 * 16 % 128 == 0 ? 16 : 0 );
-    static constexpr int RAWOFF = 16 - 6;                 // byte offset of pixel x0-2 in a staged row
-    static constexpr int NC = CW * CH;
-    static constexpr uint32_t FULL = ( 1u << S ) - 1u;
-    static constexpr uint32_t ROWMASK = ( 1u << R ) - 1u;
-    static constexpr uint32_t WIDE = PACK ? 0x40000000u : 0x80000000u; // flag in the high word (PACK, window form) / in row 0 (rows)
-    // PACK masks live in shared memory and in the tables in WINDOW form (to_window below): four 16-bit fields, each
-    // already positioned on the S x S output pixels (bit S*y + x) of the cell whose resolver will read it:
-    //   lo[0,16)  F0 the cell's own S x S samples
-    //   lo[16,32) F1 bit S*y+S-1 <- halo sample (-1, y): it lies in the LEFT neighbour's square, last column there;
-    //                bit S*y     <- halo sample (S, y): first column of the RIGHT neighbour's square
-    //   hi[0,16)  F2 bit S*(S-1)+x <- halo sample (x, -1): top row of the square BELOW; bit x <- (x, S): bottom row ABOVE
-    //   hi[16,32) F3 the four corner halo samples: bit S*S-1 <- (-1,-1), bit S*(S-1) <- (S,-1), bit S-1 <- (-1,S),
-    //                bit 0 <- (S,S); bit 14 = WIDE
-    static constexpr uint32_t ALL = PACK ? ( 1u << ( S * S ) ) - 1u : 0u;
-    static constexpr uint32_t M_COL0 = S == 1 ? 1u : ( S == 2 ? 0x5u : ( S == 3 ? 0x49u : 0x1111u ) ); // bits S*y, y < S
-    static constexpr uint32_t M_LEFTCOL = M_COL0;                       // my column 0   <- F1 of the cell to the left
-    static constexpr uint32_t M_RIGHTCOL = M_COL0 << ( S - 1 );         // my column S-1 <- F1 of the cell to the right
-    static constexpr uint32_t M_BOTROW = ( 1u << S ) - 1u;              // my row 0      <- F2 of the cell below
-    static constexpr uint32_t M_TOPROW = M_BOTROW << ( S * ( S - 1 ) ); // my row S-1    <- F2 of the cell above
-    // Shared memory carve-up (bytes).  The first region has two lives: (1) the staged graph and BGR rows (the TMA
-    // destinations) until the staging pass has turned them into keys and colours; (2) the geometric path's vertex
-    // buffers next to the list of cells queued for it.  Keeping the CTA at 24 KB lets five of them share an SM with
-    // 124 KB left as L1 for the tables — the kernel is sensitive to both.
-    static constexpr int off_graph = 0;
-    static constexpr int off_raw = ( KH * GP + 127 ) / 128 * 128;
-    static constexpr int off_vbuf = 0;
-    static constexpr int off_work = ( kMaxVerts * kGeoThreads * 2 + 15 ) / 16 * 16;
-    static constexpr int sz_stage = off_raw + KH * RAWP, sz_lists = off_work + NC * 2;
-    static constexpr int off_keys = ( ( sz_stage > sz_lists ? sz_stage : sz_lists ) + 127 ) / 128 * 128;
-    static constexpr int off_col = off_keys + ( KW * KH * 2 + 15 ) / 16 * 16;
-    static constexpr int off_mask = off_col + KW * KH * 4;
-    static constexpr int off_bar = ( off_mask + NC * MW * 4 + 15 ) / 16 * 16;
-    static constexpr int off_nwork = off_bar + 16; // four counters / flags
-    static constexpr int smem_bytes = off_nwork + 16 + 4 * ( ( NC + kThreads - 1 ) / kThreads ) * ( kThreads / 32 ); // counters, then the ballots of the mask pass
-};
-
-// number of sample columns c in [0,N) with F - c*G > 0, i.e. clamp(ceil(F/G), 0, N), G > 0
-template< int S, int N >
-__device__ __forceinline__ int columns_left_of( int F, int G, float rcpG )
-{
-    if( Cfg< S >::POW2 )
-    {
-        // (F - 1/2)/G is never an integer and stays >= 1/(2G) >= 4e-5 away from one, far more than the error of
-        // the approximate reciprocal on a quotient of magnitude <= N, so the floor is exact (G <= 64*154).
-        const int q = __float2int_rd( ( ( float )F - 0.5f ) * rcpG ) + 1;
-        return min( max( q, 0 ), N );
-    }
-    int cnt = 0;
-#pragma unroll
-    for( int c = 0; c < N; c++ ) cnt += ( F > c * G ) ? 1 : 0;
-    return cnt;
-}
-
-// Toggle, on every sample row an edge crosses, the samples strictly left of the crossing (even-odd rule with
-// the (+eps, -eps^2) displacement).  Sample (c, r) sits at (ox + SSP c, oy + SSP r).  Row r is crossed iff
-// min(y0,y1) < y_r <= max(y0,y1), which is the (y0 < y) != (y1 < y) rule.
-template< int S, int N, class Toggle >
-__device__ __forceinline__ void cover_edge( int ox, int oy, int x0, int y0, int x1, int y1, Toggle& toggle )
-{
-    typedef Cfg< S > C;
-    const int dy = y1 - y0;
-    if( dy == 0 ) return;
-    const int dx = x1 - x0;
-    const int r_lo = max( ( ( min( y0, y1 ) - oy ) >> C::SSP_LOG2 ) + 1, 0 );
-    const int r_hi = min( ( max( y0, y1 ) - oy ) >> C::SSP_LOG2, N - 1 );
-    const int G = C::SSP * ( dy < 0 ? -dy : dy );                 // F decreases by G per sample column
-    const int step = dy < 0 ? -C::SSP * dx : C::SSP * dx;          // F increases by step per sample row
-    int F = dx * ( oy - y0 ) - ( ox - x0 ) * dy;                   // edge function at sample (0, 0) ...
-    F = ( dy < 0 ? -F : F ) + r_lo * step;                         // ... oriented, at row r_lo
-    const float rcpG = __fdividef( 1.0f, ( float )G );
-#pragma unroll 1
-    for( int r = r_lo; r <= r_hi; r++, F += step ) toggle( r, columns_left_of< S, N >( F, G, rcpG ) );
-}
-
-template< int R >
-struct PackedToggle // R x R mask in one 64-bit register, row r at bits [R r, R r + R)
-{
-    uint64_t m;
-    __device__ __forceinline__ void operator()( int r, int cnt ) { m ^= ( uint64_t )( ( 1u << cnt ) - 1u ) << ( R * r ); }
-};
-struct RowToggle // rows in memory (shared memory on the fast path), row r at rows[r * stride]
-{
-    uint32_t* rows;
-    int stride;
-    __device__ __forceinline__ void operator()( int r, int cnt ) { rows[ r * stride ] ^= ( 1u << cnt ) - 1u; }
-};
-
-// R-stride packed mask (bit R*r + c = sample (c - H, r - H)) -> window form (see Cfg)
-template< int S >
-__device__ __forceinline__ uint2 to_window( uint64_t m )
-{
-    typedef Cfg< S > C;
-    constexpr int R = C::R, H = C::H;
-    uint32_t f0 = 0u, f1 = 0u, f2 = 0u, f3 = 0u;
-#pragma unroll
-    for( int y = 0; y < S; y++ )
-    {
-        const uint32_t row = ( uint32_t )( m >> ( R * ( y + H ) ) );
-        f0 |= ( ( row >> H ) & C::FULL ) << ( S * y );
-        if( H > 0 )
-        {
-            f1 |= ( row & 1u ) << ( S * y + S - 1 );
-            f1 |= ( ( row >> ( S + H ) ) & 1u ) << ( S * y );
-        }
-    }
-    if( H > 0 )
-    {
-        const uint32_t bot = ( uint32_t )m, top = ( uint32_t )( m >> ( R * ( S + H ) ) );
-        f2 = ( ( ( bot >> H ) & C::FULL ) << ( S * ( S - 1 ) ) ) | ( ( top >> H ) & C::FULL );
-        f3 = ( ( bot & 1u ) << ( S * S - 1 ) ) | ( ( ( bot >> ( S + H ) ) & 1u ) << ( S * ( S - 1 ) ) ) | ( ( top & 1u ) << ( S - 1 ) ) |
-             ( ( top >> ( S + H ) ) & 1u );
-    }
-    return make_uint2( f0 | f1 << 16, f2 | f3 << 16 );
-}
-
-// Slots of build_cell_polygon in a small buffer (slot k at buf[k * stride]), packed as (x64 + 64) << 8 | (y64 + 64)
-struct PackedSlots
-{
-    uint16_t* buf;
-    int stride;
-    __device__ __forceinline__ void put( int slot, int x64, int y64 ) { buf[ slot * stride ] = ( uint16_t )( ( ( x64 + 64 ) << 8 ) | ( y64 + 64 ) ); }
-};
-
-// Coverage of the polygon held in `slots` over an N x N sample window whose sample (0,0) sits at (ox, oy).
-// Returns the polygon's coordinate range through lo/hi (vertex units, i.e. already multiplied by VM).
-template< int S, int N, class Toggle >
-__device__ __forceinline__ void cover_polygon( const uint16_t* buf, int stride, CellPoly poly, int ox, int oy, Toggle& toggle, int& lo, int& hi )
-{
-    constexpr int VM = Cfg< S >::VM;
-    uint32_t v = buf[ 0 ];
-    int x0 = ( ( int )( v >> 8 ) - 64 ) * VM, y0 = ( ( int )( v & 255u ) - 64 ) * VM;
-    const int fx = x0, fy = y0;
-    lo = min( x0, y0 );
-    hi = max( x0, y0 );
-    const int last = 2 * poly.n - 1 - ( int )( ( ~poly.two >> ( poly.n - 1 ) ) & 1u ); // last occupied slot
-    int slot = 0;
-#pragma unroll 1
-    while( true )
-    {
-        // next occupied slot: 2t+1 follows 2t only when hull vertex t was split
-        const bool done = slot == last;
-        slot = ( ( slot & 1 ) || !( ( poly.two >> ( slot >> 1 ) ) & 1u ) ) ? ( slot | 1 ) + 1 : slot + 1;
-        int x1 = fx, y1 = fy;
-        if( !done )
-        {
-            v = buf[ slot * stride ];
-            x1 = ( ( int )( v >> 8 ) - 64 ) * VM;
-            y1 = ( ( int )( v & 255u ) - 64 ) * VM;
-            lo = min( lo, min( x1, y1 ) );
-            hi = max( hi, max( x1, y1 ) );
-        }
-        cover_edge< S, N >( ox, oy, x0, y0, x1, y1, toggle );
-        if( done ) break;
-        x0 = x1;
-        y0 = y1;
-    }
-}
-
-// next free slot of a shared-memory list, for the lanes that call it together: one atomic per warp
-__device__ __forceinline__ int warp_slot( int* counter )
-{
-    const uint32_t peers = __activemask();
-    const uint32_t lane = threadIdx.x & 31u;
-    int base = 0;
-    if( lane == ( uint32_t )__ffs( ( int )peers ) - 1u ) base = atomicAdd( counter, __popc( peers ) );
-    base = __shfl_sync( peers, base, __ffs( ( int )peers ) - 1 );
-    return base + __popc( peers & ( ( 1u << lane ) - 1u ) );
-}
-
-// one output row segment of a source pixel: S RGBA words, widest stores the alignment allows
-template< int S >
-__device__ __forceinline__ void store_row( uint8_t* dst, const uint32_t* px )
-{
-    if( S % 4 == 0 )
-    {
-#pragma unroll
-        for( int k = 0; k < S; k += 4 ) st_stream_v4( dst + 4 * k, make_uint4( px[ k ], px[ k + 1 ], px[ k + 2 ], px[ k + 3 ] ) );
-    }
-    else if( S % 2 == 0 )
-    {
-#pragma unroll
-        for( int k = 0; k < S; k += 2 ) *reinterpret_cast< uint2* >( dst + 4 * k ) = make_uint2( px[ k ], px[ k + 1 ] );
-    }
-    else
-    {
-#pragma unroll
-        for( int k = 0; k < S; k++ ) *reinterpret_cast< uint32_t* >( dst + 4 * k ) = px[ k ];
-    }
-}
-
-// Anti-aliased output (the reference's GL_MULTISAMPLE toggle, simpleVBO.cpp:238-253, as ordered-grid
-// supersampling): the kernel samples at S = A x the output scale and averages A x A samples per output pixel
-// right in the resolve step — the supersampled image never exists in memory.  RGBA sums on two pairs of 16-bit lanes.
-struct ColourSum
-{
-    uint32_t rb = 0u, ga = 0u;
-    __device__ __forceinline__ void add( uint32_t w )
-    {
-        rb += w & 0x00FF00FFu;
-        ga += ( w >> 8 ) & 0x00FF00FFu;
-    }
-    template< int N > // mean of N = 4 or 16 samples per channel, rounded to nearest (halves up)
-    __device__ __forceinline__ uint32_t mean() const
-    {
-        constexpr int SH = N == 4 ? 2 : 4;
-        constexpr uint32_t BIAS = ( N / 2 ) * 0x00010001u;
-        return ( ( ( rb + BIAS ) >> SH ) & 0x00FF00FFu ) | ( ( ( ( ga + BIAS ) >> SH ) & 0x00FF00FFu ) << 8 );
-    }
-};
-
-// S x S sample colours of one source pixel (row-major) -> its (S/A) x (S/A) output pixels, written as whole row segments
-template< int S, int A >
-__device__ __forceinline__ void store_cell( uint8_t* dst, ptrdiff_t row_step, const uint32_t* px )
-{
-    constexpr int O = S / A;
-    if( A == 1 )
-    {
-#pragma unroll
-        for( int b = 0; b < S; b++ ) store_row< S >( dst + ( ptrdiff_t )b * row_step, px + S * b );
-    }
-    else
-    {
-#pragma unroll
-        for( int oy = 0; oy < O; oy++ )
-        {
-            uint32_t row[ O ];
-#pragma unroll
-            for( int ox = 0; ox < O; ox++ )
-            {
-                ColourSum sum;
-#pragma unroll
-                for( int j = 0; j < A; j++ )
-#pragma unroll
-                    for( int i = 0; i < A; i++ ) sum.add( px[ ( oy * A + j ) * S + ox * A + i ] );
-                row[ ox ] = sum.template mean< A * A >();
-            }
-            store_row< O >( dst + ( ptrdiff_t )oy * row_step, row );
-        }
-    }
-}
-
-template< int S >
-struct TileEnv
-{
-    const uint16_t* keys; // KW x KH, origin (x0-2, y0-2)
-    const uint32_t* cols; // KW x KH RGBA words, same origin; rows at or above the image height hold colour 0
-    int x0, y0;
-    FlatImage img;
-    __device__ __forceinline__ uint32_t key( int i, int j ) const { return keys[ ( j - y0 + 2 ) * Cfg< S >::KW + ( i - x0 + 2 ) ]; }
-    // checkTJunction (subdivision_functions.cu:170-242).  Away from the first/last column the flat byte
-    // offsets the reference uses (idx +- widthstep +- 3) are exactly the 2-D neighbours, which are staged
-    // in shared memory; at i = 0 / W-1 they wrap to the adjacent rows, so those cells take the flat path.
-    __device__ __forceinline__ bool guard( int i, int j ) const { return img.guard( i, j ); }
-    __device__ __forceinline__ bool keep_corner( int i, int j, Q2 p ) const
-    {
-        if( i < 1 || i > img.width - 2 ) return img.keep_corner( i, j, p );
-        const bool px0 = p.x == 0, px1 = p.x == 4, py0 = p.y == 0, py1 = p.y == 4;
-        if( !( ( px0 || px1 ) && ( py0 || py1 ) ) ) return false;
-        const int sx = px1 ? 1 : -1, sy = py1 ? 1 : -1; // the corner's quadrant
-        const uint32_t* c = cols + ( j - y0 + 2 ) * Cfg< S >::KW + ( i - x0 + 2 );
-        const uint32_t side = c[ sx ], diag = c[ sy * Cfg< S >::KW + sx ], vert = c[ sy * Cfg< S >::KW ];
-        return side != diag || diag != vert; // the three other pixels around the corner are not one colour
-    }
-};
-
-// slow path of the resolve step: coverage of the S x S samples of target cell (ti,tj) by the polygon of
-// cell (ci,cj) = (ti+di, tj+dj), recomputed from scratch (exact for any reach < 1 pixel)
-template< int S >
-__device__ __noinline__ void window_coverage( const uint16_t* keys, const uint32_t* cols, int x0, int y0, const uint8_t* frame, int width, int height,
-                                              int widthstep, const CellRecord* rec, int ci, int cj, int di, int dj, bool subdivide, uint32_t* win )
-{
-    typedef Cfg< S > C;
-    // (everything by value: a reference to the caller's TileEnv would force it into local memory on the fast path too)
-    TileEnv< S > env;
-    env.keys = keys;
-    env.cols = cols;
-    env.x0 = x0;
-    env.y0 = y0;
-    env.img.frame = frame;
-    env.img.width = width;
-    env.img.height = height;
-    env.img.widthstep = widthstep;
-    const CellTablePtrs tab{ rec };
-    uint16_t verts[ kMaxVerts ];
-    PackedSlots slots{ verts, 1 };
-    const CellPoly poly = build_cell_polygon( env, tab, ci, cj, env.key( ci, cj ), subdivide, slots );
-    for( int r = 0; r < S; r++ ) win[ r ] = 0u;
-    RowToggle tg{ win, 1 };
-    int lo, hi;
-    cover_polygon< S, S >( verts, 1, poly, C::SSP / 2 - di * C::SQUARE, C::SSP / 2 - dj * C::SQUARE, tg, lo, hi );
-}
-
-// Exact resolve of a whole tile: every candidate's coverage of every pixel recomputed from its polygon.  Only runs
-// for tiles that contain a cell reaching beyond its mask, or under PAR_FLAG_DEBUG_WIDE.
-template< int S, int A >
-__device__ __noinline__ void resolve_tile_exact( const uint16_t* keys, const uint32_t* cols, int x0, int y0, const uint8_t* frame, int width, int height,
-                                                 int widthstep, const CellRecord* rec, bool subdivide, uint8_t* out, bool flip )
-{
-    typedef Cfg< S > C;
-    constexpr int O = S / A;
-    const size_t out_w = ( size_t )width * O, out_h = ( size_t )height * O;
-    for( int idx = threadIdx.x; idx < C::TW * C::TH; idx += kThreads )
-    {
-        const int ly = idx / C::TW, lx = idx - ly * C::TW, gx = x0 + lx, gy = y0 + ly;
-        if( gx >= width || gy >= height ) continue;
-        const uint32_t* col = cols + ( ly + 2 ) * C::KW + ( lx + 2 );
-        uint32_t px[ S * S ], rem[ S ];
-        for( int k = 0; k < S * S; k++ ) px[ k ] = 0xFF000000u; // background (main.cpp:260)
-        for( int b = 0; b < S; b++ ) rem[ b ] = C::FULL;
-        // candidates in DESCENDING node index
-        for( int dj = 1; dj >= -1; dj-- )
-            for( int di = 1; di >= -1; di-- )
-            {
-                const int ci = gx + di, cj = gy + dj;
-                if( ci < 0 || cj < 0 || ci >= width || cj >= height ) continue;
-                uint32_t win[ S ];
-                window_coverage< S >( keys, cols, x0, y0, frame, width, height, widthstep, rec, ci, cj, di, dj, subdivide, win );
-                const uint32_t cw = col[ dj * C::KW + di ];
-                for( int b = 0; b < S; b++ )
-                {
-                    const uint32_t take = win[ b ] & rem[ b ];
-                    rem[ b ] &= ~take;
-                    for( int k = 0; k < S; k++ )
-                        if( ( take >> k ) & 1u ) px[ S * b + k ] = cw;
-                }
-            }
-        const ptrdiff_t row_step = flip ? -( ptrdiff_t )( out_w * 4 ) : ( ptrdiff_t )( out_w * 4 );
-        store_cell< S, A >( out + ( ( flip ? out_h - 1 - ( size_t )gy * O : ( size_t )gy * O ) * out_w + ( size_t )gx * O ) * 4, row_step, px );
-    }
-}
-
-// General path of the mask pass: one thread per queued cell; polygon -> per-thread vertex buffer -> edge loop.  Only runs
-// for the few cells the smoothing tables cannot express (or all smoothed cells under PAR_FLAG_NO_SMOOTH_TABLES).
-template< int S >
-__device__ __noinline__ void geometric_cells( const uint16_t* keys, const uint32_t* cols, uint32_t* s_mask, const uint16_t* s_work, uint16_t* s_vbuf, int* s_nwork,
-                                              int x0, int y0, const uint8_t* frame, int width, int height, int widthstep, const CellRecord* rec,
-                                              uint32_t force_wide )
-{
-    typedef Cfg< S > C;
-    TileEnv< S > env;
-    env.keys = keys;
-    env.cols = cols;
-    env.x0 = x0;
-    env.y0 = y0;
-    env.img.frame = frame;
-    env.img.width = width;
-    env.img.height = height;
-    env.img.widthstep = widthstep;
-    const CellTablePtrs tab{ rec };
-    const int tid = threadIdx.x;
-    const int n_work = *s_nwork;
-    uint16_t* vbuf = s_vbuf + tid;
-    for( int w = tid; w < n_work && tid < kGeoThreads; w += kGeoThreads )
-    {
-        const int idx = s_work[ w ];
-        int cy = idx / C::CW, cx = idx - cy * C::CW;
-        int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
-        PackedSlots slots{ vbuf, kGeoThreads };
-        const CellPoly poly = build_cell_polygon( env, tab, gx, gy, keys[ ( cy + 1 ) * C::KW + cx + 1 ], true, slots );
-        int lo, hi;
-        if constexpr( C::PACK )
-        {
-            PackedToggle< C::R > tg{ 0ull };
-            cover_polygon< S, C::R >( vbuf, kGeoThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
-            // reach check: every sample outside the mask must be strictly outside the polygon's bounding box
-            const uint32_t wide = ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
-            uint2 wm = to_window< S >( tg.m );
-            wm.y |= wide;
-            s_mask[ idx ] = wm.x;
-            s_mask[ C::NC + idx ] = wm.y;
-            if( wide ) s_nwork[ 2 ] = 1;
-        }
-        else
-        {
-#pragma unroll
-            for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] = 0u;
-            RowToggle tg{ s_mask + idx, C::NC };
-            cover_polygon< S, C::R >( vbuf, kGeoThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
-            const uint32_t wide = ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
-            s_mask[ idx ] |= wide;
-            if( wide ) s_nwork[ 2 ] = 1;
-        }
-    }
-}
-
-// mask of a cell whose polygon is its plain hull, for every key: the per-scale table the raster kernel copies from
-struct NoEnv
-{
-    __device__ __forceinline__ uint32_t key( int, int ) const { return 0u; }
-    __device__ __forceinline__ bool guard( int, int ) const { return true; }
-    __device__ __forceinline__ bool keep_corner( int, int, Q2 ) const { return true; }
-};
-
-template< int S >
-__global__ void build_mask_lut_kernel( CellTablePtrs tab, uint32_t* lut )
-{
-    typedef Cfg< S > C;
-    const int key = blockIdx.x * blockDim.x + threadIdx.x;
-    if( key >= kCellKeys ) return;
-    uint16_t verts[ kMaxVerts ];
-    PackedSlots slots{ verts, 1 };
-    NoEnv env;
-    const CellPoly poly = build_cell_polygon( env, tab, 0, 0, ( uint32_t )key, false, slots );
-    int lo, hi;
-    if constexpr( C::PACK )
-    {
-        PackedToggle< C::R > tg{ 0ull };
-        cover_polygon< S, C::R >( verts, 1, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
-        const uint2 w = to_window< S >( tg.m );
-        lut[ 2 * key ] = w.x;
-        lut[ 2 * key + 1 ] = w.y;
-    }
-    else
-    {
-        uint32_t rows[ C::R ];
-        for( int r = 0; r < C::R; r++ ) rows[ r ] = 0u;
-        RowToggle tg{ rows, 1 };
-        cover_polygon< S, C::R >( verts, 1, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
-        for( int r = 0; r < C::R; r++ ) lut[ C::R * key + r ] = rows[ r ];
-    }
-}
-
-// ---- smoothing tables (smooth_table.h) -------------------------------------------------------------
-// Table entry = the coverage mask as 64-bit words: PACK -> one word in window form (wide flag = Cfg::WIDE of the
-// high half); rows -> R 16-bit rows, four per word, wide flag in bit 15 of row 0.
-template< int S >
-struct Entry
-{
-    static constexpr int EW = Cfg< S >::PACK ? 1 : ( Cfg< S >::R * 2 + 7 ) / 8;
-    static constexpr uint64_t FLAG = Cfg< S >::PACK ? ( ( uint64_t )Cfg< S >::WIDE << 32 ) : ( 1ull << 15 );
-};
-
-// coverage of the closed polygon (xs[k], ys[k]), k < m (1/64 px, cell-local), as a table entry
-template< int S >
-__device__ void cover_to_entry( const int* xs, const int* ys, int m, uint64_t* out )
-{
-    typedef Cfg< S > C;
-    int lo = 1 << 30, hi = -( 1 << 30 );
-    for( int k = 0; k < m; k++ )
-    {
-        lo = min( lo, min( xs[ k ], ys[ k ] ) * C::VM );
-        hi = max( hi, max( xs[ k ], ys[ k ] ) * C::VM );
-    }
-    const bool wide = lo <= -C::REACH || hi >= C::SQUARE + C::REACH;
-    if constexpr( C::PACK )
-    {
-        PackedToggle< C::R > tg{ 0ull };
-        for( int k = 0; k < m; k++ )
-        {
-            const int k1 = k + 1 == m ? 0 : k + 1;
-            cover_edge< S, C::R >( C::S_FIRST, C::S_FIRST, xs[ k ] * C::VM, ys[ k ] * C::VM, xs[ k1 ] * C::VM, ys[ k1 ] * C::VM, tg );
-        }
-        const uint2 w = to_window< S >( tg.m );
-        out[ 0 ] = ( ( uint64_t )w.y << 32 | w.x ) | ( wide ? Entry< S >::FLAG : 0ull );
-    }
-    else
-    {
-        uint32_t rows[ C::R ];
-        for( int r = 0; r < C::R; r++ ) rows[ r ] = 0u;
-        RowToggle tg{ rows, 1 };
-        for( int k = 0; k < m; k++ )
-        {
-            const int k1 = k + 1 == m ? 0 : k + 1;
-            cover_edge< S, C::R >( C::S_FIRST, C::S_FIRST, xs[ k ] * C::VM, ys[ k ] * C::VM, xs[ k1 ] * C::VM, ys[ k1 ] * C::VM, tg );
-        }
-        for( int w = 0; w < Entry< S >::EW; w++ ) out[ w ] = 0ull;
-        for( int r = 0; r < C::R; r++ ) out[ r >> 2 ] |= ( uint64_t )( rows[ r ] & 0x7FFFu ) << ( 16 * ( r & 3 ) );
-        if( wide ) out[ 0 ] |= Entry< S >::FLAG;
-    }
-}
-
-// CUT[key][kept]: the hull with its cut vertices replaced by R(prev), Q(cur) (subdivision_functions.cu:583-598),
-// except the square corners (0,0) (1,0) (1,1) (0,1) whose bit in `kept` is set
-template< int S >
-__global__ void build_cut_table_kernel( CellTablePtrs tab, uint64_t* cut )
-{
-    const int id = blockIdx.x * blockDim.x + threadIdx.x;
-    if( id >= kCellKeys * 16 ) return;
-    const uint32_t key = ( uint32_t )id >> 4, kept = ( uint32_t )id & 15u;
-    uint64_t h, info;
-    load_hull( tab, key, h, info );
-    const int n = hull_count( info );
-    const VertexClasses cls = classify_vertices( info );
-    const uint32_t cv = hull_corner_vertices( info );
-    uint32_t keptv = 0u;
-    for( int c = 0; c < 4; c++ )
-    {
-        const uint32_t v = ( cv >> ( 4 * c ) ) & 15u;
-        if( ( ( kept >> c ) & 1u ) && v != 15u ) keptv |= 1u << v;
-    }
-    int xs[ kMaxVerts ], ys[ kMaxVerts ], m = 0;
-    for( int t = 0; t < n; t++ )
-    {
-        const Q2 p = hull_vertex( h, t );
-        if( ( ( cls.cut >> t ) & 1u ) && !( ( keptv >> t ) & 1u ) )
-        {
-            cut_toward( p, hull_vertex( h, t == 0 ? n - 1 : t - 1 ), xs[ m ], ys[ m ] );
-            m++;
-            cut_toward( p, hull_vertex( h, t + 1 == n ? 0 : t + 1 ), xs[ m ], ys[ m ] );
-            m++;
-        }
-        else
-        {
-            xs[ m ] = 16 * p.x;
-            ys[ m ] = 16 * p.y;
-            m++;
-        }
-    }
-    cover_to_entry< S >( xs, ys, m, cut + ( size_t )id * Entry< S >::EW );
-}
-
-// the point with a given code (inverse of point_code, cell_table.h), quarter pixels
-__device__ __forceinline__ Q2 point_of_code( int code )
-{
-    Q2 q{ 0, 0 };
-    int seen = 0;
-    for( int pos = 0; pos < 49; pos++ )
-        if( ( kValidPoints >> pos ) & 1ull )
-        {
-            if( seen == code )
-            {
-                q.x = pos % 7 - 1;
-                q.y = pos / 7 - 1;
-            }
-            seen++;
-        }
-    return q;
-}
-
-// LINK[class][a][b]: the loop between the hull path and the smoothed path around one shared edge
-// (subdivision_functions.cu:603-647 for the two blended vertices, see smooth_table.h)
-template< int S >
-__global__ void build_link_table_kernel( const LinkClass* classes, uint64_t* link )
-{
-    const LinkClass c = classes[ blockIdx.x ];
-    const int sub = threadIdx.x;                 // = rank a | rank b << 2 (a class with one blended end ignores the other rank)
-    uint64_t* entry = link + ( size_t )( c.block * 16u + sub ) * Entry< S >::EW;
-    const int a = c.after[ sub & 3 ], b = c.before[ sub >> 2 ];
-    const int di = edge_di( c.e ), dj = edge_dj( c.e );
-    const Q2 P0{ c.px[ 0 ], c.py[ 0 ] }, P1{ c.px[ 1 ], c.py[ 1 ] }, P2{ c.px[ 2 ], c.py[ 2 ] }, P3{ c.px[ 3 ], c.py[ 3 ] };
-    int xs[ 6 ], ys[ 6 ], m = 0;
-    if( c.hasA )
-    {
-        int rx, ry, qx, qy;
-        cut_toward( P1, P0, rx, ry );                                                   // own R on the border edge arriving at P1
-        cut_toward( Q2{ P1.x - 4 * di, P1.y - 4 * dj }, point_of_code( a ), qx, qy );  // neighbour's Q on the edge leaving P1
-        xs[ m ] = rx;
-        ys[ m ] = ry;
-        m++;
-        xs[ m ] = ( rx + qx + 64 * di ) >> 1;
-        ys[ m ] = ( ry + qy + 64 * dj ) >> 1;
-        m++;
-    }
-    else
-    {
-        xs[ m ] = 16 * P1.x;
-        ys[ m ] = 16 * P1.y;
-        m++;
-    }
-    if( c.hasB )
-    {
-        int qx, qy, rx, ry;
-        cut_toward( P2, P3, qx, qy );                                                   // own Q on the border edge leaving P2
-        cut_toward( Q2{ P2.x - 4 * di, P2.y - 4 * dj }, point_of_code( b ), rx, ry );  // neighbour's R on the edge arriving at P2
-        xs[ m ] = ( qx + rx + 64 * di ) >> 1;
-        ys[ m ] = ( qy + ry + 64 * dj ) >> 1;
-        m++;
-        xs[ m ] = qx;
-        ys[ m ] = qy;
-        m++;
-    }
-    xs[ m ] = 16 * P2.x;
-    ys[ m ] = 16 * P2.y;
-    m++;
-    if( c.hasA )
-    {
-        xs[ m ] = 16 * P1.x;
-        ys[ m ] = 16 * P1.y;
-        m++;
-    }
-    cover_to_entry< S >( xs, ys, m, entry );
-}
-
-// NS link descriptors of a smoothed cell, without branches (the loads of the slots overlap; an unused slot (0)
-// compares nothing and loads nothing): XORs their LINK entries into m, ORs word 0 of the entries into `flags`, returns
-// the mismatch bits (non-zero: a blended vertex is not the end / start of the neighbour's edge).
-template< int S, int NS >
-__device__ __forceinline__ uint32_t link_slots( const SmoothTablePtrs& st, const uint16_t* keys_at_cell, const uint32_t* links, uint64_t* m, uint64_t& flags )
-{
-    typedef Cfg< S > C;
-    typedef Entry< S > E;
-    uint32_t nb[ NS ];
-#pragma unroll
-    for( int k = 0; k < NS; k++ )
-    {
-        const uint32_t d = links[ k ];
-        const uint32_t e = d & 7u;
-        // neighbour across graph edge e: offset in the key tile, one signed byte per edge
-        constexpr int KW = C::KW;
-        constexpr uint32_t off_lo = ( uint32_t )( uint8_t )( KW - 1 ) | ( uint32_t )( uint8_t )( KW ) << 8 | ( uint32_t )( uint8_t )( KW + 1 ) << 16 |
-                                    ( uint32_t )( uint8_t )( -1 ) << 24;
-        constexpr uint32_t off_hi = ( uint32_t )( uint8_t )( 1 ) | ( uint32_t )( uint8_t )( -KW - 1 ) << 8 | ( uint32_t )( uint8_t )( -KW ) << 16 |
-                                    ( uint32_t )( uint8_t )( -KW + 1 ) << 24;
-        const int koff = ( int )( int8_t )__byte_perm( off_lo, off_hi, e );
-        const uint32_t nkey = keys_at_cell[ koff ];
-        nb[ k ] = ( d >> 16 ) ? ( uint32_t )__ldg( &st.rec[ nkey ].nbr[ e ^ 7u ] ) : 0u; // (an unused slot loads nothing)
-    }
-    uint32_t mismatch = 0u;
-#pragma unroll
-    for( int k = 0; k < NS; k++ )
-    {
-        const uint32_t d = links[ k ], r = nb[ k ];
-        const uint32_t ends = ( d >> 16 ) & 255u;
-        mismatch |= ( ( r ^ d ) >> 8 ) & ends; // the blended vertices must be the end (A) / start (B) of the neighbour's edge
-        const uint32_t sub = r & ends; // rank a | rank b << 4 -> the class's 4 x 4 block (one 128-byte line at s <= 4)
-        const uint64_t* le = st.link + ( size_t )( ( d >> 24 ) * 16u + ( ( sub & 3u ) | ( ( sub >> 2 ) & 12u ) ) ) * E::EW;
-#pragma unroll
-        for( int w = 0; w < E::EW; w++ )
-        {
-            const uint64_t v = ( d >> 16 ) ? __ldg( le + w ) : 0ull;
-            if( w == 0 ) flags |= v;
-            m[ w ] ^= v;
-        }
-    }
-    return mismatch;
-}
-
-// Mask of a smoothed cell from the tables, FIRST pass: the CUT entry and the first two link descriptors (nine cells in
-// ten have no more).  `more` is set when the key has a third descriptor: the caller marks the cell for
-// smooth_lookup_more.  Returns false when a blended vertex is not a vertex of the neighbour's hull (the reference's
-// getPointIndex fallback) — the caller then takes the geometric path.
-template< int S >
-__device__ __forceinline__ bool smooth_lookup( const SmoothTablePtrs& st, const uint32_t* mask_lut, const uint16_t* keys_at_cell, uint32_t key, uint32_t cflags,
-                                               uint64_t* m, bool& wide, bool& more )
-{
-    typedef Cfg< S > C;
-    typedef Entry< S > E;
-    const uint4 rec = __ldg( reinterpret_cast< const uint4* >( st.rec + key ) ); // the four link descriptors
-    uint64_t flags = 0ull;
-    if( cflags & 16u ) // checkTJunction's early exit keeps every cut vertex: the plain hull
-    {
-        if( C::PACK )
-        {
-            const uint2 v = __ldg( reinterpret_cast< const uint2* >( mask_lut ) + key );
-            m[ 0 ] = ( uint64_t )v.y << 32 | v.x;
-        }
-        else
-        {
-#pragma unroll
-            for( int w = 0; w < E::EW; w++ ) m[ w ] = 0ull;
-#pragma unroll
-            for( int r = 0; r < C::R; r++ ) m[ r >> 2 ] |= ( uint64_t )__ldg( mask_lut + key * C::R + r ) << ( 16 * ( r & 3 ) );
-        }
-    }
-    else
-    {
-        const uint64_t* e = st.cut + ( size_t )( key * 16u + ( cflags & ( rec.x >> 4 ) & 15u ) ) * E::EW; // (only corners with a cut vertex matter)
-#pragma unroll
-        for( int w = 0; w < E::EW; w++ ) m[ w ] = __ldg( e + w );
-    }
-    bool ok = rec.x != kSmoothSlow;
-    const uint32_t links[ 2 ] = { ok ? rec.x : 0u, rec.y };
-    more = ( rec.z >> 16 ) != 0u; // (descriptors fill the slots from 0)
-    ok = ok && link_slots< S, 2 >( st, keys_at_cell, links, m, flags ) == 0u;
-    // the flag bit of word 0 was XORed along with the masks: restore it from the CUT entry (never wide) and the OR
-    wide = ( flags & E::FLAG ) != 0ull;
-    m[ 0 ] &= ~E::FLAG;
-    return ok;
-}
-
-// SECOND pass, for the cells whose key has three or four link descriptors: the XOR of the remaining LINK entries (flag
-// bit cleared), `wide` from their flags; false on a mismatch as above.
-template< int S >
-__device__ __forceinline__ bool smooth_lookup_more( const SmoothTablePtrs& st, const uint16_t* keys_at_cell, uint32_t key, uint64_t* m, bool& wide )
-{
-    typedef Entry< S > E;
-    const uint2 rec = __ldg( reinterpret_cast< const uint2* >( &st.rec[ key ].link[ 2 ] ) );
-    const uint32_t links[ 2 ] = { rec.x, rec.y };
-    uint64_t flags = 0ull;
-#pragma unroll
-    for( int w = 0; w < E::EW; w++ ) m[ w ] = 0ull;
-    const bool ok = link_slots< S, 2 >( st, keys_at_cell, links, m, flags ) == 0u;
-    wide = ( flags & E::FLAG ) != 0ull;
-    m[ 0 ] &= ~E::FLAG;
-    return ok;
-}
-
-template< int S, int A, bool kUseTma >
-__global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( const __grid_constant__ CUtensorMap graph_map, const __grid_constant__ CUtensorMap img_map,
-                                                           RasterArgs a )
-{
-    typedef Cfg< S > C;
-    extern __shared__ __align__( 128 ) uint8_t smem[];
-    uint8_t* s_graph = smem + C::off_graph;
-    uint16_t* s_keys = reinterpret_cast< uint16_t* >( smem + C::off_keys );
-    uint32_t* s_col = reinterpret_cast< uint32_t* >( smem + C::off_col );
-    uint32_t* s_mask = reinterpret_cast< uint32_t* >( smem + C::off_mask );   // PACK: [2][NC]; rows: [R][NC]
-    uint16_t* s_vbuf = reinterpret_cast< uint16_t* >( smem + C::off_vbuf );   // [kMaxVerts][kGeoThreads]
-    uint16_t* s_work = reinterpret_cast< uint16_t* >( smem + C::off_work );   // cells that need the general path
-    int* s_nwork = reinterpret_cast< int* >( smem + C::off_nwork );
-    uint64_t* s_bar = reinterpret_cast< uint64_t* >( smem + C::off_bar );
-
-    const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * C::TW, y0 = blockIdx.y * C::TH, f = blockIdx.z;
-    const size_t frame_px = ( size_t )a.width * a.height;
-    const uint8_t* frame = a.bgr + ( size_t )f * a.frame_stride;
-    const uint8_t* graph = a.graph + ( size_t )f * frame_px;
-
-    // (1) stage graph bytes: rows y0-2 .. y0+TH+1, columns x0-16 .. x0-16+GP-1; zero outside the image
-    if( tid < 3 ) s_nwork[ tid ] = 0; // [0] geometric work items, [1] smoothed cells (statistics), [2] some cell of the tile is wide
-    if( kUseTma )
-    {
-        if( tid == 0 )
-        {
-            mbar_init( s_bar, 1 );
-            fence_barrier_init();
-        }
-        __syncthreads();
-        if( tid == 0 )
-        {
-            mbar_expect_tx( s_bar, C::KH * C::GP + C::KH * C::RAWP );
-            tma_load_3d( s_graph, &graph_map, s_bar, x0 - C::GOFF, y0 - 2, f );
-            tma_load_3d( smem + C::off_raw, &img_map, s_bar, 3 * x0 - 16, y0 - 2, f ); // BGR bytes of tile + halo 2
-        }
-    }
-    else
-    {
-        for( int idx = tid; idx < C::KH * C::GP; idx += kThreads )
-        {
-            int r = idx / C::GP, c = idx - r * C::GP;
-            int gx = x0 - C::GOFF + c, gy = y0 - 2 + r;
-            uint8_t v = 0;
-            if( gx >= 0 && gy >= 0 && gx < a.width && gy < a.height ) v = graph[ ( size_t )gy * a.width + gx ];
-            s_graph[ idx ] = v;
-        }
-    }
-    // colours of the tile + halo 2 as RGBA words (kernel.cu:98-101: R = byte 2, G = byte 1, B = byte 0);
-    // pixels outside the image hold colour 0 (the reference's reads beyond the last row see zeros), except the two
-    // virtual columns x = -1 and x = width: checkTJunction addresses the pixels around a corner as FLAT byte
-    // offsets idx +- widthstep +- 3 (subdivision_functions.cu:195-202), so for the first / last pixel of a row "the
-    // pixel to the left / right" is the three bytes just before / after the row (the end of the previous row, the
-    // start of the next one, or row padding; zero beyond the end of the image, SURVEY App. B-3 contract).
-    auto virtual_colour = [ & ]( int gx, int gy ) -> uint32_t {
-        const long end = ( long )a.height * a.widthstep;
-        const long at = ( long )gy * a.widthstep + 3L * gx;
-        uint32_t b[ 3 ];
-#pragma unroll
-        for( int k = 0; k < 3; k++ ) b[ k ] = ( at + k >= 0 && at + k < end ) ? ( uint32_t )__ldg( frame + at + k ) : 0u;
-        return b[ 2 ] | b[ 1 ] << 8 | b[ 0 ] << 16 | 0xFF000000u;
-    };
-    if( kUseTma )
-    {
-        // Four pixels per thread from aligned 32-bit words of the staged rows: byte permutes build the RGBA words
-        // and the cell keys (left/right neighbour bits, kernel.cu:204-207), 128- / 64-bit stores.  TMA zero-filled
-        // everything outside the image (row padding included), which is exactly "colour 0" / "no links".
-        mbar_wait( s_bar, 0 );
-        static_assert( C::KW % 4 == 0 && C::RAWOFF == 10 && C::GOFF == 16, "group layout of the vectorised staging pass" );
-        constexpr int QW = C::KW / 4;
-        const int vl = x0 == 0 ? 1 : -1, vr = a.width - x0 + 2; // tile columns of the virtual colour columns x = -1, x = width
-        for( int idx = tid; idx < QW * C::KH; idx += kThreads )
-        {
-            const int cy = idx / QW, q = idx - cy * QW;
-            const uint32_t* rw = reinterpret_cast< const uint32_t* >( smem + C::off_raw + cy * C::RAWP + 8 + 12 * q ); // pixel 4q starts at byte 10 + 12 q
-            const uint32_t w0 = rw[ 0 ], w1 = rw[ 1 ], w2 = rw[ 2 ], w3 = rw[ 3 ];
-            uint32_t c[ 4 ] = { __byte_perm( w0, w1, 0x2234 ) | 0xFF000000u, __byte_perm( w1, w1, 0x1123 ) | 0xFF000000u,
-                                __byte_perm( w2, w2, 0x0012 ) | 0xFF000000u, __byte_perm( w2, w3, 0x3345 ) | 0xFF000000u };
-            if( ( vl >> 2 ) == q || ( vr >> 2 ) == q )
-            {
-#pragma unroll
-                for( int k = 0; k < 4; k++ )
-                    if( 4 * q + k == vl || 4 * q + k == vr ) c[ k ] = virtual_colour( x0 - 2 + 4 * q + k, y0 - 2 + cy );
-            }
-            *reinterpret_cast< uint4* >( s_col + cy * C::KW + 4 * q ) = make_uint4( c[ 0 ], c[ 1 ], c[ 2 ], c[ 3 ] );
-            const uint32_t* gw = reinterpret_cast< const uint32_t* >( s_graph + cy * C::GP + C::GOFF - 4 + 4 * q ); // cell 4q sits at staged column 14 + 4 q
-            const uint32_t g0 = gw[ 0 ], g1 = gw[ 1 ];
-            const uint32_t node = __byte_perm( g0, g1, 0x5432 ), left = __byte_perm( g0, g1, 0x4321 ), right = __byte_perm( g0, g1, 0x6543 );
-            const uint32_t high = ( ( left >> 2 ) & 0x01010101u ) | ( ( left >> 6 ) & 0x02020202u ) | ( ( right << 2 ) & 0x04040404u ) |
-                                  ( ( right >> 2 ) & 0x08080808u ); // cell_key's bits 8..11, one byte per cell
-            *reinterpret_cast< uint2* >( s_keys + cy * C::KW + 4 * q ) = make_uint2( __byte_perm( node, high, 0x5140 ), __byte_perm( node, high, 0x7362 ) );
-        }
-    }
-    else
-    {
-        for( int idx = tid; idx < C::KW * C::KH; idx += kThreads )
-        {
-            int cy = idx / C::KW, cx = idx - cy * C::KW;
-            int gx = x0 - 2 + cx, gy = y0 - 2 + cy;
-            uint32_t w = 0xFF000000u;
-            if( gx >= 0 && gy >= 0 && gx < a.width && gy < a.height )
-            {
-                const uint8_t* p = frame + ( size_t )gy * a.widthstep + 3 * gx;
-                w = ( uint32_t )__ldg( p + 2 ) | ( uint32_t )__ldg( p + 1 ) << 8 | ( uint32_t )__ldg( p ) << 16 | 0xFF000000u;
-            }
-            else if( gx == -1 || gx == a.width )
-                w = virtual_colour( gx, gy );
-            s_col[ idx ] = w;
-        }
-        __syncthreads();
-        // cell keys for tile + halo 2 (left/right neighbour bits, kernel.cu:204-207; zero outside the row)
-        for( int idx = tid; idx < C::KW * C::KH; idx += kThreads )
-        {
-            int ky = idx / C::KW, kx = idx - ky * C::KW;
-            const uint8_t* g = s_graph + ky * C::GP + kx + C::GOFF - 2; // column x0-2+kx sits at staged column kx+GOFF-2
-            s_keys[ idx ] = ( uint16_t )cell_key( g[ 0 ], g[ -1 ], g[ 1 ] );
-        }
-    }
-    __syncthreads();
-
-    TileEnv< S > env;
-    env.keys = s_keys;
-    env.cols = s_col;
-    env.x0 = x0;
-    env.y0 = y0;
-    env.img.frame = frame;
-    env.img.width = a.width;
-    env.img.height = a.height;
-    env.img.widthstep = a.widthstep;
-    const bool subdivide = a.subdivide != 0;
-    const CellTablePtrs tab = a.tables;
-    const uint32_t force_wide = a.debug_force_wide ? C::WIDE : 0u;
-    const bool use_tables = a.smooth.cut != nullptr && !a.debug_force_wide;
-
-    // (2a) Every cell of tile + halo 1 gets its mask, in tile order: a warp's cells are neighbours, so the key, colour
-    // and mask accesses are conflict-free and nothing is queued.  Cells whose polygon is their plain hull copy the mask
-    // from the per-scale table; smoothed cells assemble it from the smoothing tables (one CUT entry + one LINK entry per
-    // shared edge with a blended end); the rare cell the tables cannot express is queued for the geometric path.
-    // (Compacting the smoothed cells into a list first, so that the lookups run with full warps, was 3 % slower on the
-    // busy frames of the bench — 83 % of the cells are smoothed — and 9 % faster on frames of flat 4 x 4 blocks.)
-    int n_smoothed = 0;
-    constexpr int kRounds = ( C::NC + kThreads - 1 ) / kThreads;
-    uint32_t* s_more = reinterpret_cast< uint32_t* >( s_nwork + 4 ); // [kRounds][8 warps]: the cells of a round with a third link, as ballots
-    const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll 1
-    for( int round = 0; round < kRounds; round++ ) // (whole warps: the vote at the end needs every lane)
-    {
-        const int idx = round * kThreads + tid;
-        bool third_link = false;
-        int cy = idx / C::CW, cx = idx - cy * C::CW;
-        int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
-        const bool inside = gx >= 0 && gy >= 0 && gx < a.width && gy < a.height;
-        const uint16_t* kc = s_keys + ( cy + 1 ) * C::KW + cx + 1;
-        const uint32_t key = idx < C::NC ? *kc : 90u;
-        const bool plain = !subdivide || ( key & 0xFFu ) == 90u;
-        if( idx >= C::NC )
-            ;
-        else if( inside && !plain )
-        {
-            n_smoothed++;
-            // checkTJunction for the four corners of the pixel square (bit c: corner c stays), 16 = its early exit
-            uint32_t cf = 16u;
-            if( !env.guard( gx, gy ) )
-            {
-                const uint32_t* c = s_col + ( cy + 1 ) * C::KW + ( cx + 1 );
-                const uint32_t l = c[ -1 ], r = c[ 1 ], d = c[ -C::KW ], u = c[ C::KW ];
-                const uint32_t dl = c[ -C::KW - 1 ], dr = c[ -C::KW + 1 ], ul = c[ C::KW - 1 ], ur = c[ C::KW + 1 ];
-                cf = ( ( l != dl || dl != d ) ? 1u : 0u ) | ( ( r != dr || dr != d ) ? 2u : 0u ) | ( ( r != ur || ur != u ) ? 4u : 0u ) |
-                     ( ( l != ul || ul != u ) ? 8u : 0u );
-            }
-            uint64_t mw[ Entry< S >::EW ];
-            bool wide = false, more = false;
-            if( use_tables && smooth_lookup< S >( a.smooth, a.mask_lut, kc, key, cf, mw, wide, more ) )
-            {
-                third_link = more;
-                if( C::PACK )
-                {
-                    s_mask[ idx ] = ( uint32_t )mw[ 0 ];
-                    s_mask[ C::NC + idx ] = ( uint32_t )( mw[ 0 ] >> 32 ) | ( wide ? C::WIDE : 0u );
-                    if( wide ) s_nwork[ 2 ] = 1;
-                }
-                else
-                {
-#pragma unroll
-                    for( int r = 0; r < C::R; r++ )
-                    {
-                        const uint32_t row = ( uint32_t )( mw[ r >> 2 ] >> ( 16 * ( r & 3 ) ) ) & 0x7FFFu;
-                        s_mask[ r * C::NC + idx ] = row | ( ( r == 0 && wide ) ? C::WIDE : 0u );
-                    }
-                    if( wide ) s_nwork[ 2 ] = 1;
-                }
-            }
-            else
-                s_work[ warp_slot( s_nwork ) ] = ( uint16_t )idx;
-        }
-        else if( C::PACK )
-        {
-            uint2 m = make_uint2( 0u, 0u );
-            if( inside )
-            {
-                m = __ldg( reinterpret_cast< const uint2* >( a.mask_lut ) + key );
-                m.y |= force_wide;
-            }
-            s_mask[ idx ] = m.x; // (PACK: the two halves live in separate arrays, conflict-free 32-bit accesses)
-            s_mask[ C::NC + idx ] = m.y;
-        }
-        else
-        {
-#pragma unroll
-            for( int r = 0; r < C::R; r++ )
-                s_mask[ r * C::NC + idx ] = inside ? ( __ldg( a.mask_lut + key * C::R + r ) | ( r == 0 ? force_wide : 0u ) ) : 0u;
-        }
-        const uint32_t vote = __ballot_sync( 0xFFFFFFFFu, third_link );
-        if( lane == 0 ) s_more[ round * ( kThreads / 32 ) + warp ] = vote;
-    }
-    // (2a') cells with three or four link descriptors (one in ten): the remaining LINK entries are XORed in.  (All four
-    // slots in the first pass would cost every warp of it the instructions of the two slots that nine cells in ten do
-    // not use.)  Each warp takes the cells of its own rounds, found in the ballots it left above: no list, no atomics and
-    // no barrier — the dependent gathers of these few cells run under the other warps' first pass.
-    __syncwarp();
-    {
-        uint32_t votes[ kRounds ];
-        int total = 0;
-#pragma unroll
-        for( int r = 0; r < kRounds; r++ )
-        {
-            votes[ r ] = s_more[ r * ( kThreads / 32 ) + warp ];
-            total += __popc( votes[ r ] );
-        }
-        for( int j = lane; j < total; j += 32 ) // lane j takes the j-th marked cell
-        {
-            int skip = j, round = 0;
-            uint32_t word = votes[ 0 ];
-#pragma unroll
-            for( int r = 0; r + 1 < kRounds; r++ )
-            {
-                const int c = __popc( votes[ r ] );
-                if( round == r && skip >= c )
-                {
-                    skip -= c;
-                    round = r + 1;
-                    word = votes[ r + 1 ];
-                }
-            }
-            for( ; skip > 0; skip-- ) word &= word - 1u;
-            const int idx = round * kThreads + warp * 32 + ( __ffs( ( int )word ) - 1 );
-            const int cy = idx / C::CW, cx = idx - cy * C::CW;
-            const uint16_t* kc = s_keys + ( cy + 1 ) * C::KW + cx + 1;
-            uint64_t mw[ Entry< S >::EW ];
-            bool wide = false;
-            const bool ok = smooth_lookup_more< S >( a.smooth, kc, *kc, mw, wide );
-            if( C::PACK )
-            {
-                s_mask[ idx ] ^= ( uint32_t )mw[ 0 ];
-                s_mask[ C::NC + idx ] ^= ( uint32_t )( mw[ 0 ] >> 32 );
-                if( wide ) s_mask[ C::NC + idx ] |= C::WIDE;
-            }
-            else
-            {
-#pragma unroll
-                for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] ^= ( uint32_t )( mw[ r >> 2 ] >> ( 16 * ( r & 3 ) ) ) & 0x7FFFu;
-                if( wide ) s_mask[ idx ] |= C::WIDE;
-            }
-            if( wide ) s_nwork[ 2 ] = 1;
-            if( !ok ) s_work[ warp_slot( s_nwork ) ] = ( uint16_t )idx; // the geometric path rebuilds the whole mask
-        }
-    }
-    if( a.smooth_stats ) // (statistics for the bench line)
-    {
-        n_smoothed = __reduce_add_sync( 0xFFFFFFFFu, n_smoothed );
-        if( lane == 0 ) atomicAdd( s_nwork + 1, n_smoothed );
-    }
-    __syncthreads();
-
-    // (2b) general path, out of line (rarely runs: it costs the common path neither registers nor code)
-    if( *s_nwork != 0 )
-    {
-        geometric_cells< S >( s_keys, s_col, s_mask, s_work, s_vbuf, s_nwork, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, force_wide );
-        __syncthreads(); // (uniform: the counter is final since the barrier before this pass)
-    }
-    if( a.smooth_stats && tid == 0 )
-    {
-        atomicAdd( a.smooth_stats, ( unsigned long long )s_nwork[ 1 ] );     // smoothed cells
-        atomicAdd( a.smooth_stats + 1, ( unsigned long long )s_nwork[ 0 ] ); // ... of which took the geometric path
-    }
-
-    // (3) resolve and write: one thread per source pixel, S output rows of S pixels each
-    constexpr int O = S / A; // output pixels per source pixel and axis (A > 1: A x A samples are averaged per output pixel)
-    const size_t out_w = ( size_t )a.width * O, out_h = ( size_t )a.height * O;
-    uint8_t* out = a.rgba + ( size_t )f * out_w * out_h * 4;
-    const ptrdiff_t row_step = a.flip_output ? -( ptrdiff_t )( out_w * 4 ) : ( ptrdiff_t )( out_w * 4 ); // bytes from one output row to the next
-    if( s_nwork[ 2 ] != 0 || a.debug_force_wide )
-    {
-        // some cell of this tile reaches beyond its mask (never seen on real frames): the whole tile is resolved by
-        // the exact path, kept out of line so that it costs the common path neither registers nor code
-        resolve_tile_exact< S, A >( s_keys, s_col, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, subdivide, out, a.flip_output != 0 );
-        return;
-    }
-    if constexpr( C::PACK )
-    {
-        // Window form: every candidate's coverage of my S x S output pixels is one masked 16-bit field of its
-        // mask, so the priority resolve runs once on whole-cell bit sets instead of once per output row.
-        for( int idx = tid; idx < C::TW * C::TH; idx += kThreads )
-        {
-            int ly = idx / C::TW, lx = idx - ly * C::TW;
-            int gx = x0 + lx, gy = y0 + ly;
-            if( gx >= a.width || gy >= a.height ) continue;
-            const uint32_t* mlo = s_mask + ( ly + 1 ) * C::CW + ( lx + 1 ); // F0 | F1 << 16
-            const uint32_t* mhi = mlo + C::NC;                             // F2 | F3 << 16
-            const uint32_t* col = s_col + ( ly + 2 ) * C::KW + ( lx + 2 );
-            uint32_t px[ S * S ];
-            const uint32_t own = col[ 0 ];
-#pragma unroll
-            for( int k = 0; k < S * S; k++ ) px[ k ] = own;
-            // candidates in DESCENDING node index: (dj,di) = (+1,+1) (+1,0) (+1,-1) (0,+1) (0,0) (0,-1) (-1,+1) (-1,0) (-1,-1);
-            // the four drawn after this cell, then the cell itself: most pixels are settled by those
-            uint32_t cov[ 9 ];
-            cov[ 0 ] = ( mhi[ C::CW + 1 ] >> 16 ) & ( 1u << ( S * S - 1 ) );
-            cov[ 1 ] = mhi[ C::CW ] & C::M_TOPROW;
-            cov[ 2 ] = ( mhi[ C::CW - 1 ] >> 16 ) & ( 1u << ( S * ( S - 1 ) ) );
-            cov[ 3 ] = ( mlo[ 1 ] >> 16 ) & C::M_RIGHTCOL;
-            cov[ 4 ] = mlo[ 0 ] & C::ALL;
-            if( C::H == 0 ) cov[ 0 ] = cov[ 1 ] = cov[ 2 ] = cov[ 3 ] = 0u; // no halo samples at this scale
-            if( ( cov[ 4 ] & ~( cov[ 0 ] | cov[ 1 ] | cov[ 2 ] | cov[ 3 ] ) ) != C::ALL )
-            {
-                cov[ 5 ] = ( mlo[ -1 ] >> 16 ) & C::M_LEFTCOL;
-                cov[ 6 ] = ( mhi[ -C::CW + 1 ] >> 16 ) & ( 1u << ( S - 1 ) );
-                cov[ 7 ] = mhi[ -C::CW ] & C::M_BOTROW;
-                cov[ 8 ] = ( mhi[ -C::CW - 1 ] >> 16 ) & 1u;
-                if( C::H == 0 ) cov[ 5 ] = cov[ 6 ] = cov[ 7 ] = cov[ 8 ] = 0u;
-                uint32_t rem = C::ALL;
-#pragma unroll
-                for( int k = 0; k < 9; k++ )
-                {
-                    const uint32_t take = cov[ k ] & rem;
-                    rem &= ~cov[ k ];
-                    if( k == 4 ) continue;
-                    const int dj = 1 - k / 3, di = 1 - k % 3;
-                    const uint32_t cw = take ? col[ dj * C::KW + di ] : 0u; // (predicated load: no branch per candidate)
-                    // a candidate can only hold pixels of its own window
-#pragma unroll
-                    for( int bit = 0; bit < S * S; bit++ )
-                    {
-                        const int bx = bit % S, by = bit / S;
-                        const bool in_window = ( di == 0 || bx == ( di > 0 ? S - 1 : 0 ) ) && ( dj == 0 || by == ( dj > 0 ? S - 1 : 0 ) );
-                        if( in_window && ( ( take >> bit ) & 1u ) ) px[ bit ] = cw;
-                    }
-                }
-                if( rem ) // nobody covers these: background (main.cpp:260)
-                {
-#pragma unroll
-                    for( int bit = 0; bit < S * S; bit++ )
-                        if( ( rem >> bit ) & 1u ) px[ bit ] = 0xFF000000u;
-                }
-            }
-            uint8_t* dst = out + ( ( size_t )( a.flip_output ? out_h - 1 - ( size_t )gy * O : ( size_t )gy * O ) * out_w + ( size_t )gx * O ) * 4;
-            store_cell< S, A >( dst, row_step, px );
-        }
-    }
-    else
-    {
-        for( int idx = tid; idx < C::TW * C::TH; idx += kThreads )
-        {
-            int ly = idx / C::TW, lx = idx - ly * C::TW;
-            int gx = x0 + lx, gy = y0 + ly;
-            if( gx >= a.width || gy >= a.height ) continue;
-            const int cell = ( ly + 1 ) * C::CW + ( lx + 1 );
-            const uint32_t* col = s_col + ( ly + 2 ) * C::KW + ( lx + 2 );
-            // the 3x3 neighbourhood's masks; candidates are visited in DESCENDING node index:
-            // (dj,di) = (+1,+1) (+1,0) (+1,-1) (0,+1) (0,0) (0,-1) (-1,+1) (-1,0) (-1,-1)
-            uint8_t* dst = out + ( ( size_t )( a.flip_output ? out_h - 1 - ( size_t )gy * O : ( size_t )gy * O ) * out_w + ( size_t )gx * O ) * 4;
-#pragma unroll 1
-            for( int ob = 0; ob < O; ob++ ) // one output row = A sample rows
-            {
-                ColourSum sum[ O ];
-                uint32_t px[ S ];
-#pragma unroll 1
-                for( int r = 0; r < A; r++ )
-                {
-                    const int b = ob * A + r;
-#pragma unroll
-                    for( int k = 0; k < S; k++ ) px[ k ] = 0xFF000000u; // background (main.cpp:260)
-                    uint32_t rem = C::FULL;
-#pragma unroll
-                    for( int dj = 1; dj >= -1; dj-- )
-                    {
-                        const int ky = b - dj * S + C::H;
-                        if( ky < 0 || ky >= C::R ) continue;
-#pragma unroll
-                        for( int di = 1; di >= -1; di-- )
-                        {
-                            const uint32_t m = s_mask[ ky * C::NC + cell + dj * C::CW + di ] & ~C::WIDE;
-                            const uint32_t field = di == 0 ? ( m >> C::H ) : ( di > 0 ? ( m << ( S - C::H ) ) : ( m >> ( S + C::H ) ) );
-                            const uint32_t take = field & rem;
-                            if( take )
-                            {
-                                const uint32_t cw = col[ dj * C::KW + di ];
-#pragma unroll
-                                for( int k = 0; k < S; k++ )
-                                    if( ( take >> k ) & 1u ) px[ k ] = cw;
-                                rem &= ~take;
-                            }
-                        }
-                    }
-                    if( A > 1 )
-                    {
-#pragma unroll
-                        for( int k = 0; k < S; k++ ) sum[ k / A ].add( px[ k ] );
-                    }
-                }
-                if( A > 1 )
-                {
-#pragma unroll
-                    for( int k = 0; k < O; k++ ) px[ k ] = sum[ k ].template mean< A * A >();
-                }
-                store_row< O >( dst + ( ptrdiff_t )ob * row_step, px );
-            }
-        }
-    }
-}
 
 // ---- polygon export: one thread per pixel, everything from global memory ----------------------
 struct GlobalEnv
@@ -1236,41 +92,6 @@ __global__ void __launch_bounds__( kThreads ) polygon_kernel( RasterArgs a )
     if( a.poly_count ) a.poly_count[ n ] = m;
 }
 
-template< int S, int A >
-cudaError_t launch_raster_sa( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream )
-{
-    typedef Cfg< S > C;
-    dim3 grid( ( a.width + C::TW - 1 ) / C::TW, ( a.height + C::TH - 1 ) / C::TH, a.n_frames );
-    cudaError_t e;
-    if( graph_map && img_map )
-    {
-        e = cudaFuncSetAttribute( raster_kernel< S, A, true >, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes );
-        if( e != cudaSuccess ) return e;
-        raster_kernel< S, A, true ><<< grid, kThreads, C::smem_bytes, stream >>>( *graph_map, *img_map, a );
-    }
-    else
-    {
-        CUtensorMap dummy;
-        memset( &dummy, 0, sizeof( dummy ) );
-        e = cudaFuncSetAttribute( raster_kernel< S, A, false >, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes );
-        if( e != cudaSuccess ) return e;
-        raster_kernel< S, A, false ><<< grid, kThreads, C::smem_bytes, stream >>>( dummy, dummy, a );
-    }
-    return cudaGetLastError();
-}
-
-// a.scale is the SAMPLING scale S; a.aa = A (1, 2 or 4) samples per output pixel and axis, S % A == 0
-template< int S >
-cudaError_t launch_raster_s( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream )
-{
-    if( a.aa == 1 ) return launch_raster_sa< S, 1 >( a, graph_map, img_map, stream );
-    if constexpr( S % 2 == 0 )
-        if( a.aa == 2 ) return launch_raster_sa< S, 2 >( a, graph_map, img_map, stream );
-    if constexpr( S % 4 == 0 )
-        if( a.aa == 4 ) return launch_raster_sa< S, 4 >( a, graph_map, img_map, stream );
-    return cudaErrorInvalidValue;
-}
-
 template< int S >
 cudaError_t build_lut_s( const CellTablePtrs& tab, uint32_t* lut, cudaStream_t stream )
 {
@@ -1280,23 +101,11 @@ cudaError_t build_lut_s( const CellTablePtrs& tab, uint32_t* lut, cudaStream_t s
 
 } // namespace
 
-bool raster_scale_supported( int scale ) { return scale >= 1 && scale <= 8 && scale != 5 && scale != 7; }
+bool raster_scale_supported( int scale ) { return scale >= 1 && scale <= 8; }
 bool raster_aa_supported( int out_scale, int aa )
 {
     return ( aa == 1 || aa == 2 || aa == 4 ) && out_scale >= 1 && raster_scale_supported( out_scale * aa );
 }
-
-#define PAR_FOR_SCALE( scale, CALL )  \
-    switch( scale )                    \
-    {                                  \
-        case 1: { CALL( 1 ); }         \
-        case 2: { CALL( 2 ); }         \
-        case 3: { CALL( 3 ); }         \
-        case 4: { CALL( 4 ); }         \
-        case 6: { CALL( 6 ); }         \
-        case 8: { CALL( 8 ); }         \
-        default: break;                \
-    }
 
 size_t mask_lut_words( int scale )
 {
@@ -1355,12 +164,20 @@ void raster_img_tma_box( int scale, uint32_t box[ 3 ] )
 #undef PAR_RAWP
 }
 
+cudaError_t launch_raster_rgba8( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream )
+{
+    return launch_raster_fmt< kFmtRgba8 >( a, graph_map, img_map, stream );
+}
+
 cudaError_t launch_raster( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream )
 {
-#define PAR_RASTER( S ) return launch_raster_s< S >( a, graph_map, img_map, stream )
-    PAR_FOR_SCALE( a.scale, PAR_RASTER )
-#undef PAR_RASTER
-    return cudaErrorInvalidValue;
+    switch( a.out_format ) // one translation unit per output format (they compile in parallel)
+    {
+        case PAR_OUT_RGBA8: return launch_raster_rgba8( a, graph_map, img_map, stream );
+        case PAR_OUT_BGR8: return launch_raster_bgr8( a, graph_map, img_map, stream );
+        case PAR_OUT_INDEX8: return launch_raster_index8( a, graph_map, img_map, stream );
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_polygons( const RasterArgs& a, cudaStream_t stream )

@@ -10,13 +10,18 @@
 // topology allows).  Every device then runs the ordinary single-GPU path on its extended strip and
 // returns its own rows.  Connected components are labelled per extended strip (labels are global
 // pixel indices) and stitched exactly: on the last own row of every strip both neighbours have
-// labelled the same pixels, which yields label equivalences; a tiny host union-find keeps the
-// minimum of every class and a relabel kernel applies the map.  Because the label of a component is
+// labelled the same pixels, which yields label equivalences; every device gathers the seam rows of all
+// strips (peer copies), closes the equivalences with a one-CTA union-find that keeps the minimum of
+// every class, and relabels its own rows — no host round trip.  Because the label of a component is
 // its minimum index, the result equals the single-GPU labelling bit for bit.
+// Two entries: host image in / host results out (par_group_remaster_host), and device-resident
+// (par_group_remaster_device: the strips' own rows are already in their input buffers, results stay
+// on the devices) — the halo exchange, the kernels and the stitch are the same stream-ordered code.
 #include "../../include/pixelart_b200.h"
 #include "kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <string>
@@ -36,9 +41,9 @@ struct Strip
     cudaStream_t stream = nullptr, copy_stream = nullptr; // copy_stream: image / graph rows back to the host while the labels are stitched
     uint8_t *d_in = nullptr, *d_rgba = nullptr, *d_graph = nullptr, *d_aux = nullptr;
     int32_t* d_labels = nullptr;
-    int32_t *d_map_keys = nullptr, *d_map_vals = nullptr;
-    size_t map_cap = 0;
-    cudaEvent_t uploaded = nullptr, computed = nullptr;
+    int32_t* d_seams = nullptr;                    // [n_seams][2][W]: the label rows of every seam, gathered from all strips
+    int32_t *d_tab_keys = nullptr, *d_tab_parent = nullptr; // the seam labels' union-find (open-addressing table)
+    cudaEvent_t ready = nullptr, computed = nullptr, labelled = nullptr, t_begin = nullptr, t_end = nullptr;
 };
 
 __global__ void offset_labels_kernel( int32_t* lab, size_t n, int32_t offset )
@@ -47,26 +52,100 @@ __global__ void offset_labels_kernel( int32_t* lab, size_t n, int32_t offset )
     if( t < n ) lab[ t ] += offset;
 }
 
-// labels that appear in `keys` (sorted) are replaced by the class minimum in `vals`
-__global__ void relabel_kernel( int32_t* lab, size_t n, const int32_t* __restrict__ keys, const int32_t* __restrict__ vals, int m )
+// ---- label stitch on the device ---------------------------------------------------------------------------------
+// On the last own row of strip k both k and k+1 labelled the same pixels: every column gives an equivalence between two
+// labels.  The distinct seam labels are the nodes of a union-find held in an open-addressing table (key = label,
+// parent = a label of the same class, roots point at themselves); link-by-minimum makes the root the class minimum,
+// which is the canonical label.  One CTA closes the equivalences of ALL seams (<= 7 x 4096 pairs), every device does so
+// redundantly on its own copy of the seam rows, then relabels its own rows through the table.
+constexpr int32_t kNoKey = -1;
+__device__ __forceinline__ uint32_t tab_hash( int32_t label, uint32_t mask ) { return ( ( uint32_t )label * 0x9E3779B1u ) >> 7 & mask; }
+
+__device__ __forceinline__ int tab_find_slot( const int32_t* keys, uint32_t mask, int32_t label )
+{
+    uint32_t h = tab_hash( label, mask );
+    for( ;; )
+    {
+        const int32_t k = keys[ h ];
+        if( k == label ) return ( int )h;
+        if( k == kNoKey ) return -1;
+        h = ( h + 1u ) & mask;
+    }
+}
+
+__device__ __forceinline__ int32_t tab_root( const int32_t* keys, const int32_t* parent, uint32_t mask, int32_t label )
+{
+    for( ;; )
+    {
+        const int32_t p = *( volatile const int32_t* )&parent[ tab_find_slot( keys, mask, label ) ];
+        if( p == label ) return label;
+        label = p;
+    }
+}
+
+__global__ void __launch_bounds__( 1024 ) stitch_labels_kernel( const int32_t* __restrict__ seams, int n_seams, int width, int32_t* keys, int32_t* parent,
+                                                                uint32_t mask )
+{
+    const int n_labels = 2 * n_seams * width;
+    // (1) the distinct labels become nodes, each its own root
+    for( int i = threadIdx.x; i < n_labels; i += blockDim.x )
+    {
+        const int32_t label = seams[ i ];
+        uint32_t h = tab_hash( label, mask );
+        for( ;; )
+        {
+            const int32_t k = atomicCAS( &keys[ h ], kNoKey, label );
+            if( k == kNoKey ) parent[ h ] = label;
+            if( k == kNoKey || k == label ) break;
+            h = ( h + 1u ) & mask;
+        }
+    }
+    __syncthreads();
+    // (2) one union per column of every seam: the larger root goes under the smaller one (lock-free, roots only decrease)
+    for( int i = threadIdx.x; i < n_seams * width; i += blockDim.x )
+    {
+        const int k = i / width, x = i - k * width;
+        int32_t a = seams[ ( 2 * k ) * width + x ], b = seams[ ( 2 * k + 1 ) * width + x ];
+        for( ;; )
+        {
+            a = tab_root( keys, parent, mask, a );
+            b = tab_root( keys, parent, mask, b );
+            if( a == b ) break;
+            if( a < b )
+            {
+                const int32_t t = a;
+                a = b;
+                b = t;
+            }
+            const int32_t old = atomicMin( &parent[ tab_find_slot( keys, mask, a ) ], b );
+            if( old == a ) break;
+            a = old;
+        }
+    }
+    __syncthreads();
+    // (3) flatten: every node points at its class minimum
+    for( uint32_t h = threadIdx.x; h <= mask; h += blockDim.x )
+        if( keys[ h ] != kNoKey ) parent[ h ] = tab_root( keys, parent, mask, keys[ h ] );
+}
+
+// labels that are nodes of the seam union-find are replaced by their class minimum (most labels are not: one probe)
+__global__ void relabel_kernel( int32_t* lab, size_t n, const int32_t* __restrict__ keys, const int32_t* __restrict__ parent, uint32_t mask )
 {
     size_t t = ( size_t )blockIdx.x * blockDim.x + threadIdx.x;
     if( t >= n ) return;
     const int32_t v = lab[ t ];
-    int lo = 0, hi = m - 1;
-    while( lo <= hi )
+    uint32_t h = tab_hash( v, mask );
+    for( ;; )
     {
-        int mid = ( lo + hi ) >> 1;
-        int32_t k = __ldg( keys + mid );
+        const int32_t k = __ldg( keys + h );
+        if( k == kNoKey ) return;
         if( k == v )
         {
-            lab[ t ] = __ldg( vals + mid );
+            const int32_t r = __ldg( parent + h );
+            if( r != v ) lab[ t ] = r;
             return;
         }
-        if( k < v )
-            lo = mid + 1;
-        else
-            hi = mid - 1;
+        h = ( h + 1u ) & mask;
     }
 }
 
@@ -76,6 +155,8 @@ struct par_group
 {
     int width = 0, height = 0, scale = 0;
     std::vector< Strip > strips;
+    uint32_t tab_mask = 0; // slots - 1 of the seam tables
+    double last_wall_ms = 0.0, last_device_ms = 0.0;
     std::string error;
     int fail( int st, const char* fmt, ... )
     {
@@ -89,11 +170,137 @@ struct par_group
     }
 };
 
+namespace {
+
+// the caller's current device is restored when an entry point returns
+struct GroupDeviceGuard
+{
+    int prev = -1;
+    GroupDeviceGuard() { if( cudaGetDevice( &prev ) != cudaSuccess ) prev = -1; }
+    ~GroupDeviceGuard() { if( prev >= 0 ) cudaSetDevice( prev ); }
+};
+
+int bytes_per_pixel_of( int out_format ) { return out_format == PAR_OUT_RGBA8 ? 4 : ( out_format == PAR_OUT_BGR8 ? 3 : 1 ); }
+
+// Steps (2) and (3) of the tiled path, everything stream-ordered and asynchronous: apron rows from the neighbouring
+// devices (ordered after their `ready` event), the ordinary path on every extended strip, and — with labels — the
+// per-strip labelling, the gather of all seam rows onto every device, the stitch and the relabelling of the own rows.
+int exchange_and_compute( par_group* g, unsigned flags, int out_format, bool want_image, bool want_labels )
+{
+    const int W = g->width;
+    const size_t row_in = ( size_t )3 * W; // strips are stored densely on the devices
+    cudaError_t e = cudaSuccess;
+    // (2) apron rows come from the neighbouring devices (peer copies over NVLink)
+    for( size_t k = 0; k < g->strips.size(); k++ )
+    {
+        Strip& s = g->strips[ k ];
+        cudaSetDevice( s.device );
+        if( k > 0 && s.load_b < s.own_b )
+        {
+            Strip& n = g->strips[ k - 1 ];
+            cudaStreamWaitEvent( s.stream, n.ready, 0 );
+            const size_t bytes = ( size_t )( s.own_b - s.load_b ) * row_in;
+            e = cudaMemcpyPeerAsync( s.d_in, s.device, n.d_in + ( size_t )( s.load_b - n.load_b ) * row_in, n.device, bytes, s.stream );
+            if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "peer copy: %s", cudaGetErrorString( e ) );
+        }
+        if( k + 1 < g->strips.size() && s.load_e > s.own_e )
+        {
+            Strip& n = g->strips[ k + 1 ];
+            cudaStreamWaitEvent( s.stream, n.ready, 0 );
+            const size_t bytes = ( size_t )( s.load_e - s.own_e ) * row_in;
+            e = cudaMemcpyPeerAsync( s.d_in + ( size_t )( s.own_e - s.load_b ) * row_in, s.device,
+                                     n.d_in + ( size_t )( s.own_e - n.load_b ) * row_in, n.device, bytes, s.stream );
+            if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "peer copy: %s", cudaGetErrorString( e ) );
+        }
+    }
+    // (3) the ordinary path on every extended strip
+    for( auto& s : g->strips )
+    {
+        cudaSetDevice( s.device );
+        par_job d = {};
+        d.bgr = s.d_in;
+        d.width = W;
+        d.height = s.load_e - s.load_b;
+        d.widthstep = 3 * W;
+        d.n_frames = 1;
+        d.scale = g->scale;
+        d.flags = flags;
+        d.out_format = out_format;
+        d.rgba = want_image ? s.d_rgba : nullptr;
+        d.graph = s.d_graph;
+        d.graph_aux = s.d_aux;
+        int st = par_remaster_device( s.ctx, &d );
+        if( st != PAR_OK ) return g->fail( st, "strip on device %d: %s", s.device, par_last_error( s.ctx ) );
+        cudaEventRecord( s.computed, s.stream );
+        if( want_labels )
+        {
+            // Label only rows whose graph bytes are exact: the strip's own rows plus ONE row either side (needed
+            // for the stitch).  The outer apron rows carry graph bytes computed without their full context and
+            // must not be allowed to connect anything.  The window is labelled as an image of its own (links
+            // leaving it are ignored) and then shifted to global pixel indices.
+            const int win_b = std::max( s.load_b, s.own_b - 1 ), win_e = std::min( s.load_e, s.own_e + 1 );
+            par_job l = d;
+            l.rgba = nullptr;
+            l.height = win_e - win_b;
+            l.graph = s.d_graph + ( size_t )( win_b - s.load_b ) * W;
+            l.labels = s.d_labels + ( size_t )( win_b - s.load_b ) * W;
+            st = par_stage_cc_labels( s.ctx, &l );
+            if( st != PAR_OK ) return g->fail( st, "labels on device %d: %s", s.device, par_last_error( s.ctx ) );
+            const size_t n = ( size_t )W * l.height;
+            offset_labels_kernel<<< ( unsigned )( ( n + 255 ) / 256 ), 256, 0, s.stream >>>( l.labels, n, win_b * W );
+            cudaEventRecord( s.labelled, s.stream );
+        }
+    }
+    // (4) stitch: every device gathers the two label rows of every seam (peer copies, ordered after the strips'
+    // `labelled` events), closes the equivalences in one CTA and relabels its own rows
+    const size_t n_seams = g->strips.size() - 1;
+    if( want_labels && n_seams > 0 )
+        for( auto& s : g->strips )
+        {
+            cudaSetDevice( s.device );
+            for( auto& o : g->strips )
+                if( &o != &s ) cudaStreamWaitEvent( s.stream, o.labelled, 0 );
+            for( size_t k = 0; k < n_seams && e == cudaSuccess; k++ )
+            {
+                Strip &a = g->strips[ k ], &b = g->strips[ k + 1 ];
+                const int row = a.own_e - 1;
+                e = cudaMemcpyPeerAsync( s.d_seams + ( 2 * k ) * W, s.device, a.d_labels + ( size_t )( row - a.load_b ) * W, a.device, ( size_t )W * 4, s.stream );
+                if( e == cudaSuccess )
+                    e = cudaMemcpyPeerAsync( s.d_seams + ( 2 * k + 1 ) * W, s.device, b.d_labels + ( size_t )( row - b.load_b ) * W, b.device, ( size_t )W * 4,
+                                             s.stream );
+            }
+            if( e == cudaSuccess ) e = cudaMemsetAsync( s.d_tab_keys, 0xFF, ( ( size_t )g->tab_mask + 1 ) * 4, s.stream );
+            if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "seam rows: %s", cudaGetErrorString( e ) );
+            stitch_labels_kernel<<< 1, 1024, 0, s.stream >>>( s.d_seams, ( int )n_seams, W, s.d_tab_keys, s.d_tab_parent, g->tab_mask );
+            const size_t n = ( size_t )W * ( s.own_e - s.own_b );
+            relabel_kernel<<< ( unsigned )( ( n + 255 ) / 256 ), 256, 0, s.stream >>>( s.d_labels + ( size_t )( s.own_b - s.load_b ) * W, n, s.d_tab_keys,
+                                                                                       s.d_tab_parent, g->tab_mask );
+            e = cudaGetLastError();
+            if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "stitch: %s", cudaGetErrorString( e ) );
+        }
+    return PAR_OK;
+}
+
+int check_group_job( par_group* g, unsigned flags, int out_format )
+{
+    if( out_format != PAR_OUT_RGBA8 && out_format != PAR_OUT_BGR8 )
+        return g->fail( PAR_ERR_INVALID, "tiled mode offers PAR_OUT_RGBA8 and PAR_OUT_BGR8 (a palette would be per strip)" );
+    if( flags & ( PAR_FLAG_AA2 | PAR_FLAG_AA4 ) )
+    {
+        const int aa = ( flags & PAR_FLAG_AA4 ) ? 4 : 2;
+        if( !par::raster_aa_supported( g->scale, aa ) ) return g->fail( PAR_ERR_INVALID, "unsupported scale %d with %dx%d samples per pixel", g->scale, aa, aa );
+    }
+    return PAR_OK;
+}
+
+} // namespace
+
 extern "C" {
 
 void par_group_destroy( par_group* g )
 {
     if( !g ) return;
+    GroupDeviceGuard guard;
     for( auto& s : g->strips )
     {
         if( !s.ctx ) continue; // never created (par_group_create failed part-way): nothing on that device
@@ -104,10 +311,11 @@ void par_group_destroy( par_group* g )
         cudaFree( s.d_graph );
         cudaFree( s.d_aux );
         cudaFree( s.d_labels );
-        cudaFree( s.d_map_keys );
-        cudaFree( s.d_map_vals );
-        if( s.uploaded ) cudaEventDestroy( s.uploaded );
-        if( s.computed ) cudaEventDestroy( s.computed );
+        cudaFree( s.d_seams );
+        cudaFree( s.d_tab_keys );
+        cudaFree( s.d_tab_parent );
+        for( cudaEvent_t ev : { s.ready, s.computed, s.labelled, s.t_begin, s.t_end } )
+            if( ev ) cudaEventDestroy( ev );
         if( s.copy_stream ) cudaStreamDestroy( s.copy_stream );
         if( s.ctx ) par_destroy( s.ctx );
         if( s.stream ) cudaStreamDestroy( s.stream );
@@ -135,11 +343,16 @@ int par_group_create( par_group** out, const int* devices, int n_devices, int wi
         g_group_create_error = "par_group_create: strips would be shorter than the 40-row apron; use fewer devices";
         return PAR_ERR_INVALID;
     }
+    GroupDeviceGuard guard;
     par_group* g = new par_group();
     g->width = width;
     g->height = height;
     g->scale = scale;
     g->strips.resize( n_devices );
+    const size_t seam_labels = ( size_t )2 * ( n_devices - 1 ) * width;
+    uint32_t slots = 1024;
+    while( slots < 4 * seam_labels ) slots <<= 1;
+    g->tab_mask = slots - 1;
     const int base = height / n_devices, extra = height % n_devices;
     for( int k = 0; k < n_devices; k++ )
     {
@@ -166,8 +379,14 @@ int par_group_create( par_group** out, const int* devices, int n_devices, int wi
         if( e == cudaSuccess ) e = cudaMalloc( &s.d_graph, px );
         if( e == cudaSuccess ) e = cudaMalloc( &s.d_aux, px );
         if( e == cudaSuccess ) e = cudaMalloc( &s.d_labels, px * 4 );
-        if( e == cudaSuccess ) e = cudaEventCreateWithFlags( &s.uploaded, cudaEventDisableTiming );
+        if( e == cudaSuccess && n_devices > 1 ) e = cudaMalloc( &s.d_seams, seam_labels * 4 );
+        if( e == cudaSuccess && n_devices > 1 ) e = cudaMalloc( &s.d_tab_keys, ( size_t )slots * 4 );
+        if( e == cudaSuccess && n_devices > 1 ) e = cudaMalloc( &s.d_tab_parent, ( size_t )slots * 4 );
+        if( e == cudaSuccess ) e = cudaEventCreateWithFlags( &s.ready, cudaEventDisableTiming );
         if( e == cudaSuccess ) e = cudaEventCreateWithFlags( &s.computed, cudaEventDisableTiming );
+        if( e == cudaSuccess ) e = cudaEventCreateWithFlags( &s.labelled, cudaEventDisableTiming );
+        if( e == cudaSuccess ) e = cudaEventCreate( &s.t_begin );
+        if( e == cudaSuccess ) e = cudaEventCreate( &s.t_end );
         if( e == cudaSuccess ) e = cudaStreamCreateWithFlags( &s.copy_stream, cudaStreamNonBlocking );
         if( e != cudaSuccess )
         {
@@ -176,24 +395,82 @@ int par_group_create( par_group** out, const int* devices, int n_devices, int wi
             return PAR_ERR_CUDA;
         }
     }
-    // direct NVLink/PCIe peer access between neighbouring strips where the topology allows it
-    for( int k = 0; k + 1 < n_devices; k++ )
-    {
-        const int a = g->strips[ k ].device, b = g->strips[ k + 1 ].device;
-        if( a == b ) continue;
-        int ok = 0;
-        if( cudaDeviceCanAccessPeer( &ok, a, b ) == cudaSuccess && ok )
+    // direct NVLink/PCIe peer access between all pairs of devices where the topology allows it (aprons travel between
+    // neighbours, seam label rows between all strips)
+    for( int p = 0; p < n_devices; p++ )
+        for( int q = 0; q < n_devices; q++ )
         {
-            cudaSetDevice( a );
-            if( cudaDeviceEnablePeerAccess( b, 0 ) != cudaSuccess ) cudaGetLastError();
+            const int a = g->strips[ p ].device, b = g->strips[ q ].device;
+            if( a == b ) continue;
+            int ok = 0;
+            if( cudaDeviceCanAccessPeer( &ok, a, b ) == cudaSuccess && ok )
+            {
+                cudaSetDevice( a );
+                if( cudaDeviceEnablePeerAccess( b, 0 ) != cudaSuccess ) cudaGetLastError(); // (already enabled)
+            }
         }
-        if( cudaDeviceCanAccessPeer( &ok, b, a ) == cudaSuccess && ok )
-        {
-            cudaSetDevice( b );
-            if( cudaDeviceEnablePeerAccess( a, 0 ) != cudaSuccess ) cudaGetLastError();
-        }
-    }
     *out = g;
+    return PAR_OK;
+}
+
+int par_group_n_strips( const par_group* g ) { return g ? ( int )g->strips.size() : 0; }
+
+int par_group_strip( const par_group* g, int k, par_strip* out )
+{
+    if( !g || !out || k < 0 || k >= ( int )g->strips.size() ) return PAR_ERR_INVALID;
+    const Strip& s = g->strips[ k ];
+    out->device = s.device;
+    out->own_begin = s.own_b;
+    out->own_end = s.own_e;
+    out->load_begin = s.load_b;
+    out->load_end = s.load_e;
+    out->bgr = s.d_in;
+    out->image = s.d_rgba;
+    out->graph = s.d_graph;
+    out->graph_aux = s.d_aux;
+    out->labels = s.d_labels;
+    return PAR_OK;
+}
+
+int par_group_remaster_device( par_group* g, unsigned flags, int out_format, int want_image, int want_labels )
+{
+    if( !g ) return PAR_ERR_INVALID;
+    int st = check_group_job( g, flags, out_format );
+    if( st ) return st;
+    GroupDeviceGuard guard;
+    const auto t0 = std::chrono::steady_clock::now();
+    for( auto& s : g->strips ) // the caller has put every strip's own rows into its input buffer
+    {
+        cudaSetDevice( s.device );
+        cudaEventRecord( s.t_begin, s.stream );
+        cudaEventRecord( s.ready, s.stream );
+    }
+    st = exchange_and_compute( g, flags, out_format, want_image != 0, want_labels != 0 );
+    if( st ) return st;
+    for( auto& s : g->strips )
+    {
+        cudaSetDevice( s.device );
+        cudaEventRecord( s.t_end, s.stream );
+    }
+    g->last_device_ms = 0.0;
+    for( auto& s : g->strips )
+    {
+        cudaSetDevice( s.device );
+        cudaError_t e = cudaStreamSynchronize( s.stream );
+        if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "strip on device %d: %s", s.device, cudaGetErrorString( e ) );
+        float ms = 0.f;
+        cudaEventElapsedTime( &ms, s.t_begin, s.t_end );
+        g->last_device_ms = std::max( g->last_device_ms, ( double )ms );
+    }
+    g->last_wall_ms = std::chrono::duration< double, std::milli >( std::chrono::steady_clock::now() - t0 ).count();
+    return PAR_OK;
+}
+
+int par_group_last_ms( const par_group* g, double* wall_ms, double* device_ms )
+{
+    if( !g ) return PAR_ERR_INVALID;
+    if( wall_ms ) *wall_ms = g->last_wall_ms;
+    if( device_ms ) *device_ms = g->last_device_ms;
     return PAR_OK;
 }
 
@@ -205,8 +482,11 @@ int par_group_remaster_host( par_group* g, const par_job* j )
         return g->fail( PAR_ERR_INVALID, "job does not match the group (%dx%d s=%d, one frame)", g->width, g->height, g->scale );
     if( j->widthstep < 3 * j->width ) return g->fail( PAR_ERR_INVALID, "widthstep < 3*width" );
     if( j->polygons ) return g->fail( PAR_ERR_INVALID, "polygon export is not offered in tiled mode" );
+    int st = check_group_job( g, j->flags, j->out_format );
+    if( st ) return st;
+    GroupDeviceGuard guard;
     const int W = g->width, S = g->scale;
-    const size_t row_in = ( size_t )3 * W; // strips are stored densely on the devices
+    const size_t row_in = ( size_t )3 * W;
     cudaError_t e = cudaSuccess;
 
     // (1) every device receives its OWN rows from the host
@@ -217,69 +497,14 @@ int par_group_remaster_host( par_group* g, const par_job* j )
         e = cudaMemcpy2DAsync( dst, row_in, j->bgr + ( size_t )s.own_b * j->widthstep, j->widthstep, row_in, s.own_e - s.own_b,
                                cudaMemcpyHostToDevice, s.stream );
         if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "H2D: %s", cudaGetErrorString( e ) );
-        cudaEventRecord( s.uploaded, s.stream );
+        cudaEventRecord( s.ready, s.stream );
     }
-    // (2) apron rows come from the neighbouring devices (peer copies over NVLink), ordered after their upload
-    for( size_t k = 0; k < g->strips.size(); k++ )
-    {
-        Strip& s = g->strips[ k ];
-        cudaSetDevice( s.device );
-        if( k > 0 && s.load_b < s.own_b )
-        {
-            Strip& n = g->strips[ k - 1 ];
-            cudaStreamWaitEvent( s.stream, n.uploaded, 0 );
-            const size_t bytes = ( size_t )( s.own_b - s.load_b ) * row_in;
-            e = cudaMemcpyPeerAsync( s.d_in, s.device, n.d_in + ( size_t )( s.load_b - n.load_b ) * row_in, n.device, bytes, s.stream );
-            if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "peer copy: %s", cudaGetErrorString( e ) );
-        }
-        if( k + 1 < g->strips.size() && s.load_e > s.own_e )
-        {
-            Strip& n = g->strips[ k + 1 ];
-            cudaStreamWaitEvent( s.stream, n.uploaded, 0 );
-            const size_t bytes = ( size_t )( s.load_e - s.own_e ) * row_in;
-            e = cudaMemcpyPeerAsync( s.d_in + ( size_t )( s.own_e - s.load_b ) * row_in, s.device,
-                                     n.d_in + ( size_t )( s.own_e - n.load_b ) * row_in, n.device, bytes, s.stream );
-            if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "peer copy: %s", cudaGetErrorString( e ) );
-        }
-    }
-    // (3) the ordinary path on every extended strip
-    for( auto& s : g->strips )
-    {
-        cudaSetDevice( s.device );
-        par_job d = *j;
-        d.bgr = s.d_in;
-        d.height = s.load_e - s.load_b;
-        d.widthstep = 3 * W;
-        d.frame_stride = 0;
-        d.rgba = j->rgba ? s.d_rgba : nullptr;
-        d.graph = s.d_graph;
-        d.graph_aux = s.d_aux;
-        d.labels = nullptr;
-        d.polygons = nullptr;
-        d.poly_count = nullptr;
-        int st = par_remaster_device( s.ctx, &d );
-        if( st != PAR_OK ) return g->fail( st, "strip on device %d: %s", s.device, par_last_error( s.ctx ) );
-        cudaEventRecord( s.computed, s.stream );
-        if( j->labels )
-        {
-            // Label only rows whose graph bytes are exact: the strip's own rows plus ONE row either side (needed
-            // for the stitch).  The outer apron rows carry graph bytes computed without their full context and
-            // must not be allowed to connect anything.  The window is labelled as an image of its own (links
-            // leaving it are ignored) and then shifted to global pixel indices.
-            const int win_b = std::max( s.load_b, s.own_b - 1 ), win_e = std::min( s.load_e, s.own_e + 1 );
-            par_job l = d;
-            l.height = win_e - win_b;
-            l.graph = s.d_graph + ( size_t )( win_b - s.load_b ) * W;
-            l.labels = s.d_labels + ( size_t )( win_b - s.load_b ) * W;
-            st = par_stage_cc_labels( s.ctx, &l );
-            if( st != PAR_OK ) return g->fail( st, "labels on device %d: %s", s.device, par_last_error( s.ctx ) );
-            const size_t n = ( size_t )W * l.height;
-            offset_labels_kernel<<< ( unsigned )( ( n + 255 ) / 256 ), 256, 0, s.stream >>>( l.labels, n, win_b * W );
-        }
-    }
-    // (4) own rows of the image and the graphs go back to the host as soon as the strip has them — the big copies
-    // overlap the label stitching below (the labels follow once they are final)
-    const size_t out_row = ( size_t )W * S * 4;
+    // (2)-(4) halo exchange, kernels, label stitch: all on the devices
+    st = exchange_and_compute( g, j->flags, j->out_format, j->rgba != nullptr, j->labels != nullptr );
+    if( st ) return st;
+    // (5) own rows of the image and the graphs go back to the host as soon as the strip has them (second stream: the big
+    // copies overlap the label stitching); the labels follow on the strip's stream once they are final
+    const size_t out_row = ( size_t )W * S * bytes_per_pixel_of( j->out_format );
     for( auto& s : g->strips )
     {
         cudaSetDevice( s.device );
@@ -297,93 +522,15 @@ int par_group_remaster_host( par_group* g, const par_job* j )
         if( e == cudaSuccess && j->graph ) e = cudaMemcpyAsync( j->graph + ( size_t )W * s.own_b, s.d_graph + off_px, own_px, cudaMemcpyDeviceToHost, cs );
         if( e == cudaSuccess && j->graph_aux )
             e = cudaMemcpyAsync( j->graph_aux + ( size_t )W * s.own_b, s.d_aux + off_px, own_px, cudaMemcpyDeviceToHost, cs );
+        if( e == cudaSuccess && j->labels )
+            e = cudaMemcpyAsync( j->labels + ( size_t )W * s.own_b, s.d_labels + off_px, own_px * 4, cudaMemcpyDeviceToHost, s.stream );
         if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "D2H: %s", cudaGetErrorString( e ) );
     }
-    // (5) stitch the labels: on the last own row of strip k both k and k+1 labelled the same pixels.  All seam rows
-    // are fetched at once; the equivalences (<= 7 x 4096 pairs) are closed by a union-find over the distinct labels.
-    std::vector< int32_t > keys, vals; // relabelling map, alive until the final synchronize
-    if( j->labels && g->strips.size() > 1 )
-    {
-        const size_t n_seams = g->strips.size() - 1;
-        std::vector< int32_t > rows( 2 * n_seams * W );
-        for( size_t k = 0; k < n_seams; k++ )
-        {
-            Strip &a = g->strips[ k ], &b = g->strips[ k + 1 ];
-            const int row = a.own_e - 1;
-            cudaSetDevice( a.device );
-            cudaMemcpyAsync( rows.data() + ( 2 * k ) * W, a.d_labels + ( size_t )( row - a.load_b ) * W, ( size_t )W * 4, cudaMemcpyDeviceToHost, a.stream );
-            cudaSetDevice( b.device );
-            cudaMemcpyAsync( rows.data() + ( 2 * k + 1 ) * W, b.d_labels + ( size_t )( row - b.load_b ) * W, ( size_t )W * 4, cudaMemcpyDeviceToHost, b.stream );
-        }
-        for( auto& s : g->strips )
-        {
-            cudaSetDevice( s.device );
-            e = cudaStreamSynchronize( s.stream );
-            if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "label rows: %s", cudaGetErrorString( e ) );
-        }
-        std::vector< int32_t > ids( rows ); // the distinct labels on the seams, sorted: position = union-find node
-        std::sort( ids.begin(), ids.end() );
-        ids.erase( std::unique( ids.begin(), ids.end() ), ids.end() );
-        std::vector< int32_t > parent( ids.size() );
-        for( size_t k = 0; k < parent.size(); k++ ) parent[ k ] = ( int32_t )k;
-        auto node = [ & ]( int32_t label ) { return ( int32_t )( std::lower_bound( ids.begin(), ids.end(), label ) - ids.begin() ); };
-        auto find = [ & ]( int32_t x ) {
-            while( parent[ x ] != x ) x = parent[ x ] = parent[ parent[ x ] ];
-            return x;
-        };
-        for( size_t k = 0; k < n_seams; k++ )
-            for( int x = 0; x < W; x++ )
-            {
-                const int32_t p = find( node( rows[ ( 2 * k ) * W + x ] ) ), q = find( node( rows[ ( 2 * k + 1 ) * W + x ] ) );
-                if( p != q ) parent[ std::max( p, q ) ] = std::min( p, q ); // ids are sorted: the smaller node is the smaller label
-            }
-        for( size_t k = 0; k < ids.size(); k++ )
-        {
-            const int32_t r = find( ( int32_t )k );
-            if( r != ( int32_t )k )
-            {
-                keys.push_back( ids[ k ] ); // ascending: the relabel kernel searches them
-                vals.push_back( ids[ r ] );
-            }
-        }
-        if( !keys.empty() )
-            for( auto& s : g->strips )
-            {
-                cudaSetDevice( s.device );
-                if( keys.size() > s.map_cap )
-                {
-                    cudaFree( s.d_map_keys );
-                    cudaFree( s.d_map_vals );
-                    s.map_cap = keys.size() * 2;
-                    cudaMalloc( &s.d_map_keys, s.map_cap * 4 );
-                    cudaMalloc( &s.d_map_vals, s.map_cap * 4 );
-                }
-                cudaMemcpyAsync( s.d_map_keys, keys.data(), keys.size() * 4, cudaMemcpyHostToDevice, s.stream );
-                cudaMemcpyAsync( s.d_map_vals, vals.data(), vals.size() * 4, cudaMemcpyHostToDevice, s.stream );
-                const size_t n = ( size_t )W * ( s.own_e - s.own_b );
-                relabel_kernel<<< ( unsigned )( ( n + 255 ) / 256 ), 256, 0, s.stream >>>(
-                    s.d_labels + ( size_t )( s.own_b - s.load_b ) * W, n, s.d_map_keys, s.d_map_vals, ( int )keys.size() );
-            }
-    }
-    if( j->labels )
-        for( auto& s : g->strips )
-        {
-            cudaSetDevice( s.device );
-            const size_t own_px = ( size_t )W * ( s.own_e - s.own_b ), off_px = ( size_t )W * ( s.own_b - s.load_b );
-            e = cudaMemcpyAsync( j->labels + ( size_t )W * s.own_b, s.d_labels + off_px, own_px * 4, cudaMemcpyDeviceToHost, s.stream );
-            if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "D2H: %s", cudaGetErrorString( e ) );
-        }
     for( auto& s : g->strips )
     {
         cudaSetDevice( s.device );
         e = cudaStreamSynchronize( s.copy_stream );
         if( e == cudaSuccess ) e = cudaStreamSynchronize( s.stream );
-        if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "strip on device %d: %s", s.device, cudaGetErrorString( e ) );
-    }
-    for( auto& s : g->strips )
-    {
-        cudaSetDevice( s.device );
-        e = cudaStreamSynchronize( s.stream );
         if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "strip on device %d: %s", s.device, cudaGetErrorString( e ) );
     }
     return PAR_OK;

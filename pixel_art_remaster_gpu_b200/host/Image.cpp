@@ -39,6 +39,11 @@ uint32_t be32( const unsigned char* p ) { return ( uint32_t )p[ 0 ] << 24 | ( ui
 // decoded image as top-down rows of `ch` interleaved channels in R,G,B[,A] / grey order
 struct Decoded { int w = 0, h = 0, ch = 0; std::vector< unsigned char > px; };
 
+// Header fields come from untrusted files: sizes are bounded before anything is allocated or indexed.
+constexpr int kMaxSide = 1 << 15;               // 32768 pixels per side
+constexpr size_t kMaxPixels = ( size_t )1 << 28; // 268 M pixels
+bool sane_size( long long w, long long h ) { return w > 0 && h > 0 && w <= kMaxSide && h <= kMaxSide && ( size_t )w * ( size_t )h <= kMaxPixels; }
+
 bool decode_png( const std::vector< unsigned char >& file, Decoded& out, std::string& err )
 {
     static const unsigned char sig[ 8 ] = { 137, 80, 78, 71, 13, 10, 26, 10 };
@@ -54,6 +59,8 @@ bool decode_png( const std::vector< unsigned char >& file, Decoded& out, std::st
         if( pos + 12 + len > file.size() ) { err = "truncated PNG"; return false; }
         if( !memcmp( type, "IHDR", 4 ) )
         {
+            if( len != 13 ) { err = "bad PNG header"; return false; }
+            if( be32( data ) > ( uint32_t )kMaxSide || be32( data + 4 ) > ( uint32_t )kMaxSide ) { err = "PNG too large"; return false; }
             w = ( int )be32( data );
             h = ( int )be32( data + 4 );
             depth = data[ 8 ];
@@ -66,7 +73,7 @@ bool decode_png( const std::vector< unsigned char >& file, Decoded& out, std::st
         else if( !memcmp( type, "IEND", 4 ) ) break;
         pos += 12 + len;
     }
-    if( w <= 0 || h <= 0 || interlace != 0 ) { err = "unsupported PNG (interlaced or empty)"; return false; }
+    if( !sane_size( w, h ) || interlace != 0 ) { err = "unsupported PNG (interlaced, empty or too large)"; return false; }
     int samples = ctype == 0 ? 1 : ( ctype == 2 ? 3 : ( ctype == 3 ? 1 : ( ctype == 4 ? 2 : ( ctype == 6 ? 4 : 0 ) ) ) );
     if( !samples || ( depth != 8 && !( ctype == 3 && ( depth == 1 || depth == 2 || depth == 4 ) ) ) ) { err = "unsupported PNG bit depth / colour type"; return false; }
     const int bpp = std::max( 1, samples * depth / 8 );
@@ -161,20 +168,27 @@ bool decode_pnm( const std::vector< unsigned char >& file, Decoded& out, std::st
 {
     if( file.size() < 7 || file[ 0 ] != 'P' || ( file[ 1 ] != '6' && file[ 1 ] != '5' ) ) { err = "not a binary PPM/PGM"; return false; }
     size_t pos = 2;
-    int vals[ 3 ], got = 0;
+    long long vals[ 3 ] = { 0, 0, 0 };
+    int got = 0;
     while( got < 3 && pos < file.size() )
     {
         if( file[ pos ] == '#' ) { while( pos < file.size() && file[ pos ] != '\n' ) pos++; continue; }
         if( isspace( file[ pos ] ) ) { pos++; continue; }
-        int v = 0;
-        while( pos < file.size() && isdigit( file[ pos ] ) ) v = v * 10 + ( file[ pos++ ] - '0' );
+        if( !isdigit( file[ pos ] ) ) { err = "bad PNM header"; return false; }
+        long long v = 0;
+        while( pos < file.size() && isdigit( file[ pos ] ) )
+        {
+            v = v * 10 + ( file[ pos++ ] - '0' );
+            if( v > 1000000 ) { err = "bad PNM header"; return false; }
+        }
         vals[ got++ ] = v;
     }
+    if( got < 3 || vals[ 2 ] != 255 || !sane_size( vals[ 0 ], vals[ 1 ] ) ) { err = "unsupported or truncated PNM"; return false; }
     pos++; // single whitespace after maxval
-    out.w = vals[ 0 ];
-    out.h = vals[ 1 ];
+    out.w = ( int )vals[ 0 ];
+    out.h = ( int )vals[ 1 ];
     out.ch = file[ 1 ] == '6' ? 3 : 1;
-    if( got < 3 || vals[ 2 ] != 255 || pos + ( size_t )out.w * out.h * out.ch > file.size() ) { err = "unsupported or truncated PNM"; return false; }
+    if( pos > file.size() || ( size_t )out.w * out.h * out.ch > file.size() - pos ) { err = "unsupported or truncated PNM"; return false; }
     out.px.assign( file.begin() + pos, file.begin() + pos + ( size_t )out.w * out.h * out.ch );
     return true;
 }
@@ -183,17 +197,18 @@ bool decode_bmp( const std::vector< unsigned char >& f, Decoded& out, std::strin
 {
     if( f.size() < 54 || f[ 0 ] != 'B' || f[ 1 ] != 'M' ) { err = "not a BMP"; return false; }
     auto le32 = [ & ]( size_t o ) { return ( int32_t )( f[ o ] | f[ o + 1 ] << 8 | f[ o + 2 ] << 16 | ( uint32_t )f[ o + 3 ] << 24 ); };
-    int off = le32( 10 ), w = le32( 18 ), h = le32( 22 ), bits = f[ 28 ] | f[ 29 ] << 8, comp = le32( 30 );
-    bool top_down = h < 0;
-    h = std::abs( h );
-    if( ( bits != 24 && bits != 32 ) || comp != 0 || w <= 0 ) { err = "unsupported BMP (need uncompressed 24/32 bit)"; return false; }
-    size_t stride = ( ( size_t )w * bits / 8 + 3 ) & ~( size_t )3;
-    if( ( size_t )off + stride * h > f.size() ) { err = "truncated BMP"; return false; }
-    out.w = w; out.h = h; out.ch = 3;
+    const long long off = le32( 10 ), w = le32( 18 ), h_signed = le32( 22 );
+    const int bits = f[ 28 ] | f[ 29 ] << 8, comp = le32( 30 );
+    const bool top_down = h_signed < 0;
+    const long long h = top_down ? -h_signed : h_signed; // (64-bit: INT_MIN has no int negation)
+    if( ( bits != 24 && bits != 32 ) || comp != 0 || !sane_size( w, h ) ) { err = "unsupported BMP (need uncompressed 24/32 bit of a sane size)"; return false; }
+    const size_t stride = ( ( size_t )w * bits / 8 + 3 ) & ~( size_t )3;
+    if( off < 54 || ( size_t )off > f.size() || stride * ( size_t )h > f.size() - ( size_t )off ) { err = "truncated BMP"; return false; }
+    out.w = ( int )w; out.h = ( int )h; out.ch = 3;
     out.px.resize( ( size_t )w * h * 3 );
     for( int y = 0; y < h; y++ )
     {
-        const unsigned char* src = &f[ off + stride * ( top_down ? y : h - 1 - y ) ];
+        const unsigned char* src = &f[ ( size_t )off + stride * ( size_t )( top_down ? y : h - 1 - y ) ];
         for( int x = 0; x < w; x++ )
             for( int k = 0; k < 3; k++ ) out.px[ ( ( size_t )y * w + x ) * 3 + k ] = src[ x * ( bits / 8 ) + 2 - k ]; // BGR -> RGB
     }

@@ -113,11 +113,20 @@ static bool save_graph_image( const char* path )
 
 static bool save_plane( const char* path, const void* data, int w, int h, int bytes_per_px )
 {
-    // 1 byte/px -> PGM/PNG grey; 4 byte labels -> RGBA PNG of the raw int32 (lossless)
+    // 1 byte/px -> PGM/PNG grey; 4 byte labels -> RGBA PNG whose R,G,B,A bytes are the little-endian bytes of the int32
+    // (lossless).  A 4-channel Image holds B,G,R,A (saveImage swaps channels 0 and 2 on the way out), so the label bytes
+    // go in pre-swapped.
     Image out;
     out.createImage( w, h, IPL_DEPTH_8U, bytes_per_px == 1 ? 1 : 4 );
     for( int y = 0; y < h; y++ ) // stored top scanline first
-        memcpy( out.getImageData() + ( size_t )y * out.getWidthStep(), ( const char* )data + ( size_t )( h - 1 - y ) * w * bytes_per_px, ( size_t )w * bytes_per_px );
+    {
+        char* o = out.getImageData() + ( size_t )y * out.getWidthStep();
+        const char* s = ( const char* )data + ( size_t )( h - 1 - y ) * w * bytes_per_px;
+        if( bytes_per_px == 1 )
+            memcpy( o, s, ( size_t )w );
+        else
+            for( int x = 0; x < w; x++ ) { o[ 4 * x ] = s[ 4 * x + 2 ]; o[ 4 * x + 1 ] = s[ 4 * x + 1 ]; o[ 4 * x + 2 ] = s[ 4 * x ]; o[ 4 * x + 3 ] = s[ 4 * x + 3 ]; }
+    }
     out.saveImage( path );
     return out.error().empty();
 }
@@ -152,6 +161,11 @@ int main( int argc, char** argv )
         else if( a == "--device" && k + 1 < argc ) device = atoi( argv[ ++k ] );
         else if( a == "--convert-only" ) convert_only = true;
         else { fprintf( stderr, "remaster_cli: unknown option %s\n", a.c_str() ); return 2; }
+    }
+    if( ( aa != 1 && aa != 2 && aa != 4 ) || scale < 1 || scale * aa > 8 ) // (before anything is sized from the scale)
+    {
+        fprintf( stderr, "remaster_cli: unsupported scale %d with --aa %d (scale x aa must be an integer 1..8, aa 1, 2 or 4)\n", scale, aa );
+        return 2;
     }
     if( !load_image( argv[ 1 ] ) ) return 1;
     allocate_graph();
@@ -217,7 +231,8 @@ int main( int argc, char** argv )
         return 0;
     }
     const size_t N = ( size_t )img_width * img_height;
-    std::vector< uint8_t > rgba( N * scale * scale * 4 );
+    // the result arrives as the 3-channel B,G,R image Image::saveImage takes (Image.cpp:64-71): PAR_OUT_BGR8, dense rows
+    std::vector< uint8_t > bgr_out( N * scale * scale * 3 );
     std::vector< int32_t > labels( labels_path.empty() ? 0 : N );
     par_job job;
     memset( &job, 0, sizeof( job ) );
@@ -230,7 +245,8 @@ int main( int argc, char** argv )
     job.flags = ( subdivide ? PAR_FLAG_SUBDIVIDE : 0u ) | PAR_FLAG_FLIP_OUTPUT; // output rows top scanline first
     if( aa == 2 ) job.flags |= PAR_FLAG_AA2;
     if( aa == 4 ) job.flags |= PAR_FLAG_AA4;
-    job.rgba = rgba.data();
+    job.rgba = bgr_out.data();
+    job.out_format = PAR_OUT_BGR8;
     job.graph = reinterpret_cast< uint8_t* >( graph );
     job.labels = labels.empty() ? nullptr : labels.data();
     if( strips > 0 )
@@ -274,12 +290,8 @@ int main( int argc, char** argv )
     }
     Image out;
     out.createImage( img_width * scale, img_height * scale, IPL_DEPTH_8U, 3 );
-    for( int y = 0; y < img_height * scale; y++ )
-    {
-        const uint8_t* s = &rgba[ ( size_t )y * img_width * scale * 4 ];
-        char* o = out.getImageData() + ( size_t )y * out.getWidthStep();
-        for( int x = 0; x < img_width * scale; x++ ) { o[ 3 * x ] = ( char )s[ 4 * x + 2 ]; o[ 3 * x + 1 ] = ( char )s[ 4 * x + 1 ]; o[ 3 * x + 2 ] = ( char )s[ 4 * x ]; }
-    }
+    for( int y = 0; y < img_height * scale; y++ ) // (an Image's rows are padded to 4 bytes, IplImage style)
+        memcpy( out.getImageData() + ( size_t )y * out.getWidthStep(), &bgr_out[ ( size_t )y * img_width * scale * 3 ], ( size_t )img_width * scale * 3 );
     out.saveImage( out_path.c_str() );
     if( !out.error().empty() ) { fprintf( stderr, "remaster_cli: %s\n", out.error().c_str() ); return 1; }
     if( !graph_path.empty() && !save_plane( graph_path.c_str(), graph, img_width, img_height, 1 ) ) return 1;

@@ -155,7 +155,7 @@ def test_border_walks_equal_the_reference_walker(oracle):
 
 def test_product_yuv_word_on_the_host(oracle):
     """The product's packed-YUV conversion (csrc/common.cuh, the same function the kernels inline, here through the C ABI's
-    host entry par_yuv_word): every grey (the 256-bit rounding table), every colour whose 299 b0 + 587 b1 + 114 b2 is a
+    host entry par_yuv_word): every grey (the 256-bit rounding table), EVERY colour whose 299 b0 + 587 b1 + 114 b2 is a
     multiple of 1000 (the only ones the FMA chain decides), and a random sample, against the oracle's fused conversion."""
     import pixel_art_remaster_gpu_b200 as par
     for v in range(256):
@@ -164,9 +164,27 @@ def test_product_yuv_word_on_the_host(oracle):
     T = (299 * b[:, None, None] + 587 * b[None, :, None] + 114 * b[None, None, :])
     hits = np.argwhere(T % 1000 == 0)
     assert 15000 < len(hits) < 20000
-    for b0, b1, b2 in hits[::3]:
+    for b0, b1, b2 in hits:  # every one of them
         assert par.yuv_word(int(b0), int(b1), int(b2)) == oracle.yuv_word(int(b0), int(b1), int(b2), True), (b0, b1, b2)
     rng = np.random.default_rng(3)
     for col in rng.integers(0, 1 << 24, 20000):
         b0, b1, b2 = int(col) & 255, (int(col) >> 8) & 255, int(col) >> 16
         assert par.yuv_word(b0, b1, b2) == oracle.yuv_word(b0, b1, b2, True)
+
+
+def test_numpy_graph_builder_equals_the_oracle(oracle):
+    """tests/np_graph.py (used by the GPU suite to build the expected graph of the 4096 x 4096 all-colours frame) against the
+    oracle's stages A + B on small frames, on a slab of the all-colours frame and on degenerate shapes."""
+    from np_graph import all_colours_frame, graph_aux_from_yuv
+    from pixel_art_remaster_gpu_b200 import synth
+    table = oracle.yuv_all(True)
+
+    def words(img):
+        c = img.astype(np.uint32)
+        return table[c[..., 0] | c[..., 1] << 8 | c[..., 2] << 16]
+
+    cases = [synth.snes_frame(64, 48, 3), synth.adversarial_sprite(72, 60), synth.snes_frame(1, 1, 4), synth.snes_frame(40, 1, 5),
+             synth.snes_frame(1, 40, 6), np.ascontiguousarray(all_colours_frame()[2000:2040, 1000:1300])]
+    for img in cases:
+        want = oracle.trivial_crossings(oracle.similarity_graph(img))
+        assert np.array_equal(graph_aux_from_yuv(words(img)), want), img.shape

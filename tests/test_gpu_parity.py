@@ -93,7 +93,8 @@ def test_polygons_equal(ctx, oracle, name, img, subdivide):
 
 
 @pytest.mark.parametrize("name,img", _cases(), ids=[c[0] for c in _cases()])
-@pytest.mark.parametrize("scale,subdivide", [(4, True), (4, False), (8, True), (1, True), (2, True), (3, True), (6, False)])
+@pytest.mark.parametrize("scale,subdivide", [(4, True), (4, False), (8, True), (1, True), (2, True), (3, True), (6, False), (5, True), (7, True),
+                                             (5, False), (7, False), (6, True), (8, False)])
 def test_raster_within_one_lsb(ctx, oracle, name, img, scale, subdivide):
     want = oracle.pipeline(img, subdivide=subdivide, scale=scale, want=("graph", "raster"))
     import torch
@@ -106,7 +107,7 @@ def test_raster_within_one_lsb(ctx, oracle, name, img, scale, subdivide):
         assert diff.max() == 0
 
 
-@pytest.mark.parametrize("scale", [4, 8, 3])
+@pytest.mark.parametrize("scale", [4, 8, 3, 5, 7])
 def test_raster_exact_slow_path(ctx, oracle, scale):
     """Cells that reach beyond their sample mask are rasterized by an exact slow path; force every cell
     through it (PAR_FLAG_DEBUG_WIDE) and require the same image."""
@@ -177,25 +178,21 @@ def test_config5_adversarial_512x448(ctx, oracle):
 
 
 def test_exhaustive_yuv_words(ctx, oracle):
-    """All 2^24 colours through the graph kernel's conversion: a 4096x4096 frame holding every colour
-    once; neighbours differ by one step in byte 0 / byte 1 so the edges exercise the thresholds.
-    Checked against the oracle's graph for the same frame (bit-exact)."""
-    c = np.arange(1 << 24, dtype=np.uint32).reshape(4096, 4096)
-    img = np.stack([c & 255, (c >> 8) & 255, c >> 16], -1).astype(np.uint8)
-    small = np.ascontiguousarray(img[1024:1024 + 512])  # oracle on a slab (seconds), GPU on the whole frame
-    want = oracle.similarity_graph(small)
-    want = oracle.trivial_crossings(want)
-    import torch
+    """All 2^24 colours through the graph kernel's conversion: a 4096x4096 frame holding every colour once;
+    neighbours differ by one step in byte 0 / byte 1 so the edges exercise the thresholds.  The WHOLE device graph
+    (every pixel, so every colour's packed word takes part in up to eight comparisons) is compared with the graph
+    numpy builds from the oracle's conversion table for all 2^24 colours (tests/np_graph.py, itself pinned against the
+    oracle's stages A+B), and a slab of it with the oracle's own stages A+B."""
+    from np_graph import all_colours_frame, graph_aux_from_yuv
+    img = all_colours_frame()
+    want = graph_aux_from_yuv(oracle.yuv_all(True).reshape(4096, 4096))
+    slab = np.ascontiguousarray(img[1024:1024 + 256])
+    assert np.array_equal(oracle.trivial_crossings(oracle.similarity_graph(slab))[1:-1], want[1025:1024 + 255])
     big = ctx._torch.from_numpy(img[None]).to(ctx.device)
-    aux = ctx.similarity_graph(big)[0].cpu().numpy()
-    assert np.array_equal(aux[1025:1024 + 511], want[1:-1])
-    # and the host-side restatement of the device conversion against the oracle, all colours
-    import pixel_art_remaster_gpu_b200 as par
-    rng = np.random.default_rng(0)
-    for col in rng.integers(0, 1 << 24, 20000):
-        b0, b1, b2 = int(col) & 255, (int(col) >> 8) & 255, int(col) >> 16
-        assert par.yuv_word(b0, b1, b2) == oracle.yuv_word(b0, b1, b2, True)
-    del torch
+    for no_tma in (False, True):
+        aux = ctx.similarity_graph(big, no_tma=no_tma)[0].cpu().numpy()
+        bad = np.argwhere(aux != want)
+        assert len(bad) == 0, (no_tma, len(bad), bad[:5])
 
 
 def test_smoothing_tables_equal_the_geometric_path(lib, oracle):
@@ -214,7 +211,7 @@ def test_smoothing_tables_equal_the_geometric_path(lib, oracle):
             "noise": np.ascontiguousarray(noise)}
     for name, frames_np in sets.items():
         frames = torch.from_numpy(frames_np).cuda()
-        for scale in (1, 2, 3, 4, 6, 8):
+        for scale in (1, 2, 3, 4, 5, 6, 7, 8):
             with lib.Remaster(0, 128, 96, frames_np.shape[0]) as c:
                 tab = c.remaster(frames, scale=scale, subdivide=True)["rgba"].cpu().numpy()
                 st = c.smooth_stats()
@@ -226,7 +223,7 @@ def test_smoothing_tables_equal_the_geometric_path(lib, oracle):
                 st2 = c.smooth_stats()
                 assert st2["geometric"] - st["geometric"] == st2["smoothed"] - st["smoothed"]
             assert np.array_equal(tab, geo), (name, scale, int((tab != geo).any(-1).sum()))
-            if scale in (4, 8):
+            if scale in (4, 5, 7, 8):
                 assert np.array_equal(tab[0], oracle.pipeline(frames_np[0], scale=scale, want=("raster",))["raster"]), (name, scale)
 
 
@@ -367,7 +364,9 @@ def test_c_abi_error_behaviour(lib):
 
         INVALID, CAPACITY = 1, 4
         for bad, status in ((job(n_frames=0), INVALID), (job(width=0), INVALID), (job(height=-3), INVALID), (job(bgr=None), INVALID),
-                            (job(widthstep=100), INVALID), (job(frame_stride=100), INVALID), (job(scale=5), INVALID), (job(scale=7), INVALID),
+                            (job(widthstep=100), INVALID), (job(frame_stride=100), INVALID), (job(scale=0), INVALID), (job(scale=9), INVALID),
+                            (job(out_format=3), INVALID), (job(out_format=2, flags=1 | 32), INVALID),   # unknown format; indexed + anti-aliased
+                            (job(rgba=rgba.data_ptr() + 4), INVALID),                                  # the image must be 16-byte aligned
                             (job(scale=4, flags=1 | 64), INVALID),            # 4x4 samples at scale 4 would need a sampling scale of 16
                             (job(n_frames=3), CAPACITY)):                     # more frames than the context was created for (scratch graphs)
             assert L.par_remaster_device(c.handle, C.byref(bad)) == status
@@ -376,3 +375,150 @@ def test_c_abi_error_behaviour(lib):
         assert L.par_border_walks(c.handle, None, None, 40, 30, 2, None, None, None, 10, None) == INVALID
         assert c.launch_count == launches                                     # nothing ran
         assert torch.equal(c.remaster(frames, scale=2, subdivide=True)["rgba"], good)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_output_formats_hold_the_same_image(lib, oracle, scale):
+    """PAR_OUT_BGR8 (the 3-channel image Image::saveImage writes, Image.cpp:64-71) and PAR_OUT_INDEX8 (palette indices:
+    every output pixel is a source colour, kernel.cu:98-101, or the background, main.cpp:260) are the RGBA8 image in
+    another layout: byte for byte on the TMA and plain-load paths, on the exact path, flipped, with padded rows, through
+    the stage entry and the host entry; the palette is ascending, starts with black and counts the frame's colours."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    frames_np = np.concatenate([synth.snes_stream(2, 72, 40, first_seed=77), synth.adversarial_sprite(72, 40, 3)[None]])
+    F, H, W = frames_np.shape[:3]
+    padded = np.zeros((F, H, 3 * W + 8), np.uint8)
+    padded[:, :, :3 * W] = frames_np.reshape(F, H, 3 * W)
+    padded[:, :, 3 * W:] = 201  # row padding is never a pixel
+    with lib.Remaster(0, W, H, F) as c:
+        for src in ("dense", "padded"):
+            if src == "dense":
+                frames = torch.from_numpy(frames_np).cuda()
+            else:
+                frames = torch.from_numpy(padded).cuda().as_strided((F, H, W, 3), (H * (3 * W + 8), 3 * W + 8, 3, 1))
+            for flip in (False, True):
+                for no_tma in (False, True):
+                    ref = c.remaster(frames, scale=scale, subdivide=True, want=("rgba", "graph"), flip_output=flip, no_tma=no_tma)
+                    rgba = ref["rgba"].cpu().numpy()
+                    if scale in (4, 5) and not flip and not no_tma:
+                        assert np.array_equal(rgba[0], oracle.pipeline(frames_np[0], scale=scale, want=("raster",))["raster"])
+                    bgr = c.remaster(frames, scale=scale, subdivide=True, flip_output=flip, no_tma=no_tma, out_format=lib.OUT_BGR8)["rgba"]
+                    assert bgr.shape == (F, scale * H, scale * W, 3)
+                    assert np.array_equal(bgr.cpu().numpy(), rgba[..., [2, 1, 0]]), (src, flip, no_tma)
+                    idx = c.remaster(frames, scale=scale, subdivide=True, flip_output=flip, no_tma=no_tma, out_format=lib.OUT_INDEX8)
+                    assert idx["rgba"].shape == (F, scale * H, scale * W)
+                    assert np.array_equal(lib.Remaster.expand_indexed(idx["rgba"], idx["palette"]), rgba), (src, flip, no_tma)
+                    pal = idx["palette"].cpu().numpy().view(np.uint32)
+                    cnt = idx["palette_count"].cpu().numpy()
+                    for k in range(F):
+                        cols = frames_np[k].reshape(-1, 3).astype(np.uint32)
+                        words = np.unique(np.concatenate([[0], cols[:, 2] | cols[:, 1] << 8 | cols[:, 0] << 16]))
+                        assert cnt[k] == len(words)
+                        assert np.array_equal(pal[k, :cnt[k]] & 0xFFFFFF, words) and np.all(pal[k] >> 24 == 255)
+                    # the stage entry and the exact slow path
+                    st = c.raster(frames, ref["graph"], scale, True, flip_output=flip, no_tma=no_tma, out_format=lib.OUT_INDEX8)
+                    assert torch.equal(st["rgba"], idx["rgba"]) and torch.equal(st["palette"], idx["palette"])
+                    if not no_tma:
+                        wide = c.raster(frames, ref["graph"], scale, True, flip_output=flip, debug_wide=True, out_format=lib.OUT_BGR8)
+                        assert torch.equal(wide, bgr)
+                        widx = c.raster(frames, ref["graph"], scale, True, flip_output=flip, debug_wide=True, out_format=lib.OUT_INDEX8)
+                        assert torch.equal(widx["rgba"], idx["rgba"])
+        host_in = torch.from_numpy(frames_np).pin_memory()
+        rgba = c.remaster_host(host_in, scale=scale, subdivide=True)["rgba"].numpy()
+        hb = c.remaster_host(host_in, scale=scale, subdivide=True, out_format=lib.OUT_BGR8)["rgba"].numpy()
+        hi = c.remaster_host(host_in, scale=scale, subdivide=True, out_format=lib.OUT_INDEX8)
+        assert np.array_equal(hb, rgba[..., [2, 1, 0]])
+        assert np.array_equal(lib.Remaster.expand_indexed(hi["rgba"], hi["palette"]), rgba)
+        # anti-aliased output in BGR8
+        if scale <= 4:
+            c.aa = 2
+            a = c.remaster(torch.from_numpy(frames_np).cuda(), scale=scale, subdivide=True)["rgba"].cpu().numpy()
+            b = c.remaster(torch.from_numpy(frames_np).cuda(), scale=scale, subdivide=True, out_format=lib.OUT_BGR8)["rgba"].cpu().numpy()
+            assert np.array_equal(b, a[..., [2, 1, 0]])
+            c.aa = 1
+
+
+@pytest.mark.gpu
+def test_indexed_output_of_frames_with_many_colours(lib):
+    """A frame with exactly 256 colours (incl. black) is representable, one with more reports its count (> 256) and
+    leaves the other frames of the batch intact; a frame larger than one palette chunk (64 K pixels) merges its chunks."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    rng = np.random.default_rng(5)
+    H, W = 48, 64
+    pal255 = np.unique(rng.integers(1, 1 << 24, 400, dtype=np.uint32))[:255]          # 255 colours + black = 256
+    pal300 = np.unique(rng.integers(1, 1 << 24, 500, dtype=np.uint32))[:300]
+
+    def frame(pal, h=H, w=W):
+        idx = rng.integers(0, len(pal), (h, w))
+        idx.reshape(-1)[:len(pal)] = np.arange(len(pal))   # every colour occurs
+        c = pal[idx]
+        return np.stack([(c >> 16) & 255, (c >> 8) & 255, c & 255], -1).astype(np.uint8)
+
+    frames_np = np.stack([frame(pal255), frame(pal300), frame(pal255[:17])])
+    with lib.Remaster(0, W, H, 3) as c:
+        frames = torch.from_numpy(frames_np).cuda()
+        rgba = c.remaster(frames, scale=4, subdivide=True)["rgba"].cpu().numpy()
+        idx = c.remaster(frames, scale=4, subdivide=True, out_format=lib.OUT_INDEX8)
+        cnt = idx["palette_count"].cpu().numpy()
+        assert cnt[0] == 256 and cnt[1] > 256 and cnt[2] == 18, cnt
+        full = lib.Remaster.expand_indexed(idx["rgba"], idx["palette"])
+        assert np.array_equal(full[0], rgba[0]) and np.array_equal(full[2], rgba[2])
+    big = frame(pal255[:40], 300, 400)                      # 120 000 pixels: two chunks
+    with lib.Remaster(0, 400, 300, 1) as c:
+        frames = torch.from_numpy(big[None]).cuda()
+        rgba = c.remaster(frames, scale=2, subdivide=True)["rgba"].cpu().numpy()
+        idx = c.remaster(frames, scale=2, subdivide=True, out_format=lib.OUT_INDEX8)
+        assert int(idx["palette_count"][0]) == 41
+        assert np.array_equal(lib.Remaster.expand_indexed(idx["rgba"], idx["palette"]), rgba)
+
+
+@pytest.mark.gpu
+def test_streams_devices_and_sub_batches(lib):
+    """A context follows torch's current stream call by call (outputs allocated under `with torch.cuda.stream(s)` are
+    produced on s), leaves the caller's current device alone, refuses tensors of another device, and gives the same
+    result whether a batch runs as one launch per stage or in rounds of a few frames."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    frames_np = synth.snes_stream(7, 64, 48, first_seed=900)
+    frames = torch.from_numpy(frames_np).cuda()
+    with lib.Remaster(0, 64, 48, 7) as c:
+        want = c.remaster(frames, scale=3, subdivide=True, want=("rgba", "graph", "labels"))
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        for _ in range(3):
+            with torch.cuda.stream(s):
+                # a long-running producer on s, then the remaster of ITS output on s: a context still bound to the
+                # default stream would read the frames before the copy has happened
+                staged = torch.zeros_like(frames)
+                big = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+                for _k in range(4):
+                    big.fill_(1)
+                staged.copy_(frames)
+                got = c.remaster(staged, scale=3, subdivide=True, want=("rgba", "graph", "labels"))
+            s.synchronize()
+            for k in want:
+                assert torch.equal(got[k], want[k]), k
+        for sub in (1, 2, 3, 7, 100):
+            c.set_sub_batch(sub)
+            got = c.remaster(frames, scale=3, subdivide=True, want=("rgba", "graph", "labels"))
+            idx = c.remaster(frames, scale=3, subdivide=True, out_format=lib.OUT_INDEX8)
+            for k in want:
+                assert torch.equal(got[k], want[k]), (sub, k)
+            assert np.array_equal(lib.Remaster.expand_indexed(idx["rgba"], idx["palette"]), want["rgba"].cpu().numpy())
+        c.set_sub_batch(0)
+        assert torch.cuda.current_device() == 0
+        with pytest.raises(ValueError):
+            c._job(_other_device(), 3, 0)
+
+
+def _other_device():
+    """A stand-in tensor that claims to live on another CUDA device (a one-GPU box cannot make a real one)."""
+    class Fake:
+        is_cuda = True
+        device = __import__("torch").device("cuda", 1)
+    return Fake()

@@ -47,6 +47,42 @@ def test_strips_on_two_gpus(lib, oracle):
     assert np.array_equal(got["rgba"], want["raster"])
 
 
+@pytest.mark.parametrize("n_strips", [1, 2, 4])
+def test_device_resident_strips(lib, oracle, n_strips):
+    """par_group_remaster_device: the strips' own rows are written into their device buffers, halo exchange, kernels and
+    the on-device label stitch run without the host, and the own rows of every output equal the single-image result
+    (RGBA8 and BGR8).  Strips are spread over the GPUs that exist (all on one device on a 1-GPU box)."""
+    import torch
+    if _n_gpus() < 1:
+        pytest.skip("no GPU")
+    W, H, S = 128, 40 * n_strips + 23, 3
+    img = synth.adversarial_sprite(W, H, 31) if n_strips != 2 else synth.snes_frame(W, H, 32)
+    want = oracle.pipeline(img, scale=S, want=("graph", "labels", "raster"))
+    devices = [k % _n_gpus() for k in range(n_strips)]
+    with lib.RemasterGroup(devices, W, H, S) as grp:
+        strips = grp.strips()
+        assert len(strips) == n_strips and strips[0]["own"][0] == 0 and strips[-1]["own"][1] == H
+        for st in strips:
+            b, e = st["own"]
+            lb = st["load"][0]
+            st["bgr"].zero_()
+            st["bgr"][b - lb:e - lb].copy_(torch.from_numpy(img[b:e]))
+        torch.cuda.synchronize()
+        for fmt in (lib.OUT_RGBA8, lib.OUT_BGR8):
+            wall, dev_ms = grp.remaster_device(subdivide=True, out_format=fmt, want_labels=True)
+            assert wall > 0 and dev_ms > 0
+            for st in strips:
+                b, e = st["own"]
+                lb = st["load"][0]
+                assert np.array_equal(st["graph"][b - lb:e - lb].cpu().numpy(), want["graph"][b:e])
+                assert np.array_equal(st["labels"][b - lb:e - lb].cpu().numpy(), want["labels"][b:e])
+                image = st["image"](fmt)[(b - lb) * S:(e - lb) * S].cpu().numpy()
+                ref = want["raster"][b * S:e * S]
+                assert np.array_equal(image, ref if fmt == lib.OUT_RGBA8 else ref[..., [2, 1, 0]])
+        with pytest.raises(lib.RemasterError):
+            grp.remaster_device(out_format=lib.OUT_INDEX8)
+
+
 def test_long_component_across_all_seams(lib, oracle):
     """A one-pixel-wide snake that crosses every seam several times: the stitched labels must still be
     the global minimum index."""
