@@ -13,9 +13,13 @@ max-over-ranks reduction of the device time.
 
 Prints ONE JSON line.  `value` is whole-job frames/s with inputs resident in HBM; `e2e` is the same
 metric through the host-buffer entry point of the C ABI (pinned host memory, H2D + D2H inside the
-timed region); `roofline` is for the dominant kernel (the rasterizer), timed with CUDA events on the
-launching stream inside the same timed region; `cpu_baseline` is the reference's own routines
-(oracle/_ref, host build) on this box's cores over a bounded sample.
+timed region, the same 4096-frame step, output as palette indices + palette; RGBA8 beside it);
+`roofline` is for the dominant kernel (the rasterizer), timed with CUDA events on the launching
+stream inside the same timed region; `cpu_baseline` is the reference's own routines (oracle/_ref,
+host build) on this box's cores over a bounded sample.  Also in the line: `sustained` (the same step
+back to back for >= 2 s with its clock samples), `strong_scaling` (the one 4096-frame stream split
+over the ranks), `tiled` (config C4: one 4096 x 4096 map over all GPUs of the job, device-resident,
+checked against one context), `parity` (what each result is pinned by).
 
 --impl reference: the reference's CPU implementation of the path (oracle/_ref/libref_host_fma.so,
 the reference's own .cu files compiled as host C++; falls back to the oracle port when that build is
@@ -48,14 +52,16 @@ def workload(n_frames=FRAMES_PER_GPU):
 
 
 def profiled_traffic_per_frame():
-    """DRAM bytes (read + write) per frame of the raster kernel from the committed `ncu --set full` capture
-    (profiles/r1_raster_traffic.json, written by tools/ncu_traffic.py); None when the capture is absent."""
-    p = os.path.join(ROOT, "profiles", "r1_raster_traffic.json")
-    try:
-        t = json.load(open(p))
-        return float(t["dram_bytes_per_frame"]), t.get("source", "profiles/r1_raster_traffic.json")
-    except Exception:
-        return None, None
+    """DRAM bytes (read + write) per frame of the raster kernel from the committed ncu capture of a launch over the bench's own
+    4096-frame batch (profiles/r2_raster_traffic.json, written by tools/ncu_traffic.py; round 1's 256-frame capture as a
+    fallback); None when neither is there."""
+    for name in ("r2_raster_traffic.json", "r1_raster_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))
+            return float(t["dram_bytes_per_frame"]), t.get("source", "profiles/" + name)
+        except Exception:
+            continue
+    return None, None
 
 
 def measured_peak_gbs():
@@ -201,6 +207,26 @@ def time_drop_in(par, img, n_calls):
                     "cells + subdivision + ear clipping into the 45-slot VBO arrays, D2H of the triangle list, graph and counts"}
 
 
+def bench_config(n_frames=FRAMES_PER_GPU):
+    """The `config` object of the JSON line — the same in both arms (ours and --impl reference)."""
+    return {"workload": workload(n_frames), "width": W, "height": H, "scale": SCALE, "subdivide": True, "labels": False,
+            "frames_per_gpu": n_frames, "algorithmic_bytes_per_frame": ALGO_BYTES_PER_PX * W * H,
+            "l2": "inputs (%.0f MB) and outputs (%.1f GB) per step exceed the 126 MB L2; no flush needed"
+                  % (n_frames * W * H * 3 / 1e6, n_frames * W * H * SCALE * SCALE * 4 / 1e9)}
+
+
+PARITY_NOTES = {
+    "graph": "similarity graph and crossing decisions bit-exact vs the oracle, which equals the reference's own .cu files compiled here "
+             "(host build) and its kernel.cu built for sm_100a on the GPU (tests/test_oracle_vs_reference.py, test_gpu_reference_cuda.py)",
+    "polygons": "cell and subdivision vertices equal (exact dyadic arithmetic) vs the same",
+    "cc_labels": "reference implementation is dead code (cc_functions.cu is not in its build): parity vs the canonical definition "
+                 "(minimum row-major index per component of the final graph) + 1 reference fixture (alex_png.txt, 19 components)",
+    "raster": "the reference rasterizes inside the OpenGL driver, so the sampling rule is unpinned by it: parity vs the oracle's restated "
+              "GL point-sampling rule painting the REFERENCE'S OWN triangle list (bit-exact, scales 1..8); BGR8 / INDEX8 are the RGBA8 image "
+              "in another layout (byte-exact)",
+}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -228,7 +254,7 @@ def run_reference(args):
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "impl": "reference",
-            "config": {"workload": workload(), "width": W, "height": H, "scale": SCALE, "subdivide": True},
+            "config": bench_config(args.frames),
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -236,11 +262,83 @@ def run_reference(args):
     return 0
 
 
+def bind_to_gpu_numa_node(local):
+    """Run this rank (and first-touch its pinned buffers) on the cores next to its GPU: /sys/bus/pci/devices/<bus id>/local_cpulist.
+    Returns what was done, for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/" % (dom, bus, dev)
+        cpus = open(path + "local_cpulist").read().strip()
+        node = open(path + "numa_node").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        allowed = ids & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": cpus, "bound": bool(allowed)}
+    except Exception as exc:
+        return {"bound": False, "why": str(exc)[:120]}
+
+
+def tiled_map_check(par, synth, torch, n_devices, side):
+    """Config C4 under the driver's eyes: one side x side map cut into strips over `n_devices` GPUs (two strips on one GPU at
+    N = 1), device-resident (par_group_remaster_device: halo rows by peer copies, kernels, on-device label stitch), compared
+    with the same map through ONE context on GPU 0, and timed."""
+    S = SCALE
+    img = synth.pixel_art_map(side, side, synth.BASE_SEED + 4)
+    devices = list(range(n_devices)) if n_devices > 1 else [0, 0]
+    res = {"map": "%dx%d synthetic pixel-art map -> %dx RGBA8 + CC labels" % (side, side, S), "n_devices": n_devices, "strips": len(devices)}
+    with par.Remaster(0, side, side, 1) as one:
+        dev0 = torch.device("cuda", 0)
+        whole_in = torch.from_numpy(img[None]).to(dev0)
+        want = one.remaster(whole_in, S, True, want=("rgba", "graph", "labels"))
+        torch.cuda.synchronize(dev0)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            one.remaster(whole_in, S, True, out=want)
+        b.record()
+        torch.cuda.synchronize(dev0)
+        res["one_gpu_ms"] = a.elapsed_time(b) / 3
+        with par.RemasterGroup(devices, side, side, S) as grp:
+            strips = grp.strips()
+            for st in strips:
+                lo, hi = st["own"]
+                lb = st["load"][0]
+                st["bgr"].zero_()
+                st["bgr"][lo - lb:hi - lb].copy_(torch.from_numpy(img[lo:hi]))
+            for d in set(devices):
+                torch.cuda.synchronize(d)
+            grp.remaster_device(True)  # warm-up (tables, peer mappings)
+            walls, devs = [], []
+            for _ in range(5):
+                w, d = grp.remaster_device(True)
+                walls.append(w)
+                devs.append(d)
+            ok = True
+            for st in strips:
+                lo, hi = st["own"]
+                lb = st["load"][0]
+                ok = ok and bool(torch.equal(st["graph"][lo - lb:hi - lb].to(dev0), want["graph"][0, lo:hi]))
+                ok = ok and bool(torch.equal(st["labels"][lo - lb:hi - lb].to(dev0), want["labels"][0, lo:hi]))
+                ok = ok and bool(torch.equal(st["image"](par.OUT_RGBA8)[(lo - lb) * S:(hi - lb) * S].to(dev0), want["rgba"][0, lo * S:hi * S]))
+            res.update({"ok": ok, "ms": min(walls), "strip_device_ms": min(devs),
+                        "what": "ms = host wall clock of par_group_remaster_device (enqueue on all devices .. last synchronize), best of 5; "
+                                "strip_device_ms = the slowest strip's own stream time (CUDA events); one_gpu_ms = the whole map through one "
+                                "context on GPU 0; ok = own rows of every strip (graph, labels, RGBA) equal the one-context result"})
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import pixel_art_remaster_gpu_b200 as par
-    from pixel_art_remaster_gpu_b200 import synth
+    from pixel_art_remaster_gpu_b200 import sharding, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -249,6 +347,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -257,9 +356,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     n_frames = args.frames
     # this rank's shard of the stream: its own consecutive seeds (no frame is shared between ranks)
-    host_frames = torch.from_numpy(synth.snes_stream(n_frames, W, H, first_seed=synth.BASE_SEED + rank * n_frames))
+    host_frames = torch.from_numpy(synth.snes_stream(n_frames, W, H, first_seed=sharding.stream_seed(rank, n_frames, synth.BASE_SEED)))
     frames = host_frames.to(dev)
     ctx = par.Remaster(local, W, H, n_frames)
     out = {"rgba": torch.empty((n_frames, SCALE * H, SCALE * W, 4), dtype=torch.uint8, device=dev),
@@ -293,34 +398,101 @@ def run_ours(args):
     ctx.profile(False)
     smooth1 = ctx.smooth_stats()
     launches = ctx.launch_count - launches0
-
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = max_over_ranks(ms)
     value = world * n_frames * args.steps / (ms_max * 1e-3)
 
-    # ---- end to end through the host-buffer entry point (pinned memory, H2D + D2H in the timed region)
-    e2e_n = min(E2E_FRAMES, n_frames)
-    pin_in = host_frames[:e2e_n].clone().pin_memory()
-    pin_out = {"rgba": torch.empty((e2e_n, SCALE * H, SCALE * W, 4), dtype=torch.uint8).pin_memory(),
-               "graph": torch.empty((e2e_n, H, W), dtype=torch.uint8).pin_memory()}
-    e2e_steps = max(1, min(args.steps, 5))
-    ctx.remaster_host(pin_in, SCALE, True, out=pin_out)
+    # ---- sustained: the same step back to back for >= 2 s, with its own clock samples (the headline's timed region is ~0.1 s)
+    sus_clocks = ClockSampler(local)
+    if rank == 0:
+        sus_clocks.start()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    sus_steps = max(args.steps, int(2200.0 / max(ms_max / args.steps, 1e-3)) + 1)
+    sus_clocks.mark_begin()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(sus_steps):
+        step()
+    s1.record()
+    barrier()
+    sus_clocks.mark_end()
+    sus_info = sus_clocks.stop() if rank == 0 else None
+    sus_ms = max_over_ranks(s0.elapsed_time(s1))
+    sustained = {"value": world * n_frames * sus_steps / (sus_ms * 1e-3), "unit": "frames/s", "seconds": sus_ms * 1e-3, "steps": sus_steps,
+                 "ms_per_step": sus_ms / sus_steps, "clocks": sus_info}
+
+    # ---- strong scaling: the SAME 4096-frame stream cut into contiguous shards (sharding.frame_shard), one per rank
+    lo, hi = sharding.frame_shard(n_frames, rank, world)
+    shard_out = {"rgba": out["rgba"][:hi - lo], "graph": out["graph"][:hi - lo]}
+    shard_in = frames[:hi - lo]  # (synthetic frames of the same generator: which ones a rank holds does not change the work)
+
+    def strong_step():
+        ctx.remaster(shard_in, SCALE, True, out=shard_out)
+
+    for _ in range(3):
+        strong_step()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        strong_step()
+    g1.record()
+    barrier()
+    strong_ms = max_over_ranks(g0.elapsed_time(g1))
+    strong = {"value": n_frames * args.steps / (strong_ms * 1e-3), "unit": "frames/s", "frames_total": n_frames, "frames_per_gpu": hi - lo,
+              "ms_per_step": strong_ms / args.steps, "scaling": "strong",
+              "what": "the 4096-frame stream of config C3 split into contiguous per-GPU shards (sharding.frame_shard), no collective"}
+    step()  # (restore the full batch in `out` for the checks below)
+
+    # ---- end to end through the host-buffer entry point of the C ABI (pinned memory, H2D + D2H in the timed region), at the
+    # same 4096-frame step.  Headline format: INDEX8 (palette indices + per-frame palette: the same image, losslessly, in a
+    # quarter of the bytes — every output pixel is a source colour or black); RGBA8 beside it on a 512-frame step.
+    e2e_steps = max(1, min(args.steps, 3))
+    pin_in = host_frames.clone().pin_memory()
+    pin_idx = ctx._alloc(n_frames, H, W, SCALE, ("rgba", "graph"), par.OUT_INDEX8, host=True)
+    ctx.remaster_host(pin_in, SCALE, True, out=pin_idx, out_format=par.OUT_INDEX8)
+    barrier()
+    t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.remaster_host(pin_in, SCALE, True, out=pin_out)  # H2D, kernels, D2H on the same stream; synchronizes
-    e1.record()
+        ctx.remaster_host(pin_in, SCALE, True, out=pin_idx, out_format=par.OUT_INDEX8)  # H2D, kernels, D2H; synchronizes
     barrier()
-    e2e_s = e0.elapsed_time(e1) * 1e-3
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_n * e2e_steps / float(te.item())
-    # spot-check that the end-to-end output is the device-resident output
-    same = bool(torch.equal(pin_out["rgba"][:2], out["rgba"][:2].cpu()))
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * n_frames * e2e_steps / e2e_s
+    d2h_idx = sum(v.numel() * v.element_size() for v in pin_idx.values())
+    # every frame of the end-to-end result against the device-resident RGBA8 result
+    same = bool((pin_idx["palette_count"] <= 256).all()) and bool(torch.equal(pin_idx["graph"], out["graph"].cpu()))
+    for c0 in range(0, n_frames, 128):
+        c1 = min(c0 + 128, n_frames)
+        idx = pin_idx["rgba"][c0:c1].to(dev).view(c1 - c0, -1).long()
+        pal = pin_idx["palette"][c0:c1].to(dev)
+        same = same and bool(torch.equal(torch.gather(pal, 1, idx), out["rgba"][c0:c1].view(torch.int32).view(c1 - c0, -1)))
+        del idx, pal
+    # pinned-copy ceiling of this rank with every rank copying at once (the host side is shared)
+    peak_buf_d = out["rgba"].view(-1)[: 1 << 30]
+    peak_buf_h = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+    peak_buf_h.copy_(peak_buf_d, non_blocking=True)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(3):
+        peak_buf_h.copy_(peak_buf_d, non_blocking=True)
+    p1.record()
+    barrier()
+    d2h_peak = 3 * (1 << 30) / (max_over_ranks(p0.elapsed_time(p1)) * 1e-3) / 1e9  # GB/s per rank, all ranks busy
+    del peak_buf_h
+    # RGBA8 beside it (512 frames: 1.9 GB of pinned memory per rank instead of 15 GB)
+    n_small = min(E2E_FRAMES, n_frames)
+    pin_rgba = ctx._alloc(n_small, H, W, SCALE, ("rgba", "graph"), par.OUT_RGBA8, host=True)
+    ctx.remaster_host(pin_in[:n_small], SCALE, True, out=pin_rgba)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.remaster_host(pin_in[:n_small], SCALE, True, out=pin_rgba)
+    barrier()
+    rgba_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_rgba = {"value": world * n_small * e2e_steps / rgba_s, "unit": "frames/s", "frames_per_step": n_small,
+                "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in pin_rgba.values())),
+                "matches_device_path": bool(torch.equal(pin_rgba["rgba"], out["rgba"][:n_small].cpu()))}
+    del pin_rgba
 
     def timed(fn, reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -332,7 +504,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
-    # side measurements on rank 0 (not the headline): other frames, smoothing tables off, subdivision off
+    # side measurements on rank 0 (not the headline): other frames, smoothing tables off, subdivision off, labels on, other formats
     extras = {}
     if rank == 0:
         n_new = min(512, n_frames)
@@ -349,33 +521,68 @@ def run_ours(args):
         ctx.no_tables = False
         extras["subdivide_off"] = {"value": n_new / (timed(lambda: ctx.remaster(sub, SCALE, False, out=o_new), 3) * 1e-3), "unit": "frames/s",
                                    "what": "the reference's default (simpleVBO.cpp:43 subdivide = false): hull cells only"}
+        lab = torch.empty((n_new, H, W), dtype=torch.int32, device=dev)
+        o_lab = dict(o_new, labels=lab)
+        extras["labels_on"] = {"value": n_new / (timed(lambda: ctx.remaster(sub, SCALE, True, out=o_lab), 3) * 1e-3), "unit": "frames/s",
+                               "what": "the same path + CC labels (union-find: tile, seam and flatten kernels)"}
+        del lab, o_lab
+        for fmt, name in ((par.OUT_BGR8, "bgr8"), (par.OUT_INDEX8, "index8")):
+            o_fmt = ctx._alloc(n_new, H, W, SCALE, ("rgba", "graph"), fmt)
+            extras["device_resident_" + name] = {"value": n_new / (timed(lambda: ctx.remaster(sub, SCALE, True, out=o_fmt, out_format=fmt), 3) * 1e-3),
+                                                 "unit": "frames/s", "what": "output left in HBM as " + name.upper()}
+            del o_fmt
+    # ---- config C4 (one large map over the GPUs of the job), rank 0 drives all devices while the others wait
+    tiled = None
+    barrier()
+    if rank == 0 and not args.no_tiled:
+        try:
+            del novel
+        except NameError:
+            pass
+        torch.cuda.empty_cache()
+        try:
+            tiled = tiled_map_check(par, synth, torch, world, args.tiled_side)
+        except Exception as exc:  # a side check must never break the bench line
+            tiled = {"ok": False, "error": str(exc)[:300]}
+        torch.cuda.set_device(local)
+    barrier()
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         traffic_pf, traffic_src = profiled_traffic_per_frame()
-        r_ms, r_n = prof["raster"]
         px = n_frames * W * H
-        raster_gbs = (RASTER_BYTES_PER_PX * px) / ((r_ms / max(r_n, 1)) * 1e-3) / 1e9
-        stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in prof.items() if v[1]}
+        stage_ms = {k: v[0] / args.steps for k, v in prof.items() if v[1]}  # per step (a stage may take several launches)
+        r_ms = stage_ms["raster"]
+        raster_gbs = (RASTER_BYTES_PER_PX * px) / (r_ms * 1e-3) / 1e9
+        frame_bytes_idx = d2h_idx / n_frames
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload(n_frames), "width": W, "height": H, "scale": SCALE, "subdivide": True, "labels": False,
-                       "frames_per_gpu": n_frames, "l2": "inputs (%.0f MB) and outputs (%.1f GB) per step exceed the 126 MB L2; no flush needed"
-                       % (frames.numel() / 1e6, out["rgba"].numel() / 1e9),
-                       "algorithmic_bytes_per_frame": ALGO_BYTES_PER_PX * W * H},
+            "config": bench_config(n_frames),
             "hbm_gbs_algorithmic": value / world * ALGO_BYTES_PER_PX * W * H / 1e9,
             "roofline": {"kernel": "raster_kernel<4> (cells + subdivision + direct raster)", "bound": "hbm",
                          "achieved": raster_gbs, "peak": peak, "unit": "GB/s", "frac": raster_gbs / peak,
                          "traffic": (traffic_pf * n_frames) if traffic_pf else None, "traffic_source": traffic_src,
-                         "peak_source": peak_src, "launch_ms": r_ms / max(r_n, 1), "bytes_per_launch": RASTER_BYTES_PER_PX * px,
+                         "peak_source": peak_src, "launch_ms": r_ms, "bytes_per_launch": RASTER_BYTES_PER_PX * px,
                          "other_kernels": {k: {"launch_ms": stage_ms[k], "achieved": b * px / (stage_ms[k] * 1e-3) / 1e9,
                                                "frac": b * px / (stage_ms[k] * 1e-3) / 1e9 / peak, "bytes_per_px": b}
                                            for k, b in (("similarity_graph", 4), ("resolve_crossings", 2)) if k in stage_ms}},
             "stage_ms_per_step": stage_ms,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(pin_in.numel()),
-                    "d2h_bytes_per_step": int(pin_out["rgba"].numel() + pin_out["graph"].numel()),
-                    "frames_per_step": e2e_n, "steps": e2e_steps, "matches_device_path": same},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(pin_in.numel()), "d2h_bytes_per_step": int(d2h_idx),
+                    "frames_per_step": n_frames, "steps": e2e_steps, "matches_device_path": same, "frames_compared": n_frames,
+                    "output_format": "INDEX8: one palette index per output pixel + the frame's palette (<= 256 RGBA8 entries) + final graph; "
+                                     "lossless (every output pixel is a source colour or the black background)",
+                    "d2h_gbs": world * d2h_idx * e2e_steps / e2e_s / 1e9,
+                    "pinned_d2h_peak_gbs_per_rank": d2h_peak,
+                    "frac_of_pinned_copy_peak": (d2h_idx * e2e_steps / e2e_s / 1e9) / d2h_peak,
+                    "host_ceiling_fps": world * d2h_peak * 1e9 / frame_bytes_idx,
+                    "numa": numa,
+                    "rgba8": e2e_rgba},
+            "sustained": sustained,
+            "strong_scaling": strong,
+            "tiled": tiled,
+            "parity": PARITY_NOTES,
             "gpu_launches": int(launches), "clocks": clock_info,
             "smoothing": {"cells": smooth1["smoothed"] - smooth0["smoothed"], "geometric_path": smooth1["geometric"] - smooth0["geometric"],
                           "what": "cells stage E ran on in the timed region, and how many of them the precomputed smoothing "
@@ -426,6 +633,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help="frames per GPU per step (default: the C3 stream)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tiled", action="store_true", help="skip the config-C4 tiled-map check")
+    ap.add_argument("--tiled-side", type=int, default=4096, help="side of the square map of the tiled check")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -7,6 +7,10 @@
 // canonical minimum-index label produced here, so any correct labeller is bit-exact.
 //
 // Design: lock-free union-find with link-by-minimum-index over the label array itself.
+// (Tried and dropped in round 2: one CTA per frame of <= 65536 pixels with the whole forest as 16-bit labels in 168 KB of
+// shared memory — no seams, no global atomics, no flatten kernel, but one CTA per SM, two CTA-wide barriers per 1024 pixels
+// and CAS loops for the 16-bit minimum: 2.08 ms per 1024 frames against 0.91 ms for the three kernels below,
+// profiles/r2e_stage_times_*.)
 //   (1) tile pass: one CTA per 64x16 tile builds the tile's forest in SHARED memory (horizontal runs by
 //       warp ballot, the few unions that can still connect two runs queued and executed one per lane,
 //       flatten) and writes tile-local roots as global indices;

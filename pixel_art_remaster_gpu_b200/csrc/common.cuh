@@ -63,18 +63,25 @@ __host__ __device__ __forceinline__ int luma_chain( int y, int b0, int b1, int b
     return ( int )__builtin_fma( 0.114, ( double )b2, __builtin_fma( 0.299, ( double )b0, 0.587 * ( double )b1 ) );
 #endif
 }
-// U and V from y, the packed word (graph_functions.cu:93-97)
-__host__ __device__ __forceinline__ uint32_t yuv_pack( int y, int b0, int b2 )
+// U and V from y, the packed word (graph_functions.cu:93-97): float products truncated toward zero, added into the word as
+// signed terms (a negative U or V borrows from the field above it, as in the reference).  d = b2 - y resp. b0 - y.
+__host__ __device__ __forceinline__ uint32_t yuv_u_term( int d )
 {
 #ifdef __CUDA_ARCH__
-    int u = __float2int_rz( __fmul_rn( ( float )( b2 - y ), 0.492f ) );
-    int v = __float2int_rz( __fmul_rn( ( float )( b0 - y ), 0.877f ) );
+    return ( uint32_t )( __float2int_rz( __fmul_rn( ( float )d, 0.492f ) ) * 256 );
 #else
-    int u = ( int )( ( float )( b2 - y ) * 0.492f );
-    int v = ( int )( ( float )( b0 - y ) * 0.877f );
+    return ( uint32_t )( ( int )( ( float )d * 0.492f ) * 256 );
 #endif
-    return ( uint32_t )( y << 16 ) + ( uint32_t )( u * 256 ) + ( uint32_t )v;
 }
+__host__ __device__ __forceinline__ uint32_t yuv_v_term( int d )
+{
+#ifdef __CUDA_ARCH__
+    return ( uint32_t )__float2int_rz( __fmul_rn( ( float )d, 0.877f ) );
+#else
+    return ( uint32_t )( int )( ( float )d * 0.877f );
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t yuv_pack( int y, int b0, int b2 ) { return ( uint32_t )( y << 16 ) + yuv_u_term( b2 - y ) + yuv_v_term( b0 - y ); }
 __host__ __device__ __forceinline__ uint32_t yuv_word_t( int T, int b0, int b1, int b2 )
 {
     int y = luma_div( T );

@@ -56,7 +56,7 @@ EncodeTiledFn load_encode_tiled()
 
 struct par_context
 {
-    int device = 0;
+    int device = 0, n_sms = 0;
     int max_w = 0, max_h = 0, max_frames = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr; // copy_stream: D2H of par_remaster_host
     int sub_batch = 0; // frames per round of stage launches (0 = the whole batch per launch), par_set_sub_batch
@@ -431,6 +431,7 @@ int par_create( par_context** out, int device, int max_width, int max_height, in
     }
     par_context* c = new par_context();
     c->device = device;
+    c->n_sms = prop.multiProcessorCount;
     c->max_w = max_width;
     c->max_h = max_height;
     c->max_frames = max_frames;

@@ -48,6 +48,44 @@ def test_graph_stages_bit_exact(ctx, oracle, name, img, no_tma):
     assert np.array_equal(g[0].cpu().numpy(), want["graph"]), "stage C differs"
 
 
+@pytest.mark.parametrize("name,img", _cases(), ids=[c[0] for c in _cases()])
+@pytest.mark.parametrize("no_tma", [False, True], ids=["tma", "plain"])
+def test_whole_path_graphs_bit_exact(ctx, oracle, name, img, no_tma):
+    """Both graphs as the whole path (par_remaster_device) leaves them — same bytes as the stage entry points and as the oracle."""
+    want = oracle.pipeline(img, want=("graph_aux", "graph"))
+    out = ctx.remaster(_dev(ctx, img[None]), scale=1, subdivide=False, want=("graph", "graph_aux"), no_tma=no_tma)
+    assert np.array_equal(out["graph_aux"][0].cpu().numpy(), want["graph_aux"]), "stage A+B differs"
+    assert np.array_equal(out["graph"][0].cpu().numpy(), want["graph"]), "stage C differs"
+
+
+def test_whole_path_graphs_on_hard_inputs(lib, oracle):
+    """The graph stages on inputs chosen against them: a checkerboard (every block ambiguous and falling through to the
+    curve-length walks), 2- and 4-colour noise (all rules, chains that cross tile seams), near-black pixels on the borders,
+    widths that are not multiples of 4 or of the tile, batches — whole path and stage entries against the oracle, frame by frame."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    rng = np.random.default_rng(11)
+    for W, H, F in ((64, 32, 3), (65, 33, 3), (130, 70, 4), (63, 95, 2), (200, 129, 3), (5, 300, 2), (301, 6, 2)):
+        frames = np.zeros((F, H, W, 3), np.uint8)
+        yy, xx = np.mgrid[0:H, 0:W]
+        frames[0][(yy + xx) % 2 == 0] = (250, 250, 250)                                      # checkerboard
+        pal = np.array([[0, 0, 0], [3, 2, 4], [200, 40, 90], [250, 250, 250]], np.uint8)
+        frames[1] = pal[rng.integers(0, 2, (H, W)) * 2]                                       # 2-colour noise (black / colour)
+        for k in range(2, F):
+            frames[k] = pal[rng.integers(0, 4, (H, W))]                                       # near-black + colours
+        for no_tma in (False, True):
+            with lib.Remaster(0, W, H, F) as c:
+                out = c.remaster(torch.from_numpy(frames).cuda(), scale=1, subdivide=False, want=("graph", "graph_aux"), no_tma=no_tma)
+                aux = c.similarity_graph(torch.from_numpy(frames).cuda(), no_tma=no_tma)
+                assert torch.equal(aux, out["graph_aux"])
+                assert torch.equal(c.resolve_crossings(aux, no_tma=no_tma), out["graph"])
+            for k in range(F):
+                want = oracle.pipeline(frames[k], want=("graph_aux", "graph"))
+                assert np.array_equal(out["graph_aux"][k].cpu().numpy(), want["graph_aux"]), (W, H, k, no_tma)
+                assert np.array_equal(out["graph"][k].cpu().numpy(), want["graph"]), (W, H, k, no_tma)
+
+
 @pytest.mark.parametrize("w,h", [(1, 1), (2, 3), (4, 4), (7, 5), (63, 31), (64, 32), (65, 33), (128, 64), (129, 35), (200, 70)])
 @pytest.mark.parametrize("no_tma", [False, True], ids=["tma", "plain"])
 def test_graph_black_and_dark_pixels_on_the_border(ctx, oracle, w, h, no_tma):
@@ -75,6 +113,35 @@ def test_cc_labels_bit_exact(ctx, oracle, name, img):
     g = torch.from_numpy(want["graph"][None]).to(ctx.device)
     lab = ctx.cc_labels(g)
     assert np.array_equal(lab[0].cpu().numpy(), want["labels"])
+
+
+def test_cc_labels_on_hard_graphs(lib, oracle):
+    """The labeller on inputs chosen against union-find: one component that snakes through the whole frame, a checkerboard
+    graph (diagonal links only), noise, widths that are not multiples of the tile, and a batch."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    rng = np.random.default_rng(21)
+    for W, H in ((256, 256), (257, 256), (255, 257), (33, 70), (31, 3), (1, 50), (400, 160)):
+        imgs = []
+        snake = np.zeros((H, W, 3), np.uint8)
+        snake[...] = (10, 200, 30)
+        for x in range(1, W - 1, 4):
+            snake[1:H - 1, x] = (250, 20, 20)
+            if x + 4 < W - 1:
+                snake[(H - 2) if (x // 4) % 2 else 1, x:x + 5] = (250, 20, 20)
+        imgs.append(snake)
+        chk = np.zeros((H, W, 3), np.uint8)
+        yy, xx = np.mgrid[0:H, 0:W]
+        chk[(yy + xx) % 2 == 0] = (255, 255, 255)
+        imgs.append(chk)
+        pal = rng.integers(0, 256, (3, 3), dtype=np.uint8)
+        imgs.append(pal[rng.integers(0, 3, (H, W))])
+        graphs = np.stack([oracle.pipeline(im, want=("graph",))["graph"] for im in imgs])
+        want = np.stack([oracle.cc_labels(g) for g in graphs])
+        with lib.Remaster(0, W, H, len(imgs)) as c:
+            g = torch.from_numpy(graphs).cuda()
+            assert np.array_equal(c.cc_labels(g).cpu().numpy(), want), (W, H)
 
 
 @pytest.mark.parametrize("name,img", _cases(), ids=[c[0] for c in _cases()])
