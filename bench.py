@@ -348,8 +348,15 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa = bind_to_gpu_numa_node(local)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")  # host-side barriers: waiting ranks must not keep a kernel spinning on their GPU
+
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=host_group)
 
     def barrier():
         if world > 1:
@@ -532,8 +539,11 @@ def run_ours(args):
                                                  "unit": "frames/s", "what": "output left in HBM as " + name.upper()}
             del o_fmt
     # ---- config C4 (one large map over the GPUs of the job), rank 0 drives all devices while the others wait
+    # (host-side barriers around it: an NCCL barrier would leave a kernel of the waiting ranks spinning on the very GPUs rank 0
+    # is about to use, and two processes' kernels on one GPU are time-sliced)
     tiled = None
     barrier()
+    host_barrier()
     if rank == 0 and not args.no_tiled:
         try:
             del novel
@@ -545,6 +555,7 @@ def run_ours(args):
         except Exception as exc:  # a side check must never break the bench line
             tiled = {"ok": False, "error": str(exc)[:300]}
         torch.cuda.set_device(local)
+    host_barrier()
     barrier()
 
     if rank == 0:

@@ -156,6 +156,17 @@ int par_smooth_stats( par_context* ctx, uint64_t* out2 );
 int par_border_walks( par_context* ctx, const uint8_t* graph, const int32_t* labels, int width, int height, int n_frames, int32_t* walk_len,
                       int32_t* walk_begin, int32_t* walk_nodes, long long capacity_per_frame, long long* total );
 
+/* Splines through the border walks (the Kopf-Lischinski stage the reference's walker, cc_functions.cu:348-503,
+ * was written for and never reached): every walk is taken as a closed control polygon — the centres (x + 1/2, y + 1/2) of its
+ * nodes, in source-pixel coordinates, row 0 = bottom — and sampled as the closed uniform quadratic B-spline over it, at
+ * `samples_per_segment` (1, 2, 4 or 8) parameter values per node: sample (b + i) * samples + s belongs to node i of the walk
+ * that begins at entry b of the frame's walk_nodes (segment i runs from the midpoint of nodes i-1, i to the midpoint of i, i+1).
+ * walk_len, walk_begin, walk_nodes, total: the outputs of par_border_walks (DEVICE pointers); points: out, DEVICE,
+ * n_frames * capacity_per_frame * samples_per_segment (x, y) float pairs; a frame with total > capacity_per_frame writes
+ * none.  Results are exact dyadic rationals (no rounding).  Asynchronous. */
+int par_walk_splines( par_context* ctx, const int32_t* walk_len, const int32_t* walk_begin, const int32_t* walk_nodes, const long long* total, int width,
+                      int height, int n_frames, long long capacity_per_frame, int samples_per_segment, float* points );
+
 /* Whole path on device-resident frames; asynchronous on the context's stream. */
 int par_remaster_device( par_context* ctx, const par_job* job );
 /* Whole path on host buffers: H2D of the frames, the kernels, D2H of every non-NULL output, then a

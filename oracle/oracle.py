@@ -141,6 +141,19 @@ class Oracle:
             pos += int(wl[n])
         return out
 
+    @staticmethod
+    def walk_spline(nodes, W, samples=4):
+        """Closed uniform quadratic B-spline over one walk's node centres (the product's own rule, the reference stops at the
+        walk, cc_functions.cu:348-503): (len * samples, 2) float64 points, segment i from the midpoint of nodes i-1, i to
+        the midpoint of i, i+1, sampled at t = s / samples."""
+        n = np.asarray(nodes, np.int64)
+        P = np.stack([n % W + 0.5, n // W + 0.5], -1)
+        prev, nxt = np.roll(P, 1, 0), np.roll(P, -1, 0)
+        t = (np.arange(samples) / samples)[None, :, None]
+        w0, w2 = 0.5 * (1 - t) ** 2, 0.5 * t ** 2
+        pts = w0 * prev[:, None] + (1 - w0 - w2) * P[:, None] + w2 * nxt[:, None]
+        return pts.reshape(-1, 2)
+
     def all_dyadic64(self, xy):
         a = np.ascontiguousarray(xy, np.float32).reshape(-1)
         return bool(self.lib.orc_all_dyadic64(a, a.size))

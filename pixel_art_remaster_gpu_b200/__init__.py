@@ -82,6 +82,8 @@ def load_library():
     L.par_set_sub_batch.argtypes = [C.c_void_p, C.c_int]
     L.par_border_walks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_longlong, C.c_void_p]
+    L.par_walk_splines.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int,
+                                   C.c_void_p]
     L.par_smooth_stats.argtypes = [C.c_void_p, P(C.c_uint64)]
     L.par_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.par_profile_read.argtypes = [C.c_void_p, P(C.c_double), P(C.c_int)]
@@ -332,6 +334,19 @@ class Remaster:
         self._check(self.lib.par_border_walks(self.handle, graph.data_ptr(), labels.data_ptr(), W, H, F, wl.data_ptr(), wb.data_ptr(),
                                               nodes.data_ptr(), cap, total.data_ptr()))
         return wl, wb, nodes, total
+
+    def walk_splines(self, walk_len, walk_begin, walk_nodes, total, samples=4):
+        """Closed uniform quadratic B-spline of every border walk (par_walk_splines): (F, capacity * samples, 2) float32
+        device tensor of curve points in source-pixel coordinates; sample (b + i) * samples + s belongs to node i of the
+        walk that begins at entry b."""
+        t = self._torch
+        F, H, W = walk_len.shape
+        cap = walk_nodes.shape[1]
+        self._bind_stream()
+        pts = t.zeros((F, cap * samples, 2), dtype=t.float32, device=walk_len.device)
+        self._check(self.lib.par_walk_splines(self.handle, walk_len.data_ptr(), walk_begin.data_ptr(), walk_nodes.data_ptr(), total.data_ptr(),
+                                              W, H, F, cap, int(samples), pts.data_ptr()))
+        return pts
 
     @staticmethod
     def walks_as_dict(walk_len, walk_begin, walk_nodes, frame=0):

@@ -664,6 +664,21 @@ int par_border_walks( par_context* c, const uint8_t* graph, const int32_t* label
     return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "border_walks" );
 }
 
+int par_walk_splines( par_context* c, const int32_t* walk_len, const int32_t* walk_begin, const int32_t* walk_nodes, const long long* total, int width,
+                      int height, int n_frames, long long capacity_per_frame, int samples_per_segment, float* points )
+{
+    if( !c ) return PAR_ERR_INVALID;
+    if( !walk_len || !walk_begin || !walk_nodes || !total || !points ) return c->fail( PAR_ERR_INVALID, "walk_splines: NULL pointer" );
+    if( width <= 0 || height <= 0 || n_frames <= 0 || capacity_per_frame <= 0 ) return c->fail( PAR_ERR_INVALID, "walk_splines: empty frame, batch or capacity" );
+    if( samples_per_segment != 1 && samples_per_segment != 2 && samples_per_segment != 4 && samples_per_segment != 8 )
+        return c->fail( PAR_ERR_INVALID, "walk_splines: samples_per_segment must be 1, 2, 4 or 8 (exact float results)" );
+    DeviceGuard guard( c->device );
+    cudaError_t e = launch_walk_splines( walk_len, walk_begin, total, walk_nodes, width, height, n_frames, capacity_per_frame, samples_per_segment, points,
+                                         c->stream );
+    c->launches += ( n_frames + 65534 ) / 65535;
+    return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "walk_splines" );
+}
+
 int par_remaster_device( par_context* c, const par_job* j )
 {
     int st = check_job( c, j, true );

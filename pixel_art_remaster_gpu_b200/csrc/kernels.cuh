@@ -88,6 +88,9 @@ cudaError_t launch_cc_labels( const LabelArgs& a, cudaStream_t stream, int* n_la
 cudaError_t launch_border_walks( const uint8_t* graph, const int32_t* labels, int width, int height, int n_frames, int32_t* walk_len,
                                  int32_t* walk_begin, long long* total, int32_t* nodes, long long capacity, cudaStream_t stream );
 
+cudaError_t launch_walk_splines( const int32_t* walk_len, const int32_t* walk_begin, const long long* total, const int32_t* nodes, int width, int height,
+                                 int n_frames, long long capacity, int samples, float* points, cudaStream_t stream );
+
 cudaError_t launch_polygons( const RasterArgs& a, cudaStream_t stream );
 void raster_tma_box( int scale, uint32_t box[ 3 ] );
 size_t mask_lut_words( int scale );

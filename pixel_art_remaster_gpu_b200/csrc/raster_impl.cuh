@@ -750,29 +750,23 @@ __device__ __forceinline__ uint32_t link_slots( const Tabs& tabs, const uint16_t
     return mismatch;
 }
 
-// Mask of a smoothed cell from the tables, FIRST pass: the CUT entry and the first two link descriptors (nine cells in
-// ten have no more).  `more` is set when the key has a third descriptor: the caller marks the cell for
-// smooth_lookup_more.  Returns false when a blended vertex is not a vertex of the neighbour's hull (the reference's
-// getPointIndex fallback) — the caller then takes the geometric path.
-// checkTJunction for the corners of the pixel square named in `need` (bit c: corner (0,0) (1,0) (1,1) (0,1)): bit c of the
-// result is set when corner c stays, i.e. the three other pixels around it are not one colour (subdivision_functions.cu:
-// 195-242).  c points at the cell's colour in the tile; loads of pixels no needed corner looks at are predicated off.
+// checkTJunction for the four corners of the pixel square (0,0) (1,0) (1,1) (0,1): bit c of the result is set when corner c
+// stays, i.e. the three other pixels around it are not one colour (subdivision_functions.cu:195-242).  c points at the
+// cell's colour in the tile.  (Loads predicated on the corners the hull has a cut vertex at were measured: no faster.)
 template< int KW >
-__device__ __forceinline__ uint32_t corner_flags( const uint32_t* c, uint32_t need )
+__device__ __forceinline__ uint32_t corner_flags( const uint32_t* c )
 {
-    const uint32_t l = ( need & 9u ) ? c[ -1 ] : 0u, r = ( need & 6u ) ? c[ 1 ] : 0u, d = ( need & 3u ) ? c[ -KW ] : 0u, u = ( need & 12u ) ? c[ KW ] : 0u;
-    const uint32_t dl = ( need & 1u ) ? c[ -KW - 1 ] : 0u, dr = ( need & 2u ) ? c[ -KW + 1 ] : 0u, ur = ( need & 4u ) ? c[ KW + 1 ] : 0u,
-                   ul = ( need & 8u ) ? c[ KW - 1 ] : 0u;
-    return ( ( ( l != dl || dl != d ) ? 1u : 0u ) | ( ( r != dr || dr != d ) ? 2u : 0u ) | ( ( r != ur || ur != u ) ? 4u : 0u ) |
-             ( ( l != ul || ul != u ) ? 8u : 0u ) ) & need;
+    const uint32_t l = c[ -1 ], r = c[ 1 ], d = c[ -KW ], u = c[ KW ];
+    const uint32_t dl = c[ -KW - 1 ], dr = c[ -KW + 1 ], ul = c[ KW - 1 ], ur = c[ KW + 1 ];
+    return ( ( l != dl || dl != d ) ? 1u : 0u ) | ( ( r != dr || dr != d ) ? 2u : 0u ) | ( ( r != ur || ur != u ) ? 4u : 0u ) | ( ( l != ul || ul != u ) ? 8u : 0u );
 }
 
 // Mask of a smoothed cell from the tables, FIRST pass: the CUT entry and the first two link descriptors (nine cells in
 // ten have no more).  `more` is set when the key has a third descriptor: the caller marks the cell for
 // smooth_lookup_more.  Returns false when a blended vertex is not a vertex of the neighbour's hull (the reference's
 // getPointIndex fallback) — the caller then takes the geometric path.
-// colours: the cell's colour in the tile (for checkTJunction, only the corners where the hull has a cut vertex are looked
-// at); guarded: checkTJunction's early exit (:187) keeps every cut vertex, the mask is the plain hull's.
+// colours: the cell's colour in the tile (for checkTJunction); guarded: checkTJunction's early exit (:187) keeps every cut
+// vertex, the mask is the plain hull's.
 // (Tried and dropped in round 2: a per-scale 16-byte "head" record per key — the first two descriptors and CUT[key][0] in one
 // gather, so that most cells skip the CUT gather: one gather in six less, no change in time, profiles/r2d_*.)
 template< int S, class Tabs >
@@ -784,7 +778,11 @@ __device__ __forceinline__ bool smooth_lookup( const Tabs& tabs, const uint32_t*
     const SmoothTablePtrs& st = tabs.st;
     const uint4 rec = __ldg( reinterpret_cast< const uint4* >( st.rec + key ) ); // the four link descriptors
     more = ( rec.z >> 16 ) != 0u; // (descriptors fill the slots from 0)
-    const uint32_t kept = guarded ? 0u : corner_flags< C::KW >( colours, ( rec.x >> 4 ) & 15u ); // (only corners with a cut vertex matter)
+#if PAR_CF_EARLY
+    const uint32_t kept = ( uint32_t )( uintptr_t )colours & ( rec.x >> 4 ) & 15u; // (the caller passes the flags in place of the pointer)
+#else
+    const uint32_t kept = guarded ? 0u : ( corner_flags< C::KW >( colours ) & ( rec.x >> 4 ) & 15u ); // (only corners with a cut vertex matter)
+#endif
     uint64_t flags = 0ull;
     if( guarded ) // the plain hull
     {
@@ -1040,7 +1038,16 @@ __device__ __forceinline__ void raster_tile( const CUtensorMap* graph_map, const
             n_smoothed++;
             uint64_t mw[ Entry< S >::EW ];
             bool wide = false, more = false;
+#ifndef PAR_CF_EARLY
+#define PAR_CF_EARLY 0
+#endif
+#if PAR_CF_EARLY
+            const bool guarded = env.guard( gx, gy );
+            const uint32_t cf_early = guarded ? 0u : corner_flags< C::KW >( s_col + ( cy + 1 ) * C::KW + ( cx + 1 ) );
+            if( use_tables && smooth_lookup< S >( tabs, a.mask_lut, kc, reinterpret_cast< const uint32_t* >( ( uintptr_t )cf_early ), guarded, key, mw, wide, more ) )
+#else
             if( use_tables && smooth_lookup< S >( tabs, a.mask_lut, kc, s_col + ( cy + 1 ) * C::KW + ( cx + 1 ), env.guard( gx, gy ), key, mw, wide, more ) )
+#endif
             {
                 third_link = more;
                 if( C::PACK )

@@ -129,6 +129,44 @@ __global__ void __launch_bounds__( kThreads ) walk_write_kernel( const uint8_t* 
     walk_component( graph + f * n_px, ( int )n, width, n_px, [ out ]( int k, int node ) { out[ k ] = node; } );
 }
 
+// ---- splines through the walks -------------------------------------------------------------------------------------
+// The stage the reference's author had started the walker for (Kopf-Lischinski: quadratic B-splines along the region
+// outlines; the reference stops at the walk, cc_functions.cu:348-503).  Every walk is a closed control polygon — the centres
+// (x + 1/2, y + 1/2) of its nodes in walk order — and the curve is the closed uniform quadratic B-spline over it: segment i
+// runs from the midpoint of P(i-1) P(i) to the midpoint of P(i) P(i+1),
+//     B_i(t) = 1/2 [ (1-t)^2 P(i-1) + (-2t^2 + 2t + 1) P(i) + t^2 P(i+1) ],   t in [0, 1),
+// sampled at t = s / k, s = 0 .. k-1, for k a power of two: every weight is a multiple of 1/(2 k^2) and every coordinate a
+// multiple of 1/2, so the float results are exact and equal any other evaluation order bit for bit.
+// One thread per walk start walks its own nodes: sample (b + i) * k + s of the frame belongs to node i of the walk that
+// begins at entry b — the layout of walk_nodes, times k.
+__global__ void __launch_bounds__( kThreads ) walk_spline_kernel( const int32_t* walk_len, const int32_t* walk_begin, const long long* total, const int32_t* nodes,
+                                                                int width, long n_px, long long capacity, int k, float2* points )
+{
+    const long n = ( long )blockIdx.x * kThreads + threadIdx.x;
+    if( n >= n_px ) return;
+    const size_t f = blockIdx.y;
+    const int len = walk_len[ f * n_px + n ];
+    if( len == 0 || total[ f ] > capacity ) return;
+    const long long b = walk_begin[ f * n_px + n ];
+    const int32_t* w = nodes + f * capacity + b;
+    float2* out = points + ( f * capacity + b ) * k;
+    auto centre = [ width ]( int node ) { return make_float2( ( float )( node % width ) + 0.5f, ( float )( node / width ) + 0.5f ); };
+    float2 prev = centre( w[ len - 1 ] ), cur = centre( w[ 0 ] );
+    const float inv_k = 1.0f / ( float )k;
+    for( int i = 0; i < len; i++ )
+    {
+        const float2 next = centre( w[ i + 1 == len ? 0 : i + 1 ] );
+        for( int s = 0; s < k; s++ )
+        {
+            const float t = ( float )s * inv_k;
+            const float w0 = 0.5f * ( 1.0f - t ) * ( 1.0f - t ), w2 = 0.5f * t * t, w1 = 1.0f - w0 - w2;
+            out[ ( size_t )i * k + s ] = make_float2( w0 * prev.x + w1 * cur.x + w2 * next.x, w0 * prev.y + w1 * cur.y + w2 * next.y );
+        }
+        prev = cur;
+        cur = next;
+    }
+}
+
 } // namespace
 
 cudaError_t launch_border_walks( const uint8_t* graph, const int32_t* labels, int width, int height, int n_frames, int32_t* walk_len,
@@ -144,6 +182,25 @@ cudaError_t launch_border_walks( const uint8_t* graph, const int32_t* labels, in
         walk_scan_kernel<<< nf, 1024, 0, stream >>>( walk_len + off, n_px, walk_begin + off, total + f0 );
         walk_write_kernel<<< grid, kThreads, 0, stream >>>( graph + off, width, height, walk_len + off, walk_begin + off, total + f0,
                                                             nodes + ( size_t )f0 * capacity, capacity );
+    }
+    return cudaGetLastError();
+}
+
+} // namespace par
+
+namespace par {
+
+cudaError_t launch_walk_splines( const int32_t* walk_len, const int32_t* walk_begin, const long long* total, const int32_t* nodes, int width, int height,
+                                 int n_frames, long long capacity, int samples, float* points, cudaStream_t stream )
+{
+    const long n_px = ( long )width * height;
+    for( int f0 = 0; f0 < n_frames; f0 += 65535 ) // (grid.y limit)
+    {
+        const int nf = n_frames - f0 < 65535 ? n_frames - f0 : 65535;
+        const size_t off = ( size_t )f0 * n_px;
+        const dim3 grid( ( unsigned )( ( n_px + kThreads - 1 ) / kThreads ), nf );
+        walk_spline_kernel<<< grid, kThreads, 0, stream >>>( walk_len + off, walk_begin + off, total + f0, nodes + ( size_t )f0 * capacity, width, n_px, capacity,
+                                                             samples, reinterpret_cast< float2* >( points ) + ( size_t )f0 * capacity * samples );
     }
     return cudaGetLastError();
 }

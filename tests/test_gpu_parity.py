@@ -369,6 +369,21 @@ def test_border_walks(lib, oracle):
             wl2, wb2, nodes2, total2 = c.border_walks(out["graph"], out["labels"], capacity_per_frame=8)
             torch.cuda.synchronize()
             assert torch.equal(total2, total) and torch.equal(wl2, wl)
+            # splines through the walks (par_walk_splines): closed uniform quadratic B-spline over the node centres, exact
+            # dyadic arithmetic -> equal to the numpy restatement bit for bit, at every sample count
+            for samples in (1, 2, 4, 8):
+                pts = c.walk_splines(wl, wb, nodes, total, samples).cpu().numpy()
+                for k in range(F):
+                    for start, walk in c.walks_as_dict(wl, wb, nodes, k).items():
+                        b = int(wb[k].reshape(-1)[start])
+                        want_pts = oracle.walk_spline(walk, W, samples)
+                        got_pts = pts[k, b * samples:(b + len(walk)) * samples]
+                        assert np.array_equal(got_pts.astype(np.float64), want_pts), (W, H, k, start, samples)
+                        # the curve of a closed polygon stays inside the polygon's bounding box and passes through the edge midpoints
+                        P = np.stack([np.asarray(walk) % W + 0.5, np.asarray(walk) // W + 0.5], -1)
+                        assert np.array_equal(got_pts[::samples].astype(np.float64), (np.roll(P, 1, 0) + P) / 2)
+            with pytest.raises(lib.RemasterError):
+                c.walk_splines(wl, wb, nodes, total, 3)
     here = os.path.dirname(os.path.abspath(__file__))
     cases = json.load(open(os.path.join(here, "golden", "border_walks_small.json")))
     for case in cases:

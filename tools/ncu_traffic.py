@@ -1,7 +1,9 @@
-"""DRAM traffic of the raster kernel from an `ncu --set full` report -> profiles/r1_raster_traffic.json (bench.py reads
-it for roofline.traffic).  Usage: python tools/ncu_traffic.py report.ncu-rep frames_in_the_profiled_launch"""
+"""DRAM traffic of the raster kernel from an ncu report (dram__bytes_read.sum, dram__bytes_write.sum) -> profiles/<name>
+(bench.py reads profiles/r2_raster_traffic.json for roofline.traffic).
+Usage: python tools/ncu_traffic.py report.ncu-rep frames_in_the_profiled_launch [output name]"""
 import csv, io, json, subprocess, sys
 rep, frames = sys.argv[1], int(sys.argv[2])
+name = sys.argv[3] if len(sys.argv) > 3 else "r2_raster_traffic.json"
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 h, u = rows[0], rows[1]
@@ -13,6 +15,6 @@ def val(name):
 rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
 json.dump({"dram_bytes_read": rd, "dram_bytes_write": wr, "frames": frames, "dram_bytes_per_frame": (rd + wr) / frames,
            "algorithmic_bytes_per_frame": 256 * 224 * 68,
-           "source": "ncu --set full, %s, raster_kernel<4> over %d frames of 256x224 (dram__bytes_read.sum + dram__bytes_write.sum)" % (rep.split("/")[-1], frames)},
-          open("profiles/r1_raster_traffic.json", "w"), indent=1)
-print(open("profiles/r1_raster_traffic.json").read())
+           "source": "ncu, %s, raster_kernel<4> over ONE launch of %d frames of 256x224 (dram__bytes_read.sum + dram__bytes_write.sum)" % (rep.split("/")[-1], frames)},
+          open("profiles/" + name, "w"), indent=1)
+print(open("profiles/" + name).read())

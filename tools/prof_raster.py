@@ -9,4 +9,6 @@ frames = torch.from_numpy(synth.snes_stream(F, 256, 224)).cuda()
 ctx = par.Remaster(0, 256, 224, F)
 for it in range(3):
     out = ctx.remaster(frames, S, True, want=("rgba", "graph", "graph_aux", "labels"))
+    del out
+idx = ctx.remaster(frames, S, True, out_format=par.OUT_INDEX8)  # + the palette kernels, the raster kernel writing indices
 torch.cuda.synchronize()

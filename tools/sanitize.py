@@ -15,6 +15,11 @@ for (W, H, S) in ((96, 80, 4), (50, 37, 8), (65, 33, 3)):
             out = ctx.remaster(frames, S, True, want=("rgba",), no_tma=no_tma)  # geometric path for every smoothed cell
             ctx.no_tables = False
             out = ctx.remaster(frames, S, False, want=("rgba",), no_tma=no_tma)  # hull cells only
+            for fmt in (par.OUT_BGR8, par.OUT_INDEX8):  # output formats (+ the palette kernels)
+                out = ctx.remaster(frames, S, True, no_tma=no_tma, out_format=fmt)
+        lab = ctx.remaster(frames, 1, False, want=("graph", "labels"))
+        wl, wb, nodes, total = ctx.border_walks(lab["graph"], lab["labels"])
+        ctx.walk_splines(wl, wb, nodes, total, 4)
         torch.cuda.synchronize()
 # 3-colour noise: every key, cells with three and four link descriptors (second table pass), blends whose vertex the
 # neighbour does not have (geometric path, and from the second pass the exact tile resolve)
@@ -26,6 +31,12 @@ with par.Remaster(0, 90, 70, 2) as ctx:
     torch.cuda.synchronize()
 img = synth.adversarial_sprite(96, 100, 3)
 par.launch_kernel(img, True)
-with par.RemasterGroup([0, 0], 96, 100, 4) as g:
-    g.remaster_host(img, want=("rgba", "graph", "labels"))
+with par.RemasterGroup([0, 0, 0], 96, 130, 4) as g:
+    big = synth.adversarial_sprite(96, 130, 3)
+    g.remaster_host(big, want=("rgba", "graph", "labels"))
+    for st in g.strips():  # the device-resident entry: halo rows by peer copies, on-device label stitch
+        lo, hi = st["own"]
+        st["bgr"][lo - st["load"][0]:hi - st["load"][0]].copy_(torch.from_numpy(big[lo:hi]))
+    torch.cuda.synchronize()
+    g.remaster_device(True)
 print("sanitize run done")
