@@ -408,12 +408,12 @@ __device__ __noinline__ void window_coverage( const uint16_t* keys, const uint32
 // for tiles that contain a cell reaching beyond its mask, or under PAR_FLAG_DEBUG_WIDE.
 template< int S, int A, int FMT >
 __device__ __noinline__ void resolve_tile_exact( const uint16_t* keys, const uint32_t* cols, int x0, int y0, const uint8_t* frame, int width, int height,
-                                                 int widthstep, const CellRecord* rec, bool subdivide, uint8_t* out, bool flip, int tid )
+                                                 int widthstep, const CellRecord* rec, bool subdivide, uint8_t* out, bool flip )
 {
     typedef Cfg< S > C;
     constexpr int O = S / A;
     const size_t out_w = ( size_t )width * O, out_h = ( size_t )height * O;
-    for( int idx = tid; idx < C::TW * C::TH; idx += kThreads )
+    for( int idx = threadIdx.x; idx < C::TW * C::TH; idx += kThreads )
     {
         const int ly = idx / C::TW, lx = idx - ly * C::TW, gx = x0 + lx, gy = y0 + ly;
         if( gx >= width || gy >= height ) continue;
@@ -449,7 +449,7 @@ __device__ __noinline__ void resolve_tile_exact( const uint16_t* keys, const uin
 template< int S >
 __device__ __noinline__ void geometric_cells( const uint16_t* keys, const uint32_t* cols, uint32_t* s_mask, const uint16_t* s_work, uint16_t* s_vbuf, int* s_nwork,
                                               int x0, int y0, const uint8_t* frame, int width, int height, int widthstep, const CellRecord* rec,
-                                              uint32_t force_wide, int tid )
+                                              uint32_t force_wide )
 {
     typedef Cfg< S > C;
     TileEnv< S > env;
@@ -462,6 +462,7 @@ __device__ __noinline__ void geometric_cells( const uint16_t* keys, const uint32
     env.img.height = height;
     env.img.widthstep = widthstep;
     const CellTablePtrs tab{ rec };
+    const int tid = threadIdx.x;
     const int n_work = *s_nwork;
     uint16_t* vbuf = s_vbuf + tid;
     for( int w = tid; w < n_work && tid < kGeoThreads; w += kGeoThreads )
@@ -698,19 +699,8 @@ __global__ void build_link_table_kernel( const LinkClass* classes, uint64_t* lin
 // NS link descriptors of a smoothed cell, without branches (the loads of the slots overlap; an unused slot (0)
 // compares nothing and loads nothing): XORs their LINK entries into m, ORs word 0 of the entries into `flags`, returns
 // the mismatch bits (non-zero: a blended vertex is not the end / start of the neighbour's edge).
-// Where the mask pass finds the smoothing tables: in HBM / L2 / L1, one gather per lane and entry (up to 32 L1 wavefronts for
-// a warp whose lanes hold 32 different keys).  (A policy type, because a second home was tried and dropped in round 2: a
-// persistent kernel, one CTA of four 256-thread groups per SM, with the first two link descriptors, the neighbour records
-// and the LINK entries in 120 KB of shared memory.  It took the LSU data pipe from 87 % to 64 %, but with 28 KB of L1 left
-// for the CUT entries and 32 warps per SM instead of 40 it was latency-bound and 20 % slower: profiles/r2b_*, r2c_*.)
-struct GlobalTables
-{
-    const SmoothTablePtrs& st; // (the kernel's parameter itself: read from the constant bank where it is used, no registers)
-    __device__ __forceinline__ uint32_t nbr( uint32_t nkey, uint32_t e ) const { return ( uint32_t )__ldg( &st.rec[ nkey ].nbr[ e ] ); }
-    __device__ __forceinline__ uint64_t link( size_t entry_word ) const { return __ldg( st.link + entry_word ); }
-};
-template< int S, int NS, class Tabs >
-__device__ __forceinline__ uint32_t link_slots( const Tabs& tabs, const uint16_t* keys_at_cell, const uint32_t* links, uint64_t* m, uint64_t& flags )
+template< int S, int NS >
+__device__ __forceinline__ uint32_t link_slots( const SmoothTablePtrs& st, const uint16_t* keys_at_cell, const uint32_t* links, uint64_t* m, uint64_t& flags )
 {
     typedef Cfg< S > C;
     typedef Entry< S > E;
@@ -728,7 +718,7 @@ __device__ __forceinline__ uint32_t link_slots( const Tabs& tabs, const uint16_t
                                     ( uint32_t )( uint8_t )( -KW + 1 ) << 24;
         const int koff = ( int )( int8_t )__byte_perm( off_lo, off_hi, e );
         const uint32_t nkey = keys_at_cell[ koff ];
-        nb[ k ] = ( d >> 16 ) ? tabs.nbr( nkey, e ^ 7u ) : 0u; // (an unused slot loads nothing)
+        nb[ k ] = ( d >> 16 ) ? ( uint32_t )__ldg( &st.rec[ nkey ].nbr[ e ^ 7u ] ) : 0u; // (an unused slot loads nothing)
     }
     uint32_t mismatch = 0u;
 #pragma unroll
@@ -738,11 +728,11 @@ __device__ __forceinline__ uint32_t link_slots( const Tabs& tabs, const uint16_t
         const uint32_t ends = ( d >> 16 ) & 255u;
         mismatch |= ( ( r ^ d ) >> 8 ) & ends; // the blended vertices must be the end (A) / start (B) of the neighbour's edge
         const uint32_t sub = r & ends; // rank a | rank b << 4 -> the class's 4 x 4 block (one 128-byte line at s <= 4)
-        const size_t le = ( size_t )( ( d >> 24 ) * 16u + ( ( sub & 3u ) | ( ( sub >> 2 ) & 12u ) ) ) * E::EW;
+        const uint64_t* le = st.link + ( size_t )( ( d >> 24 ) * 16u + ( ( sub & 3u ) | ( ( sub >> 2 ) & 12u ) ) ) * E::EW;
 #pragma unroll
         for( int w = 0; w < E::EW; w++ )
         {
-            const uint64_t v = ( d >> 16 ) ? tabs.link( le + w ) : 0ull;
+            const uint64_t v = ( d >> 16 ) ? __ldg( le + w ) : 0ull;
             if( w == 0 ) flags |= v;
             m[ w ] ^= v;
         }
@@ -750,41 +740,33 @@ __device__ __forceinline__ uint32_t link_slots( const Tabs& tabs, const uint16_t
     return mismatch;
 }
 
-// checkTJunction for the four corners of the pixel square (0,0) (1,0) (1,1) (0,1): bit c of the result is set when corner c
-// stays, i.e. the three other pixels around it are not one colour (subdivision_functions.cu:195-242).  c points at the
-// cell's colour in the tile.  (Loads predicated on the corners the hull has a cut vertex at were measured: no faster.)
-template< int KW >
-__device__ __forceinline__ uint32_t corner_flags( const uint32_t* c )
-{
-    const uint32_t l = c[ -1 ], r = c[ 1 ], d = c[ -KW ], u = c[ KW ];
-    const uint32_t dl = c[ -KW - 1 ], dr = c[ -KW + 1 ], ul = c[ KW - 1 ], ur = c[ KW + 1 ];
-    return ( ( l != dl || dl != d ) ? 1u : 0u ) | ( ( r != dr || dr != d ) ? 2u : 0u ) | ( ( r != ur || ur != u ) ? 4u : 0u ) | ( ( l != ul || ul != u ) ? 8u : 0u );
-}
-
+// (Round 2, measured and dropped — the numbers are under profiles/r2b_*, r2c_*, r2d_*, r2h_*, r2j_*:
+//  * a persistent kernel, one CTA of four 256-thread groups per SM, with the first two link descriptors, the neighbour
+//    records and the LINK entries in 120 KB of shared memory (bank-aware layouts): the LSU data pipe went from 87 % to 64 %,
+//    but with 28 KB of L1 left for the CUT entries (hit rate 64 % -> 20 %) and 32 warps per SM instead of 40 the kernel
+//    became latency-bound: 5.45 ms against 4.49 ms per 4096 frames;
+//  * a per-scale 16-byte "head" record per key (first two descriptors + CUT[key][0] in one gather, so that most cells skip
+//    the CUT gather) and colour loads predicated on the corners the hull has a cut vertex at: one gather in six and most
+//    of the eight shared loads per cell less, no change in time (4.42 ms) — the kernel is bound by instruction issue and
+//    load latency together, not by LSU wavefronts alone;
+//  * the corner flags computed after the descriptor load instead of before it: 1 % slower;
+//  * for the scales above 4, the window form on four 64-bit fields per cell (nine 64-bit shared loads per pixel instead of
+//    a word per candidate and sample row, an early exit for pixels that are all their own colour): bit-exact, and slower at
+//    every scale (8x: 2.32 against 2.14 ms per 512 frames, 6x: 1.89 / 1.41, 5x: 1.95 / 1.29, 7x: 3.86 / 2.03) — 64-bit shifts
+//    and selects cost more instructions than the shared loads they replace.)
 // Mask of a smoothed cell from the tables, FIRST pass: the CUT entry and the first two link descriptors (nine cells in
 // ten have no more).  `more` is set when the key has a third descriptor: the caller marks the cell for
 // smooth_lookup_more.  Returns false when a blended vertex is not a vertex of the neighbour's hull (the reference's
 // getPointIndex fallback) — the caller then takes the geometric path.
-// colours: the cell's colour in the tile (for checkTJunction); guarded: checkTJunction's early exit (:187) keeps every cut
-// vertex, the mask is the plain hull's.
-// (Tried and dropped in round 2: a per-scale 16-byte "head" record per key — the first two descriptors and CUT[key][0] in one
-// gather, so that most cells skip the CUT gather: one gather in six less, no change in time, profiles/r2d_*.)
-template< int S, class Tabs >
-__device__ __forceinline__ bool smooth_lookup( const Tabs& tabs, const uint32_t* mask_lut, const uint16_t* keys_at_cell, const uint32_t* colours, bool guarded,
-                                               uint32_t key, uint64_t* m, bool& wide, bool& more )
+template< int S >
+__device__ __forceinline__ bool smooth_lookup( const SmoothTablePtrs& st, const uint32_t* mask_lut, const uint16_t* keys_at_cell, uint32_t key, uint32_t cflags,
+                                               uint64_t* m, bool& wide, bool& more )
 {
     typedef Cfg< S > C;
     typedef Entry< S > E;
-    const SmoothTablePtrs& st = tabs.st;
     const uint4 rec = __ldg( reinterpret_cast< const uint4* >( st.rec + key ) ); // the four link descriptors
-    more = ( rec.z >> 16 ) != 0u; // (descriptors fill the slots from 0)
-#if PAR_CF_EARLY
-    const uint32_t kept = ( uint32_t )( uintptr_t )colours & ( rec.x >> 4 ) & 15u; // (the caller passes the flags in place of the pointer)
-#else
-    const uint32_t kept = guarded ? 0u : ( corner_flags< C::KW >( colours ) & ( rec.x >> 4 ) & 15u ); // (only corners with a cut vertex matter)
-#endif
     uint64_t flags = 0ull;
-    if( guarded ) // the plain hull
+    if( cflags & 16u ) // checkTJunction's early exit keeps every cut vertex: the plain hull
     {
         if( C::PACK )
         {
@@ -801,13 +783,14 @@ __device__ __forceinline__ bool smooth_lookup( const Tabs& tabs, const uint32_t*
     }
     else
     {
-        const uint64_t* e = st.cut + ( size_t )( key * 16u + kept ) * E::EW;
+        const uint64_t* e = st.cut + ( size_t )( key * 16u + ( cflags & ( rec.x >> 4 ) & 15u ) ) * E::EW; // (only corners with a cut vertex matter)
 #pragma unroll
         for( int w = 0; w < E::EW; w++ ) m[ w ] = __ldg( e + w );
     }
     bool ok = rec.x != kSmoothSlow;
     const uint32_t links[ 2 ] = { ok ? rec.x : 0u, rec.y };
-    ok = ok && link_slots< S, 2 >( tabs, keys_at_cell, links, m, flags ) == 0u;
+    more = ( rec.z >> 16 ) != 0u; // (descriptors fill the slots from 0)
+    ok = ok && link_slots< S, 2 >( st, keys_at_cell, links, m, flags ) == 0u;
     // the flag bit of word 0 was XORed along with the masks: restore it from the CUT entry (never wide) and the OR
     wide = ( flags & E::FLAG ) != 0ull;
     m[ 0 ] &= ~E::FLAG;
@@ -816,16 +799,16 @@ __device__ __forceinline__ bool smooth_lookup( const Tabs& tabs, const uint32_t*
 
 // SECOND pass, for the cells whose key has three or four link descriptors: the XOR of the remaining LINK entries (flag
 // bit cleared), `wide` from their flags; false on a mismatch as above.
-template< int S, class Tabs >
-__device__ __forceinline__ bool smooth_lookup_more( const Tabs& tabs, const uint16_t* keys_at_cell, uint32_t key, uint64_t* m, bool& wide )
+template< int S >
+__device__ __forceinline__ bool smooth_lookup_more( const SmoothTablePtrs& st, const uint16_t* keys_at_cell, uint32_t key, uint64_t* m, bool& wide )
 {
     typedef Entry< S > E;
-    const uint2 rec = __ldg( reinterpret_cast< const uint2* >( &tabs.st.rec[ key ].link[ 2 ] ) );
+    const uint2 rec = __ldg( reinterpret_cast< const uint2* >( &st.rec[ key ].link[ 2 ] ) );
     const uint32_t links[ 2 ] = { rec.x, rec.y };
     uint64_t flags = 0ull;
 #pragma unroll
     for( int w = 0; w < E::EW; w++ ) m[ w ] = 0ull;
-    const bool ok = link_slots< S, 2 >( tabs, keys_at_cell, links, m, flags ) == 0u;
+    const bool ok = link_slots< S, 2 >( st, keys_at_cell, links, m, flags ) == 0u;
     wide = ( flags & E::FLAG ) != 0ull;
     m[ 0 ] &= ~E::FLAG;
     return ok;
@@ -848,29 +831,12 @@ __device__ __forceinline__ uint32_t palette_index( const uint32_t* __restrict__ 
     return 255u;
 }
 
-// Who runs a tile: one CTA of kThreads threads per tile, __syncthreads, the TMA barrier used once.
-struct CtaTile // (everything comes from special registers: nothing is kept live across the kernel)
-{
-    static constexpr uint32_t parity = 0u;
-    // (read from the special register at every use: a thread index kept in a register for the whole kernel costs the one
-    // register that makes the difference between 48 registers with and without spills)
-    __device__ __forceinline__ int tid() const
-    {
-        int t;
-        asm volatile( "mov.u32 %0, %%tid.x;" : "=r"( t ) );
-        return t;
-    }
-    __device__ __forceinline__ int tile_x() const { return ( int )blockIdx.x; }
-    __device__ __forceinline__ int tile_y() const { return ( int )blockIdx.y; }
-    __device__ __forceinline__ int frame() const { return ( int )blockIdx.z; }
-    __device__ __forceinline__ void sync() const { __syncthreads(); }
-};
-// One tile: stages (1)-(3) of the design notes.  smem: the caller's Cfg< S >::smem_bytes of working memory (128-byte aligned);
-// the TMA barrier in it is initialised by the caller.
-template< int S, int A, bool kUseTma, int FMT, class Who, class Tabs >
-__device__ __forceinline__ void raster_tile( const CUtensorMap* graph_map, const CUtensorMap* img_map, const RasterArgs& a, const Tabs& tabs, uint8_t* smem, const Who& who )
+template< int S, int A, bool kUseTma, int FMT >
+__global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( const __grid_constant__ CUtensorMap graph_map, const __grid_constant__ CUtensorMap img_map,
+                                                           RasterArgs a )
 {
     typedef Cfg< S > C;
+    extern __shared__ __align__( 128 ) uint8_t smem[];
     uint8_t* s_graph = smem + C::off_graph;
     uint16_t* s_keys = reinterpret_cast< uint16_t* >( smem + C::off_keys );
     uint32_t* s_col = reinterpret_cast< uint32_t* >( smem + C::off_col );
@@ -880,27 +846,32 @@ __device__ __forceinline__ void raster_tile( const CUtensorMap* graph_map, const
     int* s_nwork = reinterpret_cast< int* >( smem + C::off_nwork );
     uint64_t* s_bar = reinterpret_cast< uint64_t* >( smem + C::off_bar );
 
-    const int x0 = who.tile_x() * C::TW, y0 = who.tile_y() * C::TH, f = who.frame();
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * C::TW, y0 = blockIdx.y * C::TH, f = blockIdx.z;
     const size_t frame_px = ( size_t )a.width * a.height;
     const uint8_t* frame = a.bgr + ( size_t )f * a.frame_stride;
     const uint8_t* graph = a.graph + ( size_t )f * frame_px;
 
     // (1) stage graph bytes: rows y0-2 .. y0+TH+1, columns x0-16 .. x0-16+GP-1; zero outside the image
-    if( who.tid() < 3 ) s_nwork[ who.tid() ] = 0; // [0] geometric work items, [1] smoothed cells (statistics), [2] some cell of the tile is wide
+    if( tid < 3 ) s_nwork[ tid ] = 0; // [0] geometric work items, [1] smoothed cells (statistics), [2] some cell of the tile is wide
     if( kUseTma )
     {
-        // (the previous tile's last reads of this memory, generic proxy, are ordered before the async-proxy writes by the
-        // caller's barrier + fence; the barrier word itself was initialised by the caller)
-        if( who.tid() == 0 )
+        if( tid == 0 )
+        {
+            mbar_init( s_bar, 1 );
+            fence_barrier_init();
+        }
+        __syncthreads();
+        if( tid == 0 )
         {
             mbar_expect_tx( s_bar, C::KH * C::GP + C::KH * C::RAWP );
-            tma_load_3d( s_graph, graph_map, s_bar, x0 - C::GOFF, y0 - 2, f );
-            tma_load_3d( smem + C::off_raw, img_map, s_bar, 3 * x0 - 16, y0 - 2, f ); // BGR bytes of tile + halo 2
+            tma_load_3d( s_graph, &graph_map, s_bar, x0 - C::GOFF, y0 - 2, f );
+            tma_load_3d( smem + C::off_raw, &img_map, s_bar, 3 * x0 - 16, y0 - 2, f ); // BGR bytes of tile + halo 2
         }
     }
     else
     {
-        for( int idx = who.tid(); idx < C::KH * C::GP; idx += kThreads )
+        for( int idx = tid; idx < C::KH * C::GP; idx += kThreads )
         {
             int r = idx / C::GP, c = idx - r * C::GP;
             int gx = x0 - C::GOFF + c, gy = y0 - 2 + r;
@@ -938,11 +909,11 @@ __device__ __forceinline__ void raster_tile( const CUtensorMap* graph_map, const
         // Four pixels per thread from aligned 32-bit words of the staged rows: byte permutes build the RGBA words
         // and the cell keys (left/right neighbour bits, kernel.cu:204-207), 128- / 64-bit stores.  TMA zero-filled
         // everything outside the image (row padding included), which is exactly "colour 0" / "no links".
-        mbar_wait( s_bar, who.parity );
+        mbar_wait( s_bar, 0 );
         static_assert( C::KW % 4 == 0 && C::RAWOFF == 10 && C::GOFF == 16, "group layout of the vectorised staging pass" );
         constexpr int QW = C::KW / 4;
         const int vl = x0 == 0 ? 1 : -1, vr = a.width - x0 + 2; // tile columns of the virtual colour columns x = -1, x = width
-        for( int idx = who.tid(); idx < QW * C::KH; idx += kThreads )
+        for( int idx = tid; idx < QW * C::KH; idx += kThreads )
         {
             const int cy = idx / QW, q = idx - cy * QW;
             const uint32_t* rw = reinterpret_cast< const uint32_t* >( smem + C::off_raw + cy * C::RAWP + 8 + 12 * q ); // pixel 4q starts at byte 10 + 12 q
@@ -971,7 +942,7 @@ __device__ __forceinline__ void raster_tile( const CUtensorMap* graph_map, const
     }
     else
     {
-        for( int idx = who.tid(); idx < C::KW * C::KH; idx += kThreads )
+        for( int idx = tid; idx < C::KW * C::KH; idx += kThreads )
         {
             int cy = idx / C::KW, cx = idx - cy * C::KW;
             int gx = x0 - 2 + cx, gy = y0 - 2 + cy;
@@ -985,16 +956,16 @@ __device__ __forceinline__ void raster_tile( const CUtensorMap* graph_map, const
                 w = virtual_colour( gx, gy );
             s_col[ idx ] = indexed( w );
         }
-        who.sync();
+        __syncthreads();
         // cell keys for tile + halo 2 (left/right neighbour bits, kernel.cu:204-207; zero outside the row)
-        for( int idx = who.tid(); idx < C::KW * C::KH; idx += kThreads )
+        for( int idx = tid; idx < C::KW * C::KH; idx += kThreads )
         {
             int ky = idx / C::KW, kx = idx - ky * C::KW;
             const uint8_t* g = s_graph + ky * C::GP + kx + C::GOFF - 2; // column x0-2+kx sits at staged column kx+GOFF-2
             s_keys[ idx ] = ( uint16_t )cell_key( g[ 0 ], g[ -1 ], g[ 1 ] );
         }
     }
-    who.sync();
+    __syncthreads();
 
     TileEnv< S > env;
     env.keys = s_keys;
@@ -1008,7 +979,7 @@ __device__ __forceinline__ void raster_tile( const CUtensorMap* graph_map, const
     const bool subdivide = a.subdivide != 0;
     const CellTablePtrs tab = a.tables;
     const uint32_t force_wide = a.debug_force_wide ? C::WIDE : 0u;
-    const bool use_tables = tabs.st.cut != nullptr && !a.debug_force_wide;
+    const bool use_tables = a.smooth.cut != nullptr && !a.debug_force_wide;
 
     // (2a) Every cell of tile + halo 1 gets its mask, in tile order: a warp's cells are neighbours, so the key, colour
     // and mask accesses are conflict-free and nothing is queued.  Cells whose polygon is their plain hull copy the mask
@@ -1019,11 +990,11 @@ __device__ __forceinline__ void raster_tile( const CUtensorMap* graph_map, const
     int n_smoothed = 0;
     constexpr int kRounds = ( C::NC + kThreads - 1 ) / kThreads;
     uint32_t* s_more = reinterpret_cast< uint32_t* >( s_nwork + 4 ); // [kRounds][8 warps]: the cells of a round with a third link, as ballots
-    const int warp = who.tid() >> 5, lane = who.tid() & 31;
+    const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll 1
     for( int round = 0; round < kRounds; round++ ) // (whole warps: the vote at the end needs every lane)
     {
-        const int idx = round * kThreads + who.tid();
+        const int idx = round * kThreads + tid;
         bool third_link = false;
         int cy = idx / C::CW, cx = idx - cy * C::CW;
         int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
@@ -1036,18 +1007,19 @@ __device__ __forceinline__ void raster_tile( const CUtensorMap* graph_map, const
         else if( inside && !plain )
         {
             n_smoothed++;
+            // checkTJunction for the four corners of the pixel square (bit c: corner c stays), 16 = its early exit
+            uint32_t cf = 16u;
+            if( !env.guard( gx, gy ) )
+            {
+                const uint32_t* c = s_col + ( cy + 1 ) * C::KW + ( cx + 1 );
+                const uint32_t l = c[ -1 ], r = c[ 1 ], d = c[ -C::KW ], u = c[ C::KW ];
+                const uint32_t dl = c[ -C::KW - 1 ], dr = c[ -C::KW + 1 ], ul = c[ C::KW - 1 ], ur = c[ C::KW + 1 ];
+                cf = ( ( l != dl || dl != d ) ? 1u : 0u ) | ( ( r != dr || dr != d ) ? 2u : 0u ) | ( ( r != ur || ur != u ) ? 4u : 0u ) |
+                     ( ( l != ul || ul != u ) ? 8u : 0u );
+            }
             uint64_t mw[ Entry< S >::EW ];
             bool wide = false, more = false;
-#ifndef PAR_CF_EARLY
-#define PAR_CF_EARLY 0
-#endif
-#if PAR_CF_EARLY
-            const bool guarded = env.guard( gx, gy );
-            const uint32_t cf_early = guarded ? 0u : corner_flags< C::KW >( s_col + ( cy + 1 ) * C::KW + ( cx + 1 ) );
-            if( use_tables && smooth_lookup< S >( tabs, a.mask_lut, kc, reinterpret_cast< const uint32_t* >( ( uintptr_t )cf_early ), guarded, key, mw, wide, more ) )
-#else
-            if( use_tables && smooth_lookup< S >( tabs, a.mask_lut, kc, s_col + ( cy + 1 ) * C::KW + ( cx + 1 ), env.guard( gx, gy ), key, mw, wide, more ) )
-#endif
+            if( use_tables && smooth_lookup< S >( a.smooth, a.mask_lut, kc, key, cf, mw, wide, more ) )
             {
                 third_link = more;
                 if( C::PACK )
@@ -1125,7 +1097,7 @@ __device__ __forceinline__ void raster_tile( const CUtensorMap* graph_map, const
             const uint16_t* kc = s_keys + ( cy + 1 ) * C::KW + cx + 1;
             uint64_t mw[ Entry< S >::EW ];
             bool wide = false;
-            const bool ok = smooth_lookup_more< S >( tabs, kc, *kc, mw, wide );
+            const bool ok = smooth_lookup_more< S >( a.smooth, kc, *kc, mw, wide );
             if( C::PACK )
             {
                 s_mask[ idx ] ^= ( uint32_t )mw[ 0 ];
@@ -1147,15 +1119,15 @@ __device__ __forceinline__ void raster_tile( const CUtensorMap* graph_map, const
         n_smoothed = __reduce_add_sync( 0xFFFFFFFFu, n_smoothed );
         if( lane == 0 ) atomicAdd( s_nwork + 1, n_smoothed );
     }
-    who.sync();
+    __syncthreads();
 
     // (2b) general path, out of line (rarely runs: it costs the common path neither registers nor code)
     if( *s_nwork != 0 )
     {
-        geometric_cells< S >( s_keys, s_col, s_mask, s_work, s_vbuf, s_nwork, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, force_wide, who.tid() );
-        who.sync(); // (uniform: the counter is final since the barrier before this pass)
+        geometric_cells< S >( s_keys, s_col, s_mask, s_work, s_vbuf, s_nwork, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, force_wide );
+        __syncthreads(); // (uniform: the counter is final since the barrier before this pass)
     }
-    if( a.smooth_stats && who.tid() == 0 )
+    if( a.smooth_stats && tid == 0 )
     {
         atomicAdd( a.smooth_stats, ( unsigned long long )s_nwork[ 1 ] );     // smoothed cells
         atomicAdd( a.smooth_stats + 1, ( unsigned long long )s_nwork[ 0 ] ); // ... of which took the geometric path
@@ -1171,14 +1143,14 @@ __device__ __forceinline__ void raster_tile( const CUtensorMap* graph_map, const
     {
         // some cell of this tile reaches beyond its mask (never seen on real frames): the whole tile is resolved by
         // the exact path, kept out of line so that it costs the common path neither registers nor code
-        resolve_tile_exact< S, A, FMT >( s_keys, s_col, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, subdivide, out, a.flip_output != 0, who.tid() );
+        resolve_tile_exact< S, A, FMT >( s_keys, s_col, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, subdivide, out, a.flip_output != 0 );
         return;
     }
     if constexpr( C::PACK )
     {
         // Window form: every candidate's coverage of my S x S output pixels is one masked 16-bit field of its
         // mask, so the priority resolve runs once on whole-cell bit sets instead of once per output row.
-        for( int idx = who.tid(); idx < C::TW * C::TH; idx += kThreads )
+        for( int idx = tid; idx < C::TW * C::TH; idx += kThreads )
         {
             int ly = idx / C::TW, lx = idx - ly * C::TW;
             int gx = x0 + lx, gy = y0 + ly;
@@ -1237,7 +1209,7 @@ __device__ __forceinline__ void raster_tile( const CUtensorMap* graph_map, const
     }
     else
     {
-        for( int idx = who.tid(); idx < C::TW * C::TH; idx += kThreads )
+        for( int idx = tid; idx < C::TW * C::TH; idx += kThreads )
         {
             int ly = idx / C::TW, lx = idx - ly * C::TW;
             int gx = x0 + lx, gy = y0 + ly;
@@ -1297,39 +1269,14 @@ __device__ __forceinline__ void raster_tile( const CUtensorMap* graph_map, const
     }
 }
 
-// one CTA per tile
-template< int S, int A, bool kUseTma, int FMT >
-__global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( const __grid_constant__ CUtensorMap graph_map, const __grid_constant__ CUtensorMap img_map,
-                                                           RasterArgs a )
-{
-    typedef Cfg< S > C;
-    extern __shared__ __align__( 128 ) uint8_t smem[];
-    const CtaTile who;
-    if( kUseTma )
-    {
-        if( threadIdx.x == 0 )
-        {
-            mbar_init( reinterpret_cast< uint64_t* >( smem + C::off_bar ), 1 );
-            fence_barrier_init();
-        }
-        __syncthreads();
-    }
-    const GlobalTables tabs{ a.smooth };
-    raster_tile< S, A, kUseTma, FMT >( &graph_map, &img_map, a, tabs, smem, who );
-}
-
 template< int S, int A, int FMT >
 cudaError_t launch_raster_sa( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream )
 {
     typedef Cfg< S > C;
     cudaError_t e;
-    CUtensorMap dummy;
-    memset( &dummy, 0, sizeof( dummy ) );
-    const bool tma = graph_map && img_map;
-    const int tiles_x = ( a.width + C::TW - 1 ) / C::TW, tiles_y = ( a.height + C::TH - 1 ) / C::TH;
     // (grid.z is limited to 65535: the callers in context.cu split larger batches)
-    dim3 grid( tiles_x, tiles_y, a.n_frames );
-    if( tma )
+    dim3 grid( ( a.width + C::TW - 1 ) / C::TW, ( a.height + C::TH - 1 ) / C::TH, a.n_frames );
+    if( graph_map && img_map )
     {
         e = cudaFuncSetAttribute( raster_kernel< S, A, true, FMT >, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes );
         if( e != cudaSuccess ) return e;
@@ -1337,6 +1284,8 @@ cudaError_t launch_raster_sa( const RasterArgs& a, const CUtensorMap* graph_map,
     }
     else
     {
+        CUtensorMap dummy;
+        memset( &dummy, 0, sizeof( dummy ) );
         e = cudaFuncSetAttribute( raster_kernel< S, A, false, FMT >, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes );
         if( e != cudaSuccess ) return e;
         raster_kernel< S, A, false, FMT ><<< grid, kThreads, C::smem_bytes, stream >>>( dummy, dummy, a );

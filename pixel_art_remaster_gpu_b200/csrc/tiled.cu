@@ -22,6 +22,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <string>
@@ -182,102 +185,228 @@ struct GroupDeviceGuard
 
 int bytes_per_pixel_of( int out_format ) { return out_format == PAR_OUT_RGBA8 ? 4 : ( out_format == PAR_OUT_BGR8 ? 3 : 1 ); }
 
-// Steps (2) and (3) of the tiled path, everything stream-ordered and asynchronous: apron rows from the neighbouring
-// devices (ordered after their `ready` event), the ordinary path on every extended strip, and — with labels — the
-// per-strip labelling, the gather of all seam rows onto every device, the stitch and the relabelling of the own rows.
-int exchange_and_compute( par_group* g, unsigned flags, int out_format, bool want_image, bool want_labels )
+// One call of the tiled path: what every strip does, in three phases separated by "all strips have enqueued the phase"
+// barriers (a cudaStreamWaitEvent must find the event recorded by THIS call).  The strips are driven by one host thread
+// each (a call is ~30 enqueues per strip, serially 1 ms on eight devices against 0.1 ms of kernels per strip); everything
+// enqueued is stream-ordered and asynchronous.
+struct TiledCall
 {
+    par_group* g;
+    unsigned flags;
+    int out_format;
+    bool want_image, want_labels, timed;
+    const par_job* host; // host entry: the caller's job (image in, outputs out); nullptr for the device-resident entry
+};
+
+// phase A: the strip's own rows are on the device (host entry: uploaded here) -> `ready`
+int strip_phase_a( const TiledCall& c, Strip& s, std::string& err )
+{
+    cudaSetDevice( s.device );
+    if( c.timed ) cudaEventRecord( s.t_begin, s.stream );
+    if( c.host )
+    {
+        const size_t row_in = ( size_t )3 * c.g->width;
+        uint8_t* dst = s.d_in + ( size_t )( s.own_b - s.load_b ) * row_in;
+        cudaError_t e = cudaMemcpy2DAsync( dst, row_in, c.host->bgr + ( size_t )s.own_b * c.host->widthstep, c.host->widthstep, row_in, s.own_e - s.own_b,
+                                           cudaMemcpyHostToDevice, s.stream );
+        if( e != cudaSuccess )
+        {
+            err = std::string( "H2D: " ) + cudaGetErrorString( e );
+            return PAR_ERR_CUDA;
+        }
+    }
+    cudaEventRecord( s.ready, s.stream );
+    return PAR_OK;
+}
+
+// phase B: apron rows from the neighbouring devices (peer copies over NVLink, ordered after their `ready`), the ordinary
+// path on the extended strip -> `computed`, and with labels the strip's own labelling -> `labelled`
+int strip_phase_b( const TiledCall& c, size_t k, std::string& err )
+{
+    par_group* g = c.g;
+    Strip& s = g->strips[ k ];
     const int W = g->width;
     const size_t row_in = ( size_t )3 * W; // strips are stored densely on the devices
+    cudaSetDevice( s.device );
     cudaError_t e = cudaSuccess;
-    // (2) apron rows come from the neighbouring devices (peer copies over NVLink)
-    for( size_t k = 0; k < g->strips.size(); k++ )
+    if( k > 0 && s.load_b < s.own_b )
     {
-        Strip& s = g->strips[ k ];
-        cudaSetDevice( s.device );
-        if( k > 0 && s.load_b < s.own_b )
-        {
-            Strip& n = g->strips[ k - 1 ];
-            cudaStreamWaitEvent( s.stream, n.ready, 0 );
-            const size_t bytes = ( size_t )( s.own_b - s.load_b ) * row_in;
-            e = cudaMemcpyPeerAsync( s.d_in, s.device, n.d_in + ( size_t )( s.load_b - n.load_b ) * row_in, n.device, bytes, s.stream );
-            if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "peer copy: %s", cudaGetErrorString( e ) );
-        }
-        if( k + 1 < g->strips.size() && s.load_e > s.own_e )
-        {
-            Strip& n = g->strips[ k + 1 ];
-            cudaStreamWaitEvent( s.stream, n.ready, 0 );
-            const size_t bytes = ( size_t )( s.load_e - s.own_e ) * row_in;
-            e = cudaMemcpyPeerAsync( s.d_in + ( size_t )( s.own_e - s.load_b ) * row_in, s.device,
-                                     n.d_in + ( size_t )( s.own_e - n.load_b ) * row_in, n.device, bytes, s.stream );
-            if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "peer copy: %s", cudaGetErrorString( e ) );
-        }
+        Strip& n = g->strips[ k - 1 ];
+        cudaStreamWaitEvent( s.stream, n.ready, 0 );
+        e = cudaMemcpyPeerAsync( s.d_in, s.device, n.d_in + ( size_t )( s.load_b - n.load_b ) * row_in, n.device, ( size_t )( s.own_b - s.load_b ) * row_in, s.stream );
     }
-    // (3) the ordinary path on every extended strip
-    for( auto& s : g->strips )
+    if( e == cudaSuccess && k + 1 < g->strips.size() && s.load_e > s.own_e )
     {
-        cudaSetDevice( s.device );
-        par_job d = {};
-        d.bgr = s.d_in;
-        d.width = W;
-        d.height = s.load_e - s.load_b;
-        d.widthstep = 3 * W;
-        d.n_frames = 1;
-        d.scale = g->scale;
-        d.flags = flags;
-        d.out_format = out_format;
-        d.rgba = want_image ? s.d_rgba : nullptr;
-        d.graph = s.d_graph;
-        d.graph_aux = s.d_aux;
-        int st = par_remaster_device( s.ctx, &d );
-        if( st != PAR_OK ) return g->fail( st, "strip on device %d: %s", s.device, par_last_error( s.ctx ) );
-        cudaEventRecord( s.computed, s.stream );
-        if( want_labels )
-        {
-            // Label only rows whose graph bytes are exact: the strip's own rows plus ONE row either side (needed
-            // for the stitch).  The outer apron rows carry graph bytes computed without their full context and
-            // must not be allowed to connect anything.  The window is labelled as an image of its own (links
-            // leaving it are ignored) and then shifted to global pixel indices.
-            const int win_b = std::max( s.load_b, s.own_b - 1 ), win_e = std::min( s.load_e, s.own_e + 1 );
-            par_job l = d;
-            l.rgba = nullptr;
-            l.height = win_e - win_b;
-            l.graph = s.d_graph + ( size_t )( win_b - s.load_b ) * W;
-            l.labels = s.d_labels + ( size_t )( win_b - s.load_b ) * W;
-            st = par_stage_cc_labels( s.ctx, &l );
-            if( st != PAR_OK ) return g->fail( st, "labels on device %d: %s", s.device, par_last_error( s.ctx ) );
-            const size_t n = ( size_t )W * l.height;
-            offset_labels_kernel<<< ( unsigned )( ( n + 255 ) / 256 ), 256, 0, s.stream >>>( l.labels, n, win_b * W );
-            cudaEventRecord( s.labelled, s.stream );
-        }
+        Strip& n = g->strips[ k + 1 ];
+        cudaStreamWaitEvent( s.stream, n.ready, 0 );
+        e = cudaMemcpyPeerAsync( s.d_in + ( size_t )( s.own_e - s.load_b ) * row_in, s.device, n.d_in + ( size_t )( s.own_e - n.load_b ) * row_in, n.device,
+                                 ( size_t )( s.load_e - s.own_e ) * row_in, s.stream );
     }
-    // (4) stitch: every device gathers the two label rows of every seam (peer copies, ordered after the strips'
-    // `labelled` events), closes the equivalences in one CTA and relabels its own rows
+    if( e != cudaSuccess )
+    {
+        err = std::string( "peer copy: " ) + cudaGetErrorString( e );
+        return PAR_ERR_CUDA;
+    }
+    par_job d = {};
+    d.bgr = s.d_in;
+    d.width = W;
+    d.height = s.load_e - s.load_b;
+    d.widthstep = 3 * W;
+    d.n_frames = 1;
+    d.scale = g->scale;
+    d.flags = c.flags;
+    d.out_format = c.out_format;
+    d.rgba = c.want_image ? s.d_rgba : nullptr;
+    d.graph = s.d_graph;
+    d.graph_aux = s.d_aux;
+    int st = par_remaster_device( s.ctx, &d );
+    if( st != PAR_OK )
+    {
+        err = std::string( "strip: " ) + par_last_error( s.ctx );
+        return st;
+    }
+    cudaEventRecord( s.computed, s.stream );
+    if( c.want_labels )
+    {
+        // Label only rows whose graph bytes are exact: the strip's own rows plus ONE row either side (needed
+        // for the stitch).  The outer apron rows carry graph bytes computed without their full context and
+        // must not be allowed to connect anything.  The window is labelled as an image of its own (links
+        // leaving it are ignored) and then shifted to global pixel indices.
+        const int win_b = std::max( s.load_b, s.own_b - 1 ), win_e = std::min( s.load_e, s.own_e + 1 );
+        par_job l = d;
+        l.rgba = nullptr;
+        l.height = win_e - win_b;
+        l.graph = s.d_graph + ( size_t )( win_b - s.load_b ) * W;
+        l.labels = s.d_labels + ( size_t )( win_b - s.load_b ) * W;
+        st = par_stage_cc_labels( s.ctx, &l );
+        if( st != PAR_OK )
+        {
+            err = std::string( "labels: " ) + par_last_error( s.ctx );
+            return st;
+        }
+        const size_t n = ( size_t )W * l.height;
+        offset_labels_kernel<<< ( unsigned )( ( n + 255 ) / 256 ), 256, 0, s.stream >>>( l.labels, n, win_b * W );
+        cudaEventRecord( s.labelled, s.stream );
+    }
+    return PAR_OK;
+}
+
+// phase C: the stitch — the two label rows of every seam gathered from all strips (peer copies, ordered after their
+// `labelled`), the equivalences closed in one CTA, the strip's own rows relabelled — and, for the host entry, the results on
+// their way back: image and graphs on a second stream as soon as the strip has them, the labels once they are final
+int strip_phase_c( const TiledCall& c, size_t k, std::string& err )
+{
+    par_group* g = c.g;
+    Strip& s = g->strips[ k ];
+    const int W = g->width, S = g->scale;
     const size_t n_seams = g->strips.size() - 1;
-    if( want_labels && n_seams > 0 )
-        for( auto& s : g->strips )
+    cudaSetDevice( s.device );
+    cudaError_t e = cudaSuccess;
+    if( c.want_labels && n_seams > 0 )
+    {
+        for( auto& o : g->strips )
+            if( &o != &s ) cudaStreamWaitEvent( s.stream, o.labelled, 0 );
+        for( size_t m = 0; m < n_seams && e == cudaSuccess; m++ )
         {
-            cudaSetDevice( s.device );
-            for( auto& o : g->strips )
-                if( &o != &s ) cudaStreamWaitEvent( s.stream, o.labelled, 0 );
-            for( size_t k = 0; k < n_seams && e == cudaSuccess; k++ )
-            {
-                Strip &a = g->strips[ k ], &b = g->strips[ k + 1 ];
-                const int row = a.own_e - 1;
-                e = cudaMemcpyPeerAsync( s.d_seams + ( 2 * k ) * W, s.device, a.d_labels + ( size_t )( row - a.load_b ) * W, a.device, ( size_t )W * 4, s.stream );
-                if( e == cudaSuccess )
-                    e = cudaMemcpyPeerAsync( s.d_seams + ( 2 * k + 1 ) * W, s.device, b.d_labels + ( size_t )( row - b.load_b ) * W, b.device, ( size_t )W * 4,
-                                             s.stream );
-            }
-            if( e == cudaSuccess ) e = cudaMemsetAsync( s.d_tab_keys, 0xFF, ( ( size_t )g->tab_mask + 1 ) * 4, s.stream );
-            if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "seam rows: %s", cudaGetErrorString( e ) );
+            Strip &a = g->strips[ m ], &b = g->strips[ m + 1 ];
+            const int row = a.own_e - 1;
+            e = cudaMemcpyPeerAsync( s.d_seams + ( 2 * m ) * W, s.device, a.d_labels + ( size_t )( row - a.load_b ) * W, a.device, ( size_t )W * 4, s.stream );
+            if( e == cudaSuccess )
+                e = cudaMemcpyPeerAsync( s.d_seams + ( 2 * m + 1 ) * W, s.device, b.d_labels + ( size_t )( row - b.load_b ) * W, b.device, ( size_t )W * 4, s.stream );
+        }
+        if( e == cudaSuccess ) e = cudaMemsetAsync( s.d_tab_keys, 0xFF, ( ( size_t )g->tab_mask + 1 ) * 4, s.stream );
+        if( e == cudaSuccess )
+        {
             stitch_labels_kernel<<< 1, 1024, 0, s.stream >>>( s.d_seams, ( int )n_seams, W, s.d_tab_keys, s.d_tab_parent, g->tab_mask );
             const size_t n = ( size_t )W * ( s.own_e - s.own_b );
-            relabel_kernel<<< ( unsigned )( ( n + 255 ) / 256 ), 256, 0, s.stream >>>( s.d_labels + ( size_t )( s.own_b - s.load_b ) * W, n, s.d_tab_keys,
-                                                                                       s.d_tab_parent, g->tab_mask );
+            relabel_kernel<<< ( unsigned )( ( n + 255 ) / 256 ), 256, 0, s.stream >>>( s.d_labels + ( size_t )( s.own_b - s.load_b ) * W, n, s.d_tab_keys, s.d_tab_parent,
+                                                                                       g->tab_mask );
             e = cudaGetLastError();
-            if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "stitch: %s", cudaGetErrorString( e ) );
         }
+        if( e != cudaSuccess )
+        {
+            err = std::string( "stitch: " ) + cudaGetErrorString( e );
+            return PAR_ERR_CUDA;
+        }
+    }
+    if( c.timed ) cudaEventRecord( s.t_end, s.stream );
+    if( c.host )
+    {
+        const par_job* j = c.host;
+        const size_t out_row = ( size_t )W * S * bytes_per_pixel_of( j->out_format );
+        const size_t own_px = ( size_t )W * ( s.own_e - s.own_b ), off_px = ( size_t )W * ( s.own_b - s.load_b );
+        cudaStream_t cs = s.copy_stream;
+        cudaStreamWaitEvent( cs, s.computed, 0 );
+        if( j->rgba )
+        {
+            const bool flip = ( j->flags & PAR_FLAG_FLIP_OUTPUT ) != 0;
+            const size_t src_row = flip ? ( size_t )( s.load_e - s.own_e ) * S : ( size_t )( s.own_b - s.load_b ) * S;
+            const size_t dst_row = flip ? ( size_t )( g->height - s.own_e ) * S : ( size_t )s.own_b * S;
+            e = cudaMemcpyAsync( j->rgba + dst_row * out_row, s.d_rgba + src_row * out_row, ( size_t )( s.own_e - s.own_b ) * S * out_row, cudaMemcpyDeviceToHost, cs );
+        }
+        if( e == cudaSuccess && j->graph ) e = cudaMemcpyAsync( j->graph + ( size_t )W * s.own_b, s.d_graph + off_px, own_px, cudaMemcpyDeviceToHost, cs );
+        if( e == cudaSuccess && j->graph_aux ) e = cudaMemcpyAsync( j->graph_aux + ( size_t )W * s.own_b, s.d_aux + off_px, own_px, cudaMemcpyDeviceToHost, cs );
+        if( e == cudaSuccess && j->labels )
+            e = cudaMemcpyAsync( j->labels + ( size_t )W * s.own_b, s.d_labels + off_px, own_px * 4, cudaMemcpyDeviceToHost, s.stream );
+        if( e != cudaSuccess )
+        {
+            err = std::string( "D2H: " ) + cudaGetErrorString( e );
+            return PAR_ERR_CUDA;
+        }
+    }
+    return PAR_OK;
+}
+
+// a reusable barrier for the strips' host threads
+struct PhaseBarrier
+{
+    std::mutex m;
+    std::condition_variable cv;
+    int waiting = 0, generation = 0;
+    const int n;
+    explicit PhaseBarrier( int n_ ) : n( n_ ) {}
+    void arrive_and_wait()
+    {
+        std::unique_lock< std::mutex > lock( m );
+        const int gen = generation;
+        if( ++waiting == n )
+        {
+            waiting = 0;
+            generation++;
+            cv.notify_all();
+        }
+        else
+            cv.wait( lock, [ & ] { return generation != gen; } );
+    }
+};
+
+// enqueue one call on all strips; returns the first failure (its message in g->error)
+int run_tiled_call( const TiledCall& c )
+{
+    par_group* g = c.g;
+    const size_t n = g->strips.size();
+    std::vector< int > status( n, PAR_OK );
+    std::vector< std::string > errors( n );
+    PhaseBarrier barrier( ( int )n );
+    auto work = [ & ]( size_t k ) {
+        // (a strip that failed still goes through the barriers, so that the others are not left waiting)
+        status[ k ] = strip_phase_a( c, g->strips[ k ], errors[ k ] );
+        barrier.arrive_and_wait();
+        if( status[ k ] == PAR_OK ) status[ k ] = strip_phase_b( c, k, errors[ k ] );
+        barrier.arrive_and_wait();
+        if( status[ k ] == PAR_OK ) status[ k ] = strip_phase_c( c, k, errors[ k ] );
+    };
+    if( n == 1 )
+        work( 0 );
+    else
+    {
+        std::vector< std::thread > threads;
+        for( size_t k = 1; k < n; k++ ) threads.emplace_back( work, k );
+        work( 0 );
+        for( auto& t : threads ) t.join();
+    }
+    for( size_t k = 0; k < n; k++ )
+        if( status[ k ] != PAR_OK ) return g->fail( status[ k ], "strip %d on device %d: %s", ( int )k, g->strips[ k ].device, errors[ k ].c_str() );
     return PAR_OK;
 }
 
@@ -439,19 +568,9 @@ int par_group_remaster_device( par_group* g, unsigned flags, int out_format, int
     if( st ) return st;
     GroupDeviceGuard guard;
     const auto t0 = std::chrono::steady_clock::now();
-    for( auto& s : g->strips ) // the caller has put every strip's own rows into its input buffer
-    {
-        cudaSetDevice( s.device );
-        cudaEventRecord( s.t_begin, s.stream );
-        cudaEventRecord( s.ready, s.stream );
-    }
-    st = exchange_and_compute( g, flags, out_format, want_image != 0, want_labels != 0 );
+    const TiledCall call{ g, flags, out_format, want_image != 0, want_labels != 0, true, nullptr }; // (the caller has put every strip's own rows in place)
+    st = run_tiled_call( call );
     if( st ) return st;
-    for( auto& s : g->strips )
-    {
-        cudaSetDevice( s.device );
-        cudaEventRecord( s.t_end, s.stream );
-    }
     g->last_device_ms = 0.0;
     for( auto& s : g->strips )
     {
@@ -485,47 +604,11 @@ int par_group_remaster_host( par_group* g, const par_job* j )
     int st = check_group_job( g, j->flags, j->out_format );
     if( st ) return st;
     GroupDeviceGuard guard;
-    const int W = g->width, S = g->scale;
-    const size_t row_in = ( size_t )3 * W;
-    cudaError_t e = cudaSuccess;
-
-    // (1) every device receives its OWN rows from the host
-    for( auto& s : g->strips )
-    {
-        cudaSetDevice( s.device );
-        uint8_t* dst = s.d_in + ( size_t )( s.own_b - s.load_b ) * row_in;
-        e = cudaMemcpy2DAsync( dst, row_in, j->bgr + ( size_t )s.own_b * j->widthstep, j->widthstep, row_in, s.own_e - s.own_b,
-                               cudaMemcpyHostToDevice, s.stream );
-        if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "H2D: %s", cudaGetErrorString( e ) );
-        cudaEventRecord( s.ready, s.stream );
-    }
-    // (2)-(4) halo exchange, kernels, label stitch: all on the devices
-    st = exchange_and_compute( g, j->flags, j->out_format, j->rgba != nullptr, j->labels != nullptr );
+    // own rows up, halo exchange, kernels, label stitch, results down: all enqueued by the strips' threads
+    const TiledCall call{ g, j->flags, j->out_format, j->rgba != nullptr, j->labels != nullptr, false, j };
+    st = run_tiled_call( call );
     if( st ) return st;
-    // (5) own rows of the image and the graphs go back to the host as soon as the strip has them (second stream: the big
-    // copies overlap the label stitching); the labels follow on the strip's stream once they are final
-    const size_t out_row = ( size_t )W * S * bytes_per_pixel_of( j->out_format );
-    for( auto& s : g->strips )
-    {
-        cudaSetDevice( s.device );
-        const size_t own_px = ( size_t )W * ( s.own_e - s.own_b ), off_px = ( size_t )W * ( s.own_b - s.load_b );
-        cudaStream_t cs = s.copy_stream;
-        cudaStreamWaitEvent( cs, s.computed, 0 );
-        if( j->rgba )
-        {
-            const bool flip = ( j->flags & PAR_FLAG_FLIP_OUTPUT ) != 0;
-            const size_t src_row = flip ? ( size_t )( s.load_e - s.own_e ) * S : ( size_t )( s.own_b - s.load_b ) * S;
-            const size_t dst_row = flip ? ( size_t )( g->height - s.own_e ) * S : ( size_t )s.own_b * S;
-            e = cudaMemcpyAsync( j->rgba + dst_row * out_row, s.d_rgba + src_row * out_row, ( size_t )( s.own_e - s.own_b ) * S * out_row,
-                                 cudaMemcpyDeviceToHost, cs );
-        }
-        if( e == cudaSuccess && j->graph ) e = cudaMemcpyAsync( j->graph + ( size_t )W * s.own_b, s.d_graph + off_px, own_px, cudaMemcpyDeviceToHost, cs );
-        if( e == cudaSuccess && j->graph_aux )
-            e = cudaMemcpyAsync( j->graph_aux + ( size_t )W * s.own_b, s.d_aux + off_px, own_px, cudaMemcpyDeviceToHost, cs );
-        if( e == cudaSuccess && j->labels )
-            e = cudaMemcpyAsync( j->labels + ( size_t )W * s.own_b, s.d_labels + off_px, own_px * 4, cudaMemcpyDeviceToHost, s.stream );
-        if( e != cudaSuccess ) return g->fail( PAR_ERR_CUDA, "D2H: %s", cudaGetErrorString( e ) );
-    }
+    cudaError_t e = cudaSuccess;
     for( auto& s : g->strips )
     {
         cudaSetDevice( s.device );
