@@ -29,6 +29,11 @@
 // the masks are kept in a "window form" whose fields are already positioned on the reader's pixels) and writes whole
 // output-row segments with 128-bit streaming stores; with anti-aliasing on, A x A samples are averaged right there.
 // Algorithmic HBM traffic: 3 B/px colour + 1 B/px graph in, 4*s*s B/px out.
+//
+// The kernel itself lives in raster_impl.cuh and is instantiated once per output format (par_out_format), one translation
+// unit each so that they compile in parallel: this file (RGBA8, and the builders of the per-scale tables), raster_bgr8.cu
+// (3 bytes per pixel, the image Image::saveImage takes) and raster_index8.cu (palette indices; palette_kernels.cu).  Only
+// the stores of the resolve step differ.
 #include "raster_impl.cuh"
 
 namespace par {
