@@ -46,6 +46,7 @@ struct Strip
     int32_t* d_labels = nullptr;
     int32_t* d_seams = nullptr;                    // [n_seams][2][W]: the label rows of every seam, gathered from all strips
     int32_t *d_tab_keys = nullptr, *d_tab_parent = nullptr; // the seam labels' union-find (open-addressing table)
+    int32_t** d_seam_dst = nullptr;                // the d_seams of every strip (peer pointers), for push_seam_rows_kernel
     cudaEvent_t ready = nullptr, computed = nullptr, labelled = nullptr, t_begin = nullptr, t_end = nullptr;
 };
 
@@ -59,8 +60,8 @@ __global__ void offset_labels_kernel( int32_t* lab, size_t n, int32_t offset )
 // On the last own row of strip k both k and k+1 labelled the same pixels: every column gives an equivalence between two
 // labels.  The distinct seam labels are the nodes of a union-find held in an open-addressing table (key = label,
 // parent = a label of the same class, roots point at themselves); link-by-minimum makes the root the class minimum,
-// which is the canonical label.  One CTA closes the equivalences of ALL seams (<= 7 x 4096 pairs), every device does so
-// redundantly on its own copy of the seam rows, then relabels its own rows through the table.
+// which is the canonical label.  Three small launches close the equivalences of ALL seams (<= 7 x 4096 pairs), every device
+// does so redundantly on its own copy of the seam rows, then relabels its own rows through the table.
 constexpr int32_t kNoKey = -1;
 __device__ __forceinline__ uint32_t tab_hash( int32_t label, uint32_t mask ) { return ( ( uint32_t )label * 0x9E3779B1u ) >> 7 & mask; }
 
@@ -86,49 +87,64 @@ __device__ __forceinline__ int32_t tab_root( const int32_t* keys, const int32_t*
     }
 }
 
-__global__ void __launch_bounds__( 1024 ) stitch_labels_kernel( const int32_t* __restrict__ seams, int n_seams, int width, int32_t* keys, int32_t* parent,
-                                                                uint32_t mask )
+// (1) the distinct labels become nodes, each its own root
+__global__ void stitch_insert_kernel( const int32_t* __restrict__ seams, int n_labels, int32_t* keys, int32_t* parent, uint32_t mask )
 {
-    const int n_labels = 2 * n_seams * width;
-    // (1) the distinct labels become nodes, each its own root
-    for( int i = threadIdx.x; i < n_labels; i += blockDim.x )
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if( i >= n_labels ) return;
+    const int32_t label = seams[ i ];
+    uint32_t h = tab_hash( label, mask );
+    for( ;; )
     {
-        const int32_t label = seams[ i ];
-        uint32_t h = tab_hash( label, mask );
-        for( ;; )
-        {
-            const int32_t k = atomicCAS( &keys[ h ], kNoKey, label );
-            if( k == kNoKey ) parent[ h ] = label;
-            if( k == kNoKey || k == label ) break;
-            h = ( h + 1u ) & mask;
-        }
+        const int32_t k = atomicCAS( &keys[ h ], kNoKey, label );
+        if( k == kNoKey ) parent[ h ] = label;
+        if( k == kNoKey || k == label ) break;
+        h = ( h + 1u ) & mask;
     }
-    __syncthreads();
-    // (2) one union per column of every seam: the larger root goes under the smaller one (lock-free, roots only decrease)
-    for( int i = threadIdx.x; i < n_seams * width; i += blockDim.x )
+}
+
+// (2) one union per column of every seam: the larger root goes under the smaller one (lock-free, roots only decrease)
+__global__ void stitch_unite_kernel( const int32_t* __restrict__ seams, int n_seams, int width, const int32_t* keys, int32_t* parent, uint32_t mask )
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if( i >= n_seams * width ) return;
+    const int k = i / width, x = i - k * width;
+    int32_t a = seams[ ( 2 * k ) * width + x ], b = seams[ ( 2 * k + 1 ) * width + x ];
+    for( ;; )
     {
-        const int k = i / width, x = i - k * width;
-        int32_t a = seams[ ( 2 * k ) * width + x ], b = seams[ ( 2 * k + 1 ) * width + x ];
-        for( ;; )
+        a = tab_root( keys, parent, mask, a );
+        b = tab_root( keys, parent, mask, b );
+        if( a == b ) break;
+        if( a < b )
         {
-            a = tab_root( keys, parent, mask, a );
-            b = tab_root( keys, parent, mask, b );
-            if( a == b ) break;
-            if( a < b )
-            {
-                const int32_t t = a;
-                a = b;
-                b = t;
-            }
-            const int32_t old = atomicMin( &parent[ tab_find_slot( keys, mask, a ) ], b );
-            if( old == a ) break;
-            a = old;
+            const int32_t t = a;
+            a = b;
+            b = t;
         }
+        const int32_t old = atomicMin( &parent[ tab_find_slot( keys, mask, a ) ], b );
+        if( old == a ) break;
+        a = old;
     }
-    __syncthreads();
-    // (3) flatten: every node points at its class minimum
-    for( uint32_t h = threadIdx.x; h <= mask; h += blockDim.x )
-        if( keys[ h ] != kNoKey ) parent[ h ] = tab_root( keys, parent, mask, keys[ h ] );
+}
+
+// (3) flatten: every node points at its class minimum
+__global__ void stitch_flatten_kernel( const int32_t* keys, int32_t* parent, uint32_t mask )
+{
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if( h <= mask && keys[ h ] != kNoKey ) parent[ h ] = tab_root( keys, parent, mask, keys[ h ] );
+}
+
+// A strip's two seam rows — its last own row (row A of the seam above it... of seam k) and the row below its first own row
+// (row B of seam k-1) — written straight into the seam buffers of ALL strips: peer stores over NVLink (the buffers of the
+// other devices are mapped by peer access), one launch instead of two copies per seam and device.
+__global__ void push_seam_rows_kernel( const int32_t* __restrict__ row_a, int slot_a, const int32_t* __restrict__ row_b, int slot_b, int width,
+                                       int32_t* const* __restrict__ dst )
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if( x >= width ) return;
+    int32_t* out = dst[ blockIdx.y ];
+    if( row_a ) out[ ( size_t )slot_a * width + x ] = row_a[ x ];
+    if( row_b ) out[ ( size_t )slot_b * width + x ] = row_b[ x ];
 }
 
 // labels that are nodes of the seam union-find are replaced by their class minimum (most labels are not: one probe)
@@ -154,11 +170,17 @@ __global__ void relabel_kernel( int32_t* lab, size_t n, const int32_t* __restric
 
 } // namespace
 
+namespace {
+struct StripWorkers;
+}
+
 struct par_group
 {
     int width = 0, height = 0, scale = 0;
     std::vector< Strip > strips;
+    StripWorkers* workers = nullptr; // one host thread per strip beyond the first (the caller's thread drives strip 0)
     uint32_t tab_mask = 0; // slots - 1 of the seam tables
+    bool peer_stores = false; // every strip can store into every other strip's seam buffer (same device, or peer access enabled)
     double last_wall_ms = 0.0, last_device_ms = 0.0;
     std::string error;
     int fail( int st, const char* fmt, ... )
@@ -229,7 +251,8 @@ int strip_phase_b( const TiledCall& c, size_t k, std::string& err )
     const size_t row_in = ( size_t )3 * W; // strips are stored densely on the devices
     cudaSetDevice( s.device );
     cudaError_t e = cudaSuccess;
-    if( k > 0 && s.load_b < s.own_b )
+    if( c.want_labels && g->strips.size() > 1 ) e = cudaMemsetAsync( s.d_tab_keys, 0xFF, ( ( size_t )g->tab_mask + 1 ) * 4, s.stream ); // (off the critical path)
+    if( e == cudaSuccess && k > 0 && s.load_b < s.own_b )
     {
         Strip& n = g->strips[ k - 1 ];
         cudaStreamWaitEvent( s.stream, n.ready, 0 );
@@ -286,6 +309,15 @@ int strip_phase_b( const TiledCall& c, size_t k, std::string& err )
         }
         const size_t n = ( size_t )W * l.height;
         offset_labels_kernel<<< ( unsigned )( ( n + 255 ) / 256 ), 256, 0, s.stream >>>( l.labels, n, win_b * W );
+        const size_t n_strips = g->strips.size();
+        if( g->peer_stores && n_strips > 1 )
+        {
+            // this strip's rows of the seams above and below it, stored into every strip's seam buffer
+            const int32_t* row_a = k + 1 < n_strips ? s.d_labels + ( size_t )( s.own_e - 1 - s.load_b ) * W : nullptr;
+            const int32_t* row_b = k > 0 ? s.d_labels + ( size_t )( s.own_b - 1 - s.load_b ) * W : nullptr;
+            push_seam_rows_kernel<<< dim3( ( unsigned )( ( W + 255 ) / 256 ), ( unsigned )n_strips ), 256, 0, s.stream >>>(
+                row_a, ( int )( 2 * k ), row_b, ( int )( 2 * ( k - 1 ) + 1 ), W, s.d_seam_dst );
+        }
         cudaEventRecord( s.labelled, s.stream );
     }
     return PAR_OK;
@@ -306,18 +338,21 @@ int strip_phase_c( const TiledCall& c, size_t k, std::string& err )
     {
         for( auto& o : g->strips )
             if( &o != &s ) cudaStreamWaitEvent( s.stream, o.labelled, 0 );
-        for( size_t m = 0; m < n_seams && e == cudaSuccess; m++ )
-        {
-            Strip &a = g->strips[ m ], &b = g->strips[ m + 1 ];
-            const int row = a.own_e - 1;
-            e = cudaMemcpyPeerAsync( s.d_seams + ( 2 * m ) * W, s.device, a.d_labels + ( size_t )( row - a.load_b ) * W, a.device, ( size_t )W * 4, s.stream );
-            if( e == cudaSuccess )
-                e = cudaMemcpyPeerAsync( s.d_seams + ( 2 * m + 1 ) * W, s.device, b.d_labels + ( size_t )( row - b.load_b ) * W, b.device, ( size_t )W * 4, s.stream );
-        }
-        if( e == cudaSuccess ) e = cudaMemsetAsync( s.d_tab_keys, 0xFF, ( ( size_t )g->tab_mask + 1 ) * 4, s.stream );
+        if( !g->peer_stores ) // (no peer mapping between some pair of devices: fetch the rows with peer copies instead)
+            for( size_t m = 0; m < n_seams && e == cudaSuccess; m++ )
+            {
+                Strip &a = g->strips[ m ], &b = g->strips[ m + 1 ];
+                const int row = a.own_e - 1;
+                e = cudaMemcpyPeerAsync( s.d_seams + ( 2 * m ) * W, s.device, a.d_labels + ( size_t )( row - a.load_b ) * W, a.device, ( size_t )W * 4, s.stream );
+                if( e == cudaSuccess )
+                    e = cudaMemcpyPeerAsync( s.d_seams + ( 2 * m + 1 ) * W, s.device, b.d_labels + ( size_t )( row - b.load_b ) * W, b.device, ( size_t )W * 4, s.stream );
+            }
         if( e == cudaSuccess )
         {
-            stitch_labels_kernel<<< 1, 1024, 0, s.stream >>>( s.d_seams, ( int )n_seams, W, s.d_tab_keys, s.d_tab_parent, g->tab_mask );
+            const int n_labels = ( int )( 2 * n_seams ) * W, n_pairs = ( int )n_seams * W;
+            stitch_insert_kernel<<< ( n_labels + 255 ) / 256, 256, 0, s.stream >>>( s.d_seams, n_labels, s.d_tab_keys, s.d_tab_parent, g->tab_mask );
+            stitch_unite_kernel<<< ( n_pairs + 255 ) / 256, 256, 0, s.stream >>>( s.d_seams, ( int )n_seams, W, s.d_tab_keys, s.d_tab_parent, g->tab_mask );
+            stitch_flatten_kernel<<< ( g->tab_mask + 256 ) / 256, 256, 0, s.stream >>>( s.d_tab_keys, s.d_tab_parent, g->tab_mask );
             const size_t n = ( size_t )W * ( s.own_e - s.own_b );
             relabel_kernel<<< ( unsigned )( ( n + 255 ) / 256 ), 256, 0, s.stream >>>( s.d_labels + ( size_t )( s.own_b - s.load_b ) * W, n, s.d_tab_keys, s.d_tab_parent,
                                                                                        g->tab_mask );
@@ -380,6 +415,63 @@ struct PhaseBarrier
     }
 };
 
+// The strips' host threads: created with the group, parked on a condition variable between calls (spawning seven threads
+// per call would cost more than the call's kernels).
+struct StripWorkers
+{
+    std::vector< std::thread > threads;
+    std::mutex m;
+    std::condition_variable wake, finished;
+    const TiledCall* call = nullptr;
+    std::vector< int >* status = nullptr;
+    std::vector< std::string >* errors = nullptr;
+    PhaseBarrier* barrier = nullptr;
+    long generation = 0;
+    int running = 0;
+    bool stop = false;
+
+    static void work( const TiledCall& c, size_t k, std::vector< int >& status, std::vector< std::string >& errors, PhaseBarrier& barrier )
+    {
+        // (a strip that failed still goes through the barriers, so that the others are not left waiting)
+        status[ k ] = strip_phase_a( c, c.g->strips[ k ], errors[ k ] );
+        barrier.arrive_and_wait();
+        if( status[ k ] == PAR_OK ) status[ k ] = strip_phase_b( c, k, errors[ k ] );
+        barrier.arrive_and_wait();
+        if( status[ k ] == PAR_OK ) status[ k ] = strip_phase_c( c, k, errors[ k ] );
+    }
+    explicit StripWorkers( size_t n_strips )
+    {
+        for( size_t k = 1; k < n_strips; k++ )
+            threads.emplace_back( [ this, k ] {
+                long seen = 0;
+                for( ;; )
+                {
+                    std::unique_lock< std::mutex > lock( m );
+                    wake.wait( lock, [ & ] { return stop || generation != seen; } );
+                    if( stop ) return;
+                    seen = generation;
+                    const TiledCall* c = call;
+                    std::vector< int >* st = status;
+                    std::vector< std::string >* er = errors;
+                    PhaseBarrier* b = barrier;
+                    lock.unlock();
+                    work( *c, k, *st, *er, *b );
+                    lock.lock();
+                    if( --running == 0 ) finished.notify_one();
+                }
+            } );
+    }
+    ~StripWorkers()
+    {
+        {
+            std::lock_guard< std::mutex > lock( m );
+            stop = true;
+        }
+        wake.notify_all();
+        for( auto& t : threads ) t.join();
+    }
+};
+
 // enqueue one call on all strips; returns the first failure (its message in g->error)
 int run_tiled_call( const TiledCall& c )
 {
@@ -388,23 +480,25 @@ int run_tiled_call( const TiledCall& c )
     std::vector< int > status( n, PAR_OK );
     std::vector< std::string > errors( n );
     PhaseBarrier barrier( ( int )n );
-    auto work = [ & ]( size_t k ) {
-        // (a strip that failed still goes through the barriers, so that the others are not left waiting)
-        status[ k ] = strip_phase_a( c, g->strips[ k ], errors[ k ] );
-        barrier.arrive_and_wait();
-        if( status[ k ] == PAR_OK ) status[ k ] = strip_phase_b( c, k, errors[ k ] );
-        barrier.arrive_and_wait();
-        if( status[ k ] == PAR_OK ) status[ k ] = strip_phase_c( c, k, errors[ k ] );
-    };
-    if( n == 1 )
-        work( 0 );
-    else
+    if( n > 1 )
     {
-        std::vector< std::thread > threads;
-        for( size_t k = 1; k < n; k++ ) threads.emplace_back( work, k );
-        work( 0 );
-        for( auto& t : threads ) t.join();
+        StripWorkers& w = *g->workers;
+        {
+            std::lock_guard< std::mutex > lock( w.m );
+            w.call = &c;
+            w.status = &status;
+            w.errors = &errors;
+            w.barrier = &barrier;
+            w.running = ( int )n - 1;
+            w.generation++;
+        }
+        w.wake.notify_all();
+        StripWorkers::work( c, 0, status, errors, barrier );
+        std::unique_lock< std::mutex > lock( w.m );
+        w.finished.wait( lock, [ & ] { return w.running == 0; } );
     }
+    else
+        StripWorkers::work( c, 0, status, errors, barrier );
     for( size_t k = 0; k < n; k++ )
         if( status[ k ] != PAR_OK ) return g->fail( status[ k ], "strip %d on device %d: %s", ( int )k, g->strips[ k ].device, errors[ k ].c_str() );
     return PAR_OK;
@@ -430,6 +524,8 @@ void par_group_destroy( par_group* g )
 {
     if( !g ) return;
     GroupDeviceGuard guard;
+    delete g->workers;
+    g->workers = nullptr;
     for( auto& s : g->strips )
     {
         if( !s.ctx ) continue; // never created (par_group_create failed part-way): nothing on that device
@@ -443,6 +539,7 @@ void par_group_destroy( par_group* g )
         cudaFree( s.d_seams );
         cudaFree( s.d_tab_keys );
         cudaFree( s.d_tab_parent );
+        cudaFree( s.d_seam_dst );
         for( cudaEvent_t ev : { s.ready, s.computed, s.labelled, s.t_begin, s.t_end } )
             if( ev ) cudaEventDestroy( ev );
         if( s.copy_stream ) cudaStreamDestroy( s.copy_stream );
@@ -526,6 +623,7 @@ int par_group_create( par_group** out, const int* devices, int n_devices, int wi
     }
     // direct NVLink/PCIe peer access between all pairs of devices where the topology allows it (aprons travel between
     // neighbours, seam label rows between all strips)
+    g->peer_stores = true;
     for( int p = 0; p < n_devices; p++ )
         for( int q = 0; q < n_devices; q++ )
         {
@@ -535,9 +633,31 @@ int par_group_create( par_group** out, const int* devices, int n_devices, int wi
             if( cudaDeviceCanAccessPeer( &ok, a, b ) == cudaSuccess && ok )
             {
                 cudaSetDevice( a );
-                if( cudaDeviceEnablePeerAccess( b, 0 ) != cudaSuccess ) cudaGetLastError(); // (already enabled)
+                const cudaError_t pe = cudaDeviceEnablePeerAccess( b, 0 );
+                if( pe != cudaSuccess ) cudaGetLastError();
+                if( pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled ) g->peer_stores = false;
+            }
+            else
+                g->peer_stores = false;
+        }
+    if( g->peer_stores && n_devices > 1 ) // every strip's table of all seam buffers
+    {
+        std::vector< int32_t* > all( n_devices );
+        for( int k = 0; k < n_devices; k++ ) all[ k ] = g->strips[ k ].d_seams;
+        for( auto& s : g->strips )
+        {
+            cudaSetDevice( s.device );
+            cudaError_t e = cudaMalloc( &s.d_seam_dst, n_devices * sizeof( int32_t* ) );
+            if( e == cudaSuccess ) e = cudaMemcpy( s.d_seam_dst, all.data(), n_devices * sizeof( int32_t* ), cudaMemcpyHostToDevice );
+            if( e != cudaSuccess )
+            {
+                g_group_create_error = std::string( "par_group_create: " ) + cudaGetErrorString( e );
+                par_group_destroy( g );
+                return PAR_ERR_CUDA;
             }
         }
+    }
+    if( n_devices > 1 ) g->workers = new StripWorkers( ( size_t )n_devices );
     *out = g;
     return PAR_OK;
 }

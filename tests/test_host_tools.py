@@ -93,6 +93,42 @@ def test_missing_file_fails_loudly(cli, tmp_path):
     assert r.returncode != 0 and "cannot read" in r.stderr
 
 
+def test_bad_scale_is_refused_before_anything_is_sized(cli, tmp_path):
+    src = str(tmp_path / "in.ppm")
+    cv2.imwrite(src, np.zeros((8, 8, 3), np.uint8))
+    for args in (["-s", "0"], ["-s", "9"], ["-s", "4", "--aa", "4"], ["-s", "2", "--aa", "3"]):
+        r = subprocess.run([cli, src, "-o", str(tmp_path / "o.png")] + args, capture_output=True, text=True)
+        assert r.returncode == 2 and "unsupported scale" in r.stderr, args
+
+
+def test_hostile_image_headers_are_refused(cli, tmp_path):
+    """Header fields of untrusted files are bounded before anything is allocated or indexed (BMP data offset / height sign,
+    PNG IHDR length and size, PNM digits): every one of these ends with an error message, not a crash."""
+    import struct
+    import zlib
+
+    def bmp(off, w, h, bits=24, size=200):
+        hdr = b"BM" + struct.pack("<IHHI", size, 0, 0, off & 0xFFFFFFFF) + struct.pack("<IiiHHIIiiII", 40, w, h, 1, bits, 0, 0, 0, 0, 0, 0)
+        return hdr + b"\0" * (size - len(hdr))
+
+    def png_chunk(kind, data):
+        return struct.pack(">I", len(data)) + kind + data + struct.pack(">I", zlib.crc32(kind + data))
+
+    sig = bytes([137, 80, 78, 71, 13, 10, 26, 10])
+    cases = {
+        "neg_offset.bmp": bmp(-64, 4, 4), "int_min_height.bmp": bmp(54, 4, -2 ** 31), "huge.bmp": bmp(54, 2 ** 30, 2 ** 30),
+        "offset_past_end.bmp": bmp(1000, 4, 4), "short_ihdr.png": sig + png_chunk(b"IHDR", b"\0" * 8) + png_chunk(b"IEND", b"") + b"\0" * 16,
+        "huge.png": sig + png_chunk(b"IHDR", struct.pack(">IIBBBBB", 2 ** 31 - 1, 2 ** 31 - 1, 8, 2, 0, 0, 0)) + png_chunk(b"IDAT", zlib.compress(b"\0")) + png_chunk(b"IEND", b""),
+        "no_size.ppm": b"P6\n#only a comment\n", "overflow.ppm": b"P6 99999999999999999999 1 255\n\0\0\0", "letters.ppm": b"P6 a b 255\n",
+        "truncated.ppm": b"P6 100 100 255\n\0\0\0",
+    }
+    for name, data in cases.items():
+        path = tmp_path / name
+        path.write_bytes(data)
+        r = subprocess.run([cli, str(path), "--convert-only", "-o", str(tmp_path / "o.png")], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 1 and r.stderr.strip(), (name, r.returncode, r.stderr)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("strips", [0, 2])
 def test_cli_image_in_image_out(cli, oracle, tmp_path, strips):
@@ -104,13 +140,18 @@ def test_cli_image_in_image_out(cli, oracle, tmp_path, strips):
     src = str(tmp_path / "in.png")
     cv2.imwrite(src, _bgr_top_down(frame))
     dst, gpath, gimg = str(tmp_path / "out.png"), str(tmp_path / "graph.png"), str(tmp_path / "graph_picture.png")
-    cmd = [cli, src, "-o", dst, "-s", "4", "--graph", gpath, "--graph-image", gimg] + (["--strips", str(strips)] if strips else [])
+    lpath = str(tmp_path / "labels.png")
+    cmd = [cli, src, "-o", dst, "-s", "4", "--graph", gpath, "--graph-image", gimg, "--labels", lpath] + (["--strips", str(strips)] if strips else [])
     subprocess.run(cmd, check=True, timeout=300)
     # the CLI pads rows to 4 bytes like IplImage; 96*3 is already aligned, so the oracle sees the same bytes
     want = oracle.pipeline(frame, scale=4, want=("graph", "raster"))
     got = cv2.imread(dst, cv2.IMREAD_COLOR)
     assert np.array_equal(got, want["raster"][::-1, :, 2::-1])   # RGBA bottom-up -> BGR top-down
     assert np.array_equal(cv2.imread(gpath, cv2.IMREAD_GRAYSCALE), want["graph"][::-1])
+    # --labels: an RGBA PNG whose R, G, B, A bytes are the little-endian bytes of the int32 label (lossless)
+    lab_png = cv2.cvtColor(cv2.imread(lpath, cv2.IMREAD_UNCHANGED), cv2.COLOR_BGRA2RGBA)
+    assert lab_png.shape == (120, 96, 4)
+    assert np.array_equal(np.ascontiguousarray(lab_png).view("<i4")[..., 0], oracle.cc_labels(want["graph"])[::-1])
     # the graph picture of the same run equals the one drawn from the stored plane
     again = str(tmp_path / "graph_picture_again.png")
     subprocess.run([cli, src, "--draw-graph", gpath, "--graph-image", again], check=True, timeout=60)
