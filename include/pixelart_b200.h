@@ -167,6 +167,22 @@ int par_border_walks( par_context* ctx, const uint8_t* graph, const int32_t* lab
 int par_walk_splines( par_context* ctx, const int32_t* walk_len, const int32_t* walk_begin, const int32_t* walk_nodes, const long long* total, int width,
                       int height, int n_frames, long long capacity_per_frame, int samples_per_segment, float* points );
 
+/* Outlines of one frame, host in / host out: similarity graph, crossings, labels, the border walk of every component and
+ * its spline (par_border_walks + par_walk_splines), gathered into one malloc'd block that par_outlines_free() releases.
+ * Walks are listed in raster order of their start pixel; walk k starts at pixel `start[k]` (= its component's label; its
+ * colour is the component's colour), has `count[k]` nodes and count[k] * samples curve points, stored back to back in
+ * `points` (x, y pairs, source-pixel coordinates, row 0 = bottom).  What `remaster_cli --outlines out.svg` draws. */
+typedef struct par_outlines
+{
+    int n_walks, samples;
+    int32_t* start;     /* [n_walks] */
+    int32_t* count;     /* [n_walks] */
+    long long n_points; /* sum of count[k] * samples */
+    float* points;      /* [n_points][2] */
+} par_outlines;
+int par_outlines_host( par_context* ctx, const uint8_t* bgr, int width, int height, int widthstep, int samples_per_segment, par_outlines* out );
+void par_outlines_free( par_outlines* out );
+
 /* Whole path on device-resident frames; asynchronous on the context's stream. */
 int par_remaster_device( par_context* ctx, const par_job* job );
 /* Whole path on host buffers: H2D of the frames, the kernels, D2H of every non-NULL output, then a

@@ -41,6 +41,11 @@ class ParJob(C.Structure):
                 ("out_format", C.c_int), ("palette", C.c_void_p), ("palette_count", C.c_void_p)]
 
 
+class ParOutlines(C.Structure):
+    _fields_ = [("n_walks", C.c_int), ("samples", C.c_int), ("start", C.POINTER(C.c_int32)), ("count", C.POINTER(C.c_int32)),
+                ("n_points", C.c_longlong), ("points", C.POINTER(C.c_float))]
+
+
 class ParStrip(C.Structure):
     _fields_ = [("device", C.c_int), ("own_begin", C.c_int), ("own_end", C.c_int), ("load_begin", C.c_int), ("load_end", C.c_int),
                 ("bgr", C.c_void_p), ("image", C.c_void_p), ("graph", C.c_void_p), ("graph_aux", C.c_void_p), ("labels", C.c_void_p)]
@@ -84,6 +89,9 @@ def load_library():
                                    C.c_longlong, C.c_void_p]
     L.par_walk_splines.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int,
                                    C.c_void_p]
+    L.par_outlines_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, P(ParOutlines)]
+    L.par_outlines_free.argtypes = [P(ParOutlines)]
+    L.par_outlines_free.restype = None
     L.par_smooth_stats.argtypes = [C.c_void_p, P(C.c_uint64)]
     L.par_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.par_profile_read.argtypes = [C.c_void_p, P(C.c_double), P(C.c_int)]
@@ -347,6 +355,24 @@ class Remaster:
         self._check(self.lib.par_walk_splines(self.handle, walk_len.data_ptr(), walk_begin.data_ptr(), walk_nodes.data_ptr(), total.data_ptr(),
                                               W, H, F, cap, int(samples), pts.data_ptr()))
         return pts
+
+    def outlines_host(self, image, samples=4):
+        """par_outlines_host: numpy uint8 (H, W, 3) BGR frame (row 0 = bottom) -> [(start pixel, (count * samples, 2) float32 curve points)]
+        for every component's border walk, in raster order of the start."""
+        assert image.dtype == np.uint8 and image.ndim == 3 and image.shape[2] == 3 and image.strides[1:] == (3, 1)
+        self._bind_stream()
+        o = ParOutlines()
+        self._check(self.lib.par_outlines_host(self.handle, image.ctypes.data, image.shape[1], image.shape[0], image.strides[0], int(samples), C.byref(o)))
+        try:
+            pts = np.ctypeslib.as_array(o.points, shape=(int(o.n_points), 2)).copy() if o.n_points else np.zeros((0, 2), np.float32)
+            res, at = [], 0
+            for k in range(o.n_walks):
+                m = o.count[k] * o.samples
+                res.append((int(o.start[k]), pts[at:at + m]))
+                at += m
+            return res
+        finally:
+            self.lib.par_outlines_free(C.byref(o))
 
     @staticmethod
     def walks_as_dict(walk_len, walk_begin, walk_nodes, frame=0):

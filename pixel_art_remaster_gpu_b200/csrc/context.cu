@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -677,6 +678,86 @@ int par_walk_splines( par_context* c, const int32_t* walk_len, const int32_t* wa
                                          c->stream );
     c->launches += ( n_frames + 65534 ) / 65535;
     return e == cudaSuccess ? PAR_OK : c->cuda_fail( e, "walk_splines" );
+}
+
+int par_outlines_host( par_context* c, const uint8_t* bgr, int width, int height, int widthstep, int samples, par_outlines* out )
+{
+    if( !c ) return PAR_ERR_INVALID;
+    if( !bgr || !out || width <= 0 || height <= 0 || widthstep < 3 * width ) return c->fail( PAR_ERR_INVALID, "outlines: bad argument" );
+    memset( out, 0, sizeof( *out ) );
+    DeviceGuard guard( c->device );
+    const size_t px = ( size_t )width * height, in_bytes = ( size_t )widthstep * height;
+    const long long capacity = 4ll * ( long long )px; // (a walk visits a node at most once per link direction)
+    // one device block: frame | graph_aux | graph | labels | walk_len | walk_begin | total | nodes | points
+    uint8_t* d = nullptr;
+    auto up16 = []( size_t v ) { return ( v + 15 ) & ~( size_t )15; };
+    const size_t o_aux = up16( in_bytes + 16 ), o_graph = o_aux + up16( px ), o_lab = o_graph + up16( px ), o_len = o_lab + px * 4, o_beg = o_len + px * 4,
+                 o_tot = o_beg + px * 4, o_nodes = o_tot + 16, o_pts = o_nodes + ( size_t )capacity * 4, bytes = o_pts + ( size_t )capacity * samples * 8;
+    cudaError_t e = cudaMalloc( &d, bytes );
+    if( e != cudaSuccess ) return c->cuda_fail( e, "outlines cudaMalloc" );
+    auto fail = [ & ]( int st ) {
+        cudaFree( d );
+        par_outlines_free( out );
+        return st;
+    };
+    e = cudaMemcpyAsync( d, bgr, in_bytes, cudaMemcpyHostToDevice, c->stream );
+    if( e != cudaSuccess ) return fail( c->cuda_fail( e, "outlines H2D" ) );
+    par_job j = {};
+    j.bgr = d;
+    j.width = width;
+    j.height = height;
+    j.widthstep = widthstep;
+    j.n_frames = 1;
+    j.scale = 1;
+    j.graph_aux = d + o_aux;
+    j.graph = d + o_graph;
+    j.labels = reinterpret_cast< int32_t* >( d + o_lab );
+    int32_t *d_len = reinterpret_cast< int32_t* >( d + o_len ), *d_beg = reinterpret_cast< int32_t* >( d + o_beg ), *d_nodes = reinterpret_cast< int32_t* >( d + o_nodes );
+    long long* d_tot = reinterpret_cast< long long* >( d + o_tot );
+    float* d_pts = reinterpret_cast< float* >( d + o_pts );
+    int st = par_remaster_device( c, &j );
+    if( st == PAR_OK ) st = par_border_walks( c, j.graph, j.labels, width, height, 1, d_len, d_beg, d_nodes, capacity, d_tot );
+    if( st == PAR_OK ) st = par_walk_splines( c, d_len, d_beg, d_nodes, d_tot, width, height, 1, capacity, samples, d_pts );
+    if( st != PAR_OK ) return fail( st );
+    std::vector< int32_t > len( px ), beg( px );
+    long long total = 0;
+    e = cudaMemcpyAsync( len.data(), d_len, px * 4, cudaMemcpyDeviceToHost, c->stream );
+    if( e == cudaSuccess ) e = cudaMemcpyAsync( beg.data(), d_beg, px * 4, cudaMemcpyDeviceToHost, c->stream );
+    if( e == cudaSuccess ) e = cudaMemcpyAsync( &total, d_tot, sizeof( total ), cudaMemcpyDeviceToHost, c->stream );
+    if( e == cudaSuccess ) e = cudaStreamSynchronize( c->stream );
+    if( e != cudaSuccess ) return fail( c->cuda_fail( e, "outlines D2H" ) );
+    if( total > capacity ) return fail( c->fail( PAR_ERR_CAPACITY, "outlines: the walks need %lld entries, capacity %lld", total, capacity ) );
+    int n_walks = 0;
+    for( size_t n = 0; n < px; n++ ) n_walks += len[ n ] > 0;
+    out->n_walks = n_walks;
+    out->samples = samples;
+    out->n_points = total * samples;
+    out->start = static_cast< int32_t* >( malloc( sizeof( int32_t ) * ( n_walks ? n_walks : 1 ) ) );
+    out->count = static_cast< int32_t* >( malloc( sizeof( int32_t ) * ( n_walks ? n_walks : 1 ) ) );
+    out->points = static_cast< float* >( malloc( sizeof( float ) * 2 * ( size_t )( out->n_points ? out->n_points : 1 ) ) );
+    if( !out->start || !out->count || !out->points ) return fail( c->fail( PAR_ERR_INVALID, "outlines: out of host memory" ) );
+    // walks are stored in raster order of their start, so the points of all walks are one contiguous range
+    e = cudaMemcpy( out->points, d_pts, sizeof( float ) * 2 * ( size_t )out->n_points, cudaMemcpyDeviceToHost );
+    if( e != cudaSuccess ) return fail( c->cuda_fail( e, "outlines D2H" ) );
+    int k = 0;
+    for( size_t n = 0; n < px; n++ )
+        if( len[ n ] > 0 )
+        {
+            out->start[ k ] = ( int32_t )n;
+            out->count[ k ] = len[ n ];
+            k++;
+        }
+    cudaFree( d );
+    return PAR_OK;
+}
+
+void par_outlines_free( par_outlines* out )
+{
+    if( !out ) return;
+    free( out->start );
+    free( out->count );
+    free( out->points );
+    memset( out, 0, sizeof( *out ) );
 }
 
 int par_remaster_device( par_context* c, const par_job* j )

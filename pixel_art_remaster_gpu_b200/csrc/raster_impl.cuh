@@ -753,7 +753,12 @@ __device__ __forceinline__ uint32_t link_slots( const SmoothTablePtrs& st, const
 //  * for the scales above 4, the window form on four 64-bit fields per cell (nine 64-bit shared loads per pixel instead of
 //    a word per candidate and sample row, an early exit for pixels that are all their own colour): bit-exact, and slower at
 //    every scale (8x: 2.32 against 2.14 ms per 512 frames, 6x: 1.89 / 1.41, 5x: 1.95 / 1.29, 7x: 3.86 / 2.03) — 64-bit shifts
-//    and selects cost more instructions than the shared loads they replace.)
+//    and selects cost more instructions than the shared loads they replace;
+//  * the output rows through shared memory and out by bulk copies (cp.async.bulk shared -> global, SASS UBLKCP.G.S; two
+//    512-byte row buffers per warp, one copy per warp and output row) instead of STG.128, so that the 64 bytes per pixel do
+//    not cross the LSU's 32-byte-per-clock path to the crossbar (the stores are a third of the kernel's LSU data-pipe
+//    cycles): bit-exact, 4.93 against 4.37 ms (and 3.20 against 2.60 with subdivision off) — a wait, two warp barriers, a
+//    proxy fence and a command flush per 512 bytes cost more than the path they relieve.)
 // Mask of a smoothed cell from the tables, FIRST pass: the CUT entry and the first two link descriptors (nine cells in
 // ten have no more).  `more` is set when the key has a third descriptor: the caller marks the cell for
 // smooth_lookup_more.  Returns false when a blended vertex is not a vertex of the neighbour's hull (the reference's

@@ -131,14 +131,58 @@ static bool save_plane( const char* path, const void* data, int w, int h, int by
     return out.error().empty();
 }
 
+// --outlines: the spline outline of every connected component (par_outlines_host: graph, labels, border walks, closed
+// quadratic B-splines over the walks — the stage the reference's extractBorderPoints, cc_functions.cu:348-503, was written
+// for) as an SVG, one filled path per component in its own colour, coordinates in output pixels, top scanline first.
+static bool save_outlines_svg( const char* path, int device, int scale )
+{
+    par_context* ctx = nullptr;
+    if( par_create( &ctx, device, img_width, img_height, 1 ) != PAR_OK )
+    {
+        fprintf( stderr, "remaster_cli: %s\n", par_last_error( nullptr ) );
+        return false;
+    }
+    par_outlines o;
+    if( par_outlines_host( ctx, reinterpret_cast< const uint8_t* >( img_data ), img_width, img_height, img_widthstep, 4, &o ) != PAR_OK )
+    {
+        fprintf( stderr, "remaster_cli: %s\n", par_last_error( ctx ) );
+        par_destroy( ctx );
+        return false;
+    }
+    FILE* f = fopen( path, "w" );
+    bool ok = f != nullptr;
+    if( ok )
+    {
+        fprintf( f, "<svg xmlns=\"http://www.w3.org/2000/svg\" width=\"%d\" height=\"%d\" viewBox=\"0 0 %d %d\">\n", img_width * scale, img_height * scale,
+                 img_width * scale, img_height * scale );
+        const float* p = o.points;
+        for( int k = 0; k < o.n_walks; k++ )
+        {
+            const int n = o.start[ k ], x = n % img_width, y = n / img_width;
+            const unsigned char* c = reinterpret_cast< const unsigned char* >( img_data ) + ( size_t )y * img_widthstep + 3 * x; // B, G, R
+            fprintf( f, "<path fill=\"#%02x%02x%02x\" d=\"", c[ 2 ], c[ 1 ], c[ 0 ] );
+            const long long m = ( long long )o.count[ k ] * o.samples;
+            for( long long t = 0; t < m; t++, p += 2 )
+                fprintf( f, "%c%.8g %.8g", t ? 'L' : 'M', p[ 0 ] * scale, ( img_height - p[ 1 ] ) * scale ); // (row 0 of the path is the bottom scanline)
+            fprintf( f, "Z\"/>\n" );
+        }
+        fprintf( f, "</svg>\n" );
+        ok = fclose( f ) == 0;
+    }
+    if( !ok ) fprintf( stderr, "remaster_cli: cannot write %s\n", path );
+    par_outlines_free( &o );
+    par_destroy( ctx );
+    return ok;
+}
+
 int main( int argc, char** argv )
 {
     if( argc < 2 )
     {
-        fprintf( stderr, "usage: %s <input image> [-o out.png] [-s scale] [--aa 2|4] [--no-subdivide] [--graph g.pgm] [--labels l.png] [--graph-image g.png] [--draw-graph g.pgm] [--strips N] [--device D] [--convert-only] [--raw-video in.bin --raw-out out.bin [--skip K] [--frames M]]\n", argv[ 0 ] );
+        fprintf( stderr, "usage: %s <input image> [-o out.png] [-s scale] [--aa 2|4] [--no-subdivide] [--graph g.pgm] [--labels l.png] [--graph-image g.png] [--outlines o.svg] [--draw-graph g.pgm] [--strips N] [--device D] [--convert-only] [--raw-video in.bin --raw-out out.bin [--skip K] [--frames M]]\n", argv[ 0 ] );
         return 2;
     }
-    std::string out_path = "remastered.png", graph_path, labels_path, graph_image_path, draw_graph_path, raw_video_path, raw_out_path;
+    std::string out_path = "remastered.png", graph_path, labels_path, graph_image_path, draw_graph_path, raw_video_path, raw_out_path, outlines_path;
     long skip_frames = 0, max_video_frames = 2000;
     int scale = 4, strips = 0, device = 0, aa = 1; // aa: anti-aliasing samples per axis (the reference's GL_MULTISAMPLE toggle, simpleVBO.cpp:238-253)
     bool subdivide = true, convert_only = false;
@@ -152,6 +196,7 @@ int main( int argc, char** argv )
         else if( a == "--graph" && k + 1 < argc ) graph_path = argv[ ++k ];
         else if( a == "--labels" && k + 1 < argc ) labels_path = argv[ ++k ];
         else if( a == "--graph-image" && k + 1 < argc ) graph_image_path = argv[ ++k ];
+        else if( a == "--outlines" && k + 1 < argc ) outlines_path = argv[ ++k ];
         else if( a == "--draw-graph" && k + 1 < argc ) draw_graph_path = argv[ ++k ];
         else if( a == "--raw-video" && k + 1 < argc ) raw_video_path = argv[ ++k ];
         else if( a == "--raw-out" && k + 1 < argc ) raw_out_path = argv[ ++k ];
@@ -297,6 +342,7 @@ int main( int argc, char** argv )
     if( !graph_path.empty() && !save_plane( graph_path.c_str(), graph, img_width, img_height, 1 ) ) return 1;
     if( !labels_path.empty() && !save_plane( labels_path.c_str(), labels.data(), img_width, img_height, 4 ) ) return 1;
     if( !graph_image_path.empty() && !save_graph_image( graph_image_path.c_str() ) ) return 1;
+    if( !outlines_path.empty() && !save_outlines_svg( outlines_path.c_str(), device, scale ) ) return 1;
     printf( "%s: %dx%d -> %dx%d (scale %d, subdivide %s) -> %s\n", argv[ 1 ], img_width, img_height, img_width * scale, img_height * scale, scale,
             subdivide ? "on" : "off", out_path.c_str() );
     free( graph );

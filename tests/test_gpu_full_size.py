@@ -75,3 +75,33 @@ def test_c4_map_4096_tiled_equals_whole(lib, oracle):
         want = oracle.pipeline(win, scale=4, want=("graph", "raster"))
         assert np.array_equal(want["graph"][40:-40, 40:-40], w_graph[y0:y0 + 200, x0:x0 + 200])
         assert np.array_equal(want["raster"][160:-160, 160:-160], w_rgba[4 * y0:4 * (y0 + 200), 4 * x0:4 * (x0 + 200)])
+
+
+def test_more_frames_than_one_launch_can_index(lib, oracle):
+    """A batch of more than 65 535 frames (the grid.z limit: every stage splits its launches): 70 000 frames of 8 x 8,
+    whole path with labels, all three output formats — equal to the same frames run in two halves, a sample against the oracle."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    F, W, H, S = 70_000, 8, 8, 2
+    rng = np.random.default_rng(9)
+    pal = rng.integers(0, 256, (5, 3), dtype=np.uint8)
+    frames_np = pal[rng.integers(0, 5, (F, H, W))]
+    frames = torch.from_numpy(frames_np).cuda()
+    with lib.Remaster(0, W, H, F) as c:
+        whole = c.remaster(frames, scale=S, subdivide=True, want=("rgba", "graph", "graph_aux", "labels"))
+        idx = c.remaster(frames, scale=S, subdivide=True, out_format=lib.OUT_INDEX8)
+        bgr = c.remaster(frames, scale=S, subdivide=True, out_format=lib.OUT_BGR8)["rgba"]
+        half = F // 2
+        for lo, hi in ((0, half), (half, F)):
+            part = c.remaster(frames[lo:hi], scale=S, subdivide=True, want=("rgba", "graph", "graph_aux", "labels"))
+            for k in part:
+                assert torch.equal(part[k], whole[k][lo:hi]), (k, lo)
+        assert torch.equal(bgr, whole["rgba"][..., [2, 1, 0]])
+        for lo in range(0, F, 10_000):  # (expanded in pieces: the gather index is 8 bytes per pixel)
+            hi = min(lo + 10_000, F)
+            assert np.array_equal(lib.Remaster.expand_indexed(idx["rgba"][lo:hi], idx["palette"][lo:hi]), whole["rgba"][lo:hi].cpu().numpy())
+        for k in (0, 65_534, 65_535, 65_536, F - 1):
+            want = oracle.pipeline(frames_np[k], scale=S, want=("graph_aux", "graph", "labels", "raster"))
+            assert np.array_equal(whole["graph"][k].cpu().numpy(), want["graph"]) and np.array_equal(whole["labels"][k].cpu().numpy(), want["labels"])
+            assert np.array_equal(whole["rgba"][k].cpu().numpy(), want["raster"]), k

@@ -181,3 +181,35 @@ def test_cli_raw_video_stream(cli, oracle, tmp_path):
         src = np.lib.stride_tricks.as_strided(padded[skip + k], shape=(h, w, 3), strides=(152, 3, 1))  # the same padding bytes
         want = oracle.pipeline(src, scale=2, want=("raster",))["raster"]
         assert np.array_equal(got[k], want), k
+
+
+@pytest.mark.gpu
+def test_outlines_host_and_svg(cli, lib, oracle, tmp_path):
+    """par_outlines_host (graph -> labels -> border walks -> closed quadratic B-splines, gathered on the host) against the
+    oracle's walks and the numpy spline, and `remaster_cli --outlines out.svg`: one filled path per walk, in the colour of
+    the walk's start pixel, with the same points (scaled, top scanline first)."""
+    import re
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    W, H, S = 48, 40, 4
+    frame = synth.snes_frame(W, H, 23)
+    want = oracle.pipeline(frame, want=("graph", "labels"))
+    walks = oracle.border_walks(want["graph"], want["labels"])
+    with lib.Remaster(0, W, H, 1) as c:
+        got = c.outlines_host(frame, samples=4)
+    assert [s for s, _ in got] == sorted(walks)
+    for start, pts in got:
+        assert np.array_equal(pts.astype(np.float64), oracle.walk_spline(walks[start], W, 4)), start
+    src, svg = str(tmp_path / "in.png"), str(tmp_path / "out.svg")
+    cv2.imwrite(src, _bgr_top_down(frame))
+    subprocess.run([cli, src, "-o", str(tmp_path / "o.png"), "-s", str(S), "--outlines", svg], check=True, timeout=300)
+    text = open(svg).read()
+    paths = re.findall(r'<path fill="#([0-9a-f]{6})" d="([^"]*)"/>', text)
+    assert len(paths) == len(got) and 'viewBox="0 0 %d %d"' % (W * S, H * S) in text
+    for (fill, d), (start, pts) in zip(paths, got):
+        b, g, r = frame[start // W, start % W]
+        assert fill == "%02x%02x%02x" % (r, g, b)
+        xy = np.array([[float(v) for v in m] for m in re.findall(r"[ML]([-0-9.e+]+) ([-0-9.e+]+)", d)])
+        assert xy.shape == pts.shape and d.endswith("Z")
+        np.testing.assert_allclose(xy, np.stack([pts[:, 0] * S, (H - pts[:, 1]) * S], -1), rtol=2e-4, atol=1e-3)
