@@ -758,7 +758,11 @@ __device__ __forceinline__ uint32_t link_slots( const SmoothTablePtrs& st, const
 //    512-byte row buffers per warp, one copy per warp and output row) instead of STG.128, so that the 64 bytes per pixel do
 //    not cross the LSU's 32-byte-per-clock path to the crossbar (the stores are a third of the kernel's LSU data-pipe
 //    cycles): bit-exact, 4.93 against 4.37 ms (and 3.20 against 2.60 with subdivision off) — a wait, two warp barriers, a
-//    proxy fence and a command flush per 512 bytes cost more than the path they relieve.)
+//    proxy fence and a command flush per 512 bytes cost more than the path they relieve;
+//  * the same with ONE bulk-tensor store per warp and tile row (cp.async.bulk.tensor.3d shared -> global, SASS UTMASTG.3D: a
+//    2 KB band of 4 output rows x 128 pixels per warp, the tensor unit clipping at the image edge): bit-exact, 5.13 against
+//    4.37 ms (2.86 against 2.60 with subdivision off) — 16 KB more shared memory per CTA means four CTAs per SM and 92 KB
+//    instead of 124 KB of L1 for the tables.)
 // Mask of a smoothed cell from the tables, FIRST pass: the CUT entry and the first two link descriptors (nine cells in
 // ten have no more).  `more` is set when the key has a third descriptor: the caller marks the cell for
 // smooth_lookup_more.  Returns false when a blended vertex is not a vertex of the neighbour's hull (the reference's
