@@ -65,7 +65,7 @@ struct par_context
     CellRecord* d_tables = nullptr;        // kCellKeys 32-byte records
     uint32_t* d_mask_lut[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // per scale, built on first use
     // smoothing tables (smooth_table.h): link descriptors + neighbour bytes + class list (scale-independent), CUT / LINK masks per scale
-    SmoothRecord* d_smooth_rec = nullptr;
+    uint32_t* d_smooth_words = nullptr; // head | head2 (kCellKeys words each) | pack (kCellKeys x 2 words)
     LinkClass* d_link_classes = nullptr;
     int n_link_classes = 0;
     uint32_t link_entries = 0;
@@ -359,7 +359,8 @@ int run_raster( par_context* c, const par_job* j, const uint8_t* graph, const ui
         built = true;
     }
     a.mask_lut = c->d_mask_lut[ S ];
-    a.smooth = SmoothTablePtrs{ c->d_smooth_rec, nullptr, nullptr };
+    a.smooth = SmoothTablePtrs{ c->d_smooth_words, c->d_smooth_words + kCellKeys, reinterpret_cast< const uint2* >( c->d_smooth_words + 2 * kCellKeys ),
+                                nullptr, nullptr };
     a.smooth_stats = c->d_smooth_stats;
     if( a.subdivide && !( j->flags & PAR_FLAG_NO_SMOOTH_TABLES ) )
     {
@@ -456,13 +457,15 @@ int par_create( par_context** out, int device, int max_width, int max_height, in
             build_smooth_tables( tables, &smooth );
         } );
         static_assert( sizeof( CellTables ) == 32 * kCellKeys, "one 32-byte record per key" );
-        static_assert( sizeof( SmoothRecord ) == 32, "one 32-byte record per key" );
         e = cudaMemcpy( c->d_tables, &tables, sizeof( tables ), cudaMemcpyHostToDevice );
         c->n_link_classes = ( int )smooth.classes.size();
         c->link_entries = smooth.link_entries;
-        if( e == cudaSuccess ) e = cudaMalloc( &c->d_smooth_rec, sizeof( smooth.rec ) );
+        const size_t kw = ( size_t )kCellKeys * sizeof( uint32_t );
+        if( e == cudaSuccess ) e = cudaMalloc( &c->d_smooth_words, 4 * kw );
         if( e == cudaSuccess ) e = cudaMalloc( &c->d_link_classes, smooth.classes.size() * sizeof( LinkClass ) );
-        if( e == cudaSuccess ) e = cudaMemcpy( c->d_smooth_rec, smooth.rec, sizeof( smooth.rec ), cudaMemcpyHostToDevice );
+        if( e == cudaSuccess ) e = cudaMemcpy( c->d_smooth_words, smooth.head, kw, cudaMemcpyHostToDevice );
+        if( e == cudaSuccess ) e = cudaMemcpy( c->d_smooth_words + kCellKeys, smooth.head2, kw, cudaMemcpyHostToDevice );
+        if( e == cudaSuccess ) e = cudaMemcpy( c->d_smooth_words + 2 * kCellKeys, smooth.pack, 2 * kw, cudaMemcpyHostToDevice );
         if( e == cudaSuccess )
             e = cudaMemcpy( c->d_link_classes, smooth.classes.data(), smooth.classes.size() * sizeof( LinkClass ), cudaMemcpyHostToDevice );
     }
@@ -493,7 +496,7 @@ void par_destroy( par_context* c )
     for( int k = 0; k < 9; k++ ) cudaFree( c->d_mask_lut[ k ] );
     for( int k = 0; k < 9; k++ ) cudaFree( c->d_cut[ k ] );
     for( int k = 0; k < 9; k++ ) cudaFree( c->d_link[ k ] );
-    cudaFree( c->d_smooth_rec );
+    cudaFree( c->d_smooth_words );
     cudaFree( c->d_link_classes );
     cudaFree( c->d_smooth_stats );
     cudaFree( c->d_pal_lut );

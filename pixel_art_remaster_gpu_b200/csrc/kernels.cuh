@@ -33,9 +33,11 @@ struct LabelArgs
 // device pointers of the smoothing tables (smooth_table.h); cut / link are per scale
 struct SmoothTablePtrs
 {
-    const SmoothRecord* rec; // [kCellKeys] link descriptors + neighbour records, 32 bytes each
-    const uint64_t* cut;  // [kCellKeys][16] entries
-    const uint64_t* link; // [link_entries] entries
+    const uint32_t* head;   // [kCellKeys] link descriptors 0, 1 + corner bits + flags
+    const uint32_t* head2;  // [kCellKeys] link descriptors 2, 3
+    const uint2* pack;      // [kCellKeys] IDs of the key's neighbour records: x = directions 4..7 in bits [12,32), y = directions 0..3
+    const uint64_t* cut;    // [kCellKeys][16] entries (per scale)
+    const uint64_t* link;   // [link_entries] entries: kNbrIds per class (per scale)
 };
 
 struct RasterArgs

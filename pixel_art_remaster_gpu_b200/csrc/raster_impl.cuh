@@ -11,7 +11,6 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxVerts = 16;    // 8 hull vertices, each replaced by at most two
-constexpr int kGeoThreads = 128; // threads that take part in the (rare) geometric path: one vertex buffer each
 
 template< int S >
 struct Cfg
@@ -61,21 +60,24 @@ struct Cfg
     static constexpr uint32_t M_RIGHTCOL = M_COL0 << ( S - 1 );         // my column S-1 <- F1 of the cell to the right
     static constexpr uint32_t M_BOTROW = ( 1u << S ) - 1u;              // my row 0      <- F2 of the cell below
     static constexpr uint32_t M_TOPROW = M_BOTROW << ( S * ( S - 1 ) ); // my row S-1    <- F2 of the cell above
-    // Shared memory carve-up (bytes).  The first region has two lives: (1) the staged graph and BGR rows (the TMA
-    // destinations) until the staging pass has turned them into keys and colours; (2) the geometric path's vertex
-    // buffers next to the list of cells queued for it.  Keeping the CTA at 24 KB lets five of them share an SM with
-    // 124 KB left as L1 for the tables — the kernel is sensitive to both.
-    static constexpr int off_graph = 0;
-    static constexpr int off_raw = ( KH * GP + 127 ) / 128 * 128;
-    static constexpr int off_vbuf = 0;
-    static constexpr int off_work = ( kMaxVerts * kGeoThreads * 2 + 15 ) / 16 * 16;
-    static constexpr int sz_stage = off_raw + KH * RAWP, sz_lists = off_work + NC * 2;
-    static constexpr int off_keys = ( ( sz_stage > sz_lists ? sz_stage : sz_lists ) + 127 ) / 128 * 128;
-    static constexpr int off_col = off_keys + ( KW * KH * 2 + 15 ) / 16 * 16;
-    static constexpr int off_mask = off_col + KW * KH * 4;
+    // Shared memory carve-up (bytes).  The mask array has two lives: until the staging pass has turned them into cell
+    // words and colours it holds the staged graph and BGR rows (the TMA destinations); the masks are written after
+    // that.  Keeping the CTA under 25.4 KB lets five of them share an SM with 124 KB left as L1 for the tables — the kernel
+    // is sensitive to both.
+    // two 32-bit words per cell (smooth_table.h): x = 12-bit key | IDs of directions 4..7 << 12, y = IDs of directions 0..3;
+    // row r of the tile is KW x-words followed by KW y-words (consecutive cells on consecutive banks, and every
+    // neighbour's word of either kind within a signed byte of word offsets)
+    static constexpr int KP = 2 * KW;                      // words per row of cell words
+    static constexpr int off_keys = 0;
+    static constexpr int off_col = off_keys + KW * KH * 8;
+    static constexpr int off_mask = ( off_col + KW * KH * 4 + 127 ) / 128 * 128;
+    static constexpr int off_graph = off_mask;
+    static constexpr int off_raw = off_graph + ( KH * GP + 127 ) / 128 * 128;
+    static constexpr int sz_stage = off_raw - off_graph + KH * RAWP;
+    static_assert( sz_stage <= NC * MW * 4, "the staged rows fit in the mask array" );
     static constexpr int off_bar = ( off_mask + NC * MW * 4 + 15 ) / 16 * 16;
     static constexpr int off_nwork = off_bar + 16; // four counters / flags
-    static constexpr int smem_bytes = off_nwork + 16 + 4 * ( ( NC + kThreads - 1 ) / kThreads ) * ( kThreads / 32 ); // counters, then the ballots of the mask pass
+    static constexpr int smem_bytes = off_nwork + 16 + 2 * 4 * ( ( NC + kThreads - 1 ) / kThreads ) * ( kThreads / 32 ); // counters, then the two ballot arrays of the mask pass
 };
 
 // number of sample columns c in [0,N) with F - c*G > 0, i.e. clamp(ceil(F/G), 0, N), G > 0
@@ -200,15 +202,12 @@ __device__ __forceinline__ void cover_polygon( const uint16_t* buf, int stride, 
     }
 }
 
-// next free slot of a shared-memory list, for the lanes that call it together: one atomic per warp
-__device__ __forceinline__ int warp_slot( int* counter )
+// 64-bit read-only load under a predicate, 0 otherwise (no branch: the compiler will not speculate a load on its own)
+__device__ __forceinline__ uint64_t ldg_u64_if( const uint64_t* p, bool pred )
 {
-    const uint32_t peers = __activemask();
-    const uint32_t lane = threadIdx.x & 31u;
-    int base = 0;
-    if( lane == ( uint32_t )__ffs( ( int )peers ) - 1u ) base = atomicAdd( counter, __popc( peers ) );
-    base = __shfl_sync( peers, base, __ffs( ( int )peers ) - 1 );
-    return base + __popc( peers & ( ( 1u << lane ) - 1u ) );
+    uint64_t v = 0ull;
+    asm( "{ .reg .pred q; setp.ne.u32 q, %2, 0; @q ld.global.nc.u64 %0, [%1]; }" : "+l"( v ) : "l"( p ), "r"( ( uint32_t )pred ) );
+    return v;
 }
 
 // Output formats (par_out_format): how the S words of a row segment leave the kernel.  In INDEX8 mode a "colour word" carries
@@ -356,11 +355,11 @@ __device__ __forceinline__ void store_cell( uint8_t* dst, ptrdiff_t row_step, co
 template< int S >
 struct TileEnv
 {
-    const uint16_t* keys; // KW x KH, origin (x0-2, y0-2)
+    const uint32_t* keys; // KH rows of cell words (Cfg::KP words each; key = low 12 bits of the x-word), origin (x0-2, y0-2)
     const uint32_t* cols; // KW x KH RGBA words, same origin; rows at or above the image height hold colour 0
     int x0, y0;
     FlatImage img;
-    __device__ __forceinline__ uint32_t key( int i, int j ) const { return keys[ ( j - y0 + 2 ) * Cfg< S >::KW + ( i - x0 + 2 ) ]; }
+    __device__ __forceinline__ uint32_t key( int i, int j ) const { return keys[ ( j - y0 + 2 ) * Cfg< S >::KP + ( i - x0 + 2 ) ] & 0xFFFu; }
     // checkTJunction (subdivision_functions.cu:170-242).  Away from the first/last column the flat byte
     // offsets the reference uses (idx +- widthstep +- 3) are exactly the 2-D neighbours, which are staged
     // in shared memory; at i = 0 / W-1 they wrap to the adjacent rows, so those cells take the flat path.
@@ -380,7 +379,7 @@ struct TileEnv
 // slow path of the resolve step: coverage of the S x S samples of target cell (ti,tj) by the polygon of
 // cell (ci,cj) = (ti+di, tj+dj), recomputed from scratch (exact for any reach < 1 pixel)
 template< int S >
-__device__ __noinline__ void window_coverage( const uint16_t* keys, const uint32_t* cols, int x0, int y0, const uint8_t* frame, int width, int height,
+__device__ __noinline__ void window_coverage( const uint32_t* keys, const uint32_t* cols, int x0, int y0, const uint8_t* frame, int width, int height,
                                               int widthstep, const CellRecord* rec, int ci, int cj, int di, int dj, bool subdivide, uint32_t* win )
 {
     typedef Cfg< S > C;
@@ -407,7 +406,7 @@ __device__ __noinline__ void window_coverage( const uint16_t* keys, const uint32
 // Exact resolve of a whole tile: every candidate's coverage of every pixel recomputed from its polygon.  Only runs
 // for tiles that contain a cell reaching beyond its mask, or under PAR_FLAG_DEBUG_WIDE.
 template< int S, int A, int FMT >
-__device__ __noinline__ void resolve_tile_exact( const uint16_t* keys, const uint32_t* cols, int x0, int y0, const uint8_t* frame, int width, int height,
+__device__ __noinline__ void resolve_tile_exact( const uint32_t* keys, const uint32_t* cols, int x0, int y0, const uint8_t* frame, int width, int height,
                                                  int widthstep, const CellRecord* rec, bool subdivide, uint8_t* out, bool flip )
 {
     typedef Cfg< S > C;
@@ -444,12 +443,13 @@ __device__ __noinline__ void resolve_tile_exact( const uint16_t* keys, const uin
     }
 }
 
-// General path of the mask pass: one thread per queued cell; polygon -> per-thread vertex buffer -> edge loop.  Only runs
-// for the few cells the smoothing tables cannot express (or all smoothed cells under PAR_FLAG_NO_SMOOTH_TABLES).
+// General path of the mask pass: one thread per queued cell (a bit per cell in `workbits`, a word per warp and round of
+// the mask pass); polygon -> per-thread vertex buffer -> edge loop.  Only runs for the few cells the smoothing tables
+// cannot express (or all smoothed cells under PAR_FLAG_NO_SMOOTH_TABLES).  Out of line, with its vertex buffer in local
+// memory: the common path pays neither its registers nor its code nor shared memory.
 template< int S >
-__device__ __noinline__ void geometric_cells( const uint16_t* keys, const uint32_t* cols, uint32_t* s_mask, const uint16_t* s_work, uint16_t* s_vbuf, int* s_nwork,
-                                              int x0, int y0, const uint8_t* frame, int width, int height, int widthstep, const CellRecord* rec,
-                                              uint32_t force_wide )
+__device__ __noinline__ void geometric_cells( const uint32_t* keys, const uint32_t* cols, uint32_t* s_mask, const uint32_t* workbits, int* s_nwork, int x0, int y0,
+                                              const uint8_t* frame, int width, int height, int widthstep, const CellRecord* rec, uint32_t force_wide )
 {
     typedef Cfg< S > C;
     TileEnv< S > env;
@@ -462,21 +462,19 @@ __device__ __noinline__ void geometric_cells( const uint16_t* keys, const uint32
     env.img.height = height;
     env.img.widthstep = widthstep;
     const CellTablePtrs tab{ rec };
-    const int tid = threadIdx.x;
-    const int n_work = *s_nwork;
-    uint16_t* vbuf = s_vbuf + tid;
-    for( int w = tid; w < n_work && tid < kGeoThreads; w += kGeoThreads )
+    uint16_t verts[ kMaxVerts ];
+    for( int idx = threadIdx.x; idx < C::NC; idx += kThreads )
     {
-        const int idx = s_work[ w ];
+        if( !( ( workbits[ idx >> 5 ] >> ( idx & 31 ) ) & 1u ) ) continue;
         int cy = idx / C::CW, cx = idx - cy * C::CW;
         int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
-        PackedSlots slots{ vbuf, kGeoThreads };
-        const CellPoly poly = build_cell_polygon( env, tab, gx, gy, keys[ ( cy + 1 ) * C::KW + cx + 1 ], true, slots );
+        PackedSlots slots{ verts, 1 };
+        const CellPoly poly = build_cell_polygon( env, tab, gx, gy, keys[ ( cy + 1 ) * C::KP + cx + 1 ] & 0xFFFu, true, slots );
         int lo, hi;
         if constexpr( C::PACK )
         {
             PackedToggle< C::R > tg{ 0ull };
-            cover_polygon< S, C::R >( vbuf, kGeoThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
+            cover_polygon< S, C::R >( verts, 1, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
             // reach check: every sample outside the mask must be strictly outside the polygon's bounding box
             const uint32_t wide = ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
             uint2 wm = to_window< S >( tg.m );
@@ -490,7 +488,7 @@ __device__ __noinline__ void geometric_cells( const uint16_t* keys, const uint32
 #pragma unroll
             for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] = 0u;
             RowToggle tg{ s_mask + idx, C::NC };
-            cover_polygon< S, C::R >( vbuf, kGeoThreads, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
+            cover_polygon< S, C::R >( verts, 1, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
             const uint32_t wide = ( lo <= -C::REACH || hi >= C::SQUARE + C::REACH ) ? C::WIDE : force_wide;
             s_mask[ idx ] |= wide;
             if( wide ) s_nwork[ 2 ] = 1;
@@ -543,6 +541,11 @@ struct Entry
 {
     static constexpr int EW = Cfg< S >::PACK ? 1 : ( Cfg< S >::R * 2 + 7 ) / 8;
     static constexpr uint64_t FLAG = Cfg< S >::PACK ? ( ( uint64_t )Cfg< S >::WIDE << 32 ) : ( 1ull << 15 );
+    // link table only: the neighbour's record does not fit the class (its end / start vertex is not the blended vertex, or it
+    // has no edge in that direction) — the cell takes the geometric path.  A bit no mask uses: bit 13 of the corner field
+    // (window form) / bit 14 of row 0 (rows are at most 14 samples wide).
+    static constexpr uint64_t MISMATCH = Cfg< S >::PACK ? ( 1ull << 61 ) : ( 1ull << 14 );
+    static_assert( Cfg< S >::PACK || Cfg< S >::R <= 14, "bit 14 of a row is free" );
 };
 
 // coverage of the closed polygon (xs[k], ys[k]), k < m (1/64 px, cell-local), as a table entry
@@ -642,15 +645,22 @@ __device__ __forceinline__ Q2 point_of_code( int code )
     return q;
 }
 
-// LINK[class][a][b]: the loop between the hull path and the smoothed path around one shared edge
-// (subdivision_functions.cu:603-647 for the two blended vertices, see smooth_table.h)
+// LINK[class][ID]: the loop between the hull path and the smoothed path around one shared edge
+// (subdivision_functions.cu:603-647 for the two blended vertices, see smooth_table.h), for the neighbour record the ID
+// names; MISMATCH when that record's end / start vertex is not the class's blended vertex (getPointIndex's fallback, :527-538)
 template< int S >
 __global__ void build_link_table_kernel( const LinkClass* classes, uint64_t* link )
 {
-    const LinkClass c = classes[ blockIdx.x ];
-    const int sub = threadIdx.x;                 // = rank a | rank b << 2 (a class with one blended end ignores the other rank)
-    uint64_t* entry = link + ( size_t )( c.block * 16u + sub ) * Entry< S >::EW;
-    const int a = c.after[ sub & 3 ], b = c.before[ sub >> 2 ];
+    const LinkClass& c = classes[ blockIdx.x ];
+    const int id = threadIdx.x;
+    uint64_t* entry = link + ( size_t )( c.block * ( uint32_t )kNbrIds + id ) * Entry< S >::EW;
+    const uint32_t r = c.nrec[ id ];
+    if( id == 0 || r == 0xFFFFu || ( c.hasA && ( ( r >> 8 ) & 15u ) != c.codeA ) || ( c.hasB && ( ( r >> 12 ) & 15u ) != c.codeB ) )
+    {
+        for( int w = 0; w < Entry< S >::EW; w++ ) entry[ w ] = w == 0 ? Entry< S >::MISMATCH : 0ull;
+        return;
+    }
+    const int a = c.after[ r & 3u ], b = c.before[ ( r >> 4 ) & 3u ]; // (a class with one blended end ignores the other rank)
     const int di = edge_di( c.e ), dj = edge_dj( c.e );
     const Q2 P0{ c.px[ 0 ], c.py[ 0 ] }, P1{ c.px[ 1 ], c.py[ 1 ] }, P2{ c.px[ 2 ], c.py[ 2 ] }, P3{ c.px[ 3 ], c.py[ 3 ] };
     int xs[ 6 ], ys[ 6 ], m = 0;
@@ -696,48 +706,45 @@ __global__ void build_link_table_kernel( const LinkClass* classes, uint64_t* lin
     cover_to_entry< S >( xs, ys, m, entry );
 }
 
-// NS link descriptors of a smoothed cell, without branches (the loads of the slots overlap; an unused slot (0)
-// compares nothing and loads nothing): XORs their LINK entries into m, ORs word 0 of the entries into `flags`, returns
-// the mismatch bits (non-zero: a blended vertex is not the end / start of the neighbour's edge).
+// NS link descriptors of a smoothed cell (12 bits each in `desc`, smooth_table.h), without branches: XORs their LINK
+// entries into m and ORs word 0 of the entries into `flags` (WIDE and MISMATCH travel there).  The neighbour's record is
+// named by a 5-bit ID that sits in the neighbour's cell word: one shared-memory load of the half that holds the field of
+// direction 7 - e, one shift — no neighbour record is gathered, and a neighbour without an edge in that direction has ID 0,
+// whose entry is MISMATCH.
 template< int S, int NS >
-__device__ __forceinline__ uint32_t link_slots( const SmoothTablePtrs& st, const uint16_t* keys_at_cell, const uint32_t* links, uint64_t* m, uint64_t& flags )
+__device__ __forceinline__ void link_slots( const SmoothTablePtrs& st, const uint32_t* words_at_cell, uint32_t desc, uint64_t* m, uint64_t& flags )
 {
     typedef Cfg< S > C;
     typedef Entry< S > E;
-    uint32_t nb[ NS ];
 #pragma unroll
     for( int k = 0; k < NS; k++ )
     {
-        const uint32_t d = links[ k ];
+        const uint32_t d = desc >> ( 12 * k );
         const uint32_t e = d & 7u;
-        // neighbour across graph edge e: offset in the key tile, one signed byte per edge
-        constexpr int KW = C::KW;
-        constexpr uint32_t off_lo = ( uint32_t )( uint8_t )( KW - 1 ) | ( uint32_t )( uint8_t )( KW ) << 8 | ( uint32_t )( uint8_t )( KW + 1 ) << 16 |
+        const bool used = ( d >> 11 ) & 1u;
+        // neighbour across graph edge e: offset of the word of its cell that holds the ID for direction 7 - e (the x-word:
+        // directions 4..7 = e < 4, the y-word, KW words further: directions 0..3 = e >= 4), one signed byte per edge; and
+        // the field's shift
+        constexpr int KP = C::KP, KW = C::KW;
+        constexpr uint32_t off_lo = ( uint32_t )( uint8_t )( KP - 1 ) | ( uint32_t )( uint8_t )( KP ) << 8 | ( uint32_t )( uint8_t )( KP + 1 ) << 16 |
                                     ( uint32_t )( uint8_t )( -1 ) << 24;
-        constexpr uint32_t off_hi = ( uint32_t )( uint8_t )( 1 ) | ( uint32_t )( uint8_t )( -KW - 1 ) << 8 | ( uint32_t )( uint8_t )( -KW ) << 16 |
-                                    ( uint32_t )( uint8_t )( -KW + 1 ) << 24;
-        const int koff = ( int )( int8_t )__byte_perm( off_lo, off_hi, e );
-        const uint32_t nkey = keys_at_cell[ koff ];
-        nb[ k ] = ( d >> 16 ) ? ( uint32_t )__ldg( &st.rec[ nkey ].nbr[ e ^ 7u ] ) : 0u; // (an unused slot loads nothing)
-    }
-    uint32_t mismatch = 0u;
-#pragma unroll
-    for( int k = 0; k < NS; k++ )
-    {
-        const uint32_t d = links[ k ], r = nb[ k ];
-        const uint32_t ends = ( d >> 16 ) & 255u;
-        mismatch |= ( ( r ^ d ) >> 8 ) & ends; // the blended vertices must be the end (A) / start (B) of the neighbour's edge
-        const uint32_t sub = r & ends; // rank a | rank b << 4 -> the class's 4 x 4 block (one 128-byte line at s <= 4)
-        const uint64_t* le = st.link + ( size_t )( ( d >> 24 ) * 16u + ( ( sub & 3u ) | ( ( sub >> 2 ) & 12u ) ) ) * E::EW;
+        constexpr uint32_t off_hi = ( uint32_t )( uint8_t )( KW + 1 ) | ( uint32_t )( uint8_t )( -KP + KW - 1 ) << 8 | ( uint32_t )( uint8_t )( -KP + KW ) << 16 |
+                                    ( uint32_t )( uint8_t )( -KP + KW + 1 ) << 24;
+        static_assert( KP + 1 < 128, "word offsets fit a signed byte" );
+        constexpr uint32_t sh_lo = 27u | 22u << 8 | 17u << 16 | 12u << 24, sh_hi = 15u | 10u << 8 | 5u << 16 | 0u << 24;
+        const int woff = ( int )( int8_t )__byte_perm( off_lo, off_hi, e );
+        const uint32_t shift = __byte_perm( sh_lo, sh_hi, e ) & 255u;
+        const uint32_t id = ( words_at_cell[ woff ] >> shift ) & 31u;
+        const uint64_t* le = st.link + ( size_t )( ( ( d << 2 ) & ( 255u * ( uint32_t )kNbrIds ) ) | id ) * E::EW;
+        static_assert( kNbrIds == 32, "block << 5 | id" );
 #pragma unroll
         for( int w = 0; w < E::EW; w++ )
         {
-            const uint64_t v = ( d >> 16 ) ? __ldg( le + w ) : 0ull;
+            const uint64_t v = ldg_u64_if( le + w, used ); // (an unused slot loads nothing)
             if( w == 0 ) flags |= v;
             m[ w ] ^= v;
         }
     }
-    return mismatch;
 }
 
 // (Round 2, measured and dropped — the numbers are under profiles/r2b_*, r2c_*, r2d_*, r2h_*, r2j_*:
@@ -765,15 +772,17 @@ __device__ __forceinline__ uint32_t link_slots( const SmoothTablePtrs& st, const
 //    instead of 124 KB of L1 for the tables.)
 // Mask of a smoothed cell from the tables, FIRST pass: the CUT entry and the first two link descriptors (nine cells in
 // ten have no more).  `more` is set when the key has a third descriptor: the caller marks the cell for
-// smooth_lookup_more.  Returns false when a blended vertex is not a vertex of the neighbour's hull (the reference's
-// getPointIndex fallback) — the caller then takes the geometric path.
+// smooth_lookup_more.  Returns 0 when the mask is complete as it stands (nearly always); otherwise the rare cases as flag
+// bits, with m[0] still carrying whatever the XOR left in the flag positions: E::MISMATCH — a blended vertex is not a vertex
+// of the neighbour's hull (the reference's getPointIndex fallback), or the key is not in the tables: the caller takes the
+// geometric path; E::FLAG — some piece reaches beyond the mask (wide).
 template< int S >
-__device__ __forceinline__ bool smooth_lookup( const SmoothTablePtrs& st, const uint32_t* mask_lut, const uint16_t* keys_at_cell, uint32_t key, uint32_t cflags,
-                                               uint64_t* m, bool& wide, bool& more )
+__device__ __forceinline__ uint64_t smooth_lookup( const SmoothTablePtrs& st, const uint32_t* mask_lut, const uint32_t* keys_at_cell, uint32_t key, uint32_t cflags,
+                                                   uint64_t* m, bool& more )
 {
     typedef Cfg< S > C;
     typedef Entry< S > E;
-    const uint4 rec = __ldg( reinterpret_cast< const uint4* >( st.rec + key ) ); // the four link descriptors
+    const uint32_t head = __ldg( st.head + key ); // the first two link descriptors, the corners with a cut vertex, flags
     uint64_t flags = 0ull;
     if( cflags & 16u ) // checkTJunction's early exit keeps every cut vertex: the plain hull
     {
@@ -792,35 +801,32 @@ __device__ __forceinline__ bool smooth_lookup( const SmoothTablePtrs& st, const 
     }
     else
     {
-        const uint64_t* e = st.cut + ( size_t )( key * 16u + ( cflags & ( rec.x >> 4 ) & 15u ) ) * E::EW; // (only corners with a cut vertex matter)
+        const uint64_t* e = st.cut + ( size_t )( key * 16u + ( cflags & ( head >> 24 ) & 15u ) ) * E::EW; // (only corners with a cut vertex matter)
 #pragma unroll
         for( int w = 0; w < E::EW; w++ ) m[ w ] = __ldg( e + w );
     }
-    bool ok = rec.x != kSmoothSlow;
-    const uint32_t links[ 2 ] = { ok ? rec.x : 0u, rec.y };
-    more = ( rec.z >> 16 ) != 0u; // (descriptors fill the slots from 0)
-    ok = ok && link_slots< S, 2 >( st, keys_at_cell, links, m, flags ) == 0u;
-    // the flag bit of word 0 was XORed along with the masks: restore it from the CUT entry (never wide) and the OR
-    wide = ( flags & E::FLAG ) != 0ull;
-    m[ 0 ] &= ~E::FLAG;
-    return ok;
+    more = ( head & kHeadMore ) != 0u;
+#ifndef PAR_WHATIF_NOLINKS
+    link_slots< S, 2 >( st, keys_at_cell, head, m, flags ); // (a key that always takes the geometric path has no descriptors)
+#else
+    more = false;
+#endif
+    // the flag bits of word 0 were XORed along with the masks: take them from the OR (the CUT entry has none)
+    return ( flags & ( E::FLAG | E::MISMATCH ) ) | ( ( head & kHeadSlow ) ? E::MISMATCH : 0ull );
 }
 
-// SECOND pass, for the cells whose key has three or four link descriptors: the XOR of the remaining LINK entries (flag
-// bit cleared), `wide` from their flags; false on a mismatch as above.
+// SECOND pass, for the cells whose key has three or four link descriptors: the XOR of the remaining LINK entries; returns
+// the rare cases as above.
 template< int S >
-__device__ __forceinline__ bool smooth_lookup_more( const SmoothTablePtrs& st, const uint16_t* keys_at_cell, uint32_t key, uint64_t* m, bool& wide )
+__device__ __forceinline__ uint64_t smooth_lookup_more( const SmoothTablePtrs& st, const uint32_t* keys_at_cell, uint32_t key, uint64_t* m )
 {
     typedef Entry< S > E;
-    const uint2 rec = __ldg( reinterpret_cast< const uint2* >( &st.rec[ key ].link[ 2 ] ) );
-    const uint32_t links[ 2 ] = { rec.x, rec.y };
+    const uint32_t head2 = __ldg( st.head2 + key );
     uint64_t flags = 0ull;
 #pragma unroll
     for( int w = 0; w < E::EW; w++ ) m[ w ] = 0ull;
-    const bool ok = link_slots< S, 2 >( st, keys_at_cell, links, m, flags ) == 0u;
-    wide = ( flags & E::FLAG ) != 0ull;
-    m[ 0 ] &= ~E::FLAG;
-    return ok;
+    link_slots< S, 2 >( st, keys_at_cell, head2, m, flags );
+    return flags & ( E::FLAG | E::MISMATCH );
 }
 
 // palette index of a colour (low 24 bits of a colour word) in the frame's lookup table (palette_kernels.cu): 1024 slots of
@@ -846,12 +852,10 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
 {
     typedef Cfg< S > C;
     extern __shared__ __align__( 128 ) uint8_t smem[];
-    uint8_t* s_graph = smem + C::off_graph;
-    uint16_t* s_keys = reinterpret_cast< uint16_t* >( smem + C::off_keys );
+    uint8_t* s_graph = smem + C::off_graph;                                   // (staged rows live in the mask array)
+    uint32_t* s_keys = reinterpret_cast< uint32_t* >( smem + C::off_keys );   // cell words, KP per row: x = key | IDs << 12, then y = IDs
     uint32_t* s_col = reinterpret_cast< uint32_t* >( smem + C::off_col );
     uint32_t* s_mask = reinterpret_cast< uint32_t* >( smem + C::off_mask );   // PACK: [2][NC]; rows: [R][NC]
-    uint16_t* s_vbuf = reinterpret_cast< uint16_t* >( smem + C::off_vbuf );   // [kMaxVerts][kGeoThreads]
-    uint16_t* s_work = reinterpret_cast< uint16_t* >( smem + C::off_work );   // cells that need the general path
     int* s_nwork = reinterpret_cast< int* >( smem + C::off_nwork );
     uint64_t* s_bar = reinterpret_cast< uint64_t* >( smem + C::off_bar );
 
@@ -862,7 +866,11 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     const uint8_t* graph = a.graph + ( size_t )f * frame_px;
 
     // (1) stage graph bytes: rows y0-2 .. y0+TH+1, columns x0-16 .. x0-16+GP-1; zero outside the image
+    constexpr int kRounds = ( C::NC + kThreads - 1 ) / kThreads;     // rounds of the mask pass
+    uint32_t* s_more = reinterpret_cast< uint32_t* >( s_nwork + 4 ); // [kRounds][8 warps]: the cells of a round with a third link, as ballots
+    uint32_t* s_geo = s_more + kRounds * ( kThreads / 32 );          // a bit per cell (idx): queued for the geometric path
     if( tid < 3 ) s_nwork[ tid ] = 0; // [0] geometric work items, [1] smoothed cells (statistics), [2] some cell of the tile is wide
+    if( tid < kRounds * ( kThreads / 32 ) ) s_geo[ tid ] = 0u;
     if( kUseTma )
     {
         if( tid == 0 )
@@ -913,6 +921,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
         w &= 0x00FFFFFFu;
         return pal_lut ? ( w | palette_index( pal_lut, w ) << 24 ) : w;
     };
+    const uint2* pack_tab = ( a.smooth.cut != nullptr && !a.debug_force_wide ) ? a.smooth.pack : nullptr;
     if( kUseTma )
     {
         // Four pixels per thread from aligned 32-bit words of the staged rows: byte permutes build the RGBA words
@@ -946,7 +955,19 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
             const uint32_t node = __byte_perm( g0, g1, 0x5432 ), left = __byte_perm( g0, g1, 0x4321 ), right = __byte_perm( g0, g1, 0x6543 );
             const uint32_t high = ( ( left >> 2 ) & 0x01010101u ) | ( ( left >> 6 ) & 0x02020202u ) | ( ( right << 2 ) & 0x04040404u ) |
                                   ( ( right >> 2 ) & 0x08080808u ); // cell_key's bits 8..11, one byte per cell
-            *reinterpret_cast< uint2* >( s_keys + cy * C::KW + 4 * q ) = make_uint2( __byte_perm( node, high, 0x5140 ), __byte_perm( node, high, 0x7362 ) );
+            const uint32_t k01 = __byte_perm( node, high, 0x5140 ), k23 = __byte_perm( node, high, 0x7362 );
+            uint32_t kw[ 4 ] = { k01 & 0xFFFFu, k01 >> 16, k23 & 0xFFFFu, k23 >> 16 };
+            uint32_t* kd = s_keys + cy * C::KP + 4 * q;
+            if( pack_tab ) // the IDs of the cell's records, for the neighbours that will read these words (smooth_table.h)
+            {
+                uint2 cw[ 4 ];
+#pragma unroll
+                for( int k = 0; k < 4; k++ ) cw[ k ] = __ldg( pack_tab + kw[ k ] );
+#pragma unroll
+                for( int k = 0; k < 4; k++ ) kw[ k ] |= cw[ k ].x;
+                *reinterpret_cast< uint4* >( kd + C::KW ) = make_uint4( cw[ 0 ].y, cw[ 1 ].y, cw[ 2 ].y, cw[ 3 ].y );
+            }
+            *reinterpret_cast< uint4* >( kd ) = make_uint4( kw[ 0 ], kw[ 1 ], kw[ 2 ], kw[ 3 ] );
         }
     }
     else
@@ -971,7 +992,10 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
         {
             int ky = idx / C::KW, kx = idx - ky * C::KW;
             const uint8_t* g = s_graph + ky * C::GP + kx + C::GOFF - 2; // column x0-2+kx sits at staged column kx+GOFF-2
-            s_keys[ idx ] = ( uint16_t )cell_key( g[ 0 ], g[ -1 ], g[ 1 ] );
+            const uint32_t key = cell_key( g[ 0 ], g[ -1 ], g[ 1 ] );
+            const uint2 ids = pack_tab ? __ldg( pack_tab + key ) : make_uint2( 0u, 0u );
+            s_keys[ ky * C::KP + kx ] = ids.x | key;
+            s_keys[ ky * C::KP + C::KW + kx ] = ids.y;
         }
     }
     __syncthreads();
@@ -997,8 +1021,6 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     // (Compacting the smoothed cells into a list first, so that the lookups run with full warps, was 3 % slower on the
     // busy frames of the bench — 83 % of the cells are smoothed — and 9 % faster on frames of flat 4 x 4 blocks.)
     int n_smoothed = 0;
-    constexpr int kRounds = ( C::NC + kThreads - 1 ) / kThreads;
-    uint32_t* s_more = reinterpret_cast< uint32_t* >( s_nwork + 4 ); // [kRounds][8 warps]: the cells of a round with a third link, as ballots
     const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll 1
     for( int round = 0; round < kRounds; round++ ) // (whole warps: the vote at the end needs every lane)
@@ -1008,8 +1030,8 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
         int cy = idx / C::CW, cx = idx - cy * C::CW;
         int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
         const bool inside = gx >= 0 && gy >= 0 && gx < a.width && gy < a.height;
-        const uint16_t* kc = s_keys + ( cy + 1 ) * C::KW + cx + 1;
-        const uint32_t key = idx < C::NC ? *kc : 90u;
+        const uint32_t* kc = s_keys + ( cy + 1 ) * C::KP + cx + 1;
+        const uint32_t key = idx < C::NC ? ( *kc & 0xFFFu ) : 90u;
         const bool plain = !subdivide || ( key & 0xFFu ) == 90u;
         if( idx >= C::NC )
             ;
@@ -1018,7 +1040,12 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
             n_smoothed++;
             // checkTJunction for the four corners of the pixel square (bit c: corner c stays), 16 = its early exit
             uint32_t cf = 16u;
+#ifdef PAR_WHATIF_CF
+            cf = key & 15u;
+            if( false )
+#else
             if( !env.guard( gx, gy ) )
+#endif
             {
                 const uint32_t* c = s_col + ( cy + 1 ) * C::KW + ( cx + 1 );
                 const uint32_t l = c[ -1 ], r = c[ 1 ], d = c[ -C::KW ], u = c[ C::KW ];
@@ -1026,30 +1053,40 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
                 cf = ( ( l != dl || dl != d ) ? 1u : 0u ) | ( ( r != dr || dr != d ) ? 2u : 0u ) | ( ( r != ur || ur != u ) ? 4u : 0u ) |
                      ( ( l != ul || ul != u ) ? 8u : 0u );
             }
-            uint64_t mw[ Entry< S >::EW ];
-            bool wide = false, more = false;
-            if( use_tables && smooth_lookup< S >( a.smooth, a.mask_lut, kc, key, cf, mw, wide, more ) )
+            typedef Entry< S > E;
+            uint64_t mw[ E::EW ];
+            bool more = false;
+            const uint64_t rare = use_tables ? smooth_lookup< S >( a.smooth, a.mask_lut, kc, key, cf, mw, more ) : E::MISMATCH;
+            if( rare & E::MISMATCH ) // (rare: queued for the geometric path, a bit per cell)
+            {
+                atomicOr( &s_geo[ idx >> 5 ], 1u << ( idx & 31 ) );
+                atomicAdd( s_nwork, 1 );
+            }
+            else
             {
                 third_link = more;
+                uint32_t wide = 0u;
+                if( rare ) // (rare: some piece reaches beyond the mask)
+                {
+                    mw[ 0 ] &= ~( E::FLAG | E::MISMATCH );
+                    wide = C::WIDE;
+                    s_nwork[ 2 ] = 1;
+                }
                 if( C::PACK )
                 {
                     s_mask[ idx ] = ( uint32_t )mw[ 0 ];
-                    s_mask[ C::NC + idx ] = ( uint32_t )( mw[ 0 ] >> 32 ) | ( wide ? C::WIDE : 0u );
-                    if( wide ) s_nwork[ 2 ] = 1;
+                    s_mask[ C::NC + idx ] = ( uint32_t )( mw[ 0 ] >> 32 ) | wide;
                 }
                 else
                 {
 #pragma unroll
                     for( int r = 0; r < C::R; r++ )
                     {
-                        const uint32_t row = ( uint32_t )( mw[ r >> 2 ] >> ( 16 * ( r & 3 ) ) ) & 0x7FFFu;
-                        s_mask[ r * C::NC + idx ] = row | ( ( r == 0 && wide ) ? C::WIDE : 0u );
+                        const uint32_t row = ( uint32_t )( mw[ r >> 2 ] >> ( 16 * ( r & 3 ) ) ) & 0xFFFFu;
+                        s_mask[ r * C::NC + idx ] = row | ( r == 0 ? wide : 0u );
                     }
-                    if( wide ) s_nwork[ 2 ] = 1;
                 }
             }
-            else
-                s_work[ warp_slot( s_nwork ) ] = ( uint16_t )idx;
         }
         else if( C::PACK )
         {
@@ -1085,6 +1122,9 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
             votes[ r ] = s_more[ r * ( kThreads / 32 ) + warp ];
             total += __popc( votes[ r ] );
         }
+#ifdef PAR_WHATIF_NOSECOND
+        total = 0;
+#endif
         for( int j = lane; j < total; j += 32 ) // lane j takes the j-th marked cell
         {
             int skip = j, round = 0;
@@ -1103,24 +1143,37 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
             for( ; skip > 0; skip-- ) word &= word - 1u;
             const int idx = round * kThreads + warp * 32 + ( __ffs( ( int )word ) - 1 );
             const int cy = idx / C::CW, cx = idx - cy * C::CW;
-            const uint16_t* kc = s_keys + ( cy + 1 ) * C::KW + cx + 1;
-            uint64_t mw[ Entry< S >::EW ];
-            bool wide = false;
-            const bool ok = smooth_lookup_more< S >( a.smooth, kc, *kc, mw, wide );
+            const uint32_t* kc = s_keys + ( cy + 1 ) * C::KP + cx + 1;
+            typedef Entry< S > E;
+            uint64_t mw[ E::EW ];
+            const uint64_t rare = smooth_lookup_more< S >( a.smooth, kc, *kc & 0xFFFu, mw );
+            uint32_t wide = 0u;
+            if( rare )
+            {
+                mw[ 0 ] &= ~( E::FLAG | E::MISMATCH );
+                if( rare & E::FLAG )
+                {
+                    wide = C::WIDE;
+                    s_nwork[ 2 ] = 1;
+                }
+                if( rare & E::MISMATCH ) // the geometric path rebuilds the whole mask
+                {
+                    atomicOr( &s_geo[ idx >> 5 ], 1u << ( idx & 31 ) );
+                    atomicAdd( s_nwork, 1 );
+                }
+            }
             if( C::PACK )
             {
                 s_mask[ idx ] ^= ( uint32_t )mw[ 0 ];
-                s_mask[ C::NC + idx ] ^= ( uint32_t )( mw[ 0 ] >> 32 );
-                if( wide ) s_mask[ C::NC + idx ] |= C::WIDE;
+                const uint32_t hi = s_mask[ C::NC + idx ] ^ ( uint32_t )( mw[ 0 ] >> 32 );
+                s_mask[ C::NC + idx ] = hi | wide;
             }
             else
             {
 #pragma unroll
-                for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] ^= ( uint32_t )( mw[ r >> 2 ] >> ( 16 * ( r & 3 ) ) ) & 0x7FFFu;
-                if( wide ) s_mask[ idx ] |= C::WIDE;
+                for( int r = 0; r < C::R; r++ ) s_mask[ r * C::NC + idx ] ^= ( uint32_t )( mw[ r >> 2 ] >> ( 16 * ( r & 3 ) ) ) & 0xFFFFu;
+                if( wide ) s_mask[ idx ] |= wide;
             }
-            if( wide ) s_nwork[ 2 ] = 1;
-            if( !ok ) s_work[ warp_slot( s_nwork ) ] = ( uint16_t )idx; // the geometric path rebuilds the whole mask
         }
     }
     if( a.smooth_stats ) // (statistics for the bench line)
@@ -1133,7 +1186,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     // (2b) general path, out of line (rarely runs: it costs the common path neither registers nor code)
     if( *s_nwork != 0 )
     {
-        geometric_cells< S >( s_keys, s_col, s_mask, s_work, s_vbuf, s_nwork, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, force_wide );
+        geometric_cells< S >( s_keys, s_col, s_mask, s_geo, s_nwork, x0, y0, frame, a.width, a.height, a.widthstep, tab.rec, force_wide );
         __syncthreads(); // (uniform: the counter is final since the barrier before this pass)
     }
     if( a.smooth_stats && tid == 0 )
@@ -1180,7 +1233,11 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
             cov[ 3 ] = ( mlo[ 1 ] >> 16 ) & C::M_RIGHTCOL;
             cov[ 4 ] = mlo[ 0 ] & C::ALL;
             if( C::H == 0 ) cov[ 0 ] = cov[ 1 ] = cov[ 2 ] = cov[ 3 ] = 0u; // no halo samples at this scale
+#ifdef PAR_WHATIF_FASTRES
+            if( ( cov[ 4 ] & ~( cov[ 0 ] | cov[ 1 ] | cov[ 2 ] | cov[ 3 ] ) ) == 0x12345u )
+#else
             if( ( cov[ 4 ] & ~( cov[ 0 ] | cov[ 1 ] | cov[ 2 ] | cov[ 3 ] ) ) != C::ALL )
+#endif
             {
                 cov[ 5 ] = ( mlo[ -1 ] >> 16 ) & C::M_LEFTCOL;
                 cov[ 6 ] = ( mhi[ -C::CW + 1 ] >> 16 ) & ( 1u << ( S - 1 ) );
@@ -1213,6 +1270,12 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
                 }
             }
             uint8_t* dst = out + ( ( size_t )( a.flip_output ? out_h - 1 - ( size_t )gy * O : ( size_t )gy * O ) * out_w + ( size_t )gx * O ) * BPP;
+#ifdef PAR_WHATIF_NOSTORE
+            uint32_t acc = 0u;
+#pragma unroll
+            for( int k = 0; k < S * S; k++ ) acc += px[ k ] * ( k + 1 );
+            if( acc == 0x12345u )
+#endif
             store_cell< S, A, FMT >( dst, row_step, px );
         }
     }

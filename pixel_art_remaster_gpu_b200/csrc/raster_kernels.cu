@@ -141,8 +141,8 @@ cudaError_t launch_build_smooth_tables( int scale, const CellTablePtrs& tab, con
 {
 #define PAR_BUILD_SMOOTH( S )                                                                        \
     build_cut_table_kernel< S ><<< kCellKeys * 16 / 128, 128, 0, stream >>>( tab, cut );             \
-    cudaMemsetAsync( link, 0, 16 * Entry< S >::EW * sizeof( uint64_t ), stream ); /* block 0: the all-zero block */ \
-    build_link_table_kernel< S ><<< n_classes, 16, 0, stream >>>( d_classes, link );                 \
+    cudaMemsetAsync( link, 0, kNbrIds * Entry< S >::EW * sizeof( uint64_t ), stream ); /* block 0: the all-zero block */ \
+    build_link_table_kernel< S ><<< n_classes, kNbrIds, 0, stream >>>( d_classes, link );            \
     return cudaGetLastError()
     PAR_FOR_SCALE( scale, PAR_BUILD_SMOOTH )
 #undef PAR_BUILD_SMOOTH

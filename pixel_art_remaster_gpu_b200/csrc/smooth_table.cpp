@@ -1,6 +1,7 @@
 // Host-side construction of the smoothing tables (see smooth_table.h): per key the link descriptors, per
 // (key, link direction) the neighbour record, and the list of link classes the device turns into masks.
 #include "smooth_table.h"
+#include <algorithm>
 #include <map>
 #include <string.h>
 #include <tuple>
@@ -36,7 +37,7 @@ void build_smooth_tables( const CellTables& cells, SmoothTables* out )
 {
     memset( out->rec, 0, sizeof( out->rec ) );
     out->classes.clear();
-    out->link_entries = 16; // block 0: the all-zero block unused descriptor slots point at
+    out->link_entries = kNbrIds; // block 0: the all-zero block
     out->slow_keys = 0;
     typedef std::tuple< int, int, int, int, int, int, int, int, int, int, int > ClassKey; // e, hasA, hasB, 4 x (x, y)
     std::map< ClassKey, uint32_t > class_block;
@@ -132,15 +133,17 @@ void build_smooth_tables( const CellTables& cells, SmoothTables* out )
                     c.after[ k ] = ( int8_t )after_code[ 7 - h.link[ t ] ][ k ];
                     c.before[ k ] = ( int8_t )before_code[ 7 - h.link[ t ] ][ k ];
                 }
-                c.block = out->link_entries / 16;
-                out->link_entries += 16;
+                c.codeA = ( uint8_t )( hasA ? codeA : 0u );
+                c.codeB = ( uint8_t )( hasB ? codeB : 0u );
+                c.block = out->link_entries / kNbrIds;
+                out->link_entries += kNbrIds;
                 out->classes.push_back( c );
                 it = class_block.insert( std::make_pair( ck, c.block ) ).first;
             }
             links[ n_links++ ] = ( uint32_t )h.link[ t ] | ( ( hasA ? codeA : 0u ) | ( hasB ? codeB << 4 : 0u ) ) << 8 |
                                  ( ( hasA ? 0x0Fu : 0u ) | ( hasB ? 0xF0u : 0u ) ) << 16 | it->second << 24;
         }
-        if( slow || !ranks_ok || n_links > kMaxLinks || out->link_entries / 16 > 255 )
+        if( slow || !ranks_ok || n_links > kMaxLinks || out->link_entries / kNbrIds > 255 )
         {
             out->rec[ key ].link[ 0 ] = kSmoothSlow;
             out->slow_keys++;
@@ -176,6 +179,61 @@ void build_smooth_tables( const CellTables& cells, SmoothTables* out )
     }
     if( out->slow_keys == ( uint32_t )kCellKeys )
         for( unsigned key = 0; key < ( unsigned )kCellKeys; key++ ) out->rec[ key ].link[ 0 ] = kSmoothSlow;
+
+    // ---- the kernel's view: IDs of the neighbour records, HEAD / HEAD2 / PACK words, per-class ID -> record lists ----
+    uint16_t id_rec[ 8 ][ kNbrIds ];
+    int n_ids[ 8 ];
+    bool ids_ok = true;
+    for( int e = 0; e < 8; e++ )
+    {
+        n_ids[ e ] = 1; // ID 0: no hull edge through this direction
+        for( int k = 0; k < kNbrIds; k++ ) id_rec[ e ][ k ] = 0xFFFFu;
+        // the direction's different records in ascending order: the end / start codes are the high bits, so the records a
+        // class accepts (those with its blended vertices) are neighbours in the class's block of the link table
+        std::vector< uint16_t > recs;
+        for( unsigned key = 0; key < ( unsigned )kCellKeys; key++ )
+            if( has_edge[ key ][ e ] ) recs.push_back( out->rec[ key ].nbr[ e ] );
+        std::sort( recs.begin(), recs.end() );
+        recs.erase( std::unique( recs.begin(), recs.end() ), recs.end() );
+        if( recs.size() >= ( size_t )kNbrIds )
+        {
+            ids_ok = false;
+            recs.resize( kNbrIds - 1 );
+        }
+        for( size_t k = 0; k < recs.size(); k++ ) id_rec[ e ][ n_ids[ e ]++ ] = recs[ k ];
+        for( unsigned key = 0; key < ( unsigned )kCellKeys; key++ )
+        {
+            out->nbr_id[ key ][ e ] = 0;
+            if( !has_edge[ key ][ e ] ) continue;
+            for( int k = 1; k < n_ids[ e ]; k++ )
+                if( id_rec[ e ][ k ] == out->rec[ key ].nbr[ e ] ) out->nbr_id[ key ][ e ] = ( uint8_t )k;
+            if( !out->nbr_id[ key ][ e ] ) ids_ok = false;
+        }
+    }
+    for( LinkClass& c : out->classes )
+        for( int k = 0; k < kNbrIds; k++ ) c.nrec[ k ] = id_rec[ 7 - c.e ][ k ];
+    for( unsigned key = 0; key < ( unsigned )kCellKeys; key++ )
+    {
+        const SmoothRecord& r = out->rec[ key ];
+        out->pack[ key ][ 0 ] = out->pack[ key ][ 1 ] = 0u;
+        for( int e = 0; e < 4; e++ )
+        {
+            out->pack[ key ][ 0 ] |= ( uint32_t )out->nbr_id[ key ][ 4 + e ] << ( 12 + 5 * e );
+            out->pack[ key ][ 1 ] |= ( uint32_t )out->nbr_id[ key ][ e ] << ( 5 * e );
+        }
+        uint32_t w[ 2 ] = { 0u, 0u };
+        if( r.link[ 0 ] == kSmoothSlow || !ids_ok )
+            w[ 0 ] = kHeadSlow;
+        else
+        {
+            for( int k = 0; k < kMaxLinks; k++ )
+                if( r.link[ k ] >> 16 ) w[ k >> 1 ] |= ( ( r.link[ k ] & 7u ) | ( r.link[ k ] >> 24 ) << 3 | 1u << 11 ) << ( 12 * ( k & 1 ) );
+            w[ 0 ] |= ( ( r.link[ 0 ] >> 4 ) & 15u ) << 24;
+            if( w[ 1 ] ) w[ 0 ] |= kHeadMore;
+        }
+        out->head[ key ] = w[ 0 ];
+        out->head2[ key ] = w[ 1 ];
+    }
 }
 
 } // namespace par

@@ -56,6 +56,26 @@ struct SmoothRecord
     uint16_t nbr[ 8 ];
 };
 
+// What the raster kernel reads (round 3: the records above are only the host-side source of these).
+//
+// * HEAD[key] / HEAD2[key] (32 bits each): the key's link descriptors reduced to what the kernel still needs — the
+//   direction e of the neighbour and the class's block of the link table — two descriptors per word:
+//       [0,3) e   [3,11) block   [11] used     (slot 0 / slot 2)
+//       [12,15) e [15,23) block  [23] used     (slot 1 / slot 3)
+//   HEAD only: [24,28) corners (which square corners hold a cut vertex), [28] the key has a third descriptor (HEAD2),
+//   [29] the key always takes the geometric path.
+// * a neighbour record is one of at most 30 different 16-bit values per direction, so it is named by a 5-bit ID
+//   (1..30; 0 = the neighbour has no hull edge shared through that direction).  NBR_ID[key][e'] is that ID, and
+//   PACK[key] = { IDs of directions 4..7 in bits [12 + 5 (e' - 4)), IDs of directions 0..3 in bits [5 e') } is what the
+//   raster kernel keeps per staged cell (the low word ORed onto the 12-bit key): a cell that blends across its link e finds
+//   the ID of its neighbour's record for direction 7 - e in the shared-memory word it would read the neighbour's key from —
+//   no neighbour record is gathered from global memory, and nothing depends on how many links the neighbour has.
+// * the link table has 32 entries per class, indexed by the neighbour's ID: entry = the loop mask for the ranks the ID's
+//   record gives, or the MISMATCH flag when the record's end / start vertex is not the class's blended vertex (the
+//   comparison the kernel used to make per cell is made once, when the table is built).
+constexpr int kNbrIds = 32;
+constexpr uint32_t kHeadSlow = 1u << 29, kHeadMore = 1u << 28;
+
 // geometry of one class, consumed by the device table builder (quarter-pixel units)
 struct LinkClass
 {
@@ -63,12 +83,16 @@ struct LinkClass
     int8_t px[ 4 ], py[ 4 ]; // hull vertices t-1, t, t+1, t+2
     uint32_t block;          // its 16-entry block of the link table (>= 1)
     int8_t after[ 4 ], before[ 4 ]; // rank -> point code of the neighbour's vertex after the edge end / before its start
-    uint32_t pad2;
+    uint8_t codeA, codeB;           // the blended vertices as point codes in the neighbour's frame (what its record must hold)
+    uint16_t pad2;
+    uint16_t nrec[ kNbrIds ];       // ID -> the neighbour's 16-bit record for direction 7 - e (0xFFFF: no such ID)
 };
 
 struct SmoothTables
 {
     SmoothRecord rec[ kCellKeys ];
+    uint32_t head[ kCellKeys ], head2[ kCellKeys ], pack[ kCellKeys ][ 2 ];
+    uint8_t nbr_id[ kCellKeys ][ 8 ];
     std::vector< LinkClass > classes;
     uint32_t link_entries = 0; // total entries of the link table (16 per class + the zero block)
     uint32_t slow_keys = 0;    // keys that always take the geometric path

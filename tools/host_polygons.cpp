@@ -121,7 +121,9 @@ extern "C" void host_smooth_check( const uint8_t* img_zero_tailed, const uint8_t
             cover( poly, S, halo, direct );
             // the pieces, as the kernel assembles them
             const SmoothRecord& rec = ST.rec[ key ];
+            if( ( rec.link[ 0 ] == kSmoothSlow ) != ( ( ST.head[ key ] & kHeadSlow ) != 0u ) ) out[ 2 ]++;
             if( rec.link[ 0 ] == kSmoothSlow ) { out[ 1 ]++; continue; }
+            if( ( ( ST.head[ key ] >> 24 ) & 15u ) != ( ( rec.link[ 0 ] >> 4 ) & 15u ) || ( ( ST.head[ key ] & kHeadMore ) != 0u ) != ( ( rec.link[ 2 ] >> 16 ) != 0u ) ) out[ 2 ]++;
             const uint64_t h = T.rec[ key ].verts, info = T.rec[ key ].info;
             const int n = hull_count( info );
             const VertexClasses cls = classify_vertices( info );
@@ -164,8 +166,20 @@ extern "C" void host_smooth_check( const uint8_t* img_zero_tailed, const uint8_t
                 const uint32_t nkey = env.key( i + edge_di( e ), j + edge_dj( e ) );
                 const uint32_t r = ST.rec[ nkey ].nbr[ e ^ 7 ];
                 const uint32_t ends = ( d >> 16 ) & 255u;
-                if( ( ( r ^ d ) >> 8 ) & ends ) { ok = false; break; }
                 const LinkClass& c = ST.classes[ ( d >> 24 ) - 1 ];
+                {   // the kernel's view of the same lookup (HEAD / PACK / NBR_ID / per-class ID lists) must agree with the records
+                    const uint32_t hd = ( k < 2 ? ST.head[ key ] : ST.head2[ key ] ) >> ( 12 * ( k & 1 ) );
+                    if( ( hd & 7u ) != ( d & 7u ) || ( ( hd >> 3 ) & 255u ) != ( d >> 24 ) || !( ( hd >> 11 ) & 1u ) ) out[ 2 ]++;
+                    static const int shift_of[ 8 ] = { 27, 22, 17, 12, 15, 10, 5, 0 }; // the kernel's: word (e >= 4 ? y : x) >> shift
+                    const uint32_t half = e >= 4 ? ST.pack[ nkey ][ 1 ] : ( nkey | ST.pack[ nkey ][ 0 ] );
+                    const uint32_t id = ( half >> shift_of[ e ] ) & 31u;
+                    if( id != ST.nbr_id[ nkey ][ e ^ 7 ] ) out[ 2 ]++;
+                    const uint32_t r2 = c.nrec[ id ];
+                    const bool mis2 = id == 0u || r2 == 0xFFFFu || ( c.hasA && ( ( r2 >> 8 ) & 15u ) != c.codeA ) || ( c.hasB && ( ( r2 >> 12 ) & 15u ) != c.codeB );
+                    const bool mis = ( ( ( r ^ d ) >> 8 ) & ends ) != 0u;
+                    if( mis != mis2 || ( !mis && ( ( r2 ^ r ) & ends ) != 0u ) ) out[ 2 ]++;
+                }
+                if( ( ( r ^ d ) >> 8 ) & ends ) { ok = false; break; }
                 const uint32_t sub = r & ends;
                 const int di = edge_di( c.e ), dj = edge_dj( c.e );
                 const Q2 P0{ c.px[ 0 ], c.py[ 0 ] }, P1{ c.px[ 1 ], c.py[ 1 ] }, P2{ c.px[ 2 ], c.py[ 2 ] }, P3{ c.px[ 3 ], c.py[ 3 ] };
