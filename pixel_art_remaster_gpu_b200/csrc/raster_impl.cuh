@@ -782,7 +782,7 @@ __device__ __forceinline__ uint64_t smooth_lookup( const SmoothTablePtrs& st, co
 {
     typedef Cfg< S > C;
     typedef Entry< S > E;
-    const uint32_t head = __ldg( st.head + key ); // the first two link descriptors, the corners with a cut vertex, flags
+    const uint32_t head = __ldg( st.head + key ); // the first two link descriptors, flags
     uint64_t flags = 0ull;
     if( cflags & 16u ) // checkTJunction's early exit keeps every cut vertex: the plain hull
     {
@@ -801,7 +801,9 @@ __device__ __forceinline__ uint64_t smooth_lookup( const SmoothTablePtrs& st, co
     }
     else
     {
-        const uint64_t* e = st.cut + ( size_t )( key * 16u + ( cflags & ( head >> 24 ) & 15u ) ) * E::EW; // (only corners with a cut vertex matter)
+        // (the bits of corners without a cut vertex do not matter, and the 16 entries of a key are one 128-byte line at s <= 4:
+        // not masking them off lets the gather start before the descriptors have arrived — 1.2 % on the bench frames)
+        const uint64_t* e = st.cut + ( size_t )( key * 16u + ( cflags & 15u ) ) * E::EW;
 #pragma unroll
         for( int w = 0; w < E::EW; w++ ) m[ w ] = __ldg( e + w );
     }
@@ -1022,6 +1024,9 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     // busy frames of the bench — 83 % of the cells are smoothed — and 9 % faster on frames of flat 4 x 4 blocks.)
     int n_smoothed = 0;
     const int warp = tid >> 5, lane = tid & 31;
+    // checkTJunction's early exit only ever holds on the image's rows 0, 1 and height - 1 (FlatImage::guard): tiles away
+    // from them skip the test
+    const bool tile_may_guard = y0 <= 2 || y0 + C::TH + 1 >= a.height - 1;
 #pragma unroll 1
     for( int round = 0; round < kRounds; round++ ) // (whole warps: the vote at the end needs every lane)
     {
@@ -1029,7 +1034,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
         bool third_link = false;
         int cy = idx / C::CW, cx = idx - cy * C::CW;
         int gx = x0 - 1 + cx, gy = y0 - 1 + cy;
-        const bool inside = gx >= 0 && gy >= 0 && gx < a.width && gy < a.height;
+        const bool inside = ( unsigned )gx < ( unsigned )a.width && ( unsigned )gy < ( unsigned )a.height;
         const uint32_t* kc = s_keys + ( cy + 1 ) * C::KP + cx + 1;
         const uint32_t key = idx < C::NC ? ( *kc & 0xFFFu ) : 90u;
         const bool plain = !subdivide || ( key & 0xFFu ) == 90u;
@@ -1044,7 +1049,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
             cf = key & 15u;
             if( false )
 #else
-            if( !env.guard( gx, gy ) )
+            if( !( tile_may_guard && env.guard( gx, gy ) ) )
 #endif
             {
                 const uint32_t* c = s_col + ( cy + 1 ) * C::KW + ( cx + 1 );
@@ -1140,8 +1145,19 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
                     word = votes[ r + 1 ];
                 }
             }
-            for( ; skip > 0; skip-- ) word &= word - 1u;
-            const int idx = round * kThreads + warp * 32 + ( __ffs( ( int )word ) - 1 );
+            // the skip-th set bit of the ballot (skip < popc), by halving
+            int bitpos = 0;
+#pragma unroll
+            for( int h = 16; h >= 1; h >>= 1 )
+            {
+                const int c = __popc( ( word >> bitpos ) & ( ( 1u << h ) - 1u ) );
+                if( skip >= c )
+                {
+                    skip -= c;
+                    bitpos += h;
+                }
+            }
+            const int idx = round * kThreads + warp * 32 + bitpos;
             const int cy = idx / C::CW, cx = idx - cy * C::CW;
             const uint32_t* kc = s_keys + ( cy + 1 ) * C::KP + cx + 1;
             typedef Entry< S > E;
@@ -1212,10 +1228,16 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     {
         // Window form: every candidate's coverage of my S x S output pixels is one masked 16-bit field of its
         // mask, so the priority resolve runs once on whole-cell bit sets instead of once per output row.
-        for( int idx = tid; idx < C::TW * C::TH; idx += kThreads )
+        // (a thread keeps its column; its output pointer advances by a constant per round instead of being rebuilt)
+        static_assert( C::TW == 32 && kThreads % C::TW == 0, "a warp is one row of the tile" );
+        constexpr int kRowsPerRound = kThreads / C::TW;
+        const int lx = tid & 31, gx = x0 + lx;
+        const int gy0 = y0 + ( tid >> 5 );
+        uint8_t* dst = out + ( ( size_t )( a.flip_output ? out_h - 1 - ( size_t )gy0 * O : ( size_t )gy0 * O ) * out_w + ( size_t )gx * O ) * BPP;
+        const ptrdiff_t round_step = row_step * ( kRowsPerRound * O );
+        for( int ly = tid >> 5; ly < C::TH; ly += kRowsPerRound, dst += round_step )
         {
-            int ly = idx / C::TW, lx = idx - ly * C::TW;
-            int gx = x0 + lx, gy = y0 + ly;
+            const int gy = y0 + ly;
             if( gx >= a.width || gy >= a.height ) continue;
             const uint32_t* mlo = s_mask + ( ly + 1 ) * C::CW + ( lx + 1 ); // F0 | F1 << 16
             const uint32_t* mhi = mlo + C::NC;                             // F2 | F3 << 16
@@ -1269,7 +1291,6 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
                         if( ( rem >> bit ) & 1u ) px[ bit ] = Fmt< FMT >::BACKGROUND;
                 }
             }
-            uint8_t* dst = out + ( ( size_t )( a.flip_output ? out_h - 1 - ( size_t )gy * O : ( size_t )gy * O ) * out_w + ( size_t )gx * O ) * BPP;
 #ifdef PAR_WHATIF_NOSTORE
             uint32_t acc = 0u;
 #pragma unroll
