@@ -65,12 +65,14 @@ struct par_context
     CellRecord* d_tables = nullptr;        // kCellKeys 32-byte records
     uint32_t* d_mask_lut[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // per scale, built on first use
     // smoothing tables (smooth_table.h): link descriptors + neighbour bytes + class list (scale-independent), CUT / LINK masks per scale
-    uint32_t* d_smooth_words = nullptr; // head | head2 (kCellKeys words each) | pack (kCellKeys x 2 words)
+    uint32_t* d_smooth_words = nullptr; // desc (kCellKeys x 4 words) | pack (kCellKeys x 2 words) | 256 bytes of scratch
     LinkClass* d_link_classes = nullptr;
     int n_link_classes = 0;
     uint32_t link_entries = 0;
     uint64_t* d_cut[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     uint64_t* d_link[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    uint2* d_head[ 9 ] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    int n_canon = 0;
     unsigned long long* d_smooth_stats = nullptr; // 2 counters
     CellTablePtrs tables() const { return CellTablePtrs{ d_tables }; }
     EncodeTiledFn encode = nullptr;
@@ -359,8 +361,8 @@ int run_raster( par_context* c, const par_job* j, const uint8_t* graph, const ui
         built = true;
     }
     a.mask_lut = c->d_mask_lut[ S ];
-    a.smooth = SmoothTablePtrs{ c->d_smooth_words, c->d_smooth_words + kCellKeys, reinterpret_cast< const uint2* >( c->d_smooth_words + 2 * kCellKeys ),
-                                nullptr, nullptr };
+    // (generic descriptors: kCellKeys x 4 words, then the ID words: kCellKeys x 2)
+    a.smooth = SmoothTablePtrs{ nullptr, nullptr, reinterpret_cast< const uint2* >( c->d_smooth_words + 4 * kCellKeys ), nullptr, nullptr };
     a.smooth_stats = c->d_smooth_stats;
     if( a.subdivide && !( j->flags & PAR_FLAG_NO_SMOOTH_TABLES ) )
     {
@@ -370,10 +372,14 @@ int run_raster( par_context* c, const par_job* j, const uint8_t* graph, const ui
             const size_t ew = smooth_entry_words( S ) * sizeof( uint64_t );
             cudaError_t me = cudaMalloc( &c->d_cut[ S ], ( size_t )kCellKeys * 16 * ew );
             if( me == cudaSuccess ) me = cudaMalloc( &c->d_link[ S ], ( size_t )c->link_entries * ew );
+            if( me == cudaSuccess ) me = cudaMalloc( &c->d_head[ S ], 2 * ( size_t )kCellKeys * sizeof( uint2 ) );
             if( me == cudaSuccess )
-                me = launch_build_smooth_tables( S, c->tables(), c->d_link_classes, c->n_link_classes, c->d_cut[ S ], c->d_link[ S ],
-                                                 c->stream );
-            c->launches += 2;
+            {
+                uint8_t* bytes = reinterpret_cast< uint8_t* >( c->d_smooth_words + 6 * kCellKeys ); // 256 scratch, then the shared ranges
+                me = launch_build_smooth_tables( S, c->tables(), c->d_link_classes, c->n_link_classes, reinterpret_cast< const uint4* >( c->d_smooth_words ),
+                                                 bytes + 256, c->n_canon, c->d_cut[ S ], c->d_link[ S ], c->d_head[ S ], bytes, c->stream );
+            }
+            c->launches += 5;
             if( me != cudaSuccess )
             {
                 cudaFree( c->d_cut[ S ] );
@@ -384,6 +390,8 @@ int run_raster( par_context* c, const par_job* j, const uint8_t* graph, const ui
         }
         a.smooth.cut = c->d_cut[ S ];
         a.smooth.link = c->d_link[ S ];
+        a.smooth.head = c->d_head[ S ];
+        a.smooth.head2 = c->d_head[ S ] + kCellKeys;
     }
     if( built )
     {
@@ -461,11 +469,18 @@ int par_create( par_context** out, int device, int max_width, int max_height, in
         c->n_link_classes = ( int )smooth.classes.size();
         c->link_entries = smooth.link_entries;
         const size_t kw = ( size_t )kCellKeys * sizeof( uint32_t );
-        if( e == cudaSuccess ) e = cudaMalloc( &c->d_smooth_words, 4 * kw );
+        if( e == cudaSuccess ) e = cudaMalloc( &c->d_smooth_words, 6 * kw + 256 + 128 );
+        c->n_canon = ( int )smooth.n_canon;
         if( e == cudaSuccess ) e = cudaMalloc( &c->d_link_classes, smooth.classes.size() * sizeof( LinkClass ) );
-        if( e == cudaSuccess ) e = cudaMemcpy( c->d_smooth_words, smooth.head, kw, cudaMemcpyHostToDevice );
-        if( e == cudaSuccess ) e = cudaMemcpy( c->d_smooth_words + kCellKeys, smooth.head2, kw, cudaMemcpyHostToDevice );
-        if( e == cudaSuccess ) e = cudaMemcpy( c->d_smooth_words + 2 * kCellKeys, smooth.pack, 2 * kw, cudaMemcpyHostToDevice );
+        if( e == cudaSuccess ) e = cudaMemcpy( c->d_smooth_words, smooth.desc, 4 * kw, cudaMemcpyHostToDevice );
+        if( e == cudaSuccess ) e = cudaMemcpy( c->d_smooth_words + 4 * kCellKeys, smooth.pack, 2 * kw, cudaMemcpyHostToDevice );
+        if( e == cudaSuccess && smooth.n_canon )
+        {
+            uint8_t ranges[ 128 ];
+            memcpy( ranges, smooth.canon_lo, smooth.n_canon );
+            memcpy( ranges + smooth.n_canon, smooth.canon_span, smooth.n_canon );
+            e = cudaMemcpy( reinterpret_cast< uint8_t* >( c->d_smooth_words + 6 * kCellKeys ) + 256, ranges, 2 * smooth.n_canon, cudaMemcpyHostToDevice );
+        }
         if( e == cudaSuccess )
             e = cudaMemcpy( c->d_link_classes, smooth.classes.data(), smooth.classes.size() * sizeof( LinkClass ), cudaMemcpyHostToDevice );
     }
@@ -496,6 +511,7 @@ void par_destroy( par_context* c )
     for( int k = 0; k < 9; k++ ) cudaFree( c->d_mask_lut[ k ] );
     for( int k = 0; k < 9; k++ ) cudaFree( c->d_cut[ k ] );
     for( int k = 0; k < 9; k++ ) cudaFree( c->d_link[ k ] );
+    for( int k = 0; k < 9; k++ ) cudaFree( c->d_head[ k ] );
     cudaFree( c->d_smooth_words );
     cudaFree( c->d_link_classes );
     cudaFree( c->d_smooth_stats );

@@ -33,8 +33,8 @@ struct LabelArgs
 // device pointers of the smoothing tables (smooth_table.h); cut / link are per scale
 struct SmoothTablePtrs
 {
-    const uint32_t* head;   // [kCellKeys] link descriptors 0, 1 + corner bits + flags
-    const uint32_t* head2;  // [kCellKeys] link descriptors 2, 3
+    const uint2* head;      // [kCellKeys] link descriptors 0, 1 + flags, as this scale needs them (per scale)
+    const uint2* head2;     // [kCellKeys] link descriptors 2, 3 (per scale)
     const uint2* pack;      // [kCellKeys] IDs of the key's neighbour records: x = directions 4..7 in bits [12,32), y = directions 0..3
     const uint64_t* cut;    // [kCellKeys][16] entries (per scale)
     const uint64_t* link;   // [link_entries] entries: kNbrIds per class (per scale)
@@ -97,8 +97,10 @@ cudaError_t launch_polygons( const RasterArgs& a, cudaStream_t stream );
 void raster_tma_box( int scale, uint32_t box[ 3 ] );
 size_t mask_lut_words( int scale );
 size_t smooth_entry_words( int scale ); // 64-bit words per CUT / LINK entry
-cudaError_t launch_build_smooth_tables( int scale, const CellTablePtrs& tab, const LinkClass* d_classes, int n_classes, uint64_t* cut, uint64_t* link,
-                                        cudaStream_t stream );
+// desc: the keys' generic descriptors (SmoothTables::desc) on the device; canon: n_canon x lo, then n_canon x span (bytes);
+// head: [2][kCellKeys] out (descriptors 0, 1 then 2, 3); scratch: [256] bytes
+cudaError_t launch_build_smooth_tables( int scale, const CellTablePtrs& tab, const LinkClass* d_classes, int n_classes, const uint4* desc, const uint8_t* canon,
+                                        int n_canon, uint64_t* cut, uint64_t* link, uint2* head, uint8_t* scratch, cudaStream_t stream );
 cudaError_t launch_build_mask_lut( int scale, const CellTablePtrs& tab, uint32_t* lut, cudaStream_t stream );
 void raster_img_tma_box( int scale, uint32_t box[ 3 ] );
 cudaError_t launch_raster( const RasterArgs& a, const CUtensorMap* graph_map, const CUtensorMap* img_map, cudaStream_t stream );

@@ -706,37 +706,76 @@ __global__ void build_link_table_kernel( const LinkClass* classes, uint64_t* lin
     cover_to_entry< S >( xs, ys, m, entry );
 }
 
-// NS link descriptors of a smoothed cell (12 bits each in `desc`, smooth_table.h), without branches: XORs their LINK
+// The blocks shared by the classes that only say which IDs do not fit them: entry = MISMATCH outside lo .. lo + span, else 0.
+template< int S >
+__global__ void build_range_blocks_kernel( const uint8_t* lo, const uint8_t* span, uint32_t first_block, uint64_t* link )
+{
+    const uint32_t id = threadIdx.x;
+    uint64_t* entry = link + ( size_t )( ( first_block + blockIdx.x ) * ( uint32_t )kNbrIds + id ) * Entry< S >::EW;
+    for( int w = 0; w < Entry< S >::EW; w++ ) entry[ w ] = 0ull;
+    if( id - lo[ blockIdx.x ] > span[ blockIdx.x ] ) entry[ 0 ] = Entry< S >::MISMATCH;
+}
+
+// Which classes have something to XOR at this scale — a mask bit or the WIDE flag in some entry — and so keep their own
+// block; the others are served by the shared block of their ID range.  block_of[ own block ] = the block to use.
+template< int S >
+__global__ void choose_class_blocks_kernel( const LinkClass* classes, int n_classes, const uint64_t* link, uint8_t* block_of )
+{
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if( ci == 0 ) block_of[ 0 ] = 0;
+    if( ci >= n_classes ) return;
+    const LinkClass& c = classes[ ci ];
+    bool any = c.canon == 0; // (no shared block for its range: keeps its own)
+    for( int id = 0; id < kNbrIds; id++ )
+        for( int w = 0; w < Entry< S >::EW; w++ )
+        {
+            const uint64_t v = link[ ( size_t )( c.block * ( uint32_t )kNbrIds + id ) * Entry< S >::EW + w ];
+            any = any || ( w == 0 ? ( v & ~Entry< S >::MISMATCH ) : v ) != 0ull;
+        }
+    block_of[ c.block ] = ( uint8_t )( any ? c.block : c.canon );
+}
+
+// The kernel's descriptors at this scale (smooth_table.h): the key's descriptors with their blocks as chosen above, those
+// whose class keeps its own block first (stable), then the ones on shared blocks; slots 0, 1 -> head01, slots 2, 3 -> head23.
+__global__ void build_head_tables_kernel( const uint4* desc, const uint8_t* block_of, uint2* head01, uint2* head23 )
+{
+    const int key = blockIdx.x * blockDim.x + threadIdx.x;
+    if( key >= kCellKeys ) return;
+    const uint4 in = desc[ key ];
+    const uint32_t d[ 4 ] = { in.x, in.y, in.z, in.w };
+    uint32_t out[ 4 ] = { 0u, 0u, 0u, 0u };
+    int n = 0;
+    for( int pass = 0; pass < 2; pass++ )
+        for( int k = 0; k < 4; k++ )
+        {
+            if( !( d[ k ] & kDescUsed ) ) continue;
+            const uint32_t own = ( d[ k ] >> 13 ) & 255u, use = block_of[ own ];
+            if( ( use == own ) == ( pass == 0 ) ) out[ n++ ] = ( d[ k ] & ~( 255u << 13 ) & ~( kDescSlow | kDescMore ) ) | use << 13;
+        }
+    out[ 0 ] |= ( d[ 0 ] & kDescSlow ) | ( out[ 2 ] ? kDescMore : 0u );
+    head01[ key ] = make_uint2( out[ 0 ], out[ 1 ] );
+    head23[ key ] = make_uint2( out[ 2 ], out[ 3 ] );
+}
+
+// NS link descriptors of a smoothed cell (smooth_table.h: one word each, ready to use), without branches: XORs their LINK
 // entries into m and ORs word 0 of the entries into `flags` (WIDE and MISMATCH travel there).  The neighbour's record is
-// named by a 5-bit ID that sits in the neighbour's cell word: one shared-memory load of the half that holds the field of
-// direction 7 - e, one shift — no neighbour record is gathered, and a neighbour without an edge in that direction has ID 0,
-// whose entry is MISMATCH.
+// named by a 5-bit ID that sits in the neighbour's cell word: one shared-memory load at the descriptor's offset from the
+// cell's own word, one shift by the descriptor's amount — no neighbour record is gathered, and a neighbour without an edge
+// in that direction has ID 0, whose entry is MISMATCH.
 template< int S, int NS >
-__device__ __forceinline__ void link_slots( const SmoothTablePtrs& st, const uint32_t* words_at_cell, uint32_t desc, uint64_t* m, uint64_t& flags )
+__device__ __forceinline__ void link_slots( const SmoothTablePtrs& st, const uint32_t* words_at_cell, const uint32_t* desc, uint64_t* m, uint64_t& flags )
 {
     typedef Cfg< S > C;
     typedef Entry< S > E;
+    static_assert( C::KP == kHeadRowWords && kNbrIds == 32, "descriptor word offsets; block << 5 | id" );
+    const uint32_t* base = words_at_cell - ( kHeadRowWords + 1 ); // (the offsets are biased)
 #pragma unroll
     for( int k = 0; k < NS; k++ )
     {
-        const uint32_t d = desc >> ( 12 * k );
-        const uint32_t e = d & 7u;
-        const bool used = ( d >> 11 ) & 1u;
-        // neighbour across graph edge e: offset of the word of its cell that holds the ID for direction 7 - e (the x-word:
-        // directions 4..7 = e < 4, the y-word, KW words further: directions 0..3 = e >= 4), one signed byte per edge; and
-        // the field's shift
-        constexpr int KP = C::KP, KW = C::KW;
-        constexpr uint32_t off_lo = ( uint32_t )( uint8_t )( KP - 1 ) | ( uint32_t )( uint8_t )( KP ) << 8 | ( uint32_t )( uint8_t )( KP + 1 ) << 16 |
-                                    ( uint32_t )( uint8_t )( -1 ) << 24;
-        constexpr uint32_t off_hi = ( uint32_t )( uint8_t )( KW + 1 ) | ( uint32_t )( uint8_t )( -KP + KW - 1 ) << 8 | ( uint32_t )( uint8_t )( -KP + KW ) << 16 |
-                                    ( uint32_t )( uint8_t )( -KP + KW + 1 ) << 24;
-        static_assert( KP + 1 < 128, "word offsets fit a signed byte" );
-        constexpr uint32_t sh_lo = 27u | 22u << 8 | 17u << 16 | 12u << 24, sh_hi = 15u | 10u << 8 | 5u << 16 | 0u << 24;
-        const int woff = ( int )( int8_t )__byte_perm( off_lo, off_hi, e );
-        const uint32_t shift = __byte_perm( sh_lo, sh_hi, e ) & 255u;
-        const uint32_t id = ( words_at_cell[ woff ] >> shift ) & 31u;
-        const uint64_t* le = st.link + ( size_t )( ( ( d << 2 ) & ( 255u * ( uint32_t )kNbrIds ) ) | id ) * E::EW;
-        static_assert( kNbrIds == 32, "block << 5 | id" );
+        const uint32_t d = desc[ k ];
+        const bool used = ( d & kDescUsed ) != 0u;
+        const uint32_t id = ( base[ d & 255u ] >> ( ( d >> 8 ) & 31u ) ) & 31u;
+        const uint64_t* le = st.link + ( size_t )( ( ( d >> 8 ) & ( 255u << 5 ) ) | id ) * E::EW;
 #pragma unroll
         for( int w = 0; w < E::EW; w++ )
         {
@@ -777,12 +816,11 @@ __device__ __forceinline__ void link_slots( const SmoothTablePtrs& st, const uin
 // of the neighbour's hull (the reference's getPointIndex fallback), or the key is not in the tables: the caller takes the
 // geometric path; E::FLAG — some piece reaches beyond the mask (wide).
 template< int S >
-__device__ __forceinline__ uint64_t smooth_lookup( const SmoothTablePtrs& st, const uint32_t* mask_lut, const uint32_t* keys_at_cell, uint32_t key, uint32_t cflags,
-                                                   uint64_t* m, bool& more )
+__device__ __forceinline__ uint64_t smooth_lookup( const SmoothTablePtrs& st, const uint32_t* mask_lut, const uint32_t* keys_at_cell, uint32_t key, uint2 head,
+                                                   uint32_t cflags, uint64_t* m, bool& more )
 {
     typedef Cfg< S > C;
     typedef Entry< S > E;
-    const uint32_t head = __ldg( st.head + key ); // the first two link descriptors, flags
     uint64_t flags = 0ull;
     if( cflags & 16u ) // checkTJunction's early exit keeps every cut vertex: the plain hull
     {
@@ -807,14 +845,15 @@ __device__ __forceinline__ uint64_t smooth_lookup( const SmoothTablePtrs& st, co
 #pragma unroll
         for( int w = 0; w < E::EW; w++ ) m[ w ] = __ldg( e + w );
     }
-    more = ( head & kHeadMore ) != 0u;
+    more = ( head.x & kDescMore ) != 0u;
 #ifndef PAR_WHATIF_NOLINKS
-    link_slots< S, 2 >( st, keys_at_cell, head, m, flags ); // (a key that always takes the geometric path has no descriptors)
+    const uint32_t desc[ 2 ] = { head.x, head.y };
+    link_slots< S, 2 >( st, keys_at_cell, desc, m, flags ); // (a key that always takes the geometric path has no descriptors)
 #else
     more = false;
 #endif
     // the flag bits of word 0 were XORed along with the masks: take them from the OR (the CUT entry has none)
-    return ( flags & ( E::FLAG | E::MISMATCH ) ) | ( ( head & kHeadSlow ) ? E::MISMATCH : 0ull );
+    return ( flags & ( E::FLAG | E::MISMATCH ) ) | ( ( head.x & kDescSlow ) ? E::MISMATCH : 0ull );
 }
 
 // SECOND pass, for the cells whose key has three or four link descriptors: the XOR of the remaining LINK entries; returns
@@ -823,11 +862,12 @@ template< int S >
 __device__ __forceinline__ uint64_t smooth_lookup_more( const SmoothTablePtrs& st, const uint32_t* keys_at_cell, uint32_t key, uint64_t* m )
 {
     typedef Entry< S > E;
-    const uint32_t head2 = __ldg( st.head2 + key );
+    const uint2 head2 = __ldg( st.head2 + key );
+    const uint32_t desc[ 2 ] = { head2.x, head2.y };
     uint64_t flags = 0ull;
 #pragma unroll
     for( int w = 0; w < E::EW; w++ ) m[ w ] = 0ull;
-    link_slots< S, 2 >( st, keys_at_cell, head2, m, flags );
+    link_slots< S, 2 >( st, keys_at_cell, desc, m, flags );
     return flags & ( E::FLAG | E::MISMATCH );
 }
 
@@ -1043,6 +1083,8 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
         else if( inside && !plain )
         {
             n_smoothed++;
+            // the first two link descriptors + flags of the key: requested before the corner test below, which hides the gather
+            const uint2 head = use_tables ? __ldg( a.smooth.head + key ) : make_uint2( 0u, 0u );
             // checkTJunction for the four corners of the pixel square (bit c: corner c stays), 16 = its early exit
             uint32_t cf = 16u;
 #ifdef PAR_WHATIF_CF
@@ -1061,7 +1103,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
             typedef Entry< S > E;
             uint64_t mw[ E::EW ];
             bool more = false;
-            const uint64_t rare = use_tables ? smooth_lookup< S >( a.smooth, a.mask_lut, kc, key, cf, mw, more ) : E::MISMATCH;
+            const uint64_t rare = use_tables ? smooth_lookup< S >( a.smooth, a.mask_lut, kc, key, head, cf, mw, more ) : E::MISMATCH;
             if( rare & E::MISMATCH ) // (rare: queued for the geometric path, a bit per cell)
             {
                 atomicOr( &s_geo[ idx >> 5 ], 1u << ( idx & 31 ) );

@@ -136,13 +136,16 @@ size_t smooth_entry_words( int scale )
     return 0;
 }
 
-cudaError_t launch_build_smooth_tables( int scale, const CellTablePtrs& tab, const LinkClass* d_classes, int n_classes, uint64_t* cut, uint64_t* link,
-                                        cudaStream_t stream )
+cudaError_t launch_build_smooth_tables( int scale, const CellTablePtrs& tab, const LinkClass* d_classes, int n_classes, const uint4* desc, const uint8_t* canon,
+                                        int n_canon, uint64_t* cut, uint64_t* link, uint2* head, uint8_t* scratch, cudaStream_t stream )
 {
 #define PAR_BUILD_SMOOTH( S )                                                                        \
     build_cut_table_kernel< S ><<< kCellKeys * 16 / 128, 128, 0, stream >>>( tab, cut );             \
     cudaMemsetAsync( link, 0, kNbrIds * Entry< S >::EW * sizeof( uint64_t ), stream ); /* block 0: the all-zero block */ \
     build_link_table_kernel< S ><<< n_classes, kNbrIds, 0, stream >>>( d_classes, link );            \
+    if( n_canon > 0 ) build_range_blocks_kernel< S ><<< n_canon, kNbrIds, 0, stream >>>( canon, canon + n_canon, ( uint32_t )n_classes + 1u, link ); \
+    choose_class_blocks_kernel< S ><<< ( n_classes + 63 ) / 64, 64, 0, stream >>>( d_classes, n_classes, link, scratch ); \
+    build_head_tables_kernel<<< kCellKeys / 128, 128, 0, stream >>>( desc, scratch, head, head + kCellKeys ); \
     return cudaGetLastError()
     PAR_FOR_SCALE( scale, PAR_BUILD_SMOOTH )
 #undef PAR_BUILD_SMOOTH

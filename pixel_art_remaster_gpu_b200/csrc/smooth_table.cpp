@@ -39,6 +39,7 @@ void build_smooth_tables( const CellTables& cells, SmoothTables* out )
     out->classes.clear();
     out->link_entries = kNbrIds; // block 0: the all-zero block
     out->slow_keys = 0;
+    out->n_canon = 0;
     typedef std::tuple< int, int, int, int, int, int, int, int, int, int, int > ClassKey; // e, hasA, hasB, 4 x (x, y)
     std::map< ClassKey, uint32_t > class_block;
     uint32_t expected[ 8 ] = { 0, 0, 0, 0, 0, 0, 0, 0 }; // per link direction e: point codes some cell expects at the neighbour's edge ends
@@ -211,7 +212,36 @@ void build_smooth_tables( const CellTables& cells, SmoothTables* out )
         }
     }
     for( LinkClass& c : out->classes )
+    {
         for( int k = 0; k < kNbrIds; k++ ) c.nrec[ k ] = id_rec[ 7 - c.e ][ k ];
+        // the IDs whose record holds the class's blended vertices
+        int lo = kNbrIds, hi = -1, n_fit = 0;
+        for( int k = 1; k < kNbrIds; k++ )
+        {
+            const uint32_t r = c.nrec[ k ];
+            if( r == 0xFFFFu || ( c.hasA && ( ( r >> 8 ) & 15u ) != c.codeA ) || ( c.hasB && ( ( r >> 12 ) & 15u ) != c.codeB ) ) continue;
+            lo = k < lo ? k : lo;
+            hi = k > hi ? k : hi;
+            n_fit++;
+        }
+        c.exact = n_fit > 0 && hi - lo + 1 == n_fit;
+        c.id_lo = ( uint8_t )( c.exact ? lo : 0 );
+        c.id_span = ( uint8_t )( c.exact ? hi - lo : kNbrIds - 1 );
+        c.canon = 0;
+        if( c.exact )
+        {
+            uint32_t k = 0;
+            while( k < out->n_canon && ( out->canon_lo[ k ] != c.id_lo || out->canon_span[ k ] != c.id_span ) ) k++;
+            if( k == out->n_canon && out->n_canon < 64 && out->link_entries / kNbrIds < 255 )
+            {
+                out->canon_lo[ k ] = c.id_lo;
+                out->canon_span[ k ] = c.id_span;
+                out->n_canon++;
+                out->link_entries += kNbrIds;
+            }
+            if( k < out->n_canon ) c.canon = ( uint16_t )( out->classes.size() + 1 + k );
+        }
+    }
     for( unsigned key = 0; key < ( unsigned )kCellKeys; key++ )
     {
         const SmoothRecord& r = out->rec[ key ];
@@ -221,18 +251,25 @@ void build_smooth_tables( const CellTables& cells, SmoothTables* out )
             out->pack[ key ][ 0 ] |= ( uint32_t )out->nbr_id[ key ][ 4 + e ] << ( 12 + 5 * e );
             out->pack[ key ][ 1 ] |= ( uint32_t )out->nbr_id[ key ][ e ] << ( 5 * e );
         }
-        uint32_t w[ 2 ] = { 0u, 0u };
+        uint32_t* w = out->desc[ key ];
+        w[ 0 ] = w[ 1 ] = w[ 2 ] = w[ 3 ] = 0u;
         if( r.link[ 0 ] == kSmoothSlow || !ids_ok )
-            w[ 0 ] = kHeadSlow;
-        else
         {
-            for( int k = 0; k < kMaxLinks; k++ )
-                if( r.link[ k ] >> 16 ) w[ k >> 1 ] |= ( ( r.link[ k ] & 7u ) | ( r.link[ k ] >> 24 ) << 3 | 1u << 11 ) << ( 12 * ( k & 1 ) );
-            w[ 0 ] |= ( ( r.link[ 0 ] >> 4 ) & 15u ) << 24;
-            if( w[ 1 ] ) w[ 0 ] |= kHeadMore;
+            w[ 0 ] = kDescSlow;
+            continue;
         }
-        out->head[ key ] = w[ 0 ];
-        out->head2[ key ] = w[ 1 ];
+        for( int k = 0; k < kMaxLinks; k++ )
+        {
+            if( !( r.link[ k ] >> 16 ) ) continue;
+            const int e = ( int )( r.link[ k ] & 7u );
+            static const int di[ 8 ] = { -1, 0, 1, -1, 1, -1, 0, 1 }, dj[ 8 ] = { 1, 1, 1, 0, 0, -1, -1, -1 };
+            // the neighbour's word that holds the ID for its direction 7 - e: directions 4..7 (e < 4) in its x-word at
+            // bits [12 + 5 (3 - e)), directions 0..3 (e >= 4) in its y-word, half a row further, at bits [5 (7 - e))
+            const int woff = dj[ e ] * kHeadRowWords + di[ e ] + ( e >= 4 ? kHeadRowWords / 2 : 0 ) + kHeadRowWords + 1;
+            const int shift = e < 4 ? 12 + 5 * ( 3 - e ) : 5 * ( 7 - e );
+            w[ k ] = ( uint32_t )woff | ( uint32_t )shift << 8 | ( r.link[ k ] >> 24 ) << 13 | kDescUsed;
+        }
+        if( w[ 2 ] ) w[ 0 ] |= kDescMore;
     }
 }
 

@@ -58,12 +58,20 @@ struct SmoothRecord
 
 // What the raster kernel reads (round 3: the records above are only the host-side source of these).
 //
-// * HEAD[key] / HEAD2[key] (32 bits each): the key's link descriptors reduced to what the kernel still needs — the
-//   direction e of the neighbour and the class's block of the link table — two descriptors per word:
-//       [0,3) e   [3,11) block   [11] used     (slot 0 / slot 2)
-//       [12,15) e [15,23) block  [23] used     (slot 1 / slot 3)
-//   HEAD only: [24,28) corners (which square corners hold a cut vertex), [28] the key has a third descriptor (HEAD2),
-//   [29] the key always takes the geometric path.
+// * DESC[key][4] (32 bits per link descriptor): the descriptor reduced to what the kernel still needs, ready to use —
+//       [0,8)   where the neighbour's ID sits: word offset from the cell's own word in the staged tile (kHeadRowWords words
+//               per tile row, see PACK below) to the neighbour's x-word (e < 4) / y-word (e >= 4), biased by
+//               kHeadRowWords + 1 (so that it is not negative)
+//       [8,13)  shift of the ID field for direction 7 - e in that word
+//       [13,21) the class's block of the link table   [21] used
+//       slot 0 only: [30] the key has a third descriptor, [31] the key always takes the geometric path.
+//   Per SCALE the kernel reads a copy of this (built on the device next to the link table, raster_kernels.cu): at 4x more
+//   than half of the classes have an empty mask for every ID that fits them — the loop between the hull and the smoothed
+//   outline around a blended vertex is a sliver that often holds no sample — so all their block says is which IDs do NOT
+//   fit (MISMATCH).  The IDs of a direction are numbered in the order of their records, codes in the high bits, so the
+//   fitting ones are a range lo .. lo + span, and classes with the same range share ONE block (LinkClass::canon): three
+//   quarters of the lookups of the bench frames then fall on a dozen hot blocks.  The descriptors whose class keeps its
+//   own block come first.
 // * a neighbour record is one of at most 30 different 16-bit values per direction, so it is named by a 5-bit ID
 //   (1..30; 0 = the neighbour has no hull edge shared through that direction).  NBR_ID[key][e'] is that ID, and
 //   PACK[key] = { IDs of directions 4..7 in bits [12 + 5 (e' - 4)), IDs of directions 0..3 in bits [5 e') } is what the
@@ -74,7 +82,8 @@ struct SmoothRecord
 //   record gives, or the MISMATCH flag when the record's end / start vertex is not the class's blended vertex (the
 //   comparison the kernel used to make per cell is made once, when the table is built).
 constexpr int kNbrIds = 32;
-constexpr uint32_t kHeadSlow = 1u << 29, kHeadMore = 1u << 28;
+constexpr int kHeadRowWords = 72; // words per row of staged cell words: 36 x-words, then 36 y-words (raster_impl.cuh Cfg::KP)
+constexpr uint32_t kDescSlow = 1u << 31, kDescMore = 1u << 30, kDescUsed = 1u << 21;
 
 // geometry of one class, consumed by the device table builder (quarter-pixel units)
 struct LinkClass
@@ -84,17 +93,21 @@ struct LinkClass
     uint32_t block;          // its 16-entry block of the link table (>= 1)
     int8_t after[ 4 ], before[ 4 ]; // rank -> point code of the neighbour's vertex after the edge end / before its start
     uint8_t codeA, codeB;           // the blended vertices as point codes in the neighbour's frame (what its record must hold)
-    uint16_t pad2;
+    uint8_t id_lo, id_span;         // the IDs whose record holds them: lo .. lo + span (0, 31 and exact = 0 when they are not one range)
     uint16_t nrec[ kNbrIds ];       // ID -> the neighbour's 16-bit record for direction 7 - e (0xFFFF: no such ID)
+    uint16_t exact;                 // the ID range says exactly which records fit
+    uint16_t canon;                 // the block (after the classes' own) shared by the classes with this range
 };
 
 struct SmoothTables
 {
     SmoothRecord rec[ kCellKeys ];
-    uint32_t head[ kCellKeys ], head2[ kCellKeys ], pack[ kCellKeys ][ 2 ];
+    uint32_t desc[ kCellKeys ][ 4 ], pack[ kCellKeys ][ 2 ];
     uint8_t nbr_id[ kCellKeys ][ 8 ];
     std::vector< LinkClass > classes;
-    uint32_t link_entries = 0; // total entries of the link table (16 per class + the zero block)
+    uint32_t link_entries = 0; // total entries of the link table (kNbrIds per class + the zero block + the shared range blocks)
+    uint32_t n_canon = 0;      // shared range blocks
+    uint8_t canon_lo[ 64 ], canon_span[ 64 ];
     uint32_t slow_keys = 0;    // keys that always take the geometric path
 };
 

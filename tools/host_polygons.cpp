@@ -121,9 +121,8 @@ extern "C" void host_smooth_check( const uint8_t* img_zero_tailed, const uint8_t
             cover( poly, S, halo, direct );
             // the pieces, as the kernel assembles them
             const SmoothRecord& rec = ST.rec[ key ];
-            if( ( rec.link[ 0 ] == kSmoothSlow ) != ( ( ST.head[ key ] & kHeadSlow ) != 0u ) ) out[ 2 ]++;
+            if( ( rec.link[ 0 ] == kSmoothSlow ) != ( ( ST.desc[ key ][ 0 ] & kDescSlow ) != 0u ) ) out[ 2 ]++;
             if( rec.link[ 0 ] == kSmoothSlow ) { out[ 1 ]++; continue; }
-            if( ( ( ST.head[ key ] >> 24 ) & 15u ) != ( ( rec.link[ 0 ] >> 4 ) & 15u ) || ( ( ST.head[ key ] & kHeadMore ) != 0u ) != ( ( rec.link[ 2 ] >> 16 ) != 0u ) ) out[ 2 ]++;
             const uint64_t h = T.rec[ key ].verts, info = T.rec[ key ].info;
             const int n = hull_count( info );
             const VertexClasses cls = classify_vertices( info );
@@ -168,16 +167,30 @@ extern "C" void host_smooth_check( const uint8_t* img_zero_tailed, const uint8_t
                 const uint32_t ends = ( d >> 16 ) & 255u;
                 const LinkClass& c = ST.classes[ ( d >> 24 ) - 1 ];
                 {   // the kernel's view of the same lookup (HEAD / PACK / NBR_ID / per-class ID lists) must agree with the records
-                    const uint32_t hd = ( k < 2 ? ST.head[ key ] : ST.head2[ key ] ) >> ( 12 * ( k & 1 ) );
-                    if( ( hd & 7u ) != ( d & 7u ) || ( ( hd >> 3 ) & 255u ) != ( d >> 24 ) || !( ( hd >> 11 ) & 1u ) ) out[ 2 ]++;
-                    static const int shift_of[ 8 ] = { 27, 22, 17, 12, 15, 10, 5, 0 }; // the kernel's: word (e >= 4 ? y : x) >> shift
-                    const uint32_t half = e >= 4 ? ST.pack[ nkey ][ 1 ] : ( nkey | ST.pack[ nkey ][ 0 ] );
-                    const uint32_t id = ( half >> shift_of[ e ] ) & 31u;
+                    // (a tile row of cell words: 36 x-words = key | IDs of directions 4..7 << 12, then 36 y-words = IDs of 0..3)
+                    const uint32_t hd = ST.desc[ key ][ k ];
+                    if( ( ( hd >> 13 ) & 255u ) != ( d >> 24 ) || !( hd & kDescUsed ) ) out[ 2 ]++;
+                    const int woff = ( int )( hd & 255u ) - ( kHeadRowWords + 1 ); // from the cell's own x-word
+                    const int row = ( woff + kHeadRowWords / 4 + 4 * kHeadRowWords ) / kHeadRowWords - 4; // (floor)
+                    const int rest = woff - row * kHeadRowWords; // column offset, + 36 for the y-word
+                    const bool yword = rest > kHeadRowWords / 4;
+                    const int col = yword ? rest - kHeadRowWords / 2 : rest;
+                    if( row != edge_dj( e ) || col != edge_di( e ) || yword != ( e >= 4 ) ) out[ 2 ]++;
+                    const uint32_t half = yword ? ST.pack[ nkey ][ 1 ] : ( nkey | ST.pack[ nkey ][ 0 ] );
+                    const uint32_t id = ( half >> ( ( hd >> 8 ) & 31u ) ) & 31u;
                     if( id != ST.nbr_id[ nkey ][ e ^ 7 ] ) out[ 2 ]++;
                     const uint32_t r2 = c.nrec[ id ];
-                    const bool mis2 = id == 0u || r2 == 0xFFFFu || ( c.hasA && ( ( r2 >> 8 ) & 15u ) != c.codeA ) || ( c.hasB && ( ( r2 >> 12 ) & 15u ) != c.codeB );
+                    // the class's own block says MISMATCH for exactly the records that do not hold its blended vertices, and so does
+                    // the block shared by the classes with its ID range, when it has one
+                    const bool entry_mismatch = id == 0u || r2 == 0xFFFFu || ( c.hasA && ( ( r2 >> 8 ) & 15u ) != c.codeA ) || ( c.hasB && ( ( r2 >> 12 ) & 15u ) != c.codeB );
                     const bool mis = ( ( ( r ^ d ) >> 8 ) & ends ) != 0u;
-                    if( mis != mis2 || ( !mis && ( ( r2 ^ r ) & ends ) != 0u ) ) out[ 2 ]++;
+                    if( entry_mismatch != mis ) out[ 2 ]++;
+                    if( c.canon )
+                    {
+                        const uint32_t cn = c.canon - ( uint32_t )ST.classes.size() - 1u;
+                        if( cn >= ST.n_canon || ( id - ST.canon_lo[ cn ] > ( uint32_t )ST.canon_span[ cn ] ) != mis ) out[ 2 ]++;
+                    }
+                    if( !mis && ( ( r2 ^ r ) & ends ) != 0u ) out[ 2 ]++;
                 }
                 if( ( ( r ^ d ) >> 8 ) & ends ) { ok = false; break; }
                 const uint32_t sub = r & ends;
