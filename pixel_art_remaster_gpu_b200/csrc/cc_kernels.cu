@@ -11,9 +11,9 @@
 // shared memory — no seams, no global atomics, no flatten kernel, but one CTA per SM, two CTA-wide barriers per 1024 pixels
 // and CAS loops for the 16-bit minimum: 2.08 ms per 1024 frames against 0.91 ms for the three kernels below,
 // profiles/r2e_stage_times_*.)
-//   (1) tile pass: one CTA per 64x16 tile builds the tile's forest in SHARED memory (horizontal runs by
-//       warp ballot, the few unions that can still connect two runs queued and executed one per lane,
-//       flatten) and writes tile-local roots as global indices;
+//   (1) tile pass: one CTA per 64x16 tile builds the tile's forest in SHARED memory (a warp scans a band of rows with
+//       the labels in registers: horizontal runs by ballot, labels inherited from the row below by shuffle, a union only
+//       where a run joins two components; flatten) and writes tile-local roots as global indices;
 //   (2) seam pass: one thread per seam pixel unions across the seams with global atomicMin;
 //   (3) flatten pass: every pixel replaces its label by its root.
 // Roots only ever point to smaller indices, so the root of a set is its minimum index.
@@ -24,7 +24,10 @@ namespace par {
 
 namespace {
 
-constexpr int kTW = 64, kTH = 16, kThreads = 256;
+#ifndef PAR_CC_TH
+#define PAR_CC_TH 16
+#endif
+constexpr int kTW = 64, kTH = PAR_CC_TH, kThreads = 256;
 
 __device__ __forceinline__ int find_root( const int* lab, int x )
 {
@@ -73,13 +76,18 @@ __device__ __forceinline__ void unite( int* lab, int a, int b )
     }
 }
 
-// Tile pass.  Two things keep the shared-memory forest shallow and the number of unions small:
-//  * horizontal runs first: a warp owns 32 consecutive pixels of a row, one ballot gives the "linked to the right"
-//    bits and every pixel starts with the index of the first pixel of its run as its label — no union at all;
-//  * a link to the row above is only united when it can connect two runs that are not already connected through
-//    the pixel to the left (same run below, same run above, also linked upwards), and a diagonal link only when its
-//    target is not in the run of an orthogonal link that is united anyway.
-// What remains is roughly one union per pair of touching runs.
+// Tile pass (round 3).  A warp owns a band of 32 columns x 4 rows of the 64 x 16 tile and scans its rows bottom-up, a
+// lane per column, labels in registers:
+//  * horizontal runs from one ballot of the "linked to the right" bits (as before);
+//  * a pixel INHERITS the label of a pixel it is linked to in the row below (that row's labels and node bytes travel
+//    between the lanes by shuffle), and a run takes the minimum over its pixels (a segmented min-scan: five shuffle steps)
+//    — or, with no link downwards, the index of its first pixel.  Labels only ever point to a smaller index of the same
+//    component, so the array is a union-find forest from the start and almost every pixel already holds its root;
+//  * a union is only needed where a run inherits two DIFFERENT labels (it joins two components of the rows below): those
+//    few go straight to the shared-memory forest (atomicMin, link-by-minimum).
+// What the warps cannot see in their registers — the links across the band boundary (columns 31 | 32) and across the row
+// groups (rows 3 | 4, 7 | 8, 11 | 12) — is united afterwards, one thread per boundary pixel.  Before: every vertical link
+// was classified and queued per pixel (303 lane instructions per pixel); now ~100.
 __device__ __forceinline__ void unite_halving( int* lab, int a, int b )
 {
     for( ;; )
@@ -99,22 +107,25 @@ __device__ __forceinline__ void unite_halving( int* lab, int a, int b )
     }
 }
 
+constexpr int kGroupRows = kTH / 4; // rows a warp scans: kTH / ( warps per band )
+
 __global__ void __launch_bounds__( kThreads ) cc_tile_kernel( LabelArgs a )
 {
     __shared__ int s_lab[ kTW * kTH ];
-    __shared__ uint8_t s_g[ kTW * kTH ];       // node bytes with the links that leave the tile (or the image) removed
-    __shared__ uint32_t s_req[ 3 * kTW * kTH + kTW * kTH / 32 ]; // queued unions, a << 16 | b (three per pixel, one more for a warp's last lane)
-    __shared__ int s_n;
-    if( threadIdx.x == 0 ) s_n = 0;
+    __shared__ uint8_t s_g[ kTW * kTH ]; // node bytes with the links that leave the tile (or the image) removed
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH, f = blockIdx.z;
     const size_t frame_px = ( size_t )a.width * a.height;
     const uint8_t* g = a.graph + ( size_t )f * frame_px;
     int* out = a.labels + ( size_t )f * frame_px;
-    const uint32_t lane = threadIdx.x & 31u;
-    static_assert( kTW % 32 == 0 && ( kTW * kTH ) % kThreads == 0, "a warp owns 32 consecutive pixels of one tile row" );
-    for( int idx = threadIdx.x; idx < kTW * kTH; idx += kThreads )
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    static_assert( kTW == 64 && kThreads == 256 && kGroupRows * ( kThreads / 32 ) * 32 == kTW * kTH && 3 * kTW + 2 * kTH <= kThreads, "2 bands x 4 row groups" );
+    const int lx = ( warp & 1 ) * 32 + lane, row0 = ( warp >> 1 ) * kGroupRows;
+    const int gx = x0 + lx;
+    uint32_t below = 0u; // label (tile-local index) << 8 | node byte of the pixel below this lane's; node 0 = no row below in this group
+#pragma unroll
+    for( int k = 0; k < kGroupRows; k++ )
     {
-        const int ly = idx / kTW, lx = idx - ly * kTW, gx = x0 + lx, gy = y0 + ly;
+        const int ly = row0 + k, gy = y0 + ly, idx = ly * kTW + lx;
         uint32_t node = 0u;
         if( gx < a.width && gy < a.height )
         {
@@ -125,64 +136,90 @@ __global__ void __launch_bounds__( kThreads ) cc_tile_kernel( LabelArgs a )
             if( lx == 0 ) node &= ~1u;
         }
         s_g[ idx ] = ( uint8_t )node;
-        // run start inside the warp's 32 pixels: the lane after the last lane below me that is NOT linked to its right
-        const uint32_t linked = __ballot_sync( 0xFFFFFFFFu, ( node & 16u ) != 0u );
-        const uint32_t breaks = ~linked & ( ( 1u << lane ) - 1u );
-        const int start = breaks ? 32 - __clz( ( int )breaks ) : 0;
-        s_lab[ idx ] = idx - ( int )lane + start;
-    }
-    __syncthreads();
-    // the unions that are left are queued first and then executed one per lane: a warp that unites as it goes spends
-    // the time of its slowest lane three times per pixel (up, up-left, up-right), mostly on idle lanes
-    for( int idx = threadIdx.x; idx < kTW * kTH; idx += kThreads )
-    {
-        const int lx = idx & ( kTW - 1 );
-        const uint32_t node = s_g[ idx ];
-        uint32_t want = ( ( node & 16u ) && lane == 31u ) ? 8u : 0u; // a run that continues into the next warp's pixels
-        if( node & 7u )
-        {
-            const uint32_t left = lx > 0 ? s_g[ idx - 1 ] : 0u, right = lx + 1 < kTW ? s_g[ idx + 1 ] : 0u;
-            const uint32_t up = s_g[ idx + kTW ], up_left = lx > 0 ? s_g[ idx + kTW - 1 ] : 0u; // (a link says the row above exists)
-            const bool same_run_left = lane > 0u && ( left & 16u );                             // in the same run as the pixel to the left
-            if( ( node & 2u ) && !( same_run_left && ( left & 2u ) && ( up_left & 16u ) ) ) want |= 2u;
-            if( ( node & 1u ) && !( ( ( node & 2u ) && ( up_left & 16u ) ) || ( same_run_left && ( left & 2u ) ) ) ) want |= 1u;
-            if( ( node & 4u ) && !( ( ( node & 2u ) && ( up & 16u ) ) || ( lane < 31u && ( node & 16u ) && ( right & 2u ) ) ) ) want |= 4u;
-        }
-        // slots for this warp's requests: one shared atomic per warp
-        const int mine = __popc( want );
-        int before = mine;
+        // horizontal runs inside the band: the run starts after the last lane below me that is NOT linked to its right
+        const uint32_t linked = __ballot_sync( 0xFFFFFFFFu, ( node & 16u ) != 0u && lane < 31 );
+        const uint32_t breaks_below = ~linked & ( ( 1u << lane ) - 1u );
+        const int start = breaks_below ? 32 - __clz( ( int )breaks_below ) : 0;
+        const int end = lane + __ffs( ( int )( ~linked >> lane ) ) - 1; // (bit 31 of ~linked is always set)
+        // labels inherited from the row below: its pixel under me links up (bit 1), the one to the right up-left (bit 0), the
+        // one to the left up-right (bit 2)
+        const uint32_t bl = __shfl_up_sync( 0xFFFFFFFFu, below, 1 ), br = __shfl_down_sync( 0xFFFFFFFFu, below, 1 );
+        constexpr int kNone = 0x7FFFFFFF;
+        const int c0 = ( below & 2u ) ? ( int )( below >> 8 ) : kNone;
+        const int c1 = ( lane > 0 && ( bl & 4u ) ) ? ( int )( bl >> 8 ) : kNone;
+        const int c2 = ( lane < 31 && ( br & 1u ) ) ? ( int )( br >> 8 ) : kNone;
+        const int cand = min( c0, min( c1, c2 ) );
+        // minimum over the run (segmented inclusive min-scan, then the value of the run's last lane)
+        int v = cand;
 #pragma unroll
         for( int d = 1; d < 32; d <<= 1 )
         {
-            const int v = __shfl_up_sync( 0xFFFFFFFFu, before, d );
-            if( ( int )lane >= d ) before += v;
+            const int t = __shfl_up_sync( 0xFFFFFFFFu, v, d );
+            if( lane - d >= start ) v = min( v, t );
         }
-        int base = 0;
-        if( lane == 31u && before ) base = atomicAdd( &s_n, before );
-        base = __shfl_sync( 0xFFFFFFFFu, base, 31 );
-        int slot = base + before - mine;
-        if( want & 8u ) s_req[ slot++ ] = ( uint32_t )idx << 16 | ( uint32_t )( idx + 1 );
-        if( want & 2u ) s_req[ slot++ ] = ( uint32_t )idx << 16 | ( uint32_t )( idx + kTW );
-        if( want & 1u ) s_req[ slot++ ] = ( uint32_t )idx << 16 | ( uint32_t )( idx + kTW - 1 );
-        if( want & 4u ) s_req[ slot++ ] = ( uint32_t )idx << 16 | ( uint32_t )( idx + kTW + 1 );
+        v = __shfl_sync( 0xFFFFFFFFu, v, end );
+        const int label = min( v, ly * kTW + ( lx - lane + start ) ); // (no link downwards: the run's first pixel)
+        s_lab[ idx ] = label;
+        __syncwarp();
+        // a pixel that inherits another label than its run's joins two components of the rows below (rare); both trees lie in
+        // this warp's own rows
+        if( ( c0 != kNone && c0 != label ) || ( c1 != kNone && c1 != label ) || ( c2 != kNone && c2 != label ) )
+        {
+            if( c0 != kNone && c0 != label ) unite_halving( s_lab, c0, label );
+            if( c1 != kNone && c1 != label ) unite_halving( s_lab, c1, label );
+            if( c2 != kNone && c2 != label ) unite_halving( s_lab, c2, label );
+        }
+        below = ( uint32_t )label << 8 | node;
     }
     __syncthreads();
+    // links the scans did not see: across the band boundary and across the row groups; one thread per boundary pixel
     {
-        const int n = s_n;
-        for( int w = threadIdx.x; w < n; w += kThreads )
+        const int t = threadIdx.x;
+        int bx = -1, by = 0;
+        bool group_top = false;
+        if( t < 3 * kTW ) // top rows of the row groups 0..2: rows 3, 7, 11 — all their up links
         {
-            const uint32_t r = s_req[ w ];
-            unite_halving( s_lab, ( int )( r >> 16 ), ( int )( r & 0xFFFFu ) );
+            by = ( t / kTW ) * kGroupRows + kGroupRows - 1;
+            bx = t - ( t / kTW ) * kTW;
+            group_top = true;
+        }
+        else if( t < 3 * kTW + 2 * kTH ) // columns 31 and 32, all rows — the links that cross the boundary
+        {
+            const int u = t - 3 * kTW;
+            by = u >> 1;
+            bx = 31 + ( u & 1 );
+        }
+        if( bx >= 0 )
+        {
+            const int idx = by * kTW + bx;
+            const uint32_t node = s_g[ idx ];
+            if( group_top )
+            {
+                if( node & 2u ) unite_halving( s_lab, idx, idx + kTW );
+                if( node & 1u ) unite_halving( s_lab, idx, idx + kTW - 1 );
+                if( node & 4u ) unite_halving( s_lab, idx, idx + kTW + 1 );
+            }
+            else
+            {
+                const bool top = ( by % kGroupRows ) == kGroupRows - 1; // (already done above)
+                if( bx == 31 )
+                {
+                    if( node & 16u ) unite_halving( s_lab, idx, idx + 1 );
+                    if( ( node & 4u ) && !top ) unite_halving( s_lab, idx, idx + kTW + 1 );
+                }
+                else if( ( node & 1u ) && !top )
+                    unite_halving( s_lab, idx, idx + kTW - 1 );
+            }
         }
     }
     __syncthreads();
     for( int idx = threadIdx.x; idx < kTW * kTH; idx += kThreads )
     {
-        int ly = idx / kTW, lx = idx - ly * kTW, gx = x0 + lx, gy = y0 + ly;
-        if( gx >= a.width || gy >= a.height ) continue;
+        int ly = idx / kTW, lxx = idx - ly * kTW, px = x0 + lxx, py = y0 + ly;
+        if( px >= a.width || py >= a.height ) continue;
         int r = find_root( s_lab, idx );
         int ry = r / kTW, rx = r - ry * kTW;
-        out[ ( size_t )gy * a.width + gx ] = ( y0 + ry ) * a.width + ( x0 + rx ); // local min index == global min index within a tile
+        out[ ( size_t )py * a.width + px ] = ( y0 + ry ) * a.width + ( x0 + rx ); // local min index == global min index within a tile
     }
 }
 

@@ -750,6 +750,9 @@ __global__ void build_head_tables_kernel( const uint4* desc, const uint8_t* bloc
         {
             if( !( d[ k ] & kDescUsed ) ) continue;
             const uint32_t own = ( d[ k ] >> 13 ) & 255u, use = block_of[ own ];
+#ifdef PAR_WHATIF_DROPSHARED
+            if( use != own ) continue; // (what-if: as if a descriptor on a shared block could never mismatch)
+#endif
             if( ( use == own ) == ( pass == 0 ) ) out[ n++ ] = ( d[ k ] & ~( 255u << 13 ) & ~( kDescSlow | kDescMore ) ) | use << 13;
         }
     out[ 0 ] |= ( d[ 0 ] & kDescSlow ) | ( out[ 2 ] ? kDescMore : 0u );
@@ -1222,9 +1225,12 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
             }
             if( C::PACK )
             {
-                s_mask[ idx ] ^= ( uint32_t )mw[ 0 ];
-                const uint32_t hi = s_mask[ C::NC + idx ] ^ ( uint32_t )( mw[ 0 ] >> 32 );
-                s_mask[ C::NC + idx ] = hi | wide;
+                if( mw[ 0 ] | wide ) // (at small scales the third and fourth descriptors mostly sit on shared blocks: nothing to XOR)
+                {
+                    s_mask[ idx ] ^= ( uint32_t )mw[ 0 ];
+                    const uint32_t hi = s_mask[ C::NC + idx ] ^ ( uint32_t )( mw[ 0 ] >> 32 );
+                    s_mask[ C::NC + idx ] = hi | wide;
+                }
             }
             else
             {
