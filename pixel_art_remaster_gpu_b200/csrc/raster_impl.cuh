@@ -202,11 +202,20 @@ __device__ __forceinline__ void cover_polygon( const uint16_t* buf, int stride, 
     }
 }
 
-// 64-bit read-only load under a predicate, 0 otherwise (no branch: the compiler will not speculate a load on its own)
-__device__ __forceinline__ uint64_t ldg_u64_if( const uint64_t* p, bool pred )
+// 1 when a, b, c are not all equal, else 0: one three-input logic operation ((a ^ b) | (b ^ c)) and one minimum.  (As
+// inline PTX: written in C the compiler turns it back into two comparisons and a select.)
+__device__ __forceinline__ uint32_t not_one_colour( uint32_t a, uint32_t b, uint32_t c )
+{
+    uint32_t t;
+    asm( "{ .reg .b32 x; lop3.b32 x, %1, %2, %3, 0x7E; min.u32 %0, x, 1; }" : "=r"( t ) : "r"( a ), "r"( b ), "r"( c ) );
+    return t;
+}
+
+// 64-bit read-only load when `flag` is not zero, 0 otherwise (no branch: the compiler will not speculate a load on its own)
+__device__ __forceinline__ uint64_t ldg_u64_if( const uint64_t* p, uint32_t flag )
 {
     uint64_t v = 0ull;
-    asm( "{ .reg .pred q; setp.ne.u32 q, %2, 0; @q ld.global.nc.u64 %0, [%1]; }" : "+l"( v ) : "l"( p ), "r"( ( uint32_t )pred ) );
+    asm( "{ .reg .pred q; setp.ne.u32 q, %2, 0; @q ld.global.nc.u64 %0, [%1]; }" : "+l"( v ) : "l"( p ), "r"( flag ) );
     return v;
 }
 
@@ -776,7 +785,7 @@ __device__ __forceinline__ void link_slots( const SmoothTablePtrs& st, const uin
     for( int k = 0; k < NS; k++ )
     {
         const uint32_t d = desc[ k ];
-        const bool used = ( d & kDescUsed ) != 0u;
+        const uint32_t used = d & kDescUsed;
         const uint32_t id = ( base[ d & 255u ] >> ( ( d >> 8 ) & 31u ) ) & 31u;
         const uint64_t* le = st.link + ( size_t )( ( ( d >> 8 ) & ( 255u << 5 ) ) | id ) * E::EW;
 #pragma unroll
@@ -848,7 +857,7 @@ __device__ __forceinline__ uint64_t smooth_lookup( const SmoothTablePtrs& st, co
 #pragma unroll
         for( int w = 0; w < E::EW; w++ ) m[ w ] = __ldg( e + w );
     }
-    more = ( head.x & kDescMore ) != 0u;
+    more = ( int32_t )head.x < 0; // kDescMore
 #ifndef PAR_WHATIF_NOLINKS
     const uint32_t desc[ 2 ] = { head.x, head.y };
     link_slots< S, 2 >( st, keys_at_cell, desc, m, flags ); // (a key that always takes the geometric path has no descriptors)
@@ -856,6 +865,13 @@ __device__ __forceinline__ uint64_t smooth_lookup( const SmoothTablePtrs& st, co
     more = false;
 #endif
     // the flag bits of word 0 were XORed along with the masks: take them from the OR (the CUT entry has none)
+    if constexpr( C::PACK )
+    {
+        // (both flags live in the high word; kDescSlow is MISMATCH's bit there, and bit 30 of a descriptor is never set)
+        static_assert( ( E::MISMATCH >> 32 ) == kDescSlow && ( E::FLAG >> 32 ) == ( 1u << 30 ) && kDescMore == ( 1u << 31 ), "flag positions" );
+        const uint32_t rare_hi = ( ( uint32_t )( flags >> 32 ) | head.x ) & ( uint32_t )( ( E::FLAG | E::MISMATCH ) >> 32 );
+        return ( uint64_t )rare_hi << 32;
+    }
     return ( flags & ( E::FLAG | E::MISMATCH ) ) | ( ( head.x & kDescSlow ) ? E::MISMATCH : 0ull );
 }
 
@@ -1100,8 +1116,9 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
                 const uint32_t* c = s_col + ( cy + 1 ) * C::KW + ( cx + 1 );
                 const uint32_t l = c[ -1 ], r = c[ 1 ], d = c[ -C::KW ], u = c[ C::KW ];
                 const uint32_t dl = c[ -C::KW - 1 ], dr = c[ -C::KW + 1 ], ul = c[ C::KW - 1 ], ur = c[ C::KW + 1 ];
-                cf = ( ( l != dl || dl != d ) ? 1u : 0u ) | ( ( r != dr || dr != d ) ? 2u : 0u ) | ( ( r != ur || ur != u ) ? 4u : 0u ) |
-                     ( ( l != ul || ul != u ) ? 8u : 0u );
+                // corner c stays when the three other pixels around it are not one colour: one three-input logic operation and one
+                // minimum per corner (the comparisons as predicates took seven instructions more per cell)
+                cf = not_one_colour( l, dl, d ) + 2u * not_one_colour( r, dr, d ) + 4u * not_one_colour( r, ur, u ) + 8u * not_one_colour( l, ul, u );
             }
             typedef Entry< S > E;
             uint64_t mw[ E::EW ];

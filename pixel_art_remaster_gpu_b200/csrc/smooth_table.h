@@ -64,7 +64,7 @@ struct SmoothRecord
 //               kHeadRowWords + 1 (so that it is not negative)
 //       [8,13)  shift of the ID field for direction 7 - e in that word
 //       [13,21) the class's block of the link table   [21] used
-//       slot 0 only: [30] the key has a third descriptor, [31] the key always takes the geometric path.
+//       slot 0 only: [31] the key has a third descriptor, [29] the key always takes the geometric path.
 //   Per SCALE the kernel reads a copy of this (built on the device next to the link table, raster_kernels.cu): at 4x more
 //   than half of the classes have an empty mask for every ID that fits them — the loop between the hull and the smoothed
 //   outline around a blended vertex is a sliver that often holds no sample — so all their block says is which IDs do NOT
@@ -83,7 +83,9 @@ struct SmoothRecord
 //   comparison the kernel used to make per cell is made once, when the table is built).
 constexpr int kNbrIds = 32;
 constexpr int kHeadRowWords = 72; // words per row of staged cell words: 36 x-words, then 36 y-words (raster_impl.cuh Cfg::KP)
-constexpr uint32_t kDescSlow = 1u << 31, kDescMore = 1u << 30, kDescUsed = 1u << 21;
+// (kDescSlow sits where MISMATCH sits in the high word of a window-form entry, kDescMore in the sign bit: the kernel folds
+// the first into its flag test with one logic operation and tests the second with one comparison)
+constexpr uint32_t kDescSlow = 1u << 29, kDescMore = 1u << 31, kDescUsed = 1u << 21;
 
 // geometry of one class, consumed by the device table builder (quarter-pixel units)
 struct LinkClass
