@@ -1,5 +1,5 @@
 """DRAM traffic of the raster kernel from an ncu report (dram__bytes_read.sum, dram__bytes_write.sum) -> profiles/<name>
-(bench.py reads profiles/r2_raster_traffic.json for roofline.traffic).
+(bench.py reads the newest profiles/r*_raster_traffic.json for roofline.traffic).
 Usage: python tools/ncu_traffic.py report.ncu-rep frames_in_the_profiled_launch [output name]"""
 import csv, io, json, subprocess, sys
 rep, frames = sys.argv[1], int(sys.argv[2])
