@@ -269,7 +269,10 @@ __global__ void __launch_bounds__( kThreads ) cc_flatten_kernel( LabelArgs a )
     const size_t n = ( size_t )blockIdx.x * kThreads + threadIdx.x;
     if( n >= frame_px ) return;
     int* lab = a.labels + ( size_t )blockIdx.y * frame_px;
-    lab[ n ] = find_root( lab, ( int )n );
+    // (most pixels already hold their root after the seam pass — only the labels of components that were joined across a
+    // seam change — so the label is only written back when it differs: half of this kernel's traffic)
+    const int l = lab[ n ], r = find_root( lab, l );
+    if( r != l ) lab[ n ] = r;
 }
 
 } // namespace

@@ -12,18 +12,21 @@
 // (top-left rule).  Coverage is an even-odd crossing count in exact integer arithmetic: vertices
 // are multiples of 1/64, samples odd multiples of 1/(2s); both are scaled to units of 1/(128 s).
 //
-// Design (B200): one CTA per 32x32 (s <= 4) / 32x16 tile of source pixels, 24 KB of shared memory, five / four CTAs
+// Design (B200): one CTA per 32x32 (s <= 4) / 32x16 tile of source pixels, 24.6 KB of shared memory, five / four CTAs
 // per SM.  (1) The final-graph bytes and the BGR bytes of the tile (+halo) are staged in shared memory by two TMA
 // bulk-tensor copies (zero fill outside the image; plain loads when rows are not 16-byte multiples) and turned, four
-// pixels per thread, into 12-bit cell keys and RGBA words.  (2) Every cell of tile + 1 halo gets a coverage bitmask of
+// pixels per thread, into RGBA words and two 32-bit cell words per cell: the 12-bit cell key and the IDs of the cell's
+// eight neighbour records (one 8-byte gather per staged cell).  (2) Every cell of tile + 1 halo gets a coverage bitmask of
 // the (s + 2h)^2 samples it can reach.  Cells whose polygon is their hull (interior nodes, or subdivision off) copy it
 // from a per-scale 4096-entry mask table.  Smoothed cells are handled in tile order and do not build their polygon
 // at all: even-odd coverage is XOR-linear in the polygon's edges, so the mask is the XOR of a few precomputed pieces
 // (smooth_table.h) — one CUT entry for the cell's own key and kept corners, one LINK entry per shared edge with a
-// blended end, indexed by a 16-bit record read from the neighbour's key.  The tables are content-independent and built
-// once per context and scale by this file's own coverage code.  The few cells they cannot express take the geometric
+// blended end, indexed by the class's block and the 5-bit ID found in the neighbour's staged cell word (no neighbour
+// record is gathered).  The tables are content-independent; the masks and the descriptor tables are built once per
+// context and scale by raster_impl.cuh's own coverage code (classes whose masks are empty at a scale share one block per
+// ID range).  The few cells the tables cannot express take the geometric
 // path: one thread per cell, the polygon (hull from the cell table, corner cutting in exact 1/64-px integers) streamed
-// into a small per-thread vertex buffer in shared memory, then a converged loop over its edges toggling the sample
+// into a small per-thread vertex buffer, then a converged loop over its edges toggling the sample
 // rows each edge crosses.  Geometry never touches HBM.  (3) One thread per source pixel resolves its s x s output
 // pixels with bit operations over the 3x3 neighbourhood's masks in priority order (for s <= 4 on whole-cell bit sets:
 // the masks are kept in a "window form" whose fields are already positioned on the reader's pixels) and writes whole
