@@ -83,11 +83,11 @@ __device__ __forceinline__ void unite( int* lab, int a, int b )
 //    between the lanes by shuffle), and a run takes the minimum over its pixels (a segmented min-scan: five shuffle steps)
 //    — or, with no link downwards, the index of its first pixel.  Labels only ever point to a smaller index of the same
 //    component, so the array is a union-find forest from the start and almost every pixel already holds its root;
-//  * a union is only needed where a run inherits two DIFFERENT labels (it joins two components of the rows below): those
-//    few go straight to the shared-memory forest (atomicMin, link-by-minimum).
-// What the warps cannot see in their registers — the links across the band boundary (columns 31 | 32) and across the row
-// groups (rows 3 | 4, 7 | 8, 11 | 12) — is united afterwards, one thread per boundary pixel.  Before: every vertical link
-// was classified and queued per pixel (303 lane instructions per pixel); now ~100.
+//  * a union is only needed where a pixel inherits a label that is not its run's (it joins two components of the rows below:
+//    0.18 per pixel on the busy bench frames); those, and the links the warps cannot see in their registers — across the band
+//    boundary (columns 31 | 32) and across the row groups (rows 3 | 4, 7 | 8, 11 | 12) — are appended to one list (a ballot and
+//    one shared-memory atomic per warp) and executed afterwards one per thread with full warps (executing them inside the row
+//    step cost every warp the union's loops for three active lanes, row after row).
 __device__ __forceinline__ void unite_halving( int* lab, int a, int b )
 {
     for( ;; )
@@ -112,15 +112,30 @@ constexpr int kGroupRows = kTH / 4; // rows a warp scans: kTH / ( warps per band
 __global__ void __launch_bounds__( kThreads ) cc_tile_kernel( LabelArgs a )
 {
     __shared__ int s_lab[ kTW * kTH ];
-    __shared__ uint8_t s_g[ kTW * kTH ]; // node bytes with the links that leave the tile (or the image) removed
+    // unions to make, a << 16 | b (tile-local indices): at most three inherited labels per pixel, plus the links the scans do
+    // not see (three per pixel of a row group's top row, two per row at the band boundary)
+    __shared__ uint32_t s_req[ 3 * kTW * kTH + 3 * 3 * kTW + 4 * kTH ];
+    __shared__ int s_n;
+    if( threadIdx.x == 0 ) s_n = 0;
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH, f = blockIdx.z;
     const size_t frame_px = ( size_t )a.width * a.height;
     const uint8_t* g = a.graph + ( size_t )f * frame_px;
     int* out = a.labels + ( size_t )f * frame_px;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    static_assert( kTW == 64 && kThreads == 256 && kGroupRows * ( kThreads / 32 ) * 32 == kTW * kTH && 3 * kTW + 2 * kTH <= kThreads, "2 bands x 4 row groups" );
-    const int lx = ( warp & 1 ) * 32 + lane, row0 = ( warp >> 1 ) * kGroupRows;
+    static_assert( kTW == 64 && kThreads == 256 && kGroupRows * ( kThreads / 32 ) * 32 == kTW * kTH, "2 bands x 4 row groups" );
+    const int band = warp & 1, lx = band * 32 + lane, row0 = ( warp >> 1 ) * kGroupRows;
     const int gx = x0 + lx;
+    const uint32_t lanes_below = ( 1u << lane ) - 1u;
+    __syncthreads();
+    // the lanes that want a union append it to the list: one shared-memory atomic per call and warp
+    auto request = [ & ]( bool want, int ia, int ib ) {
+        const uint32_t votes = __ballot_sync( 0xFFFFFFFFu, want );
+        if( votes == 0u ) return;
+        int base = 0;
+        if( lane == 0 ) base = atomicAdd( &s_n, __popc( votes ) );
+        base = __shfl_sync( 0xFFFFFFFFu, base, 0 );
+        if( want ) s_req[ base + __popc( votes & lanes_below ) ] = ( uint32_t )ia << 16 | ( uint32_t )ib;
+    };
     uint32_t below = 0u; // label (tile-local index) << 8 | node byte of the pixel below this lane's; node 0 = no row below in this group
 #pragma unroll
     for( int k = 0; k < kGroupRows; k++ )
@@ -135,10 +150,9 @@ __global__ void __launch_bounds__( kThreads ) cc_tile_kernel( LabelArgs a )
             if( !up_ok ) node &= ~( 1u | 2u | 4u );
             if( lx == 0 ) node &= ~1u;
         }
-        s_g[ idx ] = ( uint8_t )node;
         // horizontal runs inside the band: the run starts after the last lane below me that is NOT linked to its right
         const uint32_t linked = __ballot_sync( 0xFFFFFFFFu, ( node & 16u ) != 0u && lane < 31 );
-        const uint32_t breaks_below = ~linked & ( ( 1u << lane ) - 1u );
+        const uint32_t breaks_below = ~linked & lanes_below;
         const int start = breaks_below ? 32 - __clz( ( int )breaks_below ) : 0;
         const int end = lane + __ffs( ( int )( ~linked >> lane ) ) - 1; // (bit 31 of ~linked is always set)
         // labels inherited from the row below: its pixel under me links up (bit 1), the one to the right up-left (bit 0), the
@@ -160,56 +174,30 @@ __global__ void __launch_bounds__( kThreads ) cc_tile_kernel( LabelArgs a )
         v = __shfl_sync( 0xFFFFFFFFu, v, end );
         const int label = min( v, ly * kTW + ( lx - lane + start ) ); // (no link downwards: the run's first pixel)
         s_lab[ idx ] = label;
-        __syncwarp();
-        // a pixel that inherits another label than its run's joins two components of the rows below (rare); both trees lie in
-        // this warp's own rows
-        if( ( c0 != kNone && c0 != label ) || ( c1 != kNone && c1 != label ) || ( c2 != kNone && c2 != label ) )
+        // a pixel that inherits another label than its run's joins two components of the rows below
+        request( c0 != kNone && c0 != label, c0, label );
+        request( c1 != kNone && c1 != label, c1, label );
+        request( c2 != kNone && c2 != label, c2, label );
+        // the links the scans do not see: upwards out of the row group (its top row; the tile's top row has none left), and
+        // across the band boundary (columns 31 | 32)
+        if( k == kGroupRows - 1 )
         {
-            if( c0 != kNone && c0 != label ) unite_halving( s_lab, c0, label );
-            if( c1 != kNone && c1 != label ) unite_halving( s_lab, c1, label );
-            if( c2 != kNone && c2 != label ) unite_halving( s_lab, c2, label );
+            request( ( node & 2u ) != 0u, idx, idx + kTW );
+            request( ( node & 1u ) != 0u, idx, idx + kTW - 1 );
+            request( ( node & 4u ) != 0u, idx, idx + kTW + 1 );
         }
+        else
+            request( ( band == 0 && lane == 31 && ( node & 4u ) ) || ( band == 1 && lane == 0 && ( node & 1u ) ), idx, band == 0 ? idx + kTW + 1 : idx + kTW - 1 );
+        request( band == 0 && lane == 31 && ( node & 16u ), idx, idx + 1 );
         below = ( uint32_t )label << 8 | node;
     }
     __syncthreads();
-    // links the scans did not see: across the band boundary and across the row groups; one thread per boundary pixel
     {
-        const int t = threadIdx.x;
-        int bx = -1, by = 0;
-        bool group_top = false;
-        if( t < 3 * kTW ) // top rows of the row groups 0..2: rows 3, 7, 11 — all their up links
+        const int n = s_n;
+        for( int w = threadIdx.x; w < n; w += kThreads )
         {
-            by = ( t / kTW ) * kGroupRows + kGroupRows - 1;
-            bx = t - ( t / kTW ) * kTW;
-            group_top = true;
-        }
-        else if( t < 3 * kTW + 2 * kTH ) // columns 31 and 32, all rows — the links that cross the boundary
-        {
-            const int u = t - 3 * kTW;
-            by = u >> 1;
-            bx = 31 + ( u & 1 );
-        }
-        if( bx >= 0 )
-        {
-            const int idx = by * kTW + bx;
-            const uint32_t node = s_g[ idx ];
-            if( group_top )
-            {
-                if( node & 2u ) unite_halving( s_lab, idx, idx + kTW );
-                if( node & 1u ) unite_halving( s_lab, idx, idx + kTW - 1 );
-                if( node & 4u ) unite_halving( s_lab, idx, idx + kTW + 1 );
-            }
-            else
-            {
-                const bool top = ( by % kGroupRows ) == kGroupRows - 1; // (already done above)
-                if( bx == 31 )
-                {
-                    if( node & 16u ) unite_halving( s_lab, idx, idx + 1 );
-                    if( ( node & 4u ) && !top ) unite_halving( s_lab, idx, idx + kTW + 1 );
-                }
-                else if( ( node & 1u ) && !top )
-                    unite_halving( s_lab, idx, idx + kTW - 1 );
-            }
+            const uint32_t r = s_req[ w ];
+            unite_halving( s_lab, ( int )( r >> 16 ), ( int )( r & 0xFFFFu ) );
         }
     }
     __syncthreads();
