@@ -251,16 +251,29 @@ __global__ void __launch_bounds__( kThreads ) cc_seam_kernel( LabelArgs a )
     }
 }
 
+// Flatten pass: every pixel replaces its label by its root.  Four pixels per thread (one 128-bit load, four independent
+// root walks in flight) when the frame size allows; most pixels already hold their root after the seam pass — only the
+// labels of components that were joined across a seam change — so a label is only written back when it differs.
+template< bool kVec4 >
 __global__ void __launch_bounds__( kThreads ) cc_flatten_kernel( LabelArgs a )
 {
     const size_t frame_px = ( size_t )a.width * a.height;
-    const size_t n = ( size_t )blockIdx.x * kThreads + threadIdx.x;
-    if( n >= frame_px ) return;
     int* lab = a.labels + ( size_t )blockIdx.y * frame_px;
-    // (most pixels already hold their root after the seam pass — only the labels of components that were joined across a
-    // seam change — so the label is only written back when it differs: half of this kernel's traffic)
-    const int l = lab[ n ], r = find_root( lab, l );
-    if( r != l ) lab[ n ] = r;
+    if( kVec4 )
+    {
+        const size_t q = ( size_t )blockIdx.x * kThreads + threadIdx.x;
+        if( 4 * q >= frame_px ) return;
+        const int4 l = *reinterpret_cast< const int4* >( lab + 4 * q );
+        const int r0 = find_root( lab, l.x ), r1 = find_root( lab, l.y ), r2 = find_root( lab, l.z ), r3 = find_root( lab, l.w );
+        if( r0 != l.x || r1 != l.y || r2 != l.z || r3 != l.w ) *reinterpret_cast< int4* >( lab + 4 * q ) = make_int4( r0, r1, r2, r3 );
+    }
+    else
+    {
+        const size_t n = ( size_t )blockIdx.x * kThreads + threadIdx.x;
+        if( n >= frame_px ) return;
+        const int l = lab[ n ], r = find_root( lab, l );
+        if( r != l ) lab[ n ] = r;
+    }
 }
 
 } // namespace
@@ -283,7 +296,11 @@ cudaError_t launch_cc_labels( const LabelArgs& a, cudaStream_t stream, int* n_la
         LabelArgs part = a;
         part.labels = a.labels + ( size_t )f0 * a.width * a.height;
         part.n_frames = a.n_frames - f0 < 65535 ? a.n_frames - f0 : 65535;
-        cc_flatten_kernel<<< dim3( ( unsigned )( ( ( size_t )a.width * a.height + kThreads - 1 ) / kThreads ), part.n_frames ), kThreads, 0, stream >>>( part );
+        const size_t px = ( size_t )a.width * a.height;
+        if( px % 4 == 0 && ( reinterpret_cast< uintptr_t >( part.labels ) & 15u ) == 0 )
+            cc_flatten_kernel< true ><<< dim3( ( unsigned )( ( px / 4 + kThreads - 1 ) / kThreads ), part.n_frames ), kThreads, 0, stream >>>( part );
+        else
+            cc_flatten_kernel< false ><<< dim3( ( unsigned )( ( px + kThreads - 1 ) / kThreads ), part.n_frames ), kThreads, 0, stream >>>( part );
     }
     if( n_launches ) *n_launches = 3;
     return cudaGetLastError();
