@@ -11,7 +11,7 @@
 // shared memory — no seams, no global atomics, no flatten kernel, but one CTA per SM, two CTA-wide barriers per 1024 pixels
 // and CAS loops for the 16-bit minimum: 2.08 ms per 1024 frames against 0.91 ms for the three kernels below,
 // profiles/r2e_stage_times_*.)
-//   (1) tile pass: one CTA per 64x16 tile builds the tile's forest in SHARED memory (a warp scans a band of rows with
+//   (1) tile pass: one CTA per 64x32 tile builds the tile's forest in SHARED memory (a warp scans a band of rows with
 //       the labels in registers: horizontal runs by ballot, labels inherited from the row below by shuffle, a union only
 //       where a run joins two components; flatten) and writes tile-local roots as global indices;
 //   (2) seam pass: one thread per seam pixel unions across the seams with global atomicMin;
@@ -25,7 +25,7 @@ namespace par {
 namespace {
 
 #ifndef PAR_CC_TH
-#define PAR_CC_TH 16
+#define PAR_CC_TH 32
 #endif
 constexpr int kTW = 64, kTH = PAR_CC_TH, kThreads = 256;
 
@@ -76,7 +76,7 @@ __device__ __forceinline__ void unite( int* lab, int a, int b )
     }
 }
 
-// Tile pass (round 3).  A warp owns a band of 32 columns x 4 rows of the 64 x 16 tile and scans its rows bottom-up, a
+// Tile pass (round 3).  A warp owns a band of 32 columns x 8 rows of the 64 x 32 tile and scans its rows bottom-up, a
 // lane per column, labels in registers:
 //  * horizontal runs from one ballot of the "linked to the right" bits (as before);
 //  * a pixel INHERITS the label of a pixel it is linked to in the row below (that row's labels and node bytes travel
@@ -85,7 +85,7 @@ __device__ __forceinline__ void unite( int* lab, int a, int b )
 //    component, so the array is a union-find forest from the start and almost every pixel already holds its root;
 //  * a union is only needed where a pixel inherits a label that is not its run's (it joins two components of the rows below:
 //    0.18 per pixel on the busy bench frames); those, and the links the warps cannot see in their registers — across the band
-//    boundary (columns 31 | 32) and across the row groups (rows 3 | 4, 7 | 8, 11 | 12) — are appended to one list (a ballot and
+//    boundary (columns 31 | 32) and across the row groups (rows 7 | 8, 15 | 16, 23 | 24) — are appended to one list (a ballot and
 //    one shared-memory atomic per warp) and executed afterwards one per thread with full warps (executing them inside the row
 //    step cost every warp the union's loops for three active lanes, row after row).
 __device__ __forceinline__ void unite_halving( int* lab, int a, int b )
