@@ -85,9 +85,10 @@ __device__ __forceinline__ void unite( int* lab, int a, int b )
 //    component, so the array is a union-find forest from the start and almost every pixel already holds its root;
 //  * a union is only needed where a pixel inherits a label that is not its run's (it joins two components of the rows below:
 //    0.18 per pixel on the busy bench frames); those, and the links the warps cannot see in their registers — across the band
-//    boundary (columns 31 | 32) and across the row groups (rows 7 | 8, 15 | 16, 23 | 24) — are appended to one list (a ballot and
-//    one shared-memory atomic per warp) and executed afterwards one per thread with full warps (executing them inside the row
-//    step cost every warp the union's loops for three active lanes, row after row).
+//    boundary (columns 31 | 32) and across the row groups (rows 7 | 8, 15 | 16, 23 | 24) — are appended to the warp's own list (a ballot
+//    and two population counts per call, the count in a register; one list for the tile cost a shared-memory atomic and a
+//    shuffle per call) and executed afterwards by the same warp with full lanes (executing them inside the row step cost every
+//    warp the union's loops for three active lanes, row after row).
 __device__ __forceinline__ void unite_halving( int* lab, int a, int b )
 {
     for( ;; )
@@ -108,15 +109,15 @@ __device__ __forceinline__ void unite_halving( int* lab, int a, int b )
 }
 
 constexpr int kGroupRows = kTH / 4; // rows a warp scans: kTH / ( warps per band )
+constexpr int kWarpReq = 3 * 32 * kGroupRows + 3 * 32 + 2 * kGroupRows; // capacity of a warp's union list
 
 __global__ void __launch_bounds__( kThreads ) cc_tile_kernel( LabelArgs a )
 {
     __shared__ int s_lab[ kTW * kTH ];
-    // unions to make, a << 16 | b (tile-local indices): at most three inherited labels per pixel, plus the links the scans do
-    // not see (three per pixel of a row group's top row, two per row at the band boundary)
-    __shared__ uint32_t s_req[ 3 * kTW * kTH + 3 * 3 * kTW + 4 * kTH ];
-    __shared__ int s_n;
-    if( threadIdx.x == 0 ) s_n = 0;
+    // unions to make, a << 16 | b (tile-local indices), one list per warp (no atomics: the warp's count lives in a register):
+    // at most three inherited labels per pixel, three links per pixel of the row group's top row, and two fixed slots per row
+    // for the band boundary (written by the one lane that sits on it; 0 = nothing to do)
+    __shared__ uint32_t s_req[ ( kThreads / 32 ) * kWarpReq ];
     const int x0 = blockIdx.x * kTW, y0 = blockIdx.y * kTH, f = blockIdx.z;
     const size_t frame_px = ( size_t )a.width * a.height;
     const uint8_t* g = a.graph + ( size_t )f * frame_px;
@@ -126,16 +127,15 @@ __global__ void __launch_bounds__( kThreads ) cc_tile_kernel( LabelArgs a )
     const int band = warp & 1, lx = band * 32 + lane, row0 = ( warp >> 1 ) * kGroupRows;
     const int gx = x0 + lx;
     const uint32_t lanes_below = ( 1u << lane ) - 1u;
-    __syncthreads();
-    // the lanes that want a union append it to the list: one shared-memory atomic per call and warp
+    uint32_t* req = s_req + warp * kWarpReq;
+    uint32_t* req_edge = req + kWarpReq - 2 * kGroupRows;
+    int n_req = 0; // (warp-uniform)
     auto request = [ & ]( bool want, int ia, int ib ) {
         const uint32_t votes = __ballot_sync( 0xFFFFFFFFu, want );
-        if( votes == 0u ) return;
-        int base = 0;
-        if( lane == 0 ) base = atomicAdd( &s_n, __popc( votes ) );
-        base = __shfl_sync( 0xFFFFFFFFu, base, 0 );
-        if( want ) s_req[ base + __popc( votes & lanes_below ) ] = ( uint32_t )ia << 16 | ( uint32_t )ib;
+        if( want ) req[ n_req + __popc( votes & lanes_below ) ] = ( uint32_t )ia << 16 | ( uint32_t )ib;
+        n_req += __popc( votes );
     };
+    const bool edge_lane = band == 0 ? lane == 31 : lane == 0;
     uint32_t below = 0u; // label (tile-local index) << 8 | node byte of the pixel below this lane's; node 0 = no row below in this group
 #pragma unroll
     for( int k = 0; k < kGroupRows; k++ )
@@ -180,25 +180,28 @@ __global__ void __launch_bounds__( kThreads ) cc_tile_kernel( LabelArgs a )
         request( c2 != kNone && c2 != label, c2, label );
         // the links the scans do not see: upwards out of the row group (its top row; the tile's top row has none left), and
         // across the band boundary (columns 31 | 32)
+        uint32_t edge_diag = 0u;
         if( k == kGroupRows - 1 )
         {
             request( ( node & 2u ) != 0u, idx, idx + kTW );
             request( ( node & 1u ) != 0u, idx, idx + kTW - 1 );
             request( ( node & 4u ) != 0u, idx, idx + kTW + 1 );
         }
-        else
-            request( ( band == 0 && lane == 31 && ( node & 4u ) ) || ( band == 1 && lane == 0 && ( node & 1u ) ), idx, band == 0 ? idx + kTW + 1 : idx + kTW - 1 );
-        request( band == 0 && lane == 31 && ( node & 16u ), idx, idx + 1 );
+        else if( band == 0 ? ( node & 4u ) != 0u : ( node & 1u ) != 0u )
+            edge_diag = ( uint32_t )idx << 16 | ( uint32_t )( band == 0 ? idx + kTW + 1 : idx + kTW - 1 );
+        if( edge_lane )
+        {
+            req_edge[ 2 * k ] = edge_diag;
+            req_edge[ 2 * k + 1 ] = ( band == 0 && ( node & 16u ) ) ? ( uint32_t )idx << 16 | ( uint32_t )( idx + 1 ) : 0u;
+        }
         below = ( uint32_t )label << 8 | node;
     }
     __syncthreads();
+    // every warp executes its own list (the lists of a tile's eight warps are about equally long), then its edge slots
+    for( int w = lane; w < n_req + 2 * kGroupRows; w += 32 )
     {
-        const int n = s_n;
-        for( int w = threadIdx.x; w < n; w += kThreads )
-        {
-            const uint32_t r = s_req[ w ];
-            unite_halving( s_lab, ( int )( r >> 16 ), ( int )( r & 0xFFFFu ) );
-        }
+        const uint32_t r = w < n_req ? req[ w ] : req_edge[ w - n_req ];
+        unite_halving( s_lab, ( int )( r >> 16 ), ( int )( r & 0xFFFFu ) );
     }
     __syncthreads();
     for( int idx = threadIdx.x; idx < kTW * kTH; idx += kThreads )
