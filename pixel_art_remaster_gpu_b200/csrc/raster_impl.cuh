@@ -211,6 +211,30 @@ __device__ __forceinline__ uint32_t not_one_colour( uint32_t a, uint32_t b, uint
     return t;
 }
 
+// a rows-form table entry (four 64-bit words, 32-byte aligned) by two 128-bit read-only loads: a gather costs the LSU a
+// wavefront per instruction and line, so four 64-bit loads of the same entry cost twice what these do
+__device__ __forceinline__ void ldg_entry4( const uint64_t* e, uint64_t* m )
+{
+    const ulonglong2 a = __ldg( reinterpret_cast< const ulonglong2* >( e ) ), b = __ldg( reinterpret_cast< const ulonglong2* >( e ) + 1 );
+    m[ 0 ] = a.x;
+    m[ 1 ] = a.y;
+    m[ 2 ] = b.x;
+    m[ 3 ] = b.y;
+}
+// ... XORed into m when `flag` is not zero (no branch); returns word 0 of the entry (0 when not loaded)
+__device__ __forceinline__ uint64_t ldg_entry4_xor_if( const uint64_t* e, uint32_t flag, uint64_t* m )
+{
+    uint64_t v0 = 0ull, v1 = 0ull, v2 = 0ull, v3 = 0ull;
+    asm( "{ .reg .pred q; setp.ne.u32 q, %5, 0; @q ld.global.nc.v2.u64 {%0, %1}, [%4]; @q ld.global.nc.v2.u64 {%2, %3}, [%4 + 16]; }"
+         : "+l"( v0 ), "+l"( v1 ), "+l"( v2 ), "+l"( v3 )
+         : "l"( e ), "r"( flag ) );
+    m[ 0 ] ^= v0;
+    m[ 1 ] ^= v1;
+    m[ 2 ] ^= v2;
+    m[ 3 ] ^= v3;
+    return v0;
+}
+
 // 64-bit read-only load when `flag` is not zero, 0 otherwise (no branch: the compiler will not speculate a load on its own)
 __device__ __forceinline__ uint64_t ldg_u64_if( const uint64_t* p, uint32_t flag )
 {
@@ -538,7 +562,10 @@ __global__ void build_mask_lut_kernel( CellTablePtrs tab, uint32_t* lut )
         for( int r = 0; r < C::R; r++ ) rows[ r ] = 0u;
         RowToggle tg{ rows, 1 };
         cover_polygon< S, C::R >( verts, 1, poly, C::S_FIRST, C::S_FIRST, tg, lo, hi );
-        for( int r = 0; r < C::R; r++ ) lut[ C::R * key + r ] = rows[ r ];
+        // rows form: the table holds entries (Entry< S >: four rows per 64-bit word, four words per key)
+        uint64_t* e = reinterpret_cast< uint64_t* >( lut ) + ( size_t )key * 4;
+        for( int w = 0; w < 4; w++ ) e[ w ] = 0ull;
+        for( int r = 0; r < C::R; r++ ) e[ r >> 2 ] |= ( uint64_t )( rows[ r ] & 0x7FFFu ) << ( 16 * ( r & 3 ) );
     }
 }
 
@@ -548,7 +575,9 @@ __global__ void build_mask_lut_kernel( CellTablePtrs tab, uint32_t* lut )
 template< int S >
 struct Entry
 {
-    static constexpr int EW = Cfg< S >::PACK ? 1 : ( Cfg< S >::R * 2 + 7 ) / 8;
+    // (rows form: always four words — 32 bytes, so that an entry is two aligned 128-bit loads; at 5x .. 7x the fourth word is padding)
+    static constexpr int EW = Cfg< S >::PACK ? 1 : 4;
+    static_assert( Cfg< S >::PACK || ( Cfg< S >::R * 2 + 7 ) / 8 <= 4, "sixteen rows at most" );
     static constexpr uint64_t FLAG = Cfg< S >::PACK ? ( ( uint64_t )Cfg< S >::WIDE << 32 ) : ( 1ull << 15 );
     // link table only: the neighbour's record does not fit the class (its end / start vertex is not the blended vertex, or it
     // has no edge in that direction) — the cell takes the geometric path.  A bit no mask uses: bit 13 of the corner field
@@ -788,12 +817,17 @@ __device__ __forceinline__ void link_slots( const SmoothTablePtrs& st, const uin
         const uint32_t used = d & kDescUsed;
         const uint32_t id = ( base[ d & 255u ] >> ( ( d >> 8 ) & 31u ) ) & 31u;
         const uint64_t* le = st.link + ( size_t )( ( ( d >> 8 ) & ( 255u << 5 ) ) | id ) * E::EW;
-#pragma unroll
-        for( int w = 0; w < E::EW; w++ )
+        if constexpr( E::EW == 4 )
+            flags |= ldg_entry4_xor_if( le, used, m );
+        else
         {
-            const uint64_t v = ldg_u64_if( le + w, used ); // (an unused slot loads nothing)
-            if( w == 0 ) flags |= v;
-            m[ w ] ^= v;
+#pragma unroll
+            for( int w = 0; w < E::EW; w++ )
+            {
+                const uint64_t v = ldg_u64_if( le + w, used ); // (an unused slot loads nothing)
+                if( w == 0 ) flags |= v;
+                m[ w ] ^= v;
+            }
         }
     }
 }
@@ -836,17 +870,14 @@ __device__ __forceinline__ uint64_t smooth_lookup( const SmoothTablePtrs& st, co
     uint64_t flags = 0ull;
     if( cflags & 16u ) // checkTJunction's early exit keeps every cut vertex: the plain hull
     {
-        if( C::PACK )
+        if constexpr( C::PACK )
         {
             const uint2 v = __ldg( reinterpret_cast< const uint2* >( mask_lut ) + key );
             m[ 0 ] = ( uint64_t )v.y << 32 | v.x;
         }
         else
         {
-#pragma unroll
-            for( int w = 0; w < E::EW; w++ ) m[ w ] = 0ull;
-#pragma unroll
-            for( int r = 0; r < C::R; r++ ) m[ r >> 2 ] |= ( uint64_t )__ldg( mask_lut + key * C::R + r ) << ( 16 * ( r & 3 ) );
+            ldg_entry4( reinterpret_cast< const uint64_t* >( mask_lut ) + ( size_t )key * E::EW, m ); // (rows form: the table holds entries)
         }
     }
     else
@@ -854,8 +885,13 @@ __device__ __forceinline__ uint64_t smooth_lookup( const SmoothTablePtrs& st, co
         // (the bits of corners without a cut vertex do not matter, and the 16 entries of a key are one 128-byte line at s <= 4:
         // not masking them off lets the gather start before the descriptors have arrived — 1.2 % on the bench frames)
         const uint64_t* e = st.cut + ( size_t )( key * 16u + ( cflags & 15u ) ) * E::EW;
+        if constexpr( E::EW == 4 )
+            ldg_entry4( e, m );
+        else
+        {
 #pragma unroll
-        for( int w = 0; w < E::EW; w++ ) m[ w ] = __ldg( e + w );
+            for( int w = 0; w < E::EW; w++ ) m[ w ] = __ldg( e + w );
+        }
     }
     more = ( int32_t )head.x < 0; // kDescMore
 #ifndef PAR_WHATIF_NOLINKS
@@ -1168,9 +1204,11 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
         }
         else
         {
+            uint64_t hm[ 4 ] = { 0ull, 0ull, 0ull, 0ull };
+            if( inside ) ldg_entry4( reinterpret_cast< const uint64_t* >( a.mask_lut ) + ( size_t )key * 4, hm );
 #pragma unroll
             for( int r = 0; r < C::R; r++ )
-                s_mask[ r * C::NC + idx ] = inside ? ( __ldg( a.mask_lut + key * C::R + r ) | ( r == 0 ? force_wide : 0u ) ) : 0u;
+                s_mask[ r * C::NC + idx ] = ( ( uint32_t )( hm[ r >> 2 ] >> ( 16 * ( r & 3 ) ) ) & 0xFFFFu ) | ( r == 0 && inside ? force_wide : 0u );
         }
         const uint32_t vote = __ballot_sync( 0xFFFFFFFFu, third_link );
         if( lane == 0 ) s_more[ round * ( kThreads / 32 ) + warp ] = vote;

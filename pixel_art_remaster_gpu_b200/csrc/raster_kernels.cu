@@ -117,7 +117,7 @@ bool raster_aa_supported( int out_scale, int aa )
 
 size_t mask_lut_words( int scale )
 {
-#define PAR_WORDS( S ) return ( size_t )kCellKeys * Cfg< S >::MW
+#define PAR_WORDS( S ) return ( size_t )kCellKeys * ( Cfg< S >::PACK ? 2 : 8 ) /* window form: two words; rows form: an entry of four 64-bit words */
     PAR_FOR_SCALE( scale, PAR_WORDS )
 #undef PAR_WORDS
     return 0;
