@@ -211,21 +211,17 @@ __device__ __forceinline__ uint32_t not_one_colour( uint32_t a, uint32_t b, uint
     return t;
 }
 
-// a rows-form table entry (four 64-bit words, 32-byte aligned) by two 128-bit read-only loads: a gather costs the LSU a
-// wavefront per instruction and line, so four 64-bit loads of the same entry cost twice what these do
+// a rows-form table entry (four 64-bit words, 32-byte aligned) by ONE 256-bit read-only load (sm_100: LDG.256): a gather costs
+// the LSU a wavefront per instruction and line, so four 64-bit loads of the same entry cost four times what this does
 __device__ __forceinline__ void ldg_entry4( const uint64_t* e, uint64_t* m )
 {
-    const ulonglong2 a = __ldg( reinterpret_cast< const ulonglong2* >( e ) ), b = __ldg( reinterpret_cast< const ulonglong2* >( e ) + 1 );
-    m[ 0 ] = a.x;
-    m[ 1 ] = a.y;
-    m[ 2 ] = b.x;
-    m[ 3 ] = b.y;
+    asm( "ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"( m[ 0 ] ), "=l"( m[ 1 ] ), "=l"( m[ 2 ] ), "=l"( m[ 3 ] ) : "l"( e ) );
 }
 // ... XORed into m when `flag` is not zero (no branch); returns word 0 of the entry (0 when not loaded)
 __device__ __forceinline__ uint64_t ldg_entry4_xor_if( const uint64_t* e, uint32_t flag, uint64_t* m )
 {
     uint64_t v0 = 0ull, v1 = 0ull, v2 = 0ull, v3 = 0ull;
-    asm( "{ .reg .pred q; setp.ne.u32 q, %5, 0; @q ld.global.nc.v2.u64 {%0, %1}, [%4]; @q ld.global.nc.v2.u64 {%2, %3}, [%4 + 16]; }"
+    asm( "{ .reg .pred q; setp.ne.u32 q, %5, 0; @q ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4]; }"
          : "+l"( v0 ), "+l"( v1 ), "+l"( v2 ), "+l"( v3 )
          : "l"( e ), "r"( flag ) );
     m[ 0 ] ^= v0;
@@ -255,11 +251,20 @@ struct Fmt
 
 // one output row segment of a source pixel: N pixels (colour words px[0..N)), widest stores the alignment allows
 template< int N, int FMT >
-__device__ __forceinline__ void store_row( uint8_t* dst, const uint32_t* px )
+__device__ __forceinline__ void store_row( uint8_t* dst, const uint32_t* px, bool align32 = false )
 {
     if constexpr( FMT == kFmtRgba8 )
     {
-        if( N % 4 == 0 )
+        if( N == 8 && align32 )
+        {
+            // 8x: a lane's row segment is 32 bytes — one 256-bit store (sm_100: STG.256), so that a warp's store instruction
+            // writes 1024 contiguous bytes; as two 128-bit stores each instruction touches the same eight lines half-filled
+            // (twice the LSU wavefronts)
+            asm volatile( "st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"( dst ), "r"( px[ 0 ] ), "r"( px[ 1 % N ] ), "r"( px[ 2 % N ] ),
+                          "r"( px[ 3 % N ] ), "r"( px[ 4 % N ] ), "r"( px[ 5 % N ] ), "r"( px[ 6 % N ] ), "r"( px[ 7 % N ] )
+                          : "memory" );
+        }
+        else if( N % 4 == 0 )
         {
 #pragma unroll
             for( int k = 0; k < N; k += 4 ) st_stream_v4( dst + 4 * k, make_uint4( px[ k ], px[ k + 1 ], px[ k + 2 ], px[ k + 3 ] ) );
@@ -1405,6 +1410,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
     }
     else
     {
+        const bool out_align32 = O == 8 && ( ( reinterpret_cast< uintptr_t >( out ) | ( uintptr_t )( out_w * BPP ) ) & 31u ) == 0u; // (256-bit stores)
         for( int idx = tid; idx < C::TW * C::TH; idx += kThreads )
         {
             int ly = idx / C::TW, lx = idx - ly * C::TW;
@@ -1459,7 +1465,7 @@ __global__ void __launch_bounds__( kThreads, S <= 4 ? 5 : 4 ) raster_kernel( con
 #pragma unroll
                     for( int k = 0; k < O; k++ ) px[ k ] = sum[ k ].template mean< A * A >();
                 }
-                store_row< O, FMT >( dst + ( ptrdiff_t )ob * row_step, px );
+                store_row< O, FMT >( dst + ( ptrdiff_t )ob * row_step, px, out_align32 );
             }
         }
     }
