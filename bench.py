@@ -53,9 +53,9 @@ def workload(n_frames=FRAMES_PER_GPU):
 
 def profiled_traffic_per_frame():
     """DRAM bytes (read + write) per frame of the raster kernel from the committed ncu capture of a launch over the bench's own
-    4096-frame batch (profiles/r3_raster_traffic.json, written by tools/ncu_traffic.py; round 1's 256-frame capture as a
+    4096-frame batch (profiles/r4_raster_traffic.json or an earlier round's, written by tools/ncu_traffic.py; round 1's 256-frame capture as a
     fallback); None when neither is there."""
-    for name in ("r3_raster_traffic.json", "r2_raster_traffic.json", "r1_raster_traffic.json"):
+    for name in ("r4_raster_traffic.json", "r3_raster_traffic.json", "r2_raster_traffic.json", "r1_raster_traffic.json"):
         try:
             t = json.load(open(os.path.join(ROOT, "profiles", name)))
             return float(t["dram_bytes_per_frame"]), t.get("source", "profiles/" + name)

@@ -559,6 +559,28 @@ def test_indexed_output_of_frames_with_many_colours(lib):
 
 
 @pytest.mark.gpu
+def test_8x_output_at_every_16_byte_alignment(lib):
+    """At 8x a lane's row segment is 32 bytes and leaves by one 256-bit store when the image base is 32-byte aligned,
+    by two 128-bit stores otherwise (the C ABI asks for 16-byte alignment only): both give the same image."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    F, W, H, S = 3, 72, 40, 8
+    frames = torch.from_numpy(synth.snes_stream(F, W, H, first_seed=4242)).cuda()
+    n = F * S * H * S * W * 4
+    with lib.Remaster(0, W, H, F) as c:
+        want = c.remaster(frames, scale=S, subdivide=True)["rgba"]
+        buf = torch.zeros(n + 64, dtype=torch.uint8, device="cuda")
+        base = buf.data_ptr()
+        for off in ((-base) % 32, (-base) % 32 + 16):
+            view = buf[off:off + n].view(F, S * H, S * W, 4)
+            assert view.data_ptr() % 16 == 0 and (view.data_ptr() % 32 == 0) == (off == (-base) % 32)
+            buf.zero_()
+            c.remaster(frames, scale=S, subdivide=True, out={"rgba": view})
+            assert torch.equal(view, want), off
+
+
+@pytest.mark.gpu
 def test_streams_devices_and_sub_batches(lib):
     """A context follows torch's current stream call by call (outputs allocated under `with torch.cuda.stream(s)` are
     produced on s), leaves the caller's current device alone, refuses tensors of another device, and gives the same
