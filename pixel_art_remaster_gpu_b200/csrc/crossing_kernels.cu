@@ -19,13 +19,24 @@ namespace par {
 
 namespace {
 
-constexpr int kTW = 64, kTH = 32;
+#ifndef PAR_K2_TH
+#define PAR_K2_TH 32
+#endif
+constexpr int kTW = 64, kTH = PAR_K2_TH;
 constexpr int kAW = kTW + 2, kAH = kTH + 2; // staged pixels (halo 1)
 constexpr int kAuxOff = 15;                 // TMA needs a 16-byte aligned start: rows begin at column x0 - 16
 constexpr int kAuxPitch = 96;               // 15 + 66 rounded up to 16 (TMA box row)
 constexpr int kBW = kTW + 1, kBH = kTH + 1; // blocks decided per tile
 constexpr int kDecPitch = 68;
-constexpr int kThreads = 256;
+// 128 threads per 64x32 tile, not 256: the kernel is bound by each tile's critical path (TMA round trip -> block scan ->
+// barrier -> rules -> barrier -> chain walks through L1/L2 -> barrier -> output), not by instruction issue — a sparse form that
+// removed the scan and the output pass (45 % of the instructions) was no faster (profiles/r4h_*) — so more tiles in flight per
+// SM (15 instead of 8) is what helps: 0.408 -> 0.328 ms per 4096 frames (64 / 192 / 512 threads: 0.393 / 0.375 / 0.658; 64x16
+// tiles with 128 / 64 threads: 0.398 / 0.378; profiles/r4i_*, r4j_*, r4k_*)
+#ifndef PAR_K2_THREADS
+#define PAR_K2_THREADS 128
+#endif
+constexpr int kThreads = PAR_K2_THREADS;
 
 enum : uint8_t { kNone = 0, kSlashDies = 1, kBackslashDies = 2, kPending = 3 };
 

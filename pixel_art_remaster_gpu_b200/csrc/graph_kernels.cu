@@ -24,7 +24,10 @@ namespace par {
 
 namespace {
 
-constexpr int kTW = 64, kTH = 32;            // pixels per tile
+#ifndef PAR_K1_TH
+#define PAR_K1_TH 32
+#endif
+constexpr int kTW = 64, kTH = PAR_K1_TH;     // pixels per tile
 constexpr int kYW = kTW + 2, kYH = kTH + 2;  // pixels whose colour is needed (halo 1); pixel column c = x - (x0 - 1)
 constexpr int kRawOff = 13;                  // TMA needs a 16-byte aligned start: rows begin at byte 3*x0 - 16, pixel c at 13 + 3c
 constexpr int kRawPitch = 224;               // bytes per staged row: 13 + 3*66 = 211 rounded up to 16
@@ -35,7 +38,13 @@ constexpr int kGroups = 18;
 constexpr int kBH = kTH + 1;                 // 2x2 block rows per tile (block (c,r): lower-left pixel (c,r), c = 0..64)
 constexpr int kBlkGroups = 17;               // block columns 4g-3 .. 4g, g = 0..16
 constexpr int kBlkPitch = 4 * kGroups;       // bytes
-constexpr int kThreads = 256;
+// 128 threads per 64x32 tile, not 256: a tile's passes are separated by barriers and start behind a TMA round trip, and with
+// half the threads per CTA an SM holds 11 tiles in flight instead of 8 (0.647 -> 0.609 ms per 4096 frames; 512 threads: 0.742;
+// 64x16 tiles with 128 / 64 threads: 0.687 / 0.677 — the halo; profiles/r4j_*, r4k_*)
+#ifndef PAR_K1_THREADS
+#define PAR_K1_THREADS 128
+#endif
+constexpr int kThreads = PAR_K1_THREADS;
 
 static_assert( kRawPitch >= kRawOff + 3 * kYW && kRawPitch % 16 == 0, "TMA box rows are multiples of 16 bytes" );
 static_assert( 4 + 12 * kGroups <= kRawPitch, "the last group's raw bytes are inside the staged row" );
